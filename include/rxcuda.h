@@ -1,0 +1,263 @@
+/*
+ * rxcuda.h -- C ABI of the B200-native replacement for Rusterix's CPU tile rasterizer.
+ *
+ * The reference has no FFI: the boundary it replaces is the Rust method
+ *   Rasterizer::setup(m2d, view, proj)[.ambient()/.sample_mode()/...]
+ *       .rasterize(&mut scene, pixels, width, height, tile_size, &assets)
+ * (reference src/rasterizer.rs:92-152 and :185-193).  A Rust host marshals its
+ * Scene / Batch3D / Batch2D / Tile / Texture / CompiledLight values into the POD structs
+ * below (all #[repr(C)]-mirrorable: plain pointers, sizes, fixed arrays) and calls these
+ * entry points; see INTEGRATION.md for the cc/build.rs + extern "C" stub.
+ *
+ * Conventions
+ *  - every function returns RXC_OK (0) or a negative rxc_status; nothing unwinds;
+ *    rxc_last_error(ctx) gives a human readable string owned by the context.
+ *  - host memory passed to rxc_set_* is only borrowed for the duration of the call.
+ *  - matrices are column-major (vek `Mat4.cols`, reference src/rasterizer.rs:99-101):
+ *    m[c*4+r] is row r, column c.  Mat3 likewise m[c*3+r].
+ *  - a context is bound to one GPU and one CUDA stream; it is Send but not Sync
+ *    (same as `&mut Rasterizer` + `&mut Scene` in the reference).
+ *  - there is no CPU fallback: without a usable sm_100 device rxc_create fails.
+ */
+#ifndef RXCUDA_H
+#define RXCUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RXC_ABI_VERSION 1u
+
+typedef struct rxc_ctx rxc_ctx;
+
+typedef enum rxc_status {
+    RXC_OK = 0,
+    RXC_ERR_INVALID = -1,     /* bad argument (null pointer, zero size, short buffer ...)     */
+    RXC_ERR_CUDA = -2,        /* a CUDA runtime call failed; see rxc_last_error                */
+    RXC_ERR_UNSUPPORTED = -3, /* feature of the reference path not (yet) on the device path    */
+    RXC_ERR_OOM = -4,         /* device or pinned allocation failed                            */
+    RXC_ERR_INDEX = -5,       /* index out of range where the reference would panic            */
+    RXC_ERR_NO_DEVICE = -6    /* no sm_100-class GPU visible                                   */
+} rxc_status;
+
+/* PrimitiveMode, reference src/batch/mod.rs:5-15 */
+enum { RXC_MODE_TRIANGLES = 0, RXC_MODE_LINES = 1, RXC_MODE_LINE_STRIP = 2, RXC_MODE_LINE_LOOP = 3 };
+/* CullMode, reference src/batch/mod.rs:18-26 */
+enum { RXC_CULL_OFF = 0, RXC_CULL_FRONT = 1, RXC_CULL_BACK = 2 };
+/* RepeatMode, reference src/texture.rs:15-25 */
+enum { RXC_REPEAT_CLAMP_XY = 0, RXC_REPEAT_REPEAT_XY = 1, RXC_REPEAT_REPEAT_X = 2, RXC_REPEAT_REPEAT_Y = 3 };
+/* SampleMode, reference src/texture.rs:6-12 (a field of Rasterizer, not of the batch) */
+enum { RXC_SAMPLE_NEAREST = 0, RXC_SAMPLE_LINEAR = 1 };
+/* LightType, reference src/map/light.rs:7-14 */
+enum {
+    RXC_LIGHT_POINT = 0,
+    RXC_LIGHT_AMBIENT = 1,
+    RXC_LIGHT_AMBIENT_DAYLIGHT = 2,
+    RXC_LIGHT_SPOT = 3,
+    RXC_LIGHT_AREA = 4,
+    RXC_LIGHT_DAYLIGHT = 5
+};
+/* PixelSource, reference src/map/pixelsource.rs:23-37.  Kinds the rasterizer treats alike
+ * (Off, TileId, MaterialId, Sequence, Color, ShapeFXGraphId) collapse to RXC_SRC_OTHER:
+ * opaque black in 3D (src/rasterizer.rs:1221), transparent in 2D (:757). */
+enum {
+    RXC_SRC_OTHER = 0,
+    RXC_SRC_STATIC_TILE = 1,  /* index into the tiles given to rxc_set_assets (assets.tile_list) */
+    RXC_SRC_DYNAMIC_TILE = 2, /* index into rxc_scene.dynamic_textures                           */
+    RXC_SRC_PIXEL = 3,        /* constant RGBA8                                                  */
+    RXC_SRC_ENTITY_TILE = 4,  /* unsupported on device (RXC_ERR_UNSUPPORTED)                     */
+    RXC_SRC_ITEM_TILE = 5,    /* unsupported on device                                           */
+    RXC_SRC_TERRAIN = 6       /* unsupported on device                                           */
+};
+/* Background shaders, reference src/shader/vgradient.rs, src/shader/grid.rs */
+enum { RXC_BG_NONE = 0, RXC_BG_VGRAY_GRADIENT = 1, RXC_BG_GRID = 2 };
+/* Which list of Scene a 3D batch came from; batches are passed in SUBMISSION ORDER
+ * (reference src/rasterizer.rs:314-405) and the tag only names the origin. */
+enum { RXC_PASS_STATIC = 0, RXC_PASS_DYNAMIC = 1, RXC_PASS_OVERLAY = 2, RXC_PASS_CHUNK = 3, RXC_PASS_CHUNK_OPACITY = 4 };
+/* Mat*Vec rounding convention (vek 0.17 is not vendored in the reference):
+ *  FMA_COLUMNS: r = col0*x; r = fma(col1,y,r); r = fma(col2,z,r); r = fma(col3,w,r)
+ *  PLAIN_ROWS : r_i = ((m_i0*x + m_i1*y) + m_i2*z) + m_i3*w  with every op rounded */
+enum { RXC_MATVEC_FMA_COLUMNS = 0, RXC_MATVEC_PLAIN_ROWS = 1 };
+
+/* One animation frame of a Tile: reference src/texture.rs:46-54 (data/width/height). */
+typedef struct rxc_texture {
+    const uint8_t* data; /* RGBA8 row-major, width*height*4 bytes */
+    uint32_t width;
+    uint32_t height;
+} rxc_texture;
+
+/* reference src/map/tile.rs:83-96: the frame used is animation_frame % n_textures */
+typedef struct rxc_tile {
+    const rxc_texture* textures;
+    uint32_t n_textures;
+} rxc_tile;
+
+/* reference src/map/light.rs:457-477 (CompiledLight) */
+typedef struct rxc_light {
+    uint32_t light_type;
+    float position[3];
+    float color[3];
+    float intensity;
+    uint32_t emitting;
+    float start_distance;
+    float end_distance;
+    float flicker;
+    float direction[3];
+    float cone_angle;
+    float normal[3];
+    float width;
+    float height;
+    uint32_t from_linedef;
+} rxc_light;
+
+/* reference src/batch/batch3d.rs:15-78 (inputs only; the projection caches stay on device) */
+typedef struct rxc_batch3d {
+    const float* vertices;  /* n_vertices * [x,y,z,w]                                   */
+    const float* uvs;       /* n_vertices * [u,v]                                       */
+    const float* normals;   /* n_vertices * [x,y,z], or NULL when batch.normals is empty */
+    const void* indices;    /* n_triangles * 3 indices, index_bytes wide each           */
+    uint32_t n_vertices;
+    uint32_t n_triangles;
+    uint32_t index_bytes;   /* 4 (u32) or 8 (Rust usize triples, 24 B per triangle)     */
+    uint32_t mode;          /* RXC_MODE_*; 3D batches are always rasterized as triangles */
+    uint32_t repeat_mode;   /* RXC_REPEAT_* */
+    uint32_t cull_mode;     /* RXC_CULL_*   */
+    uint32_t source_kind;   /* RXC_SRC_*    */
+    uint32_t source_index;  /* tile index for STATIC_TILE / DYNAMIC_TILE                */
+    uint8_t source_pixel[4];/* RGBA for RXC_SRC_PIXEL                                   */
+    uint32_t receives_light;
+    float ambient_color[3];
+    uint32_t has_profile_id;
+    uint32_t profile_id;
+    int32_t shader;         /* -1 = None; anything else -> RXC_ERR_UNSUPPORTED           */
+    uint32_t pass;          /* RXC_PASS_* */
+    float transform[16];    /* transform_3d, column-major                                */
+} rxc_batch3d;
+
+/* reference src/batch/batch2d.rs:10-53 */
+typedef struct rxc_batch2d {
+    const float* vertices; /* n_vertices * [x,y] */
+    const float* uvs;      /* n_vertices * [u,v] */
+    const void* indices;   /* n_triangles * 3    */
+    uint32_t n_vertices;
+    uint32_t n_triangles;
+    uint32_t index_bytes;
+    uint32_t mode;
+    uint32_t repeat_mode;
+    uint32_t source_kind;
+    uint32_t source_index;
+    uint8_t source_pixel[4];
+    uint32_t receives_light;
+    int32_t shader;
+} rxc_batch2d;
+
+/* reference src/scene.rs:8-50.  batches3d: chunks..., d3_static, d3_dynamic, d3_overlay in that
+ * order; batches2d: chunks..., d2_static, d2_dynamic.  lights = scene.lights followed by
+ * scene.dynamic_lights AFTER the per-call chunk-light append (src/rasterizer.rs:219-223). */
+typedef struct rxc_scene {
+    const rxc_batch3d* batches3d;
+    uint32_t n_batches3d;
+    const rxc_batch2d* batches2d;
+    uint32_t n_batches2d;
+    const rxc_light* lights;
+    uint32_t n_lights;
+    const rxc_tile* dynamic_textures;
+    uint32_t n_dynamic_textures;
+} rxc_scene;
+
+/* Everything Rasterizer::setup + the builder methods + rasterize()'s scalar arguments carry
+ * (reference src/rasterizer.rs:35-88, :92-193). */
+typedef struct rxc_frame {
+    float view[16];
+    float projection[16];
+    float inverse_view[16];       /* host computes with vek so the bits match its own      */
+    float inverse_projection[16];
+    uint32_t has_matrix2d;
+    float matrix2d[9];            /* projection_matrix_2d                                   */
+    uint32_t width;
+    uint32_t height;
+    uint32_t tile_size;           /* the API tile size; only used to reproduce the per-tile
+                                     batch-bbox reject exactly (src/rasterizer.rs:978-983)   */
+    uint32_t sample_mode;
+    uint32_t has_background_color;
+    uint8_t background_color[4];
+    uint32_t background_shader;   /* RXC_BG_* (scene.background)                            */
+    float grid_size;              /* GridShader parameters                                  */
+    float grid_subdivisions;
+    float grid_offset[2];
+    uint32_t has_ambient;
+    float ambient[4];
+    uint64_t animation_frame;     /* scene.animation_frame                                  */
+    float time;
+    float hour;
+    uint32_t d2_active;           /* RenderMode */
+    uint32_t d3_active;
+    uint32_t ignore_background_shader;
+    uint32_t preserve_transparency;
+    uint32_t matvec_mode;         /* RXC_MATVEC_* */
+    uint32_t band_y0;             /* multi-GPU band split: render rows [band_y0, band_y1);   */
+    uint32_t band_y1;             /* both 0 = whole frame. `pixels` then holds only the band */
+} rxc_frame;
+
+/* Counters filled by rxc_get_stats; times are device times from CUDA events (profiling on). */
+#define RXC_N_KERNELS 8
+typedef struct rxc_stats {
+    uint64_t frames;                       /* frames rasterized since create/reset           */
+    uint64_t kernel_launches;              /* kernels launched since create/reset            */
+    uint64_t launches[RXC_N_KERNELS];      /* per kernel class (rxc_kernel_name)             */
+    double kernel_ms[RXC_N_KERNELS];       /* accumulated, only while profiling is enabled   */
+    uint64_t h2d_bytes;                    /* bytes copied host->device since reset          */
+    uint64_t d2h_bytes;
+    uint32_t last_binned_refs;             /* triangle references in the last frame's bins   */
+    uint32_t last_large_tris;              /* triangles on the last frame's large list       */
+    uint32_t last_clipped_tris;            /* near-clip output triangles of the last frame   */
+    uint32_t last_visible_tris;
+} rxc_stats;
+
+uint32_t rxc_abi_version(void);
+int32_t rxc_create(int32_t device, rxc_ctx** out);
+void rxc_destroy(rxc_ctx* ctx);
+const char* rxc_last_error(const rxc_ctx* ctx);
+
+/* Launch on `cuda_stream` (a cudaStream_t) instead of the context's own stream; NULL restores it. */
+int32_t rxc_set_stream(rxc_ctx* ctx, void* cuda_stream);
+
+/* assets.tile_list (reference src/server/assets.rs:19): uploaded once, kept on device. */
+int32_t rxc_set_assets(rxc_ctx* ctx, const rxc_tile* tiles, uint32_t n_tiles);
+/* Geometry, lights and dynamic textures of a Scene: uploaded once, kept on device. */
+int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* scene);
+/* Replace only the light list (lights animate per frame in examples/cube.rs:72-73). */
+int32_t rxc_set_lights(rxc_ctx* ctx, const rxc_light* lights, uint32_t n_lights);
+
+/* The replacement for Rasterizer::rasterize.  `pixels` receives width*rows*4 bytes RGBA8
+ * (rows = height, or the band height); it may be host (pageable or pinned) or device memory.
+ * `owner` (u32 per pixel: submission ordinal of the triangle owning the pixel after the 3D
+ * passes, 0xFFFFFFFF = none) and `depth` (f32 z-buffer after the 3D passes) are optional
+ * parity outputs and may be NULL.  Synchronous: outputs are valid on return. */
+int32_t rxc_rasterize(rxc_ctx* ctx, const rxc_frame* frame, uint8_t* pixels, uint32_t* owner, float* depth);
+/* Same, but only enqueues on the stream; `pixels` must be device or pinned memory. */
+int32_t rxc_rasterize_async(rxc_ctx* ctx, const rxc_frame* frame, uint8_t* pixels, uint32_t* owner, float* depth);
+/* Camera sweep: n_frames frames of the current scene in one launch sequence; frame i is
+ * written at pixels + i*frame_stride_bytes.  All frames must share width/height/band. */
+int32_t rxc_rasterize_batch(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames, uint8_t* pixels,
+                            uint64_t frame_stride_bytes);
+int32_t rxc_rasterize_batch_async(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames, uint8_t* pixels,
+                                  uint64_t frame_stride_bytes);
+int32_t rxc_synchronize(rxc_ctx* ctx);
+
+/* Global submission ordinal of triangle 0 of 3D batch `batch` (owner ids are
+ * base + index into the batch's clipped_indices; capacity 3*n_triangles per batch). */
+int32_t rxc_owner_base(const rxc_ctx* ctx, uint32_t batch, uint32_t* base);
+
+int32_t rxc_set_profiling(rxc_ctx* ctx, int32_t enabled);
+int32_t rxc_get_stats(rxc_ctx* ctx, rxc_stats* out);
+int32_t rxc_reset_stats(rxc_ctx* ctx);
+const char* rxc_kernel_name(uint32_t kernel_class);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RXCUDA_H */

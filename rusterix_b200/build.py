@@ -1,0 +1,68 @@
+"""In-tree builds: the CUDA product library (nvcc, sm_100a only) and the CPU oracle (g++).
+`python -m rusterix_b200.build` builds both; __graft_entry__.build() calls build_all()."""
+import os
+import shutil
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_HERE)
+CSRC = os.path.join(_HERE, "csrc")
+LIB = os.path.join(_HERE, "librxcuda.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    # Rust never contracts a*b+c (SURVEY T-fma): contraction is off for the whole library and
+    # FMAs are written explicitly where the reference has mul_add.  Denormals, division and
+    # square roots stay IEEE (-ftz=false -prec-div=true -prec-sqrt=true are the defaults).
+    "-fmad=false",
+    "-Xcompiler", "-fPIC,-O2,-Wall",
+    "-shared",
+    "-cudart", "shared",
+]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def cuda_sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def build_cuda(force=False, verbose=False):
+    srcs = cuda_sources()
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    deps.append(os.path.join(ROOT, "include", "rxcuda.h"))
+    if not force and not _newer(LIB, deps):
+        return LIB
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", os.path.join(ROOT, "include"), "-o", LIB] + srcs
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stdout + r.stderr)
+    return LIB
+
+
+def build_oracle(force=False):
+    odir = os.path.join(ROOT, "oracle")
+    if force:
+        subprocess.run(["make", "-C", odir, "clean"], check=True, capture_output=True)
+    r = subprocess.run(["make", "-C", odir], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + r.stdout + r.stderr)
+    return os.path.join(odir, "_build", "librxoracle.so")
+
+
+def build_all(force=False, verbose=False):
+    return build_cuda(force, verbose), build_oracle(force)
+
+
+if __name__ == "__main__":
+    print(build_all(force="--force" in sys.argv, verbose="-v" in sys.argv))

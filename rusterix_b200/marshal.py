@@ -1,0 +1,168 @@
+"""Scene / Assets / Rasterizer state -> the POD structs of include/rxcuda.h.
+
+This is the Python twin of what the Rust `-sys` wrapper does: flatten the scene's
+batch lists into submission order (reference src/rasterizer.rs:314-405, :501-553), point the PODs
+at the host arrays, and keep those arrays alive for the duration of the call."""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from .types import Assets, Batch2D, Batch3D, CompiledLight, Scene, Tile
+from .vekmath import to_cols
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data if a.size else None
+
+
+class Marshalled:
+    """Holds a ctypes struct plus everything it points to."""
+
+    def __init__(self, struct, keep):
+        self.struct = struct
+        self.keep = keep
+
+
+def marshal_tiles(tiles):
+    keep = []
+    arr = (_abi.rxc_tile * max(1, len(tiles)))()
+    for i, tile in enumerate(tiles):
+        tex = (_abi.rxc_texture * max(1, len(tile.textures)))()
+        for j, t in enumerate(tile.textures):
+            tex[j].data = t.data.ctypes.data
+            tex[j].width = t.width
+            tex[j].height = t.height
+            keep.append(t.data)
+        arr[i].textures = tex
+        arr[i].n_textures = len(tile.textures)
+        keep.append(tex)
+    return Marshalled(arr, keep)
+
+
+def marshal_lights(lights):
+    arr = (_abi.rxc_light * max(1, len(lights)))()
+    for i, l in enumerate(lights):
+        o = arr[i]
+        o.light_type = int(l.light_type)
+        o.position[:] = [float(x) for x in l.position]
+        o.color[:] = [float(x) for x in l.color]
+        o.intensity = l.intensity
+        o.emitting = 1 if l.emitting else 0
+        o.start_distance = l.start_distance
+        o.end_distance = l.end_distance
+        o.flicker = l.flicker
+        o.direction[:] = [float(x) for x in l.direction]
+        o.cone_angle = l.cone_angle
+        o.normal[:] = [float(x) for x in l.normal]
+        o.width = l.width
+        o.height = l.height
+        o.from_linedef = 1 if l.from_linedef else 0
+    return Marshalled(arr, [])
+
+
+def _fill_source(o, src):
+    o.source_kind = int(src.kind)
+    o.source_index = int(src.index)
+    o.source_pixel[:] = list(src.pixel)
+
+
+def marshal_scene(scene: Scene, index_bytes: int = 4):
+    """index_bytes=8 marshals indices as Rust `usize` triples (24 B/triangle) to exercise that path."""
+    keep = []
+    b3_list = [(b, 0) for b in scene.d3_static] + [(b, 1) for b in scene.d3_dynamic] + [(b, 2) for b in scene.d3_overlay]
+    b2_list = list(scene.d2_static) + list(scene.d2_dynamic)
+    b3 = (_abi.rxc_batch3d * max(1, len(b3_list)))()
+    for i, (b, pass_) in enumerate(b3_list):
+        o = b3[i]
+        idx = b.indices if index_bytes == 4 else np.ascontiguousarray(b.indices.astype(np.uint64))
+        keep += [b.vertices, b.uvs, b.normals, idx]
+        o.vertices = _ptr(b.vertices)
+        o.uvs = _ptr(b.uvs)
+        o.normals = _ptr(b.normals) if len(b.normals) else None
+        o.indices = _ptr(idx)
+        o.n_vertices = len(b.vertices)
+        o.n_triangles = len(b.indices)
+        o.index_bytes = index_bytes
+        if len(b.uvs) != len(b.vertices):
+            raise ValueError("Batch3D.uvs must have one entry per vertex")
+        if len(b.normals) not in (0, len(b.vertices)):
+            raise ValueError("Batch3D.normals must be empty or have one entry per vertex")
+        o.mode = int(b.mode)
+        o.repeat_mode = int(b.repeat_mode_)
+        o.cull_mode = int(b.cull_mode_)
+        _fill_source(o, b.source_)
+        o.receives_light = 1 if b.receives_light_ else 0
+        o.ambient_color[:] = list(b.ambient_color_)
+        o.has_profile_id = 0 if b.profile_id_ is None else 1
+        o.profile_id = 0 if b.profile_id_ is None else b.profile_id_
+        o.shader = -1 if b.shader_ is None else b.shader_
+        o.pass_ = pass_
+        o.transform[:] = to_cols(b.transform_3d).tolist()
+    b2 = (_abi.rxc_batch2d * max(1, len(b2_list)))()
+    for i, b in enumerate(b2_list):
+        o = b2[i]
+        idx = b.indices if index_bytes == 4 else np.ascontiguousarray(b.indices.astype(np.uint64))
+        keep += [b.vertices, b.uvs, idx]
+        o.vertices = _ptr(b.vertices)
+        o.uvs = _ptr(b.uvs)
+        o.indices = _ptr(idx)
+        o.n_vertices = len(b.vertices)
+        o.n_triangles = len(b.indices)
+        o.index_bytes = index_bytes
+        o.mode = int(b.mode)
+        o.repeat_mode = int(b.repeat_mode_)
+        _fill_source(o, b.source_)
+        o.receives_light = 1 if b.receives_light_ else 0
+        o.shader = -1 if b.shader_ is None else b.shader_
+    lights = marshal_lights(scene.all_lights())
+    dyn = marshal_tiles(scene.dynamic_textures)
+    s = _abi.rxc_scene()
+    s.batches3d = b3
+    s.n_batches3d = len(b3_list)
+    s.batches2d = b2
+    s.n_batches2d = len(b2_list)
+    s.lights = lights.struct
+    s.n_lights = len(scene.all_lights())
+    s.dynamic_textures = dyn.struct
+    s.n_dynamic_textures = len(scene.dynamic_textures)
+    keep += [b3, b2, lights, dyn]
+    return Marshalled(s, keep)
+
+
+def make_frame(rast, scene: Scene, width: int, height: int, tile_size: int, band=None) -> _abi.rxc_frame:
+    """`rast` is a rusterix_b200.rasterizer.Rasterizer (fields mirror src/rasterizer.rs:35-88)."""
+    f = _abi.rxc_frame()
+    f.view[:] = to_cols(rast.view_matrix).tolist()
+    f.projection[:] = to_cols(rast.projection_matrix).tolist()
+    f.inverse_view[:] = to_cols(rast.inverse_view_matrix).tolist()
+    f.inverse_projection[:] = to_cols(rast.inverse_projection_matrix).tolist()
+    if rast.projection_matrix_2d is not None:
+        f.has_matrix2d = 1
+        f.matrix2d[:] = to_cols(np.asarray(rast.projection_matrix_2d, dtype=np.float32).reshape(3, 3)).tolist()
+    f.width, f.height, f.tile_size = int(width), int(height), int(tile_size)
+    f.sample_mode = int(rast.sample_mode_)
+    if rast.background_color is not None:
+        f.has_background_color = 1
+        f.background_color[:] = list(rast.background_color)
+    bg = scene.background
+    if bg is not None:
+        f.background_shader = int(bg.kind)
+        if bg.kind == 2:
+            f.grid_size = bg.grid_size
+            f.grid_subdivisions = bg.subdivisions
+            f.grid_offset[:] = list(bg.offset)
+    if rast.ambient_color is not None:
+        f.has_ambient = 1
+        f.ambient[:] = [float(x) for x in rast.ambient_color]
+    f.animation_frame = int(scene.animation_frame)
+    f.time = rast.time_
+    f.hour = rast.hour
+    f.d2_active = 1 if rast.render_mode_.d2_active else 0
+    f.d3_active = 1 if rast.render_mode_.d3_active else 0
+    f.ignore_background_shader = 1 if rast.render_mode_.ignore_background_shader_ else 0
+    f.preserve_transparency = 1 if rast.preserve_transparency else 0
+    f.matvec_mode = int(rast.matvec_mode)
+    if band is not None:
+        f.band_y0, f.band_y1 = int(band[0]), int(band[1])
+    return f

@@ -1,0 +1,206 @@
+"""Rasterizer: the drop-in for the reference's `Rasterizer::setup(..).rasterize(..)`
+(src/rasterizer.rs:35-193).  Same constructor, builder methods, public fields and call signature;
+the work happens on the GPU through the C ABI (include/rxcuda.h).  No CPU path exists here."""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi, _lib, marshal, vekmath
+from .types import Assets, MatVecMode, RenderMode, SampleMode, Scene
+
+
+class DeviceContext:
+    """One rxc_ctx (one GPU, one stream) plus the host-side cache keys of what is resident."""
+
+    _by_device = {}
+
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        st = self.lib.rxc_create(int(device), C.byref(h))
+        if st != 0:
+            raise _lib.RxcError(st, "rxc_create failed (no sm_100 GPU visible?)")
+        self.handle = h
+        self.device = device
+        self._assets_key = None
+        self._scene_key = None
+        self._lights_key = None
+
+    @classmethod
+    def get(cls, device=0) -> "DeviceContext":
+        if device not in cls._by_device:
+            cls._by_device[device] = DeviceContext(device)
+        return cls._by_device[device]
+
+    def check(self, st):
+        if st != 0:
+            raise _lib.RxcError(st, self.lib.rxc_last_error(self.handle).decode())
+
+    def close(self):
+        if self.handle:
+            self.lib.rxc_destroy(self.handle)
+            self.handle = None
+        self._by_device.pop(self.device, None)
+
+    def set_stream(self, cuda_stream):
+        self.check(self.lib.rxc_set_stream(self.handle, C.c_void_p(cuda_stream or 0)))
+
+    def upload(self, scene: Scene, assets: Assets, index_bytes=4):
+        akey = (id(assets), assets._generation, len(assets.tile_list))
+        if akey != self._assets_key:
+            m = marshal.marshal_tiles(assets.tile_list)
+            self.check(self.lib.rxc_set_assets(self.handle, m.struct, len(assets.tile_list)))
+            self._assets_key = akey
+            self._scene_key = None
+        skey = (id(scene), scene._generation, index_bytes)
+        lights = scene.all_lights()
+        lkey = tuple(
+            (int(l.light_type), tuple(l.position), tuple(l.color), l.intensity, l.emitting, l.start_distance,
+             l.end_distance, l.flicker, tuple(l.direction), l.cone_angle, tuple(l.normal), l.width, l.height,
+             l.from_linedef) for l in lights)
+        if skey != self._scene_key:
+            m = marshal.marshal_scene(scene, index_bytes)
+            self.check(self.lib.rxc_set_scene(self.handle, C.byref(m.struct)))
+            self._scene_key = skey
+            self._lights_key = lkey
+        elif lkey != self._lights_key:
+            m = marshal.marshal_lights(lights)
+            self.check(self.lib.rxc_set_lights(self.handle, m.struct, len(lights)))
+            self._lights_key = lkey
+
+    def stats(self) -> _abi.rxc_stats:
+        s = _abi.rxc_stats()
+        self.check(self.lib.rxc_get_stats(self.handle, C.byref(s)))
+        return s
+
+    def reset_stats(self):
+        self.check(self.lib.rxc_reset_stats(self.handle))
+
+    def set_profiling(self, on: bool):
+        self.check(self.lib.rxc_set_profiling(self.handle, 1 if on else 0))
+
+    def synchronize(self):
+        self.check(self.lib.rxc_synchronize(self.handle))
+
+    def kernel_names(self):
+        return [self.lib.rxc_kernel_name(i).decode() for i in range(_abi.RXC_N_KERNELS)]
+
+
+def _buffer_pointer(buf, nbytes):
+    """numpy array / torch tensor (cpu or cuda) / bytearray -> raw address, with a length check
+    (the reference panics on a short slice, src/rasterizer.rs:572)."""
+    if buf is None:
+        return None, None
+    if hasattr(buf, "data_ptr"):  # torch tensor
+        if buf.numel() * buf.element_size() < nbytes:
+            raise ValueError("output buffer too small")
+        if not buf.is_contiguous():
+            raise ValueError("output tensor must be contiguous")
+        return buf.data_ptr(), buf
+    if isinstance(buf, np.ndarray):
+        if buf.nbytes < nbytes:
+            raise ValueError("output buffer too small")
+        if not buf.flags["C_CONTIGUOUS"]:
+            raise ValueError("output array must be contiguous")
+        return buf.ctypes.data, buf
+    mv = memoryview(buf)
+    if mv.nbytes < nbytes:
+        raise ValueError("output buffer too small")
+    arr = np.frombuffer(mv, dtype=np.uint8)
+    return arr.ctypes.data, arr
+
+
+class Rasterizer:
+    def __init__(self, projection_matrix_2d, view_matrix, projection_matrix):
+        self.render_mode_ = RenderMode.render_all()
+        self.projection_matrix_2d = None if projection_matrix_2d is None else np.asarray(projection_matrix_2d, np.float32).reshape(3, 3)
+        self.view_matrix = np.asarray(view_matrix, dtype=np.float32).reshape(4, 4)
+        self.projection_matrix = np.asarray(projection_matrix, dtype=np.float32).reshape(4, 4)
+        self.inverse_view_matrix = vekmath.inverted(self.view_matrix)              # :97
+        self.inverse_projection_matrix = vekmath.inverted(self.projection_matrix)  # :116
+        self.camera_pos = self.inverse_view_matrix[:3, 3].copy()                   # :98-102
+        self.width = 0.0
+        self.height = 0.0
+        self.sample_mode_ = SampleMode.Nearest
+        self.hash_anim = 0
+        self.background_color = None
+        self.ambient_color = None
+        self.brush_preview = None
+        self.preserve_transparency = False
+        self.hour = 12.0
+        self.time_ = 0.0
+        self.matvec_mode = MatVecMode.FmaColumns
+        self.device = 0
+        self.index_bytes = 4
+
+    @staticmethod
+    def setup(projection_matrix_2d, view_matrix, projection_matrix) -> "Rasterizer":
+        return Rasterizer(projection_matrix_2d, view_matrix, projection_matrix)
+
+    # builder methods, src/rasterizer.rs:154-182
+    def render_mode(self, m: RenderMode):
+        self.render_mode_ = m
+        return self
+
+    def sample_mode(self, m):
+        self.sample_mode_ = SampleMode(m)
+        return self
+
+    def background(self, pixel):
+        self.background_color = tuple(int(c) for c in pixel)
+        return self
+
+    def ambient(self, v4):
+        self.ambient_color = tuple(float(c) for c in v4)
+        return self
+
+    def time(self, t):
+        self.time_ = float(t)
+        return self
+
+    def on_device(self, device: int):
+        self.device = int(device)
+        return self
+
+    def _check_supported(self):
+        if self.brush_preview is not None:
+            raise _lib.RxcError(_abi.RXC_ERR_UNSUPPORTED, "brush_preview is not on the device path")
+
+    def rasterize(self, scene: Scene, pixels, width: int, height: int, tile_size: int, assets: Assets,
+                  owner=None, depth=None, band=None, sync=True):
+        """Same positional arguments as the reference (src/rasterizer.rs:185-193).  `pixels` is a
+        writable uint8 buffer of at least width*height*4 bytes: a numpy array, bytearray, or a torch
+        tensor on the CPU or on the context's GPU.  `owner` (uint32) / `depth` (float32) are
+        optional parity outputs.  `band=(y0,y1)` renders only those rows into a band-sized buffer."""
+        self._check_supported()
+        self.width, self.height = float(width), float(height)
+        ctx = DeviceContext.get(self.device)
+        ctx.upload(scene, assets, self.index_bytes)
+        frame = marshal.make_frame(self, scene, width, height, tile_size, band)
+        rows = height if band is None else band[1] - band[0]
+        p, _k1 = _buffer_pointer(pixels, width * rows * 4)
+        if p is None:
+            raise ValueError("pixels is required")
+        o, _k2 = _buffer_pointer(owner, width * rows * 4)
+        d, _k3 = _buffer_pointer(depth, width * rows * 4)
+        fn = ctx.lib.rxc_rasterize if sync else ctx.lib.rxc_rasterize_async
+        ctx.check(fn(ctx.handle, C.byref(frame), C.c_void_p(p), C.c_void_p(o or 0), C.c_void_p(d or 0)))
+        return pixels
+
+    @staticmethod
+    def rasterize_batch(rasterizers, scene: Scene, pixels, width, height, tile_size, assets: Assets, band=None,
+                        sync=True, device=0):
+        """Camera sweep: one Rasterizer (camera) per frame, one scene, one launch sequence."""
+        ctx = DeviceContext.get(device)
+        ctx.upload(scene, assets, 4)
+        n = len(rasterizers)
+        frames = (_abi.rxc_frame * n)()
+        for i, r in enumerate(rasterizers):
+            r._check_supported()
+            frames[i] = marshal.make_frame(r, scene, width, height, tile_size, band)
+        rows = height if band is None else band[1] - band[0]
+        stride = width * rows * 4
+        p, _k = _buffer_pointer(pixels, stride * n)
+        fn = ctx.lib.rxc_rasterize_batch if sync else ctx.lib.rxc_rasterize_batch_async
+        ctx.check(fn(ctx.handle, frames, n, C.c_void_p(p), stride))
+        return pixels

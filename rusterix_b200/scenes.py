@@ -1,0 +1,370 @@
+"""Deterministic synthetic scenes for BASELINE.json's five configs.
+
+No file of the reference is read: textures are procedural with the dimensions of the reference's
+assets (logo 1024x1024, brick* 64x64, fence 64x80 with alpha holes, sky 256x128), the teapot is a
+lathe mesh with the OBJ's triangle count (2256), and the map is a restatement of minigame/world.rxm
+with exact integer coordinates.  Each builder returns a `Config` (scene, assets, camera set-up,
+resolution, tile size, sampling) ready for `Rasterizer.setup(..).rasterize(..)`."""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional
+
+import numpy as np
+
+from .camera import D3FirstPCamera, D3OrbitCamera
+from .rasterizer import Rasterizer
+from .types import (Assets, Batch2D, Batch3D, CullMode, Light, LightType, PixelSource, RepeatMode, SampleMode,
+                    Scene, Texture, Tile, VGrayGradientShader)
+from . import vekmath
+
+SEED = 0x52555354
+
+
+def splitmix64(n: int, seed: int = SEED) -> np.ndarray:
+    """n uint64 values of the splitmix64 sequence starting at `seed`."""
+    with np.errstate(over="ignore"):
+        idx = np.arange(1, n + 1, dtype=np.uint64)
+        z = np.uint64(seed) + idx * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def rand01(n: int, seed: int) -> np.ndarray:
+    return (splitmix64(n, seed) >> np.uint64(40)).astype(np.float32) / np.float32(1 << 24)
+
+
+# ------------------------------------------------------------------------------------------------
+# procedural textures
+# ------------------------------------------------------------------------------------------------
+def _rgba(r, g, b, a=None):
+    h, w = r.shape
+    out = np.empty((h, w, 4), dtype=np.uint8)
+    out[..., 0] = np.clip(r, 0, 255)
+    out[..., 1] = np.clip(g, 0, 255)
+    out[..., 2] = np.clip(b, 0, 255)
+    out[..., 3] = 255 if a is None else np.clip(a, 0, 255)
+    return out
+
+
+def tex_logo(size=1024) -> Texture:
+    y, x = np.mgrid[0:size, 0:size].astype(np.float32)
+    cx = (x - size / 2) / size
+    cy = (y - size / 2) / size
+    rad = np.sqrt(cx * cx + cy * cy)
+    rings = (np.sin(rad * 60.0) * 0.5 + 0.5)
+    checker = (((x // 64) + (y // 64)) % 2)
+    noise = rand01(size * size, SEED + 1).reshape(size, size)
+    r = 40 + 180 * rings + 20 * noise
+    g = 60 + 120 * checker + 50 * (y / size)
+    b = 90 + 140 * (x / size) + 20 * noise
+    return Texture.from_array(_rgba(r, g, b))
+
+
+def tex_brick(seed, base=(150, 70, 50), mortar=(190, 185, 170), w=64, h=64) -> Texture:
+    y, x = np.mgrid[0:h, 0:w]
+    row = y // 8
+    xx = (x + (row % 2) * 8) % 16
+    is_mortar = ((y % 8) == 0) | (xx == 0)
+    n = rand01(w * h, seed).reshape(h, w)
+    ch = []
+    for c in range(3):
+        ch.append(np.where(is_mortar, mortar[c], base[c] + 40 * (n - 0.5)))
+    return Texture.from_array(_rgba(*ch))
+
+
+def tex_lightpanel(w=64, h=64) -> Texture:
+    y, x = np.mgrid[0:h, 0:w].astype(np.float32)
+    d = np.maximum(np.abs(x - w / 2), np.abs(y - h / 2)) / (w / 2)
+    v = 255 - 120 * d
+    return Texture.from_array(_rgba(v, v, 0.8 * v))
+
+
+def tex_fence(w=64, h=80) -> Texture:
+    """Vertical bars + two rails; everything else alpha 0 (exercises the alpha test, SURVEY T-alpha)."""
+    y, x = np.mgrid[0:h, 0:w]
+    bar = (x % 16) < 4
+    rail = ((y >= 12) & (y < 18)) | ((y >= 60) & (y < 66))
+    solid = bar | rail
+    n = rand01(w * h, SEED + 7).reshape(h, w)
+    v = 90 + 50 * n
+    a = np.where(solid, 255, 0)
+    return Texture.from_array(_rgba(v, 0.8 * v, 0.5 * v, a))
+
+
+def tex_sky(w=256, h=128) -> Texture:
+    y, x = np.mgrid[0:h, 0:w].astype(np.float32)
+    t = y / h
+    n = rand01(w * h, SEED + 9).reshape(h, w)
+    cloud = (np.sin(x * 0.09) * np.sin(y * 0.17 + 1.3) > 0.55) * 50
+    return Texture.from_array(_rgba(70 + 120 * t + cloud, 120 + 90 * t + cloud, 215 + 30 * t + 10 * n))
+
+
+def tex_checker_noise(i: int, size=64) -> Texture:
+    y, x = np.mgrid[0:size, 0:size]
+    n = rand01(size * size, SEED + 100 + i).reshape(size, size)
+    k = 4 << (i % 3)
+    chk = (((x // k) + (y // k)) % 2).astype(np.float32)
+    hue = (i * 0.618034) % 1.0
+    base = np.array([0.5 + 0.5 * math.cos(2 * math.pi * (hue + o)) for o in (0.0, 0.33, 0.67)]) * 200 + 30
+    ch = [base[c] * (0.55 + 0.45 * chk) + 30 * (n - 0.5) for c in range(3)]
+    return Texture.from_array(_rgba(*ch))
+
+
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class Config:
+    name: str
+    scene: Scene
+    assets: Assets
+    width: int
+    height: int
+    tile_size: int
+    sample_mode: SampleMode
+    ambient: Optional[tuple]
+    camera: object
+    cameras: Optional[Callable[[int], object]] = None  # frame index -> camera (sweeps)
+    n_frames: int = 1
+    notes: str = ""
+
+    def rasterizer(self, frame: int = 0) -> Rasterizer:
+        cam = self.cameras(frame) if self.cameras is not None else self.camera
+        r = Rasterizer.setup(None, cam.view_matrix(), cam.projection_matrix(float(self.width), float(self.height)))
+        r.sample_mode(self.sample_mode)
+        if self.ambient is not None:
+            r.ambient(self.ambient)
+        return r
+
+    def counts(self):
+        v = sum(len(b.vertices) for b in self.scene.d3_static + self.scene.d3_dynamic + self.scene.d3_overlay)
+        t = sum(len(b.indices) for b in self.scene.d3_static + self.scene.d3_dynamic + self.scene.d3_overlay)
+        return v, t
+
+    def algorithmic_bytes(self) -> int:
+        """B_alg of SURVEY.md section 8d / BASELINE.md: W*H*4 + V*36 + T*12 + referenced textures + L*72 + 256."""
+        v, t = self.counts()
+        used = set()
+        for b in self.scene.d3_static + self.scene.d3_dynamic + self.scene.d3_overlay + self.scene.d2_static + self.scene.d2_dynamic:
+            if b.source_.kind in (1, 2):
+                used.add((b.source_.kind, b.source_.index))
+        tex = 0
+        for kind, idx in used:
+            tiles = self.assets.tile_list if kind == 1 else self.scene.dynamic_textures
+            if idx < len(tiles):
+                tx = tiles[idx].textures[self.scene.animation_frame % len(tiles[idx].textures)]
+                tex += tx.width * tx.height * 4
+        return self.width * self.height * 4 + v * 36 + t * 12 + tex + len(self.scene.all_lights()) * 72 + 256
+
+
+def _example_light():
+    # examples/cube.rs:45-49,72-73 at t = 0: position (2, 0.8, 0)
+    return Light.new(LightType.Point).with_intensity(1.0).with_color([1.0, 1.0, 0.95]).with_position([2.0, 0.8, 0.0]).compile()
+
+
+def cube(width=800, height=600, tile_size=200, logo_size=1024) -> Config:
+    """Config A (examples/cube.rs:27-90): textured box, CullMode::Off, 1 point light, 200x200 2D rect."""
+    scene = Scene.from_static(
+        [Batch2D.from_rectangle(0.0, 0.0, 200.0, 200.0)],
+        [Batch3D.from_box(-0.5, -0.5, -0.5, 1.0, 1.0, 1.0).source(PixelSource.StaticTileIndex(0)).cull_mode(CullMode.Off).with_computed_normals()],
+    ).lights_([_example_light()]).background_(VGrayGradientShader())
+    assets = Assets.default().textures([Tile.from_texture(tex_logo(logo_size))])
+    cam = D3OrbitCamera.new()
+    cam.set_parameter_f32("distance", 1.5)
+    return Config("cube", scene, assets, width, height, tile_size, SampleMode.Nearest, (0.1,) * 4, cam)
+
+
+def lathe_teapot(segs=47, bands=24) -> Batch3D:
+    """A teapot-like lathe body with the triangle count of examples/teapot.obj (2*47*24 = 2256)."""
+    prof = []
+    for i in range(bands + 1):
+        t = i / bands
+        y = 3.15 * t
+        r = 1.4 + 0.6 * math.sin(math.pi * min(1.0, t * 1.15)) - 1.1 * max(0.0, t - 0.8) * 5 * (t - 0.8) * 5 * 0.2
+        r = max(0.05, r * (1.0 if t < 0.86 else (1.0 - (t - 0.86) / 0.14) * 0.9 + 0.1))
+        prof.append((r, y))
+    verts, idx = [], []
+    for i, (r, y) in enumerate(prof):
+        for s in range(segs):
+            a = 2 * math.pi * s / segs
+            verts.append((r * math.cos(a), y, r * math.sin(a), 1.0))
+    for i in range(bands):
+        for s in range(segs):
+            a = i * segs + s
+            b = i * segs + (s + 1) % segs
+            c = (i + 1) * segs + s
+            d = (i + 1) * segs + (s + 1) % segs
+            idx.append((a, c, b))
+            idx.append((b, c, d))
+    v = np.asarray(verts, dtype=np.float32)
+    return Batch3D(v, idx, v[:, :2].copy())  # UV defaults to (x, y): src/wavefront.rs:91-101
+
+
+def teapot(width=1920, height=1080, tile_size=60, obj_path=None, logo_size=1024, n_frames=64) -> Config:
+    """Config B (examples/obj.rs:28-83): OBJ mesh, RepeatXY, scaling(.35,-.35,.35), Linear, orbit sweep."""
+    mesh = Batch3D.from_obj(obj_path) if obj_path else lathe_teapot()
+    mesh = (mesh.source(PixelSource.StaticTileIndex(0)).repeat_mode(RepeatMode.RepeatXY)
+            .transform(vekmath.scaling_3d(0.35, -0.35, 0.35)).with_computed_normals())
+    scene = Scene.from_static([Batch2D.from_rectangle(0.0, 0.0, 200.0, 200.0)], [mesh]).lights_([_example_light()]).background_(VGrayGradientShader())
+    assets = Assets.default().textures([Tile.from_texture(tex_logo(logo_size))])
+    cam = D3OrbitCamera.new()
+    cam.set_parameter_f32("distance", 1.5)
+
+    def cams(k):
+        c = D3OrbitCamera.new()
+        c.set_parameter_f32("distance", 1.5)
+        c.azimuth = math.pi / 2.0 + 2.0 * math.pi * k / n_frames
+        return c
+
+    return Config("teapot", scene, assets, width, height, tile_size, SampleMode.Linear, (0.8,) * 4, cam, cams, n_frames)
+
+
+def _wall_quad(x0, z0, x1, z1, height, u0=0.0):
+    length = math.hypot(x1 - x0, z1 - z0)
+    verts = [(x0, 0.0, z0, 1.0), (x1, 0.0, z1, 1.0), (x1, height, z1, 1.0), (x0, height, z0, 1.0)]
+    uvs = [(u0, height), (u0 + length, height), (u0 + length, 0.0), (u0, 0.0)]
+    return verts, uvs
+
+
+def _quads_batch(quads):
+    verts, uvs, idx = [], [], []
+    for qv, quv in quads:
+        base = len(verts)
+        verts += qv
+        uvs += quv
+        idx += [(base, base + 1, base + 2), (base, base + 2, base + 3)]
+    return Batch3D(verts, idx, uvs)
+
+
+MAP_TILES = ["logo", "brickwall", "lightpanel", "fence", "brickfloor", "sky"]
+
+
+def map_assets(logo_size=1024) -> Assets:
+    return Assets.default().textures([
+        Tile.from_texture(tex_logo(logo_size)),
+        Tile.from_texture(tex_brick(SEED + 2)),
+        Tile.from_texture(tex_lightpanel()),
+        Tile.from_texture(tex_fence()),
+        Tile.from_texture(tex_brick(SEED + 3, base=(120, 110, 100), mortar=(70, 70, 70))),
+        Tile.from_texture(tex_sky()),
+    ])
+
+
+def map_scene() -> Scene:
+    """Restatement of minigame/world.rxm with exact integer coordinates."""
+    H = 2.0
+    room = [(0, 0), (15, 0), (15, 15), (10, 15), (9, 15), (0, 15), (0, 0)]
+    brick, panel = [], []
+    for (x0, z0), (x1, z1) in zip(room[:-1], room[1:]):
+        q = _wall_quad(float(x0), float(z0), float(x1), float(z1), H)
+        (panel if (x0, z0, x1, z1) == (10, 15, 9, 15) else brick).append(q)
+    fence = [_wall_quad(6.0, 15.0, 6.0, 9.0, H), _wall_quad(6.0, 9.0, 0.0, 9.0, H)]
+    floor = Batch3D(
+        [(0.0, 0.0, 0.0, 1.0), (15.0, 0.0, 0.0, 1.0), (15.0, 0.0, 15.0, 1.0), (0.0, 0.0, 15.0, 1.0)],
+        [(0, 1, 2), (0, 2, 3)],
+        [(0.0, 0.0), (15.0, 0.0), (15.0, 15.0), (0.0, 15.0)],
+    )
+    sky = Batch3D.from_box(-32.5, -20.0, -32.5, 80.0, 60.0, 80.0)
+
+    def fin(b, tile):
+        return b.source(PixelSource.StaticTileIndex(tile)).repeat_mode(RepeatMode.RepeatXY).cull_mode(CullMode.Off).with_computed_normals()
+
+    d3 = [fin(_quads_batch(brick), 1), fin(_quads_batch(panel), 2), fin(_quads_batch(fence), 3), fin(floor, 4),
+          fin(sky, 5).receives_light(False)]
+    logo = Batch2D.from_rectangle(0.0, 0.0, 200.0, 200.0).receives_light(False).source(PixelSource.StaticTileIndex(0))
+    light = (Light.new(LightType.Point).with_color([1.0, 1.0, 0xBB / 255.0]).with_intensity(2.0)
+             .with_start_distance(2.0).with_end_distance(13.0).with_position([9.0, 0.5, 15.0]).compile())
+    return Scene.from_static([logo], d3).lights_([light])
+
+
+def _firstp(pos, center):
+    c = D3FirstPCamera.new()
+    c.position = np.asarray(pos, dtype=np.float32)
+    c.center = np.asarray(center, dtype=np.float32)
+    return c
+
+
+def map_config(width=3840, height=2160, tile_size=40, logo_size=1024) -> Config:
+    """Config C (examples/map.rs:62-125): first-person camera inside the room, Nearest, ambient 1."""
+    pos = np.array([6.0600824, 1.0, 4.5524735], dtype=np.float32)
+    cam = _firstp(pos, pos + np.array([0.03489969, 0.0, 0.99939084], dtype=np.float32))
+    return Config("map", map_scene(), map_assets(logo_size), width, height, tile_size, SampleMode.Nearest, (1.0,) * 4, cam)
+
+
+def sweep(width=1920, height=1080, tile_size=40, n_frames=4096, logo_size=1024) -> Config:
+    """Config E: n_frames views of the map scene on a circle of radius 4 around the room centre."""
+    def cams(i):
+        th = 2.0 * math.pi * i / n_frames
+        return _firstp([7.5 + 4.0 * math.cos(th), 1.0, 7.5 + 4.0 * math.sin(th)], [7.5, 1.0, 7.5])
+
+    return Config("sweep", map_scene(), map_assets(logo_size), width, height, tile_size, SampleMode.Nearest, (1.0,) * 4,
+                  cams(0), cams, n_frames)
+
+
+def _fbm(x, z, seed):
+    def hash2(ix, iz):
+        with np.errstate(over="ignore"):
+            h = (ix.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)) ^ (iz.astype(np.uint64) * np.uint64(0xC2B2AE3D27D4EB4F)) ^ np.uint64(seed)
+            h = (h ^ (h >> np.uint64(29))) * np.uint64(0xBF58476D1CE4E5B9)
+            h = h ^ (h >> np.uint64(32))
+        return (h >> np.uint64(40)).astype(np.float32) / np.float32(1 << 24)
+
+    total = np.zeros_like(x, dtype=np.float32)
+    amp, freq = 1.0, 1.0 / 8.0
+    for _ in range(4):
+        fx, fz = x * freq, z * freq
+        ix, iz = np.floor(fx).astype(np.int64), np.floor(fz).astype(np.int64)
+        tx, tz = (fx - ix).astype(np.float32), (fz - iz).astype(np.float32)
+        tx, tz = tx * tx * (3 - 2 * tx), tz * tz * (3 - 2 * tz)
+        a, b = hash2(ix, iz), hash2(ix + 1, iz)
+        c, d = hash2(ix, iz + 1), hash2(ix + 1, iz + 1)
+        total += amp * ((a * (1 - tx) + b * tx) * (1 - tz) + (c * (1 - tx) + d * tx) * tz)
+        amp *= 0.5
+        freq *= 2.0
+    return total / 1.875
+
+
+def dense(width=7680, height=4320, tile_size=40, patches=32, patch_verts=23) -> Config:
+    """Config D: patches^2 batches tiling a 64x64-unit heightfield, (patch_verts-1)^2*2 triangles each
+    (defaults: 1024 batches, 991,232 triangles, 541,696 vertices), 16 textures, 4 point + 2 spot + 1 area light."""
+    extent = 64.0
+    psize = extent / patches
+    q = patch_verts - 1
+    jj, ii = np.meshgrid(np.arange(patch_verts), np.arange(patch_verts))
+    tri = []
+    for i in range(q):
+        for j in range(q):
+            a = i * patch_verts + j
+            tri.append((a, a + patch_verts, a + 1))
+            tri.append((a + 1, a + patch_verts, a + patch_verts + 1))
+    tri = np.asarray(tri, dtype=np.uint32)
+    batches = []
+    for pz in range(patches):
+        for px in range(patches):
+            x = (px * psize + jj.reshape(-1) * (psize / q)).astype(np.float32)
+            z = (pz * psize + ii.reshape(-1) * (psize / q)).astype(np.float32)
+            y = (1.5 * _fbm(x, z, SEED)).astype(np.float32)
+            v = np.stack([x, y, z, np.ones_like(x)], axis=1)
+            b = Batch3D(v, tri, np.stack([x, z], axis=1))
+            b.source(PixelSource.StaticTileIndex((pz * patches + px) % 16)).repeat_mode(RepeatMode.RepeatXY).cull_mode(CullMode.Off)
+            b.with_computed_normals_fast()
+            batches.append(b)
+    assets = Assets.default().textures([Tile.from_texture(tex_checker_noise(i)) for i in range(16)])
+    lights = []
+    cols = [(1.0, 0.85, 0.7), (0.7, 0.85, 1.0), (0.8, 1.0, 0.8), (1.0, 0.8, 1.0)]
+    for k, (cx, cz) in enumerate([(8.0, 8.0), (56.0, 8.0), (8.0, 56.0), (56.0, 56.0)]):
+        lights.append(Light.new(LightType.Point).with_position([cx, 3.0, cz]).with_color(cols[k]).with_intensity(1.5)
+                      .with_start_distance(4.0).with_end_distance(24.0).compile())
+    for sx in (20.0, 44.0):
+        d = np.array([32.0 - sx, -6.0, 0.0])
+        lights.append(Light.new(LightType.Spot).with_position([sx, 6.0, 32.0]).with_direction(d).with_cone_angle(math.pi / 6)
+                      .with_color([1.0, 1.0, 0.9]).with_intensity(2.0).with_start_distance(2.0).with_end_distance(30.0).compile())
+    lights.append(Light.new(LightType.Area).with_position([32.0, 5.0, 32.0]).with_normal([0.0, -1.0, 0.0]).with_size(4.0, 4.0)
+                  .with_color([1.0, 0.95, 0.9]).with_intensity(0.5).with_start_distance(3.0).with_end_distance(20.0).compile())
+    scene = Scene.from_static([], batches).lights_(lights)
+    cam = _firstp([32.0, 6.0, -4.0], [32.0, 0.0, 32.0])
+    return Config("dense", scene, assets, width, height, tile_size, SampleMode.Linear, (0.2,) * 4, cam)
+
+
+BUILDERS = {"cube": cube, "teapot": teapot, "map": map_config, "dense": dense, "sweep": sweep}

@@ -1,0 +1,559 @@
+"""Host-side mirror of the reference's data types on the rasterize path: Batch3D / Batch2D / Scene /
+Texture / Tile / Assets / CompiledLight / PixelSource and the enums.  Same names, builder methods
+and defaults as the Rust types so tests read like reference call sites; the data lives in numpy
+arrays that are marshalled into the C-ABI PODs of include/rxcuda.h by `marshal.py`.
+
+Reference: src/batch/batch3d.rs:15-137,421-479,812-842; src/batch/batch2d.rs:10-127;
+src/scene.rs:8-150; src/texture.rs:46-54; src/map/tile.rs:83-110; src/map/light.rs:128-193,457-477;
+src/map/pixelsource.rs:23-37; src/server/assets.rs:19."""
+from __future__ import annotations
+
+import enum
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import vekmath
+
+
+class PrimitiveMode(enum.IntEnum):  # src/batch/mod.rs:5-15
+    Triangles = 0
+    Lines = 1
+    LineStrip = 2
+    LineLoop = 3
+
+
+class CullMode(enum.IntEnum):  # src/batch/mod.rs:18-26
+    Off = 0
+    Front = 1
+    Back = 2
+
+
+class RepeatMode(enum.IntEnum):  # src/texture.rs:15-25
+    ClampXY = 0
+    RepeatXY = 1
+    RepeatX = 2
+    RepeatY = 3
+
+
+class SampleMode(enum.IntEnum):  # src/texture.rs:6-12
+    Nearest = 0
+    Linear = 1
+
+
+class LightType(enum.IntEnum):  # src/map/light.rs:7-14
+    Point = 0
+    Ambient = 1
+    AmbientDaylight = 2
+    Spot = 3
+    Area = 4
+    Daylight = 5
+
+
+class MatVecMode(enum.IntEnum):
+    FmaColumns = 0
+    PlainRows = 1
+
+
+class _SrcKind(enum.IntEnum):
+    Other = 0
+    StaticTile = 1
+    DynamicTile = 2
+    Pixel = 3
+    EntityTile = 4
+    ItemTile = 5
+    Terrain = 6
+
+
+@dataclass(frozen=True)
+class PixelSource:
+    """src/map/pixelsource.rs:23-37.  Use the constructors: PixelSource.Off, .StaticTileIndex(i) ..."""
+
+    kind: int = _SrcKind.Other
+    index: int = 0
+    pixel: tuple = (0, 0, 0, 0)
+    name: str = "Off"
+
+    @staticmethod
+    def StaticTileIndex(i: int) -> "PixelSource":
+        return PixelSource(_SrcKind.StaticTile, int(i), (0, 0, 0, 0), "StaticTileIndex")
+
+    @staticmethod
+    def DynamicTileIndex(i: int) -> "PixelSource":
+        return PixelSource(_SrcKind.DynamicTile, int(i), (0, 0, 0, 0), "DynamicTileIndex")
+
+    @staticmethod
+    def Pixel(rgba: Sequence[int]) -> "PixelSource":
+        return PixelSource(_SrcKind.Pixel, 0, tuple(int(c) for c in rgba), "Pixel")
+
+    @staticmethod
+    def Color(rgba: Sequence[int]) -> "PixelSource":
+        # TheColor: the rasterizer's non-overlay paths do not read it (src/rasterizer.rs:1221, :757)
+        return PixelSource(_SrcKind.Other, 0, tuple(int(c) for c in rgba), "Color")
+
+    @staticmethod
+    def EntityTile(id_: int, index: int) -> "PixelSource":
+        return PixelSource(_SrcKind.EntityTile, int(index), (0, 0, 0, 0), "EntityTile")
+
+    @staticmethod
+    def ItemTile(id_: int, index: int) -> "PixelSource":
+        return PixelSource(_SrcKind.ItemTile, int(index), (0, 0, 0, 0), "ItemTile")
+
+
+PixelSource.Off = PixelSource()
+PixelSource.Terrain = PixelSource(_SrcKind.Terrain, 0, (0, 0, 0, 0), "Terrain")
+
+
+class Texture:
+    """src/texture.rs:46-54: RGBA8 row-major."""
+
+    def __init__(self, data, width: int, height: int):
+        self.data = np.ascontiguousarray(np.asarray(data, dtype=np.uint8).reshape(-1))
+        self.width = int(width)
+        self.height = int(height)
+        if self.data.size != self.width * self.height * 4:
+            raise ValueError("Texture data must be width*height*4 bytes")
+
+    @staticmethod
+    def from_array(rgba: np.ndarray) -> "Texture":
+        rgba = np.asarray(rgba, dtype=np.uint8)
+        h, w, c = rgba.shape
+        assert c == 4
+        return Texture(rgba.reshape(-1), w, h)
+
+    @staticmethod
+    def from_image(path) -> "Texture":  # src/texture.rs:150-166 (decode -> RGBA8)
+        from PIL import Image
+
+        im = Image.open(path).convert("RGBA")
+        return Texture.from_array(np.asarray(im))
+
+    @staticmethod
+    def white() -> "Texture":
+        return Texture(np.full(4 * 100 * 100, 255, np.uint8), 100, 100)
+
+    def as_array(self) -> np.ndarray:
+        return self.data.reshape(self.height, self.width, 4)
+
+
+class Tile:
+    """src/map/tile.rs:83-110: animation frames."""
+
+    def __init__(self, textures: List[Texture]):
+        self.textures = list(textures)
+
+    @staticmethod
+    def from_texture(texture: Texture) -> "Tile":
+        return Tile([texture])
+
+    @staticmethod
+    def from_textures(textures: List[Texture]) -> "Tile":
+        return Tile(textures)
+
+
+class Assets:
+    """Only the member the rasterizer reads for static tiles: assets.tile_list (src/server/assets.rs:19)."""
+
+    def __init__(self):
+        self.tile_list: List[Tile] = []
+        self._generation = 0
+
+    @staticmethod
+    def default() -> "Assets":
+        return Assets()
+
+    def textures(self, tiles: List[Tile]) -> "Assets":  # builder, src/server/assets.rs:288-291
+        self.tile_list = list(tiles)
+        self._generation += 1
+        return self
+
+    def mark_dirty(self):
+        self._generation += 1
+
+
+@dataclass
+class CompiledLight:
+    """src/map/light.rs:457-477; defaults are those of Light::compile (:128-193)."""
+
+    light_type: LightType = LightType.Point
+    position: Sequence[float] = (0.0, 0.0, 0.0)
+    color: Sequence[float] = (1.0, 1.0, 1.0)
+    intensity: float = 1.0
+    emitting: bool = True
+    start_distance: float = 1.0
+    end_distance: float = 2.0
+    flicker: float = 0.0
+    direction: Sequence[float] = (0.0, 0.0, -1.0)
+    cone_angle: float = math.pi / 4
+    normal: Sequence[float] = (0.0, 1.0, 0.0)
+    width: float = 1.0
+    height: float = 1.0
+    from_linedef: bool = False
+
+
+class Light:
+    """Builder subset of src/map/light.rs Light (new / with_* / compile)."""
+
+    def __init__(self, light_type: LightType):
+        self._c = CompiledLight(light_type=light_type)
+
+    @staticmethod
+    def new(light_type: LightType) -> "Light":
+        return Light(light_type)
+
+    def with_intensity(self, v):
+        self._c.intensity = float(v)
+        return self
+
+    def with_color(self, c):
+        self._c.color = tuple(float(x) for x in c)
+        return self
+
+    def with_position(self, p):
+        self._c.position = tuple(float(x) for x in p)
+        return self
+
+    def with_start_distance(self, v):
+        self._c.start_distance = float(v)
+        return self
+
+    def with_end_distance(self, v):
+        self._c.end_distance = float(v)
+        return self
+
+    def with_flicker(self, v):
+        self._c.flicker = float(v)
+        return self
+
+    def with_direction(self, d):
+        d = np.asarray(d, dtype=np.float32)
+        self._c.direction = tuple((d / np.float32(np.sqrt(np.dot(d, d)))).tolist())  # .normalized() (:149-155)
+        return self
+
+    def with_cone_angle(self, v):
+        self._c.cone_angle = float(v)
+        return self
+
+    def with_normal(self, n):
+        n = np.asarray(n, dtype=np.float32)
+        self._c.normal = tuple((n / np.float32(np.sqrt(np.dot(n, n)))).tolist())
+        return self
+
+    def with_size(self, w, h):
+        self._c.width, self._c.height = float(w), float(h)
+        return self
+
+    def with_emitting(self, e):
+        self._c.emitting = bool(e)
+        return self
+
+    def compile(self) -> CompiledLight:
+        return self._c
+
+
+def _as_indices(indices) -> np.ndarray:
+    a = np.asarray(indices)
+    if a.size == 0:
+        return np.zeros((0, 3), dtype=np.uint32)
+    return np.ascontiguousarray(a.reshape(-1, 3).astype(np.uint32))
+
+
+class Batch3D:
+    """src/batch/batch3d.rs:15-78."""
+
+    def __init__(self, vertices, indices, uvs):
+        self.mode = PrimitiveMode.Triangles
+        self.vertices = np.ascontiguousarray(np.asarray(vertices, dtype=np.float32).reshape(-1, 4))
+        self.indices = _as_indices(indices)
+        self.uvs = np.ascontiguousarray(np.asarray(uvs, dtype=np.float32).reshape(-1, 2))
+        self.repeat_mode_ = RepeatMode.ClampXY
+        self.cull_mode_ = CullMode.Off
+        self.source_ = PixelSource.Off
+        self.transform_3d = vekmath.identity4()
+        self.receives_light_ = True
+        self.normals = np.zeros((0, 3), dtype=np.float32)
+        self.ambient_color_ = (0.0, 0.0, 0.0)
+        self.shader_: Optional[int] = None
+        self.profile_id_: Optional[int] = None
+        self.pass_ = 0
+
+    @staticmethod
+    def empty() -> "Batch3D":
+        return Batch3D(np.zeros((0, 4)), np.zeros((0, 3)), np.zeros((0, 2)))
+
+    @staticmethod
+    def new(vertices, indices, uvs) -> "Batch3D":
+        return Batch3D(vertices, indices, uvs)
+
+    @staticmethod
+    def from_box(x, y, z, width, height, depth) -> "Batch3D":
+        """Six faces, 24 vertices, 12 triangles; layout of src/batch/batch3d.rs:140-229."""
+        x0, x1, y0, y1, z0, z1 = x, x + width, y, y + height, z, z + depth
+        faces = [
+            [(x0, y0, z0), (x1, y0, z0), (x1, y1, z0), (x0, y1, z0)],  # front
+            [(x0, y0, z1), (x1, y0, z1), (x1, y1, z1), (x0, y1, z1)],  # back
+            [(x0, y0, z0), (x0, y1, z0), (x0, y1, z1), (x0, y0, z1)],  # left
+            [(x1, y0, z0), (x1, y1, z0), (x1, y1, z1), (x1, y0, z1)],  # right
+            [(x0, y1, z0), (x1, y1, z0), (x1, y1, z1), (x0, y1, z1)],  # top
+            [(x0, y0, z0), (x1, y0, z0), (x1, y0, z1), (x0, y0, z1)],  # bottom
+        ]
+        # per-face (second, third) corner of its two triangles, both starting at corner 0
+        winding = [((1, 2), (2, 3)), ((2, 1), (3, 2)), ((1, 2), (2, 3)), ((2, 1), (3, 2)), ((1, 2), (2, 3)), ((3, 2), (2, 1))]
+        verts, idx, uvs = [], [], []
+        for fi, face in enumerate(faces):
+            base = fi * 4
+            verts += [(*p, 1.0) for p in face]
+            uvs += [(0.0, 1.0), (1.0, 1.0), (1.0, 0.0), (0.0, 0.0)]
+            for a, b in winding[fi]:
+                idx.append((base, base + a, base + b))
+        return Batch3D(verts, idx, uvs)
+
+    @staticmethod
+    def from_obj(path_or_text) -> "Batch3D":  # src/batch/batch3d.rs:407-419
+        from .wavefront import Wavefront
+
+        return Wavefront.parse(path_or_text).to_batch()
+
+    # builder methods, src/batch/batch3d.rs:421-479
+    def mode_(self, mode):
+        self.mode = PrimitiveMode(mode)
+        return self
+
+    def repeat_mode(self, m):
+        self.repeat_mode_ = RepeatMode(m)
+        return self
+
+    def cull_mode(self, m):
+        self.cull_mode_ = CullMode(m)
+        return self
+
+    def source(self, s: PixelSource):
+        self.source_ = s
+        return self
+
+    def shader(self, i: int):
+        self.shader_ = int(i)
+        return self
+
+    def ambient_color(self, c):
+        self.ambient_color_ = tuple(float(x) for x in c)
+        return self
+
+    def transform(self, m):
+        self.transform_3d = np.asarray(m, dtype=np.float32).reshape(4, 4)
+        return self
+
+    def receives_light(self, v: bool):
+        self.receives_light_ = bool(v)
+        return self
+
+    def profile_id(self, v: int):
+        self.profile_id_ = int(v)
+        return self
+
+    def with_normals(self, normals):
+        self.normals = np.ascontiguousarray(np.asarray(normals, dtype=np.float32).reshape(-1, 3))
+        return self
+
+    def with_computed_normals(self) -> "Batch3D":
+        """Smooth vertex normals, src/batch/batch3d.rs:812-842 (float32, sequential accumulation)."""
+        n = np.zeros((len(self.vertices), 3), dtype=np.float32)
+        counts = np.zeros(len(self.vertices), dtype=np.uint32)
+        p = self.vertices[:, :3]
+        for i0, i1, i2 in self.indices.tolist():
+            e1 = p[i1] - p[i0]
+            e2 = p[i2] - p[i0]
+            c = np.array(
+                [e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]],
+                dtype=np.float32,
+            )
+            with np.errstate(invalid="ignore", divide="ignore"):
+                c = c / np.float32(np.sqrt(np.float32(c[0] * c[0] + c[1] * c[1] + c[2] * c[2])))
+            n[i0] += c
+            n[i1] += c
+            n[i2] += c
+            counts[i0] += 1
+            counts[i1] += 1
+            counts[i2] += 1
+        for i in range(len(n)):
+            if counts[i] > 0:
+                v = n[i] / np.float32(counts[i])
+                with np.errstate(invalid="ignore", divide="ignore"):
+                    n[i] = v / np.float32(np.sqrt(np.float32(v[0] * v[0] + v[1] * v[1] + v[2] * v[2])))
+        self.normals = n
+        return self
+
+    def with_computed_normals_fast(self) -> "Batch3D":
+        """Vectorised variant for the large synthetic scenes (same formula; accumulation order of
+        np.add.at instead of the sequential loop).  Normals are inputs to the path, not results."""
+        p = self.vertices[:, :3]
+        i0, i1, i2 = self.indices[:, 0], self.indices[:, 1], self.indices[:, 2]
+        c = np.cross(p[i1] - p[i0], p[i2] - p[i0]).astype(np.float32)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            c = (c / np.sqrt((c * c).sum(axis=1, dtype=np.float32))[:, None]).astype(np.float32)
+        n = np.zeros((len(p), 3), dtype=np.float32)
+        cnt = np.zeros(len(p), dtype=np.float32)
+        for ix in (i0, i1, i2):
+            np.add.at(n, ix, c)
+            np.add.at(cnt, ix, 1.0)
+        m = cnt > 0
+        n[m] = n[m] / cnt[m, None]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            n[m] = n[m] / np.sqrt((n[m] * n[m]).sum(axis=1, dtype=np.float32))[:, None]
+        self.normals = np.ascontiguousarray(n.astype(np.float32))
+        return self
+
+
+class Batch2D:
+    """src/batch/batch2d.rs:10-53."""
+
+    def __init__(self, vertices, indices, uvs):
+        self.mode = PrimitiveMode.Triangles
+        self.vertices = np.ascontiguousarray(np.asarray(vertices, dtype=np.float32).reshape(-1, 2))
+        self.indices = _as_indices(indices)
+        self.uvs = np.ascontiguousarray(np.asarray(uvs, dtype=np.float32).reshape(-1, 2))
+        self.repeat_mode_ = RepeatMode.ClampXY
+        self.source_ = PixelSource.Off
+        self.receives_light_ = True
+        self.shader_: Optional[int] = None
+
+    @staticmethod
+    def empty() -> "Batch2D":
+        return Batch2D(np.zeros((0, 2)), np.zeros((0, 3)), np.zeros((0, 2)))
+
+    @staticmethod
+    def new(vertices, indices, uvs) -> "Batch2D":
+        return Batch2D(vertices, indices, uvs)
+
+    @staticmethod
+    def from_rectangle(x, y, width, height) -> "Batch2D":  # src/batch/batch2d.rs:109-127
+        v = [(x, y), (x, y + height), (x + width, y + height), (x + width, y)]
+        return Batch2D(v, [(0, 1, 2), (0, 2, 3)], [(0.0, 0.0), (0.0, 1.0), (1.0, 1.0), (1.0, 0.0)])
+
+    def add_rectangle(self, x, y, width, height):
+        base = len(self.vertices)
+        v = np.array([(x, y), (x, y + height), (x + width, y + height), (x + width, y)], dtype=np.float32)
+        self.vertices = np.ascontiguousarray(np.concatenate([self.vertices, v]))
+        self.uvs = np.ascontiguousarray(
+            np.concatenate([self.uvs, np.array([(0, 0), (0, 1), (1, 1), (1, 0)], dtype=np.float32)])
+        )
+        self.indices = np.ascontiguousarray(
+            np.concatenate([self.indices, np.array([(base, base + 1, base + 2), (base, base + 2, base + 3)], np.uint32)])
+        )
+        return self
+
+    def mode_(self, mode):
+        self.mode = PrimitiveMode(mode)
+        return self
+
+    def repeat_mode(self, m):
+        self.repeat_mode_ = RepeatMode(m)
+        return self
+
+    def source(self, s: PixelSource):
+        self.source_ = s
+        return self
+
+    def shader(self, i: int):
+        self.shader_ = int(i)
+        return self
+
+    def receives_light(self, v: bool):
+        self.receives_light_ = bool(v)
+        return self
+
+
+class Scene:
+    """src/scene.rs:8-50 (the members the rasterize path reads)."""
+
+    def __init__(self):
+        self.background: Optional[object] = None  # a shader from rusterix_b200.shader
+        self.lights: List[CompiledLight] = []
+        self.dynamic_lights: List[CompiledLight] = []
+        self.d3_static: List[Batch3D] = []
+        self.d3_dynamic: List[Batch3D] = []
+        self.d3_overlay: List[Batch3D] = []
+        self.d2_static: List[Batch2D] = []
+        self.d2_dynamic: List[Batch2D] = []
+        self.dynamic_textures: List[Tile] = []
+        self.animation_frame = 0
+        self._generation = 0
+
+    @staticmethod
+    def empty() -> "Scene":
+        return Scene()
+
+    default = empty
+
+    @staticmethod
+    def from_static(d2: List[Batch2D], d3: List[Batch3D]) -> "Scene":  # src/scene.rs:83-91
+        s = Scene()
+        s.d2_static = list(d2)
+        s.d3_static = list(d3)
+        return s
+
+    def background_(self, shader) -> "Scene":
+        self.background = shader
+        return self
+
+    def lights_(self, lights: List[CompiledLight]) -> "Scene":
+        self.lights = list(lights)
+        return self
+
+    def anim_tick(self):  # src/scene.rs:147-150
+        self.animation_frame = (self.animation_frame + 1) & 0xFFFFFFFFFFFFFFFF
+
+    def mark_dirty(self):
+        """Tell the device cache that geometry / dynamic textures changed."""
+        self._generation += 1
+
+    def all_lights(self) -> List[CompiledLight]:
+        return list(self.lights) + list(self.dynamic_lights)
+
+
+@dataclass
+class VGrayGradientShader:  # src/shader/vgradient.rs:4-15
+    kind: int = 1
+
+
+@dataclass
+class GridShader:  # src/shader/grid.rs:4-35
+    kind: int = 2
+    grid_size: float = 30.0
+    subdivisions: float = 2.0
+    offset: Sequence[float] = (0.0, 0.0)
+
+    def set_parameter_f32(self, key, value):
+        if key == "grid_size":
+            self.grid_size = float(value)
+        elif key == "subdivisions":
+            self.subdivisions = float(value)
+
+    def set_parameter_vec2(self, key, value):
+        if key == "offset":
+            self.offset = (float(value[0]), float(value[1]))
+
+
+@dataclass
+class RenderMode:  # src/rendermode.rs:3-52
+    d2_active: bool = True
+    d3_active: bool = True
+    ignore_background_shader_: bool = False
+
+    @staticmethod
+    def render_all():
+        return RenderMode(True, True, False)
+
+    @staticmethod
+    def render_2d():
+        return RenderMode(True, False, False)
+
+    @staticmethod
+    def render_3d():
+        return RenderMode(False, True, False)
+
+    def ignore_background_shader(self, v: bool):
+        self.ignore_background_shader_ = bool(v)
+        return self
