@@ -20,6 +20,9 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-O2,-Wall",
     "-shared",
     "-cudart", "shared",
+    # libcudart.so.12: the toolkit copy or the one the venv's torch loads
+    "-Xlinker", "-rpath=/usr/local/cuda/lib64",
+    "-Xlinker", "-rpath=/opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/cuda_runtime/lib",
 ]
 
 

@@ -1,0 +1,743 @@
+// rx_api.cu -- the C ABI of include/rxcuda.h: context, scene/texture residency, per-frame launch
+// sequence.  Host logic only; the kernels are in rx_kernels.cu.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rx_kernels.cuh"
+
+namespace {
+
+const char* const kKernelNames[RXC_N_KERNELS] = {"k_frame_setup", "k_tri_setup", "k_batch_finalize", "k_clip_emit",
+                                                 "k_bin_count",   "k_tile_alloc", "k_bin_fill",      "k_raster"};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PendingEvent { int cls; cudaEvent_t a, b; };
+
+}  // namespace
+
+struct rxc_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // textures: static (assets.tile_list) then dynamic (scene.dynamic_textures)
+    std::vector<uint8_t> h_static_arena;
+    std::vector<DTex> h_static_tex;
+    std::vector<DTile> h_static_tiles;
+    std::vector<uint8_t> h_dyn_arena;
+    std::vector<DTex> h_dyn_tex;
+    std::vector<DTile> h_dyn_tiles;
+    DevBuf d_arena, d_tex, d_tiles;
+    bool textures_dirty = true;
+
+    // scene
+    std::vector<DBatch3> h_b3;
+    std::vector<DBatch2> h_b2;
+    std::vector<uint32_t> owner_base;
+    DevBuf d_pos, d_uv, d_nrm, d_idx, d_b3, d_chunks, d_orphans, d_pos2, d_uv2, d_idx2, d_b2, d_lights;
+    SceneDev S = {};
+    bool have_scene = false;
+
+    // per-frame workspace
+    Workspace W = {};
+    DevBuf w_frames, w_fb, w_fb2, w_lights, w_counters, w_vis, w_shade, w_bins, w_ctot, w_cbase, w_clip, w_large, w_tcount,
+        w_tbase, w_tfill, w_lists, w_tri2d, w_rcounter;
+    uint32_t ws_frames = 0, ws_tiles = 0;   // what the workspace is currently sized for
+    uint32_t list_cap_per_frame = 0, list_cap_min = 0;
+    DevBuf d_out_px, d_out_owner, d_out_depth;  // staging for host outputs
+    DFrame* h_frames = nullptr;  size_t h_frames_cap = 0;      // pinned
+    DCounters* h_counters = nullptr; size_t h_counters_cap = 0; // pinned
+    int raster_blocks_per_sm = 1;
+
+    // stats / profiling
+    rxc_stats stats = {};
+    bool profiling = false;
+    std::vector<PendingEvent> pending;
+    std::vector<cudaEvent_t> free_events;
+    bool async_overflow = false;
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                        \
+            return RXC_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+int32_t fail(rxc_ctx* ctx, int32_t code, const std::string& msg) {
+    ctx->err = msg;
+    return code;
+}
+
+int32_t reserve(rxc_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return RXC_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (b.p) CK(cudaFree(b.p));
+    b.p = nullptr; b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, RXC_ERR_OOM, "cudaMalloc of " + std::to_string(want) + " bytes failed"); }
+    b.cap = want;
+    return RXC_OK;
+}
+
+int32_t upload(rxc_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
+    int32_t st = reserve(ctx, b, std::max<size_t>(bytes, 16));
+    if (st != RXC_OK) return st;
+    if (bytes) {
+        CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));  // the source is only borrowed for the call
+        ctx->stats.h2d_bytes += bytes;
+    }
+    return RXC_OK;
+}
+
+void free_buf(DevBuf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+
+size_t idx_at(const void* indices, uint32_t index_bytes, size_t i) {
+    return index_bytes == 8 ? (size_t)((const uint64_t*)indices)[i] : (size_t)((const uint32_t*)indices)[i];
+}
+
+int32_t build_tiles(rxc_ctx* ctx, const rxc_tile* tiles, uint32_t n, std::vector<uint8_t>& arena, std::vector<DTex>& tex,
+                    std::vector<DTile>& out_tiles) {
+    arena.clear(); tex.clear(); out_tiles.clear();
+    for (uint32_t i = 0; i < n; ++i) {
+        DTile t; t.first = (uint32_t)tex.size(); t.n_frames = tiles[i].n_textures;
+        if (t.n_frames && !tiles[i].textures) return fail(ctx, RXC_ERR_INVALID, "tile without textures pointer");
+        for (uint32_t j = 0; j < t.n_frames; ++j) {
+            const rxc_texture& x = tiles[i].textures[j];
+            if (!x.data || x.width == 0 || x.height == 0) return fail(ctx, RXC_ERR_INVALID, "empty texture");
+            DTex d; d.offset = arena.size(); d.width = x.width; d.height = x.height; d.pad = 0;
+            size_t bytes = (size_t)x.width * x.height * 4;
+            bool opaque = true;
+            for (size_t k = 3; k < bytes; k += 4) if (x.data[k] != 255) { opaque = false; break; }
+            d.all_opaque = opaque ? 1u : 0u;
+            arena.insert(arena.end(), x.data, x.data + bytes);
+            arena.resize((arena.size() + 255) & ~(size_t)255);
+            tex.push_back(d);
+        }
+        out_tiles.push_back(t);
+    }
+    return RXC_OK;
+}
+
+int32_t upload_textures(rxc_ctx* ctx) {
+    std::vector<uint8_t> arena = ctx->h_static_arena;
+    std::vector<DTex> tex = ctx->h_static_tex;
+    std::vector<DTile> tiles = ctx->h_static_tiles;
+    const size_t aoff = arena.size();
+    const uint32_t toff = (uint32_t)tex.size();
+    arena.insert(arena.end(), ctx->h_dyn_arena.begin(), ctx->h_dyn_arena.end());
+    for (DTex d : ctx->h_dyn_tex) { d.offset += aoff; tex.push_back(d); }
+    for (DTile t : ctx->h_dyn_tiles) { t.first += toff; tiles.push_back(t); }
+    int32_t st;
+    if ((st = upload(ctx, ctx->d_arena, arena.data(), arena.size())) != RXC_OK) return st;
+    if ((st = upload(ctx, ctx->d_tex, tex.data(), tex.size() * sizeof(DTex))) != RXC_OK) return st;
+    if ((st = upload(ctx, ctx->d_tiles, tiles.data(), tiles.size() * sizeof(DTile))) != RXC_OK) return st;
+    ctx->S.arena = ctx->d_arena.as<uint8_t>();
+    ctx->S.tex = ctx->d_tex.as<DTex>();
+    ctx->S.tiles = ctx->d_tiles.as<DTile>();
+    ctx->S.n_static_tiles = (uint32_t)ctx->h_static_tiles.size();
+    ctx->S.n_dynamic_tiles = (uint32_t)ctx->h_dyn_tiles.size();
+    ctx->textures_dirty = false;
+    return RXC_OK;
+}
+
+int32_t upload_lights(rxc_ctx* ctx, const rxc_light* lights, uint32_t n) {
+    std::vector<DLight> h(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        const rxc_light& l = lights[i];
+        DLight d = {};
+        d.light_type = l.light_type; d.emitting = l.emitting; d.from_linedef = l.from_linedef;
+        d.px = l.position[0]; d.py = l.position[1]; d.pz = l.position[2]; d.intensity = l.intensity;
+        d.cr = l.color[0]; d.cg = l.color[1]; d.cb = l.color[2];
+        d.flicker_factor = l.flicker;  // raw flicker; k_frame_setup turns it into the per-frame factor
+        d.start_distance = l.start_distance; d.end_distance = l.end_distance; d.cone_angle = l.cone_angle;
+        d.width = l.width; d.height = l.height;
+        d.dx = l.direction[0]; d.dy = l.direction[1]; d.dz = l.direction[2];
+        d.nx = l.normal[0]; d.ny = l.normal[1]; d.nz = l.normal[2];
+        if (l.light_type > RXC_LIGHT_DAYLIGHT) return fail(ctx, RXC_ERR_INVALID, "unknown light type");
+        h[i] = d;
+    }
+    int32_t st = upload(ctx, ctx->d_lights, h.data(), h.size() * sizeof(DLight));
+    if (st != RXC_OK) return st;
+    ctx->S.lights = ctx->d_lights.as<DLight>();
+    ctx->S.n_lights = n;
+    return RXC_OK;
+}
+
+cudaEvent_t get_event(rxc_ctx* ctx) {
+    if (!ctx->free_events.empty()) { cudaEvent_t e = ctx->free_events.back(); ctx->free_events.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+void drain_events(rxc_ctx* ctx) {  // caller has synchronized the stream
+    for (auto& p : ctx->pending) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) ctx->stats.kernel_ms[p.cls] += ms;
+        ctx->free_events.push_back(p.a);
+        ctx->free_events.push_back(p.b);
+    }
+    ctx->pending.clear();
+}
+
+struct LaunchScope {  // counts a launch and, when profiling, brackets it with events
+    rxc_ctx* ctx; int cls; cudaEvent_t a = nullptr, b = nullptr;
+    LaunchScope(rxc_ctx* c, int k) : ctx(c), cls(k) {
+        ctx->stats.kernel_launches++; ctx->stats.launches[cls]++;
+        if (ctx->profiling) { a = get_event(ctx); b = get_event(ctx); cudaEventRecord(a, ctx->stream); }
+    }
+    ~LaunchScope() {
+        if (ctx->profiling) { cudaEventRecord(b, ctx->stream); ctx->pending.push_back({cls, a, b}); }
+    }
+};
+
+bool is_device_pointer(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+int32_t ensure_workspace(rxc_ctx* ctx, uint32_t n_frames, uint32_t tiles_per_frame) {
+    SceneDev& S = ctx->S;
+    Workspace& W = ctx->W;
+    const size_t T = S.n_tris, nf = n_frames;
+    const uint32_t want_list = std::max<uint32_t>(ctx->list_cap_min, (uint32_t)std::min<size_t>(6 * T + tiles_per_frame + 1024, 0xFFFFFFF0u));
+    if (n_frames <= ctx->ws_frames && tiles_per_frame <= ctx->ws_tiles && want_list <= ctx->list_cap_per_frame) return RXC_OK;
+    ctx->list_cap_per_frame = want_list;
+    int32_t st;
+#define RES(buf, bytes) if ((st = reserve(ctx, ctx->buf, (bytes))) != RXC_OK) return st
+    RES(w_frames, nf * sizeof(DFrame));
+    RES(w_fb, nf * std::max<size_t>(1, S.n_b3) * sizeof(DFrameBatch));
+    RES(w_fb2, nf * std::max<size_t>(1, S.n_b2) * sizeof(DFrameBatch2));
+    RES(w_lights, nf * std::max<size_t>(1, S.n_lights) * sizeof(DLight));
+    RES(w_counters, nf * sizeof(DCounters));
+    RES(w_vis, nf * std::max<size_t>(1, 3 * T) * sizeof(TriVis));
+    RES(w_shade, nf * std::max<size_t>(1, 3 * T) * sizeof(TriShade));
+    RES(w_bins, nf * std::max<size_t>(1, 3 * T) * sizeof(TriBin));
+    RES(w_ctot, nf * std::max<size_t>(1, S.n_chunks) * 4);
+    RES(w_cbase, nf * std::max<size_t>(1, S.n_chunks) * 4);
+    RES(w_clip, nf * std::max<size_t>(1, T) * sizeof(DClip));
+    RES(w_large, nf * std::max<size_t>(1, 3 * T) * 4);
+    RES(w_tcount, nf * (size_t)tiles_per_frame * 4);
+    RES(w_tbase, nf * (size_t)tiles_per_frame * 4);
+    RES(w_tfill, nf * (size_t)tiles_per_frame * 4);
+    RES(w_lists, nf * (size_t)want_list * 4);
+    RES(w_tri2d, nf * std::max<size_t>(1, S.n_rec2d) * sizeof(Tri2D));
+    RES(w_rcounter, 16);
+#undef RES
+    W.frames = ctx->w_frames.as<DFrame>();
+    W.fb = ctx->w_fb.as<DFrameBatch>(); W.fb_stride = std::max(1u, S.n_b3);
+    W.fb2 = ctx->w_fb2.as<DFrameBatch2>(); W.fb2_stride = std::max(1u, S.n_b2);
+    W.lights = ctx->w_lights.as<DLight>(); W.lights_stride = std::max(1u, S.n_lights);
+    W.counters = ctx->w_counters.as<DCounters>();
+    W.vis = ctx->w_vis.as<TriVis>(); W.slot_stride = (uint32_t)std::max<size_t>(1, 3 * T);
+    W.shade = ctx->w_shade.as<TriShade>();
+    W.bins = ctx->w_bins.as<TriBin>(); W.bins_stride = (uint32_t)std::max<size_t>(1, 3 * T);
+    W.chunk_new_total = ctx->w_ctot.as<uint32_t>();
+    W.chunk_new_base = ctx->w_cbase.as<uint32_t>(); W.chunk_stride = std::max(1u, S.n_chunks);
+    W.clip = ctx->w_clip.as<DClip>(); W.clip_stride = (uint32_t)std::max<size_t>(1, T);
+    W.large = ctx->w_large.as<uint32_t>(); W.large_stride = (uint32_t)std::max<size_t>(1, 3 * T);
+    W.tile_count = ctx->w_tcount.as<uint32_t>();
+    W.tile_base = ctx->w_tbase.as<uint32_t>();
+    W.tile_fill = ctx->w_tfill.as<uint32_t>(); W.tile_stride = tiles_per_frame;
+    W.lists = ctx->w_lists.as<uint32_t>(); W.list_stride = want_list;
+    W.tri2d = ctx->w_tri2d.as<Tri2D>(); W.tri2d_stride = std::max(1u, S.n_rec2d);
+    W.raster_counter = ctx->w_rcounter.as<uint32_t>();
+    ctx->ws_frames = n_frames;
+    ctx->ws_tiles = tiles_per_frame;
+    return RXC_OK;
+}
+
+size_t workspace_bytes_per_frame(const SceneDev& S, uint32_t tiles_per_frame) {
+    const size_t T = S.n_tris;
+    return sizeof(DFrame) + S.n_b3 * sizeof(DFrameBatch) + 3 * T * (sizeof(TriVis) + sizeof(TriShade) + sizeof(TriBin) + 4) +
+           T * sizeof(DClip) + (size_t)tiles_per_frame * 12 + (6 * T + tiles_per_frame + 1024) * 4 + S.n_rec2d * sizeof(Tri2D) + 4096;
+}
+
+uint32_t hash_u32_host(uint32_t seed) {  // rasterizer.rs:199-207
+    uint32_t state = seed;
+    state = (state ^ 61u) ^ (state >> 16);
+    state = state + (state << 3);
+    state ^= state >> 4;
+    state = state * 0x27d4eb2du;
+    state ^= state >> 15;
+    return state;
+}
+
+int32_t fill_frame(rxc_ctx* ctx, const rxc_frame& f, DFrame* d) {
+    if (f.width == 0 || f.height == 0 || f.tile_size == 0) return fail(ctx, RXC_ERR_INVALID, "width, height and tile_size must be non-zero");
+    if (f.width > 16384 || f.height > 16384) return fail(ctx, RXC_ERR_UNSUPPORTED, "frames larger than 16384 pixels per side");
+    if (f.sample_mode > RXC_SAMPLE_LINEAR || f.matvec_mode > RXC_MATVEC_PLAIN_ROWS || f.background_shader > RXC_BG_GRID)
+        return fail(ctx, RXC_ERR_INVALID, "bad enum value in rxc_frame");
+    uint32_t y0 = f.band_y0, y1 = f.band_y1;
+    if (y0 == 0 && y1 == 0) y1 = f.height;
+    if (y0 >= y1 || y1 > f.height) return fail(ctx, RXC_ERR_INVALID, "bad band");
+    memset(d, 0, sizeof(*d));
+    memcpy(d->view, f.view, 64); memcpy(d->proj, f.projection, 64);
+    memcpy(d->inv_view, f.inverse_view, 64); memcpy(d->inv_proj, f.inverse_projection, 64);
+    memcpy(d->mat2d, f.matrix2d, 36);
+    d->has_mat2d = f.has_matrix2d ? 1u : 0u;
+    d->cam[0] = f.inverse_view[12]; d->cam[1] = f.inverse_view[13]; d->cam[2] = f.inverse_view[14];  // rasterizer.rs:98-102
+    d->width_f = (float)f.width; d->height_f = (float)f.height;
+    d->width = (int32_t)f.width; d->height = (int32_t)f.height;
+    d->band_y0 = (int32_t)y0; d->band_y1 = (int32_t)y1;
+    d->tiles_x = (int32_t)((f.width + RX_TILE_W - 1) / RX_TILE_W);
+    d->tiles_y = (int32_t)((y1 - y0 + RX_TILE_H - 1) / RX_TILE_H);
+    d->tile_size = std::min<uint32_t>(f.tile_size, std::max(f.width, f.height));  // one tile either way
+    d->sample_mode = f.sample_mode;
+    d->has_bg_color = f.has_background_color ? 1u : 0u;
+    memcpy(&d->bg_color, f.background_color, 4);
+    d->bg_shader = f.background_shader;
+    d->grid_size = f.grid_size; d->grid_subdiv = f.grid_subdivisions;
+    d->grid_off[0] = f.grid_offset[0]; d->grid_off[1] = f.grid_offset[1];
+    d->has_ambient = f.has_ambient ? 1u : 0u;
+    memcpy(d->ambient, f.ambient, 16);
+    d->hash_anim = hash_u32_host((uint32_t)f.animation_frame);  // rasterizer.rs:208
+    d->d2_active = f.d2_active ? 1u : 0u; d->d3_active = f.d3_active ? 1u : 0u;
+    d->ignore_bg_shader = f.ignore_background_shader ? 1u : 0u;
+    d->preserve_transparency = f.preserve_transparency ? 1u : 0u;
+    d->matvec_mode = f.matvec_mode;
+    d->trans2d[0] = 0.0f; d->trans2d[1] = 0.0f; d->scale2d = 1.0f;  // rasterizer.rs:104-110
+    if (f.has_matrix2d) { d->trans2d[0] = f.matrix2d[6]; d->trans2d[1] = f.matrix2d[7]; d->scale2d = f.matrix2d[0]; }
+    d->animation_frame = f.animation_frame;
+    return RXC_OK;
+}
+
+int32_t validate_sources(rxc_ctx* ctx) {
+    // 3D: the reference indexes tile_list / dynamic_textures directly and panics (rasterizer.rs:1103,:1126)
+    for (size_t i = 0; i < ctx->h_b3.size(); ++i) {
+        const DBatch3& b = ctx->h_b3[i];
+        if (b.source_kind == RXC_SRC_STATIC_TILE) {
+            if (b.source_index >= ctx->h_static_tiles.size() || ctx->h_static_tiles[b.source_index].n_frames == 0)
+                return fail(ctx, RXC_ERR_INDEX, "3D batch " + std::to_string(i) + ": StaticTileIndex out of range (reference panics)");
+        } else if (b.source_kind == RXC_SRC_DYNAMIC_TILE) {
+            if (b.source_index >= ctx->h_dyn_tiles.size() || ctx->h_dyn_tiles[b.source_index].n_frames == 0)
+                return fail(ctx, RXC_ERR_INDEX, "3D batch " + std::to_string(i) + ": DynamicTileIndex out of range (reference panics)");
+        }
+    }
+    for (size_t i = 0; i < ctx->h_b2.size(); ++i) {
+        const DBatch2& b = ctx->h_b2[i];
+        const auto& tiles = b.source_kind == RXC_SRC_STATIC_TILE ? ctx->h_static_tiles : ctx->h_dyn_tiles;
+        if ((b.source_kind == RXC_SRC_STATIC_TILE || b.source_kind == RXC_SRC_DYNAMIC_TILE) && b.source_index < tiles.size() &&
+            tiles[b.source_index].n_frames == 0)
+            return fail(ctx, RXC_ERR_INDEX, "2D batch " + std::to_string(i) + ": tile without textures (reference panics on % 0)");
+    }
+    return RXC_OK;
+}
+
+// Runs frames [first, first+n) of one group through the kernel sequence.
+int32_t launch_group(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n, uint8_t* d_pixels, uint64_t stride, uint32_t* d_owner,
+                     float* d_depth) {
+    SceneDev& S = ctx->S;
+    const uint32_t tiles_per_frame = (uint32_t)ctx->h_frames[0].tiles_x * (uint32_t)ctx->h_frames[0].tiles_y;
+    (void)frames;
+    CK(cudaMemcpyAsync(ctx->W.frames, ctx->h_frames, n * sizeof(DFrame), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += n * sizeof(DFrame);
+    const int wide = ctx->sm_count * 8;
+    auto grid_for = [&](size_t items, int per_block) { return (int)std::max<size_t>(1, std::min<size_t>((items + per_block - 1) / per_block, (size_t)wide)); };
+    { LaunchScope l(ctx, RXK_FRAME_SETUP); CK(rxk_frame_setup(S, ctx->W, n, tiles_per_frame, ctx->stream)); }
+    if (S.n_tris) {
+        { LaunchScope l(ctx, RXK_TRI_SETUP); CK(rxk_tri_setup(S, ctx->W, n, ctx->stream)); }
+        { LaunchScope l(ctx, RXK_BATCH_FINALIZE); CK(rxk_batch_finalize(S, ctx->W, n, ctx->stream)); }
+        { LaunchScope l(ctx, RXK_CLIP_EMIT); CK(rxk_clip_emit(S, ctx->W, n, grid_for(std::min<size_t>(S.n_tris, 65536), 128), ctx->stream)); }
+        { LaunchScope l(ctx, RXK_BIN_COUNT); CK(rxk_bin_count(S, ctx->W, n, grid_for((size_t)S.n_tris + S.n_tris / 8, 256), ctx->stream)); }
+        { LaunchScope l(ctx, RXK_TILE_ALLOC); CK(rxk_tile_alloc(S, ctx->W, n, tiles_per_frame, ctx->stream)); }
+        { LaunchScope l(ctx, RXK_BIN_FILL); CK(rxk_bin_fill(S, ctx->W, n, grid_for((size_t)S.n_tris + S.n_tris / 8, 256), ctx->stream)); }
+    }
+    RasterOut out;
+    out.pixels = d_pixels; out.frame_stride = stride; out.owner = d_owner; out.depth = d_depth;
+    out.vec_store = (((uintptr_t)d_pixels & 15) == 0 && (stride & 15) == 0 && ((ctx->h_frames[0].width * 4) & 15) == 0) ? 1u : 0u;
+    const size_t total_tiles = (size_t)n * tiles_per_frame;
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>(total_tiles, (size_t)ctx->sm_count * ctx->raster_blocks_per_sm));
+    { LaunchScope l(ctx, RXK_RASTER); CK(rxk_raster(S, ctx->W, out, n, tiles_per_frame, grid, ctx->stream)); }
+    CK(cudaMemcpyAsync(ctx->h_counters, ctx->W.counters, n * sizeof(DCounters), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->stats.frames += n;
+    return RXC_OK;
+}
+
+// checks the counters copied back by launch_group (stream must be synchronized); 1 = retry needed
+int32_t check_group(rxc_ctx* ctx, uint32_t n, bool* retry) {
+    *retry = false;
+    uint32_t ov = 0, need = 0;
+    for (uint32_t i = 0; i < n; ++i) { ov |= ctx->h_counters[i].overflow; need = std::max(need, ctx->h_counters[i].list_cursor); }
+    const DCounters& c = ctx->h_counters[n - 1];
+    ctx->stats.last_binned_refs = c.list_cursor;
+    ctx->stats.last_large_tris = c.n_large;
+    ctx->stats.last_clipped_tris = c.n_new_slots;
+    ctx->stats.last_visible_tris = c.n_visible;
+    if (ov & 1u) {  // tile-list arena too small: grow to what the frame asked for and run it again
+        ctx->list_cap_min = need + need / 4 + 1024;
+        *retry = true;
+    }
+    if (ov & 6u) return fail(ctx, RXC_ERR_OOM, "internal list overflow (large/clip); this is a bug");
+    return RXC_OK;
+}
+
+int32_t rasterize_impl(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames, uint8_t* pixels, uint64_t stride, uint32_t* owner,
+                       float* depth, bool sync) {
+    if (!ctx) return RXC_ERR_INVALID;
+    if (!frames || n_frames == 0 || !pixels) return fail(ctx, RXC_ERR_INVALID, "frames and pixels are required");
+    if (!ctx->have_scene) return fail(ctx, RXC_ERR_INVALID, "rxc_set_scene has not been called");
+    if ((owner || depth) && n_frames != 1) return fail(ctx, RXC_ERR_INVALID, "owner/depth planes are single-frame outputs");
+    CK(cudaSetDevice(ctx->device));
+    int32_t st;
+    if (ctx->textures_dirty && (st = upload_textures(ctx)) != RXC_OK) return st;
+    if ((st = validate_sources(ctx)) != RXC_OK) return st;
+
+    // all frames of a batch share the geometry of the output
+    const rxc_frame& f0 = frames[0];
+    for (uint32_t i = 1; i < n_frames; ++i)
+        if (frames[i].width != f0.width || frames[i].height != f0.height || frames[i].band_y0 != f0.band_y0 || frames[i].band_y1 != f0.band_y1)
+            return fail(ctx, RXC_ERR_INVALID, "all frames of a batch must share width/height/band");
+    DFrame probe;
+    if ((st = fill_frame(ctx, f0, &probe)) != RXC_OK) return st;
+    const uint32_t rows = (uint32_t)(probe.band_y1 - probe.band_y0);
+    const uint64_t frame_bytes = (uint64_t)f0.width * rows * 4;
+    if (n_frames > 1 && stride < frame_bytes) return fail(ctx, RXC_ERR_INVALID, "frame_stride_bytes smaller than a frame");
+    const uint32_t tiles_per_frame = (uint32_t)probe.tiles_x * (uint32_t)probe.tiles_y;
+
+    // frames are processed in groups sized to a workspace budget
+    const size_t per_frame = workspace_bytes_per_frame(ctx->S, tiles_per_frame);
+    const size_t budget = (size_t)3 << 30;
+    uint32_t group = (uint32_t)std::max<size_t>(1, std::min<size_t>(n_frames, budget / std::max<size_t>(1, per_frame)));
+    group = std::min(group, 1024u);
+
+    const bool dev_px = is_device_pointer(pixels);
+    const bool dev_owner = owner && is_device_pointer(owner);
+    const bool dev_depth = depth && is_device_pointer(depth);
+    if (!sync && ctx->async_overflow) { /* reported at the next synchronize */ }
+
+    if (ctx->h_frames_cap < group) {
+        if (ctx->h_frames) cudaFreeHost(ctx->h_frames);
+        if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+        CK(cudaMallocHost((void**)&ctx->h_frames, group * sizeof(DFrame)));
+        CK(cudaMallocHost((void**)&ctx->h_counters, group * sizeof(DCounters)));
+        ctx->h_frames_cap = group;
+    }
+
+    for (uint32_t first = 0; first < n_frames; first += group) {
+        const uint32_t n = std::min(group, n_frames - first);
+        for (int attempt = 0; attempt < 4; ++attempt) {
+            if ((st = ensure_workspace(ctx, n, tiles_per_frame)) != RXC_OK) return st;
+            // the pinned frame block is reused per group: the previous group's copy must have been consumed
+            if (first != 0 || attempt != 0 || !sync) CK(cudaStreamSynchronize(ctx->stream));
+            for (uint32_t i = 0; i < n; ++i)
+                if ((st = fill_frame(ctx, frames[first + i], &ctx->h_frames[i])) != RXC_OK) return st;
+            uint8_t* d_px = pixels + (uint64_t)first * stride;
+            uint64_t d_stride = stride;
+            if (!dev_px) {
+                if ((st = reserve(ctx, ctx->d_out_px, (size_t)n * frame_bytes)) != RXC_OK) return st;
+                d_px = ctx->d_out_px.as<uint8_t>(); d_stride = frame_bytes;
+            }
+            uint32_t* d_ow = owner; float* d_dp = depth;
+            if (owner && !dev_owner) { if ((st = reserve(ctx, ctx->d_out_owner, frame_bytes)) != RXC_OK) return st; d_ow = ctx->d_out_owner.as<uint32_t>(); }
+            if (depth && !dev_depth) { if ((st = reserve(ctx, ctx->d_out_depth, frame_bytes)) != RXC_OK) return st; d_dp = ctx->d_out_depth.as<float>(); }
+            if ((st = launch_group(ctx, frames + first, n, d_px, d_stride, d_ow, d_dp)) != RXC_OK) return st;
+            if (!sync && dev_px) break;  // truly asynchronous: counters are checked at the next synchronize
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (ctx->profiling) drain_events(ctx);
+            bool retry = false;
+            if ((st = check_group(ctx, n, &retry)) != RXC_OK) return st;
+            if (retry) continue;
+            if (!dev_px) {
+                if (stride == frame_bytes || n == 1) {
+                    CK(cudaMemcpyAsync(pixels + (uint64_t)first * stride, d_px, (size_t)n * frame_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+                } else {
+                    CK(cudaMemcpy2DAsync(pixels + (uint64_t)first * stride, stride, d_px, frame_bytes, frame_bytes, n, cudaMemcpyDeviceToHost, ctx->stream));
+                }
+                ctx->stats.d2h_bytes += (uint64_t)n * frame_bytes;
+            }
+            if (owner && !dev_owner) { CK(cudaMemcpyAsync(owner, d_ow, frame_bytes, cudaMemcpyDeviceToHost, ctx->stream)); ctx->stats.d2h_bytes += frame_bytes; }
+            if (depth && !dev_depth) { CK(cudaMemcpyAsync(depth, d_dp, frame_bytes, cudaMemcpyDeviceToHost, ctx->stream)); ctx->stats.d2h_bytes += frame_bytes; }
+            CK(cudaStreamSynchronize(ctx->stream));
+            break;
+        }
+    }
+    return RXC_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// exported C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+uint32_t rxc_abi_version(void) { return RXC_ABI_VERSION; }
+
+const char* rxc_kernel_name(uint32_t k) { return k < RXC_N_KERNELS ? kKernelNames[k] : ""; }
+
+int32_t rxc_create(int32_t device, rxc_ctx** out) {
+    if (!out) return RXC_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) { cudaGetLastError(); return RXC_ERR_NO_DEVICE; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return RXC_ERR_CUDA;
+    if (prop.major != 10) return RXC_ERR_NO_DEVICE;  // the library holds sm_100a code only
+    if (cudaSetDevice(device) != cudaSuccess) return RXC_ERR_CUDA;
+    rxc_ctx* ctx = new rxc_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RXC_ERR_CUDA; }
+    ctx->stream = ctx->own_stream;
+    ctx->raster_blocks_per_sm = rxk_raster_blocks_per_sm();
+    *out = ctx;
+    return RXC_OK;
+}
+
+void rxc_destroy(rxc_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = {&ctx->d_arena, &ctx->d_tex, &ctx->d_tiles, &ctx->d_pos, &ctx->d_uv, &ctx->d_nrm, &ctx->d_idx, &ctx->d_b3,
+                      &ctx->d_chunks, &ctx->d_orphans, &ctx->d_pos2, &ctx->d_uv2, &ctx->d_idx2, &ctx->d_b2, &ctx->d_lights,
+                      &ctx->w_frames, &ctx->w_fb, &ctx->w_fb2, &ctx->w_lights, &ctx->w_counters, &ctx->w_vis, &ctx->w_shade,
+                      &ctx->w_bins, &ctx->w_ctot, &ctx->w_cbase, &ctx->w_clip, &ctx->w_large, &ctx->w_tcount, &ctx->w_tbase,
+                      &ctx->w_tfill, &ctx->w_lists, &ctx->w_tri2d, &ctx->w_rcounter, &ctx->d_out_px, &ctx->d_out_owner, &ctx->d_out_depth};
+    for (DevBuf* b : bufs) free_buf(*b);
+    if (ctx->h_frames) cudaFreeHost(ctx->h_frames);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    for (auto& p : ctx->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (auto e : ctx->free_events) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* rxc_last_error(const rxc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int32_t rxc_set_stream(rxc_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return RXC_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return RXC_OK;
+}
+
+int32_t rxc_set_assets(rxc_ctx* ctx, const rxc_tile* tiles, uint32_t n_tiles) {
+    if (!ctx || (n_tiles && !tiles)) return RXC_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int32_t st = build_tiles(ctx, tiles, n_tiles, ctx->h_static_arena, ctx->h_static_tex, ctx->h_static_tiles);
+    if (st != RXC_OK) return st;
+    ctx->textures_dirty = true;
+    return upload_textures(ctx);
+}
+
+int32_t rxc_set_lights(rxc_ctx* ctx, const rxc_light* lights, uint32_t n_lights) {
+    if (!ctx || (n_lights && !lights)) return RXC_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t before = ctx->S.n_lights;
+    int32_t st = upload_lights(ctx, lights, n_lights);
+    if (st != RXC_OK) return st;
+    if (n_lights > before) ctx->ws_frames = 0;  // per-frame light slices must grow
+    return RXC_OK;
+}
+
+int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
+    if (!ctx || !sc) return RXC_ERR_INVALID;
+    if ((sc->n_batches3d && !sc->batches3d) || (sc->n_batches2d && !sc->batches2d) || (sc->n_lights && !sc->lights) ||
+        (sc->n_dynamic_textures && !sc->dynamic_textures))
+        return fail(ctx, RXC_ERR_INVALID, "null array with non-zero count in rxc_scene");
+    CK(cudaSetDevice(ctx->device));
+    ctx->have_scene = false;
+
+    // ---- validate + size
+    size_t V = 0, T = 0, V2 = 0, T2 = 0;
+    for (uint32_t i = 0; i < sc->n_batches3d; ++i) {
+        const rxc_batch3d& b = sc->batches3d[i];
+        const std::string who = "3D batch " + std::to_string(i) + ": ";
+        if (b.shader >= 0) return fail(ctx, RXC_ERR_UNSUPPORTED, who + "batch shaders (Rusteria VM) are not on the device path");
+        if (b.source_kind > RXC_SRC_TERRAIN) return fail(ctx, RXC_ERR_INVALID, who + "bad source kind");
+        if (b.source_kind >= RXC_SRC_ENTITY_TILE) return fail(ctx, RXC_ERR_UNSUPPORTED, who + "EntityTile/ItemTile/Terrain sources are not on the device path");
+        if (b.pass == RXC_PASS_CHUNK_OPACITY) return fail(ctx, RXC_ERR_UNSUPPORTED, who + "chunk opacity batches are not on the device path");
+        if (b.index_bytes != 4 && b.index_bytes != 8) return fail(ctx, RXC_ERR_INVALID, who + "index_bytes must be 4 or 8");
+        if (b.cull_mode > RXC_CULL_BACK || b.repeat_mode > RXC_REPEAT_REPEAT_Y) return fail(ctx, RXC_ERR_INVALID, who + "bad enum value");
+        if ((b.n_vertices && (!b.vertices || !b.uvs)) || (b.n_triangles && !b.indices)) return fail(ctx, RXC_ERR_INVALID, who + "null geometry pointer");
+        for (size_t k = 0; k < (size_t)b.n_triangles * 3; ++k)
+            if (idx_at(b.indices, b.index_bytes, k) >= b.n_vertices) return fail(ctx, RXC_ERR_INDEX, who + "vertex index out of range (reference panics)");
+        V += b.n_vertices; T += b.n_triangles;
+    }
+    for (uint32_t i = 0; i < sc->n_batches2d; ++i) {
+        const rxc_batch2d& b = sc->batches2d[i];
+        const std::string who = "2D batch " + std::to_string(i) + ": ";
+        if (b.shader >= 0) return fail(ctx, RXC_ERR_UNSUPPORTED, who + "batch shaders (Rusteria VM) are not on the device path");
+        if (b.source_kind > RXC_SRC_TERRAIN) return fail(ctx, RXC_ERR_INVALID, who + "bad source kind");
+        if (b.source_kind >= RXC_SRC_ENTITY_TILE) return fail(ctx, RXC_ERR_UNSUPPORTED, who + "EntityTile/ItemTile/Terrain sources are not on the device path");
+        if (b.mode != RXC_MODE_TRIANGLES) return fail(ctx, RXC_ERR_UNSUPPORTED, who + "line primitives are not on the device path yet");
+        if (b.index_bytes != 4 && b.index_bytes != 8) return fail(ctx, RXC_ERR_INVALID, who + "index_bytes must be 4 or 8");
+        if (b.repeat_mode > RXC_REPEAT_REPEAT_Y) return fail(ctx, RXC_ERR_INVALID, who + "bad enum value");
+        if ((b.n_vertices && (!b.vertices || !b.uvs)) || (b.n_triangles && !b.indices)) return fail(ctx, RXC_ERR_INVALID, who + "null geometry pointer");
+        for (size_t k = 0; k < (size_t)b.n_triangles * 3; ++k)
+            if (idx_at(b.indices, b.index_bytes, k) >= b.n_vertices) return fail(ctx, RXC_ERR_INDEX, who + "vertex index out of range (reference panics)");
+        V2 += b.n_vertices; T2 += b.n_triangles;
+    }
+    if (3 * T >= 0x7FFFFFFFull || V >= 0xFFFFFFFFull) return fail(ctx, RXC_ERR_UNSUPPORTED, "scene too large for 32-bit slots");
+
+    // ---- flatten 3D
+    std::vector<float> pos(V * 4), uv(V * 2), nrm(V * 3, 0.0f);
+    std::vector<uint32_t> idx(T * 3), orphans;
+    std::vector<DChunk> chunks;
+    ctx->h_b3.assign(sc->n_batches3d, DBatch3{});
+    ctx->owner_base.assign(sc->n_batches3d, 0);
+    size_t vo = 0, to = 0;
+    for (uint32_t i = 0; i < sc->n_batches3d; ++i) {
+        const rxc_batch3d& b = sc->batches3d[i];
+        DBatch3& d = ctx->h_b3[i];
+        d.v_off = (uint32_t)vo; d.n_verts = b.n_vertices; d.t_off = (uint32_t)to; d.n_tris = b.n_triangles;
+        d.owner_base = (uint32_t)(3 * to);
+        ctx->owner_base[i] = d.owner_base;
+        d.cull_mode = b.cull_mode; d.repeat_mode = b.repeat_mode; d.source_kind = b.source_kind; d.source_index = b.source_index;
+        memcpy(&d.source_pixel, b.source_pixel, 4);
+        d.has_normals = b.normals ? 1u : 0u;
+        memcpy(d.ambient, b.ambient_color, 12);
+        memcpy(d.transform, b.transform, 64);
+        if (b.n_vertices) {
+            memcpy(&pos[vo * 4], b.vertices, (size_t)b.n_vertices * 16);
+            memcpy(&uv[vo * 2], b.uvs, (size_t)b.n_vertices * 8);
+            if (b.normals) memcpy(&nrm[vo * 3], b.normals, (size_t)b.n_vertices * 12);
+        }
+        float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (uint32_t v = 0; v < b.n_vertices; ++v)
+            for (int k = 0; k < 3; ++k) { mn[k] = std::fmin(mn[k], b.vertices[v * 4 + k]); mx[k] = std::fmax(mx[k], b.vertices[v * 4 + k]); }
+        memcpy(d.aabb_min, mn, 12); memcpy(d.aabb_max, mx, 12);
+        std::vector<uint8_t> used(b.n_vertices, 0);
+        for (size_t k = 0; k < (size_t)b.n_triangles * 3; ++k) {
+            size_t v = idx_at(b.indices, b.index_bytes, k);
+            used[v] = 1;
+            idx[to * 3 + k] = (uint32_t)(vo + v);
+        }
+        d.orphan_off = (uint32_t)orphans.size();
+        if (b.n_triangles)
+            for (uint32_t v = 0; v < b.n_vertices; ++v) if (!used[v]) orphans.push_back((uint32_t)(vo + v));
+        d.n_orphans = (uint32_t)orphans.size() - d.orphan_off;
+        d.chunk_first = (uint32_t)chunks.size();
+        for (uint32_t t = 0; t < b.n_triangles; t += RX_CHUNK_TRIS)
+            chunks.push_back(DChunk{i, (uint32_t)to + t, std::min<uint32_t>(RX_CHUNK_TRIS, b.n_triangles - t), 0});
+        d.n_chunks = (uint32_t)chunks.size() - d.chunk_first;
+        vo += b.n_vertices; to += b.n_triangles;
+    }
+    // ---- flatten 2D
+    std::vector<float> pos2(V2 * 2), uv2(V2 * 2);
+    std::vector<uint32_t> idx2(T2 * 3);
+    ctx->h_b2.assign(sc->n_batches2d, DBatch2{});
+    size_t vo2 = 0, to2 = 0;
+    for (uint32_t i = 0; i < sc->n_batches2d; ++i) {
+        const rxc_batch2d& b = sc->batches2d[i];
+        DBatch2& d = ctx->h_b2[i];
+        d.v_off = (uint32_t)vo2; d.n_verts = b.n_vertices; d.t_off = (uint32_t)to2; d.n_tris = b.n_triangles;
+        d.mode = b.mode; d.repeat_mode = b.repeat_mode; d.source_kind = b.source_kind; d.source_index = b.source_index;
+        memcpy(&d.source_pixel, b.source_pixel, 4);
+        d.receives_light = b.receives_light ? 1u : 0u;
+        d.rec_off = (uint32_t)to2;
+        if (b.n_vertices) { memcpy(&pos2[vo2 * 2], b.vertices, (size_t)b.n_vertices * 8); memcpy(&uv2[vo2 * 2], b.uvs, (size_t)b.n_vertices * 8); }
+        for (size_t k = 0; k < (size_t)b.n_triangles * 3; ++k) idx2[to2 * 3 + k] = (uint32_t)(vo2 + idx_at(b.indices, b.index_bytes, k));
+        vo2 += b.n_vertices; to2 += b.n_triangles;
+    }
+
+    int32_t st;
+    if ((st = build_tiles(ctx, sc->dynamic_textures, sc->n_dynamic_textures, ctx->h_dyn_arena, ctx->h_dyn_tex, ctx->h_dyn_tiles)) != RXC_OK) return st;
+    ctx->textures_dirty = true;
+    if ((st = upload_textures(ctx)) != RXC_OK) return st;
+    if ((st = upload(ctx, ctx->d_pos, pos.data(), pos.size() * 4)) != RXC_OK) return st;
+    if ((st = upload(ctx, ctx->d_uv, uv.data(), uv.size() * 4)) != RXC_OK) return st;
+    if ((st = upload(ctx, ctx->d_nrm, nrm.data(), nrm.size() * 4)) != RXC_OK) return st;
+    if ((st = upload(ctx, ctx->d_idx, idx.data(), idx.size() * 4)) != RXC_OK) return st;
+    if ((st = upload(ctx, ctx->d_b3, ctx->h_b3.data(), ctx->h_b3.size() * sizeof(DBatch3))) != RXC_OK) return st;
+    if ((st = upload(ctx, ctx->d_chunks, chunks.data(), chunks.size() * sizeof(DChunk))) != RXC_OK) return st;
+    if ((st = upload(ctx, ctx->d_orphans, orphans.data(), orphans.size() * 4)) != RXC_OK) return st;
+    if ((st = upload(ctx, ctx->d_pos2, pos2.data(), pos2.size() * 4)) != RXC_OK) return st;
+    if ((st = upload(ctx, ctx->d_uv2, uv2.data(), uv2.size() * 4)) != RXC_OK) return st;
+    if ((st = upload(ctx, ctx->d_idx2, idx2.data(), idx2.size() * 4)) != RXC_OK) return st;
+    if ((st = upload(ctx, ctx->d_b2, ctx->h_b2.data(), ctx->h_b2.size() * sizeof(DBatch2))) != RXC_OK) return st;
+    if ((st = upload_lights(ctx, sc->lights, sc->n_lights)) != RXC_OK) return st;
+
+    SceneDev& S = ctx->S;
+    S.pos = ctx->d_pos.as<float4>(); S.uv = ctx->d_uv.as<float2>(); S.nrm = ctx->d_nrm.as<float>(); S.idx = ctx->d_idx.as<uint32_t>();
+    S.b3 = ctx->d_b3.as<DBatch3>(); S.chunks = ctx->d_chunks.as<DChunk>(); S.orphans = ctx->d_orphans.as<uint32_t>();
+    S.pos2 = ctx->d_pos2.as<float2>(); S.uv2 = ctx->d_uv2.as<float2>(); S.idx2 = ctx->d_idx2.as<uint32_t>(); S.b2 = ctx->d_b2.as<DBatch2>();
+    S.n_b3 = sc->n_batches3d; S.n_b2 = sc->n_batches2d; S.n_chunks = (uint32_t)chunks.size();
+    S.n_tris = (uint32_t)T; S.n_verts = (uint32_t)V; S.n_rec2d = (uint32_t)T2;
+    ctx->ws_frames = 0;  // workspace strides depend on the scene
+    ctx->list_cap_min = 0;
+    ctx->have_scene = true;
+    return RXC_OK;
+}
+
+int32_t rxc_rasterize(rxc_ctx* ctx, const rxc_frame* frame, uint8_t* pixels, uint32_t* owner, float* depth) {
+    return rasterize_impl(ctx, frame, 1, pixels, 0, owner, depth, true);
+}
+int32_t rxc_rasterize_async(rxc_ctx* ctx, const rxc_frame* frame, uint8_t* pixels, uint32_t* owner, float* depth) {
+    return rasterize_impl(ctx, frame, 1, pixels, 0, owner, depth, false);
+}
+int32_t rxc_rasterize_batch(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames, uint8_t* pixels, uint64_t frame_stride_bytes) {
+    return rasterize_impl(ctx, frames, n_frames, pixels, frame_stride_bytes, nullptr, nullptr, true);
+}
+int32_t rxc_rasterize_batch_async(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames, uint8_t* pixels, uint64_t frame_stride_bytes) {
+    return rasterize_impl(ctx, frames, n_frames, pixels, frame_stride_bytes, nullptr, nullptr, false);
+}
+
+int32_t rxc_synchronize(rxc_ctx* ctx) {
+    if (!ctx) return RXC_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->profiling) drain_events(ctx);
+    if (ctx->h_counters && ctx->ws_frames) {
+        bool retry = false;
+        int32_t st = check_group(ctx, 1, &retry);
+        if (st != RXC_OK) return st;
+        if (retry) return fail(ctx, RXC_ERR_OOM, "tile-list arena overflowed during an asynchronous frame; it has been grown, render the frame again");
+    }
+    return RXC_OK;
+}
+
+int32_t rxc_owner_base(const rxc_ctx* ctx, uint32_t batch, uint32_t* base) {
+    if (!ctx || !base || batch >= ctx->owner_base.size()) return RXC_ERR_INVALID;
+    *base = ctx->owner_base[batch];
+    return RXC_OK;
+}
+
+int32_t rxc_set_profiling(rxc_ctx* ctx, int32_t enabled) {
+    if (!ctx) return RXC_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    drain_events(ctx);
+    ctx->profiling = enabled != 0;
+    return RXC_OK;
+}
+
+int32_t rxc_get_stats(rxc_ctx* ctx, rxc_stats* out) {
+    if (!ctx || !out) return RXC_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->profiling) { CK(cudaStreamSynchronize(ctx->stream)); drain_events(ctx); }
+    *out = ctx->stats;
+    return RXC_OK;
+}
+
+int32_t rxc_reset_stats(rxc_ctx* ctx) {
+    if (!ctx) return RXC_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    drain_events(ctx);
+    ctx->stats = rxc_stats{};
+    return RXC_OK;
+}
+
+}  // extern "C"

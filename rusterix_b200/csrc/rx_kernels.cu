@@ -1,0 +1,1009 @@
+// rx_kernels.cu -- the sm_100a kernels of the rasterize path.
+//
+//   k_frame_setup     per (frame, batch) matrices, frustum-AABB reject, texture frame, light flicker,
+//                     2D batch projection + records, counter / tile-count zeroing
+//   k_tri_setup       per original triangle: view transform, early cull, near classification,
+//                     projection, cull/swap, edge equations, depth/uv reciprocals, pixel bbox;
+//                     batch screen bbox by block reduction + atomics; near-clip counting + block scan
+//   k_batch_finalize  per batch: scan of the per-chunk clip counts, API-tile scissor from the bbox
+//   k_clip_emit       per near-clipped triangle: Sutherland-Hodgman, fan triangles at ordered slots
+//   k_bin_count       final (scissored) bbox, tile counts, large-triangle list
+//   k_tile_alloc      per tile: list space from an atomic arena cursor
+//   k_bin_fill        tile lists
+//   k_raster          persistent, one CTA per 16x16 tile at a time: staged triangle records in shared
+//                     memory, per-pixel exact edge/depth test, alpha test, deferred shading of the
+//                     owner, miss pass, 2D pass, 128-bit RGBA8 stores
+//
+// Reference cites are to /root/reference (markusmoenig/Rusterix).
+#include "rx_kernels.cuh"
+
+#include <math_constants.h>
+
+namespace {
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// rasterizer.rs:199-207
+__device__ __forceinline__ uint32_t hash_u32(uint32_t seed) {
+    uint32_t state = seed;
+    state = (state ^ 61u) ^ (state >> 16);
+    state = state + (state << 3);
+    state ^= state >> 4;
+    state = state * 0x27d4eb2du;
+    state ^= state >> 15;
+    return state;
+}
+
+// The reference rejects a batch per API tile (rasterizer.rs:978-983 / :594-600).  Over one axis the
+// accepted tiles form a contiguous range; return the pixel range [o0, o1) they cover.
+__device__ void scissor_1d(float bx, float bw, int dim, int ts, float pad, int* o0, int* o1) {
+    const int nt = (dim + ts - 1) / ts;
+    const float far_edge = bx + bw;
+    int lo = 0, hi = nt;
+    while (lo < hi) {  // first tile with  bx < (tile.x + tile.w) as f32 (+ pad)
+        int mid = (lo + hi) >> 1;
+        long long e = (long long)(mid + 1) * ts;
+        float h = (float)(e < dim ? (int)e : dim) + pad;
+        if (bx < h) hi = mid; else lo = mid + 1;
+    }
+    const int kA = lo;
+    lo = 0; hi = nt;
+    while (lo < hi) {  // first tile where  bx + bw > tile.x as f32 (- pad)  fails
+        int mid = (lo + hi) >> 1;
+        float l = (float)((long long)mid * ts) - pad;
+        if (far_edge > l) lo = mid + 1; else hi = mid;
+    }
+    const int kB = lo - 1;
+    if (kA > kB) { *o0 = 0; *o1 = 0; return; }
+    long long e = (long long)(kB + 1) * ts;
+    *o0 = kA * ts;
+    *o1 = (int)(e < dim ? e : dim);
+}
+
+__device__ __forceinline__ void edge_eq(float x0, float y0, float x1, float y1, float* a, float* b, float* c) {
+    *a = y1 - y0;               // edge.rs:18
+    *b = x0 - x1;               // edge.rs:19
+    *c = x1 * y0 - y1 * x0;     // edge.rs:20
+}
+
+// pixel range visited for a primitive spanning [mn, mx] on one axis (rasterizer.rs:1014-1017, union over tiles)
+__device__ __forceinline__ void pixel_range(float mn, float mx, int dim, int* lo, int* hi) {
+    *lo = (mn == mn) ? rx_sat_int(floorf(mn), dim) : 0;
+    *hi = (mx == mx) ? rx_sat_int(ceilf(mx), dim) : dim;
+}
+
+struct ClipVert { f4 p; float u, v; f3 n; };
+
+// batch3d.rs:626-669.  Returns the number of polygon vertices (0, 3 or 4).
+__device__ int clip_polygon(const f4 vv[3], const float2 uv[3], const f3 nn[3], ClipVert out[4]) {
+    int n = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int j = (i + 1) % 3;
+        const f4 cur = vv[i], nxt = vv[j];
+        const bool cin = cur.z < -RX_NEAR_PLANE, nin = nxt.z < -RX_NEAR_PLANE;
+        if (cin) {
+            out[n].p = cur; out[n].u = uv[i].x; out[n].v = uv[i].y; out[n].n = nn[i];
+            ++n;
+        }
+        if (cin != nin) {
+            float t = (-RX_NEAR_PLANE - cur.z) / (nxt.z - cur.z);
+            out[n].p = {cur.x + t * (nxt.x - cur.x), cur.y + t * (nxt.y - cur.y), cur.z + t * (nxt.z - cur.z),
+                        cur.w + t * (nxt.w - cur.w)};
+            out[n].u = uv[i].x + t * (uv[j].x - uv[i].x);
+            out[n].v = uv[i].y + t * (uv[j].y - uv[i].y);
+            f3 a = rx_scale3(nn[i], 1.0f - t), b = rx_scale3(nn[j], t);
+            out[n].n = rx_normalize3(rx_add3(a, b));
+            ++n;
+        }
+    }
+    return n;
+}
+
+// batch3d.rs:706-739 + the per-triangle constants of rasterizer.rs:989-1076.
+// Returns visibility; fills the records and the raw pixel bbox when visible.
+__device__ bool make_tri(const f4 P[3], const float2 uv[3], const f3 nn[3], uint32_t cull_mode, bool edge_vis, int W, int H,
+                         uint32_t meta, TriVis* tv, TriShade* ts, uint32_t* bbx, uint32_t* bby) {
+    const f4 v0 = P[0];
+    f4 v1 = P[1], v2 = P[2];
+    const float orientation = (v1.x - v0.x) * (v2.y - v0.y) - (v1.y - v0.y) * (v2.x - v0.x);  // batch3d.rs:743-746
+    const bool front = orientation > 0.0f;
+    bool visible;
+    bool swap = false;
+    if (cull_mode == RXC_CULL_OFF) { swap = front; visible = true; }
+    else if (cull_mode == RXC_CULL_FRONT) { visible = !front; }
+    else { swap = front; visible = front; }
+    visible = visible && edge_vis;
+    if (!visible) return false;
+    if (swap) { f4 t = v1; v1 = v2; v2 = t; }
+
+    int x0, x1, y0, y1;
+    pixel_range(fminf(P[0].x, fminf(P[1].x, P[2].x)), fmaxf(P[0].x, fmaxf(P[1].x, P[2].x)), W, &x0, &x1);
+    pixel_range(fminf(P[0].y, fminf(P[1].y, P[2].y)), fmaxf(P[0].y, fmaxf(P[1].y, P[2].y)), H, &y0, &y1);
+    if (x0 >= x1 || y0 >= y1) return false;  // no pixel centre can be visited
+    *bbx = (uint32_t)x0 | ((uint32_t)x1 << 16);
+    *bby = (uint32_t)y0 | ((uint32_t)y1 << 16);
+
+    TriVis r;
+    edge_eq(v0.x, v0.y, v1.x, v1.y, &r.ea[0], &r.eb[0], &r.ec[0]);
+    edge_eq(v1.x, v1.y, v2.x, v2.y, &r.ea[1], &r.eb[1], &r.ec[1]);
+    edge_eq(v2.x, v2.y, v0.x, v0.y, &r.ea[2], &r.eb[2], &r.ec[2]);
+    r.ax = P[0].x; r.ay = P[0].y; r.bx = P[1].x; r.by = P[1].y; r.cx = P[2].x; r.cy = P[2].y;
+    r.acx = P[2].x - P[0].x; r.acy = P[2].y - P[0].y;
+    const float abx = P[1].x - P[0].x, aby = P[1].y - P[0].y;
+    r.area = r.acx * aby - r.acy * abx;  // rasterizer.rs:1767
+    r.iz0 = 1.0f / P[0].z; r.iz1 = 1.0f / P[1].z; r.iz2 = 1.0f / P[2].z;  // rasterizer.rs:1054-1055
+    r.bbx = *bbx; r.bby = *bby; r.meta = meta;
+    *tv = r;
+
+    TriShade s;
+    s.uw0 = uv[0].x / P[0].w; s.vw0 = uv[0].y / P[0].w;  // rasterizer.rs:1062-1072
+    s.uw1 = uv[1].x / P[1].w; s.vw1 = uv[1].y / P[1].w;
+    s.uw2 = uv[2].x / P[2].w; s.vw2 = uv[2].y / P[2].w;
+    s.rw0 = 1.0f / P[0].w; s.rw1 = 1.0f / P[1].w; s.rw2 = 1.0f / P[2].w;
+    s.n0x = nn[0].x; s.n0y = nn[0].y; s.n0z = nn[0].z;
+    s.n1x = nn[1].x; s.n1y = nn[1].y; s.n1z = nn[1].z;
+    s.n2x = nn[2].x; s.n2y = nn[2].y; s.n2z = nn[2].z;
+    s.pad0 = 0.0f; s.pad1 = 0.0f;
+    *ts = s;
+    return true;
+}
+
+struct MinMax {
+    float mnx, mxx, mny, mxy;
+    __device__ void init() { mnx = CUDART_INF_F; mxx = -CUDART_INF_F; mny = CUDART_INF_F; mxy = -CUDART_INF_F; }
+    __device__ void add(float x, float y) {  // f32::min / f32::max ignore NaN (batch3d.rs:755-760)
+        mnx = fminf(mnx, x); mxx = fmaxf(mxx, x); mny = fminf(mny, y); mxy = fmaxf(mxy, y);
+    }
+};
+
+__device__ void block_minmax_to_keys(MinMax m, uint32_t* kminx, uint32_t* kmaxx, uint32_t* kminy, uint32_t* kmaxy) {
+    __shared__ float s_red[4][32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m.mnx = fminf(m.mnx, __shfl_xor_sync(0xFFFFFFFFu, m.mnx, o));
+        m.mxx = fmaxf(m.mxx, __shfl_xor_sync(0xFFFFFFFFu, m.mxx, o));
+        m.mny = fminf(m.mny, __shfl_xor_sync(0xFFFFFFFFu, m.mny, o));
+        m.mxy = fmaxf(m.mxy, __shfl_xor_sync(0xFFFFFFFFu, m.mxy, o));
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    if (lane == 0) { s_red[0][warp] = m.mnx; s_red[1][warp] = m.mxx; s_red[2][warp] = m.mny; s_red[3][warp] = m.mxy; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < nw; ++w) {
+            m.mnx = fminf(m.mnx, s_red[0][w]); m.mxx = fmaxf(m.mxx, s_red[1][w]);
+            m.mny = fminf(m.mny, s_red[2][w]); m.mxy = fmaxf(m.mxy, s_red[3][w]);
+        }
+        atomicMin(kminx, rx_float_key(m.mnx)); atomicMax(kmaxx, rx_float_key(m.mxx));
+        atomicMin(kminy, rx_float_key(m.mny)); atomicMax(kmaxy, rx_float_key(m.mxy));
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_frame_setup
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_frame_setup(SceneDev S, Workspace Wk, uint32_t tiles_per_frame) {
+    const uint32_t f = blockIdx.y;
+    const DFrame& F = Wk.frames[f];
+    const uint32_t tid = threadIdx.x;
+
+    if (blockIdx.x == 0) {
+        if (tid == 0) {
+            DCounters z = {};
+            Wk.counters[f] = z;
+            if (f == 0) *Wk.raster_counter = 0u;
+        }
+        // light flicker is a per-frame constant of the light (light.rs:656-672)
+        for (uint32_t i = tid; i < S.n_lights; i += blockDim.x) {
+            DLight l = S.lights[i];
+            float factor = 1.0f;
+            if (l.flicker_factor /* holds `flicker` in the scene copy */ > 0.0f) {
+                uint32_t s = (rx_as_u32(l.px) + rx_as_u32(l.py) + rx_as_u32(l.pz)) * 100u;
+                uint32_t combined = F.hash_anim + s;
+                float fv = rx_clamp((float)combined / 4294967296.0f, 0.0f, 1.0f);
+                factor = 1.0f - fv * l.flicker_factor;
+            }
+            l.flicker_factor = factor;
+            Wk.lights[(size_t)f * Wk.lights_stride + i] = l;
+        }
+        for (uint32_t b = tid; b < S.n_b3; b += blockDim.x) {
+            const DBatch3& B = S.b3[b];
+            DFrameBatch fb;
+            float pv[16], mvp[16];
+            rx_matmat4(F.proj, F.view, pv, F.matvec_mode);          // batch3d.rs:490
+            rx_matmat4(pv, B.transform, mvp, F.matvec_mode);
+            rx_matmat4(F.view, B.transform, fb.view_model, F.matvec_mode);  // batch3d.rs:555
+            bool rejected = false;
+            if (B.n_verts != 0) {  // batch3d.rs:493-552
+                bool ol = true, orr = true, ob = true, ot = true, on = true, of = true;
+                for (int c = 0; c < 8; ++c) {
+                    f4 v = {(c & 4) ? B.aabb_max[0] : B.aabb_min[0], (c & 2) ? B.aabb_max[1] : B.aabb_min[1],
+                            (c & 1) ? B.aabb_max[2] : B.aabb_min[2], 1.0f};
+                    f4 r = rx_matvec4(mvp, v, F.matvec_mode);
+                    float w = r.w;
+                    ol &= r.x < -w; orr &= r.x > w; ob &= r.y < -w; ot &= r.y > w; on &= r.z < -w; of &= r.z > w;
+                }
+                rejected = ol || orr || ob || ot || on || of;
+            }
+            // a constant Pixel source that is not opaque can never write (rasterizer.rs:1408)
+            if (B.source_kind == RXC_SRC_PIXEL && (B.source_pixel >> 24) != 255u) rejected = true;
+            fb.tex = 0xFFFFFFFFu;
+            fb.alpha_test = 0;
+            if (B.source_kind == RXC_SRC_STATIC_TILE || B.source_kind == RXC_SRC_DYNAMIC_TILE) {
+                const DTile t = S.tiles[(B.source_kind == RXC_SRC_STATIC_TILE ? 0u : S.n_static_tiles) + B.source_index];
+                fb.tex = t.first + (uint32_t)(F.animation_frame % t.n_frames);  // rasterizer.rs:1104-1105
+                fb.alpha_test = S.tex[fb.tex].all_opaque ? 0u : 1u;
+            }
+            fb.bb_minx = rx_float_key(CUDART_INF_F); fb.bb_maxx = rx_float_key(-CUDART_INF_F);
+            fb.bb_miny = rx_float_key(CUDART_INF_F); fb.bb_maxy = rx_float_key(-CUDART_INF_F);
+            fb.sc_x0 = fb.sc_x1 = fb.sc_y0 = fb.sc_y1 = 0;
+            fb.rejected = (rejected || !F.d3_active) ? 1u : 0u;
+            fb.n_new_tris = 0;
+            Wk.fb[(size_t)f * Wk.fb_stride + b] = fb;
+        }
+        return;
+    }
+
+    if (blockIdx.x <= S.n_b2) {  // one CTA per 2D batch: batch2d.rs:373-425
+        const uint32_t b = blockIdx.x - 1;
+        const DBatch2& B = S.b2[b];
+        Tri2D* recs = Wk.tri2d + (size_t)f * Wk.tri2d_stride + B.rec_off;
+        const bool active = F.d2_active != 0;
+        MinMax mm; mm.init();
+        if (active) {
+            for (uint32_t i = tid; i < B.n_verts; i += blockDim.x) {
+                float2 p = S.pos2[B.v_off + i];
+                if (F.has_mat2d) { f3 r = rx_matvec3(F.mat2d, {p.x, p.y, 1.0f}, F.matvec_mode); p.x = r.x; p.y = r.y; }
+                mm.add(p.x, p.y);
+            }
+        }
+        __shared__ uint32_t s_key[4];
+        if (tid == 0) {
+            s_key[0] = rx_float_key(CUDART_INF_F); s_key[1] = rx_float_key(-CUDART_INF_F);
+            s_key[2] = rx_float_key(CUDART_INF_F); s_key[3] = rx_float_key(-CUDART_INF_F);
+        }
+        __syncthreads();
+        block_minmax_to_keys(mm, &s_key[0], &s_key[1], &s_key[2], &s_key[3]);
+        const float mnx = rx_key_float(s_key[0]), mxx = rx_key_float(s_key[1]);
+        const float mny = rx_key_float(s_key[2]), mxy = rx_key_float(s_key[3]);
+        int sx0, sx1, sy0, sy1;
+        scissor_1d(mnx, mxx - mnx, F.width, (int)F.tile_size, 0.5f, &sx0, &sx1);   // rasterizer.rs:594-600
+        scissor_1d(mny, mxy - mny, F.height, (int)F.tile_size, 0.5f, &sy0, &sy1);
+        sy0 = max(sy0, F.band_y0); sy1 = min(sy1, F.band_y1);
+        if (tid == 0) {
+            DFrameBatch2 fb2;
+            fb2.tex = 0xFFFFFFFFu;
+            if (B.source_kind == RXC_SRC_STATIC_TILE || B.source_kind == RXC_SRC_DYNAMIC_TILE) {
+                const uint32_t nt = (B.source_kind == RXC_SRC_STATIC_TILE) ? S.n_static_tiles : S.n_dynamic_tiles;
+                if (B.source_index < nt) {  // rasterizer.rs:674-687: a missing tile samples as transparent
+                    const DTile t = S.tiles[(B.source_kind == RXC_SRC_STATIC_TILE ? 0u : S.n_static_tiles) + B.source_index];
+                    fb2.tex = t.first + (uint32_t)(F.animation_frame % t.n_frames);
+                }
+            }
+            fb2.lit = ((B.receives_light && S.n_lights != 0) || F.has_ambient) ? 1u : 0u;  // rasterizer.rs:799-802
+            fb2.pad[0] = fb2.pad[1] = 0;
+            Wk.fb2[(size_t)f * Wk.fb2_stride + b] = fb2;
+        }
+        for (uint32_t t = tid; t < B.n_tris; t += blockDim.x) {
+            Tri2D r = {};
+            r.batch = b; r.kind = 0;
+            if (active && sx0 < sx1 && sy0 < sy1) {
+                const uint32_t i0 = S.idx2[(size_t)(B.t_off + t) * 3 + 0], i1 = S.idx2[(size_t)(B.t_off + t) * 3 + 1],
+                               i2 = S.idx2[(size_t)(B.t_off + t) * 3 + 2];
+                float2 p[3] = {S.pos2[i0], S.pos2[i1], S.pos2[i2]};
+                if (F.has_mat2d) {
+                    for (int k = 0; k < 3; ++k) { f3 q = rx_matvec3(F.mat2d, {p[k].x, p[k].y, 1.0f}, F.matvec_mode); p[k].x = q.x; p[k].y = q.y; }
+                }
+                const float2 t0 = S.uv2[i0], t1 = S.uv2[i1], t2 = S.uv2[i2];
+                r.ax = p[0].x; r.ay = p[0].y; r.bx = p[1].x; r.by = p[1].y; r.cx = p[2].x; r.cy = p[2].y;
+                r.u0 = t0.x; r.v0 = t0.y; r.u1 = t1.x; r.v1 = t1.y; r.u2 = t2.x; r.v2 = t2.y;
+                edge_eq(p[0].x, p[0].y, p[1].x, p[1].y, &r.ea[0], &r.eb[0], &r.ec[0]);
+                edge_eq(p[1].x, p[1].y, p[2].x, p[2].y, &r.ea[1], &r.eb[1], &r.ec[1]);
+                edge_eq(p[2].x, p[2].y, p[0].x, p[0].y, &r.ea[2], &r.eb[2], &r.ec[2]);
+                int x0, x1, y0, y1;
+                pixel_range(fminf(p[0].x, fminf(p[1].x, p[2].x)), fmaxf(p[0].x, fmaxf(p[1].x, p[2].x)), F.width, &x0, &x1);
+                pixel_range(fminf(p[0].y, fminf(p[1].y, p[2].y)), fmaxf(p[0].y, fmaxf(p[1].y, p[2].y)), F.height, &y0, &y1);
+                x0 = max(x0, sx0); x1 = min(x1, sx1); y0 = max(y0, sy0); y1 = min(y1, sy1);
+                if (x0 < x1 && y0 < y1) {
+                    r.bbx = (uint32_t)x0 | ((uint32_t)x1 << 16);
+                    r.bby = (uint32_t)y0 | ((uint32_t)y1 << 16);
+                }
+            }
+            recs[t] = r;
+        }
+        return;
+    }
+
+    // remaining CTAs zero the per-tile counters of this frame
+    const uint32_t zb = blockIdx.x - 1 - S.n_b2, nzb = gridDim.x - 1 - S.n_b2;
+    uint32_t* tc = Wk.tile_count + (size_t)f * Wk.tile_stride;
+    uint32_t* tf = Wk.tile_fill + (size_t)f * Wk.tile_stride;
+    for (uint32_t i = zb * blockDim.x + tid; i < tiles_per_frame; i += nzb * blockDim.x) { tc[i] = 0u; tf[i] = 0u; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_tri_setup : one CTA per chunk (<= 256 triangles of one batch), one thread per triangle
+// ---------------------------------------------------------------------------------------------
+struct TriLoad {
+    f4 vv[3];       // view space
+    float2 uv[3];
+    f3 nn[3];
+};
+
+__device__ __forceinline__ void load_tri(const SceneDev& S, const DBatch3& B, const float* view_model, uint32_t mode,
+                                         uint32_t tri, TriLoad* T) {
+    const uint32_t i0 = S.idx[(size_t)tri * 3 + 0], i1 = S.idx[(size_t)tri * 3 + 1], i2 = S.idx[(size_t)tri * 3 + 2];
+    const uint32_t ii[3] = {i0, i1, i2};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float4 p = __ldg(S.pos + ii[k]);
+        T->vv[k] = rx_matvec4(view_model, {p.x, p.y, p.z, p.w}, mode);  // batch3d.rs:557-560
+        T->uv[k] = __ldg(S.uv + ii[k]);
+        if (B.has_normals) T->nn[k] = {__ldg(S.nrm + (size_t)ii[k] * 3), __ldg(S.nrm + (size_t)ii[k] * 3 + 1), __ldg(S.nrm + (size_t)ii[k] * 3 + 2)};
+        else T->nn[k] = {0.0f, 0.0f, 0.0f};
+    }
+}
+
+__global__ void __launch_bounds__(RX_CHUNK_TRIS) k_tri_setup(SceneDev S, Workspace Wk) {
+    const uint32_t f = blockIdx.y;
+    const DFrame& F = Wk.frames[f];
+    const DChunk ch = S.chunks[blockIdx.x];
+    const DBatch3& B = S.b3[ch.batch];
+    DFrameBatch& FB = Wk.fb[(size_t)f * Wk.fb_stride + ch.batch];
+    const uint32_t tid = threadIdx.x;
+    uint32_t* chunk_total = Wk.chunk_new_total + (size_t)f * Wk.chunk_stride + blockIdx.x;
+
+    if (FB.rejected) {  // uniform for the CTA
+        if (tid == 0) *chunk_total = 0u;
+        // bins of a rejected batch must read as empty
+        if (tid < ch.n_tris) {
+            TriBin e = {0u, 0u, 0u, ch.batch};
+            Wk.bins[(size_t)f * Wk.bins_stride + ch.first_tri + tid] = e;
+        }
+        return;
+    }
+
+    MinMax mm; mm.init();
+    uint32_t n_new = 0;      // near-clip output triangles of this thread's triangle
+    bool vis = false;
+
+    if (tid < ch.n_tris) {
+        const uint32_t tri = ch.first_tri + tid;           // global original triangle index
+        const uint32_t local = tri - B.t_off;
+        const uint32_t slot = B.owner_base + local;
+        TriLoad T;
+        load_tri(S, B, FB.view_model, F.matvec_mode, tri, &T);
+
+        bool early_cull = false;  // batch3d.rs:592-600
+        if (B.cull_mode != RXC_CULL_OFF) {
+            float orient = (T.vv[1].x - T.vv[0].x) * (T.vv[2].y - T.vv[0].y) - (T.vv[1].y - T.vv[0].y) * (T.vv[2].x - T.vv[0].x);
+            bool is_front = orient > 0.0f;
+            early_cull = (B.cull_mode == RXC_CULL_BACK && is_front) || (B.cull_mode == RXC_CULL_FRONT && !is_front);
+        }
+        const bool in0 = T.vv[0].z < -RX_NEAR_PLANE, in1 = T.vv[1].z < -RX_NEAR_PLANE, in2 = T.vv[2].z < -RX_NEAR_PLANE;
+        const bool all_in = in0 && in1 && in2, all_out = !in0 && !in1 && !in2;
+        const bool edge_vis = early_cull || all_in;                // batch3d.rs:613-618
+        const bool mixed = !early_cull && !all_in && !all_out;
+
+        f4 P[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {                               // batch3d.rs:689-700
+            P[k] = rx_project(F.proj, T.vv[k], F.width_f, F.height_f, F.matvec_mode);
+            mm.add(P[k].x, P[k].y);
+        }
+        TriBin bin = {0u, 0u, slot, ch.batch};
+        const uint32_t meta = ch.batch | (FB.alpha_test << 31);
+        TriVis tv; TriShade tsh;
+        vis = make_tri(P, T.uv, T.nn, B.cull_mode, edge_vis, F.width, F.height, meta, &tv, &tsh, &bin.bbx, &bin.bby);
+        if (vis) {
+            Wk.vis[(size_t)f * Wk.slot_stride + slot] = tv;
+            Wk.shade[(size_t)f * Wk.slot_stride + slot] = tsh;
+        }
+        Wk.bins[(size_t)f * Wk.bins_stride + tri] = bin;
+
+        if (mixed) {
+            ClipVert poly[4];
+            const int nv = clip_polygon(T.vv, T.uv, T.nn, poly);
+            for (int k = 0; k < nv; ++k) {   // the appended vertices are part of projected_vertices (bbox)
+                f4 q = rx_project(F.proj, poly[k].p, F.width_f, F.height_f, F.matvec_mode);
+                mm.add(q.x, q.y);
+            }
+            n_new = nv >= 3 ? (uint32_t)(nv - 2) : 0u;
+        }
+    }
+
+    // vertices no triangle references still belong to projected_vertices (batch3d.rs:749-768)
+    if (blockIdx.x == B.chunk_first) {
+        for (uint32_t o = tid; o < B.n_orphans; o += blockDim.x) {
+            const float4 p = __ldg(S.pos + S.orphans[B.orphan_off + o]);
+            f4 vvv = rx_matvec4(FB.view_model, {p.x, p.y, p.z, p.w}, F.matvec_mode);
+            f4 q = rx_project(F.proj, vvv, F.width_f, F.height_f, F.matvec_mode);
+            mm.add(q.x, q.y);
+        }
+    }
+
+    // block exclusive scan of n_new in {0,1,2}: two ballots per warp + warp totals in shared memory
+    __shared__ uint32_t s_wtot[RX_CHUNK_TRIS / 32];
+    const uint32_t lane = tid & 31, warp = tid >> 5;
+    const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, n_new & 1u), b1 = __ballot_sync(0xFFFFFFFFu, n_new & 2u);
+    const uint32_t wprefix = __popc(b0 & lanemask_lt()) + 2u * __popc(b1 & lanemask_lt());
+    if (lane == 0) s_wtot[warp] = __popc(b0) + 2u * __popc(b1);
+    __syncthreads();
+    uint32_t base = 0, total = 0;
+    for (uint32_t w = 0; w < RX_CHUNK_TRIS / 32; ++w) { if (w < warp) base += s_wtot[w]; total += s_wtot[w]; }
+    if (tid == 0) *chunk_total = total;
+    if (n_new) {
+        const uint32_t k = atomicAdd(&Wk.counters[f].n_clip, 1u);
+        if (k < Wk.clip_stride) {
+            DClip c = {ch.first_tri + tid, blockIdx.x, base + wprefix, ch.batch};
+            Wk.clip[(size_t)f * Wk.clip_stride + k] = c;
+        } else {
+            atomicOr(&Wk.counters[f].overflow, 4u);
+        }
+    }
+    const uint32_t nvis = __popc(__ballot_sync(0xFFFFFFFFu, vis));
+    if (lane == 0 && nvis) atomicAdd(&Wk.counters[f].n_visible, nvis);
+
+    block_minmax_to_keys(mm, &FB.bb_minx, &FB.bb_maxx, &FB.bb_miny, &FB.bb_maxy);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_batch_finalize : one warp per (frame, batch)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_batch_finalize(SceneDev S, Workspace Wk) {
+    const uint32_t f = blockIdx.y;
+    const uint32_t b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31;
+    if (b >= S.n_b3) return;
+    const DFrame& F = Wk.frames[f];
+    const DBatch3& B = S.b3[b];
+    DFrameBatch& FB = Wk.fb[(size_t)f * Wk.fb_stride + b];
+    const uint32_t* tot = Wk.chunk_new_total + (size_t)f * Wk.chunk_stride + B.chunk_first;
+    uint32_t* basep = Wk.chunk_new_base + (size_t)f * Wk.chunk_stride + B.chunk_first;
+    uint32_t carry = 0;
+    for (uint32_t c0 = 0; c0 < B.n_chunks; c0 += 32) {
+        const uint32_t c = c0 + lane;
+        uint32_t v = (c < B.n_chunks) ? tot[c] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if ((int)lane >= o) incl += n;
+        }
+        if (c < B.n_chunks) basep[c] = carry + incl - v;
+        carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    if (lane == 0) {
+        FB.n_new_tris = carry;
+        if (!FB.rejected) {
+            // Rect{x: min_x, y: min_y, width: max_x - min_x, height: max_y - min_y} (batch3d.rs:762-767)
+            const float mnx = rx_key_float(FB.bb_minx), mxx = rx_key_float(FB.bb_maxx);
+            const float mny = rx_key_float(FB.bb_miny), mxy = rx_key_float(FB.bb_maxy);
+            int x0, x1, y0, y1;
+            scissor_1d(mnx, mxx - mnx, F.width, (int)F.tile_size, 0.0f, &x0, &x1);  // rasterizer.rs:978-983
+            scissor_1d(mny, mxy - mny, F.height, (int)F.tile_size, 0.0f, &y0, &y1);
+            FB.sc_x0 = x0; FB.sc_x1 = x1;
+            FB.sc_y0 = max(y0, F.band_y0); FB.sc_y1 = min(y1, F.band_y1);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_clip_emit : grid-stride over the compact list of near-clipped triangles
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_clip_emit(SceneDev S, Workspace Wk) {
+    const uint32_t f = blockIdx.y;
+    const DFrame& F = Wk.frames[f];
+    DCounters& C = Wk.counters[f];
+    const uint32_t n = min(C.n_clip, Wk.clip_stride);
+    const uint32_t new_cap = Wk.bins_stride - S.n_tris;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const DClip c = Wk.clip[(size_t)f * Wk.clip_stride + k];
+        const DBatch3& B = S.b3[c.batch];
+        const DFrameBatch& FB = Wk.fb[(size_t)f * Wk.fb_stride + c.batch];
+        TriLoad T;
+        load_tri(S, B, FB.view_model, F.matvec_mode, c.tri, &T);
+        ClipVert poly[4];
+        const int nv = clip_polygon(T.vv, T.uv, T.nn, poly);
+        f4 Q[4];
+        for (int i = 0; i < nv; ++i) Q[i] = rx_project(F.proj, poly[i].p, F.width_f, F.height_f, F.matvec_mode);
+        const uint32_t first = B.owner_base + B.n_tris + Wk.chunk_new_base[(size_t)f * Wk.chunk_stride + c.chunk] + c.local_off;
+        const uint32_t meta = c.batch | (FB.alpha_test << 31);
+        for (int j = 1; j + 1 < nv; ++j) {  // fan (c0, cj, cj+1): batch3d.rs:672-678
+            const f4 P[3] = {Q[0], Q[j], Q[j + 1]};
+            const float2 uv[3] = {{poly[0].u, poly[0].v}, {poly[j].u, poly[j].v}, {poly[j + 1].u, poly[j + 1].v}};
+            const f3 nn[3] = {poly[0].n, poly[j].n, poly[j + 1].n};
+            const uint32_t slot = first + (uint32_t)(j - 1);
+            TriBin bin = {0u, 0u, slot, c.batch};
+            TriVis tv; TriShade tsh;
+            if (make_tri(P, uv, nn, B.cull_mode, true, F.width, F.height, meta, &tv, &tsh, &bin.bbx, &bin.bby)) {
+                const uint32_t pos = atomicAdd(&C.n_new_slots, 1u);
+                if (pos < new_cap) {
+                    Wk.vis[(size_t)f * Wk.slot_stride + slot] = tv;
+                    Wk.shade[(size_t)f * Wk.slot_stride + slot] = tsh;
+                    Wk.bins[(size_t)f * Wk.bins_stride + S.n_tris + pos] = bin;
+                    atomicAdd(&C.n_visible, 1u);
+                } else {
+                    atomicOr(&C.overflow, 4u);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// binning
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool bin_tile_range(const DFrame& F, uint32_t bbx, uint32_t bby, int* tx0, int* tx1, int* ty0, int* ty1) {
+    const int x0 = bbx & 0xFFFF, x1 = bbx >> 16, y0 = bby & 0xFFFF, y1 = bby >> 16;
+    if (x0 >= x1 || y0 >= y1) return false;
+    *tx0 = x0 / RX_TILE_W; *tx1 = (x1 - 1) / RX_TILE_W;
+    *ty0 = (y0 - F.band_y0) / RX_TILE_H; *ty1 = (y1 - 1 - F.band_y0) / RX_TILE_H;
+    return true;
+}
+
+__global__ void __launch_bounds__(256) k_bin_count(SceneDev S, Workspace Wk) {
+    const uint32_t f = blockIdx.y;
+    const DFrame& F = Wk.frames[f];
+    DCounters& C = Wk.counters[f];
+    const uint32_t new_cap = Wk.bins_stride - S.n_tris;
+    const uint32_t total = S.n_tris + min(C.n_new_slots, new_cap);
+    TriBin* bins = Wk.bins + (size_t)f * Wk.bins_stride;
+    uint32_t* tc = Wk.tile_count + (size_t)f * Wk.tile_stride;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        TriBin b = bins[i];
+        int x0 = b.bbx & 0xFFFF, x1 = b.bbx >> 16, y0 = b.bby & 0xFFFF, y1 = b.bby >> 16;
+        if (x0 >= x1 || y0 >= y1) continue;
+        const DFrameBatch& FB = Wk.fb[(size_t)f * Wk.fb_stride + b.batch];
+        x0 = max(x0, FB.sc_x0); x1 = min(x1, FB.sc_x1); y0 = max(y0, FB.sc_y0); y1 = min(y1, FB.sc_y1);
+        if (x0 >= x1 || y0 >= y1) { bins[i].bbx = 0u; bins[i].bby = 0u; continue; }
+        b.bbx = (uint32_t)x0 | ((uint32_t)x1 << 16);
+        b.bby = (uint32_t)y0 | ((uint32_t)y1 << 16);
+        TriVis* tv = Wk.vis + (size_t)f * Wk.slot_stride + b.slot;
+        tv->bbx = b.bbx; tv->bby = b.bby;
+        int tx0, tx1, ty0, ty1;
+        bin_tile_range(F, b.bbx, b.bby, &tx0, &tx1, &ty0, &ty1);
+        const int nt = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
+        if (nt > RX_LARGE_TILES) {
+            const uint32_t k = atomicAdd(&C.n_large, 1u);
+            if (k < Wk.large_stride) Wk.large[(size_t)f * Wk.large_stride + k] = b.slot;
+            else atomicOr(&C.overflow, 2u);
+            b.batch |= 0x80000000u;
+        } else {
+            for (int ty = ty0; ty <= ty1; ++ty)
+                for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(&tc[ty * F.tiles_x + tx], 1u);
+        }
+        bins[i] = b;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_tile_alloc(Workspace Wk, uint32_t tiles_per_frame) {
+    const uint32_t f = blockIdx.y;
+    DCounters& C = Wk.counters[f];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= tiles_per_frame) return;
+    uint32_t* tc = Wk.tile_count + (size_t)f * Wk.tile_stride;
+    uint32_t* tb = Wk.tile_base + (size_t)f * Wk.tile_stride;
+    const uint32_t n = tc[i];
+    uint32_t base = 0;
+    if (n) {
+        base = atomicAdd(&C.list_cursor, n);
+        if (base + n > Wk.list_stride) { atomicOr(&C.overflow, 1u); tc[i] = 0u; base = 0; }
+    }
+    tb[i] = base;
+}
+
+__global__ void __launch_bounds__(256) k_bin_fill(SceneDev S, Workspace Wk) {
+    const uint32_t f = blockIdx.y;
+    const DFrame& F = Wk.frames[f];
+    DCounters& C = Wk.counters[f];
+    const uint32_t new_cap = Wk.bins_stride - S.n_tris;
+    const uint32_t total = S.n_tris + min(C.n_new_slots, new_cap);
+    const TriBin* bins = Wk.bins + (size_t)f * Wk.bins_stride;
+    const uint32_t* tc = Wk.tile_count + (size_t)f * Wk.tile_stride;
+    const uint32_t* tb = Wk.tile_base + (size_t)f * Wk.tile_stride;
+    uint32_t* tf = Wk.tile_fill + (size_t)f * Wk.tile_stride;
+    uint32_t* lists = Wk.lists + (size_t)f * Wk.list_stride;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const TriBin b = bins[i];
+        if (b.batch & 0x80000000u) continue;
+        int tx0, tx1, ty0, ty1;
+        if (!bin_tile_range(F, b.bbx, b.bby, &tx0, &tx1, &ty0, &ty1)) continue;
+        for (int ty = ty0; ty <= ty1; ++ty)
+            for (int tx = tx0; tx <= tx1; ++tx) {
+                const int t = ty * F.tiles_x + tx;
+                if (tc[t] == 0u) continue;  // list dropped on arena overflow
+                const uint32_t pos = atomicAdd(&tf[t], 1u);
+                lists[tb[t] + pos] = b.slot;
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_raster
+// ---------------------------------------------------------------------------------------------
+#define RX_STAGE 64   // triangle records staged in shared memory per step
+
+struct PixelState {
+    float best_z;
+    uint32_t best;       // owner slot
+    float alpha, beta;   // barycentrics of the owner at this pixel
+};
+
+// rasterizer.rs:1319-1404 + :1875-1951 for one fragment; returns RGBA8.
+__device__ uint32_t shade_fragment(const SceneDev& S, const DFrame& F, const DLight* __restrict__ lights, const DBatch3& B,
+                                   const DFrameBatch& FB, const TriShade& sh, float alpha, float beta, float gamma, float z,
+                                   float fpx, float fpy, float u, float v) {
+    // screen_to_world, rasterizer.rs:1707-1727
+    const float x_ndc = 2.0f * (fpx / F.width_f) - 1.0f;
+    const float y_ndc = 1.0f - 2.0f * (fpy / F.height_f);
+    f4 vs = rx_matvec4(F.inv_proj, {x_ndc, y_ndc, z, 1.0f}, F.matvec_mode);
+    vs = {vs.x / vs.w, vs.y / vs.w, vs.z / vs.w, vs.w / vs.w};
+    const f4 ws = rx_matvec4(F.inv_view, vs, F.matvec_mode);
+    const f3 world = {ws.x, ws.y, ws.z};
+    const f3 cam = {F.cam[0], F.cam[1], F.cam[2]};
+    const f3 view_dir = rx_normalize3(rx_sub3(cam, world));
+
+    f3 normal = {0.0f, 0.0f, 0.0f};
+    if (B.has_normals) {  // rasterizer.rs:1083-1099
+        const f3 n0 = {sh.n0x, sh.n0y, sh.n0z}, n1 = {sh.n1x, sh.n1y, sh.n1z}, n2 = {sh.n2x, sh.n2y, sh.n2z};
+        normal = rx_normalize3(rx_add3(rx_add3(rx_scale3(n0, alpha), rx_scale3(n1, beta)), rx_scale3(n2, gamma)));
+        if (rx_dot3(normal, view_dir) < 0.0f) normal = {-normal.x, -normal.y, -normal.z};
+    }
+
+    uint32_t texel;
+    if (FB.tex != 0xFFFFFFFFu) texel = rx_sample(S.arena, S.tex[FB.tex], u, v, F.sample_mode, B.repeat_mode);
+    else if (B.source_kind == RXC_SRC_PIXEL) texel = B.source_pixel;
+    else texel = 0xFF000000u;  // rasterizer.rs:1221
+
+    const float inv255 = 1.0f / 255.0f;
+    auto s2l = [](float x) { float x2 = x * x; return (0.6975f * x2 + 0.3025f) * x; };  // rasterizer.rs:20-25
+    const f3 base = {s2l((float)(texel & 0xFF) * inv255), s2l((float)((texel >> 8) & 0xFF) * inv255),
+                     s2l((float)((texel >> 16) & 0xFF) * inv255)};
+    const float opacity = (float)(texel >> 24) / 255.0f;
+
+    normal = rx_normalize3(normal);  // rasterizer.rs:1320
+    const float roughness = 0.5f, metallic = 0.0f;
+
+    f3 lit = {0.0f, 0.0f, 0.0f};
+    const float hemi = 0.5f * (normal.y + 1.0f);
+    const f3 kd = rx_scale3(rx_scale3(base, 1.0f - metallic), 1.0f - 0.04f);
+    if (F.has_ambient) {  // rasterizer.rs:1334-1365 (occlusion == 1.0: no occluded sectors)
+        const f3 sky = {F.ambient[0], F.ambient[1], F.ambient[2]};
+        lit = rx_add3(lit, rx_scale3(rx_mul3(sky, kd), hemi));
+        lit = rx_scale3(lit, 1.0f);
+    }
+    {  // rasterizer.rs:1368-1370
+        const f3 amb = {B.ambient[0], B.ambient[1], B.ambient[2]};
+        lit = rx_add3(lit, rx_scale3(rx_mul3(amb, kd), hemi));
+    }
+    for (uint32_t li = 0; li < S.n_lights; ++li) {  // rasterizer.rs:1373-1391
+        const DLight& L = lights[li];
+        f3 incoming;
+        if (!rx_light_color_at(L, world, false, &incoming)) continue;
+        const f3 lp = {L.px, L.py, L.pz};
+        const f3 ldir = rx_normalize3(rx_sub3(lp, world));
+        f3 radiance = incoming;
+        if (!(L.light_type == RXC_LIGHT_AMBIENT || L.light_type == RXC_LIGHT_AMBIENT_DAYLIGHT || L.light_type == RXC_LIGHT_DAYLIGHT)) {
+            const float lambert = fmaxf(rx_dot3(normal, ldir), 0.0f);  // light.rs:529-532
+            radiance = rx_scale3(incoming, lambert);
+        }
+        // shade_fast_brdf, rasterizer.rs:1912-1951 (emissive = 0)
+        const float n_dot_l = fmaxf(rx_dot3(normal, ldir), 0.0f);
+        if (n_dot_l <= 0.0f) continue;
+        const float t = rx_clamp(metallic, 0.0f, 1.0f);
+        const f3 f0 = {__fmaf_rn(t, base.x - 0.04f, 0.04f), __fmaf_rn(t, base.y - 0.04f, 0.04f), __fmaf_rn(t, base.z - 0.04f, 0.04f)};
+        f3 kdl = rx_scale3(base, 1.0f - metallic);
+        kdl = rx_scale3(kdl, 1.0f - fmaxf(f0.x, fmaxf(f0.y, f0.z)));
+        const float a = fmaxf(roughness * roughness, 1e-4f);
+        const float shininess = rx_clamp(2.0f / a - 2.0f, 1.0f, 2048.0f);
+        const f3 h = rx_normalize3(rx_add3(ldir, view_dir));
+        const float n_dot_h = fmaxf(rx_dot3(normal, h), 0.0f);
+        const float spec_b = (n_dot_h <= 0.0f) ? 0.0f : exp2f(shininess * log2f(n_dot_h));
+        const float n_dot_v = fmaxf(rx_dot3(normal, view_dir), 0.0f);
+        const float om = 1.0f - rx_clamp(n_dot_v, 0.0f, 1.0f);
+        const float x5 = om * om * om * om * om;
+        const f3 fr = {f0.x + (1.0f - f0.x) * x5, f0.y + (1.0f - f0.y) * x5, f0.z + (1.0f - f0.z) * x5};
+        const f3 diffuse = rx_scale3(kdl, n_dot_l);
+        const f3 specular = rx_scale3(rx_scale3(fr, spec_b), n_dot_l);
+        lit = rx_add3(lit, rx_mul3(rx_add3(diffuse, specular), radiance));
+    }
+    auto l2s = [](float x) { float s = sqrtf(x); return 1.055f * s - 0.055f * s * s; };  // rasterizer.rs:28-33
+    return rx_f32_to_u8_saturated(l2s(lit.x)) | (rx_f32_to_u8_saturated(l2s(lit.y)) << 8) |
+           (rx_f32_to_u8_saturated(l2s(lit.z)) << 16) | (rx_f32_to_u8_saturated(opacity) << 24);
+}
+
+// src/shader/vgradient.rs:11-14 and src/shader/grid.rs:36-108
+__device__ uint32_t shade_background(const DFrame& F, int px, int py) {
+    const float uvx = (float)px / F.width_f, uvy = (float)py / F.height_f;  // rasterizer.rs:296-302
+    if (F.bg_shader == RXC_BG_VGRAY_GRADIENT) {
+        const uint32_t i = rx_as_u8(rx_clamp(uvy * 128.0f, 0.0f, 128.0f));
+        return i | (i << 8) | (i << 16) | 0xFF000000u;
+    }
+    auto pix = [](float g) { uint32_t c = rx_f32_to_u8_saturated(g); return c | (c << 8) | (c << 16) | (rx_f32_to_u8_saturated(1.0f) << 24); };
+    const float gsz = F.grid_size, sdiv = F.grid_subdiv;
+    const float posx = uvx * F.width_f, posy = uvy * F.height_f;
+    const float orgx = F.width_f / 2.0f + F.grid_off[0], orgy = F.height_f / 2.0f + F.grid_off[1];
+    const float aox = roundf(orgx - 0.5f) + 0.5f, aoy = roundf(orgy - 0.5f) + 0.5f;
+    const float rpx = posx - aox, rpy = posy - aoy;
+    auto mul_dist = [](float delta, float value) { return fabsf(value - delta * roundf(value / delta)); };
+    const float dx = mul_dist(gsz, rpx), dy = mul_dist(gsz, rpy);
+    if (fminf(dx, dy) <= 1.0f * 0.5f) return pix(0.15f);
+    const float dfx = fabsf(rpx - gsz * floorf(rpx / gsz)), dfy = fabsf(rpy - gsz * floorf(rpy / gsz));
+    const float ssz = gsz / roundf(sdiv);
+    float sdx = mul_dist(ssz, dfx), sdy = mul_dist(ssz, dfy);
+    const float rcx = roundf(dx / ssz), rcy = roundf(dy / ssz);
+    const float extra = gsz - ssz * sdiv;
+    if (rcx == sdiv) sdx = sdx + extra;
+    if (rcy == sdiv) sdy = sdy + extra;
+    if (fminf(sdx, sdy) <= 1.0f * 0.5f) return pix(0.11f);
+    return pix(0.05f);
+}
+
+// one 2D triangle fragment: rasterizer.rs:655-895.  `color` is the tile buffer pixel (RGBA8).
+__device__ void shade_2d(const SceneDev& S, const DFrame& F, const DLight* __restrict__ lights, const Tri2D& T, const DBatch2& B,
+                         const DFrameBatch2& FB, int px, int py, float fpx, float fpy, uint32_t* color) {
+    // barycentric_weights_2d, rasterizer.rs:1731-1750
+    const float acx = T.cx - T.ax, acy = T.cy - T.ay, abx = T.bx - T.ax, aby = T.by - T.ay;
+    const float apx = fpx - T.ax, apy = fpy - T.ay, pcx = T.cx - fpx, pcy = T.cy - fpy, pbx = T.bx - fpx, pby = T.by - fpy;
+    const float area = acx * aby - acy * abx;
+    const float w0 = (pcx * pby - pcy * pbx) / area;
+    const float w1 = (acx * apy - acy * apx) / area;
+    const float w2 = 1.0f - w0 - w1;
+    const float u = T.u0 * w0 + T.u1 * w1 + T.u2 * w2;
+    const float v = T.v0 * w0 + T.v1 * w1 + T.v2 * w2;
+    // rasterizer.rs:664-670
+    const float gx = (float)px - F.width_f / 2.0f - (F.trans2d[0] - F.width_f / 2.0f);
+    const float gy = (float)py - F.height_f / 2.0f - (F.trans2d[1] - F.height_f / 2.0f);
+    const float wx = gx / F.scale2d, wy = gy / F.scale2d;
+
+    uint32_t texel = 0u;
+    if (FB.tex != 0xFFFFFFFFu) texel = rx_sample(S.arena, S.tex[FB.tex], u, v, F.sample_mode, B.repeat_mode);
+    else if (B.source_kind == RXC_SRC_PIXEL) texel = B.source_pixel;
+
+    if (FB.lit) {  // rasterizer.rs:799-873
+        float acc[3] = {0.0f, 0.0f, 0.0f};
+        if (F.has_ambient) { acc[0] += F.ambient[0] * 1.0f; acc[1] += F.ambient[1] * 1.0f; acc[2] += F.ambient[2] * 1.0f; }
+        for (uint32_t li = 0; li < S.n_lights; ++li) {
+            f3 lc;
+            if (!rx_light_color_at(lights[li], {wx, 0.0f, wy}, true, &lc)) continue;
+            acc[0] += lc.x; acc[1] += lc.y; acc[2] += lc.z;
+        }
+        uint32_t out = texel & 0xFF000000u;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float a = rx_clamp(acc[i], 0.0f, 1.0f);
+            const float t = (float)((texel >> (8 * i)) & 0xFF);
+            out |= rx_as_u8(rx_clamp((t / 255.0f) * a * 255.0f, 0.0f, 255.0f)) << (8 * i);
+        }
+        texel = out;
+    }
+    const uint32_t ta = texel >> 24;  // rasterizer.rs:876-895
+    if (ta == 255u) { *color = texel; return; }
+    const float src_alpha = (float)ta / 255.0f, dst_alpha = 1.0f - src_alpha;
+    uint32_t out = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float s = (float)((texel >> (8 * i)) & 0xFF), d = (float)((*color >> (8 * i)) & 0xFF);
+        out |= rx_as_u8((s * src_alpha) + (d * dst_alpha)) << (8 * i);
+    }
+    const uint32_t da = *color >> 24;
+    out |= (F.preserve_transparency ? max(da, ta) : 255u) << 24;
+    *color = out;
+}
+
+__global__ void __launch_bounds__(RX_TILE_THREADS) k_raster(SceneDev S, Workspace Wk, RasterOut out, uint32_t n_frames,
+                                                             uint32_t tiles_per_frame) {
+    __shared__ __align__(16) TriVis s_tri[RX_STAGE];
+    __shared__ uint32_t s_slot[RX_STAGE];
+    __shared__ uint32_t s_work;
+    __shared__ __align__(16) uint32_t s_color[RX_TILE_THREADS];
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // warp w covers an 8x4 pixel block; 2 blocks across, 4 down
+    const int bx = (int)(warp & 1) * 8, by = (int)(warp >> 1) * 4;
+    const int lx = (int)(lane & 7), ly = (int)(lane >> 3);
+    const uint32_t total = n_frames * tiles_per_frame;
+
+    for (;;) {
+        if (tid == 0) s_work = atomicAdd(Wk.raster_counter, 1u);
+        __syncthreads();
+        const uint32_t work = s_work;
+        __syncthreads();
+        if (work >= total) break;
+        const uint32_t f = work / tiles_per_frame, tile = work - f * tiles_per_frame;
+        const DFrame& F = Wk.frames[f];
+        const DCounters& C = Wk.counters[f];
+        const DLight* lights = Wk.lights + (size_t)f * Wk.lights_stride;
+        const TriVis* vis = Wk.vis + (size_t)f * Wk.slot_stride;
+        const TriShade* shade = Wk.shade + (size_t)f * Wk.slot_stride;
+        const DFrameBatch* fbs = Wk.fb + (size_t)f * Wk.fb_stride;
+
+        const int tx0 = (int)(tile % (uint32_t)F.tiles_x) * RX_TILE_W;
+        const int ty0 = F.band_y0 + (int)(tile / (uint32_t)F.tiles_x) * RX_TILE_H;
+        const int wx0 = tx0 + bx, wy0 = ty0 + by, wx1 = wx0 + 8, wy1 = wy0 + 4;
+        const int px = wx0 + lx, py = wy0 + ly;
+        const float fpx = (float)px + 0.5f, fpy = (float)py + 0.5f;  // rasterizer.rs:1022
+        const bool in_frame = px < F.width && py < F.band_y1;
+
+        PixelState ps = {1.0f, RX_OWNER_NONE, 0.0f, 0.0f};  // z_buffer starts at 1.0 (rasterizer.rs:287)
+
+        if (F.d3_active) {
+            const uint32_t n_large = min(C.n_large, Wk.large_stride);
+            const uint32_t n_list = Wk.tile_count[(size_t)f * Wk.tile_stride + tile];
+            const uint32_t* large = Wk.large + (size_t)f * Wk.large_stride;
+            const uint32_t* list = Wk.lists + (size_t)f * Wk.list_stride + Wk.tile_base[(size_t)f * Wk.tile_stride + tile];
+            for (int pass = 0; pass < 2; ++pass) {
+                const uint32_t* src = pass == 0 ? large : list;
+                const uint32_t n_src = pass == 0 ? n_large : n_list;
+                for (uint32_t base = 0; base < n_src; base += RX_STAGE) {
+                    const uint32_t n = min((uint32_t)RX_STAGE, n_src - base);
+                    __syncthreads();  // previous stage fully consumed
+                    if (tid < n) s_slot[tid] = src[base + tid];
+                    __syncthreads();
+                    {   // stage the records: 6 x 16 B each
+                        const float4* g = reinterpret_cast<const float4*>(vis);
+                        float4* s = reinterpret_cast<float4*>(s_tri);
+                        for (uint32_t i = tid; i < n * 6u; i += RX_TILE_THREADS) {
+                            const uint32_t r = i / 6u, q = i - r * 6u;
+                            s[i] = __ldg(g + (size_t)s_slot[r] * 6u + q);
+                        }
+                    }
+                    __syncthreads();
+                    for (uint32_t r = 0; r < n; ++r) {
+                        const TriVis& T = s_tri[r];
+                        const int x0 = T.bbx & 0xFFFF, x1 = T.bbx >> 16, y0 = T.bby & 0xFFFF, y1 = T.bby >> 16;
+                        if (x0 >= wx1 || x1 <= wx0 || y0 >= wy1 || y1 <= wy0) continue;  // warp-uniform
+                        if (px < x0 || px >= x1 || py < y0 || py >= y1) continue;
+                        // Edges::evaluate, edge.rs:28-36 (a NaN result passes)
+                        if ((T.ea[0] * fpx + T.eb[0] * fpy + T.ec[0]) < 0.0f) continue;
+                        if ((T.ea[1] * fpx + T.eb[1] * fpy + T.ec[1]) < 0.0f) continue;
+                        if ((T.ea[2] * fpx + T.eb[2] * fpy + T.ec[2]) < 0.0f) continue;
+                        // barycentric_weights_3d, rasterizer.rs:1754-1773
+                        const float apx = fpx - T.ax, apy = fpy - T.ay;
+                        const float pcx = T.cx - fpx, pcy = T.cy - fpy, pbx = T.bx - fpx, pby = T.by - fpy;
+                        const float alpha = (pcx * pby - pcy * pbx) / T.area;
+                        const float beta = (T.acx * apy - T.acy * apx) / T.area;
+                        const float gamma = 1.0f - alpha - beta;
+                        const float one_over_z = T.iz0 * alpha + T.iz1 * beta + T.iz2 * gamma;  // :1054-1056
+                        const float z = 1.0f / one_over_z;
+                        const uint32_t slot = s_slot[r];
+                        // sequential `z < zbuf` in submission order == lexicographic min of (z, ordinal)
+                        const bool pass_z = (z < ps.best_z) || (z == ps.best_z && ps.best != RX_OWNER_NONE && slot < ps.best);
+                        if (!pass_z) continue;
+                        if (T.meta & 0x80000000u) {  // alpha test: texel alpha must be 255 to write (:1408)
+                            const TriShade& sh = shade[slot];
+                            const float iu = sh.uw0 * alpha + sh.uw1 * beta + sh.uw2 * gamma;
+                            const float iv = sh.vw0 * alpha + sh.vw1 * beta + sh.vw2 * gamma;
+                            const float irw = sh.rw0 * alpha + sh.rw1 * beta + sh.rw2 * gamma;
+                            const uint32_t b = T.meta & 0x7FFFFFFFu;
+                            const uint32_t texel = rx_sample(S.arena, S.tex[fbs[b].tex], iu / irw, iv / irw, F.sample_mode, S.b3[b].repeat_mode);
+                            if ((texel >> 24) != 255u) continue;
+                        }
+                        ps.best_z = z; ps.best = slot; ps.alpha = alpha; ps.beta = beta;
+                    }
+                }
+            }
+        }
+
+        // resolve: deferred shade of the owner, miss pass (rasterizer.rs:409-461), or the 2D-only background
+        uint32_t color;
+        if (F.d3_active) {
+            if (ps.best != RX_OWNER_NONE) {
+                const TriVis& T = vis[ps.best];
+                const TriShade sh = shade[ps.best];
+                const uint32_t b = T.meta & 0x7FFFFFFFu;
+                const float alpha = ps.alpha, beta = ps.beta, gamma = 1.0f - alpha - beta;
+                const float iu = sh.uw0 * alpha + sh.uw1 * beta + sh.uw2 * gamma;  // rasterizer.rs:1062-1076
+                const float iv = sh.vw0 * alpha + sh.vw1 * beta + sh.vw2 * gamma;
+                const float irw = sh.rw0 * alpha + sh.rw1 * beta + sh.rw2 * gamma;
+                color = shade_fragment(S, F, lights, S.b3[b], fbs[b], sh, alpha, beta, gamma, ps.best_z, fpx, fpy, iu / irw, iv / irw);
+            } else {
+                color = 0xFF000000u;  // vec4_to_pixel((0,0,0,1))
+            }
+        } else {
+            color = F.has_bg_color ? F.bg_color : 0u;  // rasterizer.rs:277-282
+            if (!F.ignore_bg_shader && F.bg_shader != RXC_BG_NONE) color = shade_background(F, px, py);
+        }
+
+        if (F.d2_active) {  // rasterizer.rs:501-553: every 2D record in submission order
+            const Tri2D* recs = Wk.tri2d + (size_t)f * Wk.tri2d_stride;
+            for (uint32_t r = 0; r < S.n_rec2d; ++r) {
+                const Tri2D& T = recs[r];
+                const int x0 = T.bbx & 0xFFFF, x1 = T.bbx >> 16, y0 = T.bby & 0xFFFF, y1 = T.bby >> 16;
+                if (x0 >= wx1 || x1 <= wx0 || y0 >= wy1 || y1 <= wy0) continue;
+                if (px < x0 || px >= x1 || py < y0 || py >= y1) continue;
+                if ((T.ea[0] * fpx + T.eb[0] * fpy + T.ec[0]) < 0.0f) continue;
+                if ((T.ea[1] * fpx + T.eb[1] * fpy + T.ec[1]) < 0.0f) continue;
+                if ((T.ea[2] * fpx + T.eb[2] * fpy + T.ec[2]) < 0.0f) continue;
+                shade_2d(S, F, lights, T, S.b2[T.batch], Wk.fb2[(size_t)f * Wk.fb2_stride + T.batch], px, py, fpx, fpy, &color);
+            }
+        }
+
+        // write back: RGBA8 rows of the tile, 128-bit stores when rows are 16 B aligned
+        const int row = by + ly, col = bx + lx;
+        s_color[row * RX_TILE_W + col] = color;
+        if (in_frame) {
+            const size_t o = (size_t)(py - F.band_y0) * (size_t)F.width + (size_t)px;
+            if (out.owner) out.owner[o] = ps.best;
+            if (out.depth) out.depth[o] = ps.best_z;
+        }
+        __syncthreads();
+        uint8_t* frame_px = out.pixels + (size_t)f * out.frame_stride;
+        const bool full_tile = (tx0 + RX_TILE_W <= F.width) && (ty0 + RX_TILE_H <= F.band_y1);
+        if (out.vec_store && full_tile) {
+            if (tid < RX_TILE_THREADS / 4) {
+                const int r = (int)tid >> 2, c4 = (int)tid & 3;
+                const uint4 v = reinterpret_cast<const uint4*>(s_color)[tid];
+                uint4* dst = reinterpret_cast<uint4*>(frame_px + ((size_t)(ty0 - F.band_y0 + r) * (size_t)F.width + (size_t)tx0) * 4) + c4;
+                *dst = v;
+            }
+        } else if (in_frame) {
+            reinterpret_cast<uint32_t*>(frame_px)[(size_t)(py - F.band_y0) * (size_t)F.width + (size_t)px] = color;
+        }
+        // the next iteration's first __syncthreads orders s_color reuse
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// launch wrappers
+// ---------------------------------------------------------------------------------------------
+cudaError_t rxk_frame_setup(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, cudaStream_t st) {
+    const uint32_t zero_blocks = max(1u, min(64u, (tiles_per_frame + 255u) / 256u));
+    dim3 grid(1 + S.n_b2 + zero_blocks, n_frames);
+    k_frame_setup<<<grid, 256, 0, st>>>(S, W, tiles_per_frame);
+    return cudaGetLastError();
+}
+cudaError_t rxk_tri_setup(const SceneDev& S, const Workspace& W, uint32_t n_frames, cudaStream_t st) {
+    if (S.n_chunks == 0) return cudaSuccess;
+    dim3 grid(S.n_chunks, n_frames);
+    k_tri_setup<<<grid, RX_CHUNK_TRIS, 0, st>>>(S, W);
+    return cudaGetLastError();
+}
+cudaError_t rxk_batch_finalize(const SceneDev& S, const Workspace& W, uint32_t n_frames, cudaStream_t st) {
+    if (S.n_b3 == 0) return cudaSuccess;
+    dim3 grid((S.n_b3 + 7) / 8, n_frames);
+    k_batch_finalize<<<grid, 256, 0, st>>>(S, W);
+    return cudaGetLastError();
+}
+cudaError_t rxk_clip_emit(const SceneDev& S, const Workspace& W, uint32_t n_frames, int grid_x, cudaStream_t st) {
+    if (S.n_tris == 0) return cudaSuccess;
+    dim3 grid(grid_x, n_frames);
+    k_clip_emit<<<grid, 128, 0, st>>>(S, W);
+    return cudaGetLastError();
+}
+cudaError_t rxk_bin_count(const SceneDev& S, const Workspace& W, uint32_t n_frames, int grid_x, cudaStream_t st) {
+    if (S.n_tris == 0) return cudaSuccess;
+    dim3 grid(grid_x, n_frames);
+    k_bin_count<<<grid, 256, 0, st>>>(S, W);
+    return cudaGetLastError();
+}
+cudaError_t rxk_tile_alloc(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, cudaStream_t st) {
+    (void)S;
+    dim3 grid((tiles_per_frame + 255) / 256, n_frames);
+    k_tile_alloc<<<grid, 256, 0, st>>>(W, tiles_per_frame);
+    return cudaGetLastError();
+}
+cudaError_t rxk_bin_fill(const SceneDev& S, const Workspace& W, uint32_t n_frames, int grid_x, cudaStream_t st) {
+    if (S.n_tris == 0) return cudaSuccess;
+    dim3 grid(grid_x, n_frames);
+    k_bin_fill<<<grid, 256, 0, st>>>(S, W);
+    return cudaGetLastError();
+}
+cudaError_t rxk_raster(const SceneDev& S, const Workspace& W, const RasterOut& out, uint32_t n_frames, uint32_t tiles_per_frame,
+                       int grid_x, cudaStream_t st) {
+    k_raster<<<grid_x, RX_TILE_THREADS, 0, st>>>(S, W, out, n_frames, tiles_per_frame);
+    return cudaGetLastError();
+}
+int rxk_raster_blocks_per_sm() {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_raster, RX_TILE_THREADS, 0) != cudaSuccess || n < 1) n = 1;
+    return n;
+}

@@ -1,0 +1,85 @@
+// rx_kernels.cuh -- launch interface between the host API (rx_api.cu) and the kernels (rx_kernels.cu)
+#pragma once
+#include "rx_device.cuh"
+
+struct TriBin {           // 16 B per triangle: what the binning kernels stream
+    uint32_t bbx, bby;    // raw pixel bbox from setup; final (scissored) bbox after k_bin_count
+    uint32_t slot;        // owner id / record slot
+    uint32_t batch;       // 3D batch index | large<<31 (set by k_bin_count)
+};
+
+// Scene-resident device data (set by rxc_set_assets / rxc_set_scene)
+struct SceneDev {
+    const float4* pos;          // [V]   positions
+    const float2* uv;           // [V]
+    const float* nrm;           // [V*3] (unused entries for batches without normals)
+    const uint32_t* idx;        // [T*3] global vertex ids
+    const DBatch3* b3;
+    const DChunk* chunks;
+    const uint32_t* orphans;    // global vertex ids
+    const float2* pos2;         // 2D
+    const float2* uv2;
+    const uint32_t* idx2;
+    const DBatch2* b2;
+    const DLight* lights;       // scene lights (flicker factor not yet applied)
+    const DTex* tex;
+    const DTile* tiles;         // static tiles first, then dynamic tiles
+    const uint8_t* arena;
+    uint32_t n_b3, n_b2, n_chunks, n_lights;
+    uint32_t n_tris, n_verts;   // 3D totals
+    uint32_t n_rec2d;           // 2D records per frame
+    uint32_t n_static_tiles, n_dynamic_tiles;
+};
+
+// Per-frame workspace: every array holds `n_frames` slices of the given stride (in elements)
+struct Workspace {
+    DFrame* frames;
+    DFrameBatch* fb;        uint32_t fb_stride;
+    DFrameBatch2* fb2;      uint32_t fb2_stride;
+    DLight* lights;         uint32_t lights_stride;
+    DCounters* counters;
+    TriVis* vis;            uint32_t slot_stride;   // 3 * n_tris
+    TriShade* shade;
+    TriBin* bins;           uint32_t bins_stride;   // n_tris + new_cap
+    uint32_t* chunk_new_total;
+    uint32_t* chunk_new_base; uint32_t chunk_stride;
+    DClip* clip;            uint32_t clip_stride;
+    uint32_t* large;        uint32_t large_stride;
+    uint32_t* tile_count;
+    uint32_t* tile_base;
+    uint32_t* tile_fill;    uint32_t tile_stride;
+    uint32_t* lists;        uint32_t list_stride;
+    Tri2D* tri2d;           uint32_t tri2d_stride;
+    uint32_t* raster_counter;  // one work counter for the whole launch
+};
+
+struct RasterOut {
+    uint8_t* pixels;       // frame f at pixels + f*frame_stride
+    uint64_t frame_stride; // bytes
+    uint32_t* owner;       // optional, only for single-frame calls
+    float* depth;
+    uint32_t vec_store;    // rows are 16 B aligned -> 128-bit stores
+};
+
+enum {
+    RXK_FRAME_SETUP = 0,
+    RXK_TRI_SETUP = 1,
+    RXK_BATCH_FINALIZE = 2,
+    RXK_CLIP_EMIT = 3,
+    RXK_BIN_COUNT = 4,
+    RXK_TILE_ALLOC = 5,
+    RXK_BIN_FILL = 6,
+    RXK_RASTER = 7
+};
+
+// Each returns the cudaError_t of the launch.  `n_frames` frames are processed by one launch.
+cudaError_t rxk_frame_setup(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, cudaStream_t st);
+cudaError_t rxk_tri_setup(const SceneDev& S, const Workspace& W, uint32_t n_frames, cudaStream_t st);
+cudaError_t rxk_batch_finalize(const SceneDev& S, const Workspace& W, uint32_t n_frames, cudaStream_t st);
+cudaError_t rxk_clip_emit(const SceneDev& S, const Workspace& W, uint32_t n_frames, int grid, cudaStream_t st);
+cudaError_t rxk_bin_count(const SceneDev& S, const Workspace& W, uint32_t n_frames, int grid, cudaStream_t st);
+cudaError_t rxk_tile_alloc(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, cudaStream_t st);
+cudaError_t rxk_bin_fill(const SceneDev& S, const Workspace& W, uint32_t n_frames, int grid, cudaStream_t st);
+cudaError_t rxk_raster(const SceneDev& S, const Workspace& W, const RasterOut& out, uint32_t n_frames, uint32_t tiles_per_frame,
+                       int grid, cudaStream_t st);
+int rxk_raster_blocks_per_sm();

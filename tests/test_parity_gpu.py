@@ -1,0 +1,212 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs.  Run on the B200 box with `pytest -m gpu`."""
+import math
+
+import numpy as np
+import pytest
+
+from helpers import compare, render_gpu, render_oracle
+from rusterix_b200 import (Batch2D, Batch3D, CullMode, Light, LightType, MatVecMode, PixelSource, Rasterizer, RenderMode,
+                           RepeatMode, SampleMode, Scene, scenes)
+from rusterix_b200 import GridShader, VGrayGradientShader
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(cfg, frame=0, what=None, **kw):
+    r = cfg.rasterizer(frame)
+    for k, v in kw.items():
+        setattr(r, k, v)
+    g = render_gpu(r, cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size)
+    o = render_oracle(r, cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size)
+    return compare(g, o, what or cfg.name)
+
+
+def test_cube_800x600_nearest():
+    st = _run(scenes.cube(800, 600, 200, logo_size=256))
+    assert st["exact_frac"] > 0.99
+
+
+def test_cube_odd_size_partial_tiles():
+    _run(scenes.cube(333, 217, 40, logo_size=128))
+
+
+def test_cube_plain_rows_matvec():
+    _run(scenes.cube(400, 300, 60, logo_size=128), matvec_mode=MatVecMode.PlainRows)
+
+
+@pytest.mark.parametrize("frame", [0, 5, 17, 40])
+def test_teapot_linear_orbit(frame):
+    _run(scenes.teapot(960, 540, 60, logo_size=256), frame=frame)
+
+
+def test_map_nearest_alpha_fence():
+    st = _run(scenes.map_config(960, 540, 40, logo_size=256))
+    assert st["exact_frac"] > 0.99
+
+
+def test_map_full_4k_owner_and_depth():
+    cfg = scenes.map_config(3840, 2160, 40, logo_size=256)
+    _run(cfg)
+
+
+@pytest.mark.parametrize("i", [0, 100, 1024, 3000])
+def test_sweep_frames(i):
+    _run(scenes.sweep(640, 360, 40, logo_size=128), frame=i)
+
+
+def test_dense_small():
+    _run(scenes.dense(1280, 720, 40, patches=8))
+
+
+def test_near_clip_camera_inside_geometry():
+    """Camera close to a wall so triangles cross the z=-0.1 plane (SURVEY k4, T-clipvis)."""
+    cfg = scenes.map_config(640, 360, 40, logo_size=64)
+    cam = scenes._firstp([0.3, 1.0, 7.5], [5.0, 0.8, 7.7])
+    cfg.camera = cam
+    st = _run(cfg, what="near-clip")
+    cam = scenes._firstp([7.5, 0.05, 7.5], [9.0, 0.0, 9.0])
+    cfg.camera = cam
+    _run(cfg, what="near-clip-floor")
+
+
+@pytest.mark.parametrize("cull", [CullMode.Off, CullMode.Front, CullMode.Back])
+def test_cull_modes(cull):
+    cfg = scenes.cube(320, 240, 40, logo_size=64)
+    cfg.scene.d3_static[0].cull_mode(cull)
+    cfg.scene.mark_dirty()
+    _run(cfg, what=f"cull-{cull.name}")
+
+
+@pytest.mark.parametrize("repeat", list(RepeatMode))
+@pytest.mark.parametrize("sample", list(SampleMode))
+def test_repeat_and_sample_modes(repeat, sample):
+    cfg = scenes.teapot(320, 240, 60, logo_size=64)
+    cfg.scene.d3_static[0].repeat_mode(repeat)
+    cfg.scene.mark_dirty()
+    cfg.sample_mode = sample
+    _run(cfg, what=f"{repeat.name}-{sample.name}")
+
+
+def test_tile_size_invariance_and_scissor():
+    cfg = scenes.cube(400, 300, 200, logo_size=64)
+    r = cfg.rasterizer()
+    ref = None
+    for ts in (8, 40, 200, 1000):
+        g = render_gpu(r, cfg.scene, cfg.assets, cfg.width, cfg.height, ts)
+        o = render_oracle(r, cfg.scene, cfg.assets, cfg.width, cfg.height, ts)
+        compare(g, o, f"tile_size {ts}")
+        if ref is None:
+            ref = g
+        else:
+            assert np.array_equal(ref[0], g[0]) and np.array_equal(ref[1], g[1])
+
+
+def test_light_types():
+    cfg = scenes.map_config(480, 270, 40, logo_size=64)
+    L = []
+    L.append(Light.new(LightType.Point).with_position([9, 0.5, 12]).with_intensity(2).with_start_distance(2).with_end_distance(13).with_flicker(0.6).compile())
+    L.append(Light.new(LightType.Spot).with_position([4, 1.8, 8]).with_direction([0.2, -1.0, 0.5]).with_cone_angle(0.6).with_end_distance(9).compile())
+    L.append(Light.new(LightType.Area).with_position([7, 1.9, 11]).with_normal([0, -1, 0]).with_size(2, 2).with_end_distance(8).with_intensity(0.7).compile())
+    L.append(Light.new(LightType.Ambient).with_color([0.1, 0.05, 0.0]).compile())
+    L.append(Light.new(LightType.AmbientDaylight).with_color([0.0, 0.05, 0.1]).compile())
+    L.append(Light.new(LightType.Daylight).with_position([7, 6, 7]).with_normal([0, -1, 0]).with_end_distance(30).with_intensity(0.4).compile())
+    L.append(Light.new(LightType.Point).with_position([1, 1, 1]).with_emitting(False).compile())
+    cfg.scene.lights = L
+    cfg.scene.animation_frame = 12345
+    cfg.ambient = (0.2, 0.2, 0.25, 1.0)
+    _run(cfg, what="light types")
+
+
+def test_2d_only_backgrounds():
+    for bg in (VGrayGradientShader(), GridShader(), GridShader(grid_size=17.0, subdivisions=3.0, offset=(5.0, -3.0)), None):
+        cfg = scenes.cube(300, 200, 40, logo_size=64)
+        cfg.scene.background = bg
+        cfg.scene.d2_static = [Batch2D.from_rectangle(20.0, 30.0, 120.0, 90.0).source(PixelSource.StaticTileIndex(0)),
+                               Batch2D.from_rectangle(100.0, 60.0, 150.0, 100.0).source(PixelSource.Pixel([200, 40, 40, 128]))]
+        cfg.scene.mark_dirty()
+        r = cfg.rasterizer().render_mode(RenderMode.render_2d()).background([10, 20, 30, 255])
+        g = render_gpu(r, cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size, planes=False)
+        o = render_oracle(r, cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size, planes=False)
+        st = compare(g, o, f"2D bg {bg}", pixel_frac=1.0)
+        assert st["max_diff"] == 0
+
+
+def test_2d_matrix_lights_and_transparency():
+    cfg = scenes.cube(320, 200, 40, logo_size=64)
+    cfg.scene.d2_static = [Batch2D.from_rectangle(0.0, 0.0, 100.0, 60.0).source(PixelSource.StaticTileIndex(0)),
+                           Batch2D.from_rectangle(30.0, 20.0, 80.0, 50.0).source(PixelSource.Pixel([255, 255, 0, 90])).receives_light(False)]
+    cfg.scene.lights = [Light.new(LightType.Point).with_position([40, 0, 30]).with_start_distance(10).with_end_distance(90).with_intensity(1.3).compile()]
+    cfg.scene.mark_dirty()
+    m = np.array([[2.0, 0.0, 15.0], [0.0, 2.0, 9.0], [0.0, 0.0, 1.0]], dtype=np.float32)
+    for preserve in (False, True):
+        r = Rasterizer.setup(m, np.eye(4), np.eye(4)).render_mode(RenderMode.render_2d())
+        r.preserve_transparency = preserve
+        g = render_gpu(r, cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size, planes=False)
+        o = render_oracle(r, cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size, planes=False)
+        st = compare(g, o, "2D matrix+lights", pixel_frac=1.0)
+        assert st["max_diff"] <= 1
+
+
+def test_usize_indices_and_no_normals():
+    cfg = scenes.cube(320, 240, 40, logo_size=64)
+    cfg.scene.d3_static[0].normals = np.zeros((0, 3), dtype=np.float32)
+    cfg.scene.mark_dirty()
+    r = cfg.rasterizer()
+    r.index_bytes = 8
+    g = render_gpu(r, cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size)
+    o = render_oracle(r, cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size, index_bytes=8)
+    compare(g, o, "usize indices, no normals")
+
+
+def test_band_rendering_matches_full_frame():
+    cfg = scenes.map_config(640, 360, 40, logo_size=64)
+    r = cfg.rasterizer()
+    full = render_gpu(r, cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size)
+    for (y0, y1) in ((0, 96), (96, 200), (200, 360)):
+        band = render_gpu(r, cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size, band=(y0, y1))
+        assert np.array_equal(band[0], full[0][y0:y1])
+        assert np.array_equal(band[1], full[1][y0:y1])
+
+
+def test_batch_api_matches_single_frames():
+    cfg = scenes.sweep(320, 192, 40, n_frames=64, logo_size=64)
+    frames = [0, 7, 31, 50]
+    rs = [cfg.rasterizer(i) for i in frames]
+    out = np.zeros((len(frames), cfg.height, cfg.width, 4), dtype=np.uint8)
+    Rasterizer.rasterize_batch(rs, cfg.scene, out, cfg.width, cfg.height, cfg.tile_size, cfg.assets)
+    for k, r in enumerate(rs):
+        single = render_gpu(r, cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size, planes=False)
+        assert np.array_equal(out[k], single[0])
+
+
+def test_device_output_tensor():
+    import torch
+
+    cfg = scenes.cube(320, 240, 40, logo_size=64)
+    r = cfg.rasterizer()
+    t = torch.zeros((cfg.height, cfg.width, 4), dtype=torch.uint8, device="cuda:0")
+    r.rasterize(cfg.scene, t, cfg.width, cfg.height, cfg.tile_size, cfg.assets)
+    host = render_gpu(r, cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size, planes=False)
+    assert np.array_equal(t.cpu().numpy(), host[0])
+
+
+def test_errors_do_not_unwind():
+    from rusterix_b200 import RxcError
+
+    cfg = scenes.cube(64, 64, 40, logo_size=16)
+    cfg.scene.d3_static[0].source(PixelSource.StaticTileIndex(7))
+    cfg.scene.mark_dirty()
+    with pytest.raises(RxcError) as e:
+        render_gpu(cfg.rasterizer(), cfg.scene, cfg.assets, 64, 64, 40)
+    assert e.value.status == -5
+    cfg.scene.d3_static[0].source(PixelSource.StaticTileIndex(0)).shader(0)
+    cfg.scene.mark_dirty()
+    with pytest.raises(RxcError) as e:
+        render_gpu(cfg.rasterizer(), cfg.scene, cfg.assets, 64, 64, 40)
+    assert e.value.status == -3
+    cfg.scene.d3_static[0].shader_ = None
+    cfg.scene.mark_dirty()
+    with pytest.raises(ValueError):  # the reference panics on a short slice (src/rasterizer.rs:572)
+        cfg.rasterizer().rasterize(cfg.scene, np.zeros(10, np.uint8), 64, 64, 40, cfg.assets)
+    render_gpu(cfg.rasterizer(), cfg.scene, cfg.assets, 64, 64, 40)  # the context is still usable
