@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the rasterize() hot path on N B200s (driver contract in the task brief).
+
+A step = one pass of the path over one batch of synthetic input: `--frames` (default 8) camera
+positions of the workload scene rendered by one launch sequence (`rxc_rasterize_batch`), each frame a
+full `Rasterizer::setup(..).rasterize(..)` (projection, clipping, binning, raster, shading, 2D pass).
+Default workload: BASELINE.json's textured map scene at 3840x2160 (the config its target is quoted on).
+
+  value     whole-job Mpixel/s with the scene resident in HBM and frames written to device memory
+  e2e       same metric through the public API with pinned HOST pixel buffers (D2H inside the timing)
+  roofline  k_raster: algorithmic bytes / CUDA-event time of that kernel, against MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle (a port of the reference algorithm) on this box's host cores
+
+`--impl reference` times only the CPU port on the same workload (rank 0 only).
+Multi-GPU: frames are sharded across ranks (one process per GPU, torchrun), no data-path collective;
+the NCCL gather of the frames to rank 0 is timed separately and reported under "gather".
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (builder, kwargs, description)
+    "map4k": ("sweep", dict(width=3840, height=2160, tile_size=40), "minigame map scene (walls/floor/fence/sky, 1 point light, logo rect), 3840x2160, Nearest, tile 40"),
+    "teapot1080": ("teapot", dict(width=1920, height=1080, tile_size=60), "teapot-like lathe mesh 2256 tris, 1920x1080, Linear, tile 60, orbit sweep"),
+    "sweep1080": ("sweep", dict(width=1920, height=1080, tile_size=40), "camera sweep of the map scene, 1920x1080, Nearest, tile 40"),
+    "dense8k": ("dense", dict(width=7680, height=4320, tile_size=40), "991,232-triangle heightfield in 1024 batches, 7 lights, 7680x4320, Linear"),
+    "cube800": ("cube", dict(width=800, height=600, tile_size=200), "textured cube, 800x600, Nearest, tile 200"),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            p = [x.strip() for x in l.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if p[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(name, frames_per_step, rank, world):
+    from rusterix_b200 import scenes
+
+    builder, kw, desc = WORKLOADS[name]
+    cfg = scenes.BUILDERS[builder](**kw)
+    # rank r renders frames r, r+world, ... of the camera path (frame sharding)
+    n_path = max(cfg.n_frames, 1)
+    if cfg.cameras is not None:
+        stride = max(1, n_path // (frames_per_step * world)) if n_path >= frames_per_step * world else 1
+        frame_ids = [((rank + i * world) * stride) % n_path for i in range(frames_per_step)]
+    else:
+        frame_ids = [0] * frames_per_step
+    return cfg, frame_ids, desc
+
+
+def cpu_port_time(cfg, frame_ids, budget_s=20.0, max_frames=10, warm=1):
+    """Times the oracle (CPU port of the reference algorithm, all host threads) on whole frames of the
+    same workload.  Returns (Mpixel/s, cores, sample description, seconds per frame)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_ffi
+
+    lib = oracle_ffi.load()
+    cores = int(lib.rxo_hardware_threads())
+    times = []
+    t_start = time.time()
+    k = 0
+    while True:
+        r = cfg.rasterizer(frame_ids[k % len(frame_ids)])
+        t0 = time.perf_counter()
+        oracle_ffi.rasterize(r, cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size, want_planes=False, n_threads=0)
+        dt = time.perf_counter() - t0
+        if k >= warm:
+            times.append(dt)
+        k += 1
+        if len(times) >= max_frames or (time.time() - t_start > budget_s and len(times) >= 1):
+            break
+    med = statistics.median(times)
+    mpix = cfg.width * cfg.height / med / 1e6
+    return mpix, cores, f"{len(times)} whole frames of the workload after {warm} warm-up, median", med
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cfg, frame_ids, desc = build_workload(args.workload, args.frames, 0, 1)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_ffi
+
+    lib = oracle_ffi.load()
+    cores = int(lib.rxo_hardware_threads())
+    # a step of the reference arm = ONE frame of the workload (bounded sample of the GPU arm's step)
+    def step(i):
+        r = cfg.rasterizer(frame_ids[i % len(frame_ids)])
+        oracle_ffi.rasterize(r, cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size, want_planes=False, n_threads=0)
+
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i)
+    dt = time.perf_counter() - t0
+    ms = dt / args.steps * 1e3
+    val = cfg.width * cfg.height * args.steps / dt / 1e6
+    line = {
+        "impl": "reference", "metric": "Mpixels/s shaded", "value": val, "unit": "Mpixel/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "frames_per_s": args.steps / dt,
+        "config": {"workload": desc, "step": "1 frame (bounded sample of the GPU arm's multi-frame step)",
+                   "note": "the Rust reference cannot be built in this image (no cargo); this is the C++ port of its algorithm (oracle/rx_oracle.cpp), all host threads"},
+        "cpu_baseline": {"value": val, "unit": "Mpixel/s", "cores": cores, "kind": "port", "sample": f"{args.steps} frames, 1 per step"},
+        "e2e": {"value": val, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="map4k", choices=list(WORKLOADS))
+    ap.add_argument("--frames", type=int, default=8, help="frames per step (camera batch)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads and the CPU baseline")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from rusterix_b200 import DeviceContext, Rasterizer
+    from rusterix_b200._abi import RXC_N_KERNELS
+
+    cfg, frame_ids, desc = build_workload(args.workload, args.frames, rank, world)
+    F = len(frame_ids)
+    W, H = cfg.width, cfg.height
+    frame_bytes = W * H * 4
+    rasts = [cfg.rasterizer(i).on_device(local_rank) for i in frame_ids]
+    ctx = DeviceContext.get(local_rank)
+    # a dedicated (non-default) torch stream: the kernels, the L2 flush and the torch.cuda.Events
+    # all live on it, so the events bracket exactly the launches of a step
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    ctx.set_stream(stream.cuda_stream)
+
+    out_dev = torch.empty((F, H, W, 4), dtype=torch.uint8, device=dev)
+    out_host = torch.empty((F, H, W, 4), dtype=torch.uint8, pin_memory=True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    batch = Rasterizer.prepare_batch(rasts, cfg.scene, W, H, cfg.tile_size, cfg.assets, device=local_rank)
+
+    def step_device():
+        batch.run(out_dev, sync=False)
+
+    def step_e2e():
+        batch.run(out_host, sync=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps, warmup):
+        for _ in range(warmup):
+            step_fn()
+            flush.zero_()
+        barrier()
+        e0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        e1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        wall0 = time.perf_counter()
+        for i in range(steps):
+            e0[i].record()
+            step_fn()
+            e1[i].record()
+            flush.zero_()  # evict the frames and the scene from L2 between timed steps (not timed)
+        barrier()
+        wall = time.perf_counter() - wall0
+        ms = sum(a.elapsed_time(b) for a, b in zip(e0, e1))
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, wall
+
+    # ---- device-resident throughput (the headline `value`)
+    sampler = ClockSampler(local_rank)
+    ctx.synchronize()
+    step_device(); ctx.synchronize()   # first call uploads the scene / sizes the workspace
+    ctx.reset_stats()
+    if rank == 0:
+        sampler.start()
+    # warm-up is inside timed(); stats are reset after it by measuring launches per step separately
+    ms_total, _ = timed(step_device, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    st = ctx.stats()
+    launches_per_step = st.kernel_launches // (args.steps + args.warmup)
+    gpu_launches = launches_per_step * args.steps
+    ms_per_step = ms_total / args.steps
+    pixels_per_step = F * W * H * world
+    value = pixels_per_step / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end to end through the public API with host pixel buffers
+    e2e_steps = max(3, min(args.steps, 10))
+    ctx.reset_stats()
+    ms_e2e, wall_e2e = timed(step_e2e, e2e_steps, 3)
+    st2 = ctx.stats()
+    # synchronous API: host wall-clock is the honest end-to-end time (device events miss host staging)
+    e2e_ms_step = max(ms_e2e, wall_e2e * 1e3) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_ms_step], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms_step = float(t.item())
+    e2e_value = pixels_per_step / (e2e_ms_step * 1e-3) / 1e6
+    h2d_step = st2.h2d_bytes // (e2e_steps + 3)
+    d2h_step = st2.d2h_bytes // (e2e_steps + 3)
+
+    # ---- per-kernel device times (CUDA events on the launching stream) for the roofline
+    ctx.set_profiling(True)
+    ctx.reset_stats()
+    prof_steps = 5
+    for _ in range(prof_steps):
+        step_device()
+        flush.zero_()
+    ctx.synchronize()
+    stp = ctx.stats()
+    ctx.set_profiling(False)
+    names = ctx.kernel_names()
+    kernel_ms = {names[i]: (stp.kernel_ms[i] / max(1, stp.launches[i])) for i in range(RXC_N_KERNELS) if stp.launches[i]}
+    step_kernel_ms = sum(stp.kernel_ms[i] for i in range(RXC_N_KERNELS)) / prof_steps
+    raster_ms = kernel_ms.get("k_raster", float("nan"))
+    peak, peak_src = load_peaks()
+    # algorithmic bytes of one k_raster launch: F frames written once + scene/textures/lights read once
+    b_alg_frame = cfg.algorithmic_bytes()
+    b_alg_launch = F * frame_bytes + (b_alg_frame - frame_bytes)
+    achieved = b_alg_launch / (raster_ms * 1e-3) / 1e9
+    traffic = None
+    ncu_json = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    if os.path.exists(ncu_json):
+        try:
+            traffic = json.load(open(ncu_json)).get(args.workload, {}).get("k_raster_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_raster", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": b_alg_launch,
+                "kernel_ms_per_launch": raster_ms, "kernel_share_of_step": stp.kernel_ms[7] / prof_steps / step_kernel_ms if step_kernel_ms else None,
+                "all_kernels_ms_per_launch": kernel_ms,
+                "note": "shading is SM-issue bound (about 10^2 fp32 ops per pixel per light, no FMA contraction); see DESIGN.md"}
+
+    # ---- optional NCCL gather of the step's frames to rank 0 (timed separately, not part of value)
+    gather = None
+    if world > 1:
+        from rusterix_b200 import mgpu
+
+        for _ in range(2):
+            mgpu.gather_frames_to_rank0(out_dev, rank, world)
+        barrier()
+        g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
+        g0.record()
+        mgpu.gather_frames_to_rank0(out_dev, rank, world)
+        g1.record()
+        barrier()
+        t = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gather = {"ms_per_step": float(t.item()), "bytes_to_rank0": (world - 1) * F * frame_bytes}
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": "Mpixels/s shaded", "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "frames_per_s": F * world / (ms_per_step * 1e-3),
+            "config": {"workload": desc, "frames_per_step_per_gpu": F, "width": W, "height": H, "triangles": cfg.counts()[1],
+                       "sharding": "frames sharded across ranks, no data-path collective" if world > 1 else "single GPU",
+                       "l2": "256 MiB flush between timed steps; each step also writes %.0f MB of frames (> 126 MB L2)" % (F * frame_bytes / 1e6),
+                       "timing": "CUDA events per step on the launching stream, summed over steps, max over ranks"},
+            "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step),
+                    "ms_per_step": e2e_ms_step, "steps": e2e_steps, "api": "Rasterizer.rasterize_batch -> rxc_rasterize_batch, pinned host pixels"},
+            "gpu_launches": int(gpu_launches), "launches_per_step": int(launches_per_step),
+            "roofline": roofline, "clocks": clocks,
+        }
+        if gather:
+            line["gather"] = gather
+
+    # ---- CPU baseline and secondary workloads: rank 0, N=1 only
+    if rank == 0 and world == 1 and not args.no_extras:
+        mpix, cores, sample, spf = cpu_port_time(cfg, frame_ids)
+        line["cpu_baseline"] = {"value": mpix, "unit": "Mpixel/s", "cores": cores, "kind": "port", "sample": sample, "s_per_frame": spf}
+        also = {}
+        for wname in ("teapot1080", "dense8k", "sweep1080"):
+            if wname == args.workload:
+                continue
+            try:
+                also[wname] = secondary(wname, local_rank, dev, flush)
+            except Exception as e:  # a secondary workload never hides the headline
+                also[wname] = {"error": repr(e)}
+        line["also"] = also
+    elif rank == 0:
+        line["cpu_baseline"] = None
+
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def secondary(wname, local_rank, dev, flush, steps=5, warmup=3):
+    """Device-resident Mpixel/s of another BASELINE.json config (not a headline; same timing rules)."""
+    import torch
+    from rusterix_b200 import DeviceContext, Rasterizer
+
+    F = 1 if wname == "dense8k" else 8
+    cfg, frame_ids, desc = build_workload(wname, F, 0, 1)
+    rasts = [cfg.rasterizer(i).on_device(local_rank) for i in frame_ids]
+    out = torch.empty((F, cfg.height, cfg.width, 4), dtype=torch.uint8, device=dev)
+    ctx = DeviceContext.get(local_rank)
+
+    batch = Rasterizer.prepare_batch(rasts, cfg.scene, cfg.width, cfg.height, cfg.tile_size, cfg.assets, device=local_rank)
+
+    def step():
+        batch.run(out, sync=False)
+
+    for _ in range(warmup):
+        step(); flush.zero_()
+    torch.cuda.synchronize()
+    ms = 0.0
+    for _ in range(steps):
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record(); step(); b.record(); flush.zero_()
+        torch.cuda.synchronize()
+        ms += a.elapsed_time(b)
+    ms /= steps
+    ctx.set_profiling(True); ctx.reset_stats()
+    step(); ctx.synchronize()
+    s = ctx.stats(); ctx.set_profiling(False)
+    names = ctx.kernel_names()
+    return {"workload": desc, "frames_per_step": F, "ms_per_step": ms, "Mpixel_per_s": F * cfg.width * cfg.height / (ms * 1e-3) / 1e6,
+            "frames_per_s": F / (ms * 1e-3), "triangles": cfg.counts()[1],
+            "kernel_ms": {names[i]: s.kernel_ms[i] for i in range(len(names)) if s.launches[i]},
+            "binned_refs": int(s.last_binned_refs), "large_tris": int(s.last_large_tris), "visible_tris": int(s.last_visible_tris)}
+
+
+if __name__ == "__main__":
+    main()

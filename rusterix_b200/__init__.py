@@ -5,11 +5,11 @@ from .types import (Assets, Batch2D, Batch3D, CompiledLight, CullMode, GridShade
                     PixelSource, PrimitiveMode, RenderMode, RepeatMode, SampleMode, Scene, Texture, Tile,
                     VGrayGradientShader)
 from .camera import D3FirstPCamera, D3IsoCamera, D3OrbitCamera
-from .rasterizer import DeviceContext, Rasterizer
+from .rasterizer import DeviceContext, FrameBatch, Rasterizer
 from ._lib import RxcError
 
 __all__ = [
     "Assets", "Batch2D", "Batch3D", "CompiledLight", "CullMode", "GridShader", "Light", "LightType", "MatVecMode",
     "PixelSource", "PrimitiveMode", "RenderMode", "RepeatMode", "SampleMode", "Scene", "Texture", "Tile",
-    "VGrayGradientShader", "D3FirstPCamera", "D3IsoCamera", "D3OrbitCamera", "DeviceContext", "Rasterizer", "RxcError",
+    "VGrayGradientShader", "D3FirstPCamera", "D3IsoCamera", "D3OrbitCamera", "DeviceContext", "FrameBatch", "Rasterizer", "RxcError",
 ]

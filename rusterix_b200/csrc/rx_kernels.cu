@@ -797,10 +797,68 @@ __device__ void shade_2d(const SceneDev& S, const DFrame& F, const DLight* __res
     *color = out;
 }
 
+// Conservative tile-vs-triangle overlap: bbox, then for each edge the tile corner where the edge
+// function is largest.  The per-pixel test is `fl(a*px + b*py + c) < 0 -> outside` (edge.rs:28-36);
+// its rounding error is below 3 * 2^-24 * (|a|*X + |b|*Y + |c|), so a corner value below
+// -2e-6 * (|a|*X + |b|*Y + |c|) proves every pixel centre of the tile fails.  NaNs keep the triangle.
+__device__ __forceinline__ bool tile_overlaps(const TriVis& T, int tx0, int ty0, int tx1, int ty1) {
+    const int x0 = T.bbx & 0xFFFF, x1 = T.bbx >> 16, y0 = T.bby & 0xFFFF, y1 = T.bby >> 16;
+    if (x0 >= tx1 || x1 <= tx0 || y0 >= ty1 || y1 <= ty0) return false;
+    const float xmin = (float)max(tx0, x0) + 0.5f, xmax = (float)min(tx1, x1) - 0.5f;
+    const float ymin = (float)max(ty0, y0) + 0.5f, ymax = (float)min(ty1, y1) - 0.5f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float a = T.ea[i], b = T.eb[i], c = T.ec[i];
+        const float e = a * (a >= 0.0f ? xmax : xmin) + b * (b >= 0.0f ? ymax : ymin) + c;
+        const float m = (fabsf(a) * xmax + fabsf(b) * ymax + fabsf(c)) * 2e-6f;
+        if (e < -m) return false;
+    }
+    return true;
+}
+
+// coverage + depth + alpha test of one triangle at this thread's pixel (rasterizer.rs:1020-1060, :1408)
+__device__ __forceinline__ void test_fragment(const SceneDev& S, const DFrame& F, const DFrameBatch* __restrict__ fbs,
+                                              const TriShade* __restrict__ shade, const TriVis& T, uint32_t slot, int px, int py,
+                                              float fpx, float fpy, PixelState& ps) {
+    const int x0 = T.bbx & 0xFFFF, x1 = T.bbx >> 16, y0 = T.bby & 0xFFFF, y1 = T.bby >> 16;
+    if (px < x0 || px >= x1 || py < y0 || py >= y1) return;
+    // Edges::evaluate, edge.rs:28-36 (a NaN result passes)
+    if ((T.ea[0] * fpx + T.eb[0] * fpy + T.ec[0]) < 0.0f) return;
+    if ((T.ea[1] * fpx + T.eb[1] * fpy + T.ec[1]) < 0.0f) return;
+    if ((T.ea[2] * fpx + T.eb[2] * fpy + T.ec[2]) < 0.0f) return;
+    // barycentric_weights_3d, rasterizer.rs:1754-1773
+    const float apx = fpx - T.ax, apy = fpy - T.ay;
+    const float pcx = T.cx - fpx, pcy = T.cy - fpy, pbx = T.bx - fpx, pby = T.by - fpy;
+    const float alpha = (pcx * pby - pcy * pbx) / T.area;
+    const float beta = (T.acx * apy - T.acy * apx) / T.area;
+    const float gamma = 1.0f - alpha - beta;
+    const float one_over_z = T.iz0 * alpha + T.iz1 * beta + T.iz2 * gamma;  // :1054-1056
+    const float z = 1.0f / one_over_z;
+    // sequential `z < zbuf` in submission order == lexicographic min of (z, ordinal)
+    const bool pass_z = (z < ps.best_z) || (z == ps.best_z && ps.best != RX_OWNER_NONE && slot < ps.best);
+    if (!pass_z) return;
+    if (T.meta & 0x80000000u) {  // alpha test: texel alpha must be 255 to write (:1408)
+        const TriShade& sh = shade[slot];
+        const float iu = sh.uw0 * alpha + sh.uw1 * beta + sh.uw2 * gamma;
+        const float iv = sh.vw0 * alpha + sh.vw1 * beta + sh.vw2 * gamma;
+        const float irw = sh.rw0 * alpha + sh.rw1 * beta + sh.rw2 * gamma;
+        const uint32_t b = T.meta & 0x7FFFFFFFu;
+        const uint32_t texel = rx_sample(S.arena, S.tex[fbs[b].tex], iu / irw, iv / irw, F.sample_mode, S.b3[b].repeat_mode);
+        if ((texel >> 24) != 255u) return;
+    }
+    ps.best_z = z; ps.best = slot; ps.alpha = alpha; ps.beta = beta;
+}
+
+#define RX_LARGE_CACHE 160   // large-triangle records kept in shared memory across the tiles of a frame
+
 __global__ void __launch_bounds__(RX_TILE_THREADS) k_raster(SceneDev S, Workspace Wk, RasterOut out, uint32_t n_frames,
                                                              uint32_t tiles_per_frame) {
+    __shared__ __align__(16) TriVis s_large[RX_LARGE_CACHE];
+    __shared__ uint32_t s_large_slot[RX_LARGE_CACHE];
     __shared__ __align__(16) TriVis s_tri[RX_STAGE];
     __shared__ uint32_t s_slot[RX_STAGE];
+    __shared__ uint16_t s_sel[RX_LARGE_CACHE > RX_STAGE ? RX_LARGE_CACHE : RX_STAGE];
+    __shared__ uint32_t s_nsel;
     __shared__ uint32_t s_work;
     __shared__ __align__(16) uint32_t s_color[RX_TILE_THREADS];
 
@@ -809,12 +867,12 @@ __global__ void __launch_bounds__(RX_TILE_THREADS) k_raster(SceneDev S, Workspac
     const int bx = (int)(warp & 1) * 8, by = (int)(warp >> 1) * 4;
     const int lx = (int)(lane & 7), ly = (int)(lane >> 3);
     const uint32_t total = n_frames * tiles_per_frame;
+    uint32_t cached_frame = 0xFFFFFFFFu, n_cached = 0;
 
     for (;;) {
-        if (tid == 0) s_work = atomicAdd(Wk.raster_counter, 1u);
+        if (tid == 0) { s_work = atomicAdd(Wk.raster_counter, 1u); s_nsel = 0u; }
         __syncthreads();
         const uint32_t work = s_work;
-        __syncthreads();
         if (work >= total) break;
         const uint32_t f = work / tiles_per_frame, tile = work - f * tiles_per_frame;
         const DFrame& F = Wk.frames[f];
@@ -826,6 +884,7 @@ __global__ void __launch_bounds__(RX_TILE_THREADS) k_raster(SceneDev S, Workspac
 
         const int tx0 = (int)(tile % (uint32_t)F.tiles_x) * RX_TILE_W;
         const int ty0 = F.band_y0 + (int)(tile / (uint32_t)F.tiles_x) * RX_TILE_H;
+        const int tx1 = min(tx0 + RX_TILE_W, F.width), ty1 = min(ty0 + RX_TILE_H, F.band_y1);
         const int wx0 = tx0 + bx, wy0 = ty0 + by, wx1 = wx0 + 8, wy1 = wy0 + 4;
         const int px = wx0 + lx, py = wy0 + ly;
         const float fpx = (float)px + 0.5f, fpy = (float)py + 0.5f;  // rasterizer.rs:1022
@@ -835,16 +894,44 @@ __global__ void __launch_bounds__(RX_TILE_THREADS) k_raster(SceneDev S, Workspac
 
         if (F.d3_active) {
             const uint32_t n_large = min(C.n_large, Wk.large_stride);
-            const uint32_t n_list = Wk.tile_count[(size_t)f * Wk.tile_stride + tile];
             const uint32_t* large = Wk.large + (size_t)f * Wk.large_stride;
+            // (1) large triangles: records cached in shared memory per frame, culled per tile
+            if (f != cached_frame) {
+                n_cached = min(n_large, (uint32_t)RX_LARGE_CACHE);
+                for (uint32_t i = tid; i < n_cached; i += RX_TILE_THREADS) s_large_slot[i] = large[i];
+                __syncthreads();
+                const float4* g = reinterpret_cast<const float4*>(vis);
+                float4* s = reinterpret_cast<float4*>(s_large);
+                for (uint32_t i = tid; i < n_cached * 6u; i += RX_TILE_THREADS) {
+                    const uint32_t r = i / 6u, q = i - r * 6u;
+                    s[i] = __ldg(g + (size_t)s_large_slot[r] * 6u + q);
+                }
+                cached_frame = f;
+                __syncthreads();
+            }
+            if (tid < n_cached && tile_overlaps(s_large[tid], tx0, ty0, tx1, ty1)) s_sel[atomicAdd(&s_nsel, 1u)] = (uint16_t)tid;
+            __syncthreads();
+            {
+                const uint32_t n = s_nsel;
+                for (uint32_t k = 0; k < n; ++k) {
+                    const uint32_t r = s_sel[k];
+                    const TriVis& T = s_large[r];
+                    const int x0 = T.bbx & 0xFFFF, x1 = T.bbx >> 16, y0 = T.bby & 0xFFFF, y1 = T.bby >> 16;
+                    if (x0 >= wx1 || x1 <= wx0 || y0 >= wy1 || y1 <= wy0) continue;  // warp-uniform
+                    test_fragment(S, F, fbs, shade, T, s_large_slot[r], px, py, fpx, fpy, ps);
+                }
+            }
+            // (2) the rest of the large list, then the tile's binned list: staged in chunks, culled, walked
+            const uint32_t n_list = Wk.tile_count[(size_t)f * Wk.tile_stride + tile];
             const uint32_t* list = Wk.lists + (size_t)f * Wk.list_stride + Wk.tile_base[(size_t)f * Wk.tile_stride + tile];
             for (int pass = 0; pass < 2; ++pass) {
-                const uint32_t* src = pass == 0 ? large : list;
-                const uint32_t n_src = pass == 0 ? n_large : n_list;
+                const uint32_t* src = pass == 0 ? large + n_cached : list;
+                const uint32_t n_src = pass == 0 ? n_large - n_cached : n_list;
                 for (uint32_t base = 0; base < n_src; base += RX_STAGE) {
                     const uint32_t n = min((uint32_t)RX_STAGE, n_src - base);
-                    __syncthreads();  // previous stage fully consumed
+                    __syncthreads();  // previous stage and selection fully consumed
                     if (tid < n) s_slot[tid] = src[base + tid];
+                    if (tid == 0) s_nsel = 0u;
                     __syncthreads();
                     {   // stage the records: 6 x 16 B each
                         const float4* g = reinterpret_cast<const float4*>(vis);
@@ -855,37 +942,15 @@ __global__ void __launch_bounds__(RX_TILE_THREADS) k_raster(SceneDev S, Workspac
                         }
                     }
                     __syncthreads();
-                    for (uint32_t r = 0; r < n; ++r) {
+                    if (tid < n && tile_overlaps(s_tri[tid], tx0, ty0, tx1, ty1)) s_sel[atomicAdd(&s_nsel, 1u)] = (uint16_t)tid;
+                    __syncthreads();
+                    const uint32_t nk = s_nsel;
+                    for (uint32_t k = 0; k < nk; ++k) {
+                        const uint32_t r = s_sel[k];
                         const TriVis& T = s_tri[r];
                         const int x0 = T.bbx & 0xFFFF, x1 = T.bbx >> 16, y0 = T.bby & 0xFFFF, y1 = T.bby >> 16;
                         if (x0 >= wx1 || x1 <= wx0 || y0 >= wy1 || y1 <= wy0) continue;  // warp-uniform
-                        if (px < x0 || px >= x1 || py < y0 || py >= y1) continue;
-                        // Edges::evaluate, edge.rs:28-36 (a NaN result passes)
-                        if ((T.ea[0] * fpx + T.eb[0] * fpy + T.ec[0]) < 0.0f) continue;
-                        if ((T.ea[1] * fpx + T.eb[1] * fpy + T.ec[1]) < 0.0f) continue;
-                        if ((T.ea[2] * fpx + T.eb[2] * fpy + T.ec[2]) < 0.0f) continue;
-                        // barycentric_weights_3d, rasterizer.rs:1754-1773
-                        const float apx = fpx - T.ax, apy = fpy - T.ay;
-                        const float pcx = T.cx - fpx, pcy = T.cy - fpy, pbx = T.bx - fpx, pby = T.by - fpy;
-                        const float alpha = (pcx * pby - pcy * pbx) / T.area;
-                        const float beta = (T.acx * apy - T.acy * apx) / T.area;
-                        const float gamma = 1.0f - alpha - beta;
-                        const float one_over_z = T.iz0 * alpha + T.iz1 * beta + T.iz2 * gamma;  // :1054-1056
-                        const float z = 1.0f / one_over_z;
-                        const uint32_t slot = s_slot[r];
-                        // sequential `z < zbuf` in submission order == lexicographic min of (z, ordinal)
-                        const bool pass_z = (z < ps.best_z) || (z == ps.best_z && ps.best != RX_OWNER_NONE && slot < ps.best);
-                        if (!pass_z) continue;
-                        if (T.meta & 0x80000000u) {  // alpha test: texel alpha must be 255 to write (:1408)
-                            const TriShade& sh = shade[slot];
-                            const float iu = sh.uw0 * alpha + sh.uw1 * beta + sh.uw2 * gamma;
-                            const float iv = sh.vw0 * alpha + sh.vw1 * beta + sh.vw2 * gamma;
-                            const float irw = sh.rw0 * alpha + sh.rw1 * beta + sh.rw2 * gamma;
-                            const uint32_t b = T.meta & 0x7FFFFFFFu;
-                            const uint32_t texel = rx_sample(S.arena, S.tex[fbs[b].tex], iu / irw, iv / irw, F.sample_mode, S.b3[b].repeat_mode);
-                            if ((texel >> 24) != 255u) continue;
-                        }
-                        ps.best_z = z; ps.best = slot; ps.alpha = alpha; ps.beta = beta;
+                        test_fragment(S, F, fbs, shade, T, s_slot[r], px, py, fpx, fpy, ps);
                     }
                 }
             }
@@ -946,7 +1011,7 @@ __global__ void __launch_bounds__(RX_TILE_THREADS) k_raster(SceneDev S, Workspac
         } else if (in_frame) {
             reinterpret_cast<uint32_t*>(frame_px)[(size_t)(py - F.band_y0) * (size_t)F.width + (size_t)px] = color;
         }
-        // the next iteration's first __syncthreads orders s_color reuse
+        __syncthreads();  // s_color, s_work and s_nsel are rewritten by the next tile
     }
 }
 

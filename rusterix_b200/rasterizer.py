@@ -188,9 +188,9 @@ class Rasterizer:
         return pixels
 
     @staticmethod
-    def rasterize_batch(rasterizers, scene: Scene, pixels, width, height, tile_size, assets: Assets, band=None,
-                        sync=True, device=0):
-        """Camera sweep: one Rasterizer (camera) per frame, one scene, one launch sequence."""
+    def prepare_batch(rasterizers, scene: Scene, width, height, tile_size, assets: Assets, band=None, device=0):
+        """Marshal a camera sweep once: uploads the scene if needed and returns a FrameBatch that
+        `rasterize_batch` replays with a single C call per step."""
         ctx = DeviceContext.get(device)
         ctx.upload(scene, assets, 4)
         n = len(rasterizers)
@@ -199,8 +199,26 @@ class Rasterizer:
             r._check_supported()
             frames[i] = marshal.make_frame(r, scene, width, height, tile_size, band)
         rows = height if band is None else band[1] - band[0]
-        stride = width * rows * 4
-        p, _k = _buffer_pointer(pixels, stride * n)
-        fn = ctx.lib.rxc_rasterize_batch if sync else ctx.lib.rxc_rasterize_batch_async
-        ctx.check(fn(ctx.handle, frames, n, C.c_void_p(p), stride))
+        return FrameBatch(ctx, frames, n, width * rows * 4)
+
+    @staticmethod
+    def rasterize_batch(rasterizers, scene: Scene, pixels, width, height, tile_size, assets: Assets, band=None,
+                        sync=True, device=0):
+        """Camera sweep: one Rasterizer (camera) per frame, one scene, one launch sequence.
+        `rasterizers` may be a list of Rasterizer or a FrameBatch from `prepare_batch`."""
+        fb = rasterizers if isinstance(rasterizers, FrameBatch) else Rasterizer.prepare_batch(
+            rasterizers, scene, width, height, tile_size, assets, band, device)
+        return fb.run(pixels, sync)
+
+
+class FrameBatch:
+    """Pre-marshalled rxc_frame array of a camera sweep (host-side convenience, no device state)."""
+
+    def __init__(self, ctx, frames, n, stride):
+        self.ctx, self.frames, self.n, self.stride = ctx, frames, n, stride
+
+    def run(self, pixels, sync=True):
+        p, _k = _buffer_pointer(pixels, self.stride * self.n)
+        fn = self.ctx.lib.rxc_rasterize_batch if sync else self.ctx.lib.rxc_rasterize_batch_async
+        self.ctx.check(fn(self.ctx.handle, self.frames, self.n, C.c_void_p(p), self.stride))
         return pixels

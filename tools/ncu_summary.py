@@ -1,0 +1,43 @@
+#!/usr/bin/env python
+"""Condenses an .ncu-rep (read offline with `ncu -i`) into the handful of counters DESIGN.md and
+bench.py cite.  usage: ncu_summary.py <report.ncu-rep> [--json out.json]"""
+import csv
+import io
+import json
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "smsp__issue_active.avg.pct", "smsp__inst_executed.sum", "smsp__thread_inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+    "launch__occupancy_limit_registers", "launch__waves_per_multiprocessor", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__cycles_elapsed.max",
+]
+PREFIXES = ["smsp__average_warps_issue_stalled", "smsp__inst_executed_op_local", "smsp__pcsamp_warps_issue_stalled"]
+
+
+def summarize(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    res = []
+    for r in rows[2:]:
+        d = {}
+        for h, u, v in zip(hdr, units, r):
+            if h in ("Kernel Name", "ID") or h in KEYS or any(h.startswith(p) for p in PREFIXES):
+                d[h] = v if h in ("Kernel Name", "ID") else f"{v} {u}".strip()
+        res.append(d)
+    return res
+
+
+if __name__ == "__main__":
+    res = summarize(sys.argv[1])
+    if "--json" in sys.argv:
+        json.dump(res, open(sys.argv[sys.argv.index("--json") + 1], "w"), indent=1)
+    for d in res:
+        for k, v in d.items():
+            print(f"{k:90s} {v}")

@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""Joins an ncu SASS source page (per-instruction executed counts / stall samples) with nvdisasm line
+info of the in-tree library, and prints the hottest CUDA source lines of one kernel.
+usage: sass_lines.py <report.ncu-rep> <kernel-substring> [top N]"""
+import collections
+import csv
+import io
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def disasm_lines(kernel):
+    with tempfile.TemporaryDirectory() as td:
+        subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "rusterix_b200", "librxcuda.so")], cwd=td, capture_output=True)
+        cubin = [f for f in os.listdir(td) if f.startswith("rx_kernels")][0]
+        txt = subprocess.run(["nvdisasm", "-g", "-c", cubin], cwd=td, capture_output=True, text=True).stdout
+    out, cur, on = [], None, False
+    for line in txt.splitlines():
+        if line.startswith("//---") and ".text." in line:
+            on = kernel in line
+            continue
+        if not on:
+            continue
+        m = re.search(r'//## File "([^"]+)", line (\d+)', line)
+        if m:
+            cur = (os.path.basename(m.group(1)), int(m.group(2)))
+            continue
+        if re.match(r"\s+/\*[0-9a-f]{4}\*/", line):
+            out.append(cur)
+    return out
+
+
+def main():
+    rep, kernel = sys.argv[1], sys.argv[2]
+    top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+    lines = disasm_lines(kernel)
+    page = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(page)))
+    hdr = rows[1]
+    ci, cs = hdr.index("Instructions Executed"), hdr.index("# Samples")
+    body = rows[2:]
+    if len(body) != len(lines):
+        print(f"warning: {len(body)} profiled instructions vs {len(lines)} disassembled", file=sys.stderr)
+    inst, samp = collections.Counter(), collections.Counter()
+    for r, ln in zip(body, lines):
+        inst[ln] += int(r[ci] or 0)
+        samp[ln] += int(r[cs] or 0)
+    ti, tsamp = sum(inst.values()), sum(samp.values())
+    src = {}
+    print(f"total warp instructions {ti}, samples {tsamp}")
+    for ln, n in inst.most_common(top):
+        if ln is None:
+            text = "?"
+        else:
+            if ln[0] not in src:
+                p = os.path.join(ROOT, "rusterix_b200", "csrc", ln[0])
+                src[ln[0]] = open(p).read().splitlines() if os.path.exists(p) else []
+            text = src[ln[0]][ln[1] - 1].strip()[:110] if ln[1] - 1 < len(src[ln[0]]) else ""
+        print(f"{100.0 * n / ti:5.1f}% inst {100.0 * samp[ln] / max(1, tsamp):5.1f}% samp  {ln}  {text}")
+
+
+if __name__ == "__main__":
+    main()
