@@ -635,87 +635,143 @@ struct PixelState {
     float alpha, beta;   // barycentrics of the owner at this pixel
 };
 
-// rasterizer.rs:1319-1404 + :1875-1951 for one fragment; returns RGBA8.
+// ---- shading-only fast math --------------------------------------------------------------------
+// Everything below feeds only the final RGBA8 of a pixel whose owner is already decided (coverage,
+// depth and the alpha test above are exact).  The parity bar for colour is +-1 LSB, so shading uses
+// the SFU approximations (rsqrt/rcp/sqrt/ex2/lg2, <= 2 ulp) and explicit FMAs.
+__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_rsqrt(float x) { float r; asm("rsqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_ex2(float x) { float r; asm("ex2.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_lg2(float x) { float r; asm("lg2.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fdot3(f3 a, f3 b) { return __fmaf_rn(a.x, b.x, __fmaf_rn(a.y, b.y, a.z * b.z)); }
+__device__ __forceinline__ f3 fnormalize3(f3 a) { const float i = fast_rsqrt(fdot3(a, a)); return {a.x * i, a.y * i, a.z * i}; }
+__device__ __forceinline__ float fsmoothstep(float e0, float e1, float x) {
+    const float t = rx_clamp((x - e0) * fast_rcp(e1 - e0), 0.0f, 1.0f);
+    return t * t * __fmaf_rn(-2.0f, t, 3.0f);
+}
+
+// CompiledLight::radiance_at for the 3D path (light.rs:504-653): incoming colour times Lambert for
+// positional lights.  `ldir`/`dist` are the unit vector and distance from the point to the light.
+__device__ __forceinline__ bool light_radiance_fast(const DLight& l, f3 normal, f3 ldir, float dist, f3* out) {
+    if (!l.emitting) return false;
+    const f3 col = {l.cr, l.cg, l.cb};
+    float att;      // scalar applied to the light colour
+    bool lambert = true;
+    switch (l.light_type) {
+        case RXC_LIGHT_POINT:
+            if (dist >= l.end_distance) return false;
+            att = l.intensity * l.flicker_factor;
+            if (!(dist <= l.start_distance)) att *= fsmoothstep(l.end_distance, l.start_distance, dist);
+            break;
+        case RXC_LIGHT_AMBIENT:
+        case RXC_LIGHT_AMBIENT_DAYLIGHT:
+            att = l.intensity * l.flicker_factor;
+            lambert = false;
+            break;
+        case RXC_LIGHT_SPOT: {
+            if (dist >= l.end_distance) return false;
+            const float a = (dist <= l.start_distance) ? 1.0f : 1.0f - (dist - l.start_distance) * fast_rcp(l.end_distance - l.start_distance);
+            // direction_to_point = -ldir; angle = acos(dir . direction_to_point) > cone_angle -> None
+            const float c = -(l.dx * ldir.x + l.dy * ldir.y + l.dz * ldir.z);
+            if (acosf(c) > l.cone_angle) return false;
+            att = l.intensity * a * l.flicker_factor;
+            break;
+        }
+        case RXC_LIGHT_AREA: {
+            if (dist >= l.end_distance) return false;
+            if (dist < 0.1f) { att = 1.0f; break; }
+            const float d = (dist <= l.start_distance) ? 1.0f : fsmoothstep(l.end_distance, l.start_distance, dist);
+            const float area = l.width * l.height;
+            if (l.from_linedef) att = d * area * l.intensity;
+            else att = fmaxf(-(l.nx * ldir.x + l.ny * ldir.y + l.nz * ldir.z), 0.0f) * d * area * l.intensity;
+            break;
+        }
+        default: {  // Daylight: no Lambert term (light.rs:513-519)
+            if (dist >= l.end_distance) return false;
+            const float d = (dist <= l.start_distance) ? 1.0f : fsmoothstep(l.end_distance, l.start_distance, dist);
+            att = fmaxf(-(l.nx * ldir.x + l.ny * ldir.y + l.nz * ldir.z), 0.0f) * d * l.intensity;
+            lambert = false;
+            break;
+        }
+    }
+    if (lambert) att *= fmaxf(fdot3(normal, ldir), 0.0f);  // light.rs:529-532
+    *out = {col.x * att, col.y * att, col.z * att};
+    return true;
+}
+
+// rasterizer.rs:1079-1404 + :1875-1951 for the owning fragment of a pixel; returns RGBA8.
 __device__ uint32_t shade_fragment(const SceneDev& S, const DFrame& F, const DLight* __restrict__ lights, const DBatch3& B,
                                    const DFrameBatch& FB, const TriShade& sh, float alpha, float beta, float gamma, float z,
                                    float fpx, float fpy, float u, float v) {
-    // screen_to_world, rasterizer.rs:1707-1727
-    const float x_ndc = 2.0f * (fpx / F.width_f) - 1.0f;
-    const float y_ndc = 1.0f - 2.0f * (fpy / F.height_f);
-    f4 vs = rx_matvec4(F.inv_proj, {x_ndc, y_ndc, z, 1.0f}, F.matvec_mode);
-    vs = {vs.x / vs.w, vs.y / vs.w, vs.z / vs.w, vs.w / vs.w};
-    const f4 ws = rx_matvec4(F.inv_view, vs, F.matvec_mode);
-    const f3 world = {ws.x, ws.y, ws.z};
-    const f3 cam = {F.cam[0], F.cam[1], F.cam[2]};
-    const f3 view_dir = rx_normalize3(rx_sub3(cam, world));
-
-    f3 normal = {0.0f, 0.0f, 0.0f};
-    if (B.has_normals) {  // rasterizer.rs:1083-1099
-        const f3 n0 = {sh.n0x, sh.n0y, sh.n0z}, n1 = {sh.n1x, sh.n1y, sh.n1z}, n2 = {sh.n2x, sh.n2y, sh.n2z};
-        normal = rx_normalize3(rx_add3(rx_add3(rx_scale3(n0, alpha), rx_scale3(n1, beta)), rx_scale3(n2, gamma)));
-        if (rx_dot3(normal, view_dir) < 0.0f) normal = {-normal.x, -normal.y, -normal.z};
-    }
-
+    // the texel decides the colour discontinuously, so u, v (computed exactly by the caller) and the
+    // sampling are exact: texture.rs:203-460
     uint32_t texel;
     if (FB.tex != 0xFFFFFFFFu) texel = rx_sample(S.arena, S.tex[FB.tex], u, v, F.sample_mode, B.repeat_mode);
     else if (B.source_kind == RXC_SRC_PIXEL) texel = B.source_pixel;
     else texel = 0xFF000000u;  // rasterizer.rs:1221
 
+    // screen_to_world, rasterizer.rs:1707-1727
+    const float x_ndc = __fmaf_rn(2.0f, fpx * fast_rcp(F.width_f), -1.0f);
+    const float y_ndc = __fmaf_rn(-2.0f, fpy * fast_rcp(F.height_f), 1.0f);
+    f4 vs = rx_matvec4(F.inv_proj, {x_ndc, y_ndc, z, 1.0f}, RXC_MATVEC_FMA_COLUMNS);
+    const float iw = fast_rcp(vs.w);
+    vs = {vs.x * iw, vs.y * iw, vs.z * iw, 1.0f};
+    const f4 ws = rx_matvec4(F.inv_view, vs, RXC_MATVEC_FMA_COLUMNS);
+    const f3 world = {ws.x, ws.y, ws.z};
+    const f3 cam = {F.cam[0], F.cam[1], F.cam[2]};
+    const f3 view_dir = fnormalize3(rx_sub3(cam, world));
+
+    f3 normal = {0.0f, 0.0f, 0.0f};
+    if (B.has_normals) {  // rasterizer.rs:1083-1099
+        normal = {__fmaf_rn(sh.n2x, gamma, __fmaf_rn(sh.n1x, beta, sh.n0x * alpha)),
+                  __fmaf_rn(sh.n2y, gamma, __fmaf_rn(sh.n1y, beta, sh.n0y * alpha)),
+                  __fmaf_rn(sh.n2z, gamma, __fmaf_rn(sh.n1z, beta, sh.n0z * alpha))};
+        normal = fnormalize3(normal);
+        if (fdot3(normal, view_dir) < 0.0f) normal = {-normal.x, -normal.y, -normal.z};
+    } else {
+        normal = fnormalize3(normal);  // Vec3::zero().normalized() is NaN in the reference (:1320)
+    }
+
     const float inv255 = 1.0f / 255.0f;
-    auto s2l = [](float x) { float x2 = x * x; return (0.6975f * x2 + 0.3025f) * x; };  // rasterizer.rs:20-25
+    auto s2l = [](float x) { const float x2 = x * x; return __fmaf_rn(0.6975f, x2, 0.3025f) * x; };  // rasterizer.rs:20-25
     const f3 base = {s2l((float)(texel & 0xFF) * inv255), s2l((float)((texel >> 8) & 0xFF) * inv255),
                      s2l((float)((texel >> 16) & 0xFF) * inv255)};
-    const float opacity = (float)(texel >> 24) / 255.0f;
 
-    normal = rx_normalize3(normal);  // rasterizer.rs:1320
-    const float roughness = 0.5f, metallic = 0.0f;
-
-    f3 lit = {0.0f, 0.0f, 0.0f};
+    // roughness 0.5, metallic 0 (no batch shader): f0 = 0.04, kd = base * 0.96, shininess = 2/0.25 - 2 = 6
     const float hemi = 0.5f * (normal.y + 1.0f);
-    const f3 kd = rx_scale3(rx_scale3(base, 1.0f - metallic), 1.0f - 0.04f);
-    if (F.has_ambient) {  // rasterizer.rs:1334-1365 (occlusion == 1.0: no occluded sectors)
-        const f3 sky = {F.ambient[0], F.ambient[1], F.ambient[2]};
-        lit = rx_add3(lit, rx_scale3(rx_mul3(sky, kd), hemi));
-        lit = rx_scale3(lit, 1.0f);
-    }
-    {  // rasterizer.rs:1368-1370
-        const f3 amb = {B.ambient[0], B.ambient[1], B.ambient[2]};
-        lit = rx_add3(lit, rx_scale3(rx_mul3(amb, kd), hemi));
-    }
+    const f3 kd = rx_scale3(base, 1.0f - 0.04f);
+    f3 lit = {0.0f, 0.0f, 0.0f};
+    if (F.has_ambient) lit = {F.ambient[0] * kd.x * hemi, F.ambient[1] * kd.y * hemi, F.ambient[2] * kd.z * hemi};  // :1334-1365
+    lit = {__fmaf_rn(B.ambient[0] * kd.x, hemi, lit.x), __fmaf_rn(B.ambient[1] * kd.y, hemi, lit.y),
+           __fmaf_rn(B.ambient[2] * kd.z, hemi, lit.z)};  // :1368-1370
+
+    const float n_dot_v = fmaxf(fdot3(normal, view_dir), 0.0f);
+    const float om = 1.0f - fminf(n_dot_v, 1.0f);
+    const float x5 = om * om * om * om * om;
+    const float fr = __fmaf_rn(1.0f - 0.04f, x5, 0.04f);  // schlick_fresnel with f0 = 0.04 (:1882-1887)
     for (uint32_t li = 0; li < S.n_lights; ++li) {  // rasterizer.rs:1373-1391
         const DLight& L = lights[li];
-        f3 incoming;
-        if (!rx_light_color_at(L, world, false, &incoming)) continue;
-        const f3 lp = {L.px, L.py, L.pz};
-        const f3 ldir = rx_normalize3(rx_sub3(lp, world));
-        f3 radiance = incoming;
-        if (!(L.light_type == RXC_LIGHT_AMBIENT || L.light_type == RXC_LIGHT_AMBIENT_DAYLIGHT || L.light_type == RXC_LIGHT_DAYLIGHT)) {
-            const float lambert = fmaxf(rx_dot3(normal, ldir), 0.0f);  // light.rs:529-532
-            radiance = rx_scale3(incoming, lambert);
-        }
-        // shade_fast_brdf, rasterizer.rs:1912-1951 (emissive = 0)
-        const float n_dot_l = fmaxf(rx_dot3(normal, ldir), 0.0f);
-        if (n_dot_l <= 0.0f) continue;
-        const float t = rx_clamp(metallic, 0.0f, 1.0f);
-        const f3 f0 = {__fmaf_rn(t, base.x - 0.04f, 0.04f), __fmaf_rn(t, base.y - 0.04f, 0.04f), __fmaf_rn(t, base.z - 0.04f, 0.04f)};
-        f3 kdl = rx_scale3(base, 1.0f - metallic);
-        kdl = rx_scale3(kdl, 1.0f - fmaxf(f0.x, fmaxf(f0.y, f0.z)));
-        const float a = fmaxf(roughness * roughness, 1e-4f);
-        const float shininess = rx_clamp(2.0f / a - 2.0f, 1.0f, 2048.0f);
-        const f3 h = rx_normalize3(rx_add3(ldir, view_dir));
-        const float n_dot_h = fmaxf(rx_dot3(normal, h), 0.0f);
-        const float spec_b = (n_dot_h <= 0.0f) ? 0.0f : exp2f(shininess * log2f(n_dot_h));
-        const float n_dot_v = fmaxf(rx_dot3(normal, view_dir), 0.0f);
-        const float om = 1.0f - rx_clamp(n_dot_v, 0.0f, 1.0f);
-        const float x5 = om * om * om * om * om;
-        const f3 fr = {f0.x + (1.0f - f0.x) * x5, f0.y + (1.0f - f0.y) * x5, f0.z + (1.0f - f0.z) * x5};
-        const f3 diffuse = rx_scale3(kdl, n_dot_l);
-        const f3 specular = rx_scale3(rx_scale3(fr, spec_b), n_dot_l);
-        lit = rx_add3(lit, rx_mul3(rx_add3(diffuse, specular), radiance));
+        const f3 to_l = {L.px - world.x, L.py - world.y, L.pz - world.z};
+        const float d2 = fdot3(to_l, to_l);
+        const float inv_d = fast_rsqrt(d2);
+        const f3 ldir = {to_l.x * inv_d, to_l.y * inv_d, to_l.z * inv_d};
+        f3 radiance;
+        if (!light_radiance_fast(L, normal, ldir, d2 * inv_d, &radiance)) continue;
+        // shade_fast_brdf, rasterizer.rs:1912-1951
+        const float n_dot_l = fmaxf(fdot3(normal, ldir), 0.0f);
+        if (!(n_dot_l > 0.0f)) continue;
+        const f3 h = fnormalize3(rx_add3(ldir, view_dir));
+        const float n_dot_h = fmaxf(fdot3(normal, h), 0.0f);
+        const float spec_b = (n_dot_h <= 0.0f) ? 0.0f : fast_ex2(6.0f * fast_lg2(n_dot_h));
+        const float spec = fr * spec_b;
+        lit = {__fmaf_rn((kd.x + spec) * n_dot_l, radiance.x, lit.x), __fmaf_rn((kd.y + spec) * n_dot_l, radiance.y, lit.y),
+               __fmaf_rn((kd.z + spec) * n_dot_l, radiance.z, lit.z)};
     }
-    auto l2s = [](float x) { float s = sqrtf(x); return 1.055f * s - 0.055f * s * s; };  // rasterizer.rs:28-33
+    auto l2s = [](float x) { const float s = fast_sqrt(x); return __fmaf_rn(-0.055f * s, s, 1.055f * s); };  // rasterizer.rs:28-33
+    const uint32_t a8 = texel >> 24;  // f32_to_u8_saturated(a / 255) == a for every u8 a
     return rx_f32_to_u8_saturated(l2s(lit.x)) | (rx_f32_to_u8_saturated(l2s(lit.y)) << 8) |
-           (rx_f32_to_u8_saturated(l2s(lit.z)) << 16) | (rx_f32_to_u8_saturated(opacity) << 24);
+           (rx_f32_to_u8_saturated(l2s(lit.z)) << 16) | (a8 << 24);
 }
 
 // src/shader/vgradient.rs:11-14 and src/shader/grid.rs:36-108
