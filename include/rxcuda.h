@@ -252,6 +252,14 @@ int32_t rxc_synchronize(rxc_ctx* ctx);
  * base + index into the batch's clipped_indices; capacity 3*n_triangles per batch). */
 int32_t rxc_owner_base(const rxc_ctx* ctx, uint32_t batch, uint32_t* base);
 
+/* Diagnostics: the raster kernel divides barycentric numerators by the triangle area with a
+ * residual-corrected multiply by the correctly rounded reciprocal instead of div.rn (same bits,
+ * fewer instructions).  This runs that routine against div.rn on about n_pairs operand pairs drawn
+ * from the admitted ranges (hard mantissa patterns, quotients at rounding midpoints) on the device
+ * and returns how many results differ (must be 0); bad_pair (optional, 2 words) receives the bits
+ * of one failing (numerator, divisor). */
+int32_t rxc_selftest_div(rxc_ctx* ctx, uint64_t seed, uint64_t n_pairs, uint64_t* mismatches, uint32_t* bad_pair);
+
 int32_t rxc_set_profiling(rxc_ctx* ctx, int32_t enabled);
 int32_t rxc_get_stats(rxc_ctx* ctx, rxc_stats* out);
 int32_t rxc_reset_stats(rxc_ctx* ctx);

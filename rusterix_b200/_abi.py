@@ -167,6 +167,7 @@ EXPORTS = [
     ("rxc_rasterize_batch_async", C.c_int32, [C.c_void_p, C.POINTER(rxc_frame), C.c_uint32, C.c_void_p, C.c_uint64]),
     ("rxc_synchronize", C.c_int32, [C.c_void_p]),
     ("rxc_owner_base", C.c_int32, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]),
+    ("rxc_selftest_div", C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     ("rxc_set_profiling", C.c_int32, [C.c_void_p, C.c_int32]),
     ("rxc_get_stats", C.c_int32, [C.c_void_p, C.POINTER(rxc_stats)]),
     ("rxc_reset_stats", C.c_int32, [C.c_void_p]),

@@ -122,6 +122,7 @@ int32_t build_tiles(rxc_ctx* ctx, const rxc_tile* tiles, uint32_t n, std::vector
         for (uint32_t j = 0; j < t.n_frames; ++j) {
             const rxc_texture& x = tiles[i].textures[j];
             if (!x.data || x.width == 0 || x.height == 0) return fail(ctx, RXC_ERR_INVALID, "empty texture");
+            if (x.width > 65535u || x.height > 65535u) return fail(ctx, RXC_ERR_UNSUPPORTED, "textures larger than 65535 texels per side");
             DTex d; d.offset = arena.size(); d.width = x.width; d.height = x.height; d.pad = 0;
             size_t bytes = (size_t)x.width * x.height * 4;
             bool opaque = true;
@@ -146,6 +147,7 @@ int32_t upload_textures(rxc_ctx* ctx) {
     for (DTex d : ctx->h_dyn_tex) { d.offset += aoff; tex.push_back(d); }
     for (DTile t : ctx->h_dyn_tiles) { t.first += toff; tiles.push_back(t); }
     int32_t st;
+    if (arena.size() >= ((size_t)1 << 34)) return fail(ctx, RXC_ERR_UNSUPPORTED, "more than 16 GiB of texels");
     if ((st = upload(ctx, ctx->d_arena, arena.data(), arena.size())) != RXC_OK) return st;
     if ((st = upload(ctx, ctx->d_tex, tex.data(), tex.size() * sizeof(DTex))) != RXC_OK) return st;
     if ((st = upload(ctx, ctx->d_tiles, tiles.data(), tiles.size() * sizeof(DTile))) != RXC_OK) return st;
@@ -318,6 +320,24 @@ int32_t fill_frame(rxc_ctx* ctx, const rxc_frame& f, DFrame* d) {
     d->trans2d[0] = 0.0f; d->trans2d[1] = 0.0f; d->scale2d = 1.0f;  // rasterizer.rs:104-110
     if (f.has_matrix2d) { d->trans2d[0] = f.matrix2d[6]; d->trans2d[1] = f.matrix2d[7]; d->scale2d = f.matrix2d[0]; }
     d->animation_frame = f.animation_frame;
+    {   // screen_to_world (rasterizer.rs:1707-1727) as one projective map of (px+.5, py+.5, z, 1), in double
+        double IP[4][4], IV[4][4], G[4][4], N[4][4] = {{2.0 / f.width, 0, 0, -1.0}, {0, -2.0 / f.height, 0, 1.0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c) { IP[r][c] = f.inverse_projection[c * 4 + r]; IV[r][c] = f.inverse_view[c * 4 + r]; }
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c) {
+                double a = 0;
+                for (int k = 0; k < 4; ++k) a += IV[r][k] * IP[k][c];
+                G[r][c] = a;
+            }
+        for (int c = 0; c < 4; ++c) { G[3][c] = IP[3][c]; }  // the divisor is view_space.w
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c) {
+                double a = 0;
+                for (int k = 0; k < 4; ++k) a += G[r][k] * N[k][c];
+                d->s2w[r * 4 + c] = (float)a;
+            }
+    }
     return RXC_OK;
 }
 
@@ -589,6 +609,7 @@ int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
             if (idx_at(b.indices, b.index_bytes, k) >= b.n_vertices) return fail(ctx, RXC_ERR_INDEX, who + "vertex index out of range (reference panics)");
         V2 += b.n_vertices; T2 += b.n_triangles;
     }
+    if (sc->n_batches3d >= RX_META_BATCH) return fail(ctx, RXC_ERR_UNSUPPORTED, "too many 3D batches");
     if (3 * T >= 0x7FFFFFFFull || V >= 0xFFFFFFFFull) return fail(ctx, RXC_ERR_UNSUPPORTED, "scene too large for 32-bit slots");
 
     // ---- flatten 3D
@@ -711,6 +732,25 @@ int32_t rxc_synchronize(rxc_ctx* ctx) {
 int32_t rxc_owner_base(const rxc_ctx* ctx, uint32_t batch, uint32_t* base) {
     if (!ctx || !base || batch >= ctx->owner_base.size()) return RXC_ERR_INVALID;
     *base = ctx->owner_base[batch];
+    return RXC_OK;
+}
+
+int32_t rxc_selftest_div(rxc_ctx* ctx, uint64_t seed, uint64_t n_pairs, uint64_t* mismatches, uint32_t* bad_pair) {
+    if (!ctx || !mismatches) return RXC_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    unsigned long long* d = nullptr;
+    CK(cudaMalloc((void**)&d, 2 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    const uint32_t blocks = (uint32_t)ctx->sm_count * 8u;
+    const uint32_t iters = (uint32_t)std::max<uint64_t>(1, n_pairs / ((uint64_t)blocks * 256u));
+    cudaError_t e = rxk_selftest_div(seed, blocks, iters, d, ctx->stream);
+    unsigned long long h[2] = {0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) { ctx->err = std::string("rxc_selftest_div: ") + cudaGetErrorString(e); return RXC_ERR_CUDA; }
+    *mismatches = h[0];
+    if (bad_pair) { bad_pair[0] = (uint32_t)(h[1] >> 32); bad_pair[1] = (uint32_t)h[1]; }
     return RXC_OK;
 }
 

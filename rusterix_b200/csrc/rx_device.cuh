@@ -9,9 +9,11 @@
 
 #include "rxcuda.h"
 
-#define RX_TILE_W 16
-#define RX_TILE_H 16
-#define RX_TILE_THREADS (RX_TILE_W * RX_TILE_H)
+#define RX_TILE_W 32             // screen tile of one raster CTA
+#define RX_TILE_H 32
+#define RX_TILE_THREADS 256       // 8 warps; warp w owns a 16x8 region, every thread 2x2 pixels of it (stride 8, 4)
+#define RX_REGION_W 16
+#define RX_REGION_H 8
 #define RX_CHUNK_TRIS 256          // triangles of one batch handled by one setup CTA
 #define RX_LARGE_TILES 24          // a triangle covering more GPU tiles than this goes to the large list
 #define RX_OWNER_NONE 0xFFFFFFFFu
@@ -65,7 +67,7 @@ struct DLight {          // rxc_light + the per-frame flicker factor (light.rs:6
     float cr, cg, cb, flicker_factor;
     float start_distance, end_distance, cone_angle, width;
     float dx, dy, dz, height;
-    float nx, ny, nz, pad2;
+    float nx, ny, nz, inv_range;  // inv_range = 1/(start - end), filled per frame (smoothstep / linear falloff)
 };
 
 struct DChunk {          // work item of the setup kernel: <= RX_CHUNK_TRIS triangles of one batch
@@ -73,7 +75,7 @@ struct DChunk {          // work item of the setup kernel: <= RX_CHUNK_TRIS tria
 };
 
 // per (frame, 3D batch) state, written by k_frame_setup / k_tri_setup / k_batch_finalize
-struct DFrameBatch {
+struct __align__(16) DFrameBatch {
     float view_model[16];
     uint32_t bb_minx, bb_maxx, bb_miny, bb_maxy; // order-preserving uint keys of the float bbox
     int32_t sc_x0, sc_x1, sc_y0, sc_y1;          // pixel scissor equivalent to the per-tile bbox reject
@@ -81,7 +83,18 @@ struct DFrameBatch {
     uint32_t tex;                                // DTex index for this frame (animation frame applied)
     uint32_t alpha_test;                         // texture has non-opaque texels
     uint32_t n_new_tris;                         // near-clip output triangles of this batch
+    // what the deferred shade reads per owner, packed into two 16 B loads
+    uint32_t sd_tex_word;                        // texel arena offset / 4 of this frame's texture
+    uint32_t sd_wh;                              // width | height << 16   (textures <= 65535 per side)
+    uint32_t sd_flags;                           // RX_SD_* bits
+    uint32_t sd_pixel;                           // constant texel for Pixel / other sources
+    float sd_ambient[3];                         // batch.ambient_color
+    uint32_t sd_pad;
 };
+#define RX_SD_TEXTURED 1u
+#define RX_SD_REPEAT_X 2u
+#define RX_SD_REPEAT_Y 4u
+#define RX_SD_NORMALS 8u
 
 struct DFrameBatch2 {
     uint32_t tex;          // DTex index or 0xFFFFFFFF (transparent texel)
@@ -92,13 +105,16 @@ struct DFrameBatch2 {
 // Visibility record: everything the per-pixel coverage/depth test reads (96 B, 16 B aligned)
 struct __align__(16) TriVis {
     float ax, ay, bx, by;      // unswapped projected v0, v1 (xy)
-    float cx, cy, acx, acy;    // v2, ac = c - a
+    float cx, cy, rarea, spare;// v2 ; rarea = RN(1/area) for the exact fast division (see rx_div_by)
     float area, iz0, iz1, iz2; // area = ac.x*ab.y - ac.y*ab.x ; 1/z per vertex
     float ea[3], eb[3], ec[3]; // edge equations of the (possibly swapped) triangle
     uint32_t bbx;              // x0 | x1<<16  (x1 exclusive), after scissor
     uint32_t bby;              // y0 | y1<<16
-    uint32_t meta;             // batch index | alpha_test<<31
+    uint32_t meta;             // batch index | fastdiv_ok<<30 | alpha_test<<31
 };
+#define RX_META_ALPHA 0x80000000u
+#define RX_META_FASTDIV 0x40000000u
+#define RX_META_BATCH 0x3FFFFFFFu
 static_assert(sizeof(TriVis) == 96, "TriVis must be 96 bytes");
 
 // Shading record: attributes only the alpha test and the final shade read (80 B)
@@ -153,6 +169,9 @@ struct DFrame {
     uint32_t matvec_mode;
     float trans2d[2], scale2d;
     uint64_t animation_frame;
+    // screen_to_world (rasterizer.rs:1707-1727) folded by the host in double precision:
+    // (hx,hy,hz,hw) = s2w * (px+.5, py+.5, z, 1), world = (hx,hy,hz)/hw.  Row-major 4x4.
+    float s2w[16];
 };
 
 // per-frame counters (zeroed by k_frame_setup)
@@ -242,6 +261,19 @@ __device__ __forceinline__ f4 rx_project(const float* proj, f4 v, float vw, floa
     return o;
 }
 
+// a / b, correctly rounded, given rb = RN(1/b) (Markstein's residual correction: two fused
+// corrections of q = a*rb).  Exact only while no intermediate under/overflows: callers guarantee
+// |b| in [2^-20, 2^44] and a == 0 or |a| in [2^-80, 2^62], so the quotient stays normal (see make_tri);
+// checked against div.rn on
+// the device by rxc_selftest_div.
+__device__ __forceinline__ float rx_div_by(float a, float b, float rb) {
+    float q = a * rb;
+    float r = __fmaf_rn(-b, q, a);
+    q = __fmaf_rn(r, rb, q);
+    r = __fmaf_rn(-b, q, a);
+    return __fmaf_rn(r, rb, q);
+}
+
 __device__ __forceinline__ float rx_clamp(float x, float lo, float hi) {  // Rust f32::clamp (NaN stays)
     if (x < lo) return lo;
     if (x > hi) return hi;
@@ -286,12 +318,10 @@ __device__ __forceinline__ float rx_wrap(float u, bool repeat) {
     return repeat ? (u - floorf(u)) : rx_clamp(u, 0.0f, 1.0f);
 }
 // texture.rs:203-232, 307-323, 414-460.  Returns RGBA packed little endian.
-__device__ __forceinline__ uint32_t rx_sample(const uint8_t* __restrict__ arena, const DTex& t, float u, float v,
-                                              uint32_t sample_mode, uint32_t repeat_mode) {
-    u = rx_wrap(u, repeat_mode == RXC_REPEAT_REPEAT_XY || repeat_mode == RXC_REPEAT_REPEAT_X);
-    v = rx_wrap(v, repeat_mode == RXC_REPEAT_REPEAT_XY || repeat_mode == RXC_REPEAT_REPEAT_Y);
-    const uint32_t* tex = reinterpret_cast<const uint32_t*>(arena + t.offset);
-    const int W = (int)t.width, H = (int)t.height;
+__device__ __forceinline__ uint32_t rx_sample_tex(const uint32_t* __restrict__ tex, int W, int H, float u, float v,
+                                                  uint32_t sample_mode, bool repeat_x, bool repeat_y) {
+    u = rx_wrap(u, repeat_x);
+    v = rx_wrap(v, repeat_y);
     if (sample_mode == RXC_SAMPLE_NEAREST) {
         int tx = rx_sat_int(roundf(u * ((float)W - 1.0f)), W - 1);
         int ty = rx_sat_int(roundf(v * ((float)H - 1.0f)), H - 1);
@@ -318,6 +348,12 @@ __device__ __forceinline__ uint32_t rx_sample(const uint8_t* __restrict__ arena,
         out |= rx_as_u8(roundf(r)) << (8 * i);
     }
     return out;
+}
+__device__ __forceinline__ uint32_t rx_sample(const uint8_t* __restrict__ arena, const DTex& t, float u, float v,
+                                              uint32_t sample_mode, uint32_t repeat_mode) {
+    return rx_sample_tex(reinterpret_cast<const uint32_t*>(arena + t.offset), (int)t.width, (int)t.height, u, v, sample_mode,
+                         repeat_mode == RXC_REPEAT_REPEAT_XY || repeat_mode == RXC_REPEAT_REPEAT_X,
+                         repeat_mode == RXC_REPEAT_REPEAT_XY || repeat_mode == RXC_REPEAT_REPEAT_Y);
 }
 
 __device__ __forceinline__ float rx_smoothstep(float e0, float e1, float x) {  // light.rs:674-677

@@ -133,10 +133,23 @@ __device__ bool make_tri(const f4 P[3], const float2 uv[3], const f3 nn[3], uint
     edge_eq(v1.x, v1.y, v2.x, v2.y, &r.ea[1], &r.eb[1], &r.ec[1]);
     edge_eq(v2.x, v2.y, v0.x, v0.y, &r.ea[2], &r.eb[2], &r.ec[2]);
     r.ax = P[0].x; r.ay = P[0].y; r.bx = P[1].x; r.by = P[1].y; r.cx = P[2].x; r.cy = P[2].y;
-    r.acx = P[2].x - P[0].x; r.acy = P[2].y - P[0].y;
+    const float acx = P[2].x - P[0].x, acy = P[2].y - P[0].y;
     const float abx = P[1].x - P[0].x, aby = P[1].y - P[0].y;
-    r.area = r.acx * aby - r.acy * abx;  // rasterizer.rs:1767
+    r.area = acx * aby - acy * abx;  // rasterizer.rs:1767
+    r.rarea = 1.0f / r.area; r.spare = 0.0f;
     r.iz0 = 1.0f / P[0].z; r.iz1 = 1.0f / P[1].z; r.iz2 = 1.0f / P[2].z;  // rasterizer.rs:1054-1055
+    // The per-pixel barycentric divisions by `area` may use rx_div_by when nothing can leave the range
+    // in which the residual corrections are exact: finite coordinates up to 2^30 (numerators <= 2^62;
+    // pixel centres are k+0.5 < 2^14, so a non-zero (vertex - centre) is >= 2^-26), ac components zero
+    // or >= 2^-20 (non-zero numerators >= 2^-76) and |area| in [2^-20, 2^44].
+    {
+        const float big = 1073741824.0f, tiny = 9.5367431640625e-07f;
+        bool ok = fabsf(r.ax) <= big && fabsf(r.ay) <= big && fabsf(r.bx) <= big && fabsf(r.by) <= big && fabsf(r.cx) <= big &&
+                  fabsf(r.cy) <= big;  // false for NaN / Inf
+        ok = ok && (acx == 0.0f || fabsf(acx) >= tiny) && (acy == 0.0f || fabsf(acy) >= tiny);
+        ok = ok && fabsf(r.area) >= tiny && fabsf(r.area) <= 17592186044416.0f;
+        if (ok) meta |= RX_META_FASTDIV;
+    }
     r.bbx = *bbx; r.bby = *bby; r.meta = meta;
     *tv = r;
 
@@ -209,6 +222,7 @@ __global__ void __launch_bounds__(256) k_frame_setup(SceneDev S, Workspace Wk, u
                 factor = 1.0f - fv * l.flicker_factor;
             }
             l.flicker_factor = factor;
+            l.inv_range = 1.0f / (l.start_distance - l.end_distance);
             Wk.lights[(size_t)f * Wk.lights_stride + i] = l;
         }
         for (uint32_t b = tid; b < S.n_b3; b += blockDim.x) {
@@ -234,10 +248,20 @@ __global__ void __launch_bounds__(256) k_frame_setup(SceneDev S, Workspace Wk, u
             if (B.source_kind == RXC_SRC_PIXEL && (B.source_pixel >> 24) != 255u) rejected = true;
             fb.tex = 0xFFFFFFFFu;
             fb.alpha_test = 0;
+            fb.sd_tex_word = 0; fb.sd_wh = 0; fb.sd_pad = 0;
+            fb.sd_flags = B.has_normals ? RX_SD_NORMALS : 0u;
+            fb.sd_pixel = (B.source_kind == RXC_SRC_PIXEL) ? B.source_pixel : 0xFF000000u;  // rasterizer.rs:1221
+            fb.sd_ambient[0] = B.ambient[0]; fb.sd_ambient[1] = B.ambient[1]; fb.sd_ambient[2] = B.ambient[2];
+            if (B.repeat_mode == RXC_REPEAT_REPEAT_XY || B.repeat_mode == RXC_REPEAT_REPEAT_X) fb.sd_flags |= RX_SD_REPEAT_X;
+            if (B.repeat_mode == RXC_REPEAT_REPEAT_XY || B.repeat_mode == RXC_REPEAT_REPEAT_Y) fb.sd_flags |= RX_SD_REPEAT_Y;
             if (B.source_kind == RXC_SRC_STATIC_TILE || B.source_kind == RXC_SRC_DYNAMIC_TILE) {
                 const DTile t = S.tiles[(B.source_kind == RXC_SRC_STATIC_TILE ? 0u : S.n_static_tiles) + B.source_index];
                 fb.tex = t.first + (uint32_t)(F.animation_frame % t.n_frames);  // rasterizer.rs:1104-1105
-                fb.alpha_test = S.tex[fb.tex].all_opaque ? 0u : 1u;
+                const DTex tx = S.tex[fb.tex];
+                fb.alpha_test = tx.all_opaque ? 0u : 1u;
+                fb.sd_tex_word = (uint32_t)(tx.offset >> 2);
+                fb.sd_wh = tx.width | (tx.height << 16);
+                fb.sd_flags |= RX_SD_TEXTURED;
             }
             fb.bb_minx = rx_float_key(CUDART_INF_F); fb.bb_maxx = rx_float_key(-CUDART_INF_F);
             fb.bb_miny = rx_float_key(CUDART_INF_F); fb.bb_maxy = rx_float_key(-CUDART_INF_F);
@@ -397,7 +421,7 @@ __global__ void __launch_bounds__(RX_CHUNK_TRIS) k_tri_setup(SceneDev S, Workspa
             mm.add(P[k].x, P[k].y);
         }
         TriBin bin = {0u, 0u, slot, ch.batch};
-        const uint32_t meta = ch.batch | (FB.alpha_test << 31);
+        const uint32_t meta = ch.batch | (FB.alpha_test << 31);  // make_tri adds RX_META_FASTDIV
         TriVis tv; TriShade tsh;
         vis = make_tri(P, T.uv, T.nn, B.cull_mode, edge_vis, F.width, F.height, meta, &tv, &tsh, &bin.bbx, &bin.bby);
         if (vis) {
@@ -627,42 +651,46 @@ __global__ void __launch_bounds__(256) k_bin_fill(SceneDev S, Workspace Wk) {
 // ---------------------------------------------------------------------------------------------
 // k_raster
 // ---------------------------------------------------------------------------------------------
-#define RX_STAGE 64   // triangle records staged in shared memory per step
+#ifndef RX_RASTER_MIN_BLOCKS
+#define RX_RASTER_MIN_BLOCKS 3  // resident CTAs per SM the register allocation is bounded for
+#endif
+#define RX_STAGE 64          // triangle records staged in shared memory per step
+#define RX_LARGE_CACHE 160   // large-triangle records kept in shared memory across the tiles of a frame
+#define RX_COLOR_STRIDE 40   // words per tile row in shared memory: the 4 rows a warp writes hit disjoint banks
 
-struct PixelState {
-    float best_z;
-    uint32_t best;       // owner slot
-    float alpha, beta;   // barycentrics of the owner at this pixel
+// Visibility state of the 2x2 pixels of a thread: pixel k is (px0 + 8*(k&1), py0 + 4*(k>>1)).
+struct Vis4 {
+    float z[4];
+    uint32_t own[4];     // owner slot
+    float al[4], be[4];  // barycentrics of the owner at the pixel
 };
 
 // ---- shading-only fast math --------------------------------------------------------------------
 // Everything below feeds only the final RGBA8 of a pixel whose owner is already decided (coverage,
-// depth and the alpha test above are exact).  The parity bar for colour is +-1 LSB, so shading uses
-// the SFU approximations (rsqrt/rcp/sqrt/ex2/lg2, <= 2 ulp) and explicit FMAs.
+// depth and the alpha test are exact).  The parity bar for colour is +-1 LSB, so shading uses the
+// SFU approximations (rsqrt/rcp/sqrt, <= 2 ulp) and explicit FMAs.
 __device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float fast_rsqrt(float x) { float r; asm("rsqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float fast_ex2(float x) { float r; asm("ex2.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float fast_lg2(float x) { float r; asm("lg2.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float fdot3(f3 a, f3 b) { return __fmaf_rn(a.x, b.x, __fmaf_rn(a.y, b.y, a.z * b.z)); }
 __device__ __forceinline__ f3 fnormalize3(f3 a) { const float i = fast_rsqrt(fdot3(a, a)); return {a.x * i, a.y * i, a.z * i}; }
-__device__ __forceinline__ float fsmoothstep(float e0, float e1, float x) {
-    const float t = rx_clamp((x - e0) * fast_rcp(e1 - e0), 0.0f, 1.0f);
+// smoothstep(end, start, x) with inv_range = 1/(start - end)  (light.rs:674-677)
+__device__ __forceinline__ float fsmooth(const DLight& l, float x) {
+    const float t = rx_clamp((x - l.end_distance) * l.inv_range, 0.0f, 1.0f);
     return t * t * __fmaf_rn(-2.0f, t, 3.0f);
 }
 
 // CompiledLight::radiance_at for the 3D path (light.rs:504-653): incoming colour times Lambert for
 // positional lights.  `ldir`/`dist` are the unit vector and distance from the point to the light.
-__device__ __forceinline__ bool light_radiance_fast(const DLight& l, f3 normal, f3 ldir, float dist, f3* out) {
+__device__ __forceinline__ bool light_radiance_fast(const DLight& l, float n_dot_l, f3 ldir, float dist, f3* out) {
     if (!l.emitting) return false;
-    const f3 col = {l.cr, l.cg, l.cb};
     float att;      // scalar applied to the light colour
     bool lambert = true;
     switch (l.light_type) {
         case RXC_LIGHT_POINT:
             if (dist >= l.end_distance) return false;
             att = l.intensity * l.flicker_factor;
-            if (!(dist <= l.start_distance)) att *= fsmoothstep(l.end_distance, l.start_distance, dist);
+            if (!(dist <= l.start_distance)) att *= fsmooth(l, dist);
             break;
         case RXC_LIGHT_AMBIENT:
         case RXC_LIGHT_AMBIENT_DAYLIGHT:
@@ -671,7 +699,8 @@ __device__ __forceinline__ bool light_radiance_fast(const DLight& l, f3 normal, 
             break;
         case RXC_LIGHT_SPOT: {
             if (dist >= l.end_distance) return false;
-            const float a = (dist <= l.start_distance) ? 1.0f : 1.0f - (dist - l.start_distance) * fast_rcp(l.end_distance - l.start_distance);
+            // 1 - (dist - start)/(end - start)
+            const float a = (dist <= l.start_distance) ? 1.0f : __fmaf_rn(dist - l.start_distance, l.inv_range, 1.0f);
             // direction_to_point = -ldir; angle = acos(dir . direction_to_point) > cone_angle -> None
             const float c = -(l.dx * ldir.x + l.dy * ldir.y + l.dz * ldir.z);
             if (acosf(c) > l.cone_angle) return false;
@@ -681,7 +710,7 @@ __device__ __forceinline__ bool light_radiance_fast(const DLight& l, f3 normal, 
         case RXC_LIGHT_AREA: {
             if (dist >= l.end_distance) return false;
             if (dist < 0.1f) { att = 1.0f; break; }
-            const float d = (dist <= l.start_distance) ? 1.0f : fsmoothstep(l.end_distance, l.start_distance, dist);
+            const float d = (dist <= l.start_distance) ? 1.0f : fsmooth(l, dist);
             const float area = l.width * l.height;
             if (l.from_linedef) att = d * area * l.intensity;
             else att = fmaxf(-(l.nx * ldir.x + l.ny * ldir.y + l.nz * ldir.z), 0.0f) * d * area * l.intensity;
@@ -689,44 +718,64 @@ __device__ __forceinline__ bool light_radiance_fast(const DLight& l, f3 normal, 
         }
         default: {  // Daylight: no Lambert term (light.rs:513-519)
             if (dist >= l.end_distance) return false;
-            const float d = (dist <= l.start_distance) ? 1.0f : fsmoothstep(l.end_distance, l.start_distance, dist);
+            const float d = (dist <= l.start_distance) ? 1.0f : fsmooth(l, dist);
             att = fmaxf(-(l.nx * ldir.x + l.ny * ldir.y + l.nz * ldir.z), 0.0f) * d * l.intensity;
             lambert = false;
             break;
         }
     }
-    if (lambert) att *= fmaxf(fdot3(normal, ldir), 0.0f);  // light.rs:529-532
-    *out = {col.x * att, col.y * att, col.z * att};
+    if (lambert) att *= n_dot_l;  // light.rs:529-532
+    *out = {l.cr * att, l.cg * att, l.cb * att};
     return true;
 }
 
-// rasterizer.rs:1079-1404 + :1875-1951 for the owning fragment of a pixel; returns RGBA8.
-__device__ uint32_t shade_fragment(const SceneDev& S, const DFrame& F, const DLight* __restrict__ lights, const DBatch3& B,
-                                   const DFrameBatch& FB, const TriShade& sh, float alpha, float beta, float gamma, float z,
-                                   float fpx, float fpy, float u, float v) {
-    // the texel decides the colour discontinuously, so u, v (computed exactly by the caller) and the
-    // sampling are exact: texture.rs:203-460
-    uint32_t texel;
-    if (FB.tex != 0xFFFFFFFFu) texel = rx_sample(S.arena, S.tex[FB.tex], u, v, F.sample_mode, B.repeat_mode);
-    else if (B.source_kind == RXC_SRC_PIXEL) texel = B.source_pixel;
-    else texel = 0xFF000000u;  // rasterizer.rs:1221
+// Texture::sample (texture.rs:203-460) through the per-(frame,batch) descriptor of DFrameBatch.
+__device__ __forceinline__ uint32_t sample_desc(const uint8_t* __restrict__ arena, uint32_t tex_word, uint32_t wh, uint32_t flags,
+                                                float u, float v, uint32_t sample_mode) {
+    return rx_sample_tex(reinterpret_cast<const uint32_t*>(arena) + tex_word, (int)(wh & 0xFFFFu), (int)(wh >> 16), u, v,
+                         sample_mode, (flags & RX_SD_REPEAT_X) != 0u, (flags & RX_SD_REPEAT_Y) != 0u);
+}
 
-    // screen_to_world, rasterizer.rs:1707-1727
-    const float x_ndc = __fmaf_rn(2.0f, fpx * fast_rcp(F.width_f), -1.0f);
-    const float y_ndc = __fmaf_rn(-2.0f, fpy * fast_rcp(F.height_f), 1.0f);
-    f4 vs = rx_matvec4(F.inv_proj, {x_ndc, y_ndc, z, 1.0f}, RXC_MATVEC_FMA_COLUMNS);
-    const float iw = fast_rcp(vs.w);
-    vs = {vs.x * iw, vs.y * iw, vs.z * iw, 1.0f};
-    const f4 ws = rx_matvec4(F.inv_view, vs, RXC_MATVEC_FMA_COLUMNS);
-    const f3 world = {ws.x, ws.y, ws.z};
-    const f3 cam = {F.cam[0], F.cam[1], F.cam[2]};
-    const f3 view_dir = fnormalize3(rx_sub3(cam, world));
+// rasterizer.rs:1062-1404 + :1875-1951 for the owning fragment of a pixel; returns RGBA8.
+__device__ __forceinline__ uint32_t shade_owner(const SceneDev& S, const DFrame& F, const DLight* __restrict__ lights,
+                                                const DFrameBatch& FB, const TriShade* __restrict__ shp, float alpha, float beta,
+                                                float z, float fpx, float fpy) {
+    const float4* sq = reinterpret_cast<const float4*>(shp);
+    const float4 s0 = __ldg(sq), s1 = __ldg(sq + 1), s2 = __ldg(sq + 2);
+    const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(&FB.sd_tex_word));
+    const float4 d1 = __ldg(reinterpret_cast<const float4*>(&FB.sd_ambient[0]));
+    const uint32_t flags = d0.z;
+    const float gamma = 1.0f - alpha - beta;
+
+    uint32_t texel = d0.w;
+    if (flags & RX_SD_TEXTURED) {
+        // perspective-correct UV, rasterizer.rs:1062-1076.  The owner is decided; the quotients are
+        // faithful (rcp + one residual correction) instead of div.rn.
+        const float iu = s0.x * alpha + s0.z * beta + s1.x * gamma;
+        const float iv = s0.y * alpha + s0.w * beta + s1.y * gamma;
+        const float irw = s1.z * alpha + s1.w * beta + s2.x * gamma;
+        const float rr = fast_rcp(irw);
+        float u = iu * rr, v = iv * rr;
+        u = __fmaf_rn(__fmaf_rn(-irw, u, iu), rr, u);
+        v = __fmaf_rn(__fmaf_rn(-irw, v, iv), rr, v);
+        texel = sample_desc(S.arena, d0.x, d0.y, flags, u, v, F.sample_mode);
+    }
+
+    // screen_to_world, rasterizer.rs:1707-1727, folded into one affine map + divide (DFrame::s2w)
+    const float hx = __fmaf_rn(F.s2w[2], z, __fmaf_rn(F.s2w[1], fpy, __fmaf_rn(F.s2w[0], fpx, F.s2w[3])));
+    const float hy = __fmaf_rn(F.s2w[6], z, __fmaf_rn(F.s2w[5], fpy, __fmaf_rn(F.s2w[4], fpx, F.s2w[7])));
+    const float hz = __fmaf_rn(F.s2w[10], z, __fmaf_rn(F.s2w[9], fpy, __fmaf_rn(F.s2w[8], fpx, F.s2w[11])));
+    const float hw = __fmaf_rn(F.s2w[14], z, __fmaf_rn(F.s2w[13], fpy, __fmaf_rn(F.s2w[12], fpx, F.s2w[15])));
+    const float ihw = fast_rcp(hw);
+    const f3 world = {hx * ihw, hy * ihw, hz * ihw};
+    const f3 view_dir = fnormalize3({F.cam[0] - world.x, F.cam[1] - world.y, F.cam[2] - world.z});
 
     f3 normal = {0.0f, 0.0f, 0.0f};
-    if (B.has_normals) {  // rasterizer.rs:1083-1099
-        normal = {__fmaf_rn(sh.n2x, gamma, __fmaf_rn(sh.n1x, beta, sh.n0x * alpha)),
-                  __fmaf_rn(sh.n2y, gamma, __fmaf_rn(sh.n1y, beta, sh.n0y * alpha)),
-                  __fmaf_rn(sh.n2z, gamma, __fmaf_rn(sh.n1z, beta, sh.n0z * alpha))};
+    if (flags & RX_SD_NORMALS) {  // rasterizer.rs:1083-1099
+        const float4 s3 = __ldg(sq + 3), s4 = __ldg(sq + 4);
+        normal = {__fmaf_rn(s3.w, gamma, __fmaf_rn(s3.x, beta, s2.y * alpha)),
+                  __fmaf_rn(s4.x, gamma, __fmaf_rn(s3.y, beta, s2.z * alpha)),
+                  __fmaf_rn(s4.y, gamma, __fmaf_rn(s3.z, beta, s2.w * alpha))};
         normal = fnormalize3(normal);
         if (fdot3(normal, view_dir) < 0.0f) normal = {-normal.x, -normal.y, -normal.z};
     } else {
@@ -741,30 +790,29 @@ __device__ uint32_t shade_fragment(const SceneDev& S, const DFrame& F, const DLi
     // roughness 0.5, metallic 0 (no batch shader): f0 = 0.04, kd = base * 0.96, shininess = 2/0.25 - 2 = 6
     const float hemi = 0.5f * (normal.y + 1.0f);
     const f3 kd = rx_scale3(base, 1.0f - 0.04f);
-    f3 lit = {0.0f, 0.0f, 0.0f};
-    if (F.has_ambient) lit = {F.ambient[0] * kd.x * hemi, F.ambient[1] * kd.y * hemi, F.ambient[2] * kd.z * hemi};  // :1334-1365
-    lit = {__fmaf_rn(B.ambient[0] * kd.x, hemi, lit.x), __fmaf_rn(B.ambient[1] * kd.y, hemi, lit.y),
-           __fmaf_rn(B.ambient[2] * kd.z, hemi, lit.z)};  // :1368-1370
+    f3 amb = {d1.x, d1.y, d1.z};                                                        // :1368-1370
+    if (F.has_ambient) amb = {amb.x + F.ambient[0], amb.y + F.ambient[1], amb.z + F.ambient[2]};  // :1334-1365
+    f3 lit = {amb.x * kd.x * hemi, amb.y * kd.y * hemi, amb.z * kd.z * hemi};
 
     const float n_dot_v = fmaxf(fdot3(normal, view_dir), 0.0f);
     const float om = 1.0f - fminf(n_dot_v, 1.0f);
-    const float x5 = om * om * om * om * om;
-    const float fr = __fmaf_rn(1.0f - 0.04f, x5, 0.04f);  // schlick_fresnel with f0 = 0.04 (:1882-1887)
+    const float om2 = om * om;
+    const float fr = __fmaf_rn(1.0f - 0.04f, om2 * om2 * om, 0.04f);  // schlick_fresnel with f0 = 0.04 (:1882-1887)
     for (uint32_t li = 0; li < S.n_lights; ++li) {  // rasterizer.rs:1373-1391
         const DLight& L = lights[li];
         const f3 to_l = {L.px - world.x, L.py - world.y, L.pz - world.z};
         const float d2 = fdot3(to_l, to_l);
         const float inv_d = fast_rsqrt(d2);
         const f3 ldir = {to_l.x * inv_d, to_l.y * inv_d, to_l.z * inv_d};
-        f3 radiance;
-        if (!light_radiance_fast(L, normal, ldir, d2 * inv_d, &radiance)) continue;
-        // shade_fast_brdf, rasterizer.rs:1912-1951
         const float n_dot_l = fmaxf(fdot3(normal, ldir), 0.0f);
+        f3 radiance;
+        if (!light_radiance_fast(L, n_dot_l, ldir, d2 * inv_d, &radiance)) continue;
+        // shade_fast_brdf, rasterizer.rs:1912-1951
         if (!(n_dot_l > 0.0f)) continue;
         const f3 h = fnormalize3(rx_add3(ldir, view_dir));
         const float n_dot_h = fmaxf(fdot3(normal, h), 0.0f);
-        const float spec_b = (n_dot_h <= 0.0f) ? 0.0f : fast_ex2(6.0f * fast_lg2(n_dot_h));
-        const float spec = fr * spec_b;
+        const float h2 = n_dot_h * n_dot_h;
+        const float spec = fr * (h2 * h2 * h2);  // pow32_fast(n.h, 6) = exp2(6 log2 x), :1895-1908
         lit = {__fmaf_rn((kd.x + spec) * n_dot_l, radiance.x, lit.x), __fmaf_rn((kd.y + spec) * n_dot_l, radiance.y, lit.y),
                __fmaf_rn((kd.z + spec) * n_dot_l, radiance.z, lit.z)};
     }
@@ -802,8 +850,9 @@ __device__ uint32_t shade_background(const DFrame& F, int px, int py) {
 }
 
 // one 2D triangle fragment: rasterizer.rs:655-895.  `color` is the tile buffer pixel (RGBA8).
-__device__ void shade_2d(const SceneDev& S, const DFrame& F, const DLight* __restrict__ lights, const Tri2D& T, const DBatch2& B,
-                         const DFrameBatch2& FB, int px, int py, float fpx, float fpy, uint32_t* color) {
+__device__ __noinline__ uint32_t shade_2d(const uint8_t* __restrict__ arena, const DTex* __restrict__ texs, uint32_t n_lights,
+                                          const DFrame& F, const DLight* __restrict__ lights, const Tri2D& T, const DBatch2& B,
+                                          const DFrameBatch2& FB, int px, int py, float fpx, float fpy, uint32_t color) {
     // barycentric_weights_2d, rasterizer.rs:1731-1750
     const float acx = T.cx - T.ax, acy = T.cy - T.ay, abx = T.bx - T.ax, aby = T.by - T.ay;
     const float apx = fpx - T.ax, apy = fpy - T.ay, pcx = T.cx - fpx, pcy = T.cy - fpy, pbx = T.bx - fpx, pby = T.by - fpy;
@@ -819,13 +868,13 @@ __device__ void shade_2d(const SceneDev& S, const DFrame& F, const DLight* __res
     const float wx = gx / F.scale2d, wy = gy / F.scale2d;
 
     uint32_t texel = 0u;
-    if (FB.tex != 0xFFFFFFFFu) texel = rx_sample(S.arena, S.tex[FB.tex], u, v, F.sample_mode, B.repeat_mode);
+    if (FB.tex != 0xFFFFFFFFu) texel = rx_sample(arena, texs[FB.tex], u, v, F.sample_mode, B.repeat_mode);
     else if (B.source_kind == RXC_SRC_PIXEL) texel = B.source_pixel;
 
     if (FB.lit) {  // rasterizer.rs:799-873
         float acc[3] = {0.0f, 0.0f, 0.0f};
         if (F.has_ambient) { acc[0] += F.ambient[0] * 1.0f; acc[1] += F.ambient[1] * 1.0f; acc[2] += F.ambient[2] * 1.0f; }
-        for (uint32_t li = 0; li < S.n_lights; ++li) {
+        for (uint32_t li = 0; li < n_lights; ++li) {
             f3 lc;
             if (!rx_light_color_at(lights[li], {wx, 0.0f, wy}, true, &lc)) continue;
             acc[0] += lc.x; acc[1] += lc.y; acc[2] += lc.z;
@@ -840,24 +889,24 @@ __device__ void shade_2d(const SceneDev& S, const DFrame& F, const DLight* __res
         texel = out;
     }
     const uint32_t ta = texel >> 24;  // rasterizer.rs:876-895
-    if (ta == 255u) { *color = texel; return; }
+    if (ta == 255u) return texel;
     const float src_alpha = (float)ta / 255.0f, dst_alpha = 1.0f - src_alpha;
     uint32_t out = 0;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        const float s = (float)((texel >> (8 * i)) & 0xFF), d = (float)((*color >> (8 * i)) & 0xFF);
+        const float s = (float)((texel >> (8 * i)) & 0xFF), d = (float)((color >> (8 * i)) & 0xFF);
         out |= rx_as_u8((s * src_alpha) + (d * dst_alpha)) << (8 * i);
     }
-    const uint32_t da = *color >> 24;
+    const uint32_t da = color >> 24;
     out |= (F.preserve_transparency ? max(da, ta) : 255u) << 24;
-    *color = out;
+    return out;
 }
 
-// Conservative tile-vs-triangle overlap: bbox, then for each edge the tile corner where the edge
-// function is largest.  The per-pixel test is `fl(a*px + b*py + c) < 0 -> outside` (edge.rs:28-36);
+// Conservative rectangle-vs-triangle overlap: bbox, then for each edge the rectangle corner where the
+// edge function is largest.  The per-pixel test is `fl(a*px + b*py + c) < 0 -> outside` (edge.rs:28-36);
 // its rounding error is below 3 * 2^-24 * (|a|*X + |b|*Y + |c|), so a corner value below
-// -2e-6 * (|a|*X + |b|*Y + |c|) proves every pixel centre of the tile fails.  NaNs keep the triangle.
-__device__ __forceinline__ bool tile_overlaps(const TriVis& T, int tx0, int ty0, int tx1, int ty1) {
+// -2e-6 * (|a|*X + |b|*Y + |c|) proves every pixel centre of the rectangle fails.  NaNs keep the triangle.
+__device__ __forceinline__ bool rect_overlaps(const TriVis& T, int tx0, int ty0, int tx1, int ty1) {
     const int x0 = T.bbx & 0xFFFF, x1 = T.bbx >> 16, y0 = T.bby & 0xFFFF, y1 = T.bby >> 16;
     if (x0 >= tx1 || x1 <= tx0 || y0 >= ty1 || y1 <= ty0) return false;
     const float xmin = (float)max(tx0, x0) + 0.5f, xmax = (float)min(tx1, x1) - 0.5f;
@@ -872,65 +921,110 @@ __device__ __forceinline__ bool tile_overlaps(const TriVis& T, int tx0, int ty0,
     return true;
 }
 
-// coverage + depth + alpha test of one triangle at this thread's pixel (rasterizer.rs:1020-1060, :1408)
+// depth + alpha test of one covered pixel (rasterizer.rs:1051-1060, :1408)
 __device__ __forceinline__ void test_fragment(const SceneDev& S, const DFrame& F, const DFrameBatch* __restrict__ fbs,
-                                              const TriShade* __restrict__ shade, const TriVis& T, uint32_t slot, int px, int py,
-                                              float fpx, float fpy, PixelState& ps) {
-    const int x0 = T.bbx & 0xFFFF, x1 = T.bbx >> 16, y0 = T.bby & 0xFFFF, y1 = T.bby >> 16;
-    if (px < x0 || px >= x1 || py < y0 || py >= y1) return;
-    // Edges::evaluate, edge.rs:28-36 (a NaN result passes)
-    if ((T.ea[0] * fpx + T.eb[0] * fpy + T.ec[0]) < 0.0f) return;
-    if ((T.ea[1] * fpx + T.eb[1] * fpy + T.ec[1]) < 0.0f) return;
-    if ((T.ea[2] * fpx + T.eb[2] * fpy + T.ec[2]) < 0.0f) return;
-    // barycentric_weights_3d, rasterizer.rs:1754-1773
-    const float apx = fpx - T.ax, apy = fpy - T.ay;
-    const float pcx = T.cx - fpx, pcy = T.cy - fpy, pbx = T.bx - fpx, pby = T.by - fpy;
-    const float alpha = (pcx * pby - pcy * pbx) / T.area;
-    const float beta = (T.acx * apy - T.acy * apx) / T.area;
+                                              const TriShade* __restrict__ shade, const float4 q0, const float4 q1, const float4 q2,
+                                              uint32_t meta, uint32_t slot, float fpx, float fpy, float& best_z, uint32_t& best,
+                                              float& best_al, float& best_be) {
+    // barycentric_weights_3d, rasterizer.rs:1754-1773 (a = q0.xy, b = q0.zw, c = q1.xy)
+    const float acx = q1.x - q0.x, acy = q1.y - q0.y;
+    const float apx = fpx - q0.x, apy = fpy - q0.y;
+    const float pcx = q1.x - fpx, pcy = q1.y - fpy, pbx = q0.z - fpx, pby = q0.w - fpy;
+    const float na = pcx * pby - pcy * pbx, nb = acx * apy - acy * apx;
+    float alpha, beta;
+    if (meta & RX_META_FASTDIV) { alpha = rx_div_by(na, q2.x, q1.z); beta = rx_div_by(nb, q2.x, q1.z); }
+    else { alpha = na / q2.x; beta = nb / q2.x; }
     const float gamma = 1.0f - alpha - beta;
-    const float one_over_z = T.iz0 * alpha + T.iz1 * beta + T.iz2 * gamma;  // :1054-1056
+    const float one_over_z = q2.y * alpha + q2.z * beta + q2.w * gamma;  // :1054-1056
     const float z = 1.0f / one_over_z;
     // sequential `z < zbuf` in submission order == lexicographic min of (z, ordinal)
-    const bool pass_z = (z < ps.best_z) || (z == ps.best_z && ps.best != RX_OWNER_NONE && slot < ps.best);
+    const bool pass_z = (z < best_z) || (z == best_z && best != RX_OWNER_NONE && slot < best);
     if (!pass_z) return;
-    if (T.meta & 0x80000000u) {  // alpha test: texel alpha must be 255 to write (:1408)
+    if (meta & RX_META_ALPHA) {  // alpha test: texel alpha must be 255 to write (:1408)
         const TriShade& sh = shade[slot];
         const float iu = sh.uw0 * alpha + sh.uw1 * beta + sh.uw2 * gamma;
         const float iv = sh.vw0 * alpha + sh.vw1 * beta + sh.vw2 * gamma;
         const float irw = sh.rw0 * alpha + sh.rw1 * beta + sh.rw2 * gamma;
-        const uint32_t b = T.meta & 0x7FFFFFFFu;
-        const uint32_t texel = rx_sample(S.arena, S.tex[fbs[b].tex], iu / irw, iv / irw, F.sample_mode, S.b3[b].repeat_mode);
+        const DFrameBatch& FB = fbs[meta & RX_META_BATCH];
+        const uint32_t texel = sample_desc(S.arena, FB.sd_tex_word, FB.sd_wh, FB.sd_flags, iu / irw, iv / irw, F.sample_mode);
         if ((texel >> 24) != 255u) return;
     }
-    ps.best_z = z; ps.best = slot; ps.alpha = alpha; ps.beta = beta;
+    best_z = z; best = slot; best_al = alpha; best_be = beta;
 }
 
-#define RX_LARGE_CACHE 160   // large-triangle records kept in shared memory across the tiles of a frame
+// coverage of one staged triangle over the thread's 2x2 pixels (rasterizer.rs:1020-1036), then the
+// depth test of the covered ones.  `valid` masks pixels outside the frame.
+__device__ __forceinline__ void process_record(const SceneDev& S, const DFrame& F, const DFrameBatch* __restrict__ fbs,
+                                               const TriShade* __restrict__ shade, const TriVis* Tp, uint32_t slot, int px0, int py0,
+                                               float fx0, float fy0, uint32_t valid, Vis4& V) {
+    const float4* q = reinterpret_cast<const float4*>(Tp);
+    const float4 q5 = q[5];
+    const uint32_t bbx = __float_as_uint(q5.y), bby = __float_as_uint(q5.z), meta = __float_as_uint(q5.w);
+    const int x0 = (int)(bbx & 0xFFFFu), x1 = (int)(bbx >> 16), y0 = (int)(bby & 0xFFFFu), y1 = (int)(bby >> 16);
+    const bool cx0 = px0 >= x0 && px0 < x1, cx1 = px0 + 8 >= x0 && px0 + 8 < x1;
+    const bool cy0 = py0 >= y0 && py0 < y1, cy1 = py0 + 4 >= y0 && py0 + 4 < y1;
+    uint32_t m = ((cx0 && cy0) ? 1u : 0u) | ((cx1 && cy0) ? 2u : 0u) | ((cx0 && cy1) ? 4u : 0u) | ((cx1 && cy1) ? 8u : 0u);
+    m &= valid;
+    if (!m) return;
+    const float4 q3 = q[3], q4 = q[4];
+    const float fx1 = fx0 + 8.0f, fy1 = fy0 + 4.0f;
+    {   // Edges::evaluate, edge.rs:28-36: (a*px + b*py) + c < 0 -> outside (a NaN result passes)
+        const float ea[3] = {q3.x, q3.y, q3.z}, eb[3] = {q3.w, q4.x, q4.y}, ec[3] = {q4.z, q4.w, q5.x};
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float ax0 = ea[i] * fx0, ax1 = ea[i] * fx1, by0 = eb[i] * fy0, by1 = eb[i] * fy1;
+            if ((ax0 + by0) + ec[i] < 0.0f) m &= ~1u;
+            if ((ax1 + by0) + ec[i] < 0.0f) m &= ~2u;
+            if ((ax0 + by1) + ec[i] < 0.0f) m &= ~4u;
+            if ((ax1 + by1) + ec[i] < 0.0f) m &= ~8u;
+        }
+    }
+    if (!m) return;
+    const float4 q0 = q[0], q1 = q[1], q2 = q[2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (m & (1u << k))
+            test_fragment(S, F, fbs, shade, q0, q1, q2, meta, slot, (k & 1) ? fx1 : fx0, (k & 2) ? fy1 : fy0, V.z[k], V.own[k], V.al[k],
+                          V.be[k]);
+    }
+}
 
-__global__ void __launch_bounds__(RX_TILE_THREADS) k_raster(SceneDev S, Workspace Wk, RasterOut out, uint32_t n_frames,
-                                                             uint32_t tiles_per_frame) {
+__global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raster(SceneDev S, Workspace Wk, RasterOut out, uint32_t n_frames,
+                                                               uint32_t tiles_per_frame) {
     __shared__ __align__(16) TriVis s_large[RX_LARGE_CACHE];
     __shared__ uint32_t s_large_slot[RX_LARGE_CACHE];
     __shared__ __align__(16) TriVis s_tri[RX_STAGE];
     __shared__ uint32_t s_slot[RX_STAGE];
-    __shared__ uint16_t s_sel[RX_LARGE_CACHE > RX_STAGE ? RX_LARGE_CACHE : RX_STAGE];
+    __shared__ uint16_t s_sel[RX_LARGE_CACHE];
     __shared__ uint32_t s_nsel;
-    __shared__ uint32_t s_work;
-    __shared__ __align__(16) uint32_t s_color[RX_TILE_THREADS];
+    __shared__ int32_t s_work[4];   // frame (-1 = done), tile x0, tile y0
+    __shared__ __align__(16) uint32_t s_color[RX_TILE_H * RX_COLOR_STRIDE];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // warp w covers an 8x4 pixel block; 2 blocks across, 4 down
-    const int bx = (int)(warp & 1) * 8, by = (int)(warp >> 1) * 4;
+    // warp w covers a 16x8 region (2 across, 4 down); lane (lx, ly) of the 8x4 lane grid owns the
+    // pixels (lx + 8i, ly + 4j) of the region
+    const int rbx = (int)(warp & 1) * RX_REGION_W, rby = (int)(warp >> 1) * RX_REGION_H;
     const int lx = (int)(lane & 7), ly = (int)(lane >> 3);
     const uint32_t total = n_frames * tiles_per_frame;
     uint32_t cached_frame = 0xFFFFFFFFu, n_cached = 0;
 
     for (;;) {
-        if (tid == 0) { s_work = atomicAdd(Wk.raster_counter, 1u); s_nsel = 0u; }
+        if (tid == 0) {
+            const uint32_t work = atomicAdd(Wk.raster_counter, 1u);
+            if (work >= total) {
+                s_work[0] = -1;
+            } else {
+                const uint32_t f = work / tiles_per_frame, tile = work - f * tiles_per_frame;
+                const uint32_t tiles_x = (uint32_t)Wk.frames[f].tiles_x;
+                const uint32_t ty = tile / tiles_x;
+                s_work[0] = (int32_t)f; s_work[1] = (int32_t)((tile - ty * tiles_x) * RX_TILE_W); s_work[2] = (int32_t)(ty * RX_TILE_H);
+                s_work[3] = (int32_t)tile;
+            }
+            s_nsel = 0u;
+        }
         __syncthreads();
-        const uint32_t work = s_work;
-        if (work >= total) break;
-        const uint32_t f = work / tiles_per_frame, tile = work - f * tiles_per_frame;
+        if (s_work[0] < 0) break;
+        const uint32_t f = (uint32_t)s_work[0], tile = (uint32_t)s_work[3];
         const DFrame& F = Wk.frames[f];
         const DCounters& C = Wk.counters[f];
         const DLight* lights = Wk.lights + (size_t)f * Wk.lights_stride;
@@ -938,46 +1032,54 @@ __global__ void __launch_bounds__(RX_TILE_THREADS) k_raster(SceneDev S, Workspac
         const TriShade* shade = Wk.shade + (size_t)f * Wk.slot_stride;
         const DFrameBatch* fbs = Wk.fb + (size_t)f * Wk.fb_stride;
 
-        const int tx0 = (int)(tile % (uint32_t)F.tiles_x) * RX_TILE_W;
-        const int ty0 = F.band_y0 + (int)(tile / (uint32_t)F.tiles_x) * RX_TILE_H;
-        const int tx1 = min(tx0 + RX_TILE_W, F.width), ty1 = min(ty0 + RX_TILE_H, F.band_y1);
-        const int wx0 = tx0 + bx, wy0 = ty0 + by, wx1 = wx0 + 8, wy1 = wy0 + 4;
-        const int px = wx0 + lx, py = wy0 + ly;
-        const float fpx = (float)px + 0.5f, fpy = (float)py + 0.5f;  // rasterizer.rs:1022
-        const bool in_frame = px < F.width && py < F.band_y1;
+        const int fw = F.width, fy1 = F.band_y1;
+        const int tx0 = s_work[1], ty0 = F.band_y0 + s_work[2];
+        const int tx1 = min(tx0 + RX_TILE_W, fw), ty1 = min(ty0 + RX_TILE_H, fy1);
+        const int rx0 = tx0 + rbx, ry0 = ty0 + rby, rx1 = min(rx0 + RX_REGION_W, fw), ry1 = min(ry0 + RX_REGION_H, fy1);
+        const bool region_ok = rx0 < rx1 && ry0 < ry1;
+        const int px0 = rx0 + lx, py0 = ry0 + ly;
+        const float fx0 = (float)px0 + 0.5f, fy0 = (float)py0 + 0.5f;  // rasterizer.rs:1022
+        const uint32_t valid = ((px0 < fw && py0 < fy1) ? 1u : 0u) | ((px0 + 8 < fw && py0 < fy1) ? 2u : 0u) |
+                               ((px0 < fw && py0 + 4 < fy1) ? 4u : 0u) | ((px0 + 8 < fw && py0 + 4 < fy1) ? 8u : 0u);
 
-        PixelState ps = {1.0f, RX_OWNER_NONE, 0.0f, 0.0f};  // z_buffer starts at 1.0 (rasterizer.rs:287)
+        Vis4 V;  // z_buffer starts at 1.0 (rasterizer.rs:287)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { V.z[k] = 1.0f; V.own[k] = RX_OWNER_NONE; V.al[k] = 0.0f; V.be[k] = 0.0f; }
 
         if (F.d3_active) {
             const uint32_t n_large = min(C.n_large, Wk.large_stride);
             const uint32_t* large = Wk.large + (size_t)f * Wk.large_stride;
-            // (1) large triangles: records cached in shared memory per frame, culled per tile
+            // (1) large triangles: records cached in shared memory per frame, culled per tile, then per warp region
             if (f != cached_frame) {
                 n_cached = min(n_large, (uint32_t)RX_LARGE_CACHE);
-                for (uint32_t i = tid; i < n_cached; i += RX_TILE_THREADS) s_large_slot[i] = large[i];
-                __syncthreads();
                 const float4* g = reinterpret_cast<const float4*>(vis);
                 float4* s = reinterpret_cast<float4*>(s_large);
                 for (uint32_t i = tid; i < n_cached * 6u; i += RX_TILE_THREADS) {
                     const uint32_t r = i / 6u, q = i - r * 6u;
-                    s[i] = __ldg(g + (size_t)s_large_slot[r] * 6u + q);
+                    const uint32_t slot = __ldg(large + r);
+                    if (q == 0) s_large_slot[r] = slot;
+                    s[i] = __ldg(g + (size_t)slot * 6u + q);
                 }
                 cached_frame = f;
                 __syncthreads();
             }
-            if (tid < n_cached && tile_overlaps(s_large[tid], tx0, ty0, tx1, ty1)) s_sel[atomicAdd(&s_nsel, 1u)] = (uint16_t)tid;
+            if (tid < n_cached && rect_overlaps(s_large[tid], tx0, ty0, tx1, ty1)) s_sel[atomicAdd(&s_nsel, 1u)] = (uint16_t)tid;
             __syncthreads();
             {
                 const uint32_t n = s_nsel;
-                for (uint32_t k = 0; k < n; ++k) {
-                    const uint32_t r = s_sel[k];
-                    const TriVis& T = s_large[r];
-                    const int x0 = T.bbx & 0xFFFF, x1 = T.bbx >> 16, y0 = T.bby & 0xFFFF, y1 = T.bby >> 16;
-                    if (x0 >= wx1 || x1 <= wx0 || y0 >= wy1 || y1 <= wy0) continue;  // warp-uniform
-                    test_fragment(S, F, fbs, shade, T, s_large_slot[r], px, py, fpx, fpy, ps);
+                for (uint32_t base = 0; base < n; base += 32) {
+                    const uint32_t i = base + lane;
+                    const uint32_t r = i < n ? (uint32_t)s_sel[i] : 0u;
+                    uint32_t mask = __ballot_sync(0xFFFFFFFFu, i < n && region_ok && rect_overlaps(s_large[r], rx0, ry0, rx1, ry1));
+                    while (mask) {
+                        const int b = __ffs(mask) - 1;
+                        mask &= mask - 1u;
+                        const uint32_t rr = __shfl_sync(0xFFFFFFFFu, r, b);
+                        process_record(S, F, fbs, shade, &s_large[rr], s_large_slot[rr], px0, py0, fx0, fy0, valid, V);
+                    }
                 }
             }
-            // (2) the rest of the large list, then the tile's binned list: staged in chunks, culled, walked
+            // (2) the rest of the large list, then the tile's binned list: staged in chunks, culled per warp region
             const uint32_t n_list = Wk.tile_count[(size_t)f * Wk.tile_stride + tile];
             const uint32_t* list = Wk.lists + (size_t)f * Wk.list_stride + Wk.tile_base[(size_t)f * Wk.tile_stride + tile];
             for (int pass = 0; pass < 2; ++pass) {
@@ -985,90 +1087,168 @@ __global__ void __launch_bounds__(RX_TILE_THREADS) k_raster(SceneDev S, Workspac
                 const uint32_t n_src = pass == 0 ? n_large - n_cached : n_list;
                 for (uint32_t base = 0; base < n_src; base += RX_STAGE) {
                     const uint32_t n = min((uint32_t)RX_STAGE, n_src - base);
-                    __syncthreads();  // previous stage and selection fully consumed
-                    if (tid < n) s_slot[tid] = src[base + tid];
-                    if (tid == 0) s_nsel = 0u;
-                    __syncthreads();
+                    __syncthreads();  // previous stage fully consumed
                     {   // stage the records: 6 x 16 B each
                         const float4* g = reinterpret_cast<const float4*>(vis);
                         float4* s = reinterpret_cast<float4*>(s_tri);
                         for (uint32_t i = tid; i < n * 6u; i += RX_TILE_THREADS) {
                             const uint32_t r = i / 6u, q = i - r * 6u;
-                            s[i] = __ldg(g + (size_t)s_slot[r] * 6u + q);
+                            const uint32_t slot = __ldg(src + base + r);
+                            if (q == 0) s_slot[r] = slot;
+                            s[i] = __ldg(g + (size_t)slot * 6u + q);
                         }
                     }
                     __syncthreads();
-                    if (tid < n && tile_overlaps(s_tri[tid], tx0, ty0, tx1, ty1)) s_sel[atomicAdd(&s_nsel, 1u)] = (uint16_t)tid;
-                    __syncthreads();
-                    const uint32_t nk = s_nsel;
-                    for (uint32_t k = 0; k < nk; ++k) {
-                        const uint32_t r = s_sel[k];
-                        const TriVis& T = s_tri[r];
-                        const int x0 = T.bbx & 0xFFFF, x1 = T.bbx >> 16, y0 = T.bby & 0xFFFF, y1 = T.bby >> 16;
-                        if (x0 >= wx1 || x1 <= wx0 || y0 >= wy1 || y1 <= wy0) continue;  // warp-uniform
-                        test_fragment(S, F, fbs, shade, T, s_slot[r], px, py, fpx, fpy, ps);
+#pragma unroll 1
+                    for (uint32_t h = 0; h < RX_STAGE; h += 32) {
+                        const uint32_t i = h + lane;
+                        uint32_t mask = __ballot_sync(0xFFFFFFFFu, i < n && region_ok && rect_overlaps(s_tri[i], rx0, ry0, rx1, ry1));
+                        while (mask) {
+                            const uint32_t rr = h + (uint32_t)(__ffs(mask) - 1);
+                            mask &= mask - 1u;
+                            process_record(S, F, fbs, shade, &s_tri[rr], s_slot[rr], px0, py0, fx0, fy0, valid, V);
+                        }
                     }
                 }
             }
         }
 
-        // resolve: deferred shade of the owner, miss pass (rasterizer.rs:409-461), or the 2D-only background
-        uint32_t color;
-        if (F.d3_active) {
-            if (ps.best != RX_OWNER_NONE) {
-                const TriVis& T = vis[ps.best];
-                const TriShade sh = shade[ps.best];
-                const uint32_t b = T.meta & 0x7FFFFFFFu;
-                const float alpha = ps.alpha, beta = ps.beta, gamma = 1.0f - alpha - beta;
-                const float iu = sh.uw0 * alpha + sh.uw1 * beta + sh.uw2 * gamma;  // rasterizer.rs:1062-1076
-                const float iv = sh.vw0 * alpha + sh.vw1 * beta + sh.vw2 * gamma;
-                const float irw = sh.rw0 * alpha + sh.rw1 * beta + sh.rw2 * gamma;
-                color = shade_fragment(S, F, lights, S.b3[b], fbs[b], sh, alpha, beta, gamma, ps.best_z, fpx, fpy, iu / irw, iv / irw);
+        // resolve, one pixel of the 2x2 at a time (the state rotates so the body always reads element 0):
+        // deferred shade of the owner, miss pass (rasterizer.rs:409-461) or the 2D-only background, 2D pass
+        const Tri2D* recs = Wk.tri2d + (size_t)f * Wk.tri2d_stride;
+        const DFrameBatch2* fb2 = Wk.fb2 + (size_t)f * Wk.fb2_stride;
+        // 2D records whose bbox meets this warp's region: one ballot per 32 records, hoisted for the first 32
+        uint32_t mask2d = 0u;
+        if (F.d2_active) {
+            bool hit = false;
+            if (lane < S.n_rec2d && region_ok) {
+                const uint32_t bbx = recs[lane].bbx, bby = recs[lane].bby;
+                const int x0 = bbx & 0xFFFF, x1 = bbx >> 16, y0 = bby & 0xFFFF, y1 = bby >> 16;
+                hit = !(x0 >= rx1 || x1 <= rx0 || y0 >= ry1 || y1 <= ry0);
+            }
+            mask2d = __ballot_sync(0xFFFFFFFFu, hit);
+        }
+        const bool more2d = F.d2_active && S.n_rec2d > 32u;
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+            const int px = px0 + ((k & 1) << 3), py = py0 + ((k >> 1) << 2);
+            const float fpx = (float)px + 0.5f, fpy = (float)py + 0.5f;
+            const bool in_frame = px < fw && py < fy1;
+            uint32_t color;
+            if (F.d3_active) {
+                if (V.own[0] != RX_OWNER_NONE) {
+                    const uint32_t b = __ldg(&vis[V.own[0]].meta) & RX_META_BATCH;
+                    color = shade_owner(S, F, lights, fbs[b], shade + V.own[0], V.al[0], V.be[0], V.z[0], fpx, fpy);
+                } else {
+                    color = 0xFF000000u;  // vec4_to_pixel((0,0,0,1))
+                }
             } else {
-                color = 0xFF000000u;  // vec4_to_pixel((0,0,0,1))
+                color = F.has_bg_color ? F.bg_color : 0u;  // rasterizer.rs:277-282
+                if (!F.ignore_bg_shader && F.bg_shader != RXC_BG_NONE) color = shade_background(F, px, py);
             }
-        } else {
-            color = F.has_bg_color ? F.bg_color : 0u;  // rasterizer.rs:277-282
-            if (!F.ignore_bg_shader && F.bg_shader != RXC_BG_NONE) color = shade_background(F, px, py);
-        }
-
-        if (F.d2_active) {  // rasterizer.rs:501-553: every 2D record in submission order
-            const Tri2D* recs = Wk.tri2d + (size_t)f * Wk.tri2d_stride;
-            for (uint32_t r = 0; r < S.n_rec2d; ++r) {
-                const Tri2D& T = recs[r];
-                const int x0 = T.bbx & 0xFFFF, x1 = T.bbx >> 16, y0 = T.bby & 0xFFFF, y1 = T.bby >> 16;
-                if (x0 >= wx1 || x1 <= wx0 || y0 >= wy1 || y1 <= wy0) continue;
-                if (px < x0 || px >= x1 || py < y0 || py >= y1) continue;
-                if ((T.ea[0] * fpx + T.eb[0] * fpy + T.ec[0]) < 0.0f) continue;
-                if ((T.ea[1] * fpx + T.eb[1] * fpy + T.ec[1]) < 0.0f) continue;
-                if ((T.ea[2] * fpx + T.eb[2] * fpy + T.ec[2]) < 0.0f) continue;
-                shade_2d(S, F, lights, T, S.b2[T.batch], Wk.fb2[(size_t)f * Wk.fb2_stride + T.batch], px, py, fpx, fpy, &color);
+            if (mask2d | (uint32_t)more2d) {  // rasterizer.rs:501-553: every 2D record in submission order
+                for (uint32_t base = 0; base < S.n_rec2d; base += 32) {
+                    uint32_t mk = mask2d;
+                    if (base) {
+                        bool hit = false;
+                        if (base + lane < S.n_rec2d && region_ok) {
+                            const uint32_t bbx = recs[base + lane].bbx, bby = recs[base + lane].bby;
+                            const int x0 = bbx & 0xFFFF, x1 = bbx >> 16, y0 = bby & 0xFFFF, y1 = bby >> 16;
+                            hit = !(x0 >= rx1 || x1 <= rx0 || y0 >= ry1 || y1 <= ry0);
+                        }
+                        mk = __ballot_sync(0xFFFFFFFFu, hit);
+                    }
+                    while (mk) {
+                        const Tri2D& T = recs[base + (uint32_t)(__ffs(mk) - 1)];
+                        mk &= mk - 1u;
+                        const int x0 = T.bbx & 0xFFFF, x1 = T.bbx >> 16, y0 = T.bby & 0xFFFF, y1 = T.bby >> 16;
+                        if (px < x0 || px >= x1 || py < y0 || py >= y1) continue;
+                        if ((T.ea[0] * fpx + T.eb[0] * fpy + T.ec[0]) < 0.0f) continue;
+                        if ((T.ea[1] * fpx + T.eb[1] * fpy + T.ec[1]) < 0.0f) continue;
+                        if ((T.ea[2] * fpx + T.eb[2] * fpy + T.ec[2]) < 0.0f) continue;
+                        color = shade_2d(S.arena, S.tex, S.n_lights, F, lights, T, S.b2[T.batch], fb2[T.batch], px, py, fpx, fpy, color);
+                    }
+                }
             }
-        }
-
-        // write back: RGBA8 rows of the tile, 128-bit stores when rows are 16 B aligned
-        const int row = by + ly, col = bx + lx;
-        s_color[row * RX_TILE_W + col] = color;
-        if (in_frame) {
-            const size_t o = (size_t)(py - F.band_y0) * (size_t)F.width + (size_t)px;
-            if (out.owner) out.owner[o] = ps.best;
-            if (out.depth) out.depth[o] = ps.best_z;
+            s_color[(py - ty0) * RX_COLOR_STRIDE + (px - tx0)] = color;
+            if (in_frame) {
+                const size_t o = (size_t)(py - F.band_y0) * (size_t)fw + (size_t)px;
+                if (out.owner) out.owner[o] = V.own[0];
+                if (out.depth) out.depth[o] = V.z[0];
+            }
+            {   // rotate the per-pixel state
+                const float z0 = V.z[0], a0 = V.al[0], b0 = V.be[0];
+                const uint32_t o0 = V.own[0];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { V.z[j] = V.z[j + 1]; V.own[j] = V.own[j + 1]; V.al[j] = V.al[j + 1]; V.be[j] = V.be[j + 1]; }
+                V.z[3] = z0; V.own[3] = o0; V.al[3] = a0; V.be[3] = b0;
+            }
         }
         __syncthreads();
+
+        // write back: RGBA8 rows of the tile, 128-bit stores when rows are 16 B aligned
         uint8_t* frame_px = out.pixels + (size_t)f * out.frame_stride;
-        const bool full_tile = (tx0 + RX_TILE_W <= F.width) && (ty0 + RX_TILE_H <= F.band_y1);
+        const bool full_tile = (tx0 + RX_TILE_W <= fw) && (ty0 + RX_TILE_H <= fy1);
         if (out.vec_store && full_tile) {
-            if (tid < RX_TILE_THREADS / 4) {
-                const int r = (int)tid >> 2, c4 = (int)tid & 3;
-                const uint4 v = reinterpret_cast<const uint4*>(s_color)[tid];
-                uint4* dst = reinterpret_cast<uint4*>(frame_px + ((size_t)(ty0 - F.band_y0 + r) * (size_t)F.width + (size_t)tx0) * 4) + c4;
-                *dst = v;
+            const int r = (int)tid >> 3, c4 = (int)tid & 7;   // 8 x 16 B per 32-pixel row
+            const uint4 v = *reinterpret_cast<const uint4*>(&s_color[r * RX_COLOR_STRIDE + c4 * 4]);
+            uint4* dst = reinterpret_cast<uint4*>(frame_px + ((size_t)(ty0 - F.band_y0 + r) * (size_t)fw + (size_t)tx0) * 4) + c4;
+            *dst = v;
+        } else {
+            for (int i = (int)tid; i < RX_TILE_W * RX_TILE_H; i += RX_TILE_THREADS) {
+                const int r = i >> 5, c = i & 31;
+                if (tx0 + c < fw && ty0 + r < fy1)
+                    reinterpret_cast<uint32_t*>(frame_px)[(size_t)(ty0 - F.band_y0 + r) * (size_t)fw + (size_t)(tx0 + c)] =
+                        s_color[r * RX_COLOR_STRIDE + c];
             }
-        } else if (in_frame) {
-            reinterpret_cast<uint32_t*>(frame_px)[(size_t)(py - F.band_y0) * (size_t)F.width + (size_t)px] = color;
         }
         __syncthreads();  // s_color, s_work and s_nsel are rewritten by the next tile
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_selftest_div : rx_div_by against div.rn over the operand ranges make_tri admits
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t& x) {
+    uint64_t z = (x += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ float make_float(uint32_t sign, int exp2, uint32_t mant23) {
+    return __uint_as_float((sign << 31) | ((uint32_t)(exp2 + 127) << 23) | (mant23 & 0x7FFFFFu));
+}
+__global__ void __launch_bounds__(256) k_selftest_div(uint64_t seed, uint32_t iters, unsigned long long* mismatches) {
+    uint64_t st = seed ^ ((uint64_t)(blockIdx.x * blockDim.x + threadIdx.x) * 0xD1342543DE82EF95ull);
+    uint32_t bad = 0;
+    for (uint32_t it = 0; it < iters; ++it) {
+        const uint64_t r0 = splitmix64(st), r1 = splitmix64(st);
+        // divisor: |b| in [2^-20, 2^44), mantissa random or one of the hard patterns
+        uint32_t mb = (uint32_t)r0 & 0x7FFFFFu;
+        const uint32_t pat = (uint32_t)(r0 >> 23) & 7u;
+        if (pat == 0) mb = 0x7FFFFFu; else if (pat == 1) mb = 0u; else if (pat == 2) mb = 0x7FFFFEu; else if (pat == 3) mb = 1u;
+        const float b = make_float((uint32_t)(r0 >> 26) & 1u, -20 + (int)((r0 >> 27) % 64u), mb);
+        const float rb = 1.0f / b;
+        float a;
+        const uint32_t kind = (uint32_t)(r1 >> 60);
+        if (kind == 0) {
+            a = 0.0f;
+        } else if (kind < 6) {   // independent numerator, |a| in [2^-80, 2^62)
+            a = make_float((uint32_t)(r1 >> 23) & 1u, -80 + (int)((r1 >> 24) % 142u), (uint32_t)r1);
+        } else {                 // quotient near a representable value or near a rounding midpoint
+            const float q = make_float((uint32_t)(r1 >> 23) & 1u, -30 + (int)((r1 >> 24) % 48u), (uint32_t)r1);
+            const float qh = __uint_as_float(__float_as_uint(q) + 1u);
+            a = (kind < 11) ? q * b : (float)(((double)q + (double)qh) * 0.5 * (double)b);
+            a = __uint_as_float(__float_as_uint(a) + (((uint32_t)(r1 >> 40) % 5u)) - 2u);
+            if (!(fabsf(a) >= 8.271806125530277e-25f && fabsf(a) < 4.611686018427388e18f)) a = 0.0f;
+        }
+        const float want = __fdiv_rn(a, b), got = rx_div_by(a, b, rb);
+        if (__float_as_uint(want) != __float_as_uint(got) && !(want == 0.0f && got == 0.0f)) {
+            ++bad;
+            mismatches[1] = ((unsigned long long)__float_as_uint(a) << 32) | __float_as_uint(b);  // any failing pair
+        }
+    }
+    if (bad) atomicAdd(mismatches, (unsigned long long)bad);
 }
 
 }  // namespace
@@ -1127,4 +1307,8 @@ int rxk_raster_blocks_per_sm() {
     int n = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_raster, RX_TILE_THREADS, 0) != cudaSuccess || n < 1) n = 1;
     return n;
+}
+cudaError_t rxk_selftest_div(uint64_t seed, uint32_t blocks, uint32_t iters, unsigned long long* d_mismatches, cudaStream_t st) {
+    k_selftest_div<<<blocks, 256, 0, st>>>(seed, iters, d_mismatches);
+    return cudaGetLastError();
 }

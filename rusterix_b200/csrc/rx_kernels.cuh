@@ -83,3 +83,5 @@ cudaError_t rxk_bin_fill(const SceneDev& S, const Workspace& W, uint32_t n_frame
 cudaError_t rxk_raster(const SceneDev& S, const Workspace& W, const RasterOut& out, uint32_t n_frames, uint32_t tiles_per_frame,
                        int grid, cudaStream_t st);
 int rxk_raster_blocks_per_sm();
+// diagnostics: rx_div_by vs div.rn on blocks*256*iters random operand pairs; adds the mismatch count
+cudaError_t rxk_selftest_div(uint64_t seed, uint32_t blocks, uint32_t iters, unsigned long long* d_mismatches, cudaStream_t st);

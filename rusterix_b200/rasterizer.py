@@ -68,6 +68,14 @@ class DeviceContext:
             self.check(self.lib.rxc_set_lights(self.handle, m.struct, len(lights)))
             self._lights_key = lkey
 
+    def selftest_div(self, n_pairs=1 << 30, seed=0x52555354) -> int:
+        """Mismatches of the raster kernel's residual-corrected division against div.rn (must be 0)."""
+        bad = C.c_uint64(0)
+        pair = (C.c_uint32 * 2)()
+        self.check(self.lib.rxc_selftest_div(self.handle, C.c_uint64(seed), C.c_uint64(n_pairs), C.byref(bad), pair))
+        self.last_bad_pair = (int(pair[0]), int(pair[1]))
+        return int(bad.value)
+
     def stats(self) -> _abi.rxc_stats:
         s = _abi.rxc_stats()
         self.check(self.lib.rxc_get_stats(self.handle, C.byref(s)))

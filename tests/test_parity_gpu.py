@@ -210,3 +210,13 @@ def test_errors_do_not_unwind():
     with pytest.raises(ValueError):  # the reference panics on a short slice (src/rasterizer.rs:572)
         cfg.rasterizer().rasterize(cfg.scene, np.zeros(10, np.uint8), 64, 64, 40, cfg.assets)
     render_gpu(cfg.rasterizer(), cfg.scene, cfg.assets, 64, 64, 40)  # the context is still usable
+
+
+def test_fast_division_is_bit_exact():
+    """The barycentric divisions use a residual-corrected multiply by RN(1/area) (rx_div_by) where
+    the reference divides (rasterizer.rs:1768-1769); over the admitted operand ranges it must give
+    the bits of div.rn.  2^32 operand pairs incl. hard mantissas and midpoint quotients."""
+    from rusterix_b200 import DeviceContext
+
+    assert DeviceContext.get(0).selftest_div(n_pairs=1 << 32) == 0
+    assert DeviceContext.get(0).selftest_div(n_pairs=1 << 30, seed=12345) == 0

@@ -30,7 +30,7 @@ def disasm_lines(kernel):
         if m:
             cur = (os.path.basename(m.group(1)), int(m.group(2)))
             continue
-        if re.match(r"\s+/\*[0-9a-f]{4}\*/", line):
+        if re.match(r"\s+/\*[0-9a-f]{4,}\*/", line):
             out.append(cur)
     return out
 
