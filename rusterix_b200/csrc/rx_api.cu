@@ -387,7 +387,9 @@ int32_t launch_group(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n, uint8_t*
     out.vec_store = (((uintptr_t)d_pixels & 15) == 0 && (stride & 15) == 0 && ((ctx->h_frames[0].width * 4) & 15) == 0) ? 1u : 0u;
     const size_t total_tiles = (size_t)n * tiles_per_frame;
     const int grid = (int)std::max<size_t>(1, std::min<size_t>(total_tiles, (size_t)ctx->sm_count * ctx->raster_blocks_per_sm));
-    { LaunchScope l(ctx, RXK_RASTER); CK(rxk_raster(S, ctx->W, out, n, tiles_per_frame, grid, ctx->stream)); }
+    int sample_mode = (int)ctx->h_frames[0].sample_mode;
+    for (uint32_t i = 1; i < n; ++i) if ((int)ctx->h_frames[i].sample_mode != sample_mode) sample_mode = 2;
+    { LaunchScope l(ctx, RXK_RASTER); CK(rxk_raster(S, ctx->W, out, n, tiles_per_frame, sample_mode, grid, ctx->stream)); }
     CK(cudaMemcpyAsync(ctx->h_counters, ctx->W.counters, n * sizeof(DCounters), cudaMemcpyDeviceToHost, ctx->stream));
     ctx->stats.frames += n;
     return RXC_OK;

@@ -286,6 +286,14 @@ __device__ __forceinline__ int rx_sat_int(float x, int limit) {
     if (x >= (float)limit) return limit;
     return (int)x;
 }
+// `x.round() as usize` clamped to [0, limit] for x >= 0 or NaN (texture.rs:311-312; u and v are wrapped or
+// clamped to [0, 1] before): round half away from zero == floor + (frac >= 0.5); the saturating
+// cvt.rzi maps NaN to 0 like `as usize`.
+__device__ __forceinline__ int rx_round_index(float x, int limit) {
+    float r = floorf(x);
+    if (x - r >= 0.5f) r += 1.0f;
+    return min(max(__float2int_rz(r), 0), limit);
+}
 __device__ __forceinline__ uint32_t rx_as_u32(float x) {
     if (!(x == x)) return 0u;
     if (x <= 0.0f) return 0u;
@@ -300,7 +308,7 @@ __device__ __forceinline__ uint32_t rx_as_u8(float x) {
 }
 __device__ __forceinline__ uint32_t rx_f32_to_u8_saturated(float x) {  // lib.rs:65-68
     float y = __fmaf_rn(fminf(fmaxf(x, 0.0f), 1.0f), 255.0f, 0.5f);
-    return ((uint32_t)(int)y) & 0xFFu;  // y is in [0.5, 255.5]
+    return (uint32_t)__float2int_rz(y);  // y is in [0.5, 255.5]; a NaN x became 0 in fmaxf
 }
 
 __device__ __forceinline__ float rx_dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
@@ -323,8 +331,8 @@ __device__ __forceinline__ uint32_t rx_sample_tex(const uint32_t* __restrict__ t
     u = rx_wrap(u, repeat_x);
     v = rx_wrap(v, repeat_y);
     if (sample_mode == RXC_SAMPLE_NEAREST) {
-        int tx = rx_sat_int(roundf(u * ((float)W - 1.0f)), W - 1);
-        int ty = rx_sat_int(roundf(v * ((float)H - 1.0f)), H - 1);
+        int tx = rx_round_index(u * ((float)W - 1.0f), W - 1);
+        int ty = rx_round_index(v * ((float)H - 1.0f), H - 1);
         return __ldg(tex + ty * W + tx);
     }
     float x = u * ((float)W - 1.0f);

@@ -652,7 +652,7 @@ __global__ void __launch_bounds__(256) k_bin_fill(SceneDev S, Workspace Wk) {
 // k_raster
 // ---------------------------------------------------------------------------------------------
 #ifndef RX_RASTER_MIN_BLOCKS
-#define RX_RASTER_MIN_BLOCKS 3  // resident CTAs per SM the register allocation is bounded for
+#define RX_RASTER_MIN_BLOCKS 4  // resident CTAs per SM the register allocation is bounded for
 #endif
 #define RX_STAGE 64          // triangle records staged in shared memory per step
 #define RX_LARGE_CACHE 160   // large-triangle records kept in shared memory across the tiles of a frame
@@ -669,9 +669,9 @@ struct Vis4 {
 // Everything below feeds only the final RGBA8 of a pixel whose owner is already decided (coverage,
 // depth and the alpha test are exact).  The parity bar for colour is +-1 LSB, so shading uses the
 // SFU approximations (rsqrt/rcp/sqrt, <= 2 ulp) and explicit FMAs.
-__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float fast_rsqrt(float x) { float r; asm("rsqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float fdot3(f3 a, f3 b) { return __fmaf_rn(a.x, b.x, __fmaf_rn(a.y, b.y, a.z * b.z)); }
 __device__ __forceinline__ f3 fnormalize3(f3 a) { const float i = fast_rsqrt(fdot3(a, a)); return {a.x * i, a.y * i, a.z * i}; }
 // smoothstep(end, start, x) with inv_range = 1/(start - end)  (light.rs:674-677)
@@ -739,7 +739,7 @@ __device__ __forceinline__ uint32_t sample_desc(const uint8_t* __restrict__ aren
 // rasterizer.rs:1062-1404 + :1875-1951 for the owning fragment of a pixel; returns RGBA8.
 __device__ __forceinline__ uint32_t shade_owner(const SceneDev& S, const DFrame& F, const DLight* __restrict__ lights,
                                                 const DFrameBatch& FB, const TriShade* __restrict__ shp, float alpha, float beta,
-                                                float z, float fpx, float fpy) {
+                                                float z, float fpx, float fpy, uint32_t sample_mode) {
     const float4* sq = reinterpret_cast<const float4*>(shp);
     const float4 s0 = __ldg(sq), s1 = __ldg(sq + 1), s2 = __ldg(sq + 2);
     const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(&FB.sd_tex_word));
@@ -758,7 +758,7 @@ __device__ __forceinline__ uint32_t shade_owner(const SceneDev& S, const DFrame&
         float u = iu * rr, v = iv * rr;
         u = __fmaf_rn(__fmaf_rn(-irw, u, iu), rr, u);
         v = __fmaf_rn(__fmaf_rn(-irw, v, iv), rr, v);
-        texel = sample_desc(S.arena, d0.x, d0.y, flags, u, v, F.sample_mode);
+        texel = sample_desc(S.arena, d0.x, d0.y, flags, u, v, sample_mode);
     }
 
     // screen_to_world, rasterizer.rs:1707-1727, folded into one affine map + divide (DFrame::s2w)
@@ -906,26 +906,32 @@ __device__ __noinline__ uint32_t shade_2d(const uint8_t* __restrict__ arena, con
 // edge function is largest.  The per-pixel test is `fl(a*px + b*py + c) < 0 -> outside` (edge.rs:28-36);
 // its rounding error is below 3 * 2^-24 * (|a|*X + |b|*Y + |c|), so a corner value below
 // -2e-6 * (|a|*X + |b|*Y + |c|) proves every pixel centre of the rectangle fails.  NaNs keep the triangle.
-__device__ __forceinline__ bool rect_overlaps(const TriVis& T, int tx0, int ty0, int tx1, int ty1) {
+// Returns 0 = no pixel centre of the rectangle can be covered, 1 = maybe, 2 = the bbox contains the
+// rectangle and every edge function is provably >= 0 at every pixel centre of it (the corner where it is
+// smallest is above +margin), so the per-pixel edge evaluation can be skipped.
+__device__ __forceinline__ uint32_t rect_overlaps(const TriVis& T, int tx0, int ty0, int tx1, int ty1) {
     const int x0 = T.bbx & 0xFFFF, x1 = T.bbx >> 16, y0 = T.bby & 0xFFFF, y1 = T.bby >> 16;
-    if (x0 >= tx1 || x1 <= tx0 || y0 >= ty1 || y1 <= ty0) return false;
+    if (x0 >= tx1 || x1 <= tx0 || y0 >= ty1 || y1 <= ty0) return 0u;
     const float xmin = (float)max(tx0, x0) + 0.5f, xmax = (float)min(tx1, x1) - 0.5f;
     const float ymin = (float)max(ty0, y0) + 0.5f, ymax = (float)min(ty1, y1) - 0.5f;
+    bool inside = x0 <= tx0 && x1 >= tx1 && y0 <= ty0 && y1 >= ty1;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         const float a = T.ea[i], b = T.eb[i], c = T.ec[i];
-        const float e = a * (a >= 0.0f ? xmax : xmin) + b * (b >= 0.0f ? ymax : ymin) + c;
+        const float ax_hi = a * (a >= 0.0f ? xmax : xmin), ax_lo = a * (a >= 0.0f ? xmin : xmax);
+        const float by_hi = b * (b >= 0.0f ? ymax : ymin), by_lo = b * (b >= 0.0f ? ymin : ymax);
         const float m = (fabsf(a) * xmax + fabsf(b) * ymax + fabsf(c)) * 2e-6f;
-        if (e < -m) return false;
+        if (ax_hi + by_hi + c < -m) return 0u;
+        inside = inside && (ax_lo + by_lo + c > m);  // false for NaN
     }
-    return true;
+    return inside ? 2u : 1u;
 }
 
 // depth + alpha test of one covered pixel (rasterizer.rs:1051-1060, :1408)
 __device__ __forceinline__ void test_fragment(const SceneDev& S, const DFrame& F, const DFrameBatch* __restrict__ fbs,
                                               const TriShade* __restrict__ shade, const float4 q0, const float4 q1, const float4 q2,
-                                              uint32_t meta, uint32_t slot, float fpx, float fpy, float& best_z, uint32_t& best,
-                                              float& best_al, float& best_be) {
+                                              uint32_t meta, uint32_t slot, float fpx, float fpy, uint32_t sample_mode, float& best_z,
+                                              uint32_t& best, float& best_al, float& best_be) {
     // barycentric_weights_3d, rasterizer.rs:1754-1773 (a = q0.xy, b = q0.zw, c = q1.xy)
     const float acx = q1.x - q0.x, acy = q1.y - q0.y;
     const float apx = fpx - q0.x, apy = fpy - q0.y;
@@ -946,7 +952,7 @@ __device__ __forceinline__ void test_fragment(const SceneDev& S, const DFrame& F
         const float iv = sh.vw0 * alpha + sh.vw1 * beta + sh.vw2 * gamma;
         const float irw = sh.rw0 * alpha + sh.rw1 * beta + sh.rw2 * gamma;
         const DFrameBatch& FB = fbs[meta & RX_META_BATCH];
-        const uint32_t texel = sample_desc(S.arena, FB.sd_tex_word, FB.sd_wh, FB.sd_flags, iu / irw, iv / irw, F.sample_mode);
+        const uint32_t texel = sample_desc(S.arena, FB.sd_tex_word, FB.sd_wh, FB.sd_flags, iu / irw, iv / irw, sample_mode);
         if ((texel >> 24) != 255u) return;
     }
     best_z = z; best = slot; best_al = alpha; best_be = beta;
@@ -955,8 +961,8 @@ __device__ __forceinline__ void test_fragment(const SceneDev& S, const DFrame& F
 // coverage of one staged triangle over the thread's 2x2 pixels (rasterizer.rs:1020-1036), then the
 // depth test of the covered ones.  `valid` masks pixels outside the frame.
 __device__ __forceinline__ void process_record(const SceneDev& S, const DFrame& F, const DFrameBatch* __restrict__ fbs,
-                                               const TriShade* __restrict__ shade, const TriVis* Tp, uint32_t slot, int px0, int py0,
-                                               float fx0, float fy0, uint32_t valid, Vis4& V) {
+                                               const TriShade* __restrict__ shade, const TriVis* Tp, uint32_t slot, bool full, int px0,
+                                               int py0, float fx0, float fy0, uint32_t valid, uint32_t sample_mode, Vis4& V) {
     const float4* q = reinterpret_cast<const float4*>(Tp);
     const float4 q5 = q[5];
     const uint32_t bbx = __float_as_uint(q5.y), bby = __float_as_uint(q5.z), meta = __float_as_uint(q5.w);
@@ -966,9 +972,9 @@ __device__ __forceinline__ void process_record(const SceneDev& S, const DFrame& 
     uint32_t m = ((cx0 && cy0) ? 1u : 0u) | ((cx1 && cy0) ? 2u : 0u) | ((cx0 && cy1) ? 4u : 0u) | ((cx1 && cy1) ? 8u : 0u);
     m &= valid;
     if (!m) return;
-    const float4 q3 = q[3], q4 = q[4];
     const float fx1 = fx0 + 8.0f, fy1 = fy0 + 4.0f;
-    {   // Edges::evaluate, edge.rs:28-36: (a*px + b*py) + c < 0 -> outside (a NaN result passes)
+    if (!full) {   // Edges::evaluate, edge.rs:28-36: (a*px + b*py) + c < 0 -> outside (a NaN result passes)
+        const float4 q3 = q[3], q4 = q[4];
         const float ea[3] = {q3.x, q3.y, q3.z}, eb[3] = {q3.w, q4.x, q4.y}, ec[3] = {q4.z, q4.w, q5.x};
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
@@ -978,17 +984,19 @@ __device__ __forceinline__ void process_record(const SceneDev& S, const DFrame& 
             if ((ax0 + by1) + ec[i] < 0.0f) m &= ~4u;
             if ((ax1 + by1) + ec[i] < 0.0f) m &= ~8u;
         }
+        if (!m) return;
     }
-    if (!m) return;
     const float4 q0 = q[0], q1 = q[1], q2 = q[2];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         if (m & (1u << k))
-            test_fragment(S, F, fbs, shade, q0, q1, q2, meta, slot, (k & 1) ? fx1 : fx0, (k & 2) ? fy1 : fy0, V.z[k], V.own[k], V.al[k],
-                          V.be[k]);
+            test_fragment(S, F, fbs, shade, q0, q1, q2, meta, slot, (k & 1) ? fx1 : fx0, (k & 2) ? fy1 : fy0, sample_mode, V.z[k],
+                          V.own[k], V.al[k], V.be[k]);
     }
 }
 
+// SAMPLE: 0 nearest / 1 linear for every frame of the launch, 2 = read it per frame.  PLANES: owner/depth outputs.
+template <int SAMPLE, bool PLANES>
 __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raster(SceneDev S, Workspace Wk, RasterOut out, uint32_t n_frames,
                                                                uint32_t tiles_per_frame) {
     __shared__ __align__(16) TriVis s_large[RX_LARGE_CACHE];
@@ -999,6 +1007,7 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
     __shared__ uint32_t s_nsel;
     __shared__ int32_t s_work[4];   // frame (-1 = done), tile x0, tile y0
     __shared__ __align__(16) uint32_t s_color[RX_TILE_H * RX_COLOR_STRIDE];
+    __shared__ float4 s_state[4 * RX_TILE_THREADS];  // (z, owner, alpha, beta) of pixel k of thread t at [k*256 + t]
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // warp w covers a 16x8 region (2 across, 4 down); lane (lx, ly) of the 8x4 lane grid owns the
@@ -1032,6 +1041,7 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
         const TriShade* shade = Wk.shade + (size_t)f * Wk.slot_stride;
         const DFrameBatch* fbs = Wk.fb + (size_t)f * Wk.fb_stride;
 
+        const uint32_t smode = SAMPLE == 2 ? F.sample_mode : (uint32_t)SAMPLE;
         const int fw = F.width, fy1 = F.band_y1;
         const int tx0 = s_work[1], ty0 = F.band_y0 + s_work[2];
         const int tx1 = min(tx0 + RX_TILE_W, fw), ty1 = min(ty0 + RX_TILE_H, fy1);
@@ -1063,19 +1073,21 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                 cached_frame = f;
                 __syncthreads();
             }
-            if (tid < n_cached && rect_overlaps(s_large[tid], tx0, ty0, tx1, ty1)) s_sel[atomicAdd(&s_nsel, 1u)] = (uint16_t)tid;
+            if (tid < n_cached && rect_overlaps(s_large[tid], tx0, ty0, tx1, ty1) != 0u) s_sel[atomicAdd(&s_nsel, 1u)] = (uint16_t)tid;
             __syncthreads();
             {
                 const uint32_t n = s_nsel;
                 for (uint32_t base = 0; base < n; base += 32) {
                     const uint32_t i = base + lane;
                     const uint32_t r = i < n ? (uint32_t)s_sel[i] : 0u;
-                    uint32_t mask = __ballot_sync(0xFFFFFFFFu, i < n && region_ok && rect_overlaps(s_large[r], rx0, ry0, rx1, ry1));
+                    const uint32_t ov = (i < n && region_ok) ? rect_overlaps(s_large[r], rx0, ry0, rx1, ry1) : 0u;
+                    uint32_t mask = __ballot_sync(0xFFFFFFFFu, ov != 0u);
+                    const uint32_t fullm = __ballot_sync(0xFFFFFFFFu, ov == 2u);
                     while (mask) {
                         const int b = __ffs(mask) - 1;
                         mask &= mask - 1u;
                         const uint32_t rr = __shfl_sync(0xFFFFFFFFu, r, b);
-                        process_record(S, F, fbs, shade, &s_large[rr], s_large_slot[rr], px0, py0, fx0, fy0, valid, V);
+                        process_record(S, F, fbs, shade, &s_large[rr], s_large_slot[rr], (fullm >> b) & 1u, px0, py0, fx0, fy0, valid, smode, V);
                     }
                 }
             }
@@ -1102,19 +1114,25 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
 #pragma unroll 1
                     for (uint32_t h = 0; h < RX_STAGE; h += 32) {
                         const uint32_t i = h + lane;
-                        uint32_t mask = __ballot_sync(0xFFFFFFFFu, i < n && region_ok && rect_overlaps(s_tri[i], rx0, ry0, rx1, ry1));
+                        const uint32_t ov = (i < n && region_ok) ? rect_overlaps(s_tri[i], rx0, ry0, rx1, ry1) : 0u;
+                        uint32_t mask = __ballot_sync(0xFFFFFFFFu, ov != 0u);
+                        const uint32_t fullm = __ballot_sync(0xFFFFFFFFu, ov == 2u);
                         while (mask) {
-                            const uint32_t rr = h + (uint32_t)(__ffs(mask) - 1);
+                            const int b = __ffs(mask) - 1;
                             mask &= mask - 1u;
-                            process_record(S, F, fbs, shade, &s_tri[rr], s_slot[rr], px0, py0, fx0, fy0, valid, V);
+                            process_record(S, F, fbs, shade, &s_tri[h + b], s_slot[h + b], (fullm >> b) & 1u, px0, py0, fx0, fy0, valid, smode, V);
                         }
                     }
                 }
             }
         }
 
-        // resolve, one pixel of the 2x2 at a time (the state rotates so the body always reads element 0):
-        // deferred shade of the owner, miss pass (rasterizer.rs:409-461) or the 2D-only background, 2D pass
+        // resolve, one pixel of the 2x2 at a time (the visibility state goes through shared memory so the
+        // shading code is not unrolled and does not hold it in registers): deferred shade of the owner,
+        // miss pass (rasterizer.rs:409-461) or the 2D-only background, 2D pass
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            s_state[k * RX_TILE_THREADS + tid] = make_float4(V.z[k], __uint_as_float(V.own[k]), V.al[k], V.be[k]);
         const Tri2D* recs = Wk.tri2d + (size_t)f * Wk.tri2d_stride;
         const DFrameBatch2* fb2 = Wk.fb2 + (size_t)f * Wk.fb2_stride;
         // 2D records whose bbox meets this warp's region: one ballot per 32 records, hoisted for the first 32
@@ -1134,11 +1152,13 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
             const int px = px0 + ((k & 1) << 3), py = py0 + ((k >> 1) << 2);
             const float fpx = (float)px + 0.5f, fpy = (float)py + 0.5f;
             const bool in_frame = px < fw && py < fy1;
+            const float4 st = s_state[k * RX_TILE_THREADS + tid];
+            const uint32_t owner = __float_as_uint(st.y);
             uint32_t color;
             if (F.d3_active) {
-                if (V.own[0] != RX_OWNER_NONE) {
-                    const uint32_t b = __ldg(&vis[V.own[0]].meta) & RX_META_BATCH;
-                    color = shade_owner(S, F, lights, fbs[b], shade + V.own[0], V.al[0], V.be[0], V.z[0], fpx, fpy);
+                if (owner != RX_OWNER_NONE) {
+                    const uint32_t b = __ldg(&vis[owner].meta) & RX_META_BATCH;
+                    color = shade_owner(S, F, lights, fbs[b], shade + owner, st.z, st.w, st.x, fpx, fpy, smode);
                 } else {
                     color = 0xFF000000u;  // vec4_to_pixel((0,0,0,1))
                 }
@@ -1171,17 +1191,10 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                 }
             }
             s_color[(py - ty0) * RX_COLOR_STRIDE + (px - tx0)] = color;
-            if (in_frame) {
+            if (PLANES && in_frame) {
                 const size_t o = (size_t)(py - F.band_y0) * (size_t)fw + (size_t)px;
-                if (out.owner) out.owner[o] = V.own[0];
-                if (out.depth) out.depth[o] = V.z[0];
-            }
-            {   // rotate the per-pixel state
-                const float z0 = V.z[0], a0 = V.al[0], b0 = V.be[0];
-                const uint32_t o0 = V.own[0];
-#pragma unroll
-                for (int j = 0; j < 3; ++j) { V.z[j] = V.z[j + 1]; V.own[j] = V.own[j + 1]; V.al[j] = V.al[j + 1]; V.be[j] = V.be[j + 1]; }
-                V.z[3] = z0; V.own[3] = o0; V.al[3] = a0; V.be[3] = b0;
+                if (out.owner) out.owner[o] = owner;
+                if (out.depth) out.depth[o] = st.x;
             }
         }
         __syncthreads();
@@ -1299,14 +1312,20 @@ cudaError_t rxk_bin_fill(const SceneDev& S, const Workspace& W, uint32_t n_frame
     return cudaGetLastError();
 }
 cudaError_t rxk_raster(const SceneDev& S, const Workspace& W, const RasterOut& out, uint32_t n_frames, uint32_t tiles_per_frame,
-                       int grid_x, cudaStream_t st) {
-    k_raster<<<grid_x, RX_TILE_THREADS, 0, st>>>(S, W, out, n_frames, tiles_per_frame);
+                       int sample_mode, int grid_x, cudaStream_t st) {
+    const bool planes = out.owner || out.depth;
+#define RX_LAUNCH(SM, PL) k_raster<SM, PL><<<grid_x, RX_TILE_THREADS, 0, st>>>(S, W, out, n_frames, tiles_per_frame)
+    if (sample_mode == 0) { if (planes) RX_LAUNCH(0, true); else RX_LAUNCH(0, false); }
+    else if (sample_mode == 1) { if (planes) RX_LAUNCH(1, true); else RX_LAUNCH(1, false); }
+    else { if (planes) RX_LAUNCH(2, true); else RX_LAUNCH(2, false); }
+#undef RX_LAUNCH
     return cudaGetLastError();
 }
 int rxk_raster_blocks_per_sm() {
-    int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_raster, RX_TILE_THREADS, 0) != cudaSuccess || n < 1) n = 1;
-    return n;
+    int n = 0, best = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_raster<0, false>, RX_TILE_THREADS, 0) == cudaSuccess) best = n;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_raster<1, false>, RX_TILE_THREADS, 0) == cudaSuccess && n < best) best = n;
+    return best < 1 ? 1 : best;
 }
 cudaError_t rxk_selftest_div(uint64_t seed, uint32_t blocks, uint32_t iters, unsigned long long* d_mismatches, cudaStream_t st) {
     k_selftest_div<<<blocks, 256, 0, st>>>(seed, iters, d_mismatches);

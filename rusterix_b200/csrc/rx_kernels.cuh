@@ -80,8 +80,9 @@ cudaError_t rxk_clip_emit(const SceneDev& S, const Workspace& W, uint32_t n_fram
 cudaError_t rxk_bin_count(const SceneDev& S, const Workspace& W, uint32_t n_frames, int grid, cudaStream_t st);
 cudaError_t rxk_tile_alloc(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, cudaStream_t st);
 cudaError_t rxk_bin_fill(const SceneDev& S, const Workspace& W, uint32_t n_frames, int grid, cudaStream_t st);
+// sample_mode: RXC_SAMPLE_* when every frame of the launch uses it, 2 = mixed (read per frame)
 cudaError_t rxk_raster(const SceneDev& S, const Workspace& W, const RasterOut& out, uint32_t n_frames, uint32_t tiles_per_frame,
-                       int grid, cudaStream_t st);
+                       int sample_mode, int grid, cudaStream_t st);
 int rxk_raster_blocks_per_sm();
 // diagnostics: rx_div_by vs div.rn on blocks*256*iters random operand pairs; adds the mismatch count
 cudaError_t rxk_selftest_div(uint64_t seed, uint32_t blocks, uint32_t iters, unsigned long long* d_mismatches, cudaStream_t st);
