@@ -59,6 +59,10 @@ struct rxc_ctx {
     DFrame* h_frames = nullptr;  size_t h_frames_cap = 0;      // pinned
     DCounters* h_counters = nullptr; size_t h_counters_cap = 0; // pinned
     int raster_blocks_per_sm = 1;
+    // host-output pipelining: a copy stream and two staging halves so the D2H of one sub-group of
+    // frames overlaps the kernels of the next
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_render[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
 
     // stats / profiling
     rxc_stats stats = {};
@@ -364,12 +368,11 @@ int32_t validate_sources(rxc_ctx* ctx) {
 }
 
 // Runs frames [first, first+n) of one group through the kernel sequence.
-int32_t launch_group(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n, uint8_t* d_pixels, uint64_t stride, uint32_t* d_owner,
-                     float* d_depth) {
+int32_t launch_group(rxc_ctx* ctx, const DFrame* h_frames, DCounters* h_counters, uint32_t n, uint8_t* d_pixels, uint64_t stride,
+                     uint32_t* d_owner, float* d_depth) {
     SceneDev& S = ctx->S;
-    const uint32_t tiles_per_frame = (uint32_t)ctx->h_frames[0].tiles_x * (uint32_t)ctx->h_frames[0].tiles_y;
-    (void)frames;
-    CK(cudaMemcpyAsync(ctx->W.frames, ctx->h_frames, n * sizeof(DFrame), cudaMemcpyHostToDevice, ctx->stream));
+    const uint32_t tiles_per_frame = (uint32_t)h_frames[0].tiles_x * (uint32_t)h_frames[0].tiles_y;
+    CK(cudaMemcpyAsync(ctx->W.frames, h_frames, n * sizeof(DFrame), cudaMemcpyHostToDevice, ctx->stream));
     ctx->stats.h2d_bytes += n * sizeof(DFrame);
     const int wide = ctx->sm_count * 8;
     auto grid_for = [&](size_t items, int per_block) { return (int)std::max<size_t>(1, std::min<size_t>((items + per_block - 1) / per_block, (size_t)wide)); };
@@ -384,23 +387,23 @@ int32_t launch_group(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n, uint8_t*
     }
     RasterOut out;
     out.pixels = d_pixels; out.frame_stride = stride; out.owner = d_owner; out.depth = d_depth;
-    out.vec_store = (((uintptr_t)d_pixels & 15) == 0 && (stride & 15) == 0 && ((ctx->h_frames[0].width * 4) & 15) == 0) ? 1u : 0u;
+    out.vec_store = (((uintptr_t)d_pixels & 15) == 0 && (stride & 15) == 0 && ((h_frames[0].width * 4) & 15) == 0) ? 1u : 0u;
     const size_t total_tiles = (size_t)n * tiles_per_frame;
     const int grid = (int)std::max<size_t>(1, std::min<size_t>(total_tiles, (size_t)ctx->sm_count * ctx->raster_blocks_per_sm));
-    int sample_mode = (int)ctx->h_frames[0].sample_mode;
-    for (uint32_t i = 1; i < n; ++i) if ((int)ctx->h_frames[i].sample_mode != sample_mode) sample_mode = 2;
+    int sample_mode = (int)h_frames[0].sample_mode;
+    for (uint32_t i = 1; i < n; ++i) if ((int)h_frames[i].sample_mode != sample_mode) sample_mode = 2;
     { LaunchScope l(ctx, RXK_RASTER); CK(rxk_raster(S, ctx->W, out, n, tiles_per_frame, sample_mode, grid, ctx->stream)); }
-    CK(cudaMemcpyAsync(ctx->h_counters, ctx->W.counters, n * sizeof(DCounters), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_counters, ctx->W.counters, n * sizeof(DCounters), cudaMemcpyDeviceToHost, ctx->stream));
     ctx->stats.frames += n;
     return RXC_OK;
 }
 
 // checks the counters copied back by launch_group (stream must be synchronized); 1 = retry needed
-int32_t check_group(rxc_ctx* ctx, uint32_t n, bool* retry) {
+int32_t check_group(rxc_ctx* ctx, const DCounters* h_counters, uint32_t n, bool* retry) {
     *retry = false;
     uint32_t ov = 0, need = 0;
-    for (uint32_t i = 0; i < n; ++i) { ov |= ctx->h_counters[i].overflow; need = std::max(need, ctx->h_counters[i].list_cursor); }
-    const DCounters& c = ctx->h_counters[n - 1];
+    for (uint32_t i = 0; i < n; ++i) { ov |= h_counters[i].overflow; need = std::max(need, h_counters[i].list_cursor); }
+    const DCounters& c = h_counters[n - 1];
     ctx->stats.last_binned_refs = c.list_cursor;
     ctx->stats.last_large_tris = c.n_large;
     ctx->stats.last_clipped_tris = c.n_new_slots;
@@ -455,6 +458,59 @@ int32_t rasterize_impl(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames,
         ctx->h_frames_cap = group;
     }
 
+    // Host pixels, several frames: sub-groups of frames are rendered into alternating halves of the device
+    // staging buffer while the copy stream drains the previous half over PCIe.
+    if (!dev_px && sync && n_frames > 1 && !owner && !depth) {
+        const uint32_t sub = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(group, ((uint64_t)8 << 20) / std::max<uint64_t>(1, frame_bytes)));
+        if (ctx->h_frames_cap < n_frames) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (ctx->h_frames) cudaFreeHost(ctx->h_frames);
+            if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+            ctx->h_frames = nullptr; ctx->h_counters = nullptr; ctx->h_frames_cap = 0;
+            CK(cudaMallocHost((void**)&ctx->h_frames, n_frames * sizeof(DFrame)));
+            CK(cudaMallocHost((void**)&ctx->h_counters, n_frames * sizeof(DCounters)));
+            ctx->h_frames_cap = n_frames;
+        }
+        if (!ctx->copy_stream) {
+            CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; ++i) {
+                CK(cudaEventCreateWithFlags(&ctx->ev_render[i], cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
+            }
+        }
+        CK(cudaStreamSynchronize(ctx->stream));  // the pinned frame block may still feed an earlier asynchronous call
+        for (uint32_t i = 0; i < n_frames; ++i)
+            if ((st = fill_frame(ctx, frames[i], &ctx->h_frames[i])) != RXC_OK) return st;
+        for (int attempt = 0; attempt < 4; ++attempt) {
+            if ((st = ensure_workspace(ctx, sub, tiles_per_frame)) != RXC_OK) return st;
+            if ((st = reserve(ctx, ctx->d_out_px, (size_t)2 * sub * frame_bytes)) != RXC_OK) return st;
+            uint32_t k = 0;
+            for (uint32_t first = 0; first < n_frames; first += sub, ++k) {
+                const uint32_t n = std::min(sub, n_frames - first);
+                const int half = (int)(k & 1u);
+                uint8_t* d_px = ctx->d_out_px.as<uint8_t>() + (size_t)half * sub * frame_bytes;
+                if (k >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[half], 0));  // the half has been drained
+                if ((st = launch_group(ctx, ctx->h_frames + first, ctx->h_counters + first, n, d_px, frame_bytes, nullptr, nullptr)) != RXC_OK) return st;
+                CK(cudaEventRecord(ctx->ev_render[half], ctx->stream));
+                CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_render[half], 0));
+                if (stride == frame_bytes) {
+                    CK(cudaMemcpyAsync(pixels + (uint64_t)first * stride, d_px, (size_t)n * frame_bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+                } else {
+                    CK(cudaMemcpy2DAsync(pixels + (uint64_t)first * stride, stride, d_px, frame_bytes, frame_bytes, n, cudaMemcpyDeviceToHost, ctx->copy_stream));
+                }
+                CK(cudaEventRecord(ctx->ev_copy[half], ctx->copy_stream));
+                ctx->stats.d2h_bytes += (uint64_t)n * frame_bytes;
+            }
+            CK(cudaStreamSynchronize(ctx->stream));
+            CK(cudaStreamSynchronize(ctx->copy_stream));
+            if (ctx->profiling) drain_events(ctx);
+            bool retry = false;
+            if ((st = check_group(ctx, ctx->h_counters, n_frames, &retry)) != RXC_OK) return st;
+            if (!retry) return RXC_OK;  // else: a tile-list arena overflowed somewhere; it has been grown, run the call again
+        }
+        return fail(ctx, RXC_ERR_OOM, "tile-list arena kept overflowing");
+    }
+
     for (uint32_t first = 0; first < n_frames; first += group) {
         const uint32_t n = std::min(group, n_frames - first);
         for (int attempt = 0; attempt < 4; ++attempt) {
@@ -472,12 +528,12 @@ int32_t rasterize_impl(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames,
             uint32_t* d_ow = owner; float* d_dp = depth;
             if (owner && !dev_owner) { if ((st = reserve(ctx, ctx->d_out_owner, frame_bytes)) != RXC_OK) return st; d_ow = ctx->d_out_owner.as<uint32_t>(); }
             if (depth && !dev_depth) { if ((st = reserve(ctx, ctx->d_out_depth, frame_bytes)) != RXC_OK) return st; d_dp = ctx->d_out_depth.as<float>(); }
-            if ((st = launch_group(ctx, frames + first, n, d_px, d_stride, d_ow, d_dp)) != RXC_OK) return st;
+            if ((st = launch_group(ctx, ctx->h_frames, ctx->h_counters, n, d_px, d_stride, d_ow, d_dp)) != RXC_OK) return st;
             if (!sync && dev_px) break;  // truly asynchronous: counters are checked at the next synchronize
             CK(cudaStreamSynchronize(ctx->stream));
             if (ctx->profiling) drain_events(ctx);
             bool retry = false;
-            if ((st = check_group(ctx, n, &retry)) != RXC_OK) return st;
+            if ((st = check_group(ctx, ctx->h_counters, n, &retry)) != RXC_OK) return st;
             if (retry) continue;
             if (!dev_px) {
                 if (stride == frame_bytes || n == 1) {
@@ -540,6 +596,11 @@ void rxc_destroy(rxc_ctx* ctx) {
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     for (auto& p : ctx->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : ctx->free_events) cudaEventDestroy(e);
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_render[i]); cudaEventDestroy(ctx->ev_copy[i]); }
+        cudaStreamDestroy(ctx->copy_stream);
+    }
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -724,7 +785,7 @@ int32_t rxc_synchronize(rxc_ctx* ctx) {
     if (ctx->profiling) drain_events(ctx);
     if (ctx->h_counters && ctx->ws_frames) {
         bool retry = false;
-        int32_t st = check_group(ctx, 1, &retry);
+        int32_t st = check_group(ctx, ctx->h_counters, 1, &retry);
         if (st != RXC_OK) return st;
         if (retry) return fail(ctx, RXC_ERR_OOM, "tile-list arena overflowed during an asynchronous frame; it has been grown, render the frame again");
     }
