@@ -654,7 +654,6 @@ __global__ void __launch_bounds__(256) k_bin_fill(SceneDev S, Workspace Wk) {
 #ifndef RX_RASTER_MIN_BLOCKS
 #define RX_RASTER_MIN_BLOCKS 4  // resident CTAs per SM the register allocation is bounded for
 #endif
-#define RX_STAGE 64          // triangle records staged in shared memory per step
 #define RX_LARGE_CACHE 160   // large-triangle records kept in shared memory across the tiles of a frame
 #define RX_COLOR_STRIDE 40   // words per tile row in shared memory: the 4 rows a warp writes hit disjoint banks
 
@@ -1001,8 +1000,6 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                                                                uint32_t tiles_per_frame) {
     __shared__ __align__(16) TriVis s_large[RX_LARGE_CACHE];
     __shared__ uint32_t s_large_slot[RX_LARGE_CACHE];
-    __shared__ __align__(16) TriVis s_tri[RX_STAGE];
-    __shared__ uint32_t s_slot[RX_STAGE];
     __shared__ uint16_t s_sel[RX_LARGE_CACHE];
     __shared__ uint32_t s_nsel;
     __shared__ int32_t s_work[4];   // frame (-1 = done), tile x0, tile y0
@@ -1073,13 +1070,15 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                 cached_frame = f;
                 __syncthreads();
             }
-            if (tid < n_cached && rect_overlaps(s_large[tid], tx0, ty0, tx1, ty1) != 0u) s_sel[atomicAdd(&s_nsel, 1u)] = (uint16_t)tid;
-            __syncthreads();
+            if (n_cached > 32u) {  // two-level: tile-level selection by the CTA, then per warp region
+                if (tid < n_cached && rect_overlaps(s_large[tid], tx0, ty0, tx1, ty1) != 0u) s_sel[atomicAdd(&s_nsel, 1u)] = (uint16_t)tid;
+                __syncthreads();
+            }
             {
-                const uint32_t n = s_nsel;
+                const uint32_t n = n_cached > 32u ? s_nsel : n_cached;
                 for (uint32_t base = 0; base < n; base += 32) {
                     const uint32_t i = base + lane;
-                    const uint32_t r = i < n ? (uint32_t)s_sel[i] : 0u;
+                    const uint32_t r = i < n ? (n_cached > 32u ? (uint32_t)s_sel[i] : i) : 0u;
                     const uint32_t ov = (i < n && region_ok) ? rect_overlaps(s_large[r], rx0, ry0, rx1, ry1) : 0u;
                     uint32_t mask = __ballot_sync(0xFFFFFFFFu, ov != 0u);
                     const uint32_t fullm = __ballot_sync(0xFFFFFFFFu, ov == 2u);
@@ -1091,37 +1090,30 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                     }
                 }
             }
-            // (2) the rest of the large list, then the tile's binned list: staged in chunks, culled per warp region
+            // (2) the rest of the large list, then the tile's binned list.  Warp-private: every lane fetches one
+            // record of the list from L2/L1 and tests it against the warp's region, the survivors are then read
+            // by the whole warp (broadcast loads of lines the warp just touched) -- no staging, no CTA barrier.
             const uint32_t n_list = Wk.tile_count[(size_t)f * Wk.tile_stride + tile];
             const uint32_t* list = Wk.lists + (size_t)f * Wk.list_stride + Wk.tile_base[(size_t)f * Wk.tile_stride + tile];
+#pragma unroll 1
             for (int pass = 0; pass < 2; ++pass) {
                 const uint32_t* src = pass == 0 ? large + n_cached : list;
                 const uint32_t n_src = pass == 0 ? n_large - n_cached : n_list;
-                for (uint32_t base = 0; base < n_src; base += RX_STAGE) {
-                    const uint32_t n = min((uint32_t)RX_STAGE, n_src - base);
-                    __syncthreads();  // previous stage fully consumed
-                    {   // stage the records: 6 x 16 B each
-                        const float4* g = reinterpret_cast<const float4*>(vis);
-                        float4* s = reinterpret_cast<float4*>(s_tri);
-                        for (uint32_t i = tid; i < n * 6u; i += RX_TILE_THREADS) {
-                            const uint32_t r = i / 6u, q = i - r * 6u;
-                            const uint32_t slot = __ldg(src + base + r);
-                            if (q == 0) s_slot[r] = slot;
-                            s[i] = __ldg(g + (size_t)slot * 6u + q);
-                        }
-                    }
-                    __syncthreads();
 #pragma unroll 1
-                    for (uint32_t h = 0; h < RX_STAGE; h += 32) {
-                        const uint32_t i = h + lane;
-                        const uint32_t ov = (i < n && region_ok) ? rect_overlaps(s_tri[i], rx0, ry0, rx1, ry1) : 0u;
-                        uint32_t mask = __ballot_sync(0xFFFFFFFFu, ov != 0u);
-                        const uint32_t fullm = __ballot_sync(0xFFFFFFFFu, ov == 2u);
-                        while (mask) {
-                            const int b = __ffs(mask) - 1;
-                            mask &= mask - 1u;
-                            process_record(S, F, fbs, shade, &s_tri[h + b], s_slot[h + b], (fullm >> b) & 1u, px0, py0, fx0, fy0, valid, smode, V);
-                        }
+                for (uint32_t base = 0; base < n_src; base += 32) {
+                    const uint32_t i = base + lane;
+                    uint32_t slot = 0u, ov = 0u;
+                    if (i < n_src) {
+                        slot = __ldg(src + i);
+                        if (region_ok) ov = rect_overlaps(vis[slot], rx0, ry0, rx1, ry1);
+                    }
+                    uint32_t mask = __ballot_sync(0xFFFFFFFFu, ov != 0u);
+                    const uint32_t fullm = __ballot_sync(0xFFFFFFFFu, ov == 2u);
+                    while (mask) {
+                        const int b = __ffs(mask) - 1;
+                        mask &= mask - 1u;
+                        const uint32_t rr = __shfl_sync(0xFFFFFFFFu, slot, b);
+                        process_record(S, F, fbs, shade, vis + rr, rr, (fullm >> b) & 1u, px0, py0, fx0, fy0, valid, smode, V);
                     }
                 }
             }

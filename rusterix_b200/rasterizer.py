@@ -46,13 +46,13 @@ class DeviceContext:
         self.check(self.lib.rxc_set_stream(self.handle, C.c_void_p(cuda_stream or 0)))
 
     def upload(self, scene: Scene, assets: Assets, index_bytes=4):
-        akey = (id(assets), assets._generation, len(assets.tile_list))
+        akey = (assets._uid, assets._generation, len(assets.tile_list))
         if akey != self._assets_key:
             m = marshal.marshal_tiles(assets.tile_list)
             self.check(self.lib.rxc_set_assets(self.handle, m.struct, len(assets.tile_list)))
             self._assets_key = akey
             self._scene_key = None
-        skey = (id(scene), scene._generation, index_bytes)
+        skey = (scene._uid, scene._generation, index_bytes)
         lights = scene.all_lights()
         lkey = tuple(
             (int(l.light_type), tuple(l.position), tuple(l.color), l.intensity, l.emitting, l.start_distance,

@@ -9,6 +9,7 @@ src/map/pixelsource.rs:23-37; src/server/assets.rs:19."""
 from __future__ import annotations
 
 import enum
+import itertools
 import math
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
@@ -16,6 +17,8 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from . import vekmath
+
+_UIDS = itertools.count(1)
 
 
 class PrimitiveMode(enum.IntEnum):  # src/batch/mod.rs:5-15
@@ -159,6 +162,7 @@ class Assets:
     def __init__(self):
         self.tile_list: List[Tile] = []
         self._generation = 0
+        self._uid = next(_UIDS)  # device-cache identity (id() can be reused after garbage collection)
 
     @staticmethod
     def default() -> "Assets":
@@ -480,6 +484,7 @@ class Scene:
         self.dynamic_textures: List[Tile] = []
         self.animation_frame = 0
         self._generation = 0
+        self._uid = next(_UIDS)  # device-cache identity (id() can be reused after garbage collection)
 
     @staticmethod
     def empty() -> "Scene":
