@@ -225,51 +225,6 @@ __global__ void __launch_bounds__(256) k_frame_setup(SceneDev S, Workspace Wk, u
             l.inv_range = 1.0f / (l.start_distance - l.end_distance);
             Wk.lights[(size_t)f * Wk.lights_stride + i] = l;
         }
-        for (uint32_t b = tid; b < S.n_b3; b += blockDim.x) {
-            const DBatch3& B = S.b3[b];
-            DFrameBatch fb;
-            float pv[16], mvp[16];
-            rx_matmat4(F.proj, F.view, pv, F.matvec_mode);          // batch3d.rs:490
-            rx_matmat4(pv, B.transform, mvp, F.matvec_mode);
-            rx_matmat4(F.view, B.transform, fb.view_model, F.matvec_mode);  // batch3d.rs:555
-            bool rejected = false;
-            if (B.n_verts != 0) {  // batch3d.rs:493-552
-                bool ol = true, orr = true, ob = true, ot = true, on = true, of = true;
-                for (int c = 0; c < 8; ++c) {
-                    f4 v = {(c & 4) ? B.aabb_max[0] : B.aabb_min[0], (c & 2) ? B.aabb_max[1] : B.aabb_min[1],
-                            (c & 1) ? B.aabb_max[2] : B.aabb_min[2], 1.0f};
-                    f4 r = rx_matvec4(mvp, v, F.matvec_mode);
-                    float w = r.w;
-                    ol &= r.x < -w; orr &= r.x > w; ob &= r.y < -w; ot &= r.y > w; on &= r.z < -w; of &= r.z > w;
-                }
-                rejected = ol || orr || ob || ot || on || of;
-            }
-            // a constant Pixel source that is not opaque can never write (rasterizer.rs:1408)
-            if (B.source_kind == RXC_SRC_PIXEL && (B.source_pixel >> 24) != 255u) rejected = true;
-            fb.tex = 0xFFFFFFFFu;
-            fb.alpha_test = 0;
-            fb.sd_tex_word = 0; fb.sd_wh = 0; fb.sd_pad = 0;
-            fb.sd_flags = B.has_normals ? RX_SD_NORMALS : 0u;
-            fb.sd_pixel = (B.source_kind == RXC_SRC_PIXEL) ? B.source_pixel : 0xFF000000u;  // rasterizer.rs:1221
-            fb.sd_ambient[0] = B.ambient[0]; fb.sd_ambient[1] = B.ambient[1]; fb.sd_ambient[2] = B.ambient[2];
-            if (B.repeat_mode == RXC_REPEAT_REPEAT_XY || B.repeat_mode == RXC_REPEAT_REPEAT_X) fb.sd_flags |= RX_SD_REPEAT_X;
-            if (B.repeat_mode == RXC_REPEAT_REPEAT_XY || B.repeat_mode == RXC_REPEAT_REPEAT_Y) fb.sd_flags |= RX_SD_REPEAT_Y;
-            if (B.source_kind == RXC_SRC_STATIC_TILE || B.source_kind == RXC_SRC_DYNAMIC_TILE) {
-                const DTile t = S.tiles[(B.source_kind == RXC_SRC_STATIC_TILE ? 0u : S.n_static_tiles) + B.source_index];
-                fb.tex = t.first + (uint32_t)(F.animation_frame % t.n_frames);  // rasterizer.rs:1104-1105
-                const DTex tx = S.tex[fb.tex];
-                fb.alpha_test = tx.all_opaque ? 0u : 1u;
-                fb.sd_tex_word = (uint32_t)(tx.offset >> 2);
-                fb.sd_wh = tx.width | (tx.height << 16);
-                fb.sd_flags |= RX_SD_TEXTURED;
-            }
-            fb.bb_minx = rx_float_key(CUDART_INF_F); fb.bb_maxx = rx_float_key(-CUDART_INF_F);
-            fb.bb_miny = rx_float_key(CUDART_INF_F); fb.bb_maxy = rx_float_key(-CUDART_INF_F);
-            fb.sc_x0 = fb.sc_x1 = fb.sc_y0 = fb.sc_y1 = 0;
-            fb.rejected = (rejected || !F.d3_active) ? 1u : 0u;
-            fb.n_new_tris = 0;
-            Wk.fb[(size_t)f * Wk.fb_stride + b] = fb;
-        }
         return;
     }
 
@@ -343,8 +298,54 @@ __global__ void __launch_bounds__(256) k_frame_setup(SceneDev S, Workspace Wk, u
         return;
     }
 
-    // remaining CTAs zero the per-tile counters of this frame
+    // remaining CTAs: per-batch frame state, and zeroing of the per-tile counters of this frame
     const uint32_t zb = blockIdx.x - 1 - S.n_b2, nzb = gridDim.x - 1 - S.n_b2;
+    for (uint32_t b = zb * blockDim.x + tid; b < S.n_b3; b += nzb * blockDim.x) {  // per (frame, 3D batch) state
+        const DBatch3& B = S.b3[b];
+        DFrameBatch fb;
+        float pv[16], mvp[16];
+        rx_matmat4(F.proj, F.view, pv, F.matvec_mode);          // batch3d.rs:490
+        rx_matmat4(pv, B.transform, mvp, F.matvec_mode);
+        rx_matmat4(F.view, B.transform, fb.view_model, F.matvec_mode);  // batch3d.rs:555
+        bool rejected = false;
+        if (B.n_verts != 0) {  // batch3d.rs:493-552
+            bool ol = true, orr = true, ob = true, ot = true, on = true, of = true;
+            for (int c = 0; c < 8; ++c) {
+                f4 v = {(c & 4) ? B.aabb_max[0] : B.aabb_min[0], (c & 2) ? B.aabb_max[1] : B.aabb_min[1],
+                        (c & 1) ? B.aabb_max[2] : B.aabb_min[2], 1.0f};
+                f4 r = rx_matvec4(mvp, v, F.matvec_mode);
+                float w = r.w;
+                ol &= r.x < -w; orr &= r.x > w; ob &= r.y < -w; ot &= r.y > w; on &= r.z < -w; of &= r.z > w;
+            }
+            rejected = ol || orr || ob || ot || on || of;
+        }
+        // a constant Pixel source that is not opaque can never write (rasterizer.rs:1408)
+        if (B.source_kind == RXC_SRC_PIXEL && (B.source_pixel >> 24) != 255u) rejected = true;
+        fb.tex = 0xFFFFFFFFu;
+        fb.alpha_test = 0;
+        fb.sd_tex_word = 0; fb.sd_wh = 0; fb.sd_pad = 0;
+        fb.sd_flags = B.has_normals ? RX_SD_NORMALS : 0u;
+        fb.sd_pixel = (B.source_kind == RXC_SRC_PIXEL) ? B.source_pixel : 0xFF000000u;  // rasterizer.rs:1221
+        fb.sd_ambient[0] = B.ambient[0]; fb.sd_ambient[1] = B.ambient[1]; fb.sd_ambient[2] = B.ambient[2];
+        if (B.repeat_mode == RXC_REPEAT_REPEAT_XY || B.repeat_mode == RXC_REPEAT_REPEAT_X) fb.sd_flags |= RX_SD_REPEAT_X;
+        if (B.repeat_mode == RXC_REPEAT_REPEAT_XY || B.repeat_mode == RXC_REPEAT_REPEAT_Y) fb.sd_flags |= RX_SD_REPEAT_Y;
+        if (B.source_kind == RXC_SRC_STATIC_TILE || B.source_kind == RXC_SRC_DYNAMIC_TILE) {
+            const DTile t = S.tiles[(B.source_kind == RXC_SRC_STATIC_TILE ? 0u : S.n_static_tiles) + B.source_index];
+            fb.tex = t.first + (uint32_t)(F.animation_frame % t.n_frames);  // rasterizer.rs:1104-1105
+            const DTex tx = S.tex[fb.tex];
+            fb.alpha_test = tx.all_opaque ? 0u : 1u;
+            fb.sd_tex_word = (uint32_t)(tx.offset >> 2);
+            fb.sd_wh = tx.width | (tx.height << 16);
+            fb.sd_flags |= RX_SD_TEXTURED;
+        }
+        fb.bb_minx = rx_float_key(CUDART_INF_F); fb.bb_maxx = rx_float_key(-CUDART_INF_F);
+        fb.bb_miny = rx_float_key(CUDART_INF_F); fb.bb_maxy = rx_float_key(-CUDART_INF_F);
+        fb.sc_x0 = fb.sc_x1 = fb.sc_y0 = fb.sc_y1 = 0;
+        fb.rejected = (rejected || !F.d3_active) ? 1u : 0u;
+        fb.n_new_tris = 0;
+        Wk.fb[(size_t)f * Wk.fb_stride + b] = fb;
+    }
+
     uint32_t* tc = Wk.tile_count + (size_t)f * Wk.tile_stride;
     uint32_t* tf = Wk.tile_fill + (size_t)f * Wk.tile_stride;
     for (uint32_t i = zb * blockDim.x + tid; i < tiles_per_frame; i += nzb * blockDim.x) { tc[i] = 0u; tf[i] = 0u; }
@@ -1262,7 +1263,7 @@ __global__ void __launch_bounds__(256) k_selftest_div(uint64_t seed, uint32_t it
 // launch wrappers
 // ---------------------------------------------------------------------------------------------
 cudaError_t rxk_frame_setup(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, cudaStream_t st) {
-    const uint32_t zero_blocks = max(1u, min(64u, (tiles_per_frame + 255u) / 256u));
+    const uint32_t zero_blocks = max(max(1u, min(64u, (tiles_per_frame + 255u) / 256u)), min(64u, (S.n_b3 + 63u) / 64u));
     dim3 grid(1 + S.n_b2 + zero_blocks, n_frames);
     k_frame_setup<<<grid, 256, 0, st>>>(S, W, tiles_per_frame);
     return cudaGetLastError();
