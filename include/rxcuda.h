@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RXC_ABI_VERSION 1u
+#define RXC_ABI_VERSION 2u
 
 typedef struct rxc_ctx rxc_ctx;
 
@@ -68,9 +68,12 @@ enum {
     RXC_SRC_STATIC_TILE = 1,  /* index into the tiles given to rxc_set_assets (assets.tile_list) */
     RXC_SRC_DYNAMIC_TILE = 2, /* index into rxc_scene.dynamic_textures                           */
     RXC_SRC_PIXEL = 3,        /* constant RGBA8                                                  */
-    RXC_SRC_ENTITY_TILE = 4,  /* unsupported on device (RXC_ERR_UNSUPPORTED)                     */
-    RXC_SRC_ITEM_TILE = 5,    /* unsupported on device                                           */
-    RXC_SRC_TERRAIN = 6       /* unsupported on device                                           */
+    RXC_SRC_ENTITY_TILE = 4,  /* EntityTile(id, i): the host resolves assets.entity_tiles[id].get_index(i)
+                                 to an index into rxc_scene.actor_tiles; 0xFFFFFFFF = not found, which
+                                 samples as [0,0,0,0] (src/rasterizer.rs:1130-1152, :712-733)    */
+    RXC_SRC_ITEM_TILE = 5,    /* ItemTile(id, i): same, through assets.item_tiles                */
+    RXC_SRC_TERRAIN = 6       /* chunk.sample_terrain_texture of the batch's chunk (src/chunk.rs:135-151);
+                                 without a chunk: [255,0,0,255] in 3D, transparent in 2D          */
 };
 /* Background shaders, reference src/shader/vgradient.rs, src/shader/grid.rs */
 enum { RXC_BG_NONE = 0, RXC_BG_VGRAY_GRADIENT = 1, RXC_BG_GRID = 2 };
@@ -133,8 +136,11 @@ typedef struct rxc_batch3d {
     uint32_t has_profile_id;
     uint32_t profile_id;
     int32_t shader;         /* -1 = None; anything else -> RXC_ERR_UNSUPPORTED           */
-    uint32_t pass;          /* RXC_PASS_* */
+    uint32_t pass;          /* RXC_PASS_*; CHUNK_OPACITY batches go through d3_rasterize_opacity
+                               (src/rasterizer.rs:1425-1690), everything else through d3_rasterize */
     float transform[16];    /* transform_3d, column-major                                */
+    int32_t chunk;          /* index into rxc_scene.chunks of the Chunk the batch belongs to, -1 = none
+                               (the `chunk: Option<&Chunk>` argument, src/rasterizer.rs:973)      */
 } rxc_batch3d;
 
 /* reference src/batch/batch2d.rs:10-53 */
@@ -152,10 +158,46 @@ typedef struct rxc_batch2d {
     uint8_t source_pixel[4];
     uint32_t receives_light;
     int32_t shader;
+    int32_t chunk;         /* as in rxc_batch3d */
 } rxc_batch2d;
 
-/* reference src/scene.rs:8-50.  batches3d: chunks..., d3_static, d3_dynamic, d3_overlay in that
- * order; batches2d: chunks..., d2_static, d2_dynamic.  lights = scene.lights followed by
+/* (BBox, occlusion) entries of chunk.occluded_sectors / mapmini.occluded_sectors
+ * (src/chunk.rs:41, src/map/mini.rs:33, src/map/bbox.rs:35-40: contains() is inclusive). */
+typedef struct rxc_sector {
+    float min[2];
+    float max[2];
+    float occlusion;
+} rxc_sector;
+
+/* reference src/chunk.rs:23-57: the members the rasterizer reads besides the batches (which the
+ * host flattens into batches3d / batches2d) and the lights (appended to the light list). */
+typedef struct rxc_chunk {
+    int32_t origin[2];
+    int32_t size;
+    const rxc_sector* occluded_sectors; /* searched in order, first hit wins (src/chunk.rs:154-161) */
+    uint32_t n_occluded_sectors;
+    const rxc_texture* terrain_texture; /* NULL = None */
+} rxc_chunk;
+
+/* CompiledLinedef start/end (src/map/mini.rs:88-95: a light is blocked when the segment
+ * pixel->light crosses any of them) */
+typedef struct rxc_linedef {
+    float start[2];
+    float end[2];
+} rxc_linedef;
+
+/* Rasterizer.mapmini (src/rasterizer.rs:71, src/map/mini.rs:22-38): line-of-sight and sector
+ * occlusion for batches that do not belong to a chunk. */
+typedef struct rxc_mapmini {
+    const rxc_linedef* linedefs;
+    uint32_t n_linedefs;
+    const rxc_sector* occluded_sectors;
+    uint32_t n_occluded_sectors;
+} rxc_mapmini;
+
+/* reference src/scene.rs:8-50.  batches3d: per chunk (batches3d_opacity..., batches3d...,
+ * terrain_batch3d), then d3_static, d3_dynamic, d3_overlay; batches2d: per chunk (batches2d...,
+ * terrain_batch2d), then d2_static, d2_dynamic (src/rasterizer.rs:314-405, :501-553).  lights = scene.lights followed by
  * scene.dynamic_lights AFTER the per-call chunk-light append (src/rasterizer.rs:219-223). */
 typedef struct rxc_scene {
     const rxc_batch3d* batches3d;
@@ -166,6 +208,10 @@ typedef struct rxc_scene {
     uint32_t n_lights;
     const rxc_tile* dynamic_textures;
     uint32_t n_dynamic_textures;
+    const rxc_chunk* chunks;          /* scene.chunks.values() in the host's iteration order */
+    uint32_t n_chunks;
+    const rxc_tile* actor_tiles;      /* tiles RXC_SRC_ENTITY_TILE / RXC_SRC_ITEM_TILE index     */
+    uint32_t n_actor_tiles;
 } rxc_scene;
 
 /* Everything Rasterizer::setup + the builder methods + rasterize()'s scalar arguments carry
@@ -231,6 +277,8 @@ int32_t rxc_set_assets(rxc_ctx* ctx, const rxc_tile* tiles, uint32_t n_tiles);
 int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* scene);
 /* Replace only the light list (lights animate per frame in examples/cube.rs:72-73). */
 int32_t rxc_set_lights(rxc_ctx* ctx, const rxc_light* lights, uint32_t n_lights);
+/* Rasterizer.mapmini; NULL or all-empty = MapMini::default() (everything visible, occlusion 1). */
+int32_t rxc_set_mapmini(rxc_ctx* ctx, const rxc_mapmini* mapmini);
 
 /* The replacement for Rasterizer::rasterize.  `pixels` receives width*rows*4 bytes RGBA8
  * (rows = height, or the band height); it may be host (pageable or pinned) or device memory.

@@ -622,6 +622,53 @@ struct Raster {
     float width, height;
     uint32_t hash_anim;
     V2 translationd2; float scaled2;
+    const rxc_mapmini* mapmini = nullptr;
+
+    // src/map/bbox.rs:35-40 + src/chunk.rs:154-161 / src/map/mini.rs:58-65
+    static float sector_occlusion(const rxc_sector* sectors, uint32_t n, V2 at) {
+        for (uint32_t i = 0; i < n; ++i) {
+            const rxc_sector& b = sectors[i];
+            if (at.x >= b.min[0] && at.x <= b.max[0] && at.y >= b.min[1] && at.y <= b.max[1]) return b.occlusion;
+        }
+        return 1.0f;
+    }
+    float get_occlusion(int32_t chunk, V2 at) const {  // :1327-1331, :808-812
+        if (chunk >= 0) return sector_occlusion(scene->chunks[chunk].occluded_sectors, scene->chunks[chunk].n_occluded_sectors, at);
+        if (mapmini) return sector_occlusion(mapmini->occluded_sectors, mapmini->n_occluded_sectors, at);
+        return 1.0f;
+    }
+    // src/map/mini.rs:67-95
+    static bool segments_intersect(V2 a1, V2 a2, V2 b1, V2 b2) {
+        float d = (a2.x - a1.x) * (b2.y - b1.y) - (a2.y - a1.y) * (b2.x - b1.x);
+        if (d == 0.0f) return false;
+        float u = ((b1.x - a1.x) * (b2.y - b1.y) - (b1.y - a1.y) * (b2.x - b1.x)) / d;
+        float v = ((b1.x - a1.x) * (a2.y - a1.y) - (b1.y - a1.y) * (a2.x - a1.x)) / d;
+        return u >= 0.0f && u <= 1.0f && v >= 0.0f && v <= 1.0f;
+    }
+    bool is_visible(V2 from, V2 to) const {
+        if (!mapmini) return true;
+        for (uint32_t i = 0; i < mapmini->n_linedefs; ++i) {
+            const rxc_linedef& l = mapmini->linedefs[i];
+            if (segments_intersect(from, to, {l.start[0], l.start[1]}, {l.end[0], l.end[1]})) return false;
+        }
+        return true;
+    }
+    // src/chunk.rs:135-151 (scale = 1) + src/texture.rs:527-538
+    void sample_terrain_texture(int32_t chunk, V2 world_pos, uint8_t out[4]) const {
+        const rxc_chunk& c = scene->chunks[chunk];
+        float local_x = (world_pos.x / 1.0f) - (float)c.origin[0];
+        float local_y = (world_pos.y / 1.0f) - (float)c.origin[1];
+        out[0] = out[1] = out[2] = out[3] = 0;
+        if (!c.terrain_texture) return;
+        const rxc_texture& t = *c.terrain_texture;
+        int32_t pixels_per_tile = (int32_t)t.width / c.size;
+        float pixel_x = local_x * (float)pixels_per_tile;
+        float pixel_y = local_y * (float)pixels_per_tile;
+        uint32_t px = as_u32(rclamp(std::floor(pixel_x), 0.0f, (float)t.width - 1.0f));
+        uint32_t py = as_u32(rclamp(std::floor(pixel_y), 0.0f, (float)t.height - 1.0f));
+        size_t x = std::min(px, t.width - 1), y = std::min(py, t.height - 1);
+        std::memcpy(out, t.data + (y * t.width + x) * 4, 4);
+    }
 
     // src/rasterizer.rs:1707-1727
     V3 screen_to_world(float x, float y, float z_ndc) const {
@@ -691,15 +738,43 @@ struct Raster {
     const rxc_texture* tile_frame(uint32_t kind, uint32_t index) const {
         const rxc_tile* t = nullptr;
         if (kind == RXC_SRC_STATIC_TILE) { if (index < n_tiles) t = &tiles[index]; }
-        else { if (index < scene->n_dynamic_textures) t = &scene->dynamic_textures[index]; }
+        else if (kind == RXC_SRC_DYNAMIC_TILE) { if (index < scene->n_dynamic_textures) t = &scene->dynamic_textures[index]; }
+        else { if (index < scene->n_actor_tiles) t = &scene->actor_tiles[index]; }  // EntityTile / ItemTile, host-resolved
         if (!t || t->n_textures == 0) return nullptr;
         return &t->textures[f->animation_frame % t->n_textures];  // :1104-1105
     }
 
-    // src/rasterizer.rs:964-1420
+    // 3D texel of a fragment, src/rasterizer.rs:1100-1222 (and :1512-1598 for the opacity pass)
+    void texel_3d(const rxc_batch3d& batch, float u, float v, V3 world, uint8_t texel[4]) const {
+        switch (batch.source_kind) {
+            case RXC_SRC_STATIC_TILE:
+            case RXC_SRC_DYNAMIC_TILE: {
+                const rxc_texture* t = tile_frame(batch.source_kind, batch.source_index);
+                texture_sample(*t, u, v, f->sample_mode, batch.repeat_mode, texel);
+                break;
+            }
+            case RXC_SRC_PIXEL: std::memcpy(texel, batch.source_pixel, 4); break;
+            case RXC_SRC_ENTITY_TILE:
+            case RXC_SRC_ITEM_TILE: {
+                const rxc_texture* t = tile_frame(batch.source_kind, batch.source_index);
+                if (t) texture_sample(*t, u, v, f->sample_mode, batch.repeat_mode, texel);
+                else texel[0] = texel[1] = texel[2] = texel[3] = 0;
+                break;
+            }
+            case RXC_SRC_TERRAIN:
+                if (batch.chunk >= 0) sample_terrain_texture(batch.chunk, {world.x, world.z}, texel);
+                else { texel[0] = 255; texel[1] = 0; texel[2] = 0; texel[3] = 255; }
+                break;
+            default: texel[0] = texel[1] = texel[2] = 0; texel[3] = 255; break;
+        }
+    }
+
+    // src/rasterizer.rs:964-1420.  surface_id: 0 = None, else Some(value - 1) widened to 64 bits
     void d3_rasterize(std::vector<uint8_t>& buffer, std::vector<float>& z_buffer, std::vector<uint32_t>& owner,
-                      const TileRect& tile, const Batch3DState& s, Execution& execution) const {
+                      const std::vector<uint64_t>& surface_id, const TileRect& tile, const Batch3DState& s,
+                      Execution& execution) const {
         const rxc_batch3d& batch = *s.b;
+        const uint64_t profile = batch.has_profile_id ? (uint64_t)batch.profile_id + 1u : 0u;
         if (!s.bounding_box) return;
         const Rect& bbox = *s.bounding_box;
         if (!(bbox.x < (float)(tile.x + tile.width) && (bbox.x + bbox.width) > (float)tile.x &&
@@ -723,7 +798,10 @@ struct Raster {
                 for (size_t tx = min_x; tx < max_x; ++tx) {
                     float p[2] = {(float)tx + 0.5f, (float)ty + 0.5f};
                     if (!edges_evaluate(edges, p[0], p[1])) continue;
-                    // surface_id (opacity pass) is always None without chunk opacity batches (:1044)
+                    {   // :1041-1047 wall geometry behind an opacity batch of the same profile is skipped
+                        size_t idx = (ty - tile.y) * tile.width + (tx - tile.x);
+                        if (surface_id[idx] != 0 && surface_id[idx] == profile) continue;
+                    }
                     float w[3];
                     barycentric_weights(v0.x, v0.y, v1.x, v1.y, v2.x, v2.y, p[0], p[1], w);
                     float alpha = w[0], beta = w[1], gamma = w[2];
@@ -751,16 +829,7 @@ struct Raster {
                     }
 
                     uint8_t texel[4];
-                    switch (batch.source_kind) {  // :1101-1222
-                        case RXC_SRC_STATIC_TILE:
-                        case RXC_SRC_DYNAMIC_TILE: {
-                            const rxc_texture* t = tile_frame(batch.source_kind, batch.source_index);
-                            texture_sample(*t, interpolated_u, interpolated_v, f->sample_mode, batch.repeat_mode, texel);
-                            break;
-                        }
-                        case RXC_SRC_PIXEL: std::memcpy(texel, batch.source_pixel, 4); break;
-                        default: texel[0] = texel[1] = texel[2] = 0; texel[3] = 255; break;
-                    }
+                    texel_3d(batch, interpolated_u, interpolated_v, world, texel);  // :1101-1222
 
                     V4 color = pixel_to_vec4(texel);
                     // no batch shader: :1305-1317
@@ -780,7 +849,7 @@ struct Raster {
                     V3 mat_emissive = execution.emissive;
 
                     V3 lit = {0, 0, 0};
-                    float occlusion = 1.0f;  // mapmini.get_occlusion with no occluded sectors (src/map/mini.rs:58-65)
+                    float occlusion = get_occlusion(batch.chunk, {world.x, world.z});  // :1327-1331
                     if (occlusion > 0.0f) {  // :1334-1365
                         if (f->has_ambient) {
                             float hemi = 0.5f * (normal.y + 1.0f);
@@ -816,6 +885,69 @@ struct Raster {
                         z_buffer[zidx] = z;
                         owner[zidx] = s.owner_base + (uint32_t)triangle_index;
                     }
+                }
+            }
+        }
+    }
+
+    // src/rasterizer.rs:1425-1690: the opacity layer of a chunk.  Same coverage and depth arithmetic as
+    // d3_rasterize against its own z-buffer; no lighting, no alpha test; always writes colour, z and the
+    // batch's profile id into surface_id.
+    void d3_rasterize_opacity(std::vector<uint8_t>& buffer, std::vector<float>& z_buffer, std::vector<uint64_t>& surface_id,
+                              const TileRect& tile, const Batch3DState& s, Execution& execution) const {
+        const rxc_batch3d& batch = *s.b;
+        const uint64_t profile = batch.has_profile_id ? (uint64_t)batch.profile_id + 1u : 0u;
+        if (!s.bounding_box) return;
+        const Rect& bbox = *s.bounding_box;
+        if (!(bbox.x < (float)(tile.x + tile.width) && (bbox.x + bbox.width) > (float)tile.x &&
+              bbox.y < (float)(tile.y + tile.height) && (bbox.y + bbox.height) > (float)tile.y))
+            return;
+        for (size_t triangle_index = 0; triangle_index < s.edges.size(); ++triangle_index) {
+            const Edges& edges = s.edges[triangle_index];
+            if (!edges.visible) continue;
+            const Tri& tri = s.clipped_indices[triangle_index];
+            const V4 v0 = s.projected_vertices[tri.i0], v1 = s.projected_vertices[tri.i1], v2 = s.projected_vertices[tri.i2];
+            const V2 uv0 = s.clipped_uvs[tri.i0], uv1 = s.clipped_uvs[tri.i1], uv2 = s.clipped_uvs[tri.i2];
+            float min_xf = rmin(v0.x, rmin(v1.x, v2.x)), max_xf = rmax(v0.x, rmax(v1.x, v2.x));
+            float min_yf = rmin(v0.y, rmin(v1.y, v2.y)), max_yf = rmax(v0.y, rmax(v1.y, v2.y));
+            size_t min_x = as_usize(rmax(std::floor(min_xf), (float)tile.x));
+            size_t max_x = as_usize(rmin(std::ceil(max_xf), (float)(tile.x + tile.width)));
+            size_t min_y = as_usize(rmax(std::floor(min_yf), (float)tile.y));
+            size_t max_y = as_usize(rmin(std::ceil(max_yf), (float)(tile.y + tile.height)));
+            for (size_t ty = min_y; ty < max_y; ++ty) {
+                for (size_t tx = min_x; tx < max_x; ++tx) {
+                    float p[2] = {(float)tx + 0.5f, (float)ty + 0.5f};
+                    if (!edges_evaluate(edges, p[0], p[1])) continue;
+                    float w[3];
+                    barycentric_weights(v0.x, v0.y, v1.x, v1.y, v2.x, v2.y, p[0], p[1], w);
+                    float alpha = w[0], beta = w[1], gamma = w[2];
+                    float one_over_z = 1.0f / v0.z * alpha + 1.0f / v1.z * beta + 1.0f / v2.z * gamma;
+                    float z = 1.0f / one_over_z;
+                    size_t zidx = (ty - tile.y) * tile.width + (tx - tile.x);
+                    if (!(z < z_buffer[zidx])) continue;
+                    float interpolated_u = (uv0.x / v0.w) * alpha + (uv1.x / v1.w) * beta + (uv2.x / v2.w) * gamma;
+                    float interpolated_v = (uv0.y / v0.w) * alpha + (uv1.y / v1.w) * beta + (uv2.y / v2.w) * gamma;
+                    float interpolated_reciprocal_w = (1.0f / v0.w) * alpha + (1.0f / v1.w) * beta + (1.0f / v2.w) * gamma;
+                    interpolated_u /= interpolated_reciprocal_w;
+                    interpolated_v /= interpolated_reciprocal_w;
+                    V3 world = screen_to_world(p[0], p[1], z);
+                    uint8_t texel[4];
+                    texel_3d(batch, interpolated_u, interpolated_v, world, texel);  // :1512-1598
+                    V4 color = pixel_to_vec4(texel);                                // :1600-1608
+                    color.x = srgb_to_linear_fast(color.x);
+                    color.y = srgb_to_linear_fast(color.y);
+                    color.z = srgb_to_linear_fast(color.z);
+                    execution.color = {color.x, color.y, color.z};
+                    execution.opacity = (float)texel[3] / 255.0f;
+                    // no batch shader (:1611-1637)
+                    color.x = linear_to_srgb_fast(execution.color.x);  // :1639-1643
+                    color.y = linear_to_srgb_fast(execution.color.y);
+                    color.z = linear_to_srgb_fast(execution.color.z);
+                    color.w = execution.opacity;
+                    vec4_to_pixel(color, texel);
+                    std::memcpy(&buffer[zidx * 4], texel, 4);  // :1647-1651
+                    z_buffer[zidx] = z;
+                    surface_id[zidx] = profile;
                 }
             }
         }
@@ -913,13 +1045,22 @@ struct Raster {
                             break;
                         }
                         case RXC_SRC_PIXEL: std::memcpy(texel, batch.source_pixel, 4); break;
+                        case RXC_SRC_ENTITY_TILE:
+                        case RXC_SRC_ITEM_TILE: {
+                            const rxc_texture* t = tile_frame(batch.source_kind, batch.source_index);
+                            if (t) texture_sample(*t, u, v, f->sample_mode, batch.repeat_mode, texel);
+                            break;
+                        }
+                        case RXC_SRC_TERRAIN:
+                            if (batch.chunk >= 0) sample_terrain_texture(batch.chunk, world, texel);
+                            break;
                         default: break;
                     }
 
                     if ((batch.receives_light && scene->n_lights != 0) || f->has_ambient) {  // :799-873
                         float acc[3] = {0, 0, 0};
                         if (f->has_ambient) {
-                            float occlusion = 1.0f;
+                            float occlusion = get_occlusion(batch.chunk, world);
                             acc[0] += f->ambient[0] * occlusion; acc[1] += f->ambient[1] * occlusion; acc[2] += f->ambient[2] * occlusion;
                         }
                         for (uint32_t li = 0; li < scene->n_lights; ++li) {
@@ -927,10 +1068,12 @@ struct Raster {
                             float lc[3];
                             if (!light_color_at(light, {world.x, 0.0f, world.y}, hash_anim, true, lc)) continue;
                             if (light.light_type == RXC_LIGHT_AMBIENT_DAYLIGHT) {
-                                float occlusion = 1.0f;
+                                float occlusion = get_occlusion(batch.chunk, world);
                                 lc[0] *= occlusion; lc[1] *= occlusion; lc[2] *= occlusion;
                             }
-                            // mapmini.is_visible: no linedefs -> always visible (src/map/mini.rs:88-95)
+                            if (light.light_type != RXC_LIGHT_AMBIENT && light.light_type != RXC_LIGHT_AMBIENT_DAYLIGHT &&
+                                !is_visible(world, {light.position[0], light.position[2]}))  // src/map/mini.rs:88-95
+                                continue;
                             acc[0] += lc[0]; acc[1] += lc[1]; acc[2] += lc[2];
                         }
                         for (int i = 0; i < 3; ++i) {
@@ -961,9 +1104,10 @@ struct Raster {
         buffer.assign(tile.width * tile.height * 4, 0);
         if (f->has_background_color)
             for (size_t i = 0; i < buffer.size(); i += 4) std::memcpy(&buffer[i], f->background_color, 4);
-        std::vector<uint8_t> buffer_opacity(tile.width * tile.height * 4, 0);  // unused without opacity batches
+        std::vector<uint8_t> buffer_opacity(tile.width * tile.height * 4, 0);
         z_buffer.assign(tile.width * tile.height, 1.0f);
         std::vector<float> z_buffer_opacity(tile.width * tile.height, 1.0f);
+        std::vector<uint64_t> surface_id(tile.width * tile.height, 0);  // :290 (0 = None)
         owner.assign(tile.width * tile.height, 0xFFFFFFFFu);
 
         if (!f->ignore_background_shader && f->background_shader != RXC_BG_NONE) {  // :292-308
@@ -980,14 +1124,33 @@ struct Raster {
         Execution execution;  // :310
 
         if (f->d3_active) {
-            for (const Batch3DState& s : *b3) d3_rasterize(buffer, z_buffer, owner, tile, s, execution);  // :360-405
+            // batches arrive in submission order: per chunk opacity, opaque, terrain (:314-357), then
+            // static, dynamic, overlay (:360-405)
+            for (const Batch3DState& s : *b3) {
+                if (s.b->pass == RXC_PASS_CHUNK_OPACITY) d3_rasterize_opacity(buffer_opacity, z_buffer_opacity, surface_id, tile, s, execution);
+                else d3_rasterize(buffer, z_buffer, owner, surface_id, tile, s, execution);
+            }
             for (size_t i = 0; i < z_buffer.size(); ++i) {  // :409-461 (no render graph, no brush preview)
                 if (z_buffer[i] == 1.0f) {
                     V4 color = {0.0f, 0.0f, 0.0f, 1.0f};
                     vec4_to_pixel(color, &buffer[i * 4]);
                 }
-                // :464-495 opacity blend: z_buffer_opacity stays 1.0 without opacity batches
-                (void)z_buffer_opacity; (void)buffer_opacity;
+                if (z_buffer_opacity[i] < 1.0f && z_buffer[i] > z_buffer_opacity[i]) {  // :464-495
+                    const size_t idx = i * 4;
+                    float src_r = (float)buffer_opacity[idx], src_g = (float)buffer_opacity[idx + 1], src_b = (float)buffer_opacity[idx + 2];
+                    float src_a = (float)buffer_opacity[idx + 3] / 255.0f;
+                    float dst_r = (float)buffer[idx], dst_g = (float)buffer[idx + 1], dst_b = (float)buffer[idx + 2];
+                    float dst_a = (float)buffer[idx + 3] / 255.0f;
+                    float inv_a = 1.0f - src_a;
+                    float out_r = src_r * src_a + dst_r * inv_a;
+                    float out_g = src_g * src_a + dst_g * inv_a;
+                    float out_b = src_b * src_a + dst_b * inv_a;
+                    float out_a = !f->preserve_transparency ? 1.0f : rclamp(src_a + dst_a * inv_a, 0.0f, 1.0f);
+                    buffer[idx] = as_u8(rclamp(out_r, 0.0f, 255.0f));
+                    buffer[idx + 1] = as_u8(rclamp(out_g, 0.0f, 255.0f));
+                    buffer[idx + 2] = as_u8(rclamp(out_b, 0.0f, 255.0f));
+                    buffer[idx + 3] = as_u8(rclamp(out_a * 255.0f, 0.0f, 255.0f));
+                }
             }
         }
         if (f->d2_active)
@@ -1011,8 +1174,10 @@ int32_t validate(const rxc_tile* tiles, uint32_t n_tiles, const rxc_scene* scene
     for (uint32_t i = 0; i < scene->n_batches3d; ++i) {
         const rxc_batch3d& b = scene->batches3d[i];
         if (b.shader >= 0) return RXC_ERR_UNSUPPORTED;
-        if (b.source_kind >= RXC_SRC_ENTITY_TILE) return RXC_ERR_UNSUPPORTED;
-        if (b.pass == RXC_PASS_CHUNK_OPACITY) return RXC_ERR_UNSUPPORTED;
+        if (b.source_kind > RXC_SRC_TERRAIN) return RXC_ERR_INVALID;
+        if (b.chunk >= (int32_t)scene->n_chunks) return RXC_ERR_INDEX;
+        if (b.source_kind == RXC_SRC_TERRAIN && b.chunk >= 0 && scene->chunks[b.chunk].terrain_texture && scene->chunks[b.chunk].size == 0)
+            return RXC_ERR_INDEX;  // the reference divides by chunk.size (src/chunk.rs:140)
         if (b.index_bytes != 4 && b.index_bytes != 8) return RXC_ERR_INVALID;
         if (b.source_kind == RXC_SRC_STATIC_TILE && (b.source_index >= n_tiles || tiles[b.source_index].n_textures == 0)) return RXC_ERR_INDEX;
         if (b.source_kind == RXC_SRC_DYNAMIC_TILE && (b.source_index >= scene->n_dynamic_textures || scene->dynamic_textures[b.source_index].n_textures == 0)) return RXC_ERR_INDEX;
@@ -1024,7 +1189,10 @@ int32_t validate(const rxc_tile* tiles, uint32_t n_tiles, const rxc_scene* scene
     for (uint32_t i = 0; i < scene->n_batches2d; ++i) {
         const rxc_batch2d& b = scene->batches2d[i];
         if (b.shader >= 0) return RXC_ERR_UNSUPPORTED;
-        if (b.source_kind >= RXC_SRC_ENTITY_TILE) return RXC_ERR_UNSUPPORTED;
+        if (b.source_kind > RXC_SRC_TERRAIN) return RXC_ERR_INVALID;
+        if (b.chunk >= (int32_t)scene->n_chunks) return RXC_ERR_INDEX;
+        if (b.source_kind == RXC_SRC_TERRAIN && b.chunk >= 0 && scene->chunks[b.chunk].terrain_texture && scene->chunks[b.chunk].size == 0)
+            return RXC_ERR_INDEX;
         if (b.index_bytes != 4 && b.index_bytes != 8) return RXC_ERR_INVALID;
         for (uint32_t t = 0; t < b.n_triangles; ++t) {
             Tri tri = read_tri(b.indices, b.index_bytes, t);
@@ -1042,14 +1210,14 @@ extern "C" {
 // Rasterizer::rasterize, src/rasterizer.rs:185-580.  n_threads <= 0: hardware concurrency
 // (rayon's default global pool); tiles are handed out dynamically like rayon's work stealing.
 // `pixels` gets width*height*4 bytes; `owner` / `depth` (optional) width*height entries.
-int32_t rxo_rasterize(const rxc_tile* tiles, uint32_t n_tiles, const rxc_scene* scene, const rxc_frame* f,
-                      uint8_t* pixels, uint32_t* owner_out, float* depth_out, int32_t n_threads) {
+int32_t rxo_rasterize(const rxc_tile* tiles, uint32_t n_tiles, const rxc_scene* scene, const rxc_mapmini* mapmini,
+                      const rxc_frame* f, uint8_t* pixels, uint32_t* owner_out, float* depth_out, int32_t n_threads) {
     int32_t st = validate(tiles, n_tiles, scene, f);
     if (st != RXC_OK) return st;
     if (!pixels) return RXC_ERR_INVALID;
 
     Raster r;
-    r.tiles = tiles; r.n_tiles = n_tiles; r.scene = scene; r.f = f;
+    r.tiles = tiles; r.n_tiles = n_tiles; r.scene = scene; r.f = f; r.mapmini = mapmini;
     r.width = (float)f->width; r.height = (float)f->height;  // :194-195
     r.hash_anim = hash_u32((uint32_t)f->animation_frame);   // :208
     std::memcpy(r.inverse_view.m, f->inverse_view, sizeof(r.inverse_view.m));
