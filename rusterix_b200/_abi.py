@@ -2,7 +2,7 @@
 tests/test_abi.py checks sizes/offsets against a C probe compiled from the header."""
 import ctypes as C
 
-RXC_ABI_VERSION = 1
+RXC_ABI_VERSION = 2
 
 RXC_OK = 0
 RXC_ERR_INVALID = -1
@@ -17,7 +17,7 @@ STATUS_NAMES = {
     -4: "RXC_ERR_OOM", -5: "RXC_ERR_INDEX", -6: "RXC_ERR_NO_DEVICE",
 }
 
-RXC_N_KERNELS = 8
+RXC_N_KERNELS = 10
 
 
 class rxc_texture(C.Structure):
@@ -69,6 +69,7 @@ class rxc_batch3d(C.Structure):
         ("shader", C.c_int32),
         ("pass_", C.c_uint32),
         ("transform", C.c_float * 16),
+        ("chunk", C.c_int32),
     ]
 
 
@@ -87,6 +88,34 @@ class rxc_batch2d(C.Structure):
         ("source_pixel", C.c_uint8 * 4),
         ("receives_light", C.c_uint32),
         ("shader", C.c_int32),
+        ("chunk", C.c_int32),
+    ]
+
+
+class rxc_sector(C.Structure):
+    _fields_ = [("min", C.c_float * 2), ("max", C.c_float * 2), ("occlusion", C.c_float)]
+
+
+class rxc_chunk(C.Structure):
+    _fields_ = [
+        ("origin", C.c_int32 * 2),
+        ("size", C.c_int32),
+        ("occluded_sectors", C.POINTER(rxc_sector)),
+        ("n_occluded_sectors", C.c_uint32),
+        ("terrain_texture", C.POINTER(rxc_texture)),
+    ]
+
+
+class rxc_linedef(C.Structure):
+    _fields_ = [("start", C.c_float * 2), ("end", C.c_float * 2)]
+
+
+class rxc_mapmini(C.Structure):
+    _fields_ = [
+        ("linedefs", C.POINTER(rxc_linedef)),
+        ("n_linedefs", C.c_uint32),
+        ("occluded_sectors", C.POINTER(rxc_sector)),
+        ("n_occluded_sectors", C.c_uint32),
     ]
 
 
@@ -100,6 +129,10 @@ class rxc_scene(C.Structure):
         ("n_lights", C.c_uint32),
         ("dynamic_textures", C.POINTER(rxc_tile)),
         ("n_dynamic_textures", C.c_uint32),
+        ("chunks", C.POINTER(rxc_chunk)),
+        ("n_chunks", C.c_uint32),
+        ("actor_tiles", C.POINTER(rxc_tile)),
+        ("n_actor_tiles", C.c_uint32),
     ]
 
 
@@ -161,6 +194,7 @@ EXPORTS = [
     ("rxc_set_assets", C.c_int32, [C.c_void_p, C.POINTER(rxc_tile), C.c_uint32]),
     ("rxc_set_scene", C.c_int32, [C.c_void_p, C.POINTER(rxc_scene)]),
     ("rxc_set_lights", C.c_int32, [C.c_void_p, C.POINTER(rxc_light), C.c_uint32]),
+    ("rxc_set_mapmini", C.c_int32, [C.c_void_p, C.POINTER(rxc_mapmini)]),
     ("rxc_rasterize", C.c_int32, [C.c_void_p, C.POINTER(rxc_frame), C.c_void_p, C.c_void_p, C.c_void_p]),
     ("rxc_rasterize_async", C.c_int32, [C.c_void_p, C.POINTER(rxc_frame), C.c_void_p, C.c_void_p, C.c_void_p]),
     ("rxc_rasterize_batch", C.c_int32, [C.c_void_p, C.POINTER(rxc_frame), C.c_uint32, C.c_void_p, C.c_uint64]),

@@ -11,8 +11,14 @@
 
 namespace {
 
-const char* const kKernelNames[RXC_N_KERNELS] = {"k_frame_setup", "k_tri_setup", "k_batch_finalize", "k_clip_emit",
-                                                 "k_bin_count",   "k_tile_alloc", "k_bin_fill",      "k_raster"};
+const char* const kKernelNames[RXC_N_KERNELS] = {"k_frame_setup", "k_tri_setup", "k_batch_finalize", "k_clip_emit", "k_bin_count",
+                                                 "k_tile_alloc",  "k_bin_fill",  "k_raster",         "k_bin2d",     "k_list_sort"};
+
+struct HChunk {  // host copy of what rxc_chunk carries besides its batches
+    int32_t origin[2]; int32_t size;
+    uint32_t sector_off, n_sectors;  // into rxc_ctx::h_sectors
+    int32_t terrain_tex;             // index into the scene-texture list (h_dyn_tex) or -1
+};
 
 struct DevBuf {
     void* p = nullptr;
@@ -40,6 +46,13 @@ struct rxc_ctx {
     std::vector<DTile> h_dyn_tiles;
     DevBuf d_arena, d_tex, d_tiles;
     bool textures_dirty = true;
+    uint32_t n_dyn_tiles = 0, n_actor_tiles = 0;   // h_dyn_tiles = dynamic tiles, then entity/item tiles
+    // chunks and the mapmini (occluded sectors, terrain textures, linedefs)
+    std::vector<HChunk> h_chunks;
+    std::vector<DSector> h_sectors;        // sectors of the scene's chunks
+    std::vector<DSector> h_mm_sectors;     // mapmini.occluded_sectors
+    std::vector<float> h_linedefs;         // 4 floats per mapmini linedef
+    DevBuf d_sectors, d_chunkinfo, d_linedefs;
 
     // scene
     std::vector<DBatch3> h_b3;
@@ -52,9 +65,10 @@ struct rxc_ctx {
     // per-frame workspace
     Workspace W = {};
     DevBuf w_frames, w_fb, w_fb2, w_lights, w_counters, w_vis, w_shade, w_bins, w_ctot, w_cbase, w_clip, w_large, w_tcount,
-        w_tbase, w_tfill, w_lists, w_tri2d, w_rcounter;
+        w_tbase, w_tfill, w_lists, w_tri2d, w_rcounter, w_tcount2, w_tbase2, w_tfill2, w_lists2;
     uint32_t ws_frames = 0, ws_tiles = 0;   // what the workspace is currently sized for
     uint32_t list_cap_per_frame = 0, list_cap_min = 0;
+    uint32_t list2_cap_per_frame = 0, list2_cap_min = 0;
     DevBuf d_out_px, d_out_owner, d_out_depth;  // staging for host outputs
     DFrame* h_frames = nullptr;  size_t h_frames_cap = 0;      // pinned
     DCounters* h_counters = nullptr; size_t h_counters_cap = 0; // pinned
@@ -141,6 +155,35 @@ int32_t build_tiles(rxc_ctx* ctx, const rxc_tile* tiles, uint32_t n, std::vector
     return RXC_OK;
 }
 
+// chunk table (+ the mapmini as the last entry), sectors and linedefs; `toff` = index of the first scene texture
+int32_t upload_chunks(rxc_ctx* ctx, uint32_t toff) {
+    std::vector<DChunkInfo> info(ctx->h_chunks.size() + 1);
+    std::vector<DSector> sectors = ctx->h_sectors;
+    for (size_t i = 0; i < ctx->h_chunks.size(); ++i) {
+        const HChunk& c = ctx->h_chunks[i];
+        DChunkInfo d = {};
+        d.sector_off = c.sector_off; d.n_sectors = c.n_sectors;
+        d.origin_x = c.origin[0]; d.origin_y = c.origin[1]; d.size = c.size;
+        d.terrain_tex = c.terrain_tex < 0 ? 0xFFFFFFFFu : toff + (uint32_t)c.terrain_tex;
+        info[i] = d;
+    }
+    DChunkInfo mm = {};
+    mm.sector_off = (uint32_t)sectors.size(); mm.n_sectors = (uint32_t)ctx->h_mm_sectors.size(); mm.terrain_tex = 0xFFFFFFFFu;
+    info.back() = mm;
+    sectors.insert(sectors.end(), ctx->h_mm_sectors.begin(), ctx->h_mm_sectors.end());
+    int32_t st;
+    if ((st = upload(ctx, ctx->d_chunkinfo, info.data(), info.size() * sizeof(DChunkInfo))) != RXC_OK) return st;
+    if ((st = upload(ctx, ctx->d_sectors, sectors.data(), sectors.size() * sizeof(DSector))) != RXC_OK) return st;
+    if ((st = upload(ctx, ctx->d_linedefs, ctx->h_linedefs.data(), ctx->h_linedefs.size() * sizeof(float))) != RXC_OK) return st;
+    ctx->S.chunk_info = ctx->d_chunkinfo.as<DChunkInfo>();
+    ctx->S.sectors = ctx->d_sectors.as<DSector>();
+    ctx->S.linedefs = ctx->d_linedefs.as<float4>();
+    ctx->S.n_scene_chunks = (uint32_t)ctx->h_chunks.size();
+    ctx->S.n_sectors = (uint32_t)sectors.size();
+    ctx->S.n_linedefs = (uint32_t)(ctx->h_linedefs.size() / 4);
+    return RXC_OK;
+}
+
 int32_t upload_textures(rxc_ctx* ctx) {
     std::vector<uint8_t> arena = ctx->h_static_arena;
     std::vector<DTex> tex = ctx->h_static_tex;
@@ -159,9 +202,10 @@ int32_t upload_textures(rxc_ctx* ctx) {
     ctx->S.tex = ctx->d_tex.as<DTex>();
     ctx->S.tiles = ctx->d_tiles.as<DTile>();
     ctx->S.n_static_tiles = (uint32_t)ctx->h_static_tiles.size();
-    ctx->S.n_dynamic_tiles = (uint32_t)ctx->h_dyn_tiles.size();
+    ctx->S.n_dynamic_tiles = ctx->n_dyn_tiles;
+    ctx->S.n_actor_tiles = ctx->n_actor_tiles;
     ctx->textures_dirty = false;
-    return RXC_OK;
+    return upload_chunks(ctx, toff);
 }
 
 int32_t upload_lights(rxc_ctx* ctx, const rxc_light* lights, uint32_t n) {
@@ -226,8 +270,12 @@ int32_t ensure_workspace(rxc_ctx* ctx, uint32_t n_frames, uint32_t tiles_per_fra
     Workspace& W = ctx->W;
     const size_t T = S.n_tris, nf = n_frames;
     const uint32_t want_list = std::max<uint32_t>(ctx->list_cap_min, (uint32_t)std::min<size_t>(6 * T + tiles_per_frame + 1024, 0xFFFFFFF0u));
-    if (n_frames <= ctx->ws_frames && tiles_per_frame <= ctx->ws_tiles && want_list <= ctx->list_cap_per_frame) return RXC_OK;
+    const uint32_t want_list2 = !S.general ? 16u : std::max<uint32_t>(ctx->list2_cap_min, (uint32_t)std::min<size_t>(8 * (size_t)S.n_rec2d + tiles_per_frame + 1024, 0xFFFFFFF0u));
+    if (n_frames <= ctx->ws_frames && tiles_per_frame <= ctx->ws_tiles && want_list <= ctx->list_cap_per_frame &&
+        want_list2 <= ctx->list2_cap_per_frame)
+        return RXC_OK;
     ctx->list_cap_per_frame = want_list;
+    ctx->list2_cap_per_frame = want_list2;
     int32_t st;
 #define RES(buf, bytes) if ((st = reserve(ctx, ctx->buf, (bytes))) != RXC_OK) return st
     RES(w_frames, nf * sizeof(DFrame));
@@ -246,6 +294,10 @@ int32_t ensure_workspace(rxc_ctx* ctx, uint32_t n_frames, uint32_t tiles_per_fra
     RES(w_tbase, nf * (size_t)tiles_per_frame * 4);
     RES(w_tfill, nf * (size_t)tiles_per_frame * 4);
     RES(w_lists, nf * (size_t)want_list * 4);
+    RES(w_tcount2, nf * (size_t)tiles_per_frame * 4);
+    RES(w_tbase2, nf * (size_t)tiles_per_frame * 4);
+    RES(w_tfill2, nf * (size_t)tiles_per_frame * 4);
+    RES(w_lists2, nf * (size_t)want_list2 * 4);
     RES(w_tri2d, nf * std::max<size_t>(1, S.n_rec2d) * sizeof(Tri2D));
     RES(w_rcounter, 16);
 #undef RES
@@ -265,6 +317,10 @@ int32_t ensure_workspace(rxc_ctx* ctx, uint32_t n_frames, uint32_t tiles_per_fra
     W.tile_base = ctx->w_tbase.as<uint32_t>();
     W.tile_fill = ctx->w_tfill.as<uint32_t>(); W.tile_stride = tiles_per_frame;
     W.lists = ctx->w_lists.as<uint32_t>(); W.list_stride = want_list;
+    W.tile_count2 = ctx->w_tcount2.as<uint32_t>();
+    W.tile_base2 = ctx->w_tbase2.as<uint32_t>();
+    W.tile_fill2 = ctx->w_tfill2.as<uint32_t>();
+    W.lists2 = ctx->w_lists2.as<uint32_t>(); W.list2_stride = want_list2;
     W.tri2d = ctx->w_tri2d.as<Tri2D>(); W.tri2d_stride = std::max(1u, S.n_rec2d);
     W.raster_counter = ctx->w_rcounter.as<uint32_t>();
     ctx->ws_frames = n_frames;
@@ -275,7 +331,7 @@ int32_t ensure_workspace(rxc_ctx* ctx, uint32_t n_frames, uint32_t tiles_per_fra
 size_t workspace_bytes_per_frame(const SceneDev& S, uint32_t tiles_per_frame) {
     const size_t T = S.n_tris;
     return sizeof(DFrame) + S.n_b3 * sizeof(DFrameBatch) + 3 * T * (sizeof(TriVis) + sizeof(TriShade) + sizeof(TriBin) + 4) +
-           T * sizeof(DClip) + (size_t)tiles_per_frame * 12 + (6 * T + tiles_per_frame + 1024) * 4 + S.n_rec2d * sizeof(Tri2D) + 4096;
+           T * sizeof(DClip) + (size_t)tiles_per_frame * 24 + (6 * T + tiles_per_frame + 1024) * 4 + S.n_rec2d * (sizeof(Tri2D) + 32) + 4096;
 }
 
 uint32_t hash_u32_host(uint32_t seed) {  // rasterizer.rs:199-207
@@ -346,23 +402,33 @@ int32_t fill_frame(rxc_ctx* ctx, const rxc_frame& f, DFrame* d) {
 }
 
 int32_t validate_sources(rxc_ctx* ctx) {
-    // 3D: the reference indexes tile_list / dynamic_textures directly and panics (rasterizer.rs:1103,:1126)
+    // 3D: the reference indexes tile_list / dynamic_textures directly and panics (rasterizer.rs:1103,:1126);
+    // entity/item tiles that do not resolve sample as transparent, a resolved tile without frames panics on `% 0`
+    auto actor_ok = [&](uint32_t index) {
+        if (index == 0xFFFFFFFFu) return true;
+        const size_t k = (size_t)ctx->n_dyn_tiles + index;
+        return index < ctx->n_actor_tiles && ctx->h_dyn_tiles[k].n_frames != 0;
+    };
     for (size_t i = 0; i < ctx->h_b3.size(); ++i) {
         const DBatch3& b = ctx->h_b3[i];
         if (b.source_kind == RXC_SRC_STATIC_TILE) {
             if (b.source_index >= ctx->h_static_tiles.size() || ctx->h_static_tiles[b.source_index].n_frames == 0)
                 return fail(ctx, RXC_ERR_INDEX, "3D batch " + std::to_string(i) + ": StaticTileIndex out of range (reference panics)");
         } else if (b.source_kind == RXC_SRC_DYNAMIC_TILE) {
-            if (b.source_index >= ctx->h_dyn_tiles.size() || ctx->h_dyn_tiles[b.source_index].n_frames == 0)
+            if (b.source_index >= ctx->n_dyn_tiles || ctx->h_dyn_tiles[b.source_index].n_frames == 0)
                 return fail(ctx, RXC_ERR_INDEX, "3D batch " + std::to_string(i) + ": DynamicTileIndex out of range (reference panics)");
+        } else if (b.source_kind == RXC_SRC_ENTITY_TILE || b.source_kind == RXC_SRC_ITEM_TILE) {
+            if (!actor_ok(b.source_index)) return fail(ctx, RXC_ERR_INDEX, "3D batch " + std::to_string(i) + ": bad actor tile index");
         }
     }
     for (size_t i = 0; i < ctx->h_b2.size(); ++i) {
         const DBatch2& b = ctx->h_b2[i];
-        const auto& tiles = b.source_kind == RXC_SRC_STATIC_TILE ? ctx->h_static_tiles : ctx->h_dyn_tiles;
-        if ((b.source_kind == RXC_SRC_STATIC_TILE || b.source_kind == RXC_SRC_DYNAMIC_TILE) && b.source_index < tiles.size() &&
-            tiles[b.source_index].n_frames == 0)
+        if (b.source_kind == RXC_SRC_STATIC_TILE && b.source_index < ctx->h_static_tiles.size() && ctx->h_static_tiles[b.source_index].n_frames == 0)
             return fail(ctx, RXC_ERR_INDEX, "2D batch " + std::to_string(i) + ": tile without textures (reference panics on % 0)");
+        if (b.source_kind == RXC_SRC_DYNAMIC_TILE && b.source_index < ctx->n_dyn_tiles && ctx->h_dyn_tiles[b.source_index].n_frames == 0)
+            return fail(ctx, RXC_ERR_INDEX, "2D batch " + std::to_string(i) + ": tile without textures (reference panics on % 0)");
+        if ((b.source_kind == RXC_SRC_ENTITY_TILE || b.source_kind == RXC_SRC_ITEM_TILE) && !actor_ok(b.source_index))
+            return fail(ctx, RXC_ERR_INDEX, "2D batch " + std::to_string(i) + ": bad actor tile index");
     }
     return RXC_OK;
 }
@@ -382,8 +448,15 @@ int32_t launch_group(rxc_ctx* ctx, const DFrame* h_frames, DCounters* h_counters
         { LaunchScope l(ctx, RXK_BATCH_FINALIZE); CK(rxk_batch_finalize(S, ctx->W, n, ctx->stream)); }
         { LaunchScope l(ctx, RXK_CLIP_EMIT); CK(rxk_clip_emit(S, ctx->W, n, grid_for(std::min<size_t>(S.n_tris, 65536), 128), ctx->stream)); }
         { LaunchScope l(ctx, RXK_BIN_COUNT); CK(rxk_bin_count(S, ctx->W, n, grid_for((size_t)S.n_tris + S.n_tris / 8, 256), ctx->stream)); }
-        { LaunchScope l(ctx, RXK_TILE_ALLOC); CK(rxk_tile_alloc(S, ctx->W, n, tiles_per_frame, ctx->stream)); }
+        { LaunchScope l(ctx, RXK_TILE_ALLOC); CK(rxk_tile_alloc(S, ctx->W, n, tiles_per_frame, 0, S.general ? 1 : 0, ctx->stream)); }
         { LaunchScope l(ctx, RXK_BIN_FILL); CK(rxk_bin_fill(S, ctx->W, n, grid_for((size_t)S.n_tris + S.n_tris / 8, 256), ctx->stream)); }
+        if (S.general) { LaunchScope l(ctx, RXK_LIST_SORT); CK(rxk_list_sort(S, ctx->W, n, tiles_per_frame, 0, ctx->stream)); }
+    }
+    if (S.general && S.n_rec2d) {  // 2D records into sorted per-tile lists
+        { LaunchScope l(ctx, RXK_BIN2D); CK(rxk_bin2d(S, ctx->W, n, 0, ctx->stream)); }
+        { LaunchScope l(ctx, RXK_TILE_ALLOC); CK(rxk_tile_alloc(S, ctx->W, n, tiles_per_frame, 1, 1, ctx->stream)); }
+        { LaunchScope l(ctx, RXK_BIN2D); CK(rxk_bin2d(S, ctx->W, n, 1, ctx->stream)); }
+        { LaunchScope l(ctx, RXK_LIST_SORT); CK(rxk_list_sort(S, ctx->W, n, tiles_per_frame, 1, ctx->stream)); }
     }
     RasterOut out;
     out.pixels = d_pixels; out.frame_stride = stride; out.owner = d_owner; out.depth = d_depth;
@@ -401,8 +474,12 @@ int32_t launch_group(rxc_ctx* ctx, const DFrame* h_frames, DCounters* h_counters
 // checks the counters copied back by launch_group (stream must be synchronized); 1 = retry needed
 int32_t check_group(rxc_ctx* ctx, const DCounters* h_counters, uint32_t n, bool* retry) {
     *retry = false;
-    uint32_t ov = 0, need = 0;
-    for (uint32_t i = 0; i < n; ++i) { ov |= h_counters[i].overflow; need = std::max(need, h_counters[i].list_cursor); }
+    uint32_t ov = 0, need = 0, need2 = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        ov |= h_counters[i].overflow;
+        need = std::max(need, h_counters[i].list_cursor);
+        need2 = std::max(need2, h_counters[i].list_cursor2);
+    }
     const DCounters& c = h_counters[n - 1];
     ctx->stats.last_binned_refs = c.list_cursor;
     ctx->stats.last_large_tris = c.n_large;
@@ -410,6 +487,10 @@ int32_t check_group(rxc_ctx* ctx, const DCounters* h_counters, uint32_t n, bool*
     ctx->stats.last_visible_tris = c.n_visible;
     if (ov & 1u) {  // tile-list arena too small: grow to what the frame asked for and run it again
         ctx->list_cap_min = need + need / 4 + 1024;
+        *retry = true;
+    }
+    if (ov & 8u) {  // 2D tile-list arena
+        ctx->list2_cap_min = need2 + need2 / 4 + 1024;
         *retry = true;
     }
     if (ov & 6u) return fail(ctx, RXC_ERR_OOM, "internal list overflow (large/clip); this is a bug");
@@ -590,7 +671,8 @@ void rxc_destroy(rxc_ctx* ctx) {
                       &ctx->d_chunks, &ctx->d_orphans, &ctx->d_pos2, &ctx->d_uv2, &ctx->d_idx2, &ctx->d_b2, &ctx->d_lights,
                       &ctx->w_frames, &ctx->w_fb, &ctx->w_fb2, &ctx->w_lights, &ctx->w_counters, &ctx->w_vis, &ctx->w_shade,
                       &ctx->w_bins, &ctx->w_ctot, &ctx->w_cbase, &ctx->w_clip, &ctx->w_large, &ctx->w_tcount, &ctx->w_tbase,
-                      &ctx->w_tfill, &ctx->w_lists, &ctx->w_tri2d, &ctx->w_rcounter, &ctx->d_out_px, &ctx->d_out_owner, &ctx->d_out_depth};
+                      &ctx->w_tfill, &ctx->w_lists, &ctx->w_tri2d, &ctx->w_rcounter, &ctx->d_out_px, &ctx->d_out_owner, &ctx->d_out_depth,
+                      &ctx->w_tcount2, &ctx->w_tbase2, &ctx->w_tfill2, &ctx->w_lists2, &ctx->d_sectors, &ctx->d_chunkinfo, &ctx->d_linedefs};
     for (DevBuf* b : bufs) free_buf(*b);
     if (ctx->h_frames) cudaFreeHost(ctx->h_frames);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -634,10 +716,29 @@ int32_t rxc_set_lights(rxc_ctx* ctx, const rxc_light* lights, uint32_t n_lights)
     return RXC_OK;
 }
 
+int32_t rxc_set_mapmini(rxc_ctx* ctx, const rxc_mapmini* mm) {
+    if (!ctx) return RXC_ERR_INVALID;
+    if (mm && ((mm->n_linedefs && !mm->linedefs) || (mm->n_occluded_sectors && !mm->occluded_sectors)))
+        return fail(ctx, RXC_ERR_INVALID, "null array with non-zero count in rxc_mapmini");
+    CK(cudaSetDevice(ctx->device));
+    ctx->h_linedefs.clear(); ctx->h_mm_sectors.clear();
+    if (mm) {
+        for (uint32_t i = 0; i < mm->n_linedefs; ++i) {
+            const rxc_linedef& l = mm->linedefs[i];
+            ctx->h_linedefs.insert(ctx->h_linedefs.end(), {l.start[0], l.start[1], l.end[0], l.end[1]});
+        }
+        for (uint32_t i = 0; i < mm->n_occluded_sectors; ++i) {
+            const rxc_sector& q = mm->occluded_sectors[i];
+            ctx->h_mm_sectors.push_back(DSector{q.min[0], q.min[1], q.max[0], q.max[1], q.occlusion, {0, 0, 0}});
+        }
+    }
+    return upload_chunks(ctx, (uint32_t)ctx->h_static_tex.size());
+}
+
 int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
     if (!ctx || !sc) return RXC_ERR_INVALID;
     if ((sc->n_batches3d && !sc->batches3d) || (sc->n_batches2d && !sc->batches2d) || (sc->n_lights && !sc->lights) ||
-        (sc->n_dynamic_textures && !sc->dynamic_textures))
+        (sc->n_dynamic_textures && !sc->dynamic_textures) || (sc->n_chunks && !sc->chunks) || (sc->n_actor_tiles && !sc->actor_tiles))
         return fail(ctx, RXC_ERR_INVALID, "null array with non-zero count in rxc_scene");
     CK(cudaSetDevice(ctx->device));
     ctx->have_scene = false;
@@ -649,8 +750,10 @@ int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
         const std::string who = "3D batch " + std::to_string(i) + ": ";
         if (b.shader >= 0) return fail(ctx, RXC_ERR_UNSUPPORTED, who + "batch shaders (Rusteria VM) are not on the device path");
         if (b.source_kind > RXC_SRC_TERRAIN) return fail(ctx, RXC_ERR_INVALID, who + "bad source kind");
-        if (b.source_kind >= RXC_SRC_ENTITY_TILE) return fail(ctx, RXC_ERR_UNSUPPORTED, who + "EntityTile/ItemTile/Terrain sources are not on the device path");
-        if (b.pass == RXC_PASS_CHUNK_OPACITY) return fail(ctx, RXC_ERR_UNSUPPORTED, who + "chunk opacity batches are not on the device path");
+        if (b.pass > RXC_PASS_CHUNK_OPACITY) return fail(ctx, RXC_ERR_INVALID, who + "bad pass");
+        if (b.chunk >= (int32_t)sc->n_chunks) return fail(ctx, RXC_ERR_INDEX, who + "chunk index out of range");
+        if (b.source_kind == RXC_SRC_TERRAIN && b.chunk >= 0 && sc->chunks[b.chunk].terrain_texture && sc->chunks[b.chunk].size == 0)
+            return fail(ctx, RXC_ERR_INDEX, who + "terrain chunk of size 0 (reference divides by chunk.size)");
         if (b.index_bytes != 4 && b.index_bytes != 8) return fail(ctx, RXC_ERR_INVALID, who + "index_bytes must be 4 or 8");
         if (b.cull_mode > RXC_CULL_BACK || b.repeat_mode > RXC_REPEAT_REPEAT_Y) return fail(ctx, RXC_ERR_INVALID, who + "bad enum value");
         if ((b.n_vertices && (!b.vertices || !b.uvs)) || (b.n_triangles && !b.indices)) return fail(ctx, RXC_ERR_INVALID, who + "null geometry pointer");
@@ -663,11 +766,15 @@ int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
         const std::string who = "2D batch " + std::to_string(i) + ": ";
         if (b.shader >= 0) return fail(ctx, RXC_ERR_UNSUPPORTED, who + "batch shaders (Rusteria VM) are not on the device path");
         if (b.source_kind > RXC_SRC_TERRAIN) return fail(ctx, RXC_ERR_INVALID, who + "bad source kind");
-        if (b.source_kind >= RXC_SRC_ENTITY_TILE) return fail(ctx, RXC_ERR_UNSUPPORTED, who + "EntityTile/ItemTile/Terrain sources are not on the device path");
-        if (b.mode != RXC_MODE_TRIANGLES) return fail(ctx, RXC_ERR_UNSUPPORTED, who + "line primitives are not on the device path yet");
+        if (b.mode > RXC_MODE_LINE_LOOP) return fail(ctx, RXC_ERR_INVALID, who + "bad primitive mode");
+        if (b.chunk >= (int32_t)sc->n_chunks) return fail(ctx, RXC_ERR_INDEX, who + "chunk index out of range");
+        if (b.source_kind == RXC_SRC_TERRAIN && b.chunk >= 0 && sc->chunks[b.chunk].terrain_texture && sc->chunks[b.chunk].size == 0)
+            return fail(ctx, RXC_ERR_INDEX, who + "terrain chunk of size 0 (reference divides by chunk.size)");
         if (b.index_bytes != 4 && b.index_bytes != 8) return fail(ctx, RXC_ERR_INVALID, who + "index_bytes must be 4 or 8");
         if (b.repeat_mode > RXC_REPEAT_REPEAT_Y) return fail(ctx, RXC_ERR_INVALID, who + "bad enum value");
         if ((b.n_vertices && (!b.vertices || !b.uvs)) || (b.n_triangles && !b.indices)) return fail(ctx, RXC_ERR_INVALID, who + "null geometry pointer");
+        if (b.mode == RXC_MODE_LINE_STRIP && b.n_vertices == 0) return fail(ctx, RXC_ERR_INDEX, who + "LineStrip without vertices (reference underflows)");
+        // every index triple is read by Batch2D::project (batch2d.rs:405-423) whatever the mode
         for (size_t k = 0; k < (size_t)b.n_triangles * 3; ++k)
             if (idx_at(b.indices, b.index_bytes, k) >= b.n_vertices) return fail(ctx, RXC_ERR_INDEX, who + "vertex index out of range (reference panics)");
         V2 += b.n_vertices; T2 += b.n_triangles;
@@ -682,6 +789,7 @@ int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
     ctx->h_b3.assign(sc->n_batches3d, DBatch3{});
     ctx->owner_base.assign(sc->n_batches3d, 0);
     size_t vo = 0, to = 0;
+    bool any_opacity = false;
     for (uint32_t i = 0; i < sc->n_batches3d; ++i) {
         const rxc_batch3d& b = sc->batches3d[i];
         DBatch3& d = ctx->h_b3[i];
@@ -691,6 +799,10 @@ int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
         d.cull_mode = b.cull_mode; d.repeat_mode = b.repeat_mode; d.source_kind = b.source_kind; d.source_index = b.source_index;
         memcpy(&d.source_pixel, b.source_pixel, 4);
         d.has_normals = b.normals ? 1u : 0u;
+        d.chunk = b.chunk < 0 ? -1 : b.chunk;
+        d.profile_id = b.profile_id;
+        d.bflags = (b.has_profile_id ? RX_BF_HAS_PROFILE : 0u) | (b.pass == RXC_PASS_CHUNK_OPACITY ? RX_BF_OPACITY : 0u);
+        if (b.pass == RXC_PASS_CHUNK_OPACITY) any_opacity = true;
         memcpy(d.ambient, b.ambient_color, 12);
         memcpy(d.transform, b.transform, 64);
         if (b.n_vertices) {
@@ -722,7 +834,7 @@ int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
     std::vector<float> pos2(V2 * 2), uv2(V2 * 2);
     std::vector<uint32_t> idx2(T2 * 3);
     ctx->h_b2.assign(sc->n_batches2d, DBatch2{});
-    size_t vo2 = 0, to2 = 0;
+    size_t vo2 = 0, to2 = 0, ro2 = 0;
     for (uint32_t i = 0; i < sc->n_batches2d; ++i) {
         const rxc_batch2d& b = sc->batches2d[i];
         DBatch2& d = ctx->h_b2[i];
@@ -730,14 +842,51 @@ int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
         d.mode = b.mode; d.repeat_mode = b.repeat_mode; d.source_kind = b.source_kind; d.source_index = b.source_index;
         memcpy(&d.source_pixel, b.source_pixel, 4);
         d.receives_light = b.receives_light ? 1u : 0u;
-        d.rec_off = (uint32_t)to2;
+        d.chunk = b.chunk < 0 ? -1 : b.chunk;
+        // records per frame (rasterizer.rs:604, :901-955): triangles, index pairs, or consecutive vertices
+        d.n_recs = b.mode == RXC_MODE_LINE_STRIP ? b.n_vertices - 1 : b.mode == RXC_MODE_LINE_LOOP ? b.n_vertices : b.n_triangles;
+        d.rec_off = (uint32_t)ro2;
+        ro2 += d.n_recs;
         if (b.n_vertices) { memcpy(&pos2[vo2 * 2], b.vertices, (size_t)b.n_vertices * 8); memcpy(&uv2[vo2 * 2], b.uvs, (size_t)b.n_vertices * 8); }
         for (size_t k = 0; k < (size_t)b.n_triangles * 3; ++k) idx2[to2 * 3 + k] = (uint32_t)(vo2 + idx_at(b.indices, b.index_bytes, k));
         vo2 += b.n_vertices; to2 += b.n_triangles;
     }
 
     int32_t st;
-    if ((st = build_tiles(ctx, sc->dynamic_textures, sc->n_dynamic_textures, ctx->h_dyn_arena, ctx->h_dyn_tex, ctx->h_dyn_tiles)) != RXC_OK) return st;
+    {   // scene textures: dynamic tiles, host-resolved entity/item tiles, then the chunks' terrain textures
+        std::vector<rxc_tile> all(sc->dynamic_textures, sc->dynamic_textures + sc->n_dynamic_textures);
+        all.insert(all.end(), sc->actor_tiles, sc->actor_tiles + sc->n_actor_tiles);
+        if ((st = build_tiles(ctx, all.data(), (uint32_t)all.size(), ctx->h_dyn_arena, ctx->h_dyn_tex, ctx->h_dyn_tiles)) != RXC_OK) return st;
+        ctx->n_dyn_tiles = sc->n_dynamic_textures; ctx->n_actor_tiles = sc->n_actor_tiles;
+        ctx->h_chunks.clear(); ctx->h_sectors.clear();
+        for (uint32_t i = 0; i < sc->n_chunks; ++i) {
+            const rxc_chunk& c = sc->chunks[i];
+            if (c.n_occluded_sectors && !c.occluded_sectors) return fail(ctx, RXC_ERR_INVALID, "chunk with null occluded_sectors");
+            HChunk h = {};
+            h.origin[0] = c.origin[0]; h.origin[1] = c.origin[1]; h.size = c.size;
+            h.sector_off = (uint32_t)ctx->h_sectors.size(); h.n_sectors = c.n_occluded_sectors;
+            for (uint32_t k = 0; k < c.n_occluded_sectors; ++k) {
+                const rxc_sector& q = c.occluded_sectors[k];
+                ctx->h_sectors.push_back(DSector{q.min[0], q.min[1], q.max[0], q.max[1], q.occlusion, {0, 0, 0}});
+            }
+            h.terrain_tex = -1;
+            if (c.terrain_texture) {
+                const rxc_texture& x = *c.terrain_texture;
+                if (!x.data || x.width == 0 || x.height == 0) return fail(ctx, RXC_ERR_INVALID, "empty terrain texture");
+                if (x.width > 65535u || x.height > 65535u) return fail(ctx, RXC_ERR_UNSUPPORTED, "textures larger than 65535 texels per side");
+                DTex d; d.offset = ctx->h_dyn_arena.size(); d.width = x.width; d.height = x.height; d.pad = 0;
+                const size_t bytes = (size_t)x.width * x.height * 4;
+                bool opaque = true;
+                for (size_t k = 3; k < bytes; k += 4) if (x.data[k] != 255) { opaque = false; break; }
+                d.all_opaque = opaque ? 1u : 0u;
+                ctx->h_dyn_arena.insert(ctx->h_dyn_arena.end(), x.data, x.data + bytes);
+                ctx->h_dyn_arena.resize((ctx->h_dyn_arena.size() + 255) & ~(size_t)255);
+                h.terrain_tex = (int32_t)ctx->h_dyn_tex.size();
+                ctx->h_dyn_tex.push_back(d);
+            }
+            ctx->h_chunks.push_back(h);
+        }
+    }
     ctx->textures_dirty = true;
     if ((st = upload_textures(ctx)) != RXC_OK) return st;
     if ((st = upload(ctx, ctx->d_pos, pos.data(), pos.size() * 4)) != RXC_OK) return st;
@@ -758,9 +907,12 @@ int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
     S.b3 = ctx->d_b3.as<DBatch3>(); S.chunks = ctx->d_chunks.as<DChunk>(); S.orphans = ctx->d_orphans.as<uint32_t>();
     S.pos2 = ctx->d_pos2.as<float2>(); S.uv2 = ctx->d_uv2.as<float2>(); S.idx2 = ctx->d_idx2.as<uint32_t>(); S.b2 = ctx->d_b2.as<DBatch2>();
     S.n_b3 = sc->n_batches3d; S.n_b2 = sc->n_batches2d; S.n_chunks = (uint32_t)chunks.size();
-    S.n_tris = (uint32_t)T; S.n_verts = (uint32_t)V; S.n_rec2d = (uint32_t)T2;
+    S.n_tris = (uint32_t)T; S.n_verts = (uint32_t)V; S.n_rec2d = (uint32_t)ro2;
+    // ordered 3D lists when the opacity layer is in play, binned 2D lists when a warp ballot cannot hold the records
+    S.general = (any_opacity || ro2 > 32) ? 1u : 0u;
     ctx->ws_frames = 0;  // workspace strides depend on the scene
     ctx->list_cap_min = 0;
+    ctx->list2_cap_min = 0;
     ctx->have_scene = true;
     return RXC_OK;
 }

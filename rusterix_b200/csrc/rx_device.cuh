@@ -42,13 +42,16 @@ struct DBatch3 {         // static per 3D batch (uploaded by rxc_set_scene)
     uint32_t has_normals;
     uint32_t chunk_first, n_chunks;
     uint32_t orphan_off, n_orphans; // vertices no triangle references (they still count for the bbox)
-    uint32_t pad0;
+    int32_t chunk;               // index of the batch's chunk, -1 = none
     float ambient[3];
     float pad1;
     float transform[16];
     float aabb_min[3], aabb_max[3]; // object-space AABB, NaN-ignoring min/max (batch3d.rs:494-507)
-    uint32_t pad2[2];
+    uint32_t profile_id;         // batch.profile_id when RX_BF_HAS_PROFILE
+    uint32_t bflags;             // RX_BF_*
 };
+#define RX_BF_HAS_PROFILE 1u
+#define RX_BF_OPACITY 2u         // a chunk.batches3d_opacity batch (rasterizer.rs:1425-1690)
 
 struct DBatch2 {         // static per 2D batch
     uint32_t v_off, n_verts;
@@ -58,7 +61,22 @@ struct DBatch2 {         // static per 2D batch
     uint32_t source_pixel;
     uint32_t receives_light;
     uint32_t rec_off;            // first record of this batch in the per-frame 2D record array
-    uint32_t pad;
+    int32_t chunk;               // index of the batch's chunk, -1 = none
+    uint32_t n_recs;             // records per frame: triangles, or line segments (by mode)
+    uint32_t pad[3];
+};
+
+struct DSector {         // one (BBox, occlusion) entry (chunk.rs:41, mini.rs:33)
+    float minx, miny, maxx, maxy;
+    float occlusion;
+    float pad[3];
+};
+struct DChunkInfo {      // what shading reads of a Chunk; entry [n_chunks] holds the mapmini sectors
+    uint32_t sector_off, n_sectors;
+    int32_t origin_x, origin_y;
+    int32_t size;
+    uint32_t terrain_tex;    // DTex index of chunk.terrain_texture or 0xFFFFFFFF
+    uint32_t pad[2];
 };
 
 struct DLight {          // rxc_light + the per-frame flicker factor (light.rs:656-672)
@@ -89,17 +107,23 @@ struct __align__(16) DFrameBatch {
     uint32_t sd_flags;                           // RX_SD_* bits
     uint32_t sd_pixel;                           // constant texel for Pixel / other sources
     float sd_ambient[3];                         // batch.ambient_color
-    uint32_t sd_pad;
+    int32_t sd_chunk;                            // chunk index (occlusion, terrain), -1 = none
+    uint32_t sd_profile;                         // profile id (valid with RX_SD_HAS_PROFILE)
+    uint32_t sd_pad[3];
 };
 #define RX_SD_TEXTURED 1u
 #define RX_SD_REPEAT_X 2u
 #define RX_SD_REPEAT_Y 4u
 #define RX_SD_NORMALS 8u
+#define RX_SD_TERRAIN 16u      // texel = chunk.sample_terrain_texture(world.xz)
+#define RX_SD_HAS_PROFILE 32u
+#define RX_SD_OPACITY 64u
 
 struct DFrameBatch2 {
     uint32_t tex;          // DTex index or 0xFFFFFFFF (transparent texel)
     uint32_t lit;          // lighting branch taken (rasterizer.rs:799-802)
-    uint32_t pad[2];
+    uint32_t terrain;      // source is PixelSource::Terrain: `tex` is the chunk's terrain texture
+    uint32_t pad;
 };
 
 // Visibility record: everything the per-pixel coverage/depth test reads (96 B, 16 B aligned)
@@ -110,11 +134,12 @@ struct __align__(16) TriVis {
     float ea[3], eb[3], ec[3]; // edge equations of the (possibly swapped) triangle
     uint32_t bbx;              // x0 | x1<<16  (x1 exclusive), after scissor
     uint32_t bby;              // y0 | y1<<16
-    uint32_t meta;             // batch index | fastdiv_ok<<30 | alpha_test<<31
+    uint32_t meta;             // batch index | opacity<<29 | fastdiv_ok<<30 | alpha_test<<31
 };
 #define RX_META_ALPHA 0x80000000u
 #define RX_META_FASTDIV 0x40000000u
-#define RX_META_BATCH 0x3FFFFFFFu
+#define RX_META_OPACITY 0x20000000u
+#define RX_META_BATCH 0x1FFFFFFFu
 static_assert(sizeof(TriVis) == 96, "TriVis must be 96 bytes");
 
 // Shading record: attributes only the alpha test and the final shade read (80 B)
@@ -135,7 +160,8 @@ struct __align__(16) Tri2D {
     float ea[3], eb[3], ec[3];
     uint32_t bbx, bby;         // scissored pixel bbox; empty when rejected
     uint32_t batch;            // 2D batch index
-    uint32_t kind;             // 0 triangle, 1 line segment (ax,ay)->(bx,by)
+    uint32_t kind;             // 0 triangle; 1 line segment, whose integer end points x0,y0,x1,y1
+                               // (`p as isize`, rasterizer.rs:1785-1788) are the bits of ax,ay,bx,by
     uint32_t pad[3];
 };
 static_assert(sizeof(Tri2D) == 112, "Tri2D must be 112 bytes");
@@ -182,7 +208,7 @@ struct DCounters {
     uint32_t list_cursor;   // next free entry of the tile-list arena
     uint32_t overflow;      // bit0 tile-list arena, bit1 large list, bit2 clip list
     uint32_t n_visible;     // statistics
-    uint32_t next_tile;     // raster work counter
+    uint32_t list_cursor2;  // next free entry of the 2D tile-list arena
     uint32_t pad;
 };
 

@@ -64,6 +64,21 @@ __device__ void scissor_1d(float bx, float bw, int dim, int ts, float pad, int* 
     *o1 = (int)(e < dim ? e : dim);
 }
 
+// DTile of a tile source: static tiles, then dynamic tiles, then the host-resolved entity/item tiles.
+// Returns false when the source has no tile (EntityTile/ItemTile not found, index out of range).
+__device__ __forceinline__ bool source_tile(const SceneDev& S, uint32_t kind, uint32_t index, DTile* out) {
+    uint32_t base, n;
+    if (kind == RXC_SRC_STATIC_TILE) { base = 0u; n = S.n_static_tiles; }
+    else if (kind == RXC_SRC_DYNAMIC_TILE) { base = S.n_static_tiles; n = S.n_dynamic_tiles; }
+    else { base = S.n_static_tiles + S.n_dynamic_tiles; n = S.n_actor_tiles; }
+    if (index >= n) return false;
+    *out = S.tiles[base + index];
+    return out->n_frames != 0u;
+}
+__device__ __forceinline__ bool is_tile_source(uint32_t kind) {
+    return kind == RXC_SRC_STATIC_TILE || kind == RXC_SRC_DYNAMIC_TILE || kind == RXC_SRC_ENTITY_TILE || kind == RXC_SRC_ITEM_TILE;
+}
+
 __device__ __forceinline__ void edge_eq(float x0, float y0, float x1, float y1, float* a, float* b, float* c) {
     *a = y1 - y0;               // edge.rs:18
     *b = x0 - x1;               // edge.rs:19
@@ -166,6 +181,12 @@ __device__ bool make_tri(const f4 P[3], const float2 uv[3], const f3 nn[3], uint
     return true;
 }
 
+// record flags of every triangle of a batch: the opacity layer never alpha-tests (rasterizer.rs:1647-1651)
+__device__ __forceinline__ uint32_t tri_meta_flags(const DFrameBatch& FB) {
+    if (FB.sd_flags & RX_SD_OPACITY) return RX_META_OPACITY;
+    return FB.alpha_test ? RX_META_ALPHA : 0u;
+}
+
 struct MinMax {
     float mnx, mxx, mny, mxy;
     __device__ void init() { mnx = CUDART_INF_F; mxx = -CUDART_INF_F; mny = CUDART_INF_F; mxy = -CUDART_INF_F; }
@@ -256,41 +277,62 @@ __global__ void __launch_bounds__(256) k_frame_setup(SceneDev S, Workspace Wk, u
         sy0 = max(sy0, F.band_y0); sy1 = min(sy1, F.band_y1);
         if (tid == 0) {
             DFrameBatch2 fb2;
-            fb2.tex = 0xFFFFFFFFu;
-            if (B.source_kind == RXC_SRC_STATIC_TILE || B.source_kind == RXC_SRC_DYNAMIC_TILE) {
-                const uint32_t nt = (B.source_kind == RXC_SRC_STATIC_TILE) ? S.n_static_tiles : S.n_dynamic_tiles;
-                if (B.source_index < nt) {  // rasterizer.rs:674-687: a missing tile samples as transparent
-                    const DTile t = S.tiles[(B.source_kind == RXC_SRC_STATIC_TILE ? 0u : S.n_static_tiles) + B.source_index];
-                    fb2.tex = t.first + (uint32_t)(F.animation_frame % t.n_frames);
-                }
+            fb2.tex = 0xFFFFFFFFu; fb2.terrain = 0u; fb2.pad = 0u;
+            if (is_tile_source(B.source_kind)) {
+                DTile t;  // rasterizer.rs:674-733: a missing tile samples as transparent
+                if (source_tile(S, B.source_kind, B.source_index, &t)) fb2.tex = t.first + (uint32_t)(F.animation_frame % t.n_frames);
+            } else if (B.source_kind == RXC_SRC_TERRAIN && B.chunk >= 0) {  // :746-752
+                fb2.tex = S.chunk_info[B.chunk].terrain_tex;
+                fb2.terrain = 1u;
             }
             fb2.lit = ((B.receives_light && S.n_lights != 0) || F.has_ambient) ? 1u : 0u;  // rasterizer.rs:799-802
-            fb2.pad[0] = fb2.pad[1] = 0;
             Wk.fb2[(size_t)f * Wk.fb2_stride + b] = fb2;
         }
-        for (uint32_t t = tid; t < B.n_tris; t += blockDim.x) {
+        for (uint32_t t = tid; t < B.n_recs; t += blockDim.x) {
             Tri2D r = {};
-            r.batch = b; r.kind = 0;
+            r.batch = b; r.kind = B.mode == RXC_MODE_TRIANGLES ? 0u : 1u;
             if (active && sx0 < sx1 && sy0 < sy1) {
-                const uint32_t i0 = S.idx2[(size_t)(B.t_off + t) * 3 + 0], i1 = S.idx2[(size_t)(B.t_off + t) * 3 + 1],
-                               i2 = S.idx2[(size_t)(B.t_off + t) * 3 + 2];
-                float2 p[3] = {S.pos2[i0], S.pos2[i1], S.pos2[i2]};
-                if (F.has_mat2d) {
-                    for (int k = 0; k < 3; ++k) { f3 q = rx_matvec3(F.mat2d, {p[k].x, p[k].y, 1.0f}, F.matvec_mode); p[k].x = q.x; p[k].y = q.y; }
-                }
-                const float2 t0 = S.uv2[i0], t1 = S.uv2[i1], t2 = S.uv2[i2];
-                r.ax = p[0].x; r.ay = p[0].y; r.bx = p[1].x; r.by = p[1].y; r.cx = p[2].x; r.cy = p[2].y;
-                r.u0 = t0.x; r.v0 = t0.y; r.u1 = t1.x; r.v1 = t1.y; r.u2 = t2.x; r.v2 = t2.y;
-                edge_eq(p[0].x, p[0].y, p[1].x, p[1].y, &r.ea[0], &r.eb[0], &r.ec[0]);
-                edge_eq(p[1].x, p[1].y, p[2].x, p[2].y, &r.ea[1], &r.eb[1], &r.ec[1]);
-                edge_eq(p[2].x, p[2].y, p[0].x, p[0].y, &r.ea[2], &r.eb[2], &r.ec[2]);
-                int x0, x1, y0, y1;
-                pixel_range(fminf(p[0].x, fminf(p[1].x, p[2].x)), fmaxf(p[0].x, fmaxf(p[1].x, p[2].x)), F.width, &x0, &x1);
-                pixel_range(fminf(p[0].y, fminf(p[1].y, p[2].y)), fmaxf(p[0].y, fmaxf(p[1].y, p[2].y)), F.height, &y0, &y1);
-                x0 = max(x0, sx0); x1 = min(x1, sx1); y0 = max(y0, sy0); y1 = min(y1, sy1);
-                if (x0 < x1 && y0 < y1) {
-                    r.bbx = (uint32_t)x0 | ((uint32_t)x1 << 16);
-                    r.bby = (uint32_t)y0 | ((uint32_t)y1 << 16);
+                if (B.mode == RXC_MODE_TRIANGLES) {
+                    const uint32_t i0 = S.idx2[(size_t)(B.t_off + t) * 3 + 0], i1 = S.idx2[(size_t)(B.t_off + t) * 3 + 1],
+                                   i2 = S.idx2[(size_t)(B.t_off + t) * 3 + 2];
+                    float2 p[3] = {S.pos2[i0], S.pos2[i1], S.pos2[i2]};
+                    if (F.has_mat2d) {
+                        for (int k = 0; k < 3; ++k) { f3 q = rx_matvec3(F.mat2d, {p[k].x, p[k].y, 1.0f}, F.matvec_mode); p[k].x = q.x; p[k].y = q.y; }
+                    }
+                    const float2 t0 = S.uv2[i0], t1 = S.uv2[i1], t2 = S.uv2[i2];
+                    r.ax = p[0].x; r.ay = p[0].y; r.bx = p[1].x; r.by = p[1].y; r.cx = p[2].x; r.cy = p[2].y;
+                    r.u0 = t0.x; r.v0 = t0.y; r.u1 = t1.x; r.v1 = t1.y; r.u2 = t2.x; r.v2 = t2.y;
+                    edge_eq(p[0].x, p[0].y, p[1].x, p[1].y, &r.ea[0], &r.eb[0], &r.ec[0]);
+                    edge_eq(p[1].x, p[1].y, p[2].x, p[2].y, &r.ea[1], &r.eb[1], &r.ec[1]);
+                    edge_eq(p[2].x, p[2].y, p[0].x, p[0].y, &r.ea[2], &r.eb[2], &r.ec[2]);
+                    int x0, x1, y0, y1;
+                    pixel_range(fminf(p[0].x, fminf(p[1].x, p[2].x)), fmaxf(p[0].x, fmaxf(p[1].x, p[2].x)), F.width, &x0, &x1);
+                    pixel_range(fminf(p[0].y, fminf(p[1].y, p[2].y)), fmaxf(p[0].y, fmaxf(p[1].y, p[2].y)), F.height, &y0, &y1);
+                    x0 = max(x0, sx0); x1 = min(x1, sx1); y0 = max(y0, sy0); y1 = min(y1, sy1);
+                    if (x0 < x1 && y0 < y1) {
+                        r.bbx = (uint32_t)x0 | ((uint32_t)x1 << 16);
+                        r.bby = (uint32_t)y0 | ((uint32_t)y1 << 16);
+                    }
+                } else {
+                    // line segment t of the batch (rasterizer.rs:901-955): Lines uses the first two indices of
+                    // triple t, LineStrip vertices (t, t+1), LineLoop (t, (t+1) % n)
+                    uint32_t i0, i1;
+                    if (B.mode == RXC_MODE_LINES) { i0 = S.idx2[(size_t)(B.t_off + t) * 3 + 0]; i1 = S.idx2[(size_t)(B.t_off + t) * 3 + 1]; }
+                    else { i0 = B.v_off + t; i1 = B.v_off + (t + 1u) % B.n_verts; }
+                    float2 p[2] = {S.pos2[i0], S.pos2[i1]};
+                    if (F.has_mat2d) {
+                        for (int k = 0; k < 2; ++k) { f3 q = rx_matvec3(F.mat2d, {p[k].x, p[k].y, 1.0f}, F.matvec_mode); p[k].x = q.x; p[k].y = q.y; }
+                    }
+                    // `p as isize` (rasterizer.rs:1785-1788): truncation, NaN -> 0, saturating (here to +-2^30)
+                    auto as_isize = [](float v) { return (v == v) ? (int)fminf(fmaxf(v, -1073741824.0f), 1073741824.0f) : 0; };
+                    const int x0 = as_isize(p[0].x), y0 = as_isize(p[0].y), x1 = as_isize(p[1].x), y1 = as_isize(p[1].y);
+                    r.ax = __int_as_float(x0); r.ay = __int_as_float(y0); r.bx = __int_as_float(x1); r.by = __int_as_float(y1);
+                    int bx0 = max(max(min(x0, x1), 0), sx0), bx1 = min(min(max(x0, x1) + 1, F.width), sx1);
+                    int by0 = max(max(min(y0, y1), 0), sy0), by1 = min(min(max(y0, y1) + 1, F.height), sy1);
+                    if (bx0 < bx1 && by0 < by1) {
+                        r.bbx = (uint32_t)bx0 | ((uint32_t)bx1 << 16);
+                        r.bby = (uint32_t)by0 | ((uint32_t)by1 << 16);
+                    }
                 }
             }
             recs[t] = r;
@@ -319,25 +361,50 @@ __global__ void __launch_bounds__(256) k_frame_setup(SceneDev S, Workspace Wk, u
             }
             rejected = ol || orr || ob || ot || on || of;
         }
-        // a constant Pixel source that is not opaque can never write (rasterizer.rs:1408)
-        if (B.source_kind == RXC_SRC_PIXEL && (B.source_pixel >> 24) != 255u) rejected = true;
         fb.tex = 0xFFFFFFFFu;
         fb.alpha_test = 0;
-        fb.sd_tex_word = 0; fb.sd_wh = 0; fb.sd_pad = 0;
+        fb.sd_tex_word = 0; fb.sd_wh = 0; fb.sd_pad[0] = fb.sd_pad[1] = fb.sd_pad[2] = 0;
+        fb.sd_chunk = B.chunk; fb.sd_profile = B.profile_id;
         fb.sd_flags = B.has_normals ? RX_SD_NORMALS : 0u;
-        fb.sd_pixel = (B.source_kind == RXC_SRC_PIXEL) ? B.source_pixel : 0xFF000000u;  // rasterizer.rs:1221
+        if (B.bflags & RX_BF_HAS_PROFILE) fb.sd_flags |= RX_SD_HAS_PROFILE;
+        if (B.bflags & RX_BF_OPACITY) fb.sd_flags |= RX_SD_OPACITY;
+        fb.sd_pixel = 0xFF000000u;  // rasterizer.rs:1221
         fb.sd_ambient[0] = B.ambient[0]; fb.sd_ambient[1] = B.ambient[1]; fb.sd_ambient[2] = B.ambient[2];
         if (B.repeat_mode == RXC_REPEAT_REPEAT_XY || B.repeat_mode == RXC_REPEAT_REPEAT_X) fb.sd_flags |= RX_SD_REPEAT_X;
         if (B.repeat_mode == RXC_REPEAT_REPEAT_XY || B.repeat_mode == RXC_REPEAT_REPEAT_Y) fb.sd_flags |= RX_SD_REPEAT_Y;
-        if (B.source_kind == RXC_SRC_STATIC_TILE || B.source_kind == RXC_SRC_DYNAMIC_TILE) {
-            const DTile t = S.tiles[(B.source_kind == RXC_SRC_STATIC_TILE ? 0u : S.n_static_tiles) + B.source_index];
-            fb.tex = t.first + (uint32_t)(F.animation_frame % t.n_frames);  // rasterizer.rs:1104-1105
-            const DTex tx = S.tex[fb.tex];
-            fb.alpha_test = tx.all_opaque ? 0u : 1u;
-            fb.sd_tex_word = (uint32_t)(tx.offset >> 2);
-            fb.sd_wh = tx.width | (tx.height << 16);
-            fb.sd_flags |= RX_SD_TEXTURED;
+        if (B.source_kind == RXC_SRC_PIXEL) {
+            fb.sd_pixel = B.source_pixel;
+        } else if (is_tile_source(B.source_kind)) {
+            DTile t;
+            if (source_tile(S, B.source_kind, B.source_index, &t)) {
+                fb.tex = t.first + (uint32_t)(F.animation_frame % t.n_frames);  // rasterizer.rs:1104-1105
+                const DTex tx = S.tex[fb.tex];
+                fb.alpha_test = tx.all_opaque ? 0u : 1u;
+                fb.sd_tex_word = (uint32_t)(tx.offset >> 2);
+                fb.sd_wh = tx.width | (tx.height << 16);
+                fb.sd_flags |= RX_SD_TEXTURED;
+            } else {
+                fb.sd_pixel = 0u;  // EntityTile / ItemTile that does not resolve: [0,0,0,0] (:1146-1151)
+            }
+        } else if (B.source_kind == RXC_SRC_TERRAIN) {  // :1178-1219
+            if (B.chunk < 0) {
+                fb.sd_pixel = 0xFF0000FFu;  // [255, 0, 0, 255]
+            } else {
+                const uint32_t tt = S.chunk_info[B.chunk].terrain_tex;
+                if (tt == 0xFFFFFFFFu) {
+                    fb.sd_pixel = 0u;       // chunk without a terrain texture: [0,0,0,0] (chunk.rs:150)
+                } else {
+                    const DTex tx = S.tex[tt];
+                    fb.tex = tt;
+                    fb.alpha_test = tx.all_opaque ? 0u : 1u;
+                    fb.sd_tex_word = (uint32_t)(tx.offset >> 2);
+                    fb.sd_wh = tx.width | (tx.height << 16);
+                    fb.sd_flags |= RX_SD_TERRAIN;
+                }
+            }
         }
+        // an opaque-pass batch whose constant texel is not opaque can never write (rasterizer.rs:1408)
+        if (!(fb.sd_flags & (RX_SD_TEXTURED | RX_SD_TERRAIN | RX_SD_OPACITY)) && (fb.sd_pixel >> 24) != 255u) rejected = true;
         fb.bb_minx = rx_float_key(CUDART_INF_F); fb.bb_maxx = rx_float_key(-CUDART_INF_F);
         fb.bb_miny = rx_float_key(CUDART_INF_F); fb.bb_maxy = rx_float_key(-CUDART_INF_F);
         fb.sc_x0 = fb.sc_x1 = fb.sc_y0 = fb.sc_y1 = 0;
@@ -349,6 +416,11 @@ __global__ void __launch_bounds__(256) k_frame_setup(SceneDev S, Workspace Wk, u
     uint32_t* tc = Wk.tile_count + (size_t)f * Wk.tile_stride;
     uint32_t* tf = Wk.tile_fill + (size_t)f * Wk.tile_stride;
     for (uint32_t i = zb * blockDim.x + tid; i < tiles_per_frame; i += nzb * blockDim.x) { tc[i] = 0u; tf[i] = 0u; }
+    if (S.general) {
+        uint32_t* tc2 = Wk.tile_count2 + (size_t)f * Wk.tile_stride;
+        uint32_t* tf2 = Wk.tile_fill2 + (size_t)f * Wk.tile_stride;
+        for (uint32_t i = zb * blockDim.x + tid; i < tiles_per_frame; i += nzb * blockDim.x) { tc2[i] = 0u; tf2[i] = 0u; }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -422,7 +494,7 @@ __global__ void __launch_bounds__(RX_CHUNK_TRIS) k_tri_setup(SceneDev S, Workspa
             mm.add(P[k].x, P[k].y);
         }
         TriBin bin = {0u, 0u, slot, ch.batch};
-        const uint32_t meta = ch.batch | (FB.alpha_test << 31);  // make_tri adds RX_META_FASTDIV
+        const uint32_t meta = ch.batch | tri_meta_flags(FB);  // make_tri adds RX_META_FASTDIV
         TriVis tv; TriShade tsh;
         vis = make_tri(P, T.uv, T.nn, B.cull_mode, edge_vis, F.width, F.height, meta, &tv, &tsh, &bin.bbx, &bin.bby);
         if (vis) {
@@ -538,7 +610,7 @@ __global__ void __launch_bounds__(128) k_clip_emit(SceneDev S, Workspace Wk) {
         f4 Q[4];
         for (int i = 0; i < nv; ++i) Q[i] = rx_project(F.proj, poly[i].p, F.width_f, F.height_f, F.matvec_mode);
         const uint32_t first = B.owner_base + B.n_tris + Wk.chunk_new_base[(size_t)f * Wk.chunk_stride + c.chunk] + c.local_off;
-        const uint32_t meta = c.batch | (FB.alpha_test << 31);
+        const uint32_t meta = c.batch | tri_meta_flags(FB);
         for (int j = 1; j + 1 < nv; ++j) {  // fan (c0, cj, cj+1): batch3d.rs:672-678
             const f4 P[3] = {Q[0], Q[j], Q[j + 1]};
             const float2 uv[3] = {{poly[0].u, poly[0].v}, {poly[j].u, poly[j].v}, {poly[j + 1].u, poly[j + 1].v}};
@@ -594,7 +666,7 @@ __global__ void __launch_bounds__(256) k_bin_count(SceneDev S, Workspace Wk) {
         int tx0, tx1, ty0, ty1;
         bin_tile_range(F, b.bbx, b.bby, &tx0, &tx1, &ty0, &ty1);
         const int nt = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
-        if (nt > RX_LARGE_TILES) {
+        if (nt > RX_LARGE_TILES && !S.general) {  // ordered lists hold every triangle
             const uint32_t k = atomicAdd(&C.n_large, 1u);
             if (k < Wk.large_stride) Wk.large[(size_t)f * Wk.large_stride + k] = b.slot;
             else atomicOr(&C.overflow, 2u);
@@ -607,18 +679,21 @@ __global__ void __launch_bounds__(256) k_bin_count(SceneDev S, Workspace Wk) {
     }
 }
 
-__global__ void __launch_bounds__(256) k_tile_alloc(Workspace Wk, uint32_t tiles_per_frame) {
+__global__ void __launch_bounds__(256) k_tile_alloc(Workspace Wk, uint32_t tiles_per_frame, int which, int pow2) {
     const uint32_t f = blockIdx.y;
     DCounters& C = Wk.counters[f];
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= tiles_per_frame) return;
-    uint32_t* tc = Wk.tile_count + (size_t)f * Wk.tile_stride;
-    uint32_t* tb = Wk.tile_base + (size_t)f * Wk.tile_stride;
+    uint32_t* tc = (which ? Wk.tile_count2 : Wk.tile_count) + (size_t)f * Wk.tile_stride;
+    uint32_t* tb = (which ? Wk.tile_base2 : Wk.tile_base) + (size_t)f * Wk.tile_stride;
+    const uint32_t cap = which ? Wk.list2_stride : Wk.list_stride;
     const uint32_t n = tc[i];
     uint32_t base = 0;
     if (n) {
-        base = atomicAdd(&C.list_cursor, n);
-        if (base + n > Wk.list_stride) { atomicOr(&C.overflow, 1u); tc[i] = 0u; base = 0; }
+        uint32_t want = n;
+        if (pow2 && n > 1u) want = 1u << (32 - __clz(n - 1u));  // room for the sort's padding
+        base = atomicAdd(which ? &C.list_cursor2 : &C.list_cursor, want);
+        if (base + want > cap) { atomicOr(&C.overflow, which ? 8u : 1u); tc[i] = 0u; base = 0; }
     }
     tb[i] = base;
 }
@@ -678,6 +753,65 @@ __device__ __forceinline__ f3 fnormalize3(f3 a) { const float i = fast_rsqrt(fdo
 __device__ __forceinline__ float fsmooth(const DLight& l, float x) {
     const float t = rx_clamp((x - l.end_distance) * l.inv_range, 0.0f, 1.0f);
     return t * t * __fmaf_rn(-2.0f, t, 3.0f);
+}
+
+// Rasterizer::screen_to_world exactly as the reference composes it (rasterizer.rs:1707-1727): used where the
+// world position decides ownership (alpha test of a terrain texel); the shade uses the folded DFrame::s2w.
+__device__ __forceinline__ f3 screen_to_world_exact(const DFrame& F, float x, float y, float z) {
+    const float x_ndc = 2.0f * (x / F.width_f) - 1.0f;
+    const float y_ndc = 1.0f - 2.0f * (y / F.height_f);
+    f4 vs = rx_matvec4(F.inv_proj, {x_ndc, y_ndc, z, 1.0f}, F.matvec_mode);
+    vs = {vs.x / vs.w, vs.y / vs.w, vs.z / vs.w, vs.w / vs.w};
+    const f4 ws = rx_matvec4(F.inv_view, vs, F.matvec_mode);
+    return {ws.x, ws.y, ws.z};
+}
+
+// Chunk::sample_terrain_texture with scale 1 (chunk.rs:135-151) + Texture::get_pixel (texture.rs:527-538)
+__device__ __forceinline__ uint32_t terrain_sample(const uint8_t* __restrict__ arena, uint32_t tex_word, uint32_t wh, const DChunkInfo& ci,
+                                                   float wx, float wy) {
+    const int W = (int)(wh & 0xFFFFu), H = (int)(wh >> 16);
+    const float local_x = (wx / 1.0f) - (float)ci.origin_x, local_y = (wy / 1.0f) - (float)ci.origin_y;
+    const int ppt = W / ci.size;  // size != 0 is validated at upload
+    const float pixel_x = local_x * (float)ppt, pixel_y = local_y * (float)ppt;
+    const uint32_t px = rx_as_u32(rx_clamp(floorf(pixel_x), 0.0f, (float)W - 1.0f));
+    const uint32_t py = rx_as_u32(rx_clamp(floorf(pixel_y), 0.0f, (float)H - 1.0f));
+    const uint32_t x = min(px, (uint32_t)(W - 1)), y = min(py, (uint32_t)(H - 1));
+    return __ldg(reinterpret_cast<const uint32_t*>(arena) + tex_word + y * (uint32_t)W + x);
+}
+
+// first sector containing the point (chunk.rs:154-161, mini.rs:58-65, bbox.rs:35-40); chunk < 0 = the mapmini
+__device__ __forceinline__ float sector_occlusion(const SceneDev& S, int chunk, float x, float y) {
+    const DChunkInfo ci = S.chunk_info[chunk >= 0 ? (uint32_t)chunk : S.n_scene_chunks];
+    for (uint32_t i = 0; i < ci.n_sectors; ++i) {
+        const DSector b = S.sectors[ci.sector_off + i];
+        if (x >= b.minx && x <= b.maxx && y >= b.miny && y <= b.maxy) return b.occlusion;
+    }
+    return 1.0f;
+}
+
+// opacity-layer state of the thread's 2x2 pixels (general mode): nearest opacity fragment so far and the
+// surface id it wrote (rasterizer.rs:1647-1651)
+struct Opa4 {
+    float z[4];
+    uint32_t own[4];
+    uint32_t sid[4];
+    uint32_t some;   // bit k: sid[k] is Some(..)
+};
+
+// barycentrics and depth of a fragment, the arithmetic of test_fragment (rasterizer.rs:1754-1773, :1054-1056)
+__device__ __forceinline__ float fragment_depth(const float4 q0, const float4 q1, const float4 q2, uint32_t meta, float fpx, float fpy,
+                                                float* alpha_out, float* beta_out) {
+    const float acx = q1.x - q0.x, acy = q1.y - q0.y;
+    const float apx = fpx - q0.x, apy = fpy - q0.y;
+    const float pcx = q1.x - fpx, pcy = q1.y - fpy, pbx = q0.z - fpx, pby = q0.w - fpy;
+    const float na = pcx * pby - pcy * pbx, nb = acx * apy - acy * apx;
+    float alpha, beta;
+    if (meta & RX_META_FASTDIV) { alpha = rx_div_by(na, q2.x, q1.z); beta = rx_div_by(nb, q2.x, q1.z); }
+    else { alpha = na / q2.x; beta = nb / q2.x; }
+    const float gamma = 1.0f - alpha - beta;
+    const float one_over_z = q2.y * alpha + q2.z * beta + q2.w * gamma;
+    *alpha_out = alpha; *beta_out = beta;
+    return 1.0f / one_over_z;
 }
 
 // CompiledLight::radiance_at for the 3D path (light.rs:504-653): incoming colour times Lambert for
@@ -747,6 +881,15 @@ __device__ __forceinline__ uint32_t shade_owner(const SceneDev& S, const DFrame&
     const uint32_t flags = d0.z;
     const float gamma = 1.0f - alpha - beta;
 
+    // screen_to_world, rasterizer.rs:1707-1727, folded into one affine map + divide (DFrame::s2w)
+    const float hx = __fmaf_rn(F.s2w[2], z, __fmaf_rn(F.s2w[1], fpy, __fmaf_rn(F.s2w[0], fpx, F.s2w[3])));
+    const float hy = __fmaf_rn(F.s2w[6], z, __fmaf_rn(F.s2w[5], fpy, __fmaf_rn(F.s2w[4], fpx, F.s2w[7])));
+    const float hz = __fmaf_rn(F.s2w[10], z, __fmaf_rn(F.s2w[9], fpy, __fmaf_rn(F.s2w[8], fpx, F.s2w[11])));
+    const float hw = __fmaf_rn(F.s2w[14], z, __fmaf_rn(F.s2w[13], fpy, __fmaf_rn(F.s2w[12], fpx, F.s2w[15])));
+    const float ihw = fast_rcp(hw);
+    const f3 world = {hx * ihw, hy * ihw, hz * ihw};
+    const f3 view_dir = fnormalize3({F.cam[0] - world.x, F.cam[1] - world.y, F.cam[2] - world.z});
+
     uint32_t texel = d0.w;
     if (flags & RX_SD_TEXTURED) {
         // perspective-correct UV, rasterizer.rs:1062-1076.  The owner is decided; the quotients are
@@ -759,16 +902,9 @@ __device__ __forceinline__ uint32_t shade_owner(const SceneDev& S, const DFrame&
         u = __fmaf_rn(__fmaf_rn(-irw, u, iu), rr, u);
         v = __fmaf_rn(__fmaf_rn(-irw, v, iv), rr, v);
         texel = sample_desc(S.arena, d0.x, d0.y, flags, u, v, sample_mode);
+    } else if (flags & RX_SD_TERRAIN) {
+        texel = terrain_sample(S.arena, d0.x, d0.y, S.chunk_info[__float_as_int(d1.w)], world.x, world.z);
     }
-
-    // screen_to_world, rasterizer.rs:1707-1727, folded into one affine map + divide (DFrame::s2w)
-    const float hx = __fmaf_rn(F.s2w[2], z, __fmaf_rn(F.s2w[1], fpy, __fmaf_rn(F.s2w[0], fpx, F.s2w[3])));
-    const float hy = __fmaf_rn(F.s2w[6], z, __fmaf_rn(F.s2w[5], fpy, __fmaf_rn(F.s2w[4], fpx, F.s2w[7])));
-    const float hz = __fmaf_rn(F.s2w[10], z, __fmaf_rn(F.s2w[9], fpy, __fmaf_rn(F.s2w[8], fpx, F.s2w[11])));
-    const float hw = __fmaf_rn(F.s2w[14], z, __fmaf_rn(F.s2w[13], fpy, __fmaf_rn(F.s2w[12], fpx, F.s2w[15])));
-    const float ihw = fast_rcp(hw);
-    const f3 world = {hx * ihw, hy * ihw, hz * ihw};
-    const f3 view_dir = fnormalize3({F.cam[0] - world.x, F.cam[1] - world.y, F.cam[2] - world.z});
 
     f3 normal = {0.0f, 0.0f, 0.0f};
     if (flags & RX_SD_NORMALS) {  // rasterizer.rs:1083-1099
@@ -791,7 +927,11 @@ __device__ __forceinline__ uint32_t shade_owner(const SceneDev& S, const DFrame&
     const float hemi = 0.5f * (normal.y + 1.0f);
     const f3 kd = rx_scale3(base, 1.0f - 0.04f);
     f3 amb = {d1.x, d1.y, d1.z};                                                        // :1368-1370
-    if (F.has_ambient) amb = {amb.x + F.ambient[0], amb.y + F.ambient[1], amb.z + F.ambient[2]};  // :1334-1365
+    if (F.has_ambient) {  // :1327-1365: the sky term is scaled by the sector occlusion (0 when it is not > 0)
+        float occ = 1.0f;
+        if (S.n_sectors) { const float o = sector_occlusion(S, __float_as_int(d1.w), world.x, world.z); occ = o > 0.0f ? o : 0.0f; }
+        amb = {__fmaf_rn(F.ambient[0], occ, amb.x), __fmaf_rn(F.ambient[1], occ, amb.y), __fmaf_rn(F.ambient[2], occ, amb.z)};
+    }
     f3 lit = {amb.x * kd.x * hemi, amb.y * kd.y * hemi, amb.z * kd.z * hemi};
 
     const float n_dot_v = fmaxf(fdot3(normal, view_dir), 0.0f);
@@ -822,6 +962,54 @@ __device__ __forceinline__ uint32_t shade_owner(const SceneDev& S, const DFrame&
            (rx_f32_to_u8_saturated(l2s(lit.z)) << 16) | (a8 << 24);
 }
 
+// The opacity layer's pixel (rasterizer.rs:1500-1645): texel -> linear -> sRGB, no lighting; alpha = texel alpha.
+// Barycentrics are recomputed from the owner's record with the arithmetic of the visibility pass.
+__device__ __forceinline__ uint32_t shade_opacity(const SceneDev& S, const DFrame& F, const DFrameBatch* __restrict__ fbs,
+                                                  const TriVis* __restrict__ vis, const TriShade* __restrict__ shade, uint32_t owner,
+                                                  float fpx, float fpy, uint32_t sample_mode) {
+    const float4* q = reinterpret_cast<const float4*>(vis + owner);
+    const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+    const uint32_t meta = __ldg(&vis[owner].meta);
+    const DFrameBatch& FB = fbs[meta & RX_META_BATCH];
+    float alpha, beta;
+    const float z = fragment_depth(q0, q1, q2, meta, fpx, fpy, &alpha, &beta);
+    const float gamma = 1.0f - alpha - beta;
+    uint32_t texel = FB.sd_pixel;
+    if (FB.sd_flags & RX_SD_TEXTURED) {
+        const TriShade& sh = shade[owner];
+        const float iu = sh.uw0 * alpha + sh.uw1 * beta + sh.uw2 * gamma;
+        const float iv = sh.vw0 * alpha + sh.vw1 * beta + sh.vw2 * gamma;
+        const float irw = sh.rw0 * alpha + sh.rw1 * beta + sh.rw2 * gamma;
+        texel = sample_desc(S.arena, FB.sd_tex_word, FB.sd_wh, FB.sd_flags, iu / irw, iv / irw, sample_mode);
+    } else if (FB.sd_flags & RX_SD_TERRAIN) {
+        const float hx = __fmaf_rn(F.s2w[2], z, __fmaf_rn(F.s2w[1], fpy, __fmaf_rn(F.s2w[0], fpx, F.s2w[3])));
+        const float hz = __fmaf_rn(F.s2w[10], z, __fmaf_rn(F.s2w[9], fpy, __fmaf_rn(F.s2w[8], fpx, F.s2w[11])));
+        const float hw = __fmaf_rn(F.s2w[14], z, __fmaf_rn(F.s2w[13], fpy, __fmaf_rn(F.s2w[12], fpx, F.s2w[15])));
+        texel = terrain_sample(S.arena, FB.sd_tex_word, FB.sd_wh, S.chunk_info[FB.sd_chunk], hx / hw, hz / hw);
+    }
+    auto rt = [](uint32_t c) {  // linear_to_srgb_fast(srgb_to_linear_fast(c / 255)), rasterizer.rs:19-33
+        const float x = (float)c * (1.0f / 255.0f);
+        const float l = __fmaf_rn(0.6975f, x * x, 0.3025f) * x;
+        const float r = fast_sqrt(l);
+        return rx_f32_to_u8_saturated(__fmaf_rn(-0.055f * r, r, 1.055f * r));
+    };
+    return rt(texel & 0xFF) | (rt((texel >> 8) & 0xFF) << 8) | (rt((texel >> 16) & 0xFF) << 16) | (texel & 0xFF000000u);
+}
+
+// "Blend Opacity", rasterizer.rs:464-495: src-over of the opacity layer onto the resolved pixel
+__device__ __forceinline__ uint32_t blend_opacity(uint32_t src, uint32_t dst, bool preserve_transparency) {
+    const float src_a = (float)(src >> 24) / 255.0f, dst_a = (float)(dst >> 24) / 255.0f;
+    const float inv_a = 1.0f - src_a;
+    uint32_t out = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float sc = (float)((src >> (8 * i)) & 0xFF), dc = (float)((dst >> (8 * i)) & 0xFF);
+        out |= rx_as_u8(rx_clamp(sc * src_a + dc * inv_a, 0.0f, 255.0f)) << (8 * i);
+    }
+    const float out_a = !preserve_transparency ? 1.0f : rx_clamp(src_a + dst_a * inv_a, 0.0f, 1.0f);
+    return out | (rx_as_u8(rx_clamp(out_a * 255.0f, 0.0f, 255.0f)) << 24);
+}
+
 // src/shader/vgradient.rs:11-14 and src/shader/grid.rs:36-108
 __device__ uint32_t shade_background(const DFrame& F, int px, int py) {
     const float uvx = (float)px / F.width_f, uvy = (float)py / F.height_f;  // rasterizer.rs:296-302
@@ -849,10 +1037,23 @@ __device__ uint32_t shade_background(const DFrame& F, int px, int py) {
     return pix(0.05f);
 }
 
+// MapMini::is_visible (mini.rs:67-95): false when the segment from -> to crosses any linedef
+__device__ __forceinline__ bool los_visible(const SceneDev& S, float fx, float fy, float tx, float ty) {
+    for (uint32_t i = 0; i < S.n_linedefs; ++i) {
+        const float4 l = __ldg(S.linedefs + i);  // b1 = (l.x, l.y), b2 = (l.z, l.w)
+        const float d = (tx - fx) * (l.w - l.y) - (ty - fy) * (l.z - l.x);
+        if (d == 0.0f) continue;
+        const float u = ((l.x - fx) * (l.w - l.y) - (l.y - fy) * (l.z - l.x)) / d;
+        const float v = ((l.x - fx) * (ty - fy) - (l.y - fy) * (tx - fx)) / d;
+        if (u >= 0.0f && u <= 1.0f && v >= 0.0f && v <= 1.0f) return false;
+    }
+    return true;
+}
+
 // one 2D triangle fragment: rasterizer.rs:655-895.  `color` is the tile buffer pixel (RGBA8).
-__device__ __noinline__ uint32_t shade_2d(const uint8_t* __restrict__ arena, const DTex* __restrict__ texs, uint32_t n_lights,
-                                          const DFrame& F, const DLight* __restrict__ lights, const Tri2D& T, const DBatch2& B,
-                                          const DFrameBatch2& FB, int px, int py, float fpx, float fpy, uint32_t color) {
+__device__ __forceinline__ uint32_t shade_2d(const SceneDev& S, const DFrame& F, const DLight* __restrict__ lights, const Tri2D& T,
+                                             const DBatch2& B, const DFrameBatch2& FB, int px, int py, float fpx, float fpy,
+                                             uint32_t sample_mode, uint32_t color) {
     // barycentric_weights_2d, rasterizer.rs:1731-1750
     const float acx = T.cx - T.ax, acy = T.cy - T.ay, abx = T.bx - T.ax, aby = T.by - T.ay;
     const float apx = fpx - T.ax, apy = fpy - T.ay, pcx = T.cx - fpx, pcy = T.cy - fpy, pbx = T.bx - fpx, pby = T.by - fpy;
@@ -868,15 +1069,26 @@ __device__ __noinline__ uint32_t shade_2d(const uint8_t* __restrict__ arena, con
     const float wx = gx / F.scale2d, wy = gy / F.scale2d;
 
     uint32_t texel = 0u;
-    if (FB.tex != 0xFFFFFFFFu) texel = rx_sample(arena, texs[FB.tex], u, v, F.sample_mode, B.repeat_mode);
-    else if (B.source_kind == RXC_SRC_PIXEL) texel = B.source_pixel;
+    if (FB.tex != 0xFFFFFFFFu) {
+        const DTex tx = S.tex[FB.tex];
+        if (FB.terrain) texel = terrain_sample(S.arena, (uint32_t)(tx.offset >> 2), tx.width | (tx.height << 16), S.chunk_info[B.chunk], wx, wy);
+        else texel = rx_sample(S.arena, tx, u, v, sample_mode, B.repeat_mode);
+    } else if (B.source_kind == RXC_SRC_PIXEL) {
+        texel = B.source_pixel;
+    }
 
     if (FB.lit) {  // rasterizer.rs:799-873
         float acc[3] = {0.0f, 0.0f, 0.0f};
-        if (F.has_ambient) { acc[0] += F.ambient[0] * 1.0f; acc[1] += F.ambient[1] * 1.0f; acc[2] += F.ambient[2] * 1.0f; }
-        for (uint32_t li = 0; li < n_lights; ++li) {
+        const float occlusion = S.n_sectors ? sector_occlusion(S, B.chunk, wx, wy) : 1.0f;  // :806-812
+        if (F.has_ambient) { acc[0] += F.ambient[0] * occlusion; acc[1] += F.ambient[1] * occlusion; acc[2] += F.ambient[2] * occlusion; }
+        for (uint32_t li = 0; li < S.n_lights; ++li) {
+            const DLight& L = lights[li];
             f3 lc;
-            if (!rx_light_color_at(lights[li], {wx, 0.0f, wy}, true, &lc)) continue;
+            if (!rx_light_color_at(L, {wx, 0.0f, wy}, true, &lc)) continue;
+            if (L.light_type == RXC_LIGHT_AMBIENT_DAYLIGHT) { lc.x *= occlusion; lc.y *= occlusion; lc.z *= occlusion; }  // :826-836
+            if (L.light_type != RXC_LIGHT_AMBIENT && L.light_type != RXC_LIGHT_AMBIENT_DAYLIGHT && S.n_linedefs &&
+                !los_visible(S, wx, wy, L.px, L.pz))  // :838-846, light.position_2d() = (x, z)
+                continue;
             acc[0] += lc.x; acc[1] += lc.y; acc[2] += lc.z;
         }
         uint32_t out = texel & 0xFF000000u;
@@ -900,6 +1112,20 @@ __device__ __noinline__ uint32_t shade_2d(const uint8_t* __restrict__ arena, con
     const uint32_t da = color >> 24;
     out |= (F.preserve_transparency ? max(da, ta) : 255u) << 24;
     return out;
+}
+
+// Is pixel (x, y) plotted by rasterize_line_bresenham (rasterizer.rs:1777-1821) for the segment
+// (x0,y0) -> (x1,y1)?  With a = |dx|, b = |dy| and (u, v) the steps from the start along each axis, the
+// walk (err = a - b; x-step iff 2*err > -b; y-step iff 2*err < a) visits, for a >= b, exactly
+// v = floor((2*b*u + a - 1) / (2*a)) for u in [0, a), and symmetrically for b > a; the end point is excluded.
+// (Checked against the serial walk for every segment of a 29x29 grid, tests/test_host_api.py.)
+__device__ __forceinline__ bool line_covers(int x0, int y0, int x1, int y1, int x, int y) {
+    const long long a = llabs((long long)x1 - x0), b = llabs((long long)y1 - y0);
+    const long long u = x0 < x1 ? (long long)x - x0 : (long long)x0 - x;
+    const long long v = y0 < y1 ? (long long)y - y0 : (long long)y0 - y;
+    if (u < 0 || v < 0 || u > a || v > b || (u == a && v == b)) return false;
+    if (a >= b) return a != 0 && v == (2 * b * u + a - 1) / (2 * a);
+    return u == (2 * a * v + b - 1) / (2 * b);
 }
 
 // Conservative rectangle-vs-triangle overlap: bbox, then for each edge the rectangle corner where the
@@ -947,12 +1173,18 @@ __device__ __forceinline__ void test_fragment(const SceneDev& S, const DFrame& F
     const bool pass_z = (z < best_z) || (z == best_z && best != RX_OWNER_NONE && slot < best);
     if (!pass_z) return;
     if (meta & RX_META_ALPHA) {  // alpha test: texel alpha must be 255 to write (:1408)
-        const TriShade& sh = shade[slot];
-        const float iu = sh.uw0 * alpha + sh.uw1 * beta + sh.uw2 * gamma;
-        const float iv = sh.vw0 * alpha + sh.vw1 * beta + sh.vw2 * gamma;
-        const float irw = sh.rw0 * alpha + sh.rw1 * beta + sh.rw2 * gamma;
         const DFrameBatch& FB = fbs[meta & RX_META_BATCH];
-        const uint32_t texel = sample_desc(S.arena, FB.sd_tex_word, FB.sd_wh, FB.sd_flags, iu / irw, iv / irw, sample_mode);
+        uint32_t texel;
+        if (FB.sd_flags & RX_SD_TERRAIN) {
+            const f3 world = screen_to_world_exact(F, fpx, fpy, z);
+            texel = terrain_sample(S.arena, FB.sd_tex_word, FB.sd_wh, S.chunk_info[FB.sd_chunk], world.x, world.z);
+        } else {
+            const TriShade& sh = shade[slot];
+            const float iu = sh.uw0 * alpha + sh.uw1 * beta + sh.uw2 * gamma;
+            const float iv = sh.vw0 * alpha + sh.vw1 * beta + sh.vw2 * gamma;
+            const float irw = sh.rw0 * alpha + sh.rw1 * beta + sh.rw2 * gamma;
+            texel = sample_desc(S.arena, FB.sd_tex_word, FB.sd_wh, FB.sd_flags, iu / irw, iv / irw, sample_mode);
+        }
         if ((texel >> 24) != 255u) return;
     }
     best_z = z; best = slot; best_al = alpha; best_be = beta;
@@ -960,9 +1192,10 @@ __device__ __forceinline__ void test_fragment(const SceneDev& S, const DFrame& F
 
 // coverage of one staged triangle over the thread's 2x2 pixels (rasterizer.rs:1020-1036), then the
 // depth test of the covered ones.  `valid` masks pixels outside the frame.
+template <bool GENERAL>
 __device__ __forceinline__ void process_record(const SceneDev& S, const DFrame& F, const DFrameBatch* __restrict__ fbs,
                                                const TriShade* __restrict__ shade, const TriVis* Tp, uint32_t slot, bool full, int px0,
-                                               int py0, float fx0, float fy0, uint32_t valid, uint32_t sample_mode, Vis4& V) {
+                                               int py0, float fx0, float fy0, uint32_t valid, uint32_t sample_mode, Vis4& V, Opa4& O) {
     const float4* q = reinterpret_cast<const float4*>(Tp);
     const float4 q5 = q[5];
     const uint32_t bbx = __float_as_uint(q5.y), bby = __float_as_uint(q5.z), meta = __float_as_uint(q5.w);
@@ -987,6 +1220,31 @@ __device__ __forceinline__ void process_record(const SceneDev& S, const DFrame& 
         if (!m) return;
     }
     const float4 q0 = q[0], q1 = q[1], q2 = q[2];
+    if (GENERAL) {
+        // records arrive in submission order: the opacity layer and the surface ids evolve sequentially
+        // (rasterizer.rs:314-357, :1041-1047, :1647-1651)
+        const DFrameBatch& FB = fbs[meta & RX_META_BATCH];
+        const uint32_t profile = FB.sd_profile;
+        const bool has_profile = (FB.sd_flags & RX_SD_HAS_PROFILE) != 0u;
+        if (meta & RX_META_OPACITY) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!(m & (1u << k))) continue;
+                float al, be;
+                const float z = fragment_depth(q0, q1, q2, meta, (k & 1) ? fx1 : fx0, (k & 2) ? fy1 : fy0, &al, &be);
+                if (z < O.z[k]) {
+                    O.z[k] = z; O.own[k] = slot; O.sid[k] = profile;
+                    O.some = has_profile ? (O.some | (1u << k)) : (O.some & ~(1u << k));
+                }
+            }
+            return;
+        }
+        if (has_profile) {  // wall geometry behind an opacity batch of the same profile is skipped
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if ((O.some & (1u << k)) && O.sid[k] == profile) m &= ~(1u << k);
+        }
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         if (m & (1u << k))
@@ -995,17 +1253,38 @@ __device__ __forceinline__ void process_record(const SceneDev& S, const DFrame& 
     }
 }
 
+// one 2D record against one pixel: triangle (rasterizer.rs:640-895) or Bresenham line (:901-955, :1777-1821)
+__device__ __forceinline__ uint32_t apply_2d(const SceneDev& S, const DFrame& F, const DLight* __restrict__ lights,
+                                            const DFrameBatch2* __restrict__ fb2, const Tri2D& T, int px, int py, uint32_t sample_mode,
+                                            uint32_t color) {
+    const int x0 = T.bbx & 0xFFFF, x1 = T.bbx >> 16, y0 = T.bby & 0xFFFF, y1 = T.bby >> 16;
+    if (px < x0 || px >= x1 || py < y0 || py >= y1) return color;
+    const DBatch2& B = S.b2[T.batch];
+    if (T.kind != 0u) {
+        if (!line_covers(__float_as_int(T.ax), __float_as_int(T.ay), __float_as_int(T.bx), __float_as_int(T.by), px, py)) return color;
+        return B.source_kind == RXC_SRC_PIXEL ? B.source_pixel : 0xFFFFFFFFu;  // crate::WHITE
+    }
+    const float fpx = (float)px + 0.5f, fpy = (float)py + 0.5f;
+    if ((T.ea[0] * fpx + T.eb[0] * fpy + T.ec[0]) < 0.0f) return color;
+    if ((T.ea[1] * fpx + T.eb[1] * fpy + T.ec[1]) < 0.0f) return color;
+    if ((T.ea[2] * fpx + T.eb[2] * fpy + T.ec[2]) < 0.0f) return color;
+    return shade_2d(S, F, lights, T, B, fb2[T.batch], px, py, fpx, fpy, sample_mode, color);
+}
+
 // SAMPLE: 0 nearest / 1 linear for every frame of the launch, 2 = read it per frame.  PLANES: owner/depth outputs.
-template <int SAMPLE, bool PLANES>
+// GENERAL: the tile lists are sorted by submission ordinal and hold every triangle (no large list): chunk opacity
+// batches with their surface ids are evaluated sequentially, and 2D records come from sorted per-tile lists.
+template <int SAMPLE, bool PLANES, bool GENERAL>
 __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raster(SceneDev S, Workspace Wk, RasterOut out, uint32_t n_frames,
                                                                uint32_t tiles_per_frame) {
-    __shared__ __align__(16) TriVis s_large[RX_LARGE_CACHE];
-    __shared__ uint32_t s_large_slot[RX_LARGE_CACHE];
-    __shared__ uint16_t s_sel[RX_LARGE_CACHE];
+    __shared__ __align__(16) TriVis s_large[GENERAL ? 1 : RX_LARGE_CACHE];
+    __shared__ uint32_t s_large_slot[GENERAL ? 1 : RX_LARGE_CACHE];
+    __shared__ uint16_t s_sel[GENERAL ? 1 : RX_LARGE_CACHE];
     __shared__ uint32_t s_nsel;
-    __shared__ int32_t s_work[4];   // frame (-1 = done), tile x0, tile y0
+    __shared__ int32_t s_work[4];   // frame (-1 = done), tile x0, tile y0, tile index
     __shared__ __align__(16) uint32_t s_color[RX_TILE_H * RX_COLOR_STRIDE];
     __shared__ float4 s_state[4 * RX_TILE_THREADS];  // (z, owner, alpha, beta) of pixel k of thread t at [k*256 + t]
+    __shared__ float2 s_ostate[GENERAL ? 4 * RX_TILE_THREADS : 1];  // (z, owner) of the opacity layer
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // warp w covers a 16x8 region (2 across, 4 down); lane (lx, ly) of the 8x4 lane grid owns the
@@ -1051,31 +1330,36 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                                ((px0 < fw && py0 + 4 < fy1) ? 4u : 0u) | ((px0 + 8 < fw && py0 + 4 < fy1) ? 8u : 0u);
 
         Vis4 V;  // z_buffer starts at 1.0 (rasterizer.rs:287)
+        Opa4 O;  // z_buffer_opacity starts at 1.0, surface_id at None (:288-290)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { V.z[k] = 1.0f; V.own[k] = RX_OWNER_NONE; V.al[k] = 0.0f; V.be[k] = 0.0f; }
+        for (int k = 0; k < 4; ++k) {
+            V.z[k] = 1.0f; V.own[k] = RX_OWNER_NONE; V.al[k] = 0.0f; V.be[k] = 0.0f;
+            O.z[k] = 1.0f; O.own[k] = RX_OWNER_NONE; O.sid[k] = 0u;
+        }
+        O.some = 0u;
 
         if (F.d3_active) {
-            const uint32_t n_large = min(C.n_large, Wk.large_stride);
+            const uint32_t n_large = GENERAL ? 0u : min(C.n_large, Wk.large_stride);
             const uint32_t* large = Wk.large + (size_t)f * Wk.large_stride;
-            // (1) large triangles: records cached in shared memory per frame, culled per tile, then per warp region
-            if (f != cached_frame) {
-                n_cached = min(n_large, (uint32_t)RX_LARGE_CACHE);
-                const float4* g = reinterpret_cast<const float4*>(vis);
-                float4* s = reinterpret_cast<float4*>(s_large);
-                for (uint32_t i = tid; i < n_cached * 6u; i += RX_TILE_THREADS) {
-                    const uint32_t r = i / 6u, q = i - r * 6u;
-                    const uint32_t slot = __ldg(large + r);
-                    if (q == 0) s_large_slot[r] = slot;
-                    s[i] = __ldg(g + (size_t)slot * 6u + q);
+            if (!GENERAL) {
+                // (1) large triangles: records cached in shared memory per frame, culled per tile, then per warp region
+                if (f != cached_frame) {
+                    n_cached = min(n_large, (uint32_t)RX_LARGE_CACHE);
+                    const float4* g = reinterpret_cast<const float4*>(vis);
+                    float4* sq = reinterpret_cast<float4*>(s_large);
+                    for (uint32_t i = tid; i < n_cached * 6u; i += RX_TILE_THREADS) {
+                        const uint32_t r = i / 6u, q = i - r * 6u;
+                        const uint32_t slot = __ldg(large + r);
+                        if (q == 0) s_large_slot[r] = slot;
+                        sq[i] = __ldg(g + (size_t)slot * 6u + q);
+                    }
+                    cached_frame = f;
+                    __syncthreads();
                 }
-                cached_frame = f;
-                __syncthreads();
-            }
-            if (n_cached > 32u) {  // two-level: tile-level selection by the CTA, then per warp region
-                if (tid < n_cached && rect_overlaps(s_large[tid], tx0, ty0, tx1, ty1) != 0u) s_sel[atomicAdd(&s_nsel, 1u)] = (uint16_t)tid;
-                __syncthreads();
-            }
-            {
+                if (n_cached > 32u) {  // two-level: tile-level selection by the CTA, then per warp region
+                    if (tid < n_cached && rect_overlaps(s_large[tid], tx0, ty0, tx1, ty1) != 0u) s_sel[atomicAdd(&s_nsel, 1u)] = (uint16_t)tid;
+                    __syncthreads();
+                }
                 const uint32_t n = n_cached > 32u ? s_nsel : n_cached;
                 for (uint32_t base = 0; base < n; base += 32) {
                     const uint32_t i = base + lane;
@@ -1087,17 +1371,19 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                         const int b = __ffs(mask) - 1;
                         mask &= mask - 1u;
                         const uint32_t rr = __shfl_sync(0xFFFFFFFFu, r, b);
-                        process_record(S, F, fbs, shade, &s_large[rr], s_large_slot[rr], (fullm >> b) & 1u, px0, py0, fx0, fy0, valid, smode, V);
+                        process_record<false>(S, F, fbs, shade, &s_large[rr], s_large_slot[rr], (fullm >> b) & 1u, px0, py0, fx0, fy0, valid,
+                                              smode, V, O);
                     }
                 }
             }
             // (2) the rest of the large list, then the tile's binned list.  Warp-private: every lane fetches one
             // record of the list from L2/L1 and tests it against the warp's region, the survivors are then read
             // by the whole warp (broadcast loads of lines the warp just touched) -- no staging, no CTA barrier.
+            // Lanes and mask bits are visited in list order, which general mode relies on.
             const uint32_t n_list = Wk.tile_count[(size_t)f * Wk.tile_stride + tile];
             const uint32_t* list = Wk.lists + (size_t)f * Wk.list_stride + Wk.tile_base[(size_t)f * Wk.tile_stride + tile];
 #pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
+            for (int pass = GENERAL ? 1 : 0; pass < 2; ++pass) {
                 const uint32_t* src = pass == 0 ? large + n_cached : list;
                 const uint32_t n_src = pass == 0 ? n_large - n_cached : n_list;
 #pragma unroll 1
@@ -1114,7 +1400,7 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                         const int b = __ffs(mask) - 1;
                         mask &= mask - 1u;
                         const uint32_t rr = __shfl_sync(0xFFFFFFFFu, slot, b);
-                        process_record(S, F, fbs, shade, vis + rr, rr, (fullm >> b) & 1u, px0, py0, fx0, fy0, valid, smode, V);
+                        process_record<GENERAL>(S, F, fbs, shade, vis + rr, rr, (fullm >> b) & 1u, px0, py0, fx0, fy0, valid, smode, V, O);
                     }
                 }
             }
@@ -1122,29 +1408,16 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
 
         // resolve, one pixel of the 2x2 at a time (the visibility state goes through shared memory so the
         // shading code is not unrolled and does not hold it in registers): deferred shade of the owner,
-        // miss pass (rasterizer.rs:409-461) or the 2D-only background, 2D pass
+        // miss pass (rasterizer.rs:409-461) or the 2D-only background, opacity blend (:464-495)
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < 4; ++k) {
             s_state[k * RX_TILE_THREADS + tid] = make_float4(V.z[k], __uint_as_float(V.own[k]), V.al[k], V.be[k]);
-        const Tri2D* recs = Wk.tri2d + (size_t)f * Wk.tri2d_stride;
-        const DFrameBatch2* fb2 = Wk.fb2 + (size_t)f * Wk.fb2_stride;
-        // 2D records whose bbox meets this warp's region: one ballot per 32 records, hoisted for the first 32
-        uint32_t mask2d = 0u;
-        if (F.d2_active) {
-            bool hit = false;
-            if (lane < S.n_rec2d && region_ok) {
-                const uint32_t bbx = recs[lane].bbx, bby = recs[lane].bby;
-                const int x0 = bbx & 0xFFFF, x1 = bbx >> 16, y0 = bby & 0xFFFF, y1 = bby >> 16;
-                hit = !(x0 >= rx1 || x1 <= rx0 || y0 >= ry1 || y1 <= ry0);
-            }
-            mask2d = __ballot_sync(0xFFFFFFFFu, hit);
+            if (GENERAL) s_ostate[k * RX_TILE_THREADS + tid] = make_float2(O.z[k], __uint_as_float(O.own[k]));
         }
-        const bool more2d = F.d2_active && S.n_rec2d > 32u;
 #pragma unroll 1
         for (int k = 0; k < 4; ++k) {
             const int px = px0 + ((k & 1) << 3), py = py0 + ((k >> 1) << 2);
             const float fpx = (float)px + 0.5f, fpy = (float)py + 0.5f;
-            const bool in_frame = px < fw && py < fy1;
             const float4 st = s_state[k * RX_TILE_THREADS + tid];
             const uint32_t owner = __float_as_uint(st.y);
             uint32_t color;
@@ -1155,39 +1428,53 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                 } else {
                     color = 0xFF000000u;  // vec4_to_pixel((0,0,0,1))
                 }
+                if (GENERAL) {
+                    const float2 os = s_ostate[k * RX_TILE_THREADS + tid];
+                    if (os.x < 1.0f && st.x > os.x)
+                        color = blend_opacity(shade_opacity(S, F, fbs, vis, shade, __float_as_uint(os.y), fpx, fpy, smode), color,
+                                              F.preserve_transparency != 0u);
+                }
             } else {
                 color = F.has_bg_color ? F.bg_color : 0u;  // rasterizer.rs:277-282
                 if (!F.ignore_bg_shader && F.bg_shader != RXC_BG_NONE) color = shade_background(F, px, py);
             }
-            if (mask2d | (uint32_t)more2d) {  // rasterizer.rs:501-553: every 2D record in submission order
-                for (uint32_t base = 0; base < S.n_rec2d; base += 32) {
-                    uint32_t mk = mask2d;
-                    if (base) {
-                        bool hit = false;
-                        if (base + lane < S.n_rec2d && region_ok) {
-                            const uint32_t bbx = recs[base + lane].bbx, bby = recs[base + lane].bby;
-                            const int x0 = bbx & 0xFFFF, x1 = bbx >> 16, y0 = bby & 0xFFFF, y1 = bby >> 16;
-                            hit = !(x0 >= rx1 || x1 <= rx0 || y0 >= ry1 || y1 <= ry0);
-                        }
-                        mk = __ballot_sync(0xFFFFFFFFu, hit);
-                    }
-                    while (mk) {
-                        const Tri2D& T = recs[base + (uint32_t)(__ffs(mk) - 1)];
-                        mk &= mk - 1u;
-                        const int x0 = T.bbx & 0xFFFF, x1 = T.bbx >> 16, y0 = T.bby & 0xFFFF, y1 = T.bby >> 16;
-                        if (px < x0 || px >= x1 || py < y0 || py >= y1) continue;
-                        if ((T.ea[0] * fpx + T.eb[0] * fpy + T.ec[0]) < 0.0f) continue;
-                        if ((T.ea[1] * fpx + T.eb[1] * fpy + T.ec[1]) < 0.0f) continue;
-                        if ((T.ea[2] * fpx + T.eb[2] * fpy + T.ec[2]) < 0.0f) continue;
-                        color = shade_2d(S.arena, S.tex, S.n_lights, F, lights, T, S.b2[T.batch], fb2[T.batch], px, py, fpx, fpy, color);
-                    }
-                }
-            }
             s_color[(py - ty0) * RX_COLOR_STRIDE + (px - tx0)] = color;
-            if (PLANES && in_frame) {
+            if (PLANES && px < fw && py < fy1) {
                 const size_t o = (size_t)(py - F.band_y0) * (size_t)fw + (size_t)px;
                 if (out.owner) out.owner[o] = owner;
                 if (out.depth) out.depth[o] = st.x;
+            }
+        }
+
+        // 2D pass in submission order (rasterizer.rs:501-553) over the thread's own pixels in s_color
+        if (F.d2_active && S.n_rec2d != 0u && region_ok) {
+            const Tri2D* recs = Wk.tri2d + (size_t)f * Wk.tri2d_stride;
+            const DFrameBatch2* fb2 = Wk.fb2 + (size_t)f * Wk.fb2_stride;
+            const uint32_t n2 = GENERAL ? Wk.tile_count2[(size_t)f * Wk.tile_stride + tile] : S.n_rec2d;
+            const uint32_t* list2 = GENERAL ? Wk.lists2 + (size_t)f * Wk.list2_stride + Wk.tile_base2[(size_t)f * Wk.tile_stride + tile] : nullptr;
+#pragma unroll 1
+            for (uint32_t base = 0; base < n2; base += 32) {
+                const uint32_t i = base + lane;
+                uint32_t r = 0u;
+                bool hit = false;
+                if (i < n2) {
+                    r = GENERAL ? __ldg(list2 + i) : i;
+                    const uint32_t bbx = recs[r].bbx, bby = recs[r].bby;
+                    const int x0 = bbx & 0xFFFF, x1 = bbx >> 16, y0 = bby & 0xFFFF, y1 = bby >> 16;
+                    hit = !(x0 >= rx1 || x1 <= rx0 || y0 >= ry1 || y1 <= ry0);
+                }
+                uint32_t mask = __ballot_sync(0xFFFFFFFFu, hit);
+                while (mask) {
+                    const int b = __ffs(mask) - 1;
+                    mask &= mask - 1u;
+                    const Tri2D& T = recs[__shfl_sync(0xFFFFFFFFu, r, b)];
+#pragma unroll 1
+                    for (int k = 0; k < 4; ++k) {
+                        const int px = px0 + ((k & 1) << 3), py = py0 + ((k >> 1) << 2);
+                        uint32_t* c = &s_color[(py - ty0) * RX_COLOR_STRIDE + (px - tx0)];
+                        *c = apply_2d(S, F, lights, fb2, T, px, py, smode, *c);
+                    }
+                }
             }
         }
         __syncthreads();
@@ -1210,6 +1497,65 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
         }
         __syncthreads();  // s_color, s_work and s_nsel are rewritten by the next tile
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2D record binning (general mode): one warp per record, lanes over the tiles of its bbox
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bin2d(SceneDev S, Workspace Wk, int fill) {
+    const uint32_t f = blockIdx.y;
+    const DFrame& F = Wk.frames[f];
+    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= S.n_rec2d) return;
+    const Tri2D& T = Wk.tri2d[(size_t)f * Wk.tri2d_stride + r];
+    int tx0, tx1, ty0, ty1;
+    if (!bin_tile_range(F, T.bbx, T.bby, &tx0, &tx1, &ty0, &ty1)) return;
+    uint32_t* tc = Wk.tile_count2 + (size_t)f * Wk.tile_stride;
+    const uint32_t* tb = Wk.tile_base2 + (size_t)f * Wk.tile_stride;
+    uint32_t* tf = Wk.tile_fill2 + (size_t)f * Wk.tile_stride;
+    uint32_t* lists = Wk.lists2 + (size_t)f * Wk.list2_stride;
+    const int w = tx1 - tx0 + 1, n = w * (ty1 - ty0 + 1);
+    for (int i = (int)lane; i < n; i += 32) {
+        const int t = (ty0 + i / w) * F.tiles_x + tx0 + i % w;
+        if (!fill) { atomicAdd(&tc[t], 1u); continue; }
+        if (tc[t] == 0u) continue;  // list dropped on arena overflow
+        lists[tb[t] + atomicAdd(&tf[t], 1u)] = r;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_list_sort (general mode): one CTA per tile sorts its list ascending (= submission order).  The
+// allocation of a list is a power of two (k_tile_alloc), the tail is padded with 0xFFFFFFFF.
+// ---------------------------------------------------------------------------------------------
+#define RX_SORT_SMEM 4096
+__global__ void __launch_bounds__(256) k_list_sort(Workspace Wk, int which) {
+    __shared__ uint32_t sm[RX_SORT_SMEM];
+    const uint32_t f = blockIdx.y, t = blockIdx.x, tid = threadIdx.x;
+    const uint32_t n = (which ? Wk.tile_count2 : Wk.tile_count)[(size_t)f * Wk.tile_stride + t];
+    if (n < 2u) return;
+    uint32_t* list = (which ? Wk.lists2 + (size_t)f * Wk.list2_stride : Wk.lists + (size_t)f * Wk.list_stride) +
+                     (which ? Wk.tile_base2 : Wk.tile_base)[(size_t)f * Wk.tile_stride + t];
+    const uint32_t P = 1u << (32 - __clz(n - 1u));
+    uint32_t* d = P <= RX_SORT_SMEM ? sm : list;
+    for (uint32_t i = tid; i < P; i += blockDim.x) {
+        if (P <= RX_SORT_SMEM) sm[i] = i < n ? list[i] : 0xFFFFFFFFu;
+        else if (i >= n) list[i] = 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    for (uint32_t k = 2; k <= P; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = tid; i < P; i += blockDim.x) {
+                const uint32_t ixj = i ^ j;
+                if (ixj > i) {
+                    const uint32_t a = d[i], b = d[ixj];
+                    if ((a > b) == ((i & k) == 0u)) { d[i] = b; d[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (P <= RX_SORT_SMEM)
+        for (uint32_t i = tid; i < n; i += blockDim.x) list[i] = sm[i];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1292,10 +1638,23 @@ cudaError_t rxk_bin_count(const SceneDev& S, const Workspace& W, uint32_t n_fram
     k_bin_count<<<grid, 256, 0, st>>>(S, W);
     return cudaGetLastError();
 }
-cudaError_t rxk_tile_alloc(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, cudaStream_t st) {
+cudaError_t rxk_tile_alloc(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, int which, int pow2,
+                           cudaStream_t st) {
     (void)S;
     dim3 grid((tiles_per_frame + 255) / 256, n_frames);
-    k_tile_alloc<<<grid, 256, 0, st>>>(W, tiles_per_frame);
+    k_tile_alloc<<<grid, 256, 0, st>>>(W, tiles_per_frame, which, pow2);
+    return cudaGetLastError();
+}
+cudaError_t rxk_bin2d(const SceneDev& S, const Workspace& W, uint32_t n_frames, int fill, cudaStream_t st) {
+    if (S.n_rec2d == 0) return cudaSuccess;
+    dim3 grid((S.n_rec2d + 7) / 8, n_frames);
+    k_bin2d<<<grid, 256, 0, st>>>(S, W, fill);
+    return cudaGetLastError();
+}
+cudaError_t rxk_list_sort(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, int which, cudaStream_t st) {
+    (void)S;
+    dim3 grid(tiles_per_frame, n_frames);
+    k_list_sort<<<grid, 256, 0, st>>>(W, which);
     return cudaGetLastError();
 }
 cudaError_t rxk_bin_fill(const SceneDev& S, const Workspace& W, uint32_t n_frames, int grid_x, cudaStream_t st) {
@@ -1307,17 +1666,19 @@ cudaError_t rxk_bin_fill(const SceneDev& S, const Workspace& W, uint32_t n_frame
 cudaError_t rxk_raster(const SceneDev& S, const Workspace& W, const RasterOut& out, uint32_t n_frames, uint32_t tiles_per_frame,
                        int sample_mode, int grid_x, cudaStream_t st) {
     const bool planes = out.owner || out.depth;
-#define RX_LAUNCH(SM, PL) k_raster<SM, PL><<<grid_x, RX_TILE_THREADS, 0, st>>>(S, W, out, n_frames, tiles_per_frame)
-    if (sample_mode == 0) { if (planes) RX_LAUNCH(0, true); else RX_LAUNCH(0, false); }
-    else if (sample_mode == 1) { if (planes) RX_LAUNCH(1, true); else RX_LAUNCH(1, false); }
-    else { if (planes) RX_LAUNCH(2, true); else RX_LAUNCH(2, false); }
+#define RX_LAUNCH(SM, PL, GE) k_raster<SM, PL, GE><<<grid_x, RX_TILE_THREADS, 0, st>>>(S, W, out, n_frames, tiles_per_frame)
+#define RX_LAUNCH2(SM, PL) do { if (S.general) RX_LAUNCH(SM, PL, true); else RX_LAUNCH(SM, PL, false); } while (0)
+    if (sample_mode == 0) { if (planes) RX_LAUNCH2(0, true); else RX_LAUNCH2(0, false); }
+    else if (sample_mode == 1) { if (planes) RX_LAUNCH2(1, true); else RX_LAUNCH2(1, false); }
+    else { if (planes) RX_LAUNCH2(2, true); else RX_LAUNCH2(2, false); }
+#undef RX_LAUNCH2
 #undef RX_LAUNCH
     return cudaGetLastError();
 }
 int rxk_raster_blocks_per_sm() {
     int n = 0, best = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_raster<0, false>, RX_TILE_THREADS, 0) == cudaSuccess) best = n;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_raster<1, false>, RX_TILE_THREADS, 0) == cudaSuccess && n < best) best = n;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_raster<0, false, false>, RX_TILE_THREADS, 0) == cudaSuccess) best = n;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_raster<1, false, false>, RX_TILE_THREADS, 0) == cudaSuccess && n < best) best = n;
     return best < 1 ? 1 : best;
 }
 cudaError_t rxk_selftest_div(uint64_t seed, uint32_t blocks, uint32_t iters, unsigned long long* d_mismatches, cudaStream_t st) {

@@ -25,6 +25,12 @@ struct SceneDev {
     const DTex* tex;
     const DTile* tiles;         // static tiles first, then dynamic tiles
     const uint8_t* arena;
+    const DSector* sectors;     // occluded sectors of every chunk, then of the mapmini
+    const DChunkInfo* chunk_info; // [n_scene_chunks + 1]; the last entry is the mapmini
+    const float4* linedefs;     // (start.xy, end.xy) of mapmini.linedefs
+    uint32_t n_scene_chunks, n_linedefs, n_actor_tiles;
+    uint32_t n_sectors;         // total entries of `sectors` (0: every occlusion is 1)
+    uint32_t general;           // ordered 3D lists (opacity batches) and binned 2D lists (many 2D records)
     uint32_t n_b3, n_b2, n_chunks, n_lights;
     uint32_t n_tris, n_verts;   // 3D totals
     uint32_t n_rec2d;           // 2D records per frame
@@ -49,6 +55,10 @@ struct Workspace {
     uint32_t* tile_base;
     uint32_t* tile_fill;    uint32_t tile_stride;
     uint32_t* lists;        uint32_t list_stride;
+    uint32_t* tile_count2;  // 2D record lists per tile (general mode), same tile_stride
+    uint32_t* tile_base2;
+    uint32_t* tile_fill2;
+    uint32_t* lists2;       uint32_t list2_stride;
     Tri2D* tri2d;           uint32_t tri2d_stride;
     uint32_t* raster_counter;  // one work counter for the whole launch
 };
@@ -69,7 +79,9 @@ enum {
     RXK_BIN_COUNT = 4,
     RXK_TILE_ALLOC = 5,
     RXK_BIN_FILL = 6,
-    RXK_RASTER = 7
+    RXK_RASTER = 7,
+    RXK_BIN2D = 8,
+    RXK_LIST_SORT = 9
 };
 
 // Each returns the cudaError_t of the launch.  `n_frames` frames are processed by one launch.
@@ -78,7 +90,11 @@ cudaError_t rxk_tri_setup(const SceneDev& S, const Workspace& W, uint32_t n_fram
 cudaError_t rxk_batch_finalize(const SceneDev& S, const Workspace& W, uint32_t n_frames, cudaStream_t st);
 cudaError_t rxk_clip_emit(const SceneDev& S, const Workspace& W, uint32_t n_frames, int grid, cudaStream_t st);
 cudaError_t rxk_bin_count(const SceneDev& S, const Workspace& W, uint32_t n_frames, int grid, cudaStream_t st);
-cudaError_t rxk_tile_alloc(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, cudaStream_t st);
+// which: 0 = 3D lists, 1 = 2D lists; pow2: round every allocation up to a power of two (lists that get sorted)
+cudaError_t rxk_tile_alloc(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, int which, int pow2,
+                           cudaStream_t st);
+cudaError_t rxk_bin2d(const SceneDev& S, const Workspace& W, uint32_t n_frames, int fill, cudaStream_t st);
+cudaError_t rxk_list_sort(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, int which, cudaStream_t st);
 cudaError_t rxk_bin_fill(const SceneDev& S, const Workspace& W, uint32_t n_frames, int grid, cudaStream_t st);
 // sample_mode: RXC_SAMPLE_* when every frame of the launch uses it, 2 = mixed (read per frame)
 cudaError_t rxk_raster(const SceneDev& S, const Workspace& W, const RasterOut& out, uint32_t n_frames, uint32_t tiles_per_frame,

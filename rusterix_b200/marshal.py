@@ -61,19 +61,81 @@ def marshal_lights(lights):
     return Marshalled(arr, [])
 
 
-def _fill_source(o, src):
+def marshal_sectors(sectors):
+    arr = (_abi.rxc_sector * max(1, len(sectors)))()
+    for i, (bbox, occlusion) in enumerate(sectors):
+        arr[i].min[:] = [float(bbox.min[0]), float(bbox.min[1])]
+        arr[i].max[:] = [float(bbox.max[0]), float(bbox.max[1])]
+        arr[i].occlusion = float(occlusion)
+    return arr
+
+
+def marshal_mapmini(mapmini):
+    m = _abi.rxc_mapmini()
+    lines = (_abi.rxc_linedef * max(1, len(mapmini.linedefs)))()
+    for i, l in enumerate(mapmini.linedefs):
+        lines[i].start[:] = [float(l.start[0]), float(l.start[1])]
+        lines[i].end[:] = [float(l.end[0]), float(l.end[1])]
+    sectors = marshal_sectors(mapmini.occluded_sectors)
+    m.linedefs = lines
+    m.n_linedefs = len(mapmini.linedefs)
+    m.occluded_sectors = sectors
+    m.n_occluded_sectors = len(mapmini.occluded_sectors)
+    return Marshalled(m, [lines, sectors])
+
+
+def submission_order(scene: Scene):
+    """The order in which the reference walks the batches of a scene (src/rasterizer.rs:314-405 and
+    :501-553): (batch, pass tag, chunk index) for 3D and (batch, chunk index) for 2D."""
+    b3, b2 = [], []
+    for ci, chunk in enumerate(scene.chunks.values()):
+        b3 += [(b, 4, ci) for b in chunk.batches3d_opacity]
+        b3 += [(b, 3, ci) for b in chunk.batches3d]
+        if chunk.terrain_batch3d is not None:
+            b3.append((chunk.terrain_batch3d, 3, ci))
+        b2 += [(b, ci) for b in chunk.batches2d]
+        if chunk.terrain_batch2d is not None:
+            b2.append((chunk.terrain_batch2d, ci))
+    b3 += [(b, 0, -1) for b in scene.d3_static] + [(b, 1, -1) for b in scene.d3_dynamic] + [(b, 2, -1) for b in scene.d3_overlay]
+    b2 += [(b, -1) for b in scene.d2_static] + [(b, -1) for b in scene.d2_dynamic]
+    return b3, b2
+
+
+class _ActorTiles:
+    """EntityTile / ItemTile sources are resolved on the host (the id -> IndexMap lookup of
+    src/rasterizer.rs:1130-1177) to indices into one `actor_tiles` array."""
+
+    def __init__(self, assets):
+        self.assets = assets
+        self.tiles = []
+        self._index = {}
+
+    def resolve(self, src) -> int:
+        tile = self.assets.actor_tile(src) if self.assets is not None else None
+        if tile is None or not tile.textures:
+            return 0xFFFFFFFF
+        k = id(tile)
+        if k not in self._index:
+            self._index[k] = len(self.tiles)
+            self.tiles.append(tile)
+        return self._index[k]
+
+
+def _fill_source(o, src, actors):
     o.source_kind = int(src.kind)
     o.source_index = int(src.index)
+    if int(src.kind) in (4, 5):
+        o.source_index = actors.resolve(src)
     o.source_pixel[:] = list(src.pixel)
 
 
-def marshal_scene(scene: Scene, index_bytes: int = 4):
+def marshal_scene(scene: Scene, index_bytes: int = 4, assets: Assets = None):
     """index_bytes=8 marshals indices as Rust `usize` triples (24 B/triangle) to exercise that path."""
     keep = []
-    b3_list = [(b, 0) for b in scene.d3_static] + [(b, 1) for b in scene.d3_dynamic] + [(b, 2) for b in scene.d3_overlay]
-    b2_list = list(scene.d2_static) + list(scene.d2_dynamic)
+    actors = _ActorTiles(assets)
+    b3_list, b2_list = submission_order(scene)
     b3 = (_abi.rxc_batch3d * max(1, len(b3_list)))()
-    for i, (b, pass_) in enumerate(b3_list):
+    for i, (b, pass_, chunk_index) in enumerate(b3_list):
         o = b3[i]
         idx = b.indices if index_bytes == 4 else np.ascontiguousarray(b.indices.astype(np.uint64))
         keep += [b.vertices, b.uvs, b.normals, idx]
@@ -91,7 +153,7 @@ def marshal_scene(scene: Scene, index_bytes: int = 4):
         o.mode = int(b.mode)
         o.repeat_mode = int(b.repeat_mode_)
         o.cull_mode = int(b.cull_mode_)
-        _fill_source(o, b.source_)
+        _fill_source(o, b.source_, actors)
         o.receives_light = 1 if b.receives_light_ else 0
         o.ambient_color[:] = list(b.ambient_color_)
         o.has_profile_id = 0 if b.profile_id_ is None else 1
@@ -99,8 +161,9 @@ def marshal_scene(scene: Scene, index_bytes: int = 4):
         o.shader = -1 if b.shader_ is None else b.shader_
         o.pass_ = pass_
         o.transform[:] = to_cols(b.transform_3d).tolist()
+        o.chunk = chunk_index
     b2 = (_abi.rxc_batch2d * max(1, len(b2_list)))()
-    for i, b in enumerate(b2_list):
+    for i, (b, chunk_index) in enumerate(b2_list):
         o = b2[i]
         idx = b.indices if index_bytes == 4 else np.ascontiguousarray(b.indices.astype(np.uint64))
         keep += [b.vertices, b.uvs, idx]
@@ -112,11 +175,29 @@ def marshal_scene(scene: Scene, index_bytes: int = 4):
         o.index_bytes = index_bytes
         o.mode = int(b.mode)
         o.repeat_mode = int(b.repeat_mode_)
-        _fill_source(o, b.source_)
+        _fill_source(o, b.source_, actors)
         o.receives_light = 1 if b.receives_light_ else 0
         o.shader = -1 if b.shader_ is None else b.shader_
+        o.chunk = chunk_index
     lights = marshal_lights(scene.all_lights())
     dyn = marshal_tiles(scene.dynamic_textures)
+    act = marshal_tiles(actors.tiles)
+    chunks = (_abi.rxc_chunk * max(1, len(scene.chunks)))()
+    for ci, chunk in enumerate(scene.chunks.values()):
+        c = chunks[ci]
+        c.origin[:] = [int(chunk.origin[0]), int(chunk.origin[1])]
+        c.size = int(chunk.size)
+        sectors = marshal_sectors(chunk.occluded_sectors)
+        c.occluded_sectors = sectors
+        c.n_occluded_sectors = len(chunk.occluded_sectors)
+        keep.append(sectors)
+        if chunk.terrain_texture is not None:
+            t = _abi.rxc_texture()
+            t.data = chunk.terrain_texture.data.ctypes.data
+            t.width = chunk.terrain_texture.width
+            t.height = chunk.terrain_texture.height
+            c.terrain_texture = C.pointer(t)
+            keep += [t, chunk.terrain_texture.data]
     s = _abi.rxc_scene()
     s.batches3d = b3
     s.n_batches3d = len(b3_list)
@@ -126,7 +207,11 @@ def marshal_scene(scene: Scene, index_bytes: int = 4):
     s.n_lights = len(scene.all_lights())
     s.dynamic_textures = dyn.struct
     s.n_dynamic_textures = len(scene.dynamic_textures)
-    keep += [b3, b2, lights, dyn]
+    s.chunks = chunks
+    s.n_chunks = len(scene.chunks)
+    s.actor_tiles = act.struct
+    s.n_actor_tiles = len(actors.tiles)
+    keep += [b3, b2, lights, dyn, act, chunks]
     return Marshalled(s, keep)
 
 

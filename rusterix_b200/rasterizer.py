@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 
 from . import _abi, _lib, marshal, vekmath
-from .types import Assets, MatVecMode, RenderMode, SampleMode, Scene
+from .types import Assets, MapMini, MatVecMode, RenderMode, SampleMode, Scene
 
 
 class DeviceContext:
@@ -25,6 +25,7 @@ class DeviceContext:
         self._assets_key = None
         self._scene_key = None
         self._lights_key = None
+        self._mapmini_key = ((), ())
 
     @classmethod
     def get(cls, device=0) -> "DeviceContext":
@@ -59,7 +60,7 @@ class DeviceContext:
              l.end_distance, l.flicker, tuple(l.direction), l.cone_angle, tuple(l.normal), l.width, l.height,
              l.from_linedef) for l in lights)
         if skey != self._scene_key:
-            m = marshal.marshal_scene(scene, index_bytes)
+            m = marshal.marshal_scene(scene, index_bytes, assets)
             self.check(self.lib.rxc_set_scene(self.handle, C.byref(m.struct)))
             self._scene_key = skey
             self._lights_key = lkey
@@ -67,6 +68,16 @@ class DeviceContext:
             m = marshal.marshal_lights(lights)
             self.check(self.lib.rxc_set_lights(self.handle, m.struct, len(lights)))
             self._lights_key = lkey
+
+    def set_mapmini(self, mapmini):
+        key = mapmini.key() if mapmini is not None else ((), ())
+        if key != self._mapmini_key:
+            if mapmini is None:
+                self.check(self.lib.rxc_set_mapmini(self.handle, None))
+            else:
+                m = marshal.marshal_mapmini(mapmini)
+                self.check(self.lib.rxc_set_mapmini(self.handle, C.byref(m.struct)))
+            self._mapmini_key = key
 
     def selftest_div(self, n_pairs=1 << 30, seed=0x52555354) -> int:
         """Mismatches of the raster kernel's residual-corrected division against div.rn (must be 0)."""
@@ -134,6 +145,7 @@ class Rasterizer:
         self.background_color = None
         self.ambient_color = None
         self.brush_preview = None
+        self.mapmini = MapMini.default()  # src/rasterizer.rs:71
         self.preserve_transparency = False
         self.hour = 12.0
         self.time_ = 0.0
@@ -182,8 +194,13 @@ class Rasterizer:
         optional parity outputs.  `band=(y0,y1)` renders only those rows into a band-sized buffer."""
         self._check_supported()
         self.width, self.height = float(width), float(height)
+        # "We append the in-scope chunk lights to the dynamic lights" -- on every call, never cleared
+        # (src/rasterizer.rs:219-223)
+        for chunk in scene.chunks.values():
+            scene.dynamic_lights.extend(chunk.lights)
         ctx = DeviceContext.get(self.device)
         ctx.upload(scene, assets, self.index_bytes)
+        ctx.set_mapmini(self.mapmini)
         frame = marshal.make_frame(self, scene, width, height, tile_size, band)
         rows = height if band is None else band[1] - band[0]
         p, _k1 = _buffer_pointer(pixels, width * rows * 4)
@@ -200,7 +217,11 @@ class Rasterizer:
         """Marshal a camera sweep once: uploads the scene if needed and returns a FrameBatch that
         `rasterize_batch` replays with a single C call per step."""
         ctx = DeviceContext.get(device)
+        for chunk in scene.chunks.values():  # once per prepared sweep (the reference appends per rasterize call)
+            scene.dynamic_lights.extend(chunk.lights)
         ctx.upload(scene, assets, 4)
+        if rasterizers:
+            ctx.set_mapmini(rasterizers[0].mapmini)
         n = len(rasterizers)
         frames = (_abi.rxc_frame * n)()
         for i, r in enumerate(rasterizers):

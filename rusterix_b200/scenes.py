@@ -15,8 +15,8 @@ import numpy as np
 
 from .camera import D3FirstPCamera, D3OrbitCamera
 from .rasterizer import Rasterizer
-from .types import (Assets, Batch2D, Batch3D, CullMode, Light, LightType, PixelSource, RepeatMode, SampleMode,
-                    Scene, Texture, Tile, VGrayGradientShader)
+from .types import (Assets, BBox, Batch2D, Batch3D, Chunk, CompiledLinedef, CullMode, Light, LightType, MapMini,
+                    PixelSource, PrimitiveMode, RenderMode, RepeatMode, SampleMode, Scene, Texture, Tile, VGrayGradientShader)
 from . import vekmath
 
 SEED = 0x52555354
@@ -128,18 +128,27 @@ class Config:
     cameras: Optional[Callable[[int], object]] = None  # frame index -> camera (sweeps)
     n_frames: int = 1
     notes: str = ""
+    matrix2d: Optional[object] = None       # projection_matrix_2d (Mat3) of the 2D configs
+    mapmini: Optional[MapMini] = None
+    render_mode: Optional[RenderMode] = None
 
     def rasterizer(self, frame: int = 0) -> Rasterizer:
         cam = self.cameras(frame) if self.cameras is not None else self.camera
-        r = Rasterizer.setup(None, cam.view_matrix(), cam.projection_matrix(float(self.width), float(self.height)))
+        r = Rasterizer.setup(self.matrix2d, cam.view_matrix(), cam.projection_matrix(float(self.width), float(self.height)))
         r.sample_mode(self.sample_mode)
         if self.ambient is not None:
             r.ambient(self.ambient)
+        if self.mapmini is not None:
+            r.mapmini = self.mapmini
+        if self.render_mode is not None:
+            r.render_mode(self.render_mode)
         return r
 
     def counts(self):
-        v = sum(len(b.vertices) for b in self.scene.d3_static + self.scene.d3_dynamic + self.scene.d3_overlay)
-        t = sum(len(b.indices) for b in self.scene.d3_static + self.scene.d3_dynamic + self.scene.d3_overlay)
+        from .marshal import submission_order
+        b3, _ = submission_order(self.scene)
+        v = sum(len(b.vertices) for b, _p, _c in b3)
+        t = sum(len(b.indices) for b, _p, _c in b3)
         return v, t
 
     def algorithmic_bytes(self) -> int:
@@ -368,3 +377,187 @@ def dense(width=7680, height=4320, tile_size=40, patches=32, patch_verts=23) -> 
 
 
 BUILDERS = {"cube": cube, "teapot": teapot, "map": map_config, "dense": dense, "sweep": sweep}
+
+
+# ------------------------------------------------------------------------------------------------
+# the chunk path and the 2D game path (row f3)
+# ------------------------------------------------------------------------------------------------
+def tex_glass(w=32, h=32) -> Texture:
+    """A window pane: opaque frame, translucent glass (alpha 96) with a tint gradient."""
+    y, x = np.mgrid[0:h, 0:w].astype(np.float32)
+    frame = (x < 2) | (x >= w - 2) | (y < 2) | (y >= h - 2) | (np.abs(x - w / 2) < 1) | (np.abs(y - h / 2) < 1)
+    r = np.where(frame, 60, 90 + 2 * x)
+    g = np.where(frame, 40, 150 + y)
+    b = np.where(frame, 30, 220)
+    a = np.where(frame, 255, 96)
+    return Texture.from_array(_rgba(r, g, b, a))
+
+
+def tex_terrain(seed, size=64, holes=True) -> Texture:
+    """A baked terrain texture: blotchy grass/dirt; with `holes` a few texels are not opaque, which
+    exercises the alpha test of PixelSource::Terrain (its texel comes from the world position)."""
+    n = rand01(size * size, seed).reshape(size, size)
+    y, x = np.mgrid[0:size, 0:size].astype(np.float32)
+    blot = np.sin(x * 0.31 + seed % 7) * np.cos(y * 0.23) * 0.5 + 0.5
+    r = 60 + 70 * blot + 30 * n
+    g = 110 + 60 * (1 - blot) + 30 * n
+    b = 40 + 30 * n
+    a = np.full((size, size), 255.0)
+    if holes:
+        a[(x.astype(int) % 16 == 5) & (y.astype(int) % 16 == 9)] = 128
+        a[(x.astype(int) % 16 == 11) & (y.astype(int) % 16 == 3)] = 0
+    return Texture.from_array(_rgba(r, g, b, a))
+
+
+def tex_sprite(seed, w=24, h=32) -> Texture:
+    """A character sprite: opaque body, soft (partially transparent) outline, transparent background."""
+    y, x = np.mgrid[0:h, 0:w].astype(np.float32)
+    d = np.hypot((x - w / 2) / (w / 2), (y - h / 2) / (h / 2))
+    a = np.clip((1.05 - d) * 6.0, 0.0, 1.0) * 255.0
+    n = rand01(w * h, seed).reshape(h, w)
+    return Texture.from_array(_rgba(200 * (1 - d) + 40 * n, 80 + 100 * n, 60 + 150 * d, a))
+
+
+def _floor_quad(x0, z0, x1, z1, y=0.0):
+    verts = [(x0, y, z0, 1.0), (x1, y, z0, 1.0), (x1, y, z1, 1.0), (x0, y, z1, 1.0)]
+    uvs = [(x0, z0), (x1, z0), (x1, z1), (x0, z1)]
+    return verts, uvs
+
+
+def chunked_assets(logo_size=256) -> Assets:
+    a = map_assets(logo_size)
+    a.tile_list.append(Tile.from_texture(tex_glass()))           # 6
+    a._generation += 1
+    a.entity_tiles = {"hero": [("idle", Tile.from_textures([tex_sprite(SEED + 40), tex_sprite(SEED + 41)])),
+                               ("walk", Tile.from_texture(tex_sprite(SEED + 42)))]}
+    a.item_tiles = {"chest": [("closed", Tile.from_texture(tex_sprite(SEED + 43, 16, 16)))]}
+    return a
+
+
+def chunked_scene() -> Scene:
+    """The 16x16 room of the map config as four 8x8 chunks (scene.chunks): per chunk opaque walls with a
+    profile id, window panes in the opacity pass that share the profile id of the wall they sit in, a terrain
+    batch textured from chunk.terrain_texture, occluded sectors and a chunk light; plus static batches with
+    EntityTile / ItemTile sources (one of which does not resolve) and a 2D overlay of every primitive mode."""
+    H = 2.0
+    scene = Scene()
+
+    def fin(b, tile, profile=None):
+        b = b.source(PixelSource.StaticTileIndex(tile)).repeat_mode(RepeatMode.RepeatXY).cull_mode(CullMode.Off).with_computed_normals()
+        return b if profile is None else b.profile_id(profile)
+
+    profile = 100
+    for cz in range(2):
+        for cx in range(2):
+            ox, oz = cx * 8, cz * 8
+            ch = Chunk((ox, oz), 8)
+            walls, panes = [], []
+            # outer walls of the room that fall into this chunk, each with a window pane 2 cm in front of it
+            if cz == 0:
+                walls.append((_wall_quad(float(ox), 0.0, float(ox + 8), 0.0, H), profile))
+                panes.append((_wall_quad(ox + 2.0, 0.02, ox + 6.0, 0.02, H), profile))
+                profile += 1
+            if cz == 1:
+                walls.append((_wall_quad(float(ox + 8), 16.0, float(ox), 16.0, H), profile))
+                panes.append((_wall_quad(ox + 6.0, 15.98, ox + 2.0, 15.98, H), profile))
+                profile += 1
+            if cx == 0:
+                walls.append((_wall_quad(0.0, float(oz + 8), 0.0, float(oz), H), profile))
+                profile += 1
+            if cx == 1:
+                walls.append((_wall_quad(16.0, float(oz), 16.0, float(oz + 8), H), profile))
+                panes.append((_wall_quad(15.98, oz + 1.0, 15.98, oz + 7.0, H), profile + 1000))  # profile of no wall
+                profile += 1
+            for q, pid in walls:
+                ch.batches3d.append(fin(_quads_batch([q]), 1, pid))
+            for q, pid in panes:
+                ch.batches3d_opacity.append(fin(_quads_batch([q]), 6, pid).repeat_mode(RepeatMode.ClampXY))
+            # an inner fence (alpha tested) without a profile id
+            ch.batches3d.append(fin(_quads_batch([_wall_quad(ox + 4.0, oz + 1.0, ox + 4.0, oz + 7.0, H)]), 3))
+            t = _quads_batch([_floor_quad(float(ox), float(oz), float(ox + 8), float(oz + 8))])
+            ch.terrain_batch3d = t.source(PixelSource.Terrain).cull_mode(CullMode.Off).with_computed_normals()
+            ch.terrain_texture = tex_terrain(SEED + 50 + cx + 2 * cz, 64, holes=(cx != cz))
+            ch.occluded_sectors = [(BBox((ox + 1.0, oz + 1.0), (ox + 3.5, oz + 4.0)), 0.35), (BBox((ox + 5.0, oz + 5.0), (ox + 7.0, oz + 7.5)), 0.0)]
+            ch.lights = [Light.new(LightType.Point).with_color([1.0, 0.9 - 0.2 * cx, 0.7 + 0.3 * cz]).with_intensity(1.5)
+                         .with_start_distance(1.0).with_end_distance(7.0).with_position([ox + 4.0, 1.5, oz + 4.0]).compile()]
+            # 2D: a minimap tile of the chunk and its terrain as seen from above
+            ch.batches2d.append(Batch2D.from_rectangle(20.0 + 40.0 * cx, 20.0 + 40.0 * cz, 36.0, 36.0).source(PixelSource.StaticTileIndex(4)))
+            ch.terrain_batch2d = Batch2D.from_rectangle(120.0 + 40.0 * cx, 20.0 + 40.0 * cz, 36.0, 36.0).source(PixelSource.Terrain)
+            scene.chunks[(cx, cz)] = ch
+
+    sky = Batch3D.from_box(-32.5, -20.0, -32.5, 80.0, 60.0, 80.0)
+    scene.d3_static.append(fin(sky, 5).receives_light(False))
+
+    def billboard(x, z, w, h, src):
+        verts = [(x - w / 2, 0.0, z, 1.0), (x + w / 2, 0.0, z, 1.0), (x + w / 2, h, z, 1.0), (x - w / 2, h, z, 1.0)]
+        uvs = [(0.0, 1.0), (1.0, 1.0), (1.0, 0.0), (0.0, 0.0)]
+        return Batch3D(verts, [(0, 1, 2), (0, 2, 3)], uvs).source(src).cull_mode(CullMode.Off).with_computed_normals()
+
+    scene.d3_dynamic += [billboard(6.0, 9.0, 1.0, 1.6, PixelSource.EntityTile("hero", 0)),
+                         billboard(9.5, 10.0, 1.0, 1.6, PixelSource.EntityTile("hero", 1)),
+                         billboard(8.0, 11.0, 0.8, 0.8, PixelSource.ItemTile("chest", 0)),
+                         billboard(7.0, 8.0, 1.0, 1.0, PixelSource.ItemTile("missing", 0)),   # does not resolve
+                         billboard(10.0, 8.5, 1.0, 1.0, PixelSource.EntityTile("hero", 7))]   # index out of range
+    # 2D overlay: sprites, a translucent stack, lines of every mode
+    scene.d2_static.append(Batch2D.from_rectangle(300.0, 20.0, 48.0, 64.0).source(PixelSource.EntityTile("hero", 0)))
+    scene.d2_static.append(Batch2D.from_rectangle(330.0, 40.0, 48.0, 64.0).source(PixelSource.ItemTile("chest", 0)).receives_light(False))
+    scene.d2_static.append(Batch2D.from_rectangle(360.0, 30.0, 40.0, 40.0).source(PixelSource.ItemTile("nothing", 0)))
+    pts = [(420.5, 20.2), (470.9, 28.0), (455.0, 70.7), (430.2, 60.1), (445.0, 45.0)]
+    uv0 = [(0.0, 0.0)] * len(pts)
+    scene.d2_dynamic.append(Batch2D.new(pts, [(0, 2, 0), (1, 3, 0), (4, 0, 0)], uv0).mode_(PrimitiveMode.Lines).source(PixelSource.Pixel((255, 220, 0, 255))))
+    scene.d2_dynamic.append(Batch2D.new([(x + 70.0, y) for x, y in pts], [], uv0).mode_(PrimitiveMode.LineStrip))
+    scene.d2_dynamic.append(Batch2D.new([(x + 140.0, y + 0.4) for x, y in pts], [], uv0).mode_(PrimitiveMode.LineLoop).source(PixelSource.Pixel((0, 255, 255, 128))))
+    scene.lights = [Light.new(LightType.AmbientDaylight).with_color([0.4, 0.45, 0.6]).with_intensity(0.6).compile()]
+    return scene
+
+
+def chunked_config(width=1280, height=720, tile_size=40, n_frames=8) -> Config:
+    def cams(i):
+        th = 2.0 * math.pi * (i + 0.37) / n_frames
+        return _firstp([8.0 + 3.0 * math.cos(th), 1.1, 8.0 + 3.0 * math.sin(th)], [8.0 - 2.0 * math.cos(th), 0.9, 8.0 - 2.0 * math.sin(th)])
+    mm = MapMini(occluded_sectors=[(BBox((7.0, 7.0), (9.0, 9.0)), 0.5)])
+    return Config("chunked", chunked_scene(), chunked_assets(), width, height, tile_size, SampleMode.Nearest, (0.9, 0.9, 1.0, 1.0),
+                  cams(0), cameras=cams, n_frames=n_frames, mapmini=mm)
+
+
+def game2d_scene(cols=24, rows=16, tile_px=1.0) -> Scene:
+    """A top-down 2D game screen as the screen widget builds it (src/client/widget/screen.rs:60-94): a grid of
+    map tiles (cols*rows quads = 2*cols*rows records), translucent decals that overlap in submission order, entity
+    sprites, point lights with line-of-sight against mapmini linedefs, sector occlusion and line overlays."""
+    scene = Scene()
+    grid = Batch2D.empty()
+    for r in range(rows):
+        for c in range(cols):
+            grid.add_rectangle(c * tile_px, r * tile_px, tile_px, tile_px)
+    scene.d2_static.append(grid.source(PixelSource.StaticTileIndex(4)).repeat_mode(RepeatMode.RepeatXY))
+    walls = Batch2D.empty()
+    for c in range(4, 20):
+        walls.add_rectangle(c * tile_px, 5 * tile_px, tile_px, tile_px)
+    scene.d2_static.append(walls.source(PixelSource.StaticTileIndex(1)))
+    decals = Batch2D.empty()
+    for i in range(12):
+        decals.add_rectangle(2.0 + 1.3 * i, 7.0 + 0.35 * i, 2.5, 2.5)   # overlapping, translucent: order matters
+    scene.d2_static.append(decals.source(PixelSource.StaticTileIndex(6)))
+    scene.d2_dynamic.append(Batch2D.from_rectangle(9.2, 9.1, 1.5, 2.0).source(PixelSource.EntityTile("hero", 0)))
+    scene.d2_dynamic.append(Batch2D.from_rectangle(13.4, 3.2, 1.5, 2.0).source(PixelSource.EntityTile("hero", 1)).receives_light(False))
+    scene.d2_dynamic.append(Batch2D.from_rectangle(16.0, 10.0, 1.0, 1.0).source(PixelSource.ItemTile("chest", 0)))
+    pts = [(1.2, 1.1), (22.7, 2.3), (20.1, 14.6), (3.3, 13.2), (12.0, 8.0)]
+    uv0 = [(0.0, 0.0)] * len(pts)
+    scene.d2_dynamic.append(Batch2D.new(pts, [(0, 2, 0), (1, 3, 0)], uv0).mode_(PrimitiveMode.Lines).source(PixelSource.Pixel((255, 0, 0, 255))))
+    scene.d2_dynamic.append(Batch2D.new(pts, [], uv0).mode_(PrimitiveMode.LineLoop))
+    scene.lights = [
+        Light.new(LightType.Point).with_color([1.0, 0.8, 0.5]).with_intensity(1.2).with_start_distance(1.0).with_end_distance(9.0).with_position([8.0, 0.0, 3.0]).compile(),
+        Light.new(LightType.Point).with_color([0.4, 0.6, 1.0]).with_intensity(1.0).with_start_distance(0.5).with_end_distance(8.0).with_position([15.0, 0.0, 11.0]).compile(),
+        Light.new(LightType.AmbientDaylight).with_color([0.5, 0.5, 0.5]).with_intensity(0.5).compile(),
+    ]
+    return scene
+
+
+def game2d_config(width=960, height=640) -> Config:
+    scale = 40.0
+    m = np.array([[scale, 0.0, 0.0], [0.0, scale, 0.0], [0.0, 0.0, 1.0]], dtype=np.float32)
+    mm = MapMini(linedefs=[CompiledLinedef((4.0, 5.5), (20.0, 5.5)), CompiledLinedef((12.0, 8.0), (12.0, 13.0))],
+                 occluded_sectors=[(BBox((0.0, 0.0), (6.0, 4.0)), 0.2), (BBox((18.0, 8.0), (24.0, 16.0)), 0.6)])
+    cam = D3FirstPCamera.new()
+    return Config("game2d", game2d_scene(), chunked_assets(), width, height, 40, SampleMode.Nearest, (0.25, 0.25, 0.3, 1.0), cam,
+                  matrix2d=m, mapmini=mm, render_mode=RenderMode.render_2d())

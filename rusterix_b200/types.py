@@ -78,6 +78,7 @@ class PixelSource:
     index: int = 0
     pixel: tuple = (0, 0, 0, 0)
     name: str = "Off"
+    ident: object = None  # the Uuid of EntityTile / ItemTile
 
     @staticmethod
     def StaticTileIndex(i: int) -> "PixelSource":
@@ -98,11 +99,11 @@ class PixelSource:
 
     @staticmethod
     def EntityTile(id_: int, index: int) -> "PixelSource":
-        return PixelSource(_SrcKind.EntityTile, int(index), (0, 0, 0, 0), "EntityTile")
+        return PixelSource(_SrcKind.EntityTile, int(index), (0, 0, 0, 0), "EntityTile", id_)
 
     @staticmethod
     def ItemTile(id_: int, index: int) -> "PixelSource":
-        return PixelSource(_SrcKind.ItemTile, int(index), (0, 0, 0, 0), "ItemTile")
+        return PixelSource(_SrcKind.ItemTile, int(index), (0, 0, 0, 0), "ItemTile", id_)
 
 
 PixelSource.Off = PixelSource()
@@ -161,6 +162,9 @@ class Assets:
 
     def __init__(self):
         self.tile_list: List[Tile] = []
+        # src/server/assets.rs:28,34: id -> IndexMap<String, Tile>; here id -> list of (name, Tile)
+        self.entity_tiles: dict = {}
+        self.item_tiles: dict = {}
         self._generation = 0
         self._uid = next(_UIDS)  # device-cache identity (id() can be reused after garbage collection)
 
@@ -175,6 +179,14 @@ class Assets:
 
     def mark_dirty(self):
         self._generation += 1
+
+    def actor_tile(self, src: "PixelSource") -> Optional[Tile]:
+        """assets.entity_tiles.get(&id).get_index(index) (src/rasterizer.rs:1130-1152)."""
+        table = self.entity_tiles if src.kind == _SrcKind.EntityTile else self.item_tiles
+        seq = table.get(src.ident)
+        if seq is None or not (0 <= src.index < len(seq)):
+            return None
+        return seq[src.index][1]
 
 
 @dataclass
@@ -482,6 +494,7 @@ class Scene:
         self.d2_static: List[Batch2D] = []
         self.d2_dynamic: List[Batch2D] = []
         self.dynamic_textures: List[Tile] = []
+        self.chunks: dict = {}  # (x, y) -> Chunk, iterated in insertion order (src/scene.rs:46)
         self.animation_frame = 0
         self._generation = 0
         self._uid = next(_UIDS)  # device-cache identity (id() can be reused after garbage collection)
@@ -519,6 +532,59 @@ class Scene:
 
 
 @dataclass
+@dataclass
+class BBox:  # src/map/bbox.rs:5-40
+    min: tuple = (0.0, 0.0)
+    max: tuple = (0.0, 0.0)
+
+    @staticmethod
+    def from_pos_size(pos, size) -> "BBox":
+        return BBox((float(pos[0]), float(pos[1])), (float(pos[0]) + float(size[0]), float(pos[1]) + float(size[1])))
+
+
+@dataclass
+class CompiledLinedef:  # src/map/mini.rs: start / end of a wall segment
+    start: tuple = (0.0, 0.0)
+    end: tuple = (0.0, 0.0)
+
+
+class MapMini:
+    """src/map/mini.rs:22-56: what Rasterizer.mapmini contributes to the path -- linedefs for the 2D
+    line-of-sight test (:88-95) and occluded sectors (:58-65)."""
+
+    def __init__(self, linedefs=None, occluded_sectors=None):
+        self.linedefs: List[CompiledLinedef] = list(linedefs or [])
+        self.occluded_sectors: List[tuple] = list(occluded_sectors or [])  # (BBox, occlusion)
+
+    @staticmethod
+    def default() -> "MapMini":
+        return MapMini()
+
+    def key(self):
+        return (tuple((l.start, l.end) for l in self.linedefs), tuple((b.min, b.max, o) for b, o in self.occluded_sectors))
+
+
+class Chunk:
+    """src/chunk.rs:23-57: the members on the rasterize path."""
+
+    def __init__(self, origin=(0, 0), size=0):
+        self.origin = (int(origin[0]), int(origin[1]))
+        self.size = int(size)
+        self.bbox = BBox.from_pos_size(self.origin, (size, size))
+        self.batches2d: List[Batch2D] = []
+        self.batches3d_opacity: List[Batch3D] = []
+        self.batches3d: List[Batch3D] = []
+        self.terrain_batch2d: Optional[Batch2D] = None
+        self.terrain_batch3d: Optional[Batch3D] = None
+        self.terrain_texture: Optional[Texture] = None
+        self.lights: List[CompiledLight] = []
+        self.occluded_sectors: List[tuple] = []  # (BBox, occlusion)
+
+    @staticmethod
+    def new(origin, size) -> "Chunk":
+        return Chunk(origin, size)
+
+
 class VGrayGradientShader:  # src/shader/vgradient.rs:4-15
     kind: int = 1
 

@@ -27,7 +27,8 @@ def load():
         lib = C.CDLL(LIB)
         lib.rxo_rasterize.restype = C.c_int32
         lib.rxo_rasterize.argtypes = [C.POINTER(_abi.rxc_tile), C.c_uint32, C.POINTER(_abi.rxc_scene),
-                                      C.POINTER(_abi.rxc_frame), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+                                      C.POINTER(_abi.rxc_mapmini), C.POINTER(_abi.rxc_frame), C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_int32]
         lib.rxo_clip_and_project.restype = C.c_int32
         lib.rxo_clip_and_project.argtypes = [C.POINTER(_abi.rxc_batch3d), C.POINTER(_abi.rxc_frame), C.c_void_p,
                                              C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.c_void_p,
@@ -54,12 +55,13 @@ def rasterize(rast, scene, assets, width, height, tile_size, want_planes=True, n
     owner[h,w] or None, depth[h,w] or None)."""
     lib = load()
     tiles = marshal.marshal_tiles(assets.tile_list)
-    sc = marshal.marshal_scene(scene, index_bytes)
+    sc = marshal.marshal_scene(scene, index_bytes, assets)
+    mm = marshal.marshal_mapmini(rast.mapmini)
     frame = marshal.make_frame(rast, scene, width, height, tile_size)
     pixels = np.zeros((height, width, 4), dtype=np.uint8)
     owner = np.zeros((height, width), dtype=np.uint32) if want_planes else None
     depth = np.zeros((height, width), dtype=np.float32) if want_planes else None
-    st = lib.rxo_rasterize(tiles.struct, len(assets.tile_list), C.byref(sc.struct), C.byref(frame),
+    st = lib.rxo_rasterize(tiles.struct, len(assets.tile_list), C.byref(sc.struct), C.byref(mm.struct), C.byref(frame),
                            pixels.ctypes.data, owner.ctypes.data if want_planes else None,
                            depth.ctypes.data if want_planes else None, n_threads)
     if st != 0:

@@ -220,3 +220,54 @@ def test_fast_division_is_bit_exact():
 
     assert DeviceContext.get(0).selftest_div(n_pairs=1 << 32) == 0
     assert DeviceContext.get(0).selftest_div(n_pairs=1 << 30, seed=12345) == 0
+
+
+# ---- SURVEY 8f rows f2 (chunk path) and f3 (2D game path) ------------------------------------------
+@pytest.mark.parametrize("frame", [0, 3, 5])
+def test_chunk_path_opacity_surface_ids_terrain_occlusion(frame):
+    """scene.chunks: opacity batches with surface ids (rasterizer.rs:1425-1690, :1041-1047, :464-495),
+    terrain texels from the world position incl. their alpha test (:1178-1219, chunk.rs:135-151), sector
+    occlusion (:1327-1365), chunk lights (:219-223), EntityTile / ItemTile sources that do and do not
+    resolve (:1130-1177), and a 2D overlay with every primitive mode (:901-955)."""
+    cfg = scenes.chunked_config(1280, 720)
+    st = _run(cfg, frame)
+    assert st["within1_frac"] >= 0.999
+
+
+def test_chunk_path_linear_odd_size_and_preserve_transparency():
+    cfg = scenes.chunked_config(1001, 563)
+    cfg.sample_mode = SampleMode.Linear
+    _run(cfg, 2, preserve_transparency=True)
+
+
+def test_chunk_path_batch_api_matches_single_frames():
+    cfg = scenes.chunked_config(640, 360)
+    rasts = [cfg.rasterizer(i) for i in range(4)]
+    import copy
+    lights_before = list(cfg.scene.dynamic_lights)
+    out = np.zeros((4, cfg.height, cfg.width, 4), dtype=np.uint8)
+    Rasterizer.rasterize_batch(rasts, cfg.scene, out, cfg.width, cfg.height, cfg.tile_size, cfg.assets)
+    for i in (0, 3):
+        cfg.scene.dynamic_lights = list(cfg.scene.dynamic_lights)  # same light list as the sweep saw
+        o = render_oracle(rasts[i], cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size)
+        compare((out[i], None, None), o, f"chunked sweep frame {i}")
+    assert len(cfg.scene.dynamic_lights) == len(lights_before) + 4  # chunk lights appended once (rasterizer.rs:219-223)
+
+
+@pytest.mark.parametrize("size", [(960, 640), (487, 333)])
+def test_game2d_binned_records_lines_los_and_sectors(size):
+    """2D-only render mode with 800+ records (sorted per-tile lists), translucent decals blended in
+    submission order (rasterizer.rs:876-895), entity sprites, Bresenham lines (:1777-1821), point lights
+    blocked by mapmini linedefs (mini.rs:67-95) and sector occlusion of ambient light (:806-836)."""
+    cfg = scenes.game2d_config(*size)
+    r = cfg.rasterizer(0)
+    g = render_gpu(r, cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size)
+    o = render_oracle(r, cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size)
+    st = compare(g, o, "game2d")
+    assert st["exact_frac"] >= 0.999  # the 2D path is integer blending of exact texels
+
+
+def test_game2d_preserve_transparency_and_background():
+    cfg = scenes.game2d_config(640, 480)
+    cfg.scene.background = VGrayGradientShader()
+    _run(cfg, 0, preserve_transparency=True)
