@@ -881,15 +881,6 @@ __device__ __forceinline__ uint32_t shade_owner(const SceneDev& S, const DFrame&
     const uint32_t flags = d0.z;
     const float gamma = 1.0f - alpha - beta;
 
-    // screen_to_world, rasterizer.rs:1707-1727, folded into one affine map + divide (DFrame::s2w)
-    const float hx = __fmaf_rn(F.s2w[2], z, __fmaf_rn(F.s2w[1], fpy, __fmaf_rn(F.s2w[0], fpx, F.s2w[3])));
-    const float hy = __fmaf_rn(F.s2w[6], z, __fmaf_rn(F.s2w[5], fpy, __fmaf_rn(F.s2w[4], fpx, F.s2w[7])));
-    const float hz = __fmaf_rn(F.s2w[10], z, __fmaf_rn(F.s2w[9], fpy, __fmaf_rn(F.s2w[8], fpx, F.s2w[11])));
-    const float hw = __fmaf_rn(F.s2w[14], z, __fmaf_rn(F.s2w[13], fpy, __fmaf_rn(F.s2w[12], fpx, F.s2w[15])));
-    const float ihw = fast_rcp(hw);
-    const f3 world = {hx * ihw, hy * ihw, hz * ihw};
-    const f3 view_dir = fnormalize3({F.cam[0] - world.x, F.cam[1] - world.y, F.cam[2] - world.z});
-
     uint32_t texel = d0.w;
     if (flags & RX_SD_TEXTURED) {
         // perspective-correct UV, rasterizer.rs:1062-1076.  The owner is decided; the quotients are
@@ -902,9 +893,18 @@ __device__ __forceinline__ uint32_t shade_owner(const SceneDev& S, const DFrame&
         u = __fmaf_rn(__fmaf_rn(-irw, u, iu), rr, u);
         v = __fmaf_rn(__fmaf_rn(-irw, v, iv), rr, v);
         texel = sample_desc(S.arena, d0.x, d0.y, flags, u, v, sample_mode);
-    } else if (flags & RX_SD_TERRAIN) {
-        texel = terrain_sample(S.arena, d0.x, d0.y, S.chunk_info[__float_as_int(d1.w)], world.x, world.z);
     }
+
+    // screen_to_world, rasterizer.rs:1707-1727, folded into one affine map + divide (DFrame::s2w)
+    const float hx = __fmaf_rn(F.s2w[2], z, __fmaf_rn(F.s2w[1], fpy, __fmaf_rn(F.s2w[0], fpx, F.s2w[3])));
+    const float hy = __fmaf_rn(F.s2w[6], z, __fmaf_rn(F.s2w[5], fpy, __fmaf_rn(F.s2w[4], fpx, F.s2w[7])));
+    const float hz = __fmaf_rn(F.s2w[10], z, __fmaf_rn(F.s2w[9], fpy, __fmaf_rn(F.s2w[8], fpx, F.s2w[11])));
+    const float hw = __fmaf_rn(F.s2w[14], z, __fmaf_rn(F.s2w[13], fpy, __fmaf_rn(F.s2w[12], fpx, F.s2w[15])));
+    const float ihw = fast_rcp(hw);
+    const f3 world = {hx * ihw, hy * ihw, hz * ihw};
+    const f3 view_dir = fnormalize3({F.cam[0] - world.x, F.cam[1] - world.y, F.cam[2] - world.z});
+
+    if (flags & RX_SD_TERRAIN) texel = terrain_sample(S.arena, d0.x, d0.y, S.chunk_info[__float_as_int(d1.w)], world.x, world.z);
 
     f3 normal = {0.0f, 0.0f, 0.0f};
     if (flags & RX_SD_NORMALS) {  // rasterizer.rs:1083-1099

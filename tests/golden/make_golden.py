@@ -23,11 +23,17 @@ CASES = {
     "map_320x180": lambda: (scenes.map_config(320, 180, 40, logo_size=64), 0),
     "sweep_320x180_f1000": lambda: (scenes.sweep(320, 180, 40, logo_size=64), 1000),
     "dense_320x180_p4": lambda: (scenes.dense(320, 180, 40, patches=4), 0),
+    # chunk path (opacity layer, surface ids, terrain, occlusion) and 2D game path
+    "chunked_320x180_f0": lambda: (scenes.chunked_config(320, 180, 40), 0),
+    "chunked_320x180_f5": lambda: (scenes.chunked_config(320, 180, 40), 5),
+    "game2d_240x160": lambda: (scenes.game2d_config(240, 160), 0),
 }
 
 
 def digest(case):
     cfg, frame = CASES[case]()
+    for chunk in cfg.scene.chunks.values():  # the per-call chunk-light append of rasterize() (src/rasterizer.rs:219-223)
+        cfg.scene.dynamic_lights.extend(chunk.lights)
     px, ow, dp = oracle_ffi.rasterize(cfg.rasterizer(frame), cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size, n_threads=1)
     return {"pixels": hashlib.sha256(px.tobytes()).hexdigest(), "owner": hashlib.sha256(ow.tobytes()).hexdigest(),
             "depth": hashlib.sha256(dp.tobytes()).hexdigest(), "covered": int((ow != 0xFFFFFFFF).sum())}
