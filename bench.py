@@ -37,6 +37,9 @@ WORKLOADS = {
     "sweep1080": ("sweep", dict(width=1920, height=1080, tile_size=40), "camera sweep of the map scene, 1920x1080, Nearest, tile 40"),
     "dense8k": ("dense", dict(width=7680, height=4320, tile_size=40), "991,232-triangle heightfield in 1024 batches, 7 lights, 7680x4320, Linear"),
     "cube800": ("cube", dict(width=800, height=600, tile_size=200), "textured cube, 800x600, Nearest, tile 200"),
+    # the rows SURVEY 8f marks "next", measured like the others
+    "chunked1080": ("chunked", dict(width=1920, height=1080, tile_size=40), "chunked map (4 chunks: opacity panes with surface ids, terrain textures, occluded sectors, chunk lights, entity/item tiles, 2D overlay with lines), 1920x1080, Nearest"),
+    "game2d1080": ("game2d", dict(width=1920, height=1280), "2D game screen (834 2D records in sorted per-tile lists, translucent decals, sprites, 2 point lights with line of sight, sector occlusion, lines), 1920x1280, 2D-only render mode"),
 }
 
 
@@ -364,7 +367,7 @@ def main():
         mpix, cores, sample, spf = cpu_port_time(cfg, frame_ids)
         line["cpu_baseline"] = {"value": mpix, "unit": "Mpixel/s", "cores": cores, "kind": "port", "sample": sample, "s_per_frame": spf}
         also = {}
-        for wname in ("teapot1080", "dense8k", "sweep1080"):
+        for wname in ("teapot1080", "dense8k", "sweep1080", "chunked1080", "game2d1080"):
             if wname == args.workload:
                 continue
             try:

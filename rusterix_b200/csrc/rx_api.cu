@@ -61,6 +61,7 @@ struct rxc_ctx {
     DevBuf d_pos, d_uv, d_nrm, d_idx, d_b3, d_chunks, d_orphans, d_pos2, d_uv2, d_idx2, d_b2, d_lights;
     SceneDev S = {};
     bool have_scene = false;
+    bool lists_sized = false;   // a frame of this scene has been checked for tile-list overflow (the first call always is)
 
     // per-frame workspace
     Workspace W = {};
@@ -448,8 +449,10 @@ int32_t launch_group(rxc_ctx* ctx, const DFrame* h_frames, DCounters* h_counters
         { LaunchScope l(ctx, RXK_BATCH_FINALIZE); CK(rxk_batch_finalize(S, ctx->W, n, ctx->stream)); }
         { LaunchScope l(ctx, RXK_CLIP_EMIT); CK(rxk_clip_emit(S, ctx->W, n, grid_for(std::min<size_t>(S.n_tris, 65536), 128), ctx->stream)); }
         { LaunchScope l(ctx, RXK_BIN_COUNT); CK(rxk_bin_count(S, ctx->W, n, grid_for((size_t)S.n_tris + S.n_tris / 8, 256), ctx->stream)); }
+        if (S.general) { LaunchScope l(ctx, RXK_BIN_COUNT); CK(rxk_bin_large(S, ctx->W, n, 0, ctx->sm_count, ctx->stream)); }
         { LaunchScope l(ctx, RXK_TILE_ALLOC); CK(rxk_tile_alloc(S, ctx->W, n, tiles_per_frame, 0, S.general ? 1 : 0, ctx->stream)); }
         { LaunchScope l(ctx, RXK_BIN_FILL); CK(rxk_bin_fill(S, ctx->W, n, grid_for((size_t)S.n_tris + S.n_tris / 8, 256), ctx->stream)); }
+        if (S.general) { LaunchScope l(ctx, RXK_BIN_FILL); CK(rxk_bin_large(S, ctx->W, n, 1, ctx->sm_count, ctx->stream)); }
         if (S.general) { LaunchScope l(ctx, RXK_LIST_SORT); CK(rxk_list_sort(S, ctx->W, n, tiles_per_frame, 0, ctx->stream)); }
     }
     if (S.general && S.n_rec2d) {  // 2D records into sorted per-tile lists
@@ -485,12 +488,12 @@ int32_t check_group(rxc_ctx* ctx, const DCounters* h_counters, uint32_t n, bool*
     ctx->stats.last_large_tris = c.n_large;
     ctx->stats.last_clipped_tris = c.n_new_slots;
     ctx->stats.last_visible_tris = c.n_visible;
-    if (ov & 1u) {  // tile-list arena too small: grow to what the frame asked for and run it again
-        ctx->list_cap_min = need + need / 4 + 1024;
+    if (ov & 1u) {  // tile-list arena too small: grow to twice what the frame asked for and run it again
+        ctx->list_cap_min = 2 * need + 1024;
         *retry = true;
     }
     if (ov & 8u) {  // 2D tile-list arena
-        ctx->list2_cap_min = need2 + need2 / 4 + 1024;
+        ctx->list2_cap_min = 2 * need2 + 1024;
         *retry = true;
     }
     if (ov & 6u) return fail(ctx, RXC_ERR_OOM, "internal list overflow (large/clip); this is a bug");
@@ -610,12 +613,13 @@ int32_t rasterize_impl(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames,
             if (owner && !dev_owner) { if ((st = reserve(ctx, ctx->d_out_owner, frame_bytes)) != RXC_OK) return st; d_ow = ctx->d_out_owner.as<uint32_t>(); }
             if (depth && !dev_depth) { if ((st = reserve(ctx, ctx->d_out_depth, frame_bytes)) != RXC_OK) return st; d_dp = ctx->d_out_depth.as<float>(); }
             if ((st = launch_group(ctx, ctx->h_frames, ctx->h_counters, n, d_px, d_stride, d_ow, d_dp)) != RXC_OK) return st;
-            if (!sync && dev_px) break;  // truly asynchronous: counters are checked at the next synchronize
+            if (!sync && dev_px && ctx->lists_sized) break;  // truly asynchronous: counters are checked at the next synchronize
             CK(cudaStreamSynchronize(ctx->stream));
             if (ctx->profiling) drain_events(ctx);
             bool retry = false;
             if ((st = check_group(ctx, ctx->h_counters, n, &retry)) != RXC_OK) return st;
             if (retry) continue;
+            ctx->lists_sized = true;
             if (!dev_px) {
                 if (stride == frame_bytes || n == 1) {
                     CK(cudaMemcpyAsync(pixels + (uint64_t)first * stride, d_px, (size_t)n * frame_bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -913,6 +917,7 @@ int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
     ctx->ws_frames = 0;  // workspace strides depend on the scene
     ctx->list_cap_min = 0;
     ctx->list2_cap_min = 0;
+    ctx->lists_sized = false;
     ctx->have_scene = true;
     return RXC_OK;
 }

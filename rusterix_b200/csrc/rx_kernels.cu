@@ -666,7 +666,7 @@ __global__ void __launch_bounds__(256) k_bin_count(SceneDev S, Workspace Wk) {
         int tx0, tx1, ty0, ty1;
         bin_tile_range(F, b.bbx, b.bby, &tx0, &tx1, &ty0, &ty1);
         const int nt = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
-        if (nt > RX_LARGE_TILES && !S.general) {  // ordered lists hold every triangle
+        if (nt > RX_LARGE_TILES) {  // general mode: k_bin_large bins these into the ordered lists, a warp per triangle
             const uint32_t k = atomicAdd(&C.n_large, 1u);
             if (k < Wk.large_stride) Wk.large[(size_t)f * Wk.large_stride + k] = b.slot;
             else atomicOr(&C.overflow, 2u);
@@ -1524,6 +1524,39 @@ __global__ void __launch_bounds__(256) k_bin2d(SceneDev S, Workspace Wk, int fil
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_bin_large (general mode): the ordered tile lists hold every triangle, so the triangles k_bin_count put
+// on the large list are binned here, one warp per triangle, lanes over the tiles of the bbox, skipping tiles
+// the conservative overlap test excludes
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bin_large(SceneDev S, Workspace Wk, int fill) {
+    const uint32_t f = blockIdx.y;
+    const DFrame& F = Wk.frames[f];
+    const DCounters& C = Wk.counters[f];
+    const uint32_t n_large = min(C.n_large, Wk.large_stride);
+    const uint32_t lane = threadIdx.x & 31, wpg = (gridDim.x * blockDim.x) >> 5;
+    uint32_t* tc = Wk.tile_count + (size_t)f * Wk.tile_stride;
+    const uint32_t* tb = Wk.tile_base + (size_t)f * Wk.tile_stride;
+    uint32_t* tf = Wk.tile_fill + (size_t)f * Wk.tile_stride;
+    uint32_t* lists = Wk.lists + (size_t)f * Wk.list_stride;
+    for (uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n_large; k += wpg) {
+        const uint32_t slot = Wk.large[(size_t)f * Wk.large_stride + k];
+        const TriVis& T = Wk.vis[(size_t)f * Wk.slot_stride + slot];
+        int tx0, tx1, ty0, ty1;
+        if (!bin_tile_range(F, T.bbx, T.bby, &tx0, &tx1, &ty0, &ty1)) continue;
+        const int w = tx1 - tx0 + 1, n = w * (ty1 - ty0 + 1);
+        for (int i = (int)lane; i < n; i += 32) {
+            const int tx = tx0 + i % w, ty = ty0 + i / w;
+            const int px0 = tx * RX_TILE_W, py0 = F.band_y0 + ty * RX_TILE_H;
+            if (rect_overlaps(T, px0, py0, min(px0 + RX_TILE_W, F.width), min(py0 + RX_TILE_H, F.band_y1)) == 0u) continue;
+            const int t = ty * F.tiles_x + tx;
+            if (!fill) { atomicAdd(&tc[t], 1u); continue; }
+            if (tc[t] == 0u) continue;  // list dropped on arena overflow
+            lists[tb[t] + atomicAdd(&tf[t], 1u)] = slot;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_list_sort (general mode): one CTA per tile sorts its list ascending (= submission order).  The
 // allocation of a list is a power of two (k_tile_alloc), the tail is padded with 0xFFFFFFFF.
 // ---------------------------------------------------------------------------------------------
@@ -1649,6 +1682,12 @@ cudaError_t rxk_bin2d(const SceneDev& S, const Workspace& W, uint32_t n_frames, 
     if (S.n_rec2d == 0) return cudaSuccess;
     dim3 grid((S.n_rec2d + 7) / 8, n_frames);
     k_bin2d<<<grid, 256, 0, st>>>(S, W, fill);
+    return cudaGetLastError();
+}
+cudaError_t rxk_bin_large(const SceneDev& S, const Workspace& W, uint32_t n_frames, int fill, int grid_x, cudaStream_t st) {
+    if (S.n_tris == 0) return cudaSuccess;
+    dim3 grid(grid_x, n_frames);
+    k_bin_large<<<grid, 256, 0, st>>>(S, W, fill);
     return cudaGetLastError();
 }
 cudaError_t rxk_list_sort(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, int which, cudaStream_t st) {

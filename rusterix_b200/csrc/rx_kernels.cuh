@@ -93,6 +93,7 @@ cudaError_t rxk_bin_count(const SceneDev& S, const Workspace& W, uint32_t n_fram
 // which: 0 = 3D lists, 1 = 2D lists; pow2: round every allocation up to a power of two (lists that get sorted)
 cudaError_t rxk_tile_alloc(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, int which, int pow2,
                            cudaStream_t st);
+cudaError_t rxk_bin_large(const SceneDev& S, const Workspace& W, uint32_t n_frames, int fill, int grid, cudaStream_t st);
 cudaError_t rxk_bin2d(const SceneDev& S, const Workspace& W, uint32_t n_frames, int fill, cudaStream_t st);
 cudaError_t rxk_list_sort(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, int which, cudaStream_t st);
 cudaError_t rxk_bin_fill(const SceneDev& S, const Workspace& W, uint32_t n_frames, int grid, cudaStream_t st);

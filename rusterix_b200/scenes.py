@@ -377,6 +377,8 @@ def dense(width=7680, height=4320, tile_size=40, patches=32, patch_verts=23) -> 
 
 
 BUILDERS = {"cube": cube, "teapot": teapot, "map": map_config, "dense": dense, "sweep": sweep}
+BUILDERS["chunked"] = lambda **kw: chunked_config(**kw)
+BUILDERS["game2d"] = lambda **kw: game2d_config(**kw)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -554,7 +556,7 @@ def game2d_scene(cols=24, rows=16, tile_px=1.0) -> Scene:
 
 
 def game2d_config(width=960, height=640) -> Config:
-    scale = 40.0
+    scale = float(width) / 24.0
     m = np.array([[scale, 0.0, 0.0], [0.0, scale, 0.0], [0.0, 0.0, 1.0]], dtype=np.float32)
     mm = MapMini(linedefs=[CompiledLinedef((4.0, 5.5), (20.0, 5.5)), CompiledLinedef((12.0, 8.0), (12.0, 13.0))],
                  occluded_sectors=[(BBox((0.0, 0.0), (6.0, 4.0)), 0.2), (BBox((18.0, 8.0), (24.0, 16.0)), 0.6)])
