@@ -177,6 +177,13 @@ __device__ bool make_tri(const f4 P[3], const float2 uv[3], const f3 nn[3], uint
     s.n1x = nn[1].x; s.n1y = nn[1].y; s.n1z = nn[1].z;
     s.n2x = nn[2].x; s.n2y = nn[2].y; s.n2z = nn[2].z;
     s.pad0 = 0.0f; s.pad1 = 0.0f;
+    // flat triangle: the blend n*alpha + n*beta + n*gamma normalises to n/|n| (rasterizer.rs:1083-1092); the
+    // shade reads the unit normal from n0 and skips the interpolation
+    if (nn[0].x == nn[1].x && nn[0].y == nn[1].y && nn[0].z == nn[1].z && nn[0].x == nn[2].x && nn[0].y == nn[2].y && nn[0].z == nn[2].z) {
+        const f3 u = rx_normalize3(nn[0]);
+        s.n0x = u.x; s.n0y = u.y; s.n0z = u.z;
+        s.pad0 = __uint_as_float(1u);
+    }
     *ts = s;
     return true;
 }
@@ -755,6 +762,61 @@ __device__ __forceinline__ float fsmooth(const DLight& l, float x) {
     return t * t * __fmaf_rn(-2.0f, t, 3.0f);
 }
 
+// f32_to_u8_saturated (lib.rs:65-68) for an already decided owner: one multiply and a saturating
+// round-to-nearest conversion.  Differs from trunc(fma(x, 255, 0.5)) only when x*255 rounds onto k+0.5.
+__device__ __forceinline__ uint32_t fast_u8(float x) {
+    uint32_t r;
+    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(x * 255.0f));
+    return r;
+}
+// Texture::sample_nearest (texture.rs:307-323) for shading: floor(u*(W-1) + 0.5) instead of round() and
+// a saturating clamp; the exact version (rx_sample_tex) stays on the alpha-test path, which decides ownership.
+__device__ __forceinline__ float fast_wrap(float u, bool repeat) { return repeat ? (u - floorf(u)) : __saturatef(u); }
+__device__ __forceinline__ uint32_t sample_nearest_fast(const uint32_t* __restrict__ tex, int W, int H, float u, float v,
+                                                        bool repeat_x, bool repeat_y) {
+    u = fast_wrap(u, repeat_x);
+    v = fast_wrap(v, repeat_y);
+    const int tx = __float2int_rd(__fmaf_rn(u, (float)(W - 1), 0.5f));  // u in [0, 1] -> [0, W-1]; NaN -> 0
+    const int ty = __float2int_rd(__fmaf_rn(v, (float)(H - 1), 0.5f));
+    return __ldg(tex + ty * W + tx);
+}
+// Texture::sample_linear (texture.rs:414-460) for shading: same taps and weights, FMA lerps, channels
+// rounded by the saturating conversion
+__device__ __forceinline__ uint32_t sample_linear_fast(const uint32_t* __restrict__ tex, int W, int H, float u, float v,
+                                                       bool repeat_x, bool repeat_y) {
+    u = fast_wrap(u, repeat_x);
+    v = fast_wrap(v, repeat_y);
+    const float x = u * (float)(W - 1), y = v * (float)(H - 1);
+    const float fx = floorf(x), fy = floorf(y);
+    const int x0 = __float2int_rz(fx), y0 = __float2int_rz(fy);  // in [0, W-1]; NaN -> 0
+    const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+    const float dx = x - fx, dy = y - fy;
+    const uint32_t c00 = __ldg(tex + y0 * W + x0), c10 = __ldg(tex + y0 * W + x1);
+    const uint32_t c01 = __ldg(tex + y1 * W + x0), c11 = __ldg(tex + y1 * W + x1);
+    uint32_t out = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float v00 = (float)((c00 >> (8 * i)) & 0xFF), v10 = (float)((c10 >> (8 * i)) & 0xFF);
+        const float v01 = (float)((c01 >> (8 * i)) & 0xFF), v11 = (float)((c11 >> (8 * i)) & 0xFF);
+        const float a = __fmaf_rn(dx, v10 - v00, v00), b = __fmaf_rn(dx, v11 - v01, v01);
+        uint32_t c;
+        asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(c) : "f"(__fmaf_rn(dy, b - a, a)));
+        out |= c << (8 * i);
+    }
+    return out;
+}
+
+// What the deferred shade reads of the frame, staged in shared memory once per frame (DFrame lives in
+// global memory: every field read there costs an address move and a load per pixel).
+struct __align__(16) ShadeConst {
+    float s2w[16];
+    float cam[3];
+    uint32_t has_ambient;
+    float ambient[3];
+    uint32_t n_lights;
+};
+#define RX_SMEM_LIGHTS 16   // lights of the frame staged in shared memory (more: read from global memory)
+
 // Rasterizer::screen_to_world exactly as the reference composes it (rasterizer.rs:1707-1727): used where the
 // world position decides ownership (alpha test of a terrain texel); the shade uses the folded DFrame::s2w.
 __device__ __forceinline__ f3 screen_to_world_exact(const DFrame& F, float x, float y, float z) {
@@ -871,7 +933,8 @@ __device__ __forceinline__ uint32_t sample_desc(const uint8_t* __restrict__ aren
 }
 
 // rasterizer.rs:1062-1404 + :1875-1951 for the owning fragment of a pixel; returns RGBA8.
-__device__ __forceinline__ uint32_t shade_owner(const SceneDev& S, const DFrame& F, const DLight* __restrict__ lights,
+// K, lights and kd_lut are in shared memory (kd_lut[c] = srgb_to_linear_fast(c / 255) * 0.96).
+__device__ __forceinline__ uint32_t shade_owner(const SceneDev& S, const ShadeConst& K, const DLight* lights, const float* kd_lut,
                                                 const DFrameBatch& FB, const TriShade* __restrict__ shp, float alpha, float beta,
                                                 float z, float fpx, float fpy, uint32_t sample_mode) {
     const float4* sq = reinterpret_cast<const float4*>(shp);
@@ -885,52 +948,59 @@ __device__ __forceinline__ uint32_t shade_owner(const SceneDev& S, const DFrame&
     if (flags & RX_SD_TEXTURED) {
         // perspective-correct UV, rasterizer.rs:1062-1076.  The owner is decided; the quotients are
         // faithful (rcp + one residual correction) instead of div.rn.
-        const float iu = s0.x * alpha + s0.z * beta + s1.x * gamma;
-        const float iv = s0.y * alpha + s0.w * beta + s1.y * gamma;
-        const float irw = s1.z * alpha + s1.w * beta + s2.x * gamma;
+        const float iu = __fmaf_rn(s1.x, gamma, __fmaf_rn(s0.z, beta, s0.x * alpha));
+        const float iv = __fmaf_rn(s1.y, gamma, __fmaf_rn(s0.w, beta, s0.y * alpha));
+        const float irw = __fmaf_rn(s2.x, gamma, __fmaf_rn(s1.w, beta, s1.z * alpha));
         const float rr = fast_rcp(irw);
         float u = iu * rr, v = iv * rr;
         u = __fmaf_rn(__fmaf_rn(-irw, u, iu), rr, u);
         v = __fmaf_rn(__fmaf_rn(-irw, v, iv), rr, v);
-        texel = sample_desc(S.arena, d0.x, d0.y, flags, u, v, sample_mode);
+        const uint32_t* tex = reinterpret_cast<const uint32_t*>(S.arena) + d0.x;
+        const int W = (int)(d0.y & 0xFFFFu), H = (int)(d0.y >> 16);
+        if (sample_mode == RXC_SAMPLE_NEAREST) texel = sample_nearest_fast(tex, W, H, u, v, (flags & RX_SD_REPEAT_X) != 0u, (flags & RX_SD_REPEAT_Y) != 0u);
+        else texel = sample_linear_fast(tex, W, H, u, v, (flags & RX_SD_REPEAT_X) != 0u, (flags & RX_SD_REPEAT_Y) != 0u);
     }
 
-    // screen_to_world, rasterizer.rs:1707-1727, folded into one affine map + divide (DFrame::s2w)
-    const float hx = __fmaf_rn(F.s2w[2], z, __fmaf_rn(F.s2w[1], fpy, __fmaf_rn(F.s2w[0], fpx, F.s2w[3])));
-    const float hy = __fmaf_rn(F.s2w[6], z, __fmaf_rn(F.s2w[5], fpy, __fmaf_rn(F.s2w[4], fpx, F.s2w[7])));
-    const float hz = __fmaf_rn(F.s2w[10], z, __fmaf_rn(F.s2w[9], fpy, __fmaf_rn(F.s2w[8], fpx, F.s2w[11])));
-    const float hw = __fmaf_rn(F.s2w[14], z, __fmaf_rn(F.s2w[13], fpy, __fmaf_rn(F.s2w[12], fpx, F.s2w[15])));
+    // screen_to_world, rasterizer.rs:1707-1727, folded into one projective map (DFrame::s2w)
+    const float4 m0 = *reinterpret_cast<const float4*>(&K.s2w[0]), m1 = *reinterpret_cast<const float4*>(&K.s2w[4]);
+    const float4 m2 = *reinterpret_cast<const float4*>(&K.s2w[8]), m3 = *reinterpret_cast<const float4*>(&K.s2w[12]);
+    const float4 kc = *reinterpret_cast<const float4*>(&K.cam[0]), ka = *reinterpret_cast<const float4*>(&K.ambient[0]);
+    const float hx = __fmaf_rn(m0.z, z, __fmaf_rn(m0.y, fpy, __fmaf_rn(m0.x, fpx, m0.w)));
+    const float hy = __fmaf_rn(m1.z, z, __fmaf_rn(m1.y, fpy, __fmaf_rn(m1.x, fpx, m1.w)));
+    const float hz = __fmaf_rn(m2.z, z, __fmaf_rn(m2.y, fpy, __fmaf_rn(m2.x, fpx, m2.w)));
+    const float hw = __fmaf_rn(m3.z, z, __fmaf_rn(m3.y, fpy, __fmaf_rn(m3.x, fpx, m3.w)));
     const float ihw = fast_rcp(hw);
     const f3 world = {hx * ihw, hy * ihw, hz * ihw};
-    const f3 view_dir = fnormalize3({F.cam[0] - world.x, F.cam[1] - world.y, F.cam[2] - world.z});
+    const f3 view_dir = fnormalize3({kc.x - world.x, kc.y - world.y, kc.z - world.z});
 
     if (flags & RX_SD_TERRAIN) texel = terrain_sample(S.arena, d0.x, d0.y, S.chunk_info[__float_as_int(d1.w)], world.x, world.z);
 
     f3 normal = {0.0f, 0.0f, 0.0f};
     if (flags & RX_SD_NORMALS) {  // rasterizer.rs:1083-1099
-        const float4 s3 = __ldg(sq + 3), s4 = __ldg(sq + 4);
-        normal = {__fmaf_rn(s3.w, gamma, __fmaf_rn(s3.x, beta, s2.y * alpha)),
-                  __fmaf_rn(s4.x, gamma, __fmaf_rn(s3.y, beta, s2.z * alpha)),
-                  __fmaf_rn(s4.y, gamma, __fmaf_rn(s3.z, beta, s2.w * alpha))};
-        normal = fnormalize3(normal);
+        const float4 s4 = __ldg(sq + 4);
+        if (__float_as_uint(s4.z) != 0u) {
+            normal = {s2.y, s2.z, s2.w};  // the three vertex normals are equal: n0 holds the unit normal (make_tri)
+        } else {
+            const float4 s3 = __ldg(sq + 3);
+            normal = {__fmaf_rn(s3.w, gamma, __fmaf_rn(s3.x, beta, s2.y * alpha)),
+                      __fmaf_rn(s4.x, gamma, __fmaf_rn(s3.y, beta, s2.z * alpha)),
+                      __fmaf_rn(s4.y, gamma, __fmaf_rn(s3.z, beta, s2.w * alpha))};
+            normal = fnormalize3(normal);
+        }
         if (fdot3(normal, view_dir) < 0.0f) normal = {-normal.x, -normal.y, -normal.z};
     } else {
         normal = fnormalize3(normal);  // Vec3::zero().normalized() is NaN in the reference (:1320)
     }
 
-    const float inv255 = 1.0f / 255.0f;
-    auto s2l = [](float x) { const float x2 = x * x; return __fmaf_rn(0.6975f, x2, 0.3025f) * x; };  // rasterizer.rs:20-25
-    const f3 base = {s2l((float)(texel & 0xFF) * inv255), s2l((float)((texel >> 8) & 0xFF) * inv255),
-                     s2l((float)((texel >> 16) & 0xFF) * inv255)};
-
-    // roughness 0.5, metallic 0 (no batch shader): f0 = 0.04, kd = base * 0.96, shininess = 2/0.25 - 2 = 6
-    const float hemi = 0.5f * (normal.y + 1.0f);
-    const f3 kd = rx_scale3(base, 1.0f - 0.04f);
+    // roughness 0.5, metallic 0 (no batch shader): f0 = 0.04, kd = srgb_to_linear_fast(texel) * 0.96 (rasterizer.rs:20-25),
+    // shininess = 2/0.25 - 2 = 6
+    const f3 kd = {kd_lut[texel & 0xFFu], kd_lut[(texel >> 8) & 0xFFu], kd_lut[(texel >> 16) & 0xFFu]};
+    const float hemi = __fmaf_rn(0.5f, normal.y, 0.5f);
     f3 amb = {d1.x, d1.y, d1.z};                                                        // :1368-1370
-    if (F.has_ambient) {  // :1327-1365: the sky term is scaled by the sector occlusion (0 when it is not > 0)
+    if (K.has_ambient) {  // :1327-1365: the sky term is scaled by the sector occlusion (0 when it is not > 0)
         float occ = 1.0f;
         if (S.n_sectors) { const float o = sector_occlusion(S, __float_as_int(d1.w), world.x, world.z); occ = o > 0.0f ? o : 0.0f; }
-        amb = {__fmaf_rn(F.ambient[0], occ, amb.x), __fmaf_rn(F.ambient[1], occ, amb.y), __fmaf_rn(F.ambient[2], occ, amb.z)};
+        amb = {__fmaf_rn(ka.x, occ, amb.x), __fmaf_rn(ka.y, occ, amb.y), __fmaf_rn(ka.z, occ, amb.z)};
     }
     f3 lit = {amb.x * kd.x * hemi, amb.y * kd.y * hemi, amb.z * kd.z * hemi};
 
@@ -938,7 +1008,8 @@ __device__ __forceinline__ uint32_t shade_owner(const SceneDev& S, const DFrame&
     const float om = 1.0f - fminf(n_dot_v, 1.0f);
     const float om2 = om * om;
     const float fr = __fmaf_rn(1.0f - 0.04f, om2 * om2 * om, 0.04f);  // schlick_fresnel with f0 = 0.04 (:1882-1887)
-    for (uint32_t li = 0; li < S.n_lights; ++li) {  // rasterizer.rs:1373-1391
+    const uint32_t n_lights = __float_as_uint(ka.w);
+    for (uint32_t li = 0; li < n_lights; ++li) {  // rasterizer.rs:1373-1391
         const DLight& L = lights[li];
         const f3 to_l = {L.px - world.x, L.py - world.y, L.pz - world.z};
         const float d2 = fdot3(to_l, to_l);
@@ -958,8 +1029,7 @@ __device__ __forceinline__ uint32_t shade_owner(const SceneDev& S, const DFrame&
     }
     auto l2s = [](float x) { const float s = fast_sqrt(x); return __fmaf_rn(-0.055f * s, s, 1.055f * s); };  // rasterizer.rs:28-33
     const uint32_t a8 = texel >> 24;  // f32_to_u8_saturated(a / 255) == a for every u8 a
-    return rx_f32_to_u8_saturated(l2s(lit.x)) | (rx_f32_to_u8_saturated(l2s(lit.y)) << 8) |
-           (rx_f32_to_u8_saturated(l2s(lit.z)) << 16) | (a8 << 24);
+    return fast_u8(l2s(lit.x)) | (fast_u8(l2s(lit.y)) << 8) | (fast_u8(l2s(lit.z)) << 16) | (a8 << 24);
 }
 
 // The opacity layer's pixel (rasterizer.rs:1500-1645): texel -> linear -> sRGB, no lighting; alpha = texel alpha.
@@ -1153,6 +1223,23 @@ __device__ __forceinline__ uint32_t rect_overlaps(const TriVis& T, int tx0, int 
     return inside ? 2u : 1u;
 }
 
+// texel of a z-passing fragment of an alpha-tested batch (rasterizer.rs:1062-1222): exact arithmetic, it decides
+// ownership (:1408).  Out of line: rare, and the visibility loop is instantiated once per pixel of the 2x2.
+__device__ __noinline__ uint32_t alpha_test_texel(const uint8_t* __restrict__ arena, const DChunkInfo* __restrict__ chunk_info,
+                                                  const DFrame* __restrict__ F, const DFrameBatch* __restrict__ FB,
+                                                  const TriShade* __restrict__ sh, float alpha, float beta, float z, float fpx, float fpy,
+                                                  uint32_t sample_mode) {
+    if (FB->sd_flags & RX_SD_TERRAIN) {
+        const f3 world = screen_to_world_exact(*F, fpx, fpy, z);
+        return terrain_sample(arena, FB->sd_tex_word, FB->sd_wh, chunk_info[FB->sd_chunk], world.x, world.z);
+    }
+    const float gamma = 1.0f - alpha - beta;
+    const float iu = sh->uw0 * alpha + sh->uw1 * beta + sh->uw2 * gamma;
+    const float iv = sh->vw0 * alpha + sh->vw1 * beta + sh->vw2 * gamma;
+    const float irw = sh->rw0 * alpha + sh->rw1 * beta + sh->rw2 * gamma;
+    return sample_desc(arena, FB->sd_tex_word, FB->sd_wh, FB->sd_flags, iu / irw, iv / irw, sample_mode);
+}
+
 // depth + alpha test of one covered pixel (rasterizer.rs:1051-1060, :1408)
 __device__ __forceinline__ void test_fragment(const SceneDev& S, const DFrame& F, const DFrameBatch* __restrict__ fbs,
                                               const TriShade* __restrict__ shade, const float4 q0, const float4 q1, const float4 q2,
@@ -1173,18 +1260,8 @@ __device__ __forceinline__ void test_fragment(const SceneDev& S, const DFrame& F
     const bool pass_z = (z < best_z) || (z == best_z && best != RX_OWNER_NONE && slot < best);
     if (!pass_z) return;
     if (meta & RX_META_ALPHA) {  // alpha test: texel alpha must be 255 to write (:1408)
-        const DFrameBatch& FB = fbs[meta & RX_META_BATCH];
-        uint32_t texel;
-        if (FB.sd_flags & RX_SD_TERRAIN) {
-            const f3 world = screen_to_world_exact(F, fpx, fpy, z);
-            texel = terrain_sample(S.arena, FB.sd_tex_word, FB.sd_wh, S.chunk_info[FB.sd_chunk], world.x, world.z);
-        } else {
-            const TriShade& sh = shade[slot];
-            const float iu = sh.uw0 * alpha + sh.uw1 * beta + sh.uw2 * gamma;
-            const float iv = sh.vw0 * alpha + sh.vw1 * beta + sh.vw2 * gamma;
-            const float irw = sh.rw0 * alpha + sh.rw1 * beta + sh.rw2 * gamma;
-            texel = sample_desc(S.arena, FB.sd_tex_word, FB.sd_wh, FB.sd_flags, iu / irw, iv / irw, sample_mode);
-        }
+        const uint32_t texel = alpha_test_texel(S.arena, S.chunk_info, &F, fbs + (meta & RX_META_BATCH), shade + slot, alpha, beta, z, fpx, fpy,
+                                                sample_mode);
         if ((texel >> 24) != 255u) return;
     }
     best_z = z; best = slot; best_al = alpha; best_be = beta;
@@ -1285,6 +1362,9 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
     __shared__ __align__(16) uint32_t s_color[RX_TILE_H * RX_COLOR_STRIDE];
     __shared__ float4 s_state[4 * RX_TILE_THREADS];  // (z, owner, alpha, beta) of pixel k of thread t at [k*256 + t]
     __shared__ float2 s_ostate[GENERAL ? 4 * RX_TILE_THREADS : 1];  // (z, owner) of the opacity layer
+    __shared__ ShadeConst s_k;                       // frame constants of the deferred shade
+    __shared__ __align__(16) DLight s_lights[RX_SMEM_LIGHTS];
+    __shared__ float s_kd[256];                      // srgb_to_linear_fast(c / 255) * (1 - 0.04), rasterizer.rs:20-25
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // warp w covers a 16x8 region (2 across, 4 down); lane (lx, ly) of the 8x4 lane grid owns the
@@ -1293,6 +1373,10 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
     const int lx = (int)(lane & 7), ly = (int)(lane >> 3);
     const uint32_t total = n_frames * tiles_per_frame;
     uint32_t cached_frame = 0xFFFFFFFFu, n_cached = 0;
+    {
+        const float x = (float)tid * (1.0f / 255.0f);
+        s_kd[tid] = (__fmaf_rn(0.6975f, x * x, 0.3025f) * x) * (1.0f - 0.04f);  // visible after the first tile's barrier
+    }
 
     for (;;) {
         if (tid == 0) {
@@ -1313,10 +1397,36 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
         const uint32_t f = (uint32_t)s_work[0], tile = (uint32_t)s_work[3];
         const DFrame& F = Wk.frames[f];
         const DCounters& C = Wk.counters[f];
-        const DLight* lights = Wk.lights + (size_t)f * Wk.lights_stride;
+        const DLight* lights_g = Wk.lights + (size_t)f * Wk.lights_stride;
         const TriVis* vis = Wk.vis + (size_t)f * Wk.slot_stride;
         const TriShade* shade = Wk.shade + (size_t)f * Wk.slot_stride;
         const DFrameBatch* fbs = Wk.fb + (size_t)f * Wk.fb_stride;
+        const uint32_t n_large = (GENERAL || !F.d3_active) ? 0u : min(C.n_large, Wk.large_stride);
+        const uint32_t* large = Wk.large + (size_t)f * Wk.large_stride;
+
+        if (f != cached_frame) {  // uniform for the CTA: stage what every tile of this frame reads
+            if (tid < 16) s_k.s2w[tid] = F.s2w[tid];
+            else if (tid < 19) s_k.cam[tid - 16] = F.cam[tid - 16];
+            else if (tid == 19) s_k.has_ambient = F.has_ambient;
+            else if (tid < 23) s_k.ambient[tid - 20] = F.ambient[tid - 20];
+            else if (tid == 23) s_k.n_lights = S.n_lights;
+            for (uint32_t i = tid; i < min(S.n_lights, (uint32_t)RX_SMEM_LIGHTS) * (uint32_t)(sizeof(DLight) / 4); i += RX_TILE_THREADS)
+                reinterpret_cast<uint32_t*>(s_lights)[i] = __ldg(reinterpret_cast<const uint32_t*>(lights_g) + i);
+            if (!GENERAL) {  // large-triangle records of the frame
+                n_cached = min(n_large, (uint32_t)RX_LARGE_CACHE);
+                const float4* g = reinterpret_cast<const float4*>(vis);
+                float4* sq = reinterpret_cast<float4*>(s_large);
+                for (uint32_t i = tid; i < n_cached * 6u; i += RX_TILE_THREADS) {
+                    const uint32_t r = i / 6u, q = i - r * 6u;
+                    const uint32_t slot = __ldg(large + r);
+                    if (q == 0) s_large_slot[r] = slot;
+                    sq[i] = __ldg(g + (size_t)slot * 6u + q);
+                }
+            }
+            cached_frame = f;
+            __syncthreads();
+        }
+        const DLight* lights = S.n_lights <= (uint32_t)RX_SMEM_LIGHTS ? s_lights : lights_g;
 
         const uint32_t smode = SAMPLE == 2 ? F.sample_mode : (uint32_t)SAMPLE;
         const int fw = F.width, fy1 = F.band_y1;
@@ -1339,60 +1449,34 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
         O.some = 0u;
 
         if (F.d3_active) {
-            const uint32_t n_large = GENERAL ? 0u : min(C.n_large, Wk.large_stride);
-            const uint32_t* large = Wk.large + (size_t)f * Wk.large_stride;
-            if (!GENERAL) {
-                // (1) large triangles: records cached in shared memory per frame, culled per tile, then per warp region
-                if (f != cached_frame) {
-                    n_cached = min(n_large, (uint32_t)RX_LARGE_CACHE);
-                    const float4* g = reinterpret_cast<const float4*>(vis);
-                    float4* sq = reinterpret_cast<float4*>(s_large);
-                    for (uint32_t i = tid; i < n_cached * 6u; i += RX_TILE_THREADS) {
-                        const uint32_t r = i / 6u, q = i - r * 6u;
-                        const uint32_t slot = __ldg(large + r);
-                        if (q == 0) s_large_slot[r] = slot;
-                        sq[i] = __ldg(g + (size_t)slot * 6u + q);
-                    }
-                    cached_frame = f;
-                    __syncthreads();
-                }
-                if (n_cached > 32u) {  // two-level: tile-level selection by the CTA, then per warp region
-                    if (tid < n_cached && rect_overlaps(s_large[tid], tx0, ty0, tx1, ty1) != 0u) s_sel[atomicAdd(&s_nsel, 1u)] = (uint16_t)tid;
-                    __syncthreads();
-                }
-                const uint32_t n = n_cached > 32u ? s_nsel : n_cached;
-                for (uint32_t base = 0; base < n; base += 32) {
-                    const uint32_t i = base + lane;
-                    const uint32_t r = i < n ? (n_cached > 32u ? (uint32_t)s_sel[i] : i) : 0u;
-                    const uint32_t ov = (i < n && region_ok) ? rect_overlaps(s_large[r], rx0, ry0, rx1, ry1) : 0u;
-                    uint32_t mask = __ballot_sync(0xFFFFFFFFu, ov != 0u);
-                    const uint32_t fullm = __ballot_sync(0xFFFFFFFFu, ov == 2u);
-                    while (mask) {
-                        const int b = __ffs(mask) - 1;
-                        mask &= mask - 1u;
-                        const uint32_t rr = __shfl_sync(0xFFFFFFFFu, r, b);
-                        process_record<false>(S, F, fbs, shade, &s_large[rr], s_large_slot[rr], (fullm >> b) & 1u, px0, py0, fx0, fy0, valid,
-                                              smode, V, O);
-                    }
-                }
+            // Three sources of triangle records, one walk: (0) the large triangles cached in shared memory (culled
+            // per tile by the CTA when there are many), (1) the rest of the large list, (2) the tile's binned list.
+            // Warp-private: every lane fetches one record and tests it against the warp's region, the survivors are
+            // then read by the whole warp (broadcast loads) -- no staging, no CTA barrier.  Lanes and mask bits are
+            // visited in list order, which general mode relies on.
+            if (!GENERAL && n_cached > 32u) {
+                if (tid < n_cached && rect_overlaps(s_large[tid], tx0, ty0, tx1, ty1) != 0u) s_sel[atomicAdd(&s_nsel, 1u)] = (uint16_t)tid;
+                __syncthreads();
             }
-            // (2) the rest of the large list, then the tile's binned list.  Warp-private: every lane fetches one
-            // record of the list from L2/L1 and tests it against the warp's region, the survivors are then read
-            // by the whole warp (broadcast loads of lines the warp just touched) -- no staging, no CTA barrier.
-            // Lanes and mask bits are visited in list order, which general mode relies on.
             const uint32_t n_list = Wk.tile_count[(size_t)f * Wk.tile_stride + tile];
             const uint32_t* list = Wk.lists + (size_t)f * Wk.list_stride + Wk.tile_base[(size_t)f * Wk.tile_stride + tile];
 #pragma unroll 1
-            for (int pass = GENERAL ? 1 : 0; pass < 2; ++pass) {
-                const uint32_t* src = pass == 0 ? large + n_cached : list;
-                const uint32_t n_src = pass == 0 ? n_large - n_cached : n_list;
+            for (int pass = GENERAL ? 2 : 0; pass < 3; ++pass) {
+                const uint32_t n_src = pass == 0 ? (n_cached > 32u ? s_nsel : n_cached) : pass == 1 ? n_large - n_cached : n_list;
+                const uint32_t* src = pass == 1 ? large + n_cached : list;
 #pragma unroll 1
                 for (uint32_t base = 0; base < n_src; base += 32) {
                     const uint32_t i = base + lane;
                     uint32_t slot = 0u, ov = 0u;
+                    const TriVis* rp = vis;   // shared (pass 0) or global memory
                     if (i < n_src) {
-                        slot = __ldg(src + i);
-                        if (region_ok) ov = rect_overlaps(vis[slot], rx0, ry0, rx1, ry1);
+                        if (!GENERAL && pass == 0) {
+                            const uint32_t r = n_cached > 32u ? (uint32_t)s_sel[i] : i;
+                            rp = &s_large[r]; slot = s_large_slot[r];
+                        } else {
+                            slot = __ldg(src + i); rp = vis + slot;
+                        }
+                        if (region_ok) ov = rect_overlaps(*rp, rx0, ry0, rx1, ry1);
                     }
                     uint32_t mask = __ballot_sync(0xFFFFFFFFu, ov != 0u);
                     const uint32_t fullm = __ballot_sync(0xFFFFFFFFu, ov == 2u);
@@ -1400,7 +1484,8 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                         const int b = __ffs(mask) - 1;
                         mask &= mask - 1u;
                         const uint32_t rr = __shfl_sync(0xFFFFFFFFu, slot, b);
-                        process_record<GENERAL>(S, F, fbs, shade, vis + rr, rr, (fullm >> b) & 1u, px0, py0, fx0, fy0, valid, smode, V, O);
+                        const TriVis* Tp = reinterpret_cast<const TriVis*>(__shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(rp), b));
+                        process_record<GENERAL>(S, F, fbs, shade, Tp, rr, (fullm >> b) & 1u, px0, py0, fx0, fy0, valid, smode, V, O);
                     }
                 }
             }
@@ -1424,7 +1509,7 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
             if (F.d3_active) {
                 if (owner != RX_OWNER_NONE) {
                     const uint32_t b = __ldg(&vis[owner].meta) & RX_META_BATCH;
-                    color = shade_owner(S, F, lights, fbs[b], shade + owner, st.z, st.w, st.x, fpx, fpy, smode);
+                    color = shade_owner(S, s_k, lights, s_kd, fbs[b], shade + owner, st.z, st.w, st.x, fpx, fpy, smode);
                 } else {
                     color = 0xFF000000u;  // vec4_to_pixel((0,0,0,1))
                 }
