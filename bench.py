@@ -175,10 +175,35 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": val, "unit": "Mpixel/s", "cores": cores, "kind": "port", "sample": f"{args.steps} frames, 1 per step"},
         "e2e": {"value": val, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit_line(line)
+
+
+_JSON_FD = None
+
+
+def capture_stdout():
+    """Library chatter (e.g. NCCL's version banner) must not share stdout with the one JSON line the
+    driver parses: everything written to fd 1 from here on goes to stderr, emit_line() writes the result
+    to the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
 
 
 def main():
+    capture_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -379,7 +404,7 @@ def main():
         line["cpu_baseline"] = None
 
     if rank == 0:
-        print(json.dumps(line))
+        emit_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
