@@ -39,6 +39,7 @@ WORKLOADS = {
     "cube800": ("cube", dict(width=800, height=600, tile_size=200), "textured cube, 800x600, Nearest, tile 200"),
     # the rows SURVEY 8f marks "next", measured like the others
     "chunked1080": ("chunked", dict(width=1920, height=1080, tile_size=40), "chunked map (4 chunks: opacity panes with surface ids, terrain textures, occluded sectors, chunk lights, entity/item tiles, 2D overlay with lines), 1920x1080, Nearest"),
+    "shaded1080": ("shaded", dict(width=1920, height=1080, tile_size=40), "batch shaders (Rusteria VM programs on 3D, chunk, opacity-pass and 2D batches; one program cuts holes through opacity), 1920x1080, Nearest"),
     "game2d1080": ("game2d", dict(width=1920, height=1280), "2D game screen (834 2D records in sorted per-tile lists, translucent decals, sprites, 2 point lights with line of sight, sector occlusion, lines), 1920x1280, 2D-only render mode"),
 }
 
@@ -392,7 +393,7 @@ def main():
         mpix, cores, sample, spf = cpu_port_time(cfg, frame_ids)
         line["cpu_baseline"] = {"value": mpix, "unit": "Mpixel/s", "cores": cores, "kind": "port", "sample": sample, "s_per_frame": spf}
         also = {}
-        for wname in ("teapot1080", "dense8k", "sweep1080", "chunked1080", "game2d1080"):
+        for wname in ("teapot1080", "dense8k", "sweep1080", "chunked1080", "game2d1080", "shaded1080"):
             if wname == args.workload:
                 continue
             try:

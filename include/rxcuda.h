@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RXC_ABI_VERSION 2u
+#define RXC_ABI_VERSION 3u
 
 typedef struct rxc_ctx rxc_ctx;
 
@@ -135,7 +135,9 @@ typedef struct rxc_batch3d {
     float ambient_color[3];
     uint32_t has_profile_id;
     uint32_t profile_id;
-    int32_t shader;         /* -1 = None; anything else -> RXC_ERR_UNSUPPORTED           */
+    int32_t shader;         /* batch.shader: -1 = None, else an index into scene.shaders, or into the
+                               shaders of the batch's chunk (rxc_chunk.shader_base) when chunk >= 0
+                               (src/rasterizer.rs:1226-1293); an index past the list runs no program */
     uint32_t pass;          /* RXC_PASS_*; CHUNK_OPACITY batches go through d3_rasterize_opacity
                                (src/rasterizer.rs:1425-1690), everything else through d3_rasterize */
     float transform[16];    /* transform_3d, column-major                                */
@@ -161,6 +163,50 @@ typedef struct rxc_batch2d {
     int32_t chunk;         /* as in rxc_batch3d */
 } rxc_batch2d;
 
+/* Rusteria VM programs (reference rusteria/src/node/nodeop.rs:12-103, program.rs:7-29, execution.rs:109-768).
+ * The host lowers the NodeOp tree of Program.user_functions[shade_index] and of every function it can call
+ * to a stream of 32-bit words: word = opcode | (a << 8).  Opcodes 0..89 are the NodeOp variants in declaration
+ * order (RXVM_LOAD_GLOBAL = 0 ... RXVM_PALETTE_INDEX = 89); the lowering adds RXVM_JZ..RXVM_END:
+ *   LoadGlobal/StoreGlobal/LoadLocal/StoreLocal   a = index
+ *   GetComponents   a = n | c0<<3 | c1<<5 | c2<<7 with the swizzle entries > 2 already dropped; n = 7 pushes 0
+ *   SetComponents   a = n | c0<<3 | c1<<5 | c2<<7, n = swizzle length if 1..3 else 0, c = 3 is ignored
+ *   Push            followed by three words: the f32 bits of x, y, z
+ *   FunctionCall    a = arity | total_locals<<8, followed by one word: the offset of the callee
+ *   If(t, e)        Jz L1; t...; Jmp L2; L1: e...; L2:        (Jz pops and jumps when value.x == 0.0)
+ *   For(i,c,n,b)    Mark; i; Trunc; L: c; Jz E; Trunc; b; Trunc; n; Trunc; Jmp L; E: Unmark
+ *                   (Mark remembers the stack height, Trunc is stack.truncate(base), execution.rs:259-285)
+ *   every function body ends with End; Alloc / Iterate / Save (texture baking) are rejected.
+ * Device limits: value stack 32, 32 locals per frame, 16 globals, call depth 8, loop depth 8, 2^20 ops per call. */
+enum {
+    RXVM_LOAD_GLOBAL = 0, RXVM_STORE_GLOBAL, RXVM_LOAD_LOCAL, RXVM_STORE_LOCAL, RXVM_SWAP, RXVM_GET_COMPONENTS,
+    RXVM_SET_COMPONENTS, RXVM_IF, RXVM_FOR, RXVM_PUSH, RXVM_FUNCTION_CALL, RXVM_RETURN, RXVM_DUP, RXVM_CLEAR, RXVM_PACK2,
+    RXVM_PACK3, RXVM_ADD, RXVM_SUB, RXVM_MUL, RXVM_DIV, RXVM_LENGTH, RXVM_LENGTH2, RXVM_LENGTH3, RXVM_ABS, RXVM_SIN,
+    RXVM_SIN1, RXVM_SIN2, RXVM_COS, RXVM_COS1, RXVM_COS2, RXVM_TAN, RXVM_ATAN, RXVM_ATAN2, RXVM_ROTATE2D, RXVM_DOT,
+    RXVM_DOT2, RXVM_DOT3, RXVM_CROSS, RXVM_NORMALIZE, RXVM_FLOOR, RXVM_CEIL, RXVM_ROUND, RXVM_FRACT, RXVM_MOD,
+    RXVM_DEGREES, RXVM_RADIANS, RXVM_MIN, RXVM_MAX, RXVM_MIX, RXVM_SMOOTHSTEP, RXVM_STEP, RXVM_CLAMP, RXVM_SQRT,
+    RXVM_POW, RXVM_LOG, RXVM_PRINT, RXVM_EQ, RXVM_NE, RXVM_LT, RXVM_LE, RXVM_GT, RXVM_GE, RXVM_AND, RXVM_OR, RXVM_NOT,
+    RXVM_NEG, RXVM_UV, RXVM_SET_UV, RXVM_NORMAL, RXVM_SET_NORMAL, RXVM_HITPOINT, RXVM_TIME, RXVM_SAMPLE,
+    RXVM_SAMPLE_NORMAL, RXVM_COLOR, RXVM_SET_COLOR, RXVM_ROUGHNESS, RXVM_SET_ROUGHNESS, RXVM_METALLIC, RXVM_SET_METALLIC,
+    RXVM_EMISSIVE, RXVM_SET_EMISSIVE, RXVM_OPACITY, RXVM_SET_OPACITY, RXVM_BUMP, RXVM_SET_BUMP, RXVM_ALLOC, RXVM_ITERATE,
+    RXVM_SAVE, RXVM_PALETTE_INDEX,
+    RXVM_JZ, RXVM_JMP, RXVM_MARK, RXVM_TRUNC, RXVM_UNMARK, RXVM_END, RXVM_N_OPS
+};
+typedef struct rxc_program {
+    const uint32_t* code;   /* NULL / 0 words: Program.shade_index is None, nothing runs             */
+    uint32_t n_words;
+    uint32_t entry;         /* word offset of shade()                                                */
+    uint32_t shade_locals;  /* Program.shade_locals                                                  */
+    uint32_t n_globals;     /* Program.globals                                                       */
+    uint32_t sets_opacity;  /* Program::shader_supports_opacity() (program.rs:44-55)                 */
+} rxc_program;
+/* a pattern texture of the VM's `sample` op: TexStorage of Value = Vec3<f32> (rusteria/src/textures/mod.rs:11-24),
+ * nearest lookup with wrap-around (:131-146) */
+typedef struct rxc_pattern {
+    const float* data;      /* width*height * [x,y,z] */
+    uint32_t width;
+    uint32_t height;
+} rxc_pattern;
+
 /* (BBox, occlusion) entries of chunk.occluded_sectors / mapmini.occluded_sectors
  * (src/chunk.rs:41, src/map/mini.rs:33, src/map/bbox.rs:35-40: contains() is inclusive). */
 typedef struct rxc_sector {
@@ -177,6 +223,11 @@ typedef struct rxc_chunk {
     const rxc_sector* occluded_sectors; /* searched in order, first hit wins (src/chunk.rs:154-161) */
     uint32_t n_occluded_sectors;
     const rxc_texture* terrain_texture; /* NULL = None */
+    uint32_t shader_base;               /* chunk.shaders[i] is rxc_scene.shaders[shader_base + i]     */
+    uint32_t n_shaders;
+    const rxc_texture* const* shader_textures; /* chunk.shader_textures (n_shaders entries, NULL = None) or NULL:
+                                           a baked texture replaces the batch's texel and its program does
+                                           not run in the opaque 3D pass (src/rasterizer.rs:1227-1262)     */
 } rxc_chunk;
 
 /* CompiledLinedef start/end (src/map/mini.rs:88-95: a light is blocked when the segment
@@ -212,6 +263,15 @@ typedef struct rxc_scene {
     uint32_t n_chunks;
     const rxc_tile* actor_tiles;      /* tiles RXC_SRC_ENTITY_TILE / RXC_SRC_ITEM_TILE index     */
     uint32_t n_actor_tiles;
+    const rxc_program* shaders;       /* scene.shaders, then the shaders of every chunk (rxc_chunk.shader_base) */
+    uint32_t n_shaders;
+    uint32_t n_scene_shaders;         /* scene.shaders.len(): the range batches without a chunk index     */
+    const rxc_pattern* patterns;      /* rusteria patterns() bank (textures/patterns.rs:88-102), host computed */
+    uint32_t n_patterns;
+    const rxc_pattern* patterns_normal;
+    uint32_t n_patterns_normal;
+    const float* palette;             /* assets.palette.colors as n_palette * [present, r, g, b]          */
+    uint32_t n_palette;
 } rxc_scene;
 
 /* Everything Rasterizer::setup + the builder methods + rasterize()'s scalar arguments carry
@@ -307,6 +367,12 @@ int32_t rxc_owner_base(const rxc_ctx* ctx, uint32_t batch, uint32_t* base);
  * and returns how many results differ (must be 0); bad_pair (optional, 2 words) receives the bits
  * of one failing (numerator, divisor). */
 int32_t rxc_selftest_div(rxc_ctx* ctx, uint64_t seed, uint64_t n_pairs, uint64_t* mismatches, uint32_t* bad_pair);
+
+/* Diagnostics: runs shader `program` of the current scene once per record on the device, outside the
+ * rasterizer.  in: n * 18 floats (uv, color, normal, hitpoint, time, opacity as Vec3 each); out: n * 24 floats
+ * (uv, color, normal, roughness, metallic, emissive, opacity, bump).  Roughness starts at 0.5, the rest of
+ * Execution at zero (execution.rs:58-77).  faults (optional) counts records that hit a device limit. */
+int32_t rxc_vm_execute(rxc_ctx* ctx, uint32_t program, uint32_t n, const float* in, float* out, uint32_t* faults);
 
 int32_t rxc_set_profiling(rxc_ctx* ctx, int32_t enabled);
 int32_t rxc_get_stats(rxc_ctx* ctx, rxc_stats* out);

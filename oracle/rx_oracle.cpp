@@ -605,10 +605,276 @@ void project2d(Batch2DState& s, const float* matrix /*nullable*/, uint32_t mode)
 // ---------------------------------------------------------------------------------------------
 struct TileRect { size_t x, y, width, height; };  // src/rasterizer.rs:2013-2019
 
-// the subset of rusteria::Execution the no-shader path touches (src/rasterizer.rs:1305-1323)
+// ---------------------------------------------------------------------------------------------
+// rusteria::Execution + Program (rusteria/src/node/execution.rs:8-779, program.rs:7-29).
+// Programs arrive as the op TREE (rusterix_b200/vm.py Program.encode_tree), and execute() recurses over it
+// exactly like the reference; the device runs the same programs lowered to jumps, so the two interpreters
+// share nothing but the opcode numbers of include/rxcuda.h.
+// ---------------------------------------------------------------------------------------------
+struct VmProgram {
+    const uint32_t* t = nullptr;        // the encoded tree
+    uint32_t n_functions() const { return t[0]; }
+    bool has_shade() const { return t && t[1] != 0xFFFFFFFFu; }
+    uint32_t shade_index() const { return t[1]; }
+    uint32_t shade_locals() const { return t[2]; }
+    uint32_t globals() const { return t[3]; }
+    const uint32_t* function(uint32_t i, uint32_t* n) const { const uint32_t* f = t + t[5 + i]; *n = f[0]; return f + 1; }
+};
+struct VmBank {                          // set by rxo_set_programs (test infrastructure, not thread safe)
+    std::vector<std::vector<uint32_t>> trees;
+    std::vector<VmProgram> programs;
+    std::vector<rxc_pattern> patterns, patterns_normal;
+    std::vector<std::vector<float>> pattern_store;
+    std::vector<float> palette;          // n * (present, r, g, b)
+};
+VmBank g_vm;
+// 0 (default) = the reference: one Execution per screen tile, never reset (src/rasterizer.rs:310).
+// 1 = the device's documented deviation: every fragment starts from Execution::new() (rxo_set_vm_state_mode).
+int g_vm_fresh_state = 0;
+
+inline float f32_from_bits(uint32_t b) { float f; std::memcpy(&f, &b, 4); return f; }
+
 struct Execution {
-    V3 color{0, 0, 0}, normal{0, 0, 0}, emissive{0, 0, 0};
-    float roughness = 0, metallic = 0, opacity = 0;
+    std::vector<V3> globals, locals, stack;
+    std::vector<std::vector<V3>> locals_stack;
+    bool has_return = false; V3 return_value{0, 0, 0};
+    V3 uv{0, 0, 0}, color{0, 0, 0}, roughness{0.5f, 0.5f, 0.5f}, metallic{0, 0, 0}, emissive{0, 0, 0}, opacity{0, 0, 0},
+        bump{0, 0, 0}, normal{0, 0, 0}, hitpoint{0, 0, 0}, time{0, 0, 0};
+    bool fault = false;                  // the reference would have panicked (pop of an empty stack, bad index)
+
+    V3 pop() { if (stack.empty()) { fault = true; return {0, 0, 0}; } V3 v = stack.back(); stack.pop_back(); return v; }
+    static V3 map1(V3 a, float (*fn)(float)) { return {fn(a.x), fn(a.y), fn(a.z)}; }
+    static V3 splat(float x) { return {x, x, x}; }
+
+    // TexStorage::sample, rusteria/src/textures/mod.rs:20-24, :131-146
+    static V3 pattern_sample(const rxc_pattern& p, V3 uv) {
+        float u = uv.x - std::floor(uv.x), v = uv.y - std::floor(uv.y);
+        int32_t x = as_i32(std::floor(u * (float)p.width)), y = as_i32(std::floor(v * (float)p.height));
+        auto rem = [](int32_t a, int32_t m) { int32_t r = a % m; return r < 0 ? r + m : r; };
+        x = rem(x, (int32_t)p.width); y = rem(y, (int32_t)p.height);
+        const float* d = p.data + ((size_t)y * p.width + (size_t)x) * 3;
+        return {d[0], d[1], d[2]};
+    }
+
+    void reset(size_t var_size) { if (var_size != globals.size()) globals.resize(var_size, V3{0, 0, 0}); }  // execution.rs:103-107
+
+    // execution.rs:109-746
+    void execute(const uint32_t* code, uint32_t n, const VmProgram& program) {
+        for (uint32_t pc = 0; pc < n;) {
+            if (has_return || fault) break;
+            const uint32_t op = code[pc++];
+            switch (op) {
+                case RXVM_LOAD_GLOBAL: { uint32_t i = code[pc++]; if (i >= globals.size()) { fault = true; break; } stack.push_back(globals[i]); break; }
+                case RXVM_STORE_GLOBAL: { uint32_t i = code[pc++]; if (i >= globals.size()) { fault = true; break; } globals[i] = pop(); break; }
+                case RXVM_LOAD_LOCAL: { uint32_t i = code[pc++]; if (i >= locals.size()) { fault = true; break; } stack.push_back(locals[i]); break; }
+                case RXVM_STORE_LOCAL: { uint32_t i = code[pc++]; if (i >= locals.size()) { fault = true; break; } locals[i] = pop(); break; }
+                case RXVM_SWAP: { V3 b = pop(), a = pop(); stack.push_back(b); stack.push_back(a); break; }
+                case RXVM_GET_COMPONENTS: {
+                    uint32_t len = code[pc++];
+                    V3 v = pop();
+                    float r[8]; uint32_t k = 0;
+                    for (uint32_t i = 0; i < len; ++i) {
+                        uint32_t index = code[pc++];
+                        if (index > 2) continue;
+                        if (k < 8) r[k] = index == 0 ? v.x : index == 1 ? v.y : v.z;
+                        ++k;
+                    }
+                    V3 pushed = k == 1 ? splat(r[0]) : k == 2 ? V3{r[0], r[1], 0.0f} : k == 3 ? V3{r[0], r[1], r[2]} : splat(0.0f);
+                    stack.push_back(pushed);
+                    break;
+                }
+                case RXVM_SET_COMPONENTS: {
+                    uint32_t len = code[pc++];
+                    V3 value = pop(), target = pop();
+                    float comps[3] = {value.x, value.y, value.z};
+                    uint32_t ncomp = (len >= 1 && len <= 3) ? len : 0;
+                    for (uint32_t i = 0; i < len; ++i) {
+                        uint32_t idx = code[pc + i];
+                        if (i >= ncomp) break;
+                        if (idx == 0) target.x = comps[i]; else if (idx == 1) target.y = comps[i]; else if (idx == 2) target.z = comps[i];
+                    }
+                    pc += len;
+                    stack.push_back(target);
+                    break;
+                }
+                case RXVM_PUSH: stack.push_back({f32_from_bits(code[pc]), f32_from_bits(code[pc + 1]), f32_from_bits(code[pc + 2])}); pc += 3; break;
+                case RXVM_CLEAR: if (!stack.empty()) stack.pop_back(); break;
+                case RXVM_FUNCTION_CALL: {  // :186-223
+                    uint32_t arity = code[pc++], total_locals = code[pc++], index = code[pc++];
+                    locals_stack.push_back(locals);
+                    locals.assign(total_locals, V3{0, 0, 0});
+                    for (uint32_t i = arity; i-- > 0;)
+                        if (!stack.empty()) { V3 arg = stack.back(); stack.pop_back(); if (i < locals.size()) locals[i] = arg; else fault = true; }
+                    size_t stack_base = stack.size();
+                    if (index >= program.n_functions()) { fault = true; break; }
+                    uint32_t fn_n; const uint32_t* body = program.function(index, &fn_n);
+                    execute(body, fn_n, program);
+                    V3 ret{0, 0, 0};
+                    if (has_return) { ret = return_value; has_return = false; }
+                    else if (stack.size() > stack_base) { ret = stack.back(); stack.pop_back(); }
+                    if (stack.size() > stack_base) stack.resize(stack_base);
+                    locals = locals_stack.back(); locals_stack.pop_back();
+                    stack.push_back(ret);
+                    break;
+                }
+                case RXVM_RETURN: {  // :224-234
+                    V3 v{0, 0, 0};
+                    if (!stack.empty()) { v = stack.back(); stack.pop_back(); }
+                    return_value = v; has_return = true;
+                    break;
+                }
+                case RXVM_PACK2: { V3 y = pop(), x = pop(); stack.push_back({x.x, y.x, 0.0f}); break; }
+                case RXVM_PACK3: { V3 z = pop(), y = pop(), x = pop(); stack.push_back({x.x, y.x, z.x}); break; }
+                case RXVM_DUP: if (!stack.empty()) stack.push_back(stack.back()); break;
+                case RXVM_FOR: {  // :259-285.  A Return inside the loop leaves the function (the reference pops the
+                                  // condition from an empty or foreign stack after it).
+                    uint32_t n_init = code[pc], n_cond = code[pc + 1], n_incr = code[pc + 2], n_body = code[pc + 3];
+                    const uint32_t *init = code + pc + 4, *cond = init + n_init, *incr = cond + n_cond, *body = incr + n_incr;
+                    pc += 4 + n_init + n_cond + n_incr + n_body;
+                    size_t base = stack.size();
+                    size_t iter = 0;
+                    execute(init, n_init, program);
+                    if (stack.size() > base) stack.resize(base);
+                    for (;;) {
+                        execute(cond, n_cond, program);
+                        if (has_return || fault) break;
+                        V3 z = pop();
+                        if (z.x == 0.0f) break;
+                        if (stack.size() > base) stack.resize(base);
+                        execute(body, n_body, program);
+                        if (stack.size() > base) stack.resize(base);
+                        execute(incr, n_incr, program);
+                        if (stack.size() > base) stack.resize(base);
+                        if (++iter > 10000000) { fault = true; break; }
+                    }
+                    break;
+                }
+                case RXVM_IF: {  // :286-293
+                    uint32_t n_then = code[pc], n_else = code[pc + 1];
+                    const uint32_t* then_code = code + pc + 2;
+                    const uint32_t* else_code = then_code + n_then;
+                    pc += 2 + n_then + (n_else == 0xFFFFFFFFu ? 0 : n_else);
+                    bool value = pop().x != 0.0f;
+                    if (value) execute(then_code, n_then, program);
+                    else if (n_else != 0xFFFFFFFFu) execute(else_code, n_else, program);
+                    break;
+                }
+                case RXVM_ADD: { V3 b = pop(), a = pop(); stack.push_back(a + b); break; }
+                case RXVM_SUB: { V3 b = pop(), a = pop(); stack.push_back(a - b); break; }
+                case RXVM_MUL: { V3 b = pop(), a = pop(); stack.push_back(a * b); break; }
+                case RXVM_DIV: { V3 b = pop(), a = pop(); stack.push_back({a.x / b.x, a.y / b.y, a.z / b.z}); break; }
+                case RXVM_LENGTH: { V3 a = pop(); stack.push_back(splat(magnitude(a))); break; }
+                case RXVM_LENGTH2: { V3 a = pop(); stack.push_back({std::sqrt(a.x * a.x + a.y * a.y), 0.0f, 0.0f}); break; }
+                case RXVM_LENGTH3: { V3 a = pop(); stack.push_back({std::sqrt(a.x * a.x + a.y * a.y + a.z * a.z), 0.0f, 0.0f}); break; }
+                case RXVM_ABS: stack.push_back(map1(pop(), [](float x) { return std::fabs(x); })); break;
+                case RXVM_SIN: stack.push_back(map1(pop(), [](float x) { return std::sin(x); })); break;
+                case RXVM_SIN1: case RXVM_COS1: { V3 a = pop(); stack.push_back({std::sin(a.x), 0.0f, 0.0f}); break; }   // :342-345 (sin!)
+                case RXVM_SIN2: case RXVM_COS2: { V3 a = pop(); stack.push_back({std::sin(a.x), std::sin(a.y), 0.0f}); break; }
+                case RXVM_COS: stack.push_back(map1(pop(), [](float x) { return std::cos(x); })); break;
+                case RXVM_NORMALIZE: { V3 a = pop(); float len = magnitude(a); stack.push_back(len > 0.0f ? a / len : a); break; }
+                case RXVM_TAN: stack.push_back(map1(pop(), [](float x) { return std::tan(x); })); break;
+                case RXVM_ATAN: stack.push_back(map1(pop(), [](float x) { return std::atan(x); })); break;
+                case RXVM_ATAN2: { V3 b = pop(), a = pop(); stack.push_back({std::atan2(a.x, b.x), std::atan2(a.y, b.y), std::atan2(a.z, b.z)}); break; }
+                case RXVM_ROTATE2D: {
+                    V3 angle = pop(), v = pop();
+                    float rad = angle.x * 0.017453292519943295f;   // f32::to_radians
+                    float sn = std::sin(rad), c = std::cos(rad);
+                    stack.push_back({v.x * c - v.y * sn, v.x * sn + v.y * c, v.z});
+                    break;
+                }
+                case RXVM_DOT: { V3 b = pop(), a = pop(); stack.push_back(splat(dot(a, b))); break; }
+                case RXVM_DOT2: { V3 b = pop(), a = pop(); stack.push_back({a.x * b.x + a.y * b.y, 0.0f, 0.0f}); break; }
+                case RXVM_DOT3: { V3 b = pop(), a = pop(); stack.push_back({a.x * b.x + a.y * b.y + a.z * b.z, 0.0f, 0.0f}); break; }
+                case RXVM_CROSS: { V3 b = pop(), a = pop(); stack.push_back({a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}); break; }
+                case RXVM_FLOOR: stack.push_back(map1(pop(), [](float x) { return std::floor(x); })); break;
+                case RXVM_CEIL: stack.push_back(map1(pop(), [](float x) { return std::ceil(x); })); break;
+                case RXVM_ROUND: stack.push_back(map1(pop(), [](float x) { return std::round(x); })); break;
+                case RXVM_FRACT: stack.push_back(map1(pop(), [](float x) { return x - std::floor(x); })); break;
+                case RXVM_MOD: {
+                    V3 b = pop(), a = pop();
+                    stack.push_back({a.x - b.x * std::floor(a.x / b.x), a.y - b.y * std::floor(a.y / b.y), a.z - b.z * std::floor(a.z / b.z)});
+                    break;
+                }
+                case RXVM_RADIANS: stack.push_back(map1(pop(), [](float x) { return x * 0.017453292519943295f; })); break;
+                case RXVM_DEGREES: stack.push_back(map1(pop(), [](float x) { return x * 57.29577951308232f; })); break;
+                case RXVM_MIN: { V3 b = pop(), a = pop(); stack.push_back({rmin(a.x, b.x), rmin(a.y, b.y), rmin(a.z, b.z)}); break; }
+                case RXVM_MAX: { V3 b = pop(), a = pop(); stack.push_back({rmax(a.x, b.x), rmax(a.y, b.y), rmax(a.z, b.z)}); break; }
+                case RXVM_MIX: { V3 c = pop(), b = pop(), a = pop(); stack.push_back(a + (b - a) * c); break; }
+                case RXVM_SMOOTHSTEP: {
+                    V3 c = pop(), b = pop(), a = pop();
+                    float denom = b.x - a.x;
+                    float t = denom != 0.0f ? (c.x - a.x) / denom : 0.0f;
+                    if (t < 0.0f) t = 0.0f; else if (t > 1.0f) t = 1.0f;
+                    stack.push_back(splat(t * t * (3.0f - 2.0f * t)));
+                    break;
+                }
+                case RXVM_STEP: { V3 b = pop(), a = pop(); stack.push_back({b.x >= a.x ? 1.0f : 0.0f, b.y >= a.y ? 1.0f : 0.0f, b.z >= a.z ? 1.0f : 0.0f}); break; }
+                case RXVM_CLAMP: { V3 c = pop(), b = pop(), a = pop(); stack.push_back({rclamp(a.x, b.x, c.x), rclamp(a.y, b.y, c.y), rclamp(a.z, b.z, c.z)}); break; }
+                case RXVM_SQRT: stack.push_back(map1(pop(), [](float x) { return std::sqrt(x); })); break;
+                case RXVM_LOG: stack.push_back(map1(pop(), [](float x) { return std::log(x); })); break;
+                case RXVM_POW: { V3 b = pop(), a = pop(); stack.push_back({std::pow(a.x, b.x), std::pow(a.y, b.y), std::pow(a.z, b.z)}); break; }
+                case RXVM_EQ: { V3 b = pop(), a = pop(); stack.push_back(splat(a.x == b.x ? 1.0f : 0.0f)); break; }
+                case RXVM_NE: { V3 b = pop(), a = pop(); stack.push_back(splat(a.x != b.x ? 1.0f : 0.0f)); break; }
+                case RXVM_LT: { V3 b = pop(), a = pop(); stack.push_back(splat(a.x < b.x ? 1.0f : 0.0f)); break; }
+                case RXVM_LE: { V3 b = pop(), a = pop(); stack.push_back(splat(a.x <= b.x ? 1.0f : 0.0f)); break; }
+                case RXVM_GT: { V3 b = pop(), a = pop(); stack.push_back(splat(a.x > b.x ? 1.0f : 0.0f)); break; }
+                case RXVM_GE: { V3 b = pop(), a = pop(); stack.push_back(splat(a.x >= b.x ? 1.0f : 0.0f)); break; }
+                case RXVM_AND: { V3 b = pop(), a = pop(); stack.push_back(splat(((a.x != 0.0f) & (b.x != 0.0f)) ? 1.0f : 0.0f)); break; }
+                case RXVM_OR: { V3 b = pop(), a = pop(); stack.push_back(splat(((a.x != 0.0f) | (b.x != 0.0f)) ? 1.0f : 0.0f)); break; }
+                case RXVM_NOT: { V3 a = pop(); stack.push_back(splat(a.x == 0.0f ? 1.0f : 0.0f)); break; }
+                case RXVM_NEG: stack.push_back(-pop()); break;
+                case RXVM_PRINT: pop(); break;
+                case RXVM_UV: stack.push_back(uv); break;
+                case RXVM_SET_UV: uv = pop(); break;
+                case RXVM_NORMAL: stack.push_back(normal); break;
+                case RXVM_SET_NORMAL: normal = normalized(pop()); break;
+                case RXVM_HITPOINT: stack.push_back(hitpoint); break;
+                case RXVM_TIME: stack.push_back(time); break;
+                case RXVM_COLOR: stack.push_back(color); break;
+                case RXVM_SET_COLOR: color = pop(); break;
+                case RXVM_ROUGHNESS: stack.push_back(roughness); break;
+                case RXVM_SET_ROUGHNESS: roughness = pop(); break;
+                case RXVM_METALLIC: stack.push_back(metallic); break;
+                case RXVM_SET_METALLIC: metallic = pop(); break;
+                case RXVM_EMISSIVE: stack.push_back(emissive); break;
+                case RXVM_SET_EMISSIVE: emissive = pop(); break;
+                case RXVM_OPACITY: stack.push_back(opacity); break;
+                case RXVM_SET_OPACITY: opacity = pop(); break;
+                case RXVM_BUMP: stack.push_back(bump); break;
+                case RXVM_SET_BUMP: bump = pop(); break;
+                case RXVM_SAMPLE: {  // :625-633
+                    V3 b = pop(), a = pop();
+                    size_t i = as_usize(b.x);
+                    stack.push_back(i < g_vm.patterns.size() ? pattern_sample(g_vm.patterns[i], a) : V3{0, 0, 0});
+                    break;
+                }
+                case RXVM_SAMPLE_NORMAL: {  // :634-649
+                    V3 b = pop(), a = pop();
+                    size_t i = as_usize(b.x);
+                    if (i < g_vm.patterns_normal.size()) { V3 nm = pattern_sample(g_vm.patterns_normal[i], a); stack.push_back(nm * 2.0f - V3{1, 1, 1}); }
+                    else stack.push_back({0, 0, 0});
+                    break;
+                }
+                case RXVM_PALETTE_INDEX: {  // :735-742
+                    V3 a = pop();
+                    size_t i = as_usize(a.x);
+                    if (i < g_vm.palette.size() / 4 && g_vm.palette[i * 4] != 0.0f)
+                        stack.push_back({g_vm.palette[i * 4 + 1], g_vm.palette[i * 4 + 2], g_vm.palette[i * 4 + 3]});
+                    break;
+                }
+                default: fault = true; break;  // Alloc / Iterate / Save: texture baking, not reachable from the rasterizer path
+            }
+        }
+    }
+
+    // execution.rs:771-779
+    void shade(const VmProgram& program) {
+        stack.clear();
+        has_return = false;
+        locals.resize(program.shade_locals(), V3{0, 0, 0});
+        uint32_t n; const uint32_t* body = program.function(program.shade_index(), &n);
+        execute(body, n, program);
+    }
 };
 
 struct Raster {
@@ -734,6 +1000,29 @@ struct Raster {
         return (diffuse + specular) * light_radiance + emissive;
     }
 
+    // `chunk.shaders.get(i)` / `scene.shaders.get(i)` (src/rasterizer.rs:1281-1285): nullptr when nothing runs
+    const VmProgram* program_for(int32_t shader, int32_t chunk) const {
+        if (shader < 0) return nullptr;
+        uint32_t index;
+        if (chunk >= 0) {
+            const rxc_chunk& c = scene->chunks[chunk];
+            if ((uint32_t)shader >= c.n_shaders) return nullptr;
+            index = c.shader_base + (uint32_t)shader;
+        } else {
+            if ((uint32_t)shader >= scene->n_scene_shaders) return nullptr;
+            index = (uint32_t)shader;
+        }
+        if (index >= g_vm.programs.size() || !g_vm.programs[index].has_shade()) return nullptr;
+        return &g_vm.programs[index];
+    }
+    // `chunk.shader_textures.get(i)` (src/rasterizer.rs:1227-1236)
+    const rxc_texture* baked_texture(int32_t shader, int32_t chunk) const {
+        if (shader < 0 || chunk < 0) return nullptr;
+        const rxc_chunk& c = scene->chunks[chunk];
+        if (!c.shader_textures || (uint32_t)shader >= c.n_shaders) return nullptr;
+        return c.shader_textures[shader];
+    }
+
     // Texel fetch shared by d3 and d2.  Returns false when the reference would panic.
     const rxc_texture* tile_frame(uint32_t kind, uint32_t index) const {
         const rxc_tile* t = nullptr;
@@ -831,21 +1120,44 @@ struct Raster {
                     uint8_t texel[4];
                     texel_3d(batch, interpolated_u, interpolated_v, world, texel);  // :1101-1222
 
+                    if (g_vm_fresh_state) execution = Execution();
                     V4 color = pixel_to_vec4(texel);
-                    // no batch shader: :1305-1317
-                    color.x = srgb_to_linear_fast(color.x);
-                    color.y = srgb_to_linear_fast(color.y);
-                    color.z = srgb_to_linear_fast(color.z);
-                    execution.color = {color.x, color.y, color.z};
-                    execution.opacity = (float)texel[3] / 255.0f;
-                    execution.normal = normal;
-                    execution.roughness = 0.5f;
-                    execution.metallic = 0.0f;
+                    const rxc_texture* baked = baked_texture(batch.shader, batch.chunk);
+                    if (batch.shader >= 0 && baked) {  // :1227-1262: a baked shader texture replaces the texel
+                        uint8_t t2[4];
+                        texture_sample(*baked, interpolated_u, interpolated_v, f->sample_mode, batch.repeat_mode, t2);
+                        color = pixel_to_vec4(t2);
+                        color.x = srgb_to_linear_fast(color.x);
+                        color.y = srgb_to_linear_fast(color.y);
+                        color.z = srgb_to_linear_fast(color.z);
+                        execution.color = {color.x, color.y, color.z};
+                        execution.opacity.x = color.w;
+                        execution.roughness.x = 0.5f;
+                        execution.metallic.x = 0.0f;
+                        execution.normal = normal;
+                    } else {  // :1263-1317
+                        color.x = srgb_to_linear_fast(color.x);
+                        color.y = srgb_to_linear_fast(color.y);
+                        color.z = srgb_to_linear_fast(color.z);
+                        execution.color = {color.x, color.y, color.z};
+                        execution.opacity.x = (float)texel[3] / 255.0f;
+                        execution.normal = normal;
+                        execution.roughness.x = 0.5f;
+                        execution.metallic.x = 0.0f;
+                        if (const VmProgram* program = program_for(batch.shader, batch.chunk)) {  // :1281-1300
+                            execution.uv.x = interpolated_u / 4.0f;
+                            execution.uv.y = interpolated_v / 4.0f;
+                            execution.hitpoint = world;
+                            execution.time = {f->time, f->time, f->time};
+                            execution.reset(program->globals());
+                            execution.shade(*program);
+                        }
+                    }
 
                     V3 mat_base = execution.color;  // :1319-1323
                     normal = normalized(execution.normal);
-                    float mat_roughness = rclamp(execution.roughness, 0.0f, 1.0f);
-                    float mat_metallic = rclamp(execution.metallic, 0.0f, 1.0f);
+                    float mat_roughness = rclamp(execution.roughness.x, 0.0f, 1.0f);
+                    float mat_metallic = rclamp(execution.metallic.x, 0.0f, 1.0f);
                     V3 mat_emissive = execution.emissive;
 
                     V3 lit = {0, 0, 0};
@@ -876,7 +1188,7 @@ struct Raster {
                     color.x = linear_to_srgb_fast(lit.x);  // :1400-1404
                     color.y = linear_to_srgb_fast(lit.y);
                     color.z = linear_to_srgb_fast(lit.z);
-                    color.w = execution.opacity;
+                    color.w = execution.opacity.x;
                     vec4_to_pixel(color, texel);
 
                     if (texel[3] == 255) {  // :1408-1412
@@ -937,13 +1249,24 @@ struct Raster {
                     color.x = srgb_to_linear_fast(color.x);
                     color.y = srgb_to_linear_fast(color.y);
                     color.z = srgb_to_linear_fast(color.z);
+                    if (g_vm_fresh_state) execution = Execution();
                     execution.color = {color.x, color.y, color.z};
-                    execution.opacity = (float)texel[3] / 255.0f;
-                    // no batch shader (:1611-1637)
+                    execution.opacity.x = (float)texel[3] / 255.0f;
+                    if (const VmProgram* program = program_for(batch.shader, batch.chunk)) {  // :1611-1637
+                        execution.normal = {0, 0, 0};
+                        execution.uv.x = interpolated_u / 4.0f;
+                        execution.uv.y = interpolated_v / 4.0f;
+                        execution.hitpoint = world;
+                        execution.time = {f->time, f->time, f->time};
+                        execution.roughness.x = 0.5f;
+                        execution.metallic.x = 0.0f;
+                        execution.reset(program->globals());
+                        execution.shade(*program);
+                    }
                     color.x = linear_to_srgb_fast(execution.color.x);  // :1639-1643
                     color.y = linear_to_srgb_fast(execution.color.y);
                     color.z = linear_to_srgb_fast(execution.color.z);
-                    color.w = execution.opacity;
+                    color.w = execution.opacity.x;
                     vec4_to_pixel(color, texel);
                     std::memcpy(&buffer[zidx * 4], texel, 4);  // :1647-1651
                     z_buffer[zidx] = z;
@@ -975,7 +1298,7 @@ struct Raster {
     }
 
     // src/rasterizer.rs:584-959
-    void d2_rasterize(std::vector<uint8_t>& buffer, const TileRect& tile, const Batch2DState& s) const {
+    void d2_rasterize(std::vector<uint8_t>& buffer, const TileRect& tile, const Batch2DState& s, Execution& execution) const {
         const rxc_batch2d& batch = *s.b;
         if (!s.bounding_box) return;
         const Rect& bbox = *s.bounding_box;
@@ -1055,6 +1378,23 @@ struct Raster {
                             if (batch.chunk >= 0) sample_terrain_texture(batch.chunk, world, texel);
                             break;
                         default: break;
+                    }
+
+                    if (const VmProgram* program = program_for(batch.shader, batch.chunk)) {  // :760-797
+                        if (g_vm_fresh_state) execution = Execution();
+                        V4 color = pixel_to_vec4(texel);
+                        execution.uv.x = u / 4.0f;
+                        execution.uv.y = v / 4.0f;
+                        execution.color = {color.x, color.y, color.z};
+                        execution.hitpoint.x = world.x;
+                        execution.hitpoint.y = world.y;
+                        execution.time = {f->time, f->time, f->time};
+                        execution.roughness.x = 0.5f;
+                        execution.metallic.x = 0.0f;
+                        execution.reset(program->globals());
+                        execution.shade(*program);
+                        color = {execution.color.x, execution.color.y, execution.color.z, 1.0f};
+                        vec4_to_pixel(color, texel);
                     }
 
                     if ((batch.receives_light && scene->n_lights != 0) || f->has_ambient) {  // :799-873
@@ -1154,7 +1494,7 @@ struct Raster {
             }
         }
         if (f->d2_active)
-            for (const Batch2DState& s : *b2) d2_rasterize(buffer, tile, s);  // :501-553
+            for (const Batch2DState& s : *b2) d2_rasterize(buffer, tile, s, execution);  // :501-553
     }
 };
 
@@ -1173,7 +1513,6 @@ int32_t validate(const rxc_tile* tiles, uint32_t n_tiles, const rxc_scene* scene
     (void)tiles;
     for (uint32_t i = 0; i < scene->n_batches3d; ++i) {
         const rxc_batch3d& b = scene->batches3d[i];
-        if (b.shader >= 0) return RXC_ERR_UNSUPPORTED;
         if (b.source_kind > RXC_SRC_TERRAIN) return RXC_ERR_INVALID;
         if (b.chunk >= (int32_t)scene->n_chunks) return RXC_ERR_INDEX;
         if (b.source_kind == RXC_SRC_TERRAIN && b.chunk >= 0 && scene->chunks[b.chunk].terrain_texture && scene->chunks[b.chunk].size == 0)
@@ -1188,7 +1527,6 @@ int32_t validate(const rxc_tile* tiles, uint32_t n_tiles, const rxc_scene* scene
     }
     for (uint32_t i = 0; i < scene->n_batches2d; ++i) {
         const rxc_batch2d& b = scene->batches2d[i];
-        if (b.shader >= 0) return RXC_ERR_UNSUPPORTED;
         if (b.source_kind > RXC_SRC_TERRAIN) return RXC_ERR_INVALID;
         if (b.chunk >= (int32_t)scene->n_chunks) return RXC_ERR_INDEX;
         if (b.source_kind == RXC_SRC_TERRAIN && b.chunk >= 0 && scene->chunks[b.chunk].terrain_texture && scene->chunks[b.chunk].size == 0)
@@ -1283,6 +1621,55 @@ int32_t rxo_rasterize(const rxc_tile* tiles, uint32_t n_tiles, const rxc_scene* 
         }
     }
     return RXC_OK;
+}
+
+// The programs, pattern banks and palette the next rxo_rasterize / rxo_vm_execute calls use.  trees[i] is
+// Program.encode_tree() of program i (scene.shaders, then every chunk's, like rxc_scene.shaders).
+int32_t rxo_set_programs(const uint32_t* const* trees, const uint32_t* n_words, uint32_t n_programs, const rxc_pattern* patterns,
+                         uint32_t n_patterns, const rxc_pattern* patterns_normal, uint32_t n_patterns_normal, const float* palette,
+                         uint32_t n_palette) {
+    g_vm = VmBank{};
+    g_vm.trees.resize(n_programs);
+    g_vm.programs.resize(n_programs);
+    for (uint32_t i = 0; i < n_programs; ++i) {
+        g_vm.trees[i].assign(trees[i], trees[i] + n_words[i]);
+        g_vm.programs[i].t = g_vm.trees[i].data();
+    }
+    auto copy_bank = [&](const rxc_pattern* src, uint32_t n, std::vector<rxc_pattern>& dst) {
+        for (uint32_t i = 0; i < n; ++i) {
+            g_vm.pattern_store.emplace_back(src[i].data, src[i].data + (size_t)src[i].width * src[i].height * 3);
+            dst.push_back(rxc_pattern{nullptr, src[i].width, src[i].height});
+        }
+    };
+    copy_bank(patterns, n_patterns, g_vm.patterns);
+    copy_bank(patterns_normal, n_patterns_normal, g_vm.patterns_normal);
+    size_t k = 0;
+    for (auto& p : g_vm.patterns) p.data = g_vm.pattern_store[k++].data();
+    for (auto& p : g_vm.patterns_normal) p.data = g_vm.pattern_store[k++].data();
+    if (n_palette) g_vm.palette.assign(palette, palette + (size_t)n_palette * 4);
+    return RXC_OK;
+}
+
+void rxo_set_vm_state_mode(int32_t per_fragment) { g_vm_fresh_state = per_fragment ? 1 : 0; }
+
+// Execution::shade of program `program` on n records, same record layout as rxc_vm_execute (18 floats in,
+// 24 floats out); every record starts from Execution::new.  Returns the number of records that faulted.
+uint32_t rxo_vm_execute(uint32_t program, uint32_t n, const float* in, float* out) {
+    if (program >= g_vm.programs.size()) return n;
+    const VmProgram& P = g_vm.programs[program];
+    uint32_t faults = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const float* r = in + (size_t)i * 18;
+        Execution e;
+        e.uv = {r[0], r[1], r[2]}; e.color = {r[3], r[4], r[5]}; e.normal = {r[6], r[7], r[8]};
+        e.hitpoint = {r[9], r[10], r[11]}; e.time = {r[12], r[13], r[14]}; e.opacity = {r[15], r[16], r[17]};
+        if (P.has_shade()) { e.reset(P.globals()); e.shade(P); }
+        if (e.fault) ++faults;
+        const V3 v[8] = {e.uv, e.color, e.normal, e.roughness, e.metallic, e.emissive, e.opacity, e.bump};
+        float* o = out + (size_t)i * 24;
+        for (int k = 0; k < 8; ++k) { o[3 * k] = v[k].x; o[3 * k + 1] = v[k].y; o[3 * k + 2] = v[k].z; }
+    }
+    return faults;
 }
 
 // Stage output of Batch3D::clip_and_project for one batch (setup-kernel parity tests).

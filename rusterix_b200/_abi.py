@@ -2,7 +2,7 @@
 tests/test_abi.py checks sizes/offsets against a C probe compiled from the header."""
 import ctypes as C
 
-RXC_ABI_VERSION = 2
+RXC_ABI_VERSION = 3
 
 RXC_OK = 0
 RXC_ERR_INVALID = -1
@@ -96,6 +96,21 @@ class rxc_sector(C.Structure):
     _fields_ = [("min", C.c_float * 2), ("max", C.c_float * 2), ("occlusion", C.c_float)]
 
 
+class rxc_program(C.Structure):
+    _fields_ = [
+        ("code", C.c_void_p),
+        ("n_words", C.c_uint32),
+        ("entry", C.c_uint32),
+        ("shade_locals", C.c_uint32),
+        ("n_globals", C.c_uint32),
+        ("sets_opacity", C.c_uint32),
+    ]
+
+
+class rxc_pattern(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32)]
+
+
 class rxc_chunk(C.Structure):
     _fields_ = [
         ("origin", C.c_int32 * 2),
@@ -103,6 +118,9 @@ class rxc_chunk(C.Structure):
         ("occluded_sectors", C.POINTER(rxc_sector)),
         ("n_occluded_sectors", C.c_uint32),
         ("terrain_texture", C.POINTER(rxc_texture)),
+        ("shader_base", C.c_uint32),
+        ("n_shaders", C.c_uint32),
+        ("shader_textures", C.POINTER(C.POINTER(rxc_texture))),
     ]
 
 
@@ -133,6 +151,15 @@ class rxc_scene(C.Structure):
         ("n_chunks", C.c_uint32),
         ("actor_tiles", C.POINTER(rxc_tile)),
         ("n_actor_tiles", C.c_uint32),
+        ("shaders", C.POINTER(rxc_program)),
+        ("n_shaders", C.c_uint32),
+        ("n_scene_shaders", C.c_uint32),
+        ("patterns", C.POINTER(rxc_pattern)),
+        ("n_patterns", C.c_uint32),
+        ("patterns_normal", C.POINTER(rxc_pattern)),
+        ("n_patterns_normal", C.c_uint32),
+        ("palette", C.c_void_p),
+        ("n_palette", C.c_uint32),
     ]
 
 
@@ -202,6 +229,7 @@ EXPORTS = [
     ("rxc_synchronize", C.c_int32, [C.c_void_p]),
     ("rxc_owner_base", C.c_int32, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]),
     ("rxc_selftest_div", C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
+    ("rxc_vm_execute", C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]),
     ("rxc_set_profiling", C.c_int32, [C.c_void_p, C.c_int32]),
     ("rxc_get_stats", C.c_int32, [C.c_void_p, C.POINTER(rxc_stats)]),
     ("rxc_reset_stats", C.c_int32, [C.c_void_p]),

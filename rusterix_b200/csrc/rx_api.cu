@@ -53,6 +53,7 @@ struct rxc_ctx {
     std::vector<DSector> h_mm_sectors;     // mapmini.occluded_sectors
     std::vector<float> h_linedefs;         // 4 floats per mapmini linedef
     DevBuf d_sectors, d_chunkinfo, d_linedefs;
+    DevBuf d_vm_code, d_vm_programs, d_vm_patdata, d_vm_patterns, d_vm_palette;   // Rusteria VM residency
 
     // scene
     std::vector<DBatch3> h_b3;
@@ -381,6 +382,7 @@ int32_t fill_frame(rxc_ctx* ctx, const rxc_frame& f, DFrame* d) {
     d->trans2d[0] = 0.0f; d->trans2d[1] = 0.0f; d->scale2d = 1.0f;  // rasterizer.rs:104-110
     if (f.has_matrix2d) { d->trans2d[0] = f.matrix2d[6]; d->trans2d[1] = f.matrix2d[7]; d->scale2d = f.matrix2d[0]; }
     d->animation_frame = f.animation_frame;
+    d->time = f.time;
     {   // screen_to_world (rasterizer.rs:1707-1727) as one projective map of (px+.5, py+.5, z, 1), in double
         double IP[4][4], IV[4][4], G[4][4], N[4][4] = {{2.0 / f.width, 0, 0, -1.0}, {0, -2.0 / f.height, 0, 1.0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
         for (int r = 0; r < 4; ++r)
@@ -400,6 +402,80 @@ int32_t fill_frame(rxc_ctx* ctx, const rxc_frame& f, DFrame* d) {
             }
     }
     return RXC_OK;
+}
+
+// Static checks of one flat program (include/rxcuda.h): every word decodes, operands and jump targets stay inside.
+int32_t validate_program(rxc_ctx* ctx, const rxc_program& p, const std::string& who) {
+    if (p.n_words == 0) return RXC_OK;
+    if (!p.code) return fail(ctx, RXC_ERR_INVALID, who + "null code");
+    if (p.entry >= p.n_words) return fail(ctx, RXC_ERR_INVALID, who + "entry outside the code");
+    if (p.shade_locals > 32 || p.n_globals > 16) return fail(ctx, RXC_ERR_UNSUPPORTED, who + "more than 32 locals or 16 globals");
+    if (p.n_words >= (1u << 24)) return fail(ctx, RXC_ERR_UNSUPPORTED, who + "program too long");
+    for (uint32_t pc = 0; pc < p.n_words;) {
+        const uint32_t w = p.code[pc++], op = w & 0xFFu, a = w >> 8;
+        if (op >= RXVM_N_OPS || op == RXVM_IF || op == RXVM_FOR) return fail(ctx, RXC_ERR_INVALID, who + "bad opcode (If/For must be lowered to jumps)");
+        if (op == RXVM_ALLOC || op == RXVM_ITERATE || op == RXVM_SAVE) return fail(ctx, RXC_ERR_UNSUPPORTED, who + "texture baking ops (Alloc/Iterate/Save) in a shade program");
+        if (op == RXVM_PUSH) { if (pc + 3 > p.n_words) return fail(ctx, RXC_ERR_INVALID, who + "truncated Push"); pc += 3; }
+        else if (op == RXVM_FUNCTION_CALL) {
+            if (pc >= p.n_words || p.code[pc] >= p.n_words) return fail(ctx, RXC_ERR_INVALID, who + "bad call target");
+            if ((a >> 8) > 32) return fail(ctx, RXC_ERR_UNSUPPORTED, who + "more than 32 locals in a call");
+            ++pc;
+        } else if ((op == RXVM_JZ || op == RXVM_JMP) && a > p.n_words) return fail(ctx, RXC_ERR_INVALID, who + "jump outside the code");
+        else if ((op == RXVM_LOAD_GLOBAL || op == RXVM_STORE_GLOBAL) && a >= p.n_globals) return fail(ctx, RXC_ERR_INDEX, who + "global index out of range (reference panics)");
+    }
+    if ((p.code[p.n_words - 1] & 0xFFu) != RXVM_END) return fail(ctx, RXC_ERR_INVALID, who + "code must end with End");
+    return RXC_OK;
+}
+
+int32_t upload_vm(rxc_ctx* ctx, const rxc_scene* sc) {
+    std::vector<uint32_t> code;
+    std::vector<DProgram> progs(sc->n_shaders);
+    int32_t st;
+    for (uint32_t i = 0; i < sc->n_shaders; ++i) {
+        const rxc_program& p = sc->shaders[i];
+        if ((st = validate_program(ctx, p, "shader " + std::to_string(i) + ": ")) != RXC_OK) return st;
+        DProgram d = {};
+        d.code_off = (uint32_t)code.size(); d.n_words = p.n_words; d.entry = p.entry; d.shade_locals = p.shade_locals;
+        d.n_globals = p.n_globals; d.sets_opacity = p.sets_opacity ? 1u : 0u;
+        code.insert(code.end(), p.code, p.code + p.n_words);
+        progs[i] = d;
+    }
+    std::vector<float> patdata;
+    std::vector<DPattern> pats;
+    auto add_patterns = [&](const rxc_pattern* list, uint32_t n) -> int32_t {
+        for (uint32_t i = 0; i < n; ++i) {
+            const rxc_pattern& q = list[i];
+            if (!q.data || q.width == 0 || q.height == 0 || q.width > 32768 || q.height > 32768) return fail(ctx, RXC_ERR_INVALID, "bad pattern texture");
+            DPattern d = {(uint32_t)(patdata.size() / 3), q.width, q.height, 0};
+            patdata.insert(patdata.end(), q.data, q.data + (size_t)q.width * q.height * 3);
+            pats.push_back(d);
+        }
+        return RXC_OK;
+    };
+    if ((st = add_patterns(sc->patterns, sc->n_patterns)) != RXC_OK) return st;
+    if ((st = add_patterns(sc->patterns_normal, sc->n_patterns_normal)) != RXC_OK) return st;
+    if ((st = upload(ctx, ctx->d_vm_code, code.data(), code.size() * 4)) != RXC_OK) return st;
+    if ((st = upload(ctx, ctx->d_vm_programs, progs.data(), progs.size() * sizeof(DProgram))) != RXC_OK) return st;
+    if ((st = upload(ctx, ctx->d_vm_patdata, patdata.data(), patdata.size() * 4)) != RXC_OK) return st;
+    if ((st = upload(ctx, ctx->d_vm_patterns, pats.data(), pats.size() * sizeof(DPattern))) != RXC_OK) return st;
+    if ((st = upload(ctx, ctx->d_vm_palette, sc->palette, (size_t)sc->n_palette * 16)) != RXC_OK) return st;
+    VmDev& vm = ctx->S.vm;
+    vm.code = ctx->d_vm_code.as<uint32_t>(); vm.programs = ctx->d_vm_programs.as<DProgram>();
+    vm.pattern_data = ctx->d_vm_patdata.as<float>(); vm.patterns = ctx->d_vm_patterns.as<DPattern>();
+    vm.palette = ctx->d_vm_palette.as<float4>();
+    vm.n_programs = sc->n_shaders; vm.n_patterns = sc->n_patterns; vm.n_patterns_normal = sc->n_patterns_normal; vm.n_palette = sc->n_palette;
+    return RXC_OK;
+}
+
+// batch.shader -> absolute program index (scene.shaders for batches without a chunk, else the chunk's range;
+// rasterizer.rs:1281-1285), -1 when nothing runs
+int32_t resolve_program(const rxc_scene* sc, int32_t shader, int32_t chunk) {
+    if (shader < 0) return -1;
+    if (chunk >= 0) {
+        const rxc_chunk& c = sc->chunks[chunk];
+        return (uint32_t)shader < c.n_shaders ? (int32_t)(c.shader_base + (uint32_t)shader) : -1;
+    }
+    return (uint32_t)shader < sc->n_scene_shaders ? shader : -1;
 }
 
 int32_t validate_sources(rxc_ctx* ctx) {
@@ -497,6 +573,7 @@ int32_t check_group(rxc_ctx* ctx, const DCounters* h_counters, uint32_t n, bool*
         *retry = true;
     }
     if (ov & 6u) return fail(ctx, RXC_ERR_OOM, "internal list overflow (large/clip); this is a bug");
+    if (ov & 16u) return fail(ctx, RXC_ERR_UNSUPPORTED, "a batch shader exceeded a device VM limit (stack 32, call depth 8, 2^20 ops) or popped an empty stack");
     return RXC_OK;
 }
 
@@ -676,7 +753,8 @@ void rxc_destroy(rxc_ctx* ctx) {
                       &ctx->w_frames, &ctx->w_fb, &ctx->w_fb2, &ctx->w_lights, &ctx->w_counters, &ctx->w_vis, &ctx->w_shade,
                       &ctx->w_bins, &ctx->w_ctot, &ctx->w_cbase, &ctx->w_clip, &ctx->w_large, &ctx->w_tcount, &ctx->w_tbase,
                       &ctx->w_tfill, &ctx->w_lists, &ctx->w_tri2d, &ctx->w_rcounter, &ctx->d_out_px, &ctx->d_out_owner, &ctx->d_out_depth,
-                      &ctx->w_tcount2, &ctx->w_tbase2, &ctx->w_tfill2, &ctx->w_lists2, &ctx->d_sectors, &ctx->d_chunkinfo, &ctx->d_linedefs};
+                      &ctx->w_tcount2, &ctx->w_tbase2, &ctx->w_tfill2, &ctx->w_lists2, &ctx->d_sectors, &ctx->d_chunkinfo, &ctx->d_linedefs,
+                      &ctx->d_vm_code, &ctx->d_vm_programs, &ctx->d_vm_patdata, &ctx->d_vm_patterns, &ctx->d_vm_palette};
     for (DevBuf* b : bufs) free_buf(*b);
     if (ctx->h_frames) cudaFreeHost(ctx->h_frames);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -742,17 +820,22 @@ int32_t rxc_set_mapmini(rxc_ctx* ctx, const rxc_mapmini* mm) {
 int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
     if (!ctx || !sc) return RXC_ERR_INVALID;
     if ((sc->n_batches3d && !sc->batches3d) || (sc->n_batches2d && !sc->batches2d) || (sc->n_lights && !sc->lights) ||
-        (sc->n_dynamic_textures && !sc->dynamic_textures) || (sc->n_chunks && !sc->chunks) || (sc->n_actor_tiles && !sc->actor_tiles))
+        (sc->n_dynamic_textures && !sc->dynamic_textures) || (sc->n_chunks && !sc->chunks) || (sc->n_actor_tiles && !sc->actor_tiles) ||
+        (sc->n_shaders && !sc->shaders) || (sc->n_patterns && !sc->patterns) || (sc->n_patterns_normal && !sc->patterns_normal) ||
+        (sc->n_palette && !sc->palette) || sc->n_scene_shaders > sc->n_shaders)
         return fail(ctx, RXC_ERR_INVALID, "null array with non-zero count in rxc_scene");
     CK(cudaSetDevice(ctx->device));
     ctx->have_scene = false;
+    for (uint32_t i = 0; i < sc->n_chunks; ++i)
+        if ((uint64_t)sc->chunks[i].shader_base + sc->chunks[i].n_shaders > sc->n_shaders)
+            return fail(ctx, RXC_ERR_INDEX, "chunk " + std::to_string(i) + ": shader range outside rxc_scene.shaders");
+    bool any_shader = false;
 
     // ---- validate + size
     size_t V = 0, T = 0, V2 = 0, T2 = 0;
     for (uint32_t i = 0; i < sc->n_batches3d; ++i) {
         const rxc_batch3d& b = sc->batches3d[i];
         const std::string who = "3D batch " + std::to_string(i) + ": ";
-        if (b.shader >= 0) return fail(ctx, RXC_ERR_UNSUPPORTED, who + "batch shaders (Rusteria VM) are not on the device path");
         if (b.source_kind > RXC_SRC_TERRAIN) return fail(ctx, RXC_ERR_INVALID, who + "bad source kind");
         if (b.pass > RXC_PASS_CHUNK_OPACITY) return fail(ctx, RXC_ERR_INVALID, who + "bad pass");
         if (b.chunk >= (int32_t)sc->n_chunks) return fail(ctx, RXC_ERR_INDEX, who + "chunk index out of range");
@@ -768,7 +851,6 @@ int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
     for (uint32_t i = 0; i < sc->n_batches2d; ++i) {
         const rxc_batch2d& b = sc->batches2d[i];
         const std::string who = "2D batch " + std::to_string(i) + ": ";
-        if (b.shader >= 0) return fail(ctx, RXC_ERR_UNSUPPORTED, who + "batch shaders (Rusteria VM) are not on the device path");
         if (b.source_kind > RXC_SRC_TERRAIN) return fail(ctx, RXC_ERR_INVALID, who + "bad source kind");
         if (b.mode > RXC_MODE_LINE_LOOP) return fail(ctx, RXC_ERR_INVALID, who + "bad primitive mode");
         if (b.chunk >= (int32_t)sc->n_chunks) return fail(ctx, RXC_ERR_INDEX, who + "chunk index out of range");
@@ -794,6 +876,7 @@ int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
     ctx->owner_base.assign(sc->n_batches3d, 0);
     size_t vo = 0, to = 0;
     bool any_opacity = false;
+    std::vector<std::pair<uint32_t, const rxc_texture*>> baked;   // (3D batch, baked shader texture)
     for (uint32_t i = 0; i < sc->n_batches3d; ++i) {
         const rxc_batch3d& b = sc->batches3d[i];
         DBatch3& d = ctx->h_b3[i];
@@ -804,6 +887,16 @@ int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
         memcpy(&d.source_pixel, b.source_pixel, 4);
         d.has_normals = b.normals ? 1u : 0u;
         d.chunk = b.chunk < 0 ? -1 : b.chunk;
+        d.program = resolve_program(sc, b.shader, b.chunk);
+        if (b.shader >= 0 && b.chunk >= 0 && b.pass != RXC_PASS_CHUNK_OPACITY) {
+            // chunk.shader_textures[shader]: a baked texture replaces the texel and the program does not run (rasterizer.rs:1227-1262)
+            const rxc_chunk& c = sc->chunks[b.chunk];
+            if (c.shader_textures && (uint32_t)b.shader < c.n_shaders && c.shader_textures[b.shader]) {
+                baked.push_back({i, c.shader_textures[b.shader]});
+                d.program = -1;
+            }
+        }
+        if (d.program >= 0 && sc->shaders[d.program].n_words) any_shader = true;
         d.profile_id = b.profile_id;
         d.bflags = (b.has_profile_id ? RX_BF_HAS_PROFILE : 0u) | (b.pass == RXC_PASS_CHUNK_OPACITY ? RX_BF_OPACITY : 0u);
         if (b.pass == RXC_PASS_CHUNK_OPACITY) any_opacity = true;
@@ -847,6 +940,8 @@ int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
         memcpy(&d.source_pixel, b.source_pixel, 4);
         d.receives_light = b.receives_light ? 1u : 0u;
         d.chunk = b.chunk < 0 ? -1 : b.chunk;
+        d.program = resolve_program(sc, b.shader, b.chunk);
+        if (d.program >= 0 && sc->shaders[d.program].n_words) any_shader = true;
         // records per frame (rasterizer.rs:604, :901-955): triangles, index pairs, or consecutive vertices
         d.n_recs = b.mode == RXC_MODE_LINE_STRIP ? b.n_vertices - 1 : b.mode == RXC_MODE_LINE_LOOP ? b.n_vertices : b.n_triangles;
         d.rec_off = (uint32_t)ro2;
@@ -860,8 +955,13 @@ int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
     {   // scene textures: dynamic tiles, host-resolved entity/item tiles, then the chunks' terrain textures
         std::vector<rxc_tile> all(sc->dynamic_textures, sc->dynamic_textures + sc->n_dynamic_textures);
         all.insert(all.end(), sc->actor_tiles, sc->actor_tiles + sc->n_actor_tiles);
+        for (size_t k = 0; k < baked.size(); ++k) {  // baked shader textures ride along as one-frame actor tiles
+            all.push_back(rxc_tile{baked[k].second, 1u});
+            DBatch3& d = ctx->h_b3[baked[k].first];
+            d.source_kind = RXC_SRC_ENTITY_TILE; d.source_index = sc->n_actor_tiles + (uint32_t)k;
+        }
         if ((st = build_tiles(ctx, all.data(), (uint32_t)all.size(), ctx->h_dyn_arena, ctx->h_dyn_tex, ctx->h_dyn_tiles)) != RXC_OK) return st;
-        ctx->n_dyn_tiles = sc->n_dynamic_textures; ctx->n_actor_tiles = sc->n_actor_tiles;
+        ctx->n_dyn_tiles = sc->n_dynamic_textures; ctx->n_actor_tiles = sc->n_actor_tiles + (uint32_t)baked.size();
         ctx->h_chunks.clear(); ctx->h_sectors.clear();
         for (uint32_t i = 0; i < sc->n_chunks; ++i) {
             const rxc_chunk& c = sc->chunks[i];
@@ -905,6 +1005,7 @@ int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
     if ((st = upload(ctx, ctx->d_idx2, idx2.data(), idx2.size() * 4)) != RXC_OK) return st;
     if ((st = upload(ctx, ctx->d_b2, ctx->h_b2.data(), ctx->h_b2.size() * sizeof(DBatch2))) != RXC_OK) return st;
     if ((st = upload_lights(ctx, sc->lights, sc->n_lights)) != RXC_OK) return st;
+    if ((st = upload_vm(ctx, sc)) != RXC_OK) return st;
 
     SceneDev& S = ctx->S;
     S.pos = ctx->d_pos.as<float4>(); S.uv = ctx->d_uv.as<float2>(); S.nrm = ctx->d_nrm.as<float>(); S.idx = ctx->d_idx.as<uint32_t>();
@@ -913,7 +1014,8 @@ int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
     S.n_b3 = sc->n_batches3d; S.n_b2 = sc->n_batches2d; S.n_chunks = (uint32_t)chunks.size();
     S.n_tris = (uint32_t)T; S.n_verts = (uint32_t)V; S.n_rec2d = (uint32_t)ro2;
     // ordered 3D lists when the opacity layer is in play, binned 2D lists when a warp ballot cannot hold the records
-    S.general = (any_opacity || ro2 > 32) ? 1u : 0u;
+    // ... and whenever a batch carries a VM program (the interpreter is only compiled into the general kernels)
+    S.general = (any_opacity || ro2 > 32 || any_shader) ? 1u : 0u;
     ctx->ws_frames = 0;  // workspace strides depend on the scene
     ctx->list_cap_min = 0;
     ctx->list2_cap_min = 0;
@@ -971,6 +1073,29 @@ int32_t rxc_selftest_div(rxc_ctx* ctx, uint64_t seed, uint64_t n_pairs, uint64_t
     if (e != cudaSuccess) { ctx->err = std::string("rxc_selftest_div: ") + cudaGetErrorString(e); return RXC_ERR_CUDA; }
     *mismatches = h[0];
     if (bad_pair) { bad_pair[0] = (uint32_t)(h[1] >> 32); bad_pair[1] = (uint32_t)h[1]; }
+    return RXC_OK;
+}
+
+int32_t rxc_vm_execute(rxc_ctx* ctx, uint32_t program, uint32_t n, const float* in, float* out, uint32_t* faults) {
+    if (!ctx || !in || !out) return RXC_ERR_INVALID;
+    if (!ctx->have_scene || program >= ctx->S.vm.n_programs) return fail(ctx, RXC_ERR_INDEX, "rxc_vm_execute: no such program in the current scene");
+    if (n == 0) return RXC_OK;
+    CK(cudaSetDevice(ctx->device));
+    float *d_in = nullptr, *d_out = nullptr;
+    uint32_t* d_f = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d_in, (size_t)n * 18 * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_out, (size_t)n * 24 * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_f, 4);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, in, (size_t)n * 18 * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_f, 0, 4, ctx->stream);
+    if (e == cudaSuccess) { ctx->stats.kernel_launches++; e = rxk_vm_execute(ctx->S, program, n, d_in, d_out, d_f, ctx->stream); }
+    uint32_t h_f = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)n * 24 * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_f, d_f, 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_f);
+    if (e != cudaSuccess) { ctx->err = std::string("rxc_vm_execute: ") + cudaGetErrorString(e); return RXC_ERR_CUDA; }
+    if (faults) *faults = h_f;
     return RXC_OK;
 }
 

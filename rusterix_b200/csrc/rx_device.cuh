@@ -44,7 +44,7 @@ struct DBatch3 {         // static per 3D batch (uploaded by rxc_set_scene)
     uint32_t orphan_off, n_orphans; // vertices no triangle references (they still count for the bbox)
     int32_t chunk;               // index of the batch's chunk, -1 = none
     float ambient[3];
-    float pad1;
+    int32_t program;             // absolute index into VmDev::programs of batch.shader, -1 = none
     float transform[16];
     float aabb_min[3], aabb_max[3]; // object-space AABB, NaN-ignoring min/max (batch3d.rs:494-507)
     uint32_t profile_id;         // batch.profile_id when RX_BF_HAS_PROFILE
@@ -63,7 +63,8 @@ struct DBatch2 {         // static per 2D batch
     uint32_t rec_off;            // first record of this batch in the per-frame 2D record array
     int32_t chunk;               // index of the batch's chunk, -1 = none
     uint32_t n_recs;             // records per frame: triangles, or line segments (by mode)
-    uint32_t pad[3];
+    int32_t program;             // absolute index into VmDev::programs of batch.shader, -1 = none
+    uint32_t pad[2];
 };
 
 struct DSector {         // one (BBox, occlusion) entry (chunk.rs:41, mini.rs:33)
@@ -88,6 +89,25 @@ struct DLight {          // rxc_light + the per-frame flicker factor (light.rs:6
     float nx, ny, nz, inv_range;  // inv_range = 1/(start - end), filled per frame (smoothstep / linear falloff)
 };
 
+// Rusteria VM residency (rxc_program / rxc_pattern of include/rxcuda.h)
+struct DProgram {
+    uint32_t code_off, n_words;  // words of this program inside VmDev::code
+    uint32_t entry, shade_locals, n_globals, sets_opacity;
+    uint32_t pad[2];
+};
+struct DPattern {
+    uint32_t off;                // first Value (3 floats) inside VmDev::pattern_data
+    uint32_t width, height, pad;
+};
+struct VmDev {
+    const uint32_t* code;
+    const DProgram* programs;
+    const float* pattern_data;
+    const DPattern* patterns;    // patterns, then normal patterns
+    const float4* palette;       // (present, r, g, b)
+    uint32_t n_programs, n_patterns, n_patterns_normal, n_palette;
+};
+
 struct DChunk {          // work item of the setup kernel: <= RX_CHUNK_TRIS triangles of one batch
     uint32_t batch, first_tri, n_tris, pad;
 };
@@ -109,7 +129,8 @@ struct __align__(16) DFrameBatch {
     float sd_ambient[3];                         // batch.ambient_color
     int32_t sd_chunk;                            // chunk index (occlusion, terrain), -1 = none
     uint32_t sd_profile;                         // profile id (valid with RX_SD_HAS_PROFILE)
-    uint32_t sd_pad[3];
+    int32_t sd_program;                          // VM program of the batch (RX_SD_SHADER)
+    uint32_t sd_pad[2];
 };
 #define RX_SD_TEXTURED 1u
 #define RX_SD_REPEAT_X 2u
@@ -118,12 +139,14 @@ struct __align__(16) DFrameBatch {
 #define RX_SD_TERRAIN 16u      // texel = chunk.sample_terrain_texture(world.xz)
 #define RX_SD_HAS_PROFILE 32u
 #define RX_SD_OPACITY 64u
+#define RX_SD_SHADER 128u      // a Rusteria VM program shades the fragment (rasterizer.rs:1226-1293)
+#define RX_SD_VM_OPACITY 256u  // ... and it writes opacity: the alpha test runs the program
 
 struct DFrameBatch2 {
     uint32_t tex;          // DTex index or 0xFFFFFFFF (transparent texel)
     uint32_t lit;          // lighting branch taken (rasterizer.rs:799-802)
     uint32_t terrain;      // source is PixelSource::Terrain: `tex` is the chunk's terrain texture
-    uint32_t pad;
+    int32_t program;       // VM program of the batch, -1 = none
 };
 
 // Visibility record: everything the per-pixel coverage/depth test reads (96 B, 16 B aligned)
@@ -198,6 +221,8 @@ struct DFrame {
     // screen_to_world (rasterizer.rs:1707-1727) folded by the host in double precision:
     // (hx,hy,hz,hw) = s2w * (px+.5, py+.5, z, 1), world = (hx,hy,hz)/hw.  Row-major 4x4.
     float s2w[16];
+    float time;                   // Rasterizer.time (VM `time`)
+    uint32_t pad_t[3];
 };
 
 // per-frame counters (zeroed by k_frame_setup)

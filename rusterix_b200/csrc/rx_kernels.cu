@@ -16,6 +16,7 @@
 //
 // Reference cites are to /root/reference (markusmoenig/Rusterix).
 #include "rx_kernels.cuh"
+#include "rx_vm.cuh"
 
 #include <math_constants.h>
 
@@ -284,7 +285,7 @@ __global__ void __launch_bounds__(256) k_frame_setup(SceneDev S, Workspace Wk, u
         sy0 = max(sy0, F.band_y0); sy1 = min(sy1, F.band_y1);
         if (tid == 0) {
             DFrameBatch2 fb2;
-            fb2.tex = 0xFFFFFFFFu; fb2.terrain = 0u; fb2.pad = 0u;
+            fb2.tex = 0xFFFFFFFFu; fb2.terrain = 0u; fb2.program = B.program;
             if (is_tile_source(B.source_kind)) {
                 DTile t;  // rasterizer.rs:674-733: a missing tile samples as transparent
                 if (source_tile(S, B.source_kind, B.source_index, &t)) fb2.tex = t.first + (uint32_t)(F.animation_frame % t.n_frames);
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(256) k_frame_setup(SceneDev S, Workspace Wk, u
         }
         fb.tex = 0xFFFFFFFFu;
         fb.alpha_test = 0;
-        fb.sd_tex_word = 0; fb.sd_wh = 0; fb.sd_pad[0] = fb.sd_pad[1] = fb.sd_pad[2] = 0;
+        fb.sd_tex_word = 0; fb.sd_wh = 0; fb.sd_pad[0] = fb.sd_pad[1] = 0;
         fb.sd_chunk = B.chunk; fb.sd_profile = B.profile_id;
         fb.sd_flags = B.has_normals ? RX_SD_NORMALS : 0u;
         if (B.bflags & RX_BF_HAS_PROFILE) fb.sd_flags |= RX_SD_HAS_PROFILE;
@@ -410,8 +411,14 @@ __global__ void __launch_bounds__(256) k_frame_setup(SceneDev S, Workspace Wk, u
                 }
             }
         }
+        fb.sd_program = -1;
+        if (B.program >= 0 && (uint32_t)B.program < S.vm.n_programs && S.vm.programs[B.program].n_words != 0u) {  // rasterizer.rs:1226-1293
+            fb.sd_program = B.program;
+            fb.sd_flags |= RX_SD_SHADER;
+            if (S.vm.programs[B.program].sets_opacity) { fb.sd_flags |= RX_SD_VM_OPACITY; fb.alpha_test = 1u; }  // opacity is the program's
+        }
         // an opaque-pass batch whose constant texel is not opaque can never write (rasterizer.rs:1408)
-        if (!(fb.sd_flags & (RX_SD_TEXTURED | RX_SD_TERRAIN | RX_SD_OPACITY)) && (fb.sd_pixel >> 24) != 255u) rejected = true;
+        if (!(fb.sd_flags & (RX_SD_TEXTURED | RX_SD_TERRAIN | RX_SD_OPACITY | RX_SD_VM_OPACITY)) && (fb.sd_pixel >> 24) != 255u) rejected = true;
         fb.bb_minx = rx_float_key(CUDART_INF_F); fb.bb_maxx = rx_float_key(-CUDART_INF_F);
         fb.bb_miny = rx_float_key(CUDART_INF_F); fb.bb_maxy = rx_float_key(-CUDART_INF_F);
         fb.sc_x0 = fb.sc_x1 = fb.sc_y0 = fb.sc_y1 = 0;
@@ -1032,17 +1039,151 @@ __device__ __forceinline__ uint32_t shade_owner(const SceneDev& S, const ShadeCo
     return fast_u8(l2s(lit.x)) | (fast_u8(l2s(lit.y)) << 8) | (fast_u8(l2s(lit.z)) << 16) | (a8 << 24);
 }
 
+// ---- Rusteria VM batch shaders (general mode) -------------------------------------------------------
+// Everything a program can observe is derived with the reference's own arithmetic (exact divisions, no
+// approximations): a program may quantise its inputs (floor, step, pattern lookups), which would amplify
+// the +-1 ulp of the fast shading path into visible differences.
+
+// CompiledLight::radiance_at (light.rs:504-533), exact
+__device__ __forceinline__ bool light_radiance_exact(const DLight& l, f3 point, f3 normal, f3* out) {
+    f3 c;
+    if (!rx_light_color_at(l, point, false, &c)) return false;
+    if (l.light_type == RXC_LIGHT_AMBIENT || l.light_type == RXC_LIGHT_AMBIENT_DAYLIGHT || l.light_type == RXC_LIGHT_DAYLIGHT) { *out = c; return true; }
+    const f3 dir = rx_normalize3(rx_sub3({l.px, l.py, l.pz}, point));
+    const float lambert = fmaxf(rx_dot3(normal, dir), 0.0f);
+    *out = rx_scale3(c, lambert);
+    return true;
+}
+
+// shade_fast_brdf with emissive = 0 (rasterizer.rs:1912-1951), exact
+__device__ __forceinline__ f3 shade_brdf_exact(f3 base, float roughness, float metallic, f3 n, f3 v, f3 l, f3 radiance) {
+    const float n_dot_l = fmaxf(rx_dot3(n, l), 0.0f);
+    if (n_dot_l <= 0.0f) return {0.0f, 0.0f, 0.0f};
+    const float t = rx_clamp(metallic, 0.0f, 1.0f);  // vek lerp: clamped factor, mul_add
+    const f3 f0 = {__fmaf_rn(t, base.x - 0.04f, 0.04f), __fmaf_rn(t, base.y - 0.04f, 0.04f), __fmaf_rn(t, base.z - 0.04f, 0.04f)};
+    f3 kd = rx_scale3(base, 1.0f - metallic);
+    kd = rx_scale3(kd, 1.0f - fmaxf(f0.x, fmaxf(f0.y, f0.z)));
+    const float a = fmaxf(roughness * roughness, 1e-4f);
+    const float shininess = rx_clamp(2.0f / a - 2.0f, 1.0f, 2048.0f);
+    const f3 h = rx_normalize3(rx_add3(l, v));
+    const float n_dot_h = fmaxf(rx_dot3(n, h), 0.0f);
+    const float spec_b = n_dot_h <= 0.0f ? 0.0f : exp2f(shininess * log2f(n_dot_h));
+    const float n_dot_v = fmaxf(rx_dot3(n, v), 0.0f);
+    const float om = 1.0f - rx_clamp(n_dot_v, 0.0f, 1.0f);
+    const float x = om * om * om * om * om;
+    const f3 fr = {f0.x + (1.0f - f0.x) * x, f0.y + (1.0f - f0.y) * x, f0.z + (1.0f - f0.z) * x};
+    const f3 diffuse = rx_scale3(kd, n_dot_l);
+    const f3 specular = rx_scale3(rx_scale3(fr, spec_b), n_dot_l);
+    return rx_mul3(rx_add3(diffuse, specular), radiance);
+}
+
+__device__ __forceinline__ float srgb_to_linear_exact(float x) { const float x2 = x * x; return (0.6975f * x2 + 0.3025f) * x; }  // rasterizer.rs:20-25
+__device__ __forceinline__ float linear_to_srgb_exact(float x) { const float s = sqrtf(x); return 1.055f * s - 0.055f * s * s; }   // :28-33
+__device__ __forceinline__ uint32_t pack_pixel(float r, float g, float b, float a) {  // vec4_to_pixel, lib.rs:72-79
+    return rx_f32_to_u8_saturated(r) | (rx_f32_to_u8_saturated(g) << 8) | (rx_f32_to_u8_saturated(b) << 16) | (rx_f32_to_u8_saturated(a) << 24);
+}
+
+// A 3D fragment of a batch with a VM program, up to and including the program (rasterizer.rs:1062-1317 for the
+// opaque pass, :1500-1637 for the opacity pass).  Returns false when the program hit a device limit.
+__device__ __noinline__ bool vm_fragment_3d(const SceneDev& S, const DFrame& F, const DFrameBatch& FB, const TriShade& sh, float alpha, float beta,
+                                            float z, float fpx, float fpy, uint32_t sample_mode, bool opacity_pass, VmIO* io, f3* world_out) {
+    const float gamma = 1.0f - alpha - beta;
+    float u = sh.uw0 * alpha + sh.uw1 * beta + sh.uw2 * gamma;
+    float v = sh.vw0 * alpha + sh.vw1 * beta + sh.vw2 * gamma;
+    const float irw = sh.rw0 * alpha + sh.rw1 * beta + sh.rw2 * gamma;
+    u = u / irw; v = v / irw;
+    const f3 world = screen_to_world_exact(F, fpx, fpy, z);
+    *world_out = world;
+    f3 normal = {0.0f, 0.0f, 0.0f};
+    if (!opacity_pass && (FB.sd_flags & RX_SD_NORMALS)) {  // :1083-1099
+        if (__float_as_uint(sh.pad0) != 0u) {
+            normal = {sh.n0x, sh.n0y, sh.n0z};  // flat triangle: make_tri stored the unit normal
+        } else {
+            normal = rx_normalize3({sh.n0x * alpha + sh.n1x * beta + sh.n2x * gamma, sh.n0y * alpha + sh.n1y * beta + sh.n2y * gamma,
+                                    sh.n0z * alpha + sh.n1z * beta + sh.n2z * gamma});
+        }
+        const f3 view_dir = rx_normalize3({F.cam[0] - world.x, F.cam[1] - world.y, F.cam[2] - world.z});
+        if (rx_dot3(normal, view_dir) < 0.0f) normal = {-normal.x, -normal.y, -normal.z};
+    }
+    uint32_t texel = FB.sd_pixel;
+    if (FB.sd_flags & RX_SD_TEXTURED) texel = sample_desc(S.arena, FB.sd_tex_word, FB.sd_wh, FB.sd_flags, u, v, sample_mode);
+    else if (FB.sd_flags & RX_SD_TERRAIN) texel = terrain_sample(S.arena, FB.sd_tex_word, FB.sd_wh, S.chunk_info[FB.sd_chunk], world.x, world.z);
+    const float inv255 = 1.0f / 255.0f;  // pixel_to_vec4, lib.rs:55-62
+    vm_io_reset(*io);
+    io->color = {srgb_to_linear_exact((float)(texel & 0xFFu) * inv255), srgb_to_linear_exact((float)((texel >> 8) & 0xFFu) * inv255),
+                 srgb_to_linear_exact((float)((texel >> 16) & 0xFFu) * inv255)};
+    io->opacity.x = (float)(texel >> 24) / 255.0f;
+    io->normal = normal;
+    io->uv = {u / 4.0f, v / 4.0f, 0.0f};
+    io->hitpoint = world;
+    io->time = {F.time, F.time, F.time};
+    if (FB.sd_program < 0 || (uint32_t)FB.sd_program >= S.vm.n_programs) return true;
+    return vm_run(S.vm, S.vm.programs[FB.sd_program], *io);
+}
+
+// the opaque 3D pass behind a program: lighting with the material the program produced (rasterizer.rs:1319-1404)
+__device__ __noinline__ uint32_t shade_owner_vm(const SceneDev& S, const DFrame& F, const DLight* lights, const DFrameBatch& FB, const TriShade& sh,
+                                                float alpha, float beta, float z, float fpx, float fpy, uint32_t sample_mode, uint32_t* fault) {
+    VmIO io;
+    f3 world;
+    if (!vm_fragment_3d(S, F, FB, sh, alpha, beta, z, fpx, fpy, sample_mode, false, &io, &world)) *fault = 1u;
+    const f3 base = io.color;
+    const f3 normal = rx_normalize3(io.normal);
+    const float rough = rx_clamp(io.roughness.x, 0.0f, 1.0f), metal = rx_clamp(io.metallic.x, 0.0f, 1.0f);
+    f3 lit = {0.0f, 0.0f, 0.0f};
+    const float occlusion = S.n_sectors ? sector_occlusion(S, FB.sd_chunk, world.x, world.z) : 1.0f;
+    const float hemi = 0.5f * (normal.y + 1.0f);
+    const f3 kd = rx_scale3(rx_scale3(base, 1.0f - metal), 1.0f - 0.04f);
+    if (occlusion > 0.0f) {
+        if (F.has_ambient) lit = rx_add3(lit, rx_scale3(rx_mul3({F.ambient[0], F.ambient[1], F.ambient[2]}, kd), hemi));
+        lit = {lit.x * occlusion, lit.y * occlusion, lit.z * occlusion};
+    }
+    lit = rx_add3(lit, rx_scale3(rx_mul3({FB.sd_ambient[0], FB.sd_ambient[1], FB.sd_ambient[2]}, kd), hemi));
+    const f3 view_dir = rx_normalize3({F.cam[0] - world.x, F.cam[1] - world.y, F.cam[2] - world.z});
+    for (uint32_t li = 0; li < S.n_lights; ++li) {
+        const DLight& L = lights[li];
+        f3 radiance;
+        if (!light_radiance_exact(L, world, normal, &radiance)) continue;
+        const f3 ldir = rx_normalize3({L.px - world.x, L.py - world.y, L.pz - world.z});
+        lit = rx_add3(lit, shade_brdf_exact(base, rough, metal, normal, view_dir, ldir, radiance));
+    }
+    lit = rx_add3(lit, io.emissive);
+    return pack_pixel(linear_to_srgb_exact(lit.x), linear_to_srgb_exact(lit.y), linear_to_srgb_exact(lit.z), io.opacity.x);
+}
+
+// 2D fragment behind a program (rasterizer.rs:760-797): sRGB texel in, colour out, alpha forced to 1
+__device__ __noinline__ uint32_t shade_2d_vm(const SceneDev& S, const DFrame& F, int program, uint32_t texel, float u, float v, float wx, float wy,
+                                             uint32_t* fault) {
+    if (program < 0 || (uint32_t)program >= S.vm.n_programs || S.vm.programs[program].n_words == 0u) return texel;
+    VmIO io;
+    vm_io_reset(io);
+    const float inv255 = 1.0f / 255.0f;
+    io.color = {(float)(texel & 0xFFu) * inv255, (float)((texel >> 8) & 0xFFu) * inv255, (float)((texel >> 16) & 0xFFu) * inv255};
+    io.uv = {u / 4.0f, v / 4.0f, 0.0f};
+    io.hitpoint = {wx, wy, 0.0f};
+    io.time = {F.time, F.time, F.time};
+    if (!vm_run(S.vm, S.vm.programs[program], io)) *fault = 1u;
+    return pack_pixel(io.color.x, io.color.y, io.color.z, 1.0f);
+}
+
 // The opacity layer's pixel (rasterizer.rs:1500-1645): texel -> linear -> sRGB, no lighting; alpha = texel alpha.
 // Barycentrics are recomputed from the owner's record with the arithmetic of the visibility pass.
+template <bool VM>
 __device__ __forceinline__ uint32_t shade_opacity(const SceneDev& S, const DFrame& F, const DFrameBatch* __restrict__ fbs,
                                                   const TriVis* __restrict__ vis, const TriShade* __restrict__ shade, uint32_t owner,
-                                                  float fpx, float fpy, uint32_t sample_mode) {
+                                                  float fpx, float fpy, uint32_t sample_mode, uint32_t* fault) {
     const float4* q = reinterpret_cast<const float4*>(vis + owner);
     const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
     const uint32_t meta = __ldg(&vis[owner].meta);
     const DFrameBatch& FB = fbs[meta & RX_META_BATCH];
     float alpha, beta;
     const float z = fragment_depth(q0, q1, q2, meta, fpx, fpy, &alpha, &beta);
+    if (VM && (FB.sd_flags & RX_SD_SHADER)) {  // rasterizer.rs:1611-1645: the program's colour and opacity, no lighting
+        VmIO io;
+        f3 world;
+        if (!vm_fragment_3d(S, F, FB, shade[owner], alpha, beta, z, fpx, fpy, sample_mode, true, &io, &world)) *fault = 1u;
+        return pack_pixel(linear_to_srgb_exact(io.color.x), linear_to_srgb_exact(io.color.y), linear_to_srgb_exact(io.color.z), io.opacity.x);
+    }
     const float gamma = 1.0f - alpha - beta;
     uint32_t texel = FB.sd_pixel;
     if (FB.sd_flags & RX_SD_TEXTURED) {
@@ -1121,9 +1262,10 @@ __device__ __forceinline__ bool los_visible(const SceneDev& S, float fx, float f
 }
 
 // one 2D triangle fragment: rasterizer.rs:655-895.  `color` is the tile buffer pixel (RGBA8).
+template <bool VM>
 __device__ __forceinline__ uint32_t shade_2d(const SceneDev& S, const DFrame& F, const DLight* __restrict__ lights, const Tri2D& T,
                                              const DBatch2& B, const DFrameBatch2& FB, int px, int py, float fpx, float fpy,
-                                             uint32_t sample_mode, uint32_t color) {
+                                             uint32_t sample_mode, uint32_t color, uint32_t* fault) {
     // barycentric_weights_2d, rasterizer.rs:1731-1750
     const float acx = T.cx - T.ax, acy = T.cy - T.ay, abx = T.bx - T.ax, aby = T.by - T.ay;
     const float apx = fpx - T.ax, apy = fpy - T.ay, pcx = T.cx - fpx, pcy = T.cy - fpy, pbx = T.bx - fpx, pby = T.by - fpy;
@@ -1146,6 +1288,8 @@ __device__ __forceinline__ uint32_t shade_2d(const SceneDev& S, const DFrame& F,
     } else if (B.source_kind == RXC_SRC_PIXEL) {
         texel = B.source_pixel;
     }
+
+    if (VM && FB.program >= 0) texel = shade_2d_vm(S, F, FB.program, texel, u, v, wx, wy, fault);  // rasterizer.rs:760-797
 
     if (FB.lit) {  // rasterizer.rs:799-873
         float acc[3] = {0.0f, 0.0f, 0.0f};
@@ -1225,10 +1369,17 @@ __device__ __forceinline__ uint32_t rect_overlaps(const TriVis& T, int tx0, int 
 
 // texel of a z-passing fragment of an alpha-tested batch (rasterizer.rs:1062-1222): exact arithmetic, it decides
 // ownership (:1408).  Out of line: rare, and the visibility loop is instantiated once per pixel of the 2x2.
-__device__ __noinline__ uint32_t alpha_test_texel(const uint8_t* __restrict__ arena, const DChunkInfo* __restrict__ chunk_info,
+template <bool VM>
+__device__ __noinline__ uint32_t alpha_test_texel(const SceneDev& S, const uint8_t* __restrict__ arena, const DChunkInfo* __restrict__ chunk_info,
                                                   const DFrame* __restrict__ F, const DFrameBatch* __restrict__ FB,
                                                   const TriShade* __restrict__ sh, float alpha, float beta, float z, float fpx, float fpy,
                                                   uint32_t sample_mode) {
+    if (VM && (FB->sd_flags & RX_SD_VM_OPACITY)) {  // the program decides the opacity (rasterizer.rs:1398-1408)
+        VmIO io;
+        f3 world;
+        vm_fragment_3d(S, *F, *FB, *sh, alpha, beta, z, fpx, fpy, sample_mode, false, &io, &world);  // a fault is reported by the resolve
+        return rx_f32_to_u8_saturated(io.opacity.x) << 24;
+    }
     if (FB->sd_flags & RX_SD_TERRAIN) {
         const f3 world = screen_to_world_exact(*F, fpx, fpy, z);
         return terrain_sample(arena, FB->sd_tex_word, FB->sd_wh, chunk_info[FB->sd_chunk], world.x, world.z);
@@ -1241,6 +1392,7 @@ __device__ __noinline__ uint32_t alpha_test_texel(const uint8_t* __restrict__ ar
 }
 
 // depth + alpha test of one covered pixel (rasterizer.rs:1051-1060, :1408)
+template <bool VM>
 __device__ __forceinline__ void test_fragment(const SceneDev& S, const DFrame& F, const DFrameBatch* __restrict__ fbs,
                                               const TriShade* __restrict__ shade, const float4 q0, const float4 q1, const float4 q2,
                                               uint32_t meta, uint32_t slot, float fpx, float fpy, uint32_t sample_mode, float& best_z,
@@ -1260,8 +1412,8 @@ __device__ __forceinline__ void test_fragment(const SceneDev& S, const DFrame& F
     const bool pass_z = (z < best_z) || (z == best_z && best != RX_OWNER_NONE && slot < best);
     if (!pass_z) return;
     if (meta & RX_META_ALPHA) {  // alpha test: texel alpha must be 255 to write (:1408)
-        const uint32_t texel = alpha_test_texel(S.arena, S.chunk_info, &F, fbs + (meta & RX_META_BATCH), shade + slot, alpha, beta, z, fpx, fpy,
-                                                sample_mode);
+        const uint32_t texel = alpha_test_texel<VM>(S, S.arena, S.chunk_info, &F, fbs + (meta & RX_META_BATCH), shade + slot, alpha, beta, z,
+                                                         fpx, fpy, sample_mode);
         if ((texel >> 24) != 255u) return;
     }
     best_z = z; best = slot; best_al = alpha; best_be = beta;
@@ -1269,7 +1421,7 @@ __device__ __forceinline__ void test_fragment(const SceneDev& S, const DFrame& F
 
 // coverage of one staged triangle over the thread's 2x2 pixels (rasterizer.rs:1020-1036), then the
 // depth test of the covered ones.  `valid` masks pixels outside the frame.
-template <bool GENERAL>
+template <bool GENERAL, bool VM>
 __device__ __forceinline__ void process_record(const SceneDev& S, const DFrame& F, const DFrameBatch* __restrict__ fbs,
                                                const TriShade* __restrict__ shade, const TriVis* Tp, uint32_t slot, bool full, int px0,
                                                int py0, float fx0, float fy0, uint32_t valid, uint32_t sample_mode, Vis4& V, Opa4& O) {
@@ -1325,15 +1477,16 @@ __device__ __forceinline__ void process_record(const SceneDev& S, const DFrame& 
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         if (m & (1u << k))
-            test_fragment(S, F, fbs, shade, q0, q1, q2, meta, slot, (k & 1) ? fx1 : fx0, (k & 2) ? fy1 : fy0, sample_mode, V.z[k],
+            test_fragment<VM>(S, F, fbs, shade, q0, q1, q2, meta, slot, (k & 1) ? fx1 : fx0, (k & 2) ? fy1 : fy0, sample_mode, V.z[k],
                           V.own[k], V.al[k], V.be[k]);
     }
 }
 
 // one 2D record against one pixel: triangle (rasterizer.rs:640-895) or Bresenham line (:901-955, :1777-1821)
+template <bool VM>
 __device__ __forceinline__ uint32_t apply_2d(const SceneDev& S, const DFrame& F, const DLight* __restrict__ lights,
                                             const DFrameBatch2* __restrict__ fb2, const Tri2D& T, int px, int py, uint32_t sample_mode,
-                                            uint32_t color) {
+                                            uint32_t color, uint32_t* fault) {
     const int x0 = T.bbx & 0xFFFF, x1 = T.bbx >> 16, y0 = T.bby & 0xFFFF, y1 = T.bby >> 16;
     if (px < x0 || px >= x1 || py < y0 || py >= y1) return color;
     const DBatch2& B = S.b2[T.batch];
@@ -1345,15 +1498,17 @@ __device__ __forceinline__ uint32_t apply_2d(const SceneDev& S, const DFrame& F,
     if ((T.ea[0] * fpx + T.eb[0] * fpy + T.ec[0]) < 0.0f) return color;
     if ((T.ea[1] * fpx + T.eb[1] * fpy + T.ec[1]) < 0.0f) return color;
     if ((T.ea[2] * fpx + T.eb[2] * fpy + T.ec[2]) < 0.0f) return color;
-    return shade_2d(S, F, lights, T, B, fb2[T.batch], px, py, fpx, fpy, sample_mode, color);
+    return shade_2d<VM>(S, F, lights, T, B, fb2[T.batch], px, py, fpx, fpy, sample_mode, color, fault);
 }
 
 // SAMPLE: 0 nearest / 1 linear for every frame of the launch, 2 = read it per frame.  PLANES: owner/depth outputs.
 // GENERAL: the tile lists are sorted by submission ordinal and hold every triangle (no large list): chunk opacity
 // batches with their surface ids are evaluated sequentially, and 2D records come from sorted per-tile lists.
-template <int SAMPLE, bool PLANES, bool GENERAL>
+// MODE: 0 = fast path, 1 = general (below), 2 = general + Rusteria VM programs on batches.
+template <int SAMPLE, bool PLANES, int MODE>
 __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raster(SceneDev S, Workspace Wk, RasterOut out, uint32_t n_frames,
                                                                uint32_t tiles_per_frame) {
+    constexpr bool GENERAL = MODE >= 1, VM = MODE == 2;
     __shared__ __align__(16) TriVis s_large[GENERAL ? 1 : RX_LARGE_CACHE];
     __shared__ uint32_t s_large_slot[GENERAL ? 1 : RX_LARGE_CACHE];
     __shared__ uint16_t s_sel[GENERAL ? 1 : RX_LARGE_CACHE];
@@ -1485,12 +1640,13 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                         mask &= mask - 1u;
                         const uint32_t rr = __shfl_sync(0xFFFFFFFFu, slot, b);
                         const TriVis* Tp = reinterpret_cast<const TriVis*>(__shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(rp), b));
-                        process_record<GENERAL>(S, F, fbs, shade, Tp, rr, (fullm >> b) & 1u, px0, py0, fx0, fy0, valid, smode, V, O);
+                        process_record<GENERAL, VM>(S, F, fbs, shade, Tp, rr, (fullm >> b) & 1u, px0, py0, fx0, fy0, valid, smode, V, O);
                     }
                 }
             }
         }
 
+        uint32_t vm_fault = 0u;
         // resolve, one pixel of the 2x2 at a time (the visibility state goes through shared memory so the
         // shading code is not unrolled and does not hold it in registers): deferred shade of the owner,
         // miss pass (rasterizer.rs:409-461) or the 2D-only background, opacity blend (:464-495)
@@ -1509,14 +1665,17 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
             if (F.d3_active) {
                 if (owner != RX_OWNER_NONE) {
                     const uint32_t b = __ldg(&vis[owner].meta) & RX_META_BATCH;
-                    color = shade_owner(S, s_k, lights, s_kd, fbs[b], shade + owner, st.z, st.w, st.x, fpx, fpy, smode);
+                    if (VM && (fbs[b].sd_flags & RX_SD_SHADER))
+                        color = shade_owner_vm(S, F, lights_g, fbs[b], shade[owner], st.z, st.w, st.x, fpx, fpy, smode, &vm_fault);
+                    else
+                        color = shade_owner(S, s_k, lights, s_kd, fbs[b], shade + owner, st.z, st.w, st.x, fpx, fpy, smode);
                 } else {
                     color = 0xFF000000u;  // vec4_to_pixel((0,0,0,1))
                 }
                 if (GENERAL) {
                     const float2 os = s_ostate[k * RX_TILE_THREADS + tid];
                     if (os.x < 1.0f && st.x > os.x)
-                        color = blend_opacity(shade_opacity(S, F, fbs, vis, shade, __float_as_uint(os.y), fpx, fpy, smode), color,
+                        color = blend_opacity(shade_opacity<VM>(S, F, fbs, vis, shade, __float_as_uint(os.y), fpx, fpy, smode, &vm_fault), color,
                                               F.preserve_transparency != 0u);
                 }
             } else {
@@ -1557,11 +1716,12 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                     for (int k = 0; k < 4; ++k) {
                         const int px = px0 + ((k & 1) << 3), py = py0 + ((k >> 1) << 2);
                         uint32_t* c = &s_color[(py - ty0) * RX_COLOR_STRIDE + (px - tx0)];
-                        *c = apply_2d(S, F, lights, fb2, T, px, py, smode, *c);
+                        *c = apply_2d<VM>(S, F, lights, fb2, T, px, py, smode, *c, &vm_fault);
                     }
                 }
             }
         }
+        if (VM && vm_fault) atomicOr(&Wk.counters[f].overflow, 16u);  // a program hit a device limit
         __syncthreads();
 
         // write back: RGBA8 rows of the tile, 128-bit stores when rows are 16 B aligned
@@ -1721,6 +1881,24 @@ __global__ void __launch_bounds__(256) k_selftest_div(uint64_t seed, uint32_t it
     if (bad) atomicAdd(mismatches, (unsigned long long)bad);
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_vm_execute (diagnostics): one thread per record runs a program outside the rasterizer
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_vm_execute(VmDev vm, uint32_t program, uint32_t n, const float* __restrict__ in, float* __restrict__ out,
+                                                    uint32_t* faults) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* r = in + (size_t)i * 18;
+    VmIO io;
+    vm_io_reset(io);
+    io.uv = {r[0], r[1], r[2]}; io.color = {r[3], r[4], r[5]}; io.normal = {r[6], r[7], r[8]};
+    io.hitpoint = {r[9], r[10], r[11]}; io.time = {r[12], r[13], r[14]}; io.opacity = {r[15], r[16], r[17]};
+    if (!vm_run(vm, vm.programs[program], io)) atomicAdd(faults, 1u);
+    float* o = out + (size_t)i * 24;
+    const f3 v[8] = {io.uv, io.color, io.normal, io.roughness, io.metallic, io.emissive, io.opacity, io.bump};
+    for (int k = 0; k < 8; ++k) { o[3 * k] = v[k].x; o[3 * k + 1] = v[k].y; o[3 * k + 2] = v[k].z; }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -1790,8 +1968,8 @@ cudaError_t rxk_bin_fill(const SceneDev& S, const Workspace& W, uint32_t n_frame
 cudaError_t rxk_raster(const SceneDev& S, const Workspace& W, const RasterOut& out, uint32_t n_frames, uint32_t tiles_per_frame,
                        int sample_mode, int grid_x, cudaStream_t st) {
     const bool planes = out.owner || out.depth;
-#define RX_LAUNCH(SM, PL, GE) k_raster<SM, PL, GE><<<grid_x, RX_TILE_THREADS, 0, st>>>(S, W, out, n_frames, tiles_per_frame)
-#define RX_LAUNCH2(SM, PL) do { if (S.general) RX_LAUNCH(SM, PL, true); else RX_LAUNCH(SM, PL, false); } while (0)
+#define RX_LAUNCH(SM, PL, MD) k_raster<SM, PL, MD><<<grid_x, RX_TILE_THREADS, 0, st>>>(S, W, out, n_frames, tiles_per_frame)
+#define RX_LAUNCH2(SM, PL) do { if (S.general && S.vm.n_programs) RX_LAUNCH(SM, PL, 2); else if (S.general) RX_LAUNCH(SM, PL, 1); else RX_LAUNCH(SM, PL, 0); } while (0)
     if (sample_mode == 0) { if (planes) RX_LAUNCH2(0, true); else RX_LAUNCH2(0, false); }
     else if (sample_mode == 1) { if (planes) RX_LAUNCH2(1, true); else RX_LAUNCH2(1, false); }
     else { if (planes) RX_LAUNCH2(2, true); else RX_LAUNCH2(2, false); }
@@ -1801,9 +1979,13 @@ cudaError_t rxk_raster(const SceneDev& S, const Workspace& W, const RasterOut& o
 }
 int rxk_raster_blocks_per_sm() {
     int n = 0, best = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_raster<0, false, false>, RX_TILE_THREADS, 0) == cudaSuccess) best = n;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_raster<1, false, false>, RX_TILE_THREADS, 0) == cudaSuccess && n < best) best = n;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_raster<0, false, 0>, RX_TILE_THREADS, 0) == cudaSuccess) best = n;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_raster<1, false, 0>, RX_TILE_THREADS, 0) == cudaSuccess && n < best) best = n;
     return best < 1 ? 1 : best;
+}
+cudaError_t rxk_vm_execute(const SceneDev& S, uint32_t program, uint32_t n, const float* d_in, float* d_out, uint32_t* d_faults, cudaStream_t st) {
+    k_vm_execute<<<(n + 127) / 128, 128, 0, st>>>(S.vm, program, n, d_in, d_out, d_faults);
+    return cudaGetLastError();
 }
 cudaError_t rxk_selftest_div(uint64_t seed, uint32_t blocks, uint32_t iters, unsigned long long* d_mismatches, cudaStream_t st) {
     k_selftest_div<<<blocks, 256, 0, st>>>(seed, iters, d_mismatches);

@@ -35,6 +35,7 @@ struct SceneDev {
     uint32_t n_tris, n_verts;   // 3D totals
     uint32_t n_rec2d;           // 2D records per frame
     uint32_t n_static_tiles, n_dynamic_tiles;
+    VmDev vm;                   // Rusteria VM programs, pattern bank and palette
 };
 
 // Per-frame workspace: every array holds `n_frames` slices of the given stride (in elements)
@@ -101,5 +102,7 @@ cudaError_t rxk_bin_fill(const SceneDev& S, const Workspace& W, uint32_t n_frame
 cudaError_t rxk_raster(const SceneDev& S, const Workspace& W, const RasterOut& out, uint32_t n_frames, uint32_t tiles_per_frame,
                        int sample_mode, int grid, cudaStream_t st);
 int rxk_raster_blocks_per_sm();
+// diagnostics: program `program` of S.vm on n records (18 floats in, 24 floats out each)
+cudaError_t rxk_vm_execute(const SceneDev& S, uint32_t program, uint32_t n, const float* d_in, float* d_out, uint32_t* d_faults, cudaStream_t st);
 // diagnostics: rx_div_by vs div.rn on blocks*256*iters random operand pairs; adds the mismatch count
 cudaError_t rxk_selftest_div(uint64_t seed, uint32_t blocks, uint32_t iters, unsigned long long* d_mismatches, cudaStream_t st);

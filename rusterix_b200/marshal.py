@@ -182,9 +182,51 @@ def marshal_scene(scene: Scene, index_bytes: int = 4, assets: Assets = None):
     lights = marshal_lights(scene.all_lights())
     dyn = marshal_tiles(scene.dynamic_textures)
     act = marshal_tiles(actors.tiles)
+    # Rusteria VM programs: scene.shaders, then every chunk's (rxc_chunk.shader_base)
+    flat_programs = [p.flatten() for p in scene.shaders]
+    chunk_base = []
+    for chunk in scene.chunks.values():
+        chunk_base.append(len(flat_programs))
+        flat_programs += [p.flatten() for p in chunk.shaders]
+    progs = (_abi.rxc_program * max(1, len(flat_programs)))()
+    for i, fp in enumerate(flat_programs):
+        o = progs[i]
+        keep.append(fp.words)
+        o.code = fp.words.ctypes.data if len(fp.words) else None
+        o.n_words = len(fp.words)
+        o.entry, o.shade_locals, o.n_globals = fp.entry, fp.shade_locals, fp.n_globals
+        o.sets_opacity = 1 if fp.sets_opacity else 0
+
+    def marshal_patterns(bank):
+        arr = (_abi.rxc_pattern * max(1, len(bank)))()
+        for i, (w, h, data) in enumerate(bank):
+            d = np.ascontiguousarray(np.asarray(data, dtype=np.float32).reshape(h * w, 3))
+            keep.append(d)
+            arr[i].data, arr[i].width, arr[i].height = d.ctypes.data, int(w), int(h)
+        return arr
+    pats, pats_n = marshal_patterns(scene.patterns), marshal_patterns(scene.patterns_normal)
+    pal_src = list(assets.palette) if assets is not None else []
+    palette = np.zeros((max(1, len(pal_src)), 4), dtype=np.float32)
+    for i, col in enumerate(pal_src):
+        if col is not None:
+            palette[i] = [1.0, col[0], col[1], col[2]]
+    keep += [progs, pats, pats_n, palette]
+
     chunks = (_abi.rxc_chunk * max(1, len(scene.chunks)))()
     for ci, chunk in enumerate(scene.chunks.values()):
         c = chunks[ci]
+        c.shader_base = chunk_base[ci]
+        c.n_shaders = len(chunk.shaders)
+        if any(t is not None for t in chunk.shader_textures):
+            ptrs = (C.POINTER(_abi.rxc_texture) * max(1, len(chunk.shaders)))()
+            for k, tex in enumerate(chunk.shader_textures[:len(chunk.shaders)]):
+                if tex is not None:
+                    t = _abi.rxc_texture()
+                    t.data, t.width, t.height = tex.data.ctypes.data, tex.width, tex.height
+                    ptrs[k] = C.pointer(t)
+                    keep += [t, tex.data]
+            c.shader_textures = ptrs
+            keep.append(ptrs)
         c.origin[:] = [int(chunk.origin[0]), int(chunk.origin[1])]
         c.size = int(chunk.size)
         sectors = marshal_sectors(chunk.occluded_sectors)
@@ -211,6 +253,12 @@ def marshal_scene(scene: Scene, index_bytes: int = 4, assets: Assets = None):
     s.n_chunks = len(scene.chunks)
     s.actor_tiles = act.struct
     s.n_actor_tiles = len(actors.tiles)
+    s.shaders = progs
+    s.n_shaders = len(flat_programs)
+    s.n_scene_shaders = len(scene.shaders)
+    s.patterns, s.n_patterns = pats, len(scene.patterns)
+    s.patterns_normal, s.n_patterns_normal = pats_n, len(scene.patterns_normal)
+    s.palette, s.n_palette = palette.ctypes.data, len(pal_src)
     keep += [b3, b2, lights, dyn, act, chunks]
     return Marshalled(s, keep)
 

@@ -87,6 +87,15 @@ class DeviceContext:
         self.last_bad_pair = (int(pair[0]), int(pair[1]))
         return int(bad.value)
 
+    def vm_execute(self, program: int, records: np.ndarray):
+        """Diagnostics (rxc_vm_execute): run shader `program` of the resident scene on records[n, 18]
+        (uv, color, normal, hitpoint, time, opacity); returns (out[n, 24], faults)."""
+        rec = np.ascontiguousarray(records, dtype=np.float32).reshape(-1, 18)
+        out = np.zeros((len(rec), 24), dtype=np.float32)
+        faults = C.c_uint32(0)
+        self.check(self.lib.rxc_vm_execute(self.handle, int(program), len(rec), rec.ctypes.data, out.ctypes.data, C.byref(faults)))
+        return out, int(faults.value)
+
     def stats(self) -> _abi.rxc_stats:
         s = _abi.rxc_stats()
         self.check(self.lib.rxc_get_stats(self.handle, C.byref(s)))

@@ -131,6 +131,7 @@ class Config:
     matrix2d: Optional[object] = None       # projection_matrix_2d (Mat3) of the 2D configs
     mapmini: Optional[MapMini] = None
     render_mode: Optional[RenderMode] = None
+    time: float = 0.0                       # Rasterizer.time (the VM's `time`)
 
     def rasterizer(self, frame: int = 0) -> Rasterizer:
         cam = self.cameras(frame) if self.cameras is not None else self.camera
@@ -142,6 +143,7 @@ class Config:
             r.mapmini = self.mapmini
         if self.render_mode is not None:
             r.render_mode(self.render_mode)
+        r.time_ = float(self.time)
         return r
 
     def counts(self):
@@ -563,3 +565,177 @@ def game2d_config(width=960, height=640) -> Config:
     cam = D3FirstPCamera.new()
     return Config("game2d", game2d_scene(), chunked_assets(), width, height, 40, SampleMode.Nearest, (0.25, 0.25, 0.3, 1.0), cam,
                   matrix2d=m, mapmini=mm, render_mode=RenderMode.render_2d())
+
+
+# ------------------------------------------------------------------------------------------------
+# batch shaders: Rusteria VM programs on 3D, opacity-pass and 2D batches
+# ------------------------------------------------------------------------------------------------
+def pattern_bank(size=64):
+    """Stand-ins for rusteria's patterns() bank (textures/patterns.rs:27-37: value, fbm_value, perlin, fbm_perlin,
+    bricks, tiles, blocks).  The reference computes its bank on the host once per process and the rasterizer only
+    looks texels up; what matters here is that oracle and device read the same host-provided arrays."""
+    y, x = np.mgrid[0:size, 0:size].astype(np.float32)
+    bank = []
+    for k in range(7):
+        n = rand01(size * size, SEED + 900 + k).reshape(size, size).astype(np.float32)
+        if k < 4:      # smooth noise: a few octaves of box-filtered white noise, tileable through np.roll
+            v = np.zeros((size, size), np.float32)
+            amp, tot = 1.0, 0.0
+            for o in range(1 + k):
+                r = 2 ** (3 - min(o, 3))
+                s = sum(np.roll(np.roll(n, dx * (o + 1), 1), dy * (o + 1), 0) for dx in range(-r, r + 1) for dy in range(-r, r + 1)) / float((2 * r + 1) ** 2)
+                v += amp * s
+                tot += amp
+                amp *= 0.5
+            v = (v / tot - v.min() / tot) / max(1e-6, (v.max() - v.min()) / tot)
+        elif k == 4:   # bricks
+            row = (y // 8).astype(int)
+            xx = (x + 8 * (row % 2)) % 16
+            v = np.where((y % 8 < 1) | (xx < 1), 0.1, 0.6 + 0.4 * n)
+        elif k == 5:   # tiles
+            v = np.where((x % 16 < 2) | (y % 16 < 2), 0.0, 1.0)
+        else:          # blocks
+            v = ((x // 8 + y // 8) % 3) / 2.0
+        v = v.astype(np.float32)
+        bank.append((size, size, np.stack([v, 0.5 * v + 0.25 * n, 1.0 - v], axis=-1).reshape(-1, 3).astype(np.float32)))
+    return bank
+
+
+def shader_wood():
+    """examples/cube_shaded.rs:46-102, compiled by hand into the op sequence of its shade()."""
+    from . import vm
+    b = vm.Body()
+    t = b.let(vm.time_ * 0.0)
+    uv2 = b.let(vm.uv / 3.0 - vm.vec2(1.5, 1.5))
+    n1 = b.let(vm.sample(uv2 + vm.vec2(t.x, 0.0), "fbm_perlin"))
+    n2 = b.let(vm.sample(uv2 * 2.0 + vm.vec2(0.0, (t * 0.7).x), "fbm_perlin"))
+    turb = b.let(0.65 * n1 + 0.35 * n2)
+    turb_zm = b.let((turb - 0.5) * 2.0)
+    r = b.let(vm.length(uv2))
+    rings = b.let(r + 0.22 * turb_zm)
+    waves = b.let(vm.sin(rings * 10.0))
+    rings_mask = b.let(vm.pow_(1.0 - vm.abs_(waves), 3.0))
+    grain_uv = b.let(vm.vec2(uv2.x * 8.0, uv2.y * 40.0))
+    g = b.let(vm.sample(grain_uv + vm.vec2(0.0, (t * 0.5).x), "value"))
+    grain = b.let((g - 0.5) * 2.0)
+    b.set("Color", vm.mix((0.72, 0.52, 0.32), (0.45, 0.30, 0.16), rings_mask))
+    b.set("Color", vm.color * (1.0 + 0.06 * grain))
+    band = b.let(uv2.y + 0.15 * turb_zm)
+    cathedral = b.let(vm.pow_(1.0 - vm.abs_(vm.sin(band * 6.0)), 4.0))
+    b.set("Color", vm.mix(vm.color, vm.color * 0.9, cathedral * 0.2))
+    b.set("Roughness", 0.6 + cathedral * 0.3)
+    return vm.Program([b.code], 0, b.n_locals, 0)
+
+
+def shader_holes():
+    """Writes opacity at the top level of shade() (Program::shader_supports_opacity): a perforated sheet."""
+    from . import vm
+    b = vm.Body()
+    m = b.let(vm.sample(vm.uv * 6.0, "tiles"))
+    b.set("Opacity", m.x)
+    b.set("Color", vm.color * (0.6 + 0.4 * vm.sample(vm.uv * 2.0, "bricks").x))
+    b.set("Metallic", 0.7)
+    b.set("Roughness", 0.25)
+    return vm.Program([b.code], 0, b.n_locals, 0)
+
+
+def shader_control_flow(emissive=False):
+    """For / If / FunctionCall / Return / globals / swizzle writes: stripes counted in a loop through a helper.
+    `emissive`: one branch also writes `emissive`, which the reference never resets (src/rasterizer.rs:310): the
+    value then leaks into every later fragment of the screen tile, so frames with it are compared against the
+    oracle's per-fragment-state mode (deviations)."""
+    from . import vm
+    f = vm.Body(n_params=2)          # fn band(x, k): if fract(x * k) < 0.5 { return 1 } 0.25
+    inner = f.sub()
+    inner.ret(1.0)
+    f.if_(vm.fract(f.param(0) * f.param(1)) < 0.5, inner)
+    f.code += vm.X.of(0.25).ops
+    b = vm.Body()
+    acc = b.let(0.0)
+    i = b.let(0.0)
+    init, incr, body = b.sub(), b.sub(), b.sub()
+    incr.assign(i, i + 1.0)
+    body.assign(acc, acc + vm.call(1, 2, vm.uv.x * 4.0 + vm.uv.y, i + 1.0) * 0.25)
+    b.for_(init, i < 4.0, incr, body)
+    b.set_global(0, acc)
+    tint = b.let(vm.palette(2.0))
+    b.code += tint.ops + vm.X.of(0.5).ops + [("SetComponents", [1])] + [("StoreLocal", tint.ops[0][1])]   # tint.y = 0.5
+    then, other = b.sub(), b.sub()
+    then.set("Color", vm.X([("LoadGlobal", 0)]) * tint)
+    other.set("Color", vm.color * 0.5)
+    if emissive:
+        other.set("Emissive", vm.vec3(0.15, 0.0, 0.0) * vm.abs_(vm.sin(vm.hitpoint.x * 4.0)))
+    b.if_(vm.normal.y > 0.5, then, other)
+    return vm.Program([b.code, f.code], 0, b.n_locals, 1)
+
+
+def shader_glass_tint():
+    """For an opacity-pass batch: colour and opacity from the program (rasterizer.rs:1611-1645)."""
+    from . import vm
+    b = vm.Body()
+    b.set("Color", vm.mix(vm.color, (0.1, 0.4, 0.8), 0.5 + 0.5 * vm.sin(vm.hitpoint.y * 6.0)))
+    b.set("Opacity", 0.35 + 0.3 * vm.fract(vm.uv.x * 8.0))
+    return vm.Program([b.code], 0, b.n_locals, 0)
+
+
+def shader_2d_scanlines():
+    """A 2D batch program (rasterizer.rs:760-797): sRGB in, sRGB out, alpha forced to 1."""
+    from . import vm
+    b = vm.Body()
+    b.set("Color", vm.color * (0.55 + 0.45 * vm.step(0.5, vm.fract(vm.uv.y * 24.0))) + vm.vec3(0.0, 0.0, 0.1) * vm.cos(vm.hitpoint.x * 0.05))
+    return vm.Program([b.code], 0, b.n_locals, 0)
+
+
+def shaded_scene(logo_size=256, emissive=False) -> Scene:
+    scene = Scene()
+    scene.patterns = pattern_bank()
+    scene.patterns_normal = pattern_bank()[:3]
+    wood = scene.add_shader(shader_wood())
+    holes = scene.add_shader(shader_holes())
+    flow = scene.add_shader(shader_control_flow(emissive))
+    scan = scene.add_shader(shader_2d_scanlines())
+
+    def fin(b, tile):
+        return b.source(PixelSource.StaticTileIndex(tile)).cull_mode(CullMode.Off).with_computed_normals()
+
+    scene.d3_static.append(fin(Batch3D.from_box(-0.5, -0.5, -0.5, 1.0, 1.0, 1.0), 0).shader(wood))
+    scene.d3_static.append(fin(Batch3D.from_box(-1.6, -0.4, -0.4, 0.8, 0.8, 0.8), 1).repeat_mode(RepeatMode.RepeatXY).shader(flow))
+    # a perforated sheet in front of the boxes; what is behind shows through the holes the program cuts
+    sheet = Batch3D([(-1.2, -0.7, 0.9, 1.0), (1.2, -0.7, 0.9, 1.0), (1.2, 0.7, 0.9, 1.0), (-1.2, 0.7, 0.9, 1.0)], [(0, 1, 2), (0, 2, 3)],
+                    [(0.0, 0.0), (4.0, 0.0), (4.0, 2.0), (0.0, 2.0)])
+    scene.d3_static.append(fin(sheet, 1).repeat_mode(RepeatMode.RepeatXY).shader(holes))
+    scene.d3_static.append(fin(Batch3D.from_box(0.8, -0.45, -0.45, 0.9, 0.9, 0.9), 0).shader(7))   # no such program: nothing runs
+    # one chunk: a wall shaded by the chunk's own program 0, a wall whose program 1 was baked into a texture,
+    # and a pane in the opacity pass with program 2
+    ch = Chunk((-4, -4), 8)
+    ch.shaders = [shader_control_flow(emissive), shader_wood(), shader_glass_tint()]
+    ch.shader_textures = [None, tex_brick(SEED + 77, (90, 140, 60)), None]
+    ch.batches3d.append(fin(_quads_batch([_wall_quad(-2.5, -1.5, 2.5, -1.5, 2.0)]), 1).repeat_mode(RepeatMode.RepeatXY).shader(0))
+    ch.batches3d.append(fin(_quads_batch([_wall_quad(2.5, -1.5, 2.5, 1.5, 2.0)]), 1).repeat_mode(RepeatMode.RepeatXY).shader(1))
+    ch.batches3d_opacity.append(fin(_quads_batch([_wall_quad(-2.4, 1.4, -2.4, -1.4, 1.5)]), 3).repeat_mode(RepeatMode.RepeatXY).shader(2))
+    scene.chunks[(0, 0)] = ch
+    scene.d2_static.append(Batch2D.from_rectangle(8.0, 8.0, 120.0, 90.0).source(PixelSource.StaticTileIndex(0)).shader(scan))
+    scene.d2_static.append(Batch2D.from_rectangle(100.0, 60.0, 60.0, 60.0).source(PixelSource.StaticTileIndex(3)).shader(scan))
+    scene.lights = [_example_light(),
+                    Light.new(LightType.Point).with_color([0.6, 0.7, 1.0]).with_intensity(1.2).with_start_distance(1.0).with_end_distance(6.0)
+                    .with_position([-1.5, 1.2, 2.0]).compile()]
+    scene.background_(VGrayGradientShader())
+    return scene
+
+
+def shaded_config(width=640, height=480, tile_size=40, n_frames=16, emissive=False) -> Config:
+    assets = map_assets(256)
+    assets.palette = [(0.1, 0.1, 0.1), None, (0.9, 0.7, 0.3), (0.2, 0.8, 0.4)]
+
+    def cams(i):
+        cam = D3OrbitCamera.new()
+        cam.set_parameter_f32("distance", 3.2)
+        cam.azimuth = math.pi / 2 + 2.0 * math.pi * i / n_frames * 0.35 - 0.3
+        return cam
+    cfg = Config("shaded", shaded_scene(emissive=emissive), assets, width, height, tile_size, SampleMode.Nearest, (0.25, 0.25, 0.3, 1.0), cams(0),
+                 cameras=cams, n_frames=n_frames)
+    cfg.time = 1.25
+    return cfg
+
+
+BUILDERS["shaded"] = lambda **kw: shaded_config(**kw)

@@ -165,6 +165,7 @@ class Assets:
         # src/server/assets.rs:28,34: id -> IndexMap<String, Tile>; here id -> list of (name, Tile)
         self.entity_tiles: dict = {}
         self.item_tiles: dict = {}
+        self.palette: list = []   # assets.palette.colors (src/server/assets.rs:40): None or (r, g, b) in 0..1
         self._generation = 0
         self._uid = next(_UIDS)  # device-cache identity (id() can be reused after garbage collection)
 
@@ -495,6 +496,12 @@ class Scene:
         self.d2_dynamic: List[Batch2D] = []
         self.dynamic_textures: List[Tile] = []
         self.chunks: dict = {}  # (x, y) -> Chunk, iterated in insertion order (src/scene.rs:46)
+        self.shaders: list = []            # src/scene.rs:42-43: rusterix_b200.vm.Program per add_shader
+        self.shaders_with_opacity: List[bool] = []
+        # the VM's pattern banks (rusteria/src/textures/patterns.rs:88-102) as (width, height, float32[h*w,3]); the
+        # reference computes them once per process, the host passes them along with the scene
+        self.patterns: list = []
+        self.patterns_normal: list = []
         self.animation_frame = 0
         self._generation = 0
         self._uid = next(_UIDS)  # device-cache identity (id() can be reused after garbage collection)
@@ -519,6 +526,17 @@ class Scene:
     def lights_(self, lights: List[CompiledLight]) -> "Scene":
         self.lights = list(lights)
         return self
+
+    def add_shader(self, program) -> Optional[int]:
+        """src/scene.rs:108-133.  The reference compiles Rusteria source; the compiler stays on the host, so this
+        mirror takes its output, a rusterix_b200.vm.Program."""
+        if program is None:
+            return None
+        index = len(self.shaders)
+        self.shaders_with_opacity.append(program.shader_supports_opacity())
+        self.shaders.append(program)
+        self._generation += 1
+        return index
 
     def anim_tick(self):  # src/scene.rs:147-150
         self.animation_frame = (self.animation_frame + 1) & 0xFFFFFFFFFFFFFFFF
@@ -579,6 +597,8 @@ class Chunk:
         self.terrain_texture: Optional[Texture] = None
         self.lights: List[CompiledLight] = []
         self.occluded_sectors: List[tuple] = []  # (BBox, occlusion)
+        self.shaders: list = []                  # src/chunk.rs: programs batch.shader indexes for this chunk's batches
+        self.shader_textures: list = []          # Option<Texture> per shader: a baked result used instead of the program
 
     @staticmethod
     def new(origin, size) -> "Chunk":

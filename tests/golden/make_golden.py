@@ -27,6 +27,9 @@ CASES = {
     "chunked_320x180_f0": lambda: (scenes.chunked_config(320, 180, 40), 0),
     "chunked_320x180_f5": lambda: (scenes.chunked_config(320, 180, 40), 5),
     "game2d_240x160": lambda: (scenes.game2d_config(240, 160), 0),
+    # Rusteria VM programs on batches (the pixel digests also pin this image's libm: sin, pow, ...)
+    "shaded_320x240_f0": lambda: (scenes.shaded_config(320, 240, 40), 0),
+    "shaded_320x240_f9": lambda: (scenes.shaded_config(320, 240, 40), 9),
 }
 
 

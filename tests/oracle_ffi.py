@@ -46,14 +46,65 @@ def load():
         lib.rxo_shade_fast_brdf.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.rxo_mat4_mul_vec4.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         lib.rxo_hardware_threads.restype = C.c_uint32
+        lib.rxo_set_programs.restype = C.c_int32
+        lib.rxo_set_programs.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_uint32, C.POINTER(_abi.rxc_pattern), C.c_uint32,
+                                         C.POINTER(_abi.rxc_pattern), C.c_uint32, C.c_void_p, C.c_uint32]
+        lib.rxo_vm_execute.restype = C.c_uint32
+        lib.rxo_vm_execute.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         _lib = lib
     return _lib
+
+
+def set_programs(scene, assets=None):
+    """Hands the oracle the op TREES of the scene's programs (scene.shaders, then every chunk's) plus the
+    pattern banks and the palette; rasterize() calls it before every frame."""
+    lib = load()
+    programs = list(scene.shaders)
+    for chunk in scene.chunks.values():
+        programs += list(chunk.shaders)
+    trees = [p.encode_tree() for p in programs]
+    ptrs = (C.c_void_p * max(1, len(trees)))(*[t.ctypes.data for t in trees])
+    lens = np.array([len(t) for t in trees] + [0], dtype=np.uint32)
+
+    def bank(b):
+        arr = (_abi.rxc_pattern * max(1, len(b)))()
+        keep = []
+        for i, (w, h, data) in enumerate(b):
+            d = np.ascontiguousarray(np.asarray(data, dtype=np.float32).reshape(h * w, 3))
+            keep.append(d)
+            arr[i].data, arr[i].width, arr[i].height = d.ctypes.data, int(w), int(h)
+        return arr, keep
+    pats, k1 = bank(scene.patterns)
+    pats_n, k2 = bank(scene.patterns_normal)
+    pal_src = list(assets.palette) if assets is not None else []
+    palette = np.zeros((max(1, len(pal_src)), 4), dtype=np.float32)
+    for i, col in enumerate(pal_src):
+        if col is not None:
+            palette[i] = [1.0, col[0], col[1], col[2]]
+    st = lib.rxo_set_programs(ptrs, lens.ctypes.data, len(trees), pats, len(scene.patterns), pats_n, len(scene.patterns_normal),
+                              palette.ctypes.data, len(pal_src))
+    assert st == 0 and (k1 is not None) and (k2 is not None)
+
+
+def set_vm_state_mode(per_fragment: bool):
+    """False (default): the reference's per-tile Execution that is never reset; True: the device's documented
+    deviation, a fresh Execution per fragment."""
+    load().rxo_set_vm_state_mode(1 if per_fragment else 0)
+
+
+def vm_execute(program: int, records):
+    lib = load()
+    rec = np.ascontiguousarray(records, dtype=np.float32).reshape(-1, 18)
+    out = np.zeros((len(rec), 24), dtype=np.float32)
+    faults = lib.rxo_vm_execute(int(program), len(rec), rec.ctypes.data, out.ctypes.data)
+    return out, int(faults)
 
 
 def rasterize(rast, scene, assets, width, height, tile_size, want_planes=True, n_threads=0, index_bytes=4):
     """Run the oracle on the same host objects the product API takes.  Returns (pixels[h,w,4],
     owner[h,w] or None, depth[h,w] or None)."""
     lib = load()
+    set_programs(scene, assets)
     tiles = marshal.marshal_tiles(assets.tile_list)
     sc = marshal.marshal_scene(scene, index_bytes, assets)
     mm = marshal.marshal_mapmini(rast.mapmini)

@@ -362,6 +362,6 @@ def test_k10_alpha_tested_fragment_does_not_write_depth():
 
 def test_oracle_rejects_what_the_product_rejects():
     cfg = scenes.cube(32, 32, 16, logo_size=8)
-    cfg.scene.d3_static[0].shader(0)
+    cfg.scene.d3_static[0].source(PixelSource.StaticTileIndex(5))   # past assets.tile_list: the reference panics
     with pytest.raises(RuntimeError):
         oracle_ffi.rasterize(cfg.rasterizer(), cfg.scene, cfg.assets, 32, 32, 16)

@@ -200,12 +200,7 @@ def test_errors_do_not_unwind():
     with pytest.raises(RxcError) as e:
         render_gpu(cfg.rasterizer(), cfg.scene, cfg.assets, 64, 64, 40)
     assert e.value.status == -5
-    cfg.scene.d3_static[0].source(PixelSource.StaticTileIndex(0)).shader(0)
-    cfg.scene.mark_dirty()
-    with pytest.raises(RxcError) as e:
-        render_gpu(cfg.rasterizer(), cfg.scene, cfg.assets, 64, 64, 40)
-    assert e.value.status == -3
-    cfg.scene.d3_static[0].shader_ = None
+    cfg.scene.d3_static[0].source(PixelSource.StaticTileIndex(0))
     cfg.scene.mark_dirty()
     with pytest.raises(ValueError):  # the reference panics on a short slice (src/rasterizer.rs:572)
         cfg.rasterizer().rasterize(cfg.scene, np.zeros(10, np.uint8), 64, 64, 40, cfg.assets)
@@ -271,3 +266,99 @@ def test_game2d_preserve_transparency_and_background():
     cfg = scenes.game2d_config(640, 480)
     cfg.scene.background = VGrayGradientShader()
     _run(cfg, 0, preserve_transparency=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# batch shaders: the Rusteria VM on the device
+# ------------------------------------------------------------------------------------------------
+import oracle_ffi
+import vm_programs
+from rusterix_b200 import Assets, DeviceContext
+from rusterix_b200 import vm as rvm
+
+# ops whose results go through libm (sin, cos, tan, atan, atan2, pow, ln, sincos): CUDA and glibc agree to a few ulp
+_LIBM_PROGRAMS = {"libm", "wood", "control_flow", "glass", "scanlines"}
+
+
+def _vm_scene():
+    progs = vm_programs.all_programs()
+    s = Scene()
+    s.patterns, s.patterns_normal = scenes.pattern_bank(), scenes.pattern_bank()[:3]
+    for p in progs.values():
+        s.add_shader(p)
+    a = Assets.default().textures([])
+    a.palette = vm_programs.PALETTE
+    return progs, s, a
+
+
+@pytest.mark.parametrize("name", list(vm_programs.all_programs()))
+def test_vm_device_matches_oracle_interpreter(name):
+    """Every NodeOp, on 4096 random Execution states: the device runs the flat code, the oracle walks the tree."""
+    progs, scene, assets = _vm_scene()
+    ctx = DeviceContext.get(0)
+    ctx.upload(scene, assets)
+    oracle_ffi.set_programs(scene, assets)
+    recs = vm_programs.records(4096, seed=11)
+    k = list(progs).index(name)
+    got, faults = ctx.vm_execute(k, recs)
+    want, ofaults = oracle_ffi.vm_execute(k, recs)
+    assert faults == 0 and ofaults == 0
+    if name in _LIBM_PROGRAMS:
+        np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-5)
+    else:
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), np.abs(got - want).max()
+
+
+def test_vm_device_limits_are_reported():
+    """A program that overflows the 32-entry value stack: rxc_vm_execute counts the fault, rasterize returns an error."""
+    from rusterix_b200 import RxcError
+    deep = [("Push", (1.0, 1.0, 1.0))] * 40 + [("Add",)] * 39 + [("SetColor",)]
+    s = Scene()
+    s.add_shader(rvm.Program([deep], 0, 0, 0))
+    a = Assets.default().textures([])
+    ctx = DeviceContext.get(0)
+    ctx.upload(s, a)
+    _, faults = ctx.vm_execute(0, vm_programs.records(8))
+    assert faults == 8
+    cfg = scenes.cube(64, 64, 40, logo_size=16)
+    cfg.scene.add_shader(rvm.Program([deep], 0, 0, 0))
+    cfg.scene.d3_static[0].shader(0)
+    with pytest.raises(RxcError) as e:
+        render_gpu(cfg.rasterizer(), cfg.scene, cfg.assets, 64, 64, 40)
+    assert e.value.status == -3
+    cfg2 = scenes.cube(64, 64, 40, logo_size=16)
+    render_gpu(cfg2.rasterizer(), cfg2.scene, cfg2.assets, 64, 64, 40)  # the context is still usable
+
+
+@pytest.mark.parametrize("frame", [0, 5, 11])
+def test_shaded_scene_parity(frame):
+    """Programs on opaque 3D batches (incl. one that cuts holes through `opacity`), on a chunk's batches (its own
+    program list, a baked shader texture), on an opacity-pass pane and on 2D batches."""
+    cfg = scenes.shaded_config(640, 480, 40)
+    st = _run(cfg, frame=frame)
+    assert st["within1_frac"] > 0.999
+
+
+def test_shaded_scene_linear_odd_size():
+    cfg = scenes.shaded_config(501, 333, 64)
+    cfg.sample_mode = SampleMode.Linear
+    _run(cfg, frame=3)
+
+
+def test_shaded_scene_is_tile_size_invariant_on_the_device():
+    """Per-fragment Execution state: unlike the reference, the frame cannot depend on tile_size."""
+    cfg = scenes.shaded_config(320, 240, 40)
+    a = render_gpu(cfg.rasterizer(2), cfg.scene, cfg.assets, 320, 240, 16)
+    b = render_gpu(cfg.rasterizer(2), cfg.scene, cfg.assets, 320, 240, 240)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_shaded_scene_with_emissive_against_per_fragment_oracle():
+    """A program that writes `emissive` on one path only.  The reference leaks the value into later fragments of the
+    tile; the device does not, so this frame is checked against the oracle in per-fragment-state mode."""
+    cfg = scenes.shaded_config(480, 360, 40, emissive=True)
+    oracle_ffi.set_vm_state_mode(True)
+    try:
+        _run(cfg, frame=1)
+    finally:
+        oracle_ffi.set_vm_state_mode(False)
