@@ -306,6 +306,23 @@ typedef struct rxc_frame {
     uint32_t matvec_mode;         /* RXC_MATVEC_* */
     uint32_t band_y0;             /* multi-GPU band split: render rows [band_y0, band_y1);   */
     uint32_t band_y1;             /* both 0 = whole frame. `pixels` then holds only the band */
+    /* Render graph (src/rasterizer.rs:227-253, :419-461; src/shapestack/shapefx.rs:935-1223).  The graph stays
+     * on the host: it runs collect_nodes_from / render_setup / render_ambient_color (the latter lands in
+     * `ambient`) and passes what the per-pixel code reads. */
+    uint32_t has_sun;             /* self.sun_dir.is_some(): directional sun in the lighting block (:1342-1361) */
+    float sun_dir[3];
+    float day_factor;
+    uint32_t has_sky;             /* a Sky node is among render_miss: render_miss_d3 (shapefx.rs:1122-1223) colours
+                                     the pixels no geometry covered; the last Sky node wins, so one is passed */
+    float sky[6][4];              /* its `precomputed`: (sun_dir, day_factor), haze, day_horizon, day_zenith,
+                                     night_horizon, night_zenith (shapefx.rs:1016-1055)                       */
+    uint32_t sky_clouds;          /* 1 = the node's cloud layer (shapefx.rs:1172-1219), which needs noiselib 0.2.4's
+                                     perlin_noise_2d (not vendored with the reference): RXC_ERR_UNSUPPORTED.
+                                     0 = the host asks for the sky without the cloud layer                  */
+    uint32_t has_brush_preview;   /* self.brush_preview (src/rasterizer.rs:13-17, :434-456)                 */
+    float brush_position[3];
+    float brush_radius;
+    float brush_falloff;
 } rxc_frame;
 
 /* Counters filled by rxc_get_stats; times are device times from CUDA events (profiling on). */

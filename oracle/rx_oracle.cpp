@@ -947,6 +947,67 @@ struct Raster {
         return {ws.x, ws.y, ws.z};
     }
 
+    // src/rasterizer.rs:1844-1870
+    void screen_ray(float x, float y, V3* origin, V3* dir) const {
+        float ndc_x = 2.0f * (x / width) - 1.0f;
+        float ndc_y = 1.0f - 2.0f * (y / height);
+        V4 vn = mat4_mul_vec4(inverse_projection, {ndc_x, ndc_y, -1.0f, 1.0f}, f->matvec_mode);
+        V4 vf = mat4_mul_vec4(inverse_projection, {ndc_x, ndc_y, 1.0f, 1.0f}, f->matvec_mode);
+        vn = {vn.x / vn.w, vn.y / vn.w, vn.z / vn.w, vn.w / vn.w};
+        vf = {vf.x / vf.w, vf.y / vf.w, vf.z / vf.w, vf.w / vf.w};
+        V4 wn = mat4_mul_vec4(inverse_view, vn, f->matvec_mode);
+        V4 wf = mat4_mul_vec4(inverse_view, vf, f->matvec_mode);
+        *origin = {wn.x, wn.y, wn.z};
+        *dir = normalized(V3{wf.x, wf.y, wf.z} - *origin);
+    }
+    // vek Vec4::lerp: clamped factor, mul_add (see shade_fast_brdf)
+    static float lerp1(float from, float to, float t) { return std::fmaf(rclamp(t, 0.0f, 1.0f), to - from, from); }
+    // ShapeFX Sky render_miss_d3, src/shapestack/shapefx.rs:1122-1170 (the cloud layer :1172-1219 needs noiselib:
+    // frames that ask for it are rejected by validate())
+    void render_miss_sky(V4& color, V3 dir) const {
+        const float* sun = f->sky[0];
+        const float* haze_color = f->sky[1];
+        const float *day_h = f->sky[2], *day_z = f->sky[3], *night_h = f->sky[4], *night_z = f->sky[5];
+        float day_factor = sun[3];
+        float up = rclamp(dir.y, -1.0f, 1.0f);
+        float t = (up + 1.0f) * 0.5f;
+        float c[4];
+        for (int i = 0; i < 4; ++i) c[i] = lerp1(lerp1(night_h[i], night_z[i], t), lerp1(day_h[i], day_z[i], t), day_factor);
+        float om = 1.0f - up;
+        float haze = om * om * om;  // powi(3)
+        for (int i = 0; i < 4; ++i) {
+            float fog = haze_color[i] * haze * 0.3f;
+            c[i] = c[i] * (1.0f - haze * 0.2f) + fog;
+        }
+        if (day_factor > 0.0f) {
+            float d = rclamp(dot(dir, V3{sun[0], sun[1], sun[2]}), -1.0f, 1.0f);
+            float dist = rmax(1.0f - d, 0.0f);
+            if (dist < 0.04f) {
+                float k = 1.0f - dist / 0.04f;
+                float glare = k * k * (3.0f - 2.0f * k);
+                const float g[4] = {1.0f, 0.85f, 0.6f, 0.0f};
+                for (int i = 0; i < 4; ++i) c[i] += g[i] * glare * day_factor;
+            }
+        }
+        color = {c[0], c[1], c[2], c[3]};
+    }
+    // src/rasterizer.rs:434-456
+    void brush_preview(V4& color, V3 origin, V3 dir) const {
+        if (!(std::fabs(dir.y) > 1e-5f)) return;
+        float t = -origin.y / dir.y;
+        if (!(t > 0.0f)) return;
+        V3 world = origin + dir * t;
+        float dist = magnitude(world - V3{f->brush_position[0], f->brush_position[1], f->brush_position[2]});
+        if (!(dist < f->brush_radius)) return;
+        float normalized_d = dist / f->brush_radius;
+        float falloff = rclamp(f->brush_falloff, 0.001f, 1.0f);
+        float fade = rclamp((1.0f - normalized_d) / falloff, 0.0f, 1.0f);
+        float blend = 0.2f + 0.6f * fade;
+        color.x = rmin(color.x * (1.0f - blend) + blend, 1.0f);
+        color.y = rmin(color.y * (1.0f - blend) + blend, 1.0f);
+        color.z = rmin(color.z * (1.0f - blend) + blend, 1.0f);
+    }
+
     // src/rasterizer.rs:1754-1773 (and :1731-1750, same arithmetic on [f32;2])
     static void barycentric_weights(float ax, float ay, float bx, float by, float cx, float cy, float px, float py,
                                     float w[3]) {
@@ -1168,7 +1229,12 @@ struct Raster {
                             V3 kd = mat_base * (1.0f - mat_metallic) * (1.0f - 0.04f);
                             lit = lit + V3{f->ambient[0], f->ambient[1], f->ambient[2]} * kd * hemi;
                         }
-                        // sun_dir is None without a render graph (:1342)
+                        if (f->has_sun && f->day_factor > 0.0f) {  // :1342-1361 directional sun
+                            V3 ldir = normalized(-V3{f->sun_dir[0], f->sun_dir[1], f->sun_dir[2]});
+                            float r = rmax(f->day_factor, 0.0f);
+                            lit = lit + shade_fast_brdf(mat_base, mat_roughness, mat_metallic, {0, 0, 0}, normal,
+                                                        normalized(camera_pos - world), ldir, {r, r, r});
+                        }
                         lit.x *= occlusion; lit.y *= occlusion; lit.z *= occlusion;
                     }
                     float hemi = 0.5f * (normal.y + 1.0f);  // :1368-1370
@@ -1470,9 +1536,16 @@ struct Raster {
                 if (s.b->pass == RXC_PASS_CHUNK_OPACITY) d3_rasterize_opacity(buffer_opacity, z_buffer_opacity, surface_id, tile, s, execution);
                 else d3_rasterize(buffer, z_buffer, owner, surface_id, tile, s, execution);
             }
-            for (size_t i = 0; i < z_buffer.size(); ++i) {  // :409-461 (no render graph, no brush preview)
+            for (size_t i = 0; i < z_buffer.size(); ++i) {  // :409-461
                 if (z_buffer[i] == 1.0f) {
                     V4 color = {0.0f, 0.0f, 0.0f, 1.0f};
+                    const size_t tx = i % tile.width, ty = i / tile.width;
+                    if (f->has_sky || f->has_brush_preview) {
+                        V3 origin, dir;
+                        screen_ray((float)(tile.x + tx), (float)(tile.y + ty), &origin, &dir);
+                        if (f->has_sky) render_miss_sky(color, dir);
+                        if (f->has_brush_preview) brush_preview(color, origin, dir);
+                    }
                     vec4_to_pixel(color, &buffer[i * 4]);
                 }
                 if (z_buffer_opacity[i] < 1.0f && z_buffer[i] > z_buffer_opacity[i]) {  // :464-495
@@ -1510,6 +1583,7 @@ uint32_t hash_u32(uint32_t seed) {  // src/rasterizer.rs:199-207
 
 int32_t validate(const rxc_tile* tiles, uint32_t n_tiles, const rxc_scene* scene, const rxc_frame* f) {
     if (!scene || !f || f->width == 0 || f->height == 0 || f->tile_size == 0) return RXC_ERR_INVALID;
+    if (f->has_sky && f->sky_clouds) return RXC_ERR_UNSUPPORTED;  // noiselib's perlin_noise_2d is not available
     (void)tiles;
     for (uint32_t i = 0; i < scene->n_batches3d; ++i) {
         const rxc_batch3d& b = scene->batches3d[i];

@@ -193,6 +193,16 @@ class rxc_frame(C.Structure):
         ("matvec_mode", C.c_uint32),
         ("band_y0", C.c_uint32),
         ("band_y1", C.c_uint32),
+        ("has_sun", C.c_uint32),
+        ("sun_dir", C.c_float * 3),
+        ("day_factor", C.c_float),
+        ("has_sky", C.c_uint32),
+        ("sky", (C.c_float * 4) * 6),
+        ("sky_clouds", C.c_uint32),
+        ("has_brush_preview", C.c_uint32),
+        ("brush_position", C.c_float * 3),
+        ("brush_radius", C.c_float),
+        ("brush_falloff", C.c_float),
     ]
 
 

@@ -383,6 +383,18 @@ int32_t fill_frame(rxc_ctx* ctx, const rxc_frame& f, DFrame* d) {
     if (f.has_matrix2d) { d->trans2d[0] = f.matrix2d[6]; d->trans2d[1] = f.matrix2d[7]; d->scale2d = f.matrix2d[0]; }
     d->animation_frame = f.animation_frame;
     d->time = f.time;
+    if (f.has_sky && f.sky_clouds)
+        return fail(ctx, RXC_ERR_UNSUPPORTED, "the Sky node's cloud layer needs noiselib's perlin_noise_2d (not vendored with the reference); pass sky_clouds = 0");
+    if (f.has_sun && f.day_factor > 0.0f) {   // rasterizer.rs:1342-1347
+        d->sun_radiance = std::fmax(f.day_factor, 0.0f);
+        const float m = std::sqrt(f.sun_dir[0] * f.sun_dir[0] + f.sun_dir[1] * f.sun_dir[1] + f.sun_dir[2] * f.sun_dir[2]);
+        for (int k = 0; k < 3; ++k) d->sun_l[k] = -f.sun_dir[k] / m;
+    }
+    d->has_sky = f.has_sky ? 1u : 0u;
+    memcpy(d->sky, f.sky, sizeof(d->sky));
+    d->has_brush = f.has_brush_preview ? 1u : 0u;
+    memcpy(d->brush_pos, f.brush_position, 12);
+    d->brush_radius = f.brush_radius; d->brush_falloff = f.brush_falloff;
     {   // screen_to_world (rasterizer.rs:1707-1727) as one projective map of (px+.5, py+.5, z, 1), in double
         double IP[4][4], IV[4][4], G[4][4], N[4][4] = {{2.0 / f.width, 0, 0, -1.0}, {0, -2.0 / f.height, 0, 1.0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
         for (int r = 0; r < 4; ++r)

@@ -222,7 +222,13 @@ struct DFrame {
     // (hx,hy,hz,hw) = s2w * (px+.5, py+.5, z, 1), world = (hx,hy,hz)/hw.  Row-major 4x4.
     float s2w[16];
     float time;                   // Rasterizer.time (VM `time`)
-    uint32_t pad_t[3];
+    // render graph results (rxc_frame: sun, Sky node, brush preview)
+    float sun_radiance;           // max(day_factor, 0) when the sun lights the frame, else 0 (rasterizer.rs:1342-1347)
+    float sun_l[3];               // (-sun_dir).normalized()
+    uint32_t has_sky, has_brush;
+    float sky[6][4];
+    float brush_pos[3], brush_radius, brush_falloff;
+    uint32_t pad_t[1];
 };
 
 // per-frame counters (zeroed by k_frame_setup)

@@ -821,6 +821,8 @@ struct __align__(16) ShadeConst {
     uint32_t has_ambient;
     float ambient[3];
     uint32_t n_lights;
+    float sun_l[3];          // unit vector towards the sun
+    float sun_radiance;      // 0 = no sun
 };
 #define RX_SMEM_LIGHTS 16   // lights of the frame staged in shared memory (more: read from global memory)
 
@@ -1004,17 +1006,28 @@ __device__ __forceinline__ uint32_t shade_owner(const SceneDev& S, const ShadeCo
     const f3 kd = {kd_lut[texel & 0xFFu], kd_lut[(texel >> 8) & 0xFFu], kd_lut[(texel >> 16) & 0xFFu]};
     const float hemi = __fmaf_rn(0.5f, normal.y, 0.5f);
     f3 amb = {d1.x, d1.y, d1.z};                                                        // :1368-1370
-    if (K.has_ambient) {  // :1327-1365: the sky term is scaled by the sector occlusion (0 when it is not > 0)
-        float occ = 1.0f;
-        if (S.n_sectors) { const float o = sector_occlusion(S, __float_as_int(d1.w), world.x, world.z); occ = o > 0.0f ? o : 0.0f; }
-        amb = {__fmaf_rn(ka.x, occ, amb.x), __fmaf_rn(ka.y, occ, amb.y), __fmaf_rn(ka.z, occ, amb.z)};
-    }
+    const float4 ks = *reinterpret_cast<const float4*>(&K.sun_l[0]);
+    float occ = 1.0f;  // :1327-1365: the sky and sun terms are scaled by the sector occlusion (0 when it is not > 0)
+    if ((K.has_ambient || ks.w > 0.0f) && S.n_sectors) { const float o = sector_occlusion(S, __float_as_int(d1.w), world.x, world.z); occ = o > 0.0f ? o : 0.0f; }
+    if (K.has_ambient) amb = {__fmaf_rn(ka.x, occ, amb.x), __fmaf_rn(ka.y, occ, amb.y), __fmaf_rn(ka.z, occ, amb.z)};
     f3 lit = {amb.x * kd.x * hemi, amb.y * kd.y * hemi, amb.z * kd.z * hemi};
 
     const float n_dot_v = fmaxf(fdot3(normal, view_dir), 0.0f);
     const float om = 1.0f - fminf(n_dot_v, 1.0f);
     const float om2 = om * om;
     const float fr = __fmaf_rn(1.0f - 0.04f, om2 * om2 * om, 0.04f);  // schlick_fresnel with f0 = 0.04 (:1882-1887)
+    if (ks.w > 0.0f) {  // directional sun, rasterizer.rs:1342-1361
+        const f3 ldir = {ks.x, ks.y, ks.z};
+        const float n_dot_l = fmaxf(fdot3(normal, ldir), 0.0f);
+        if (n_dot_l > 0.0f) {
+            const f3 h = fnormalize3(rx_add3(ldir, view_dir));
+            const float n_dot_h = fmaxf(fdot3(normal, h), 0.0f);
+            const float h2 = n_dot_h * n_dot_h;
+            const float spec = fr * (h2 * h2 * h2);
+            const float w = n_dot_l * ks.w * occ;
+            lit = {__fmaf_rn(kd.x + spec, w, lit.x), __fmaf_rn(kd.y + spec, w, lit.y), __fmaf_rn(kd.z + spec, w, lit.z)};
+        }
+    }
     const uint32_t n_lights = __float_as_uint(ka.w);
     for (uint32_t li = 0; li < n_lights; ++li) {  // rasterizer.rs:1373-1391
         const DLight& L = lights[li];
@@ -1136,6 +1149,9 @@ __device__ __noinline__ uint32_t shade_owner_vm(const SceneDev& S, const DFrame&
     const f3 kd = rx_scale3(rx_scale3(base, 1.0f - metal), 1.0f - 0.04f);
     if (occlusion > 0.0f) {
         if (F.has_ambient) lit = rx_add3(lit, rx_scale3(rx_mul3({F.ambient[0], F.ambient[1], F.ambient[2]}, kd), hemi));
+        if (F.sun_radiance > 0.0f)  // :1342-1361
+            lit = rx_add3(lit, shade_brdf_exact(base, rough, metal, normal, rx_normalize3({F.cam[0] - world.x, F.cam[1] - world.y, F.cam[2] - world.z}),
+                                                {F.sun_l[0], F.sun_l[1], F.sun_l[2]}, {F.sun_radiance, F.sun_radiance, F.sun_radiance}));
         lit = {lit.x * occlusion, lit.y * occlusion, lit.z * occlusion};
     }
     lit = rx_add3(lit, rx_scale3(rx_mul3({FB.sd_ambient[0], FB.sd_ambient[1], FB.sd_ambient[2]}, kd), hemi));
@@ -1219,6 +1235,61 @@ __device__ __forceinline__ uint32_t blend_opacity(uint32_t src, uint32_t dst, bo
     }
     const float out_a = !preserve_transparency ? 1.0f : rx_clamp(src_a + dst_a * inv_a, 0.0f, 1.0f);
     return out | (rx_as_u8(rx_clamp(out_a * 255.0f, 0.0f, 255.0f)) << 24);
+}
+
+// A pixel no geometry covered when a Sky node or a brush preview is active (rasterizer.rs:409-461): screen_ray
+// (:1844-1870), ShapeFX Sky render_miss_d3 without its cloud layer (shapefx.rs:1122-1170), brush preview (:434-456).
+__device__ __noinline__ uint32_t miss_color(const DFrame* __restrict__ Fp, int px, int py) {
+    const DFrame& F = *Fp;
+    const float x = (float)px, y = (float)py;   // the reference passes the pixel corner here, not its centre
+    const float ndc_x = 2.0f * (x / F.width_f) - 1.0f, ndc_y = 1.0f - 2.0f * (y / F.height_f);
+    f4 vn = rx_matvec4(F.inv_proj, {ndc_x, ndc_y, -1.0f, 1.0f}, F.matvec_mode);
+    f4 vf = rx_matvec4(F.inv_proj, {ndc_x, ndc_y, 1.0f, 1.0f}, F.matvec_mode);
+    vn = {vn.x / vn.w, vn.y / vn.w, vn.z / vn.w, vn.w / vn.w};
+    vf = {vf.x / vf.w, vf.y / vf.w, vf.z / vf.w, vf.w / vf.w};
+    const f4 wn = rx_matvec4(F.inv_view, vn, F.matvec_mode), wf = rx_matvec4(F.inv_view, vf, F.matvec_mode);
+    const f3 origin = {wn.x, wn.y, wn.z};
+    const f3 dir = rx_normalize3({wf.x - wn.x, wf.y - wn.y, wf.z - wn.z});
+    float c[4] = {0.0f, 0.0f, 0.0f, 1.0f};
+    auto lerp1 = [](float from, float to, float t) { return __fmaf_rn(rx_clamp(t, 0.0f, 1.0f), to - from, from); };  // vek lerp
+    if (F.has_sky) {
+        const float day_factor = F.sky[0][3];
+        const float up = rx_clamp(dir.y, -1.0f, 1.0f);
+        const float t = (up + 1.0f) * 0.5f;
+        const float om = 1.0f - up;
+        const float haze = om * om * om;
+        for (int i = 0; i < 4; ++i) {
+            const float v = lerp1(lerp1(F.sky[4][i], F.sky[5][i], t), lerp1(F.sky[2][i], F.sky[3][i], t), day_factor);
+            const float fog = F.sky[1][i] * haze * 0.3f;
+            c[i] = v * (1.0f - haze * 0.2f) + fog;
+        }
+        if (day_factor > 0.0f) {
+            const float d = rx_clamp(rx_dot3(dir, {F.sky[0][0], F.sky[0][1], F.sky[0][2]}), -1.0f, 1.0f);
+            const float dist = fmaxf(1.0f - d, 0.0f);
+            if (dist < 0.04f) {
+                const float k = 1.0f - dist / 0.04f;
+                const float glare = k * k * (3.0f - 2.0f * k);
+                c[0] += 1.0f * glare * day_factor; c[1] += 0.85f * glare * day_factor; c[2] += 0.6f * glare * day_factor;
+                c[3] += 0.0f * glare * day_factor;
+            }
+        }
+    }
+    if (F.has_brush && fabsf(dir.y) > 1e-5f) {
+        const float t = -origin.y / dir.y;
+        if (t > 0.0f) {
+            const f3 world = {origin.x + dir.x * t, origin.y + dir.y * t, origin.z + dir.z * t};
+            const f3 dv = {world.x - F.brush_pos[0], world.y - F.brush_pos[1], world.z - F.brush_pos[2]};
+            const float dist = sqrtf(rx_dot3(dv, dv));
+            if (dist < F.brush_radius) {
+                const float nd = dist / F.brush_radius;
+                const float fade = rx_clamp((1.0f - nd) / rx_clamp(F.brush_falloff, 0.001f, 1.0f), 0.0f, 1.0f);
+                const float blend = 0.2f + 0.6f * fade;
+                for (int i = 0; i < 3; ++i) c[i] = fminf(c[i] * (1.0f - blend) + blend, 1.0f);
+            }
+        }
+    }
+    return rx_f32_to_u8_saturated(c[0]) | (rx_f32_to_u8_saturated(c[1]) << 8) | (rx_f32_to_u8_saturated(c[2]) << 16) |
+           (rx_f32_to_u8_saturated(c[3]) << 24);
 }
 
 // src/shader/vgradient.rs:11-14 and src/shader/grid.rs:36-108
@@ -1565,6 +1636,8 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
             else if (tid == 19) s_k.has_ambient = F.has_ambient;
             else if (tid < 23) s_k.ambient[tid - 20] = F.ambient[tid - 20];
             else if (tid == 23) s_k.n_lights = S.n_lights;
+            else if (tid < 27) s_k.sun_l[tid - 24] = F.sun_l[tid - 24];
+            else if (tid == 27) s_k.sun_radiance = F.sun_radiance;
             for (uint32_t i = tid; i < min(S.n_lights, (uint32_t)RX_SMEM_LIGHTS) * (uint32_t)(sizeof(DLight) / 4); i += RX_TILE_THREADS)
                 reinterpret_cast<uint32_t*>(s_lights)[i] = __ldg(reinterpret_cast<const uint32_t*>(lights_g) + i);
             if (!GENERAL) {  // large-triangle records of the frame
@@ -1671,6 +1744,7 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                         color = shade_owner(S, s_k, lights, s_kd, fbs[b], shade + owner, st.z, st.w, st.x, fpx, fpy, smode);
                 } else {
                     color = 0xFF000000u;  // vec4_to_pixel((0,0,0,1))
+                    if (F.has_sky | F.has_brush) color = miss_color(&F, px, py);
                 }
                 if (GENERAL) {
                     const float2 os = s_ostate[k * RX_TILE_THREADS + tid];

@@ -298,4 +298,20 @@ def make_frame(rast, scene: Scene, width: int, height: int, tile_size: int, band
     f.matvec_mode = int(rast.matvec_mode)
     if band is not None:
         f.band_y0, f.band_y1 = int(band[0]), int(band[1])
+    # render graph results (Rasterizer.prepare_render_graph) and the brush preview
+    if getattr(rast, "sun_dir", None) is not None:
+        f.has_sun = 1
+        f.sun_dir[:] = [float(c) for c in rast.sun_dir]
+        f.day_factor = float(rast.day_factor)
+    sky = [n for n in getattr(rast, "render_miss", []) if getattr(n, "precomputed", None)]
+    if sky:
+        f.has_sky = 1
+        for i, row in enumerate(sky[-1].precomputed):
+            f.sky[i][:] = [float(c) for c in row]
+        f.sky_clouds = 1 if sky[-1].clouds else 0
+    bp = getattr(rast, "brush_preview", None)
+    if bp is not None:
+        f.has_brush_preview = 1
+        f.brush_position[:] = [float(c) for c in bp.position]
+        f.brush_radius, f.brush_falloff = float(bp.radius), float(bp.falloff)
     return f

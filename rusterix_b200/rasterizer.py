@@ -153,7 +153,11 @@ class Rasterizer:
         self.hash_anim = 0
         self.background_color = None
         self.ambient_color = None
-        self.brush_preview = None
+        self.brush_preview = None         # src/rasterizer.rs:50 (BrushPreview)
+        self.render_graph = None          # :56: a types.RenderGraph
+        self.render_miss = []             # :78, rebuilt by every rasterize()
+        self.sun_dir = None               # :86-87
+        self.day_factor = 0.0
         self.mapmini = MapMini.default()  # src/rasterizer.rs:71
         self.preserve_transparency = False
         self.hour = 12.0
@@ -192,8 +196,20 @@ class Rasterizer:
         return self
 
     def _check_supported(self):
-        if self.brush_preview is not None:
-            raise _lib.RxcError(_abi.RXC_ERR_UNSUPPORTED, "brush_preview is not on the device path")
+        pass
+
+    def prepare_render_graph(self):
+        """src/rasterizer.rs:227-253: collect the miss nodes, render_setup them (the last Sky node's sun wins) and
+        let a Sky node replace the ambient colour.  Host-side, like in the reference."""
+        self.render_miss = list(self.render_graph.miss_nodes) if self.render_graph is not None else []
+        for node in self.render_miss:
+            r = node.render_setup(self.hour)
+            if r is not None:
+                self.sun_dir, self.day_factor = r
+        for node in self.render_miss:
+            a = node.render_ambient_color()
+            if a is not None:
+                self.ambient_color = a
 
     def rasterize(self, scene: Scene, pixels, width: int, height: int, tile_size: int, assets: Assets,
                   owner=None, depth=None, band=None, sync=True):
@@ -202,6 +218,7 @@ class Rasterizer:
         tensor on the CPU or on the context's GPU.  `owner` (uint32) / `depth` (float32) are
         optional parity outputs.  `band=(y0,y1)` renders only those rows into a band-sized buffer."""
         self._check_supported()
+        self.prepare_render_graph()
         self.width, self.height = float(width), float(height)
         # "We append the in-scope chunk lights to the dynamic lights" -- on every call, never cleared
         # (src/rasterizer.rs:219-223)
@@ -235,6 +252,7 @@ class Rasterizer:
         frames = (_abi.rxc_frame * n)()
         for i, r in enumerate(rasterizers):
             r._check_supported()
+            r.prepare_render_graph()
             frames[i] = marshal.make_frame(r, scene, width, height, tile_size, band)
         rows = height if band is None else band[1] - band[0]
         return FrameBatch(ctx, frames, n, width * rows * 4)

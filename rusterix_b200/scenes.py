@@ -132,6 +132,9 @@ class Config:
     mapmini: Optional[MapMini] = None
     render_mode: Optional[RenderMode] = None
     time: float = 0.0                       # Rasterizer.time (the VM's `time`)
+    render_graph: Optional[object] = None   # types.RenderGraph
+    hour: float = 12.0
+    brush_preview: Optional[object] = None  # types.BrushPreview
 
     def rasterizer(self, frame: int = 0) -> Rasterizer:
         cam = self.cameras(frame) if self.cameras is not None else self.camera
@@ -144,6 +147,7 @@ class Config:
         if self.render_mode is not None:
             r.render_mode(self.render_mode)
         r.time_ = float(self.time)
+        r.render_graph, r.hour, r.brush_preview = self.render_graph, float(self.hour), self.brush_preview
         return r
 
     def counts(self):
@@ -739,3 +743,36 @@ def shaded_config(width=640, height=480, tile_size=40, n_frames=16, emissive=Fal
 
 
 BUILDERS["shaded"] = lambda **kw: shaded_config(**kw)
+
+
+# ------------------------------------------------------------------------------------------------
+# render graph: Sky node on the pixels nothing covers, directional sun, brush preview
+# ------------------------------------------------------------------------------------------------
+def sky_config(width=640, height=360, tile_size=40, hour=16.5, n_frames=8) -> Config:
+    from .types import BrushPreview, RenderGraph, SkyNode
+    scene = Scene()
+
+    def fin(b, tile):
+        return b.source(PixelSource.StaticTileIndex(tile)).repeat_mode(RepeatMode.RepeatXY).cull_mode(CullMode.Off).with_computed_normals()
+
+    scene.d3_static.append(fin(Batch3D.from_box(-0.5, 0.0, -0.5, 1.0, 1.0, 1.0), 0))
+    scene.d3_static.append(fin(Batch3D.from_box(1.2, 0.0, 0.4, 0.6, 1.8, 0.6), 1))
+    scene.d3_static.append(fin(_quads_batch([_wall_quad(-3.0, -2.0, 3.0, -2.0, 1.5), _wall_quad(-1.5, 1.5, -1.5, 0.2, 1.2)]), 3))  # fences: alpha holes show the sky
+    scene.d3_static.append(fin(_quads_batch([_floor_quad(-2.0, -2.0, 2.5, 2.0)]), 2))
+    scene.lights = [Light.new(LightType.Point).with_color([1.0, 0.8, 0.6]).with_intensity(0.8).with_start_distance(1.0).with_end_distance(5.0)
+                    .with_position([0.5, 1.5, 1.5]).compile()]
+
+    def cams(i):
+        cam = D3OrbitCamera.new()
+        cam.set_parameter_f32("distance", 4.5)
+        cam.azimuth = math.pi / 2 + 2.0 * math.pi * i / n_frames
+        cam.elevation = 0.25 + 0.05 * i
+        return cam
+    cfg = Config("sky", scene, map_assets(128), width, height, tile_size, SampleMode.Nearest, None, cams(0), cameras=cams, n_frames=n_frames)
+    cfg.render_graph = RenderGraph([SkyNode(clouds=False)])
+    cfg.hour = hour
+    cfg.brush_preview = BrushPreview((3.0, 0.0, 1.0), 1.5, 0.6)
+    return cfg
+
+
+BUILDERS["sky"] = lambda **kw: sky_config(**kw)

@@ -648,3 +648,69 @@ class RenderMode:  # src/rendermode.rs:3-52
     def ignore_background_shader(self, v: bool):
         self.ignore_background_shader_ = bool(v)
         return self
+
+
+# ------------------------------------------------------------------------------------------------
+# render graph: what Rasterizer::rasterize reads of it (src/rasterizer.rs:227-253, :419-461)
+# ------------------------------------------------------------------------------------------------
+def _f32(x):
+    return np.float32(x)
+
+
+@dataclass
+class BrushPreview:  # src/rasterizer.rs:13-17
+    position: Sequence[float] = (0.0, 0.0, 0.0)
+    radius: float = 1.0
+    falloff: float = 0.5
+
+
+class SkyNode:
+    """ShapeFX role Sky (src/shapestack/shapefx.rs): render_setup (:970-1057), render_ambient_color (:1086-1120).
+    The per-pixel part, render_miss_d3 (:1122-1223), runs on the device.  `clouds=True` is the reference's
+    behaviour (a noiselib Perlin cloud layer above the horizon), which the device path does not have."""
+
+    def __init__(self, day_horizon=(0.87, 0.80, 0.70, 1.0), day_zenith=(0.36, 0.62, 0.98, 1.0),
+                 night_horizon=(0.03, 0.04, 0.08, 1.0), night_zenith=(0.00, 0.01, 0.05, 1.0), clouds=True):
+        self.day_horizon, self.day_zenith = tuple(day_horizon), tuple(day_zenith)
+        self.night_horizon, self.night_zenith = tuple(night_horizon), tuple(night_zenith)
+        self.clouds = bool(clouds)
+        self.precomputed: list = []
+
+    def render_setup(self, hour: float):
+        h = _f32(hour)
+
+        def smooth(x):   # ((x).clamp(0,2)/2).powi(2) * (3 - 2*(x).clamp(0,2)/2)
+            c = _f32(min(max(x, _f32(0.0)), _f32(2.0)))
+            return _f32(_f32(_f32(c / _f32(2.0)) * _f32(c / _f32(2.0))) * _f32(_f32(3.0) - _f32(_f32(_f32(2.0) * c) / _f32(2.0))))
+        dawn, dusk = smooth(_f32(h - _f32(6.0))), smooth(_f32(_f32(20.0) - h))
+        day_factor = _f32(0.0) if h < 6.0 else dawn if h < 8.0 else _f32(1.0) if h < 18.0 else dusk if h < 20.0 else _f32(0.0)
+        t_day = _f32(min(max(_f32(_f32(h - _f32(6.0)) / _f32(14.0)), _f32(0.0)), _f32(1.0)))
+        theta = _f32(t_day * _f32(np.pi))
+        sun_dir = (float(_f32(np.cos(theta))), float(_f32(np.sin(theta))), 0.0)
+        night, day = np.float32([0.1, 0.1, 0.15, 0.0]), np.float32([0.3, 0.3, 0.35, 0.0])
+        tcl = _f32(min(max(day_factor, _f32(0.0)), _f32(1.0)))
+        haze = [float(_f32(np.float64(tcl) * np.float64(_f32(d - n)) + np.float64(n))) for n, d in zip(night, day)]  # mul_add
+        self.precomputed = [(sun_dir[0], sun_dir[1], sun_dir[2], float(day_factor)), tuple(haze), self.day_horizon, self.day_zenith,
+                            self.night_horizon, self.night_zenith]
+        return sun_dir, float(day_factor)
+
+    def render_ambient_color(self):
+        df = _f32(self.precomputed[0][3])
+        tcl = _f32(min(max(df, _f32(0.0)), _f32(1.0)))
+        out = []
+        for i in range(3):
+            day_avg = _f32(_f32(_f32(self.day_horizon[i]) * _f32(0.5)) + _f32(_f32(self.day_zenith[i]) * _f32(0.5)))
+            night_avg = _f32(_f32(_f32(self.night_horizon[i]) * _f32(0.5)) + _f32(_f32(self.night_zenith[i]) * _f32(0.5)))
+            c = _f32(np.float64(tcl) * np.float64(_f32(day_avg - night_avg)) + np.float64(night_avg))
+            c = max(c, _f32(0.2))
+            out.append(float(_f32(c * _f32(12.92)) if c <= 0.0031308 else _f32(_f32(_f32(1.055) * _f32(np.power(c, _f32(1.0 / 2.4)))) - _f32(0.055))))
+        return (out[0], out[1], out[2], 1.0)
+
+
+class RenderGraph:
+    """The slice of ShapeFXGraph the rasterizer walks: the nodes reachable from the render node's miss terminal.
+    Only Sky nodes act in render_miss_d3; Fog's render_hit_d3 is never called by rasterize() (the hit list is only
+    set up, src/rasterizer.rs:227-233)."""
+
+    def __init__(self, miss_nodes=None):
+        self.miss_nodes: list = list(miss_nodes or [])

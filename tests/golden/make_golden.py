@@ -30,6 +30,9 @@ CASES = {
     # Rusteria VM programs on batches (the pixel digests also pin this image's libm: sin, pow, ...)
     "shaded_320x240_f0": lambda: (scenes.shaded_config(320, 240, 40), 0),
     "shaded_320x240_f9": lambda: (scenes.shaded_config(320, 240, 40), 9),
+    # Sky node miss pass, directional sun, brush preview
+    "sky_320x180_f1": lambda: (scenes.sky_config(320, 180, 40), 1),
+    "sky_320x180_f6_dawn": lambda: (scenes.sky_config(320, 180, 40, hour=7.0), 6),
 }
 
 

@@ -104,6 +104,8 @@ def rasterize(rast, scene, assets, width, height, tile_size, want_planes=True, n
     """Run the oracle on the same host objects the product API takes.  Returns (pixels[h,w,4],
     owner[h,w] or None, depth[h,w] or None)."""
     lib = load()
+    if hasattr(rast, "prepare_render_graph"):
+        rast.prepare_render_graph()   # src/rasterizer.rs:227-253 (host side)
     set_programs(scene, assets)
     tiles = marshal.marshal_tiles(assets.tile_list)
     sc = marshal.marshal_scene(scene, index_bytes, assets)

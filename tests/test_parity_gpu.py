@@ -362,3 +362,30 @@ def test_shaded_scene_with_emissive_against_per_fragment_oracle():
         _run(cfg, frame=1)
     finally:
         oracle_ffi.set_vm_state_mode(False)
+
+
+# ------------------------------------------------------------------------------------------------
+# render graph: Sky node on uncovered pixels, directional sun, brush preview
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("frame,hour", [(0, 16.5), (3, 7.0), (5, 12.0), (6, 22.0)])
+def test_sky_sun_and_brush_preview(frame, hour):
+    cfg = scenes.sky_config(640, 360, 40, hour=hour)
+    st = _run(cfg, frame=frame)
+    assert st["within1_frac"] > 0.999
+
+
+def test_sky_only_every_pixel_is_a_miss():
+    cfg = scenes.sky_config(333, 211, 64, hour=18.5)
+    cfg.scene.d3_static.clear()
+    st = _run(cfg, frame=2)
+    assert st["exact_frac"] > 0.999     # same IEEE arithmetic on both sides, no libm
+
+
+def test_sky_cloud_layer_is_reported_unsupported():
+    from rusterix_b200 import RxcError
+    from rusterix_b200.types import RenderGraph, SkyNode
+    cfg = scenes.sky_config(64, 64, 32)
+    cfg.render_graph = RenderGraph([SkyNode(clouds=True)])
+    with pytest.raises(RxcError) as e:
+        render_gpu(cfg.rasterizer(), cfg.scene, cfg.assets, 64, 64, 32)
+    assert e.value.status == -3
