@@ -7,7 +7,7 @@ from typing import List, Tuple
 import torch
 import torch.distributed as dist
 
-TILE_H = 16  # GPU tile height (csrc/rx_device.cuh RX_TILE_H): bands start on tile rows
+TILE_H = 32  # GPU tile height (csrc/rx_device.cuh RX_TILE_H): bands start on tile rows
 
 
 def shard_frames(n_frames: int, rank: int, world: int) -> List[int]:
@@ -29,12 +29,12 @@ def all_bands(height: int, world: int, align: int = TILE_H) -> List[Tuple[int, i
     return [band_for_rank(height, r, world, align) for r in range(world)]
 
 
-def gather_bands_to_rank0(band: torch.Tensor, height: int, width: int, rank: int, world: int):
+def gather_bands_to_rank0(band: torch.Tensor, height: int, width: int, rank: int, world: int, align: int = TILE_H):
     """Each rank holds its band [rows, width, 4] uint8; rank 0 returns the full [height, width, 4]
     frame, other ranks return None.  Point-to-point sends (bands differ in size)."""
     if world == 1:
         return band
-    bands = all_bands(height, world)
+    bands = all_bands(height, world, align)
     if rank == 0:
         full = torch.empty((height, width, 4), dtype=torch.uint8, device=band.device)
         y0, y1 = bands[0]
