@@ -744,6 +744,9 @@ __global__ void __launch_bounds__(256) k_bin_fill(SceneDev S, Workspace Wk) {
 #ifndef RX_RASTER_MIN_BLOCKS
 #define RX_RASTER_MIN_BLOCKS 4  // resident CTAs per SM the register allocation is bounded for
 #endif
+#ifndef RX_OPAQUE
+#define RX_OPAQUE 2
+#endif
 #define RX_LARGE_CACHE 160   // large-triangle records kept in shared memory across the tiles of a frame
 #define RX_COLOR_STRIDE 40   // words per tile row in shared memory: the 4 rows a warp writes hit disjoint banks
 
@@ -1592,11 +1595,18 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
     __shared__ __align__(16) DLight s_lights[RX_SMEM_LIGHTS];
     __shared__ float s_kd[256];                      // srgb_to_linear_fast(c / 255) * (1 - 0.04), rasterizer.rs:20-25
 
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t tid = threadIdx.x;
+#if RX_OPAQUE >= 3
+    asm volatile("" : "+r"(tid));
+#endif
+    const uint32_t lane = tid & 31, warp = tid >> 5;
     // warp w covers a 16x8 region (2 across, 4 down); lane (lx, ly) of the 8x4 lane grid owns the
     // pixels (lx + 8i, ly + 4j) of the region
     const int rbx = (int)(warp & 1) * RX_REGION_W, rby = (int)(warp >> 1) * RX_REGION_H;
-    const int lx = (int)(lane & 7), ly = (int)(lane >> 3);
+    int lx = (int)(lane & 7) + rbx, ly = (int)(lane >> 3) + rby;   // pixel offset of the thread inside the tile
+#if RX_OPAQUE >= 4
+    asm volatile("" : "+r"(lx), "+r"(ly));
+#endif
     const uint32_t total = n_frames * tiles_per_frame;
     uint32_t cached_frame = 0xFFFFFFFFu, n_cached = 0;
     {
@@ -1662,10 +1672,16 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
         const int tx1 = min(tx0 + RX_TILE_W, fw), ty1 = min(ty0 + RX_TILE_H, fy1);
         const int rx0 = tx0 + rbx, ry0 = ty0 + rby, rx1 = min(rx0 + RX_REGION_W, fw), ry1 = min(ry0 + RX_REGION_H, fy1);
         const bool region_ok = rx0 < rx1 && ry0 < ry1;
-        const int px0 = rx0 + lx, py0 = ry0 + ly;
-        const float fx0 = (float)px0 + 0.5f, fy0 = (float)py0 + 0.5f;  // rasterizer.rs:1022
-        const uint32_t valid = ((px0 < fw && py0 < fy1) ? 1u : 0u) | ((px0 + 8 < fw && py0 < fy1) ? 2u : 0u) |
-                               ((px0 < fw && py0 + 4 < fy1) ? 4u : 0u) | ((px0 + 8 < fw && py0 + 4 < fy1) ? 8u : 0u);
+        int px0 = tx0 + lx, py0 = ty0 + ly;
+        float fx0 = (float)px0 + 0.5f, fy0 = (float)py0 + 0.5f;  // rasterizer.rs:1022
+        uint32_t valid = ((px0 < fw && py0 < fy1) ? 1u : 0u) | ((px0 + 8 < fw && py0 < fy1) ? 2u : 0u) |
+                         ((px0 < fw && py0 + 4 < fy1) ? 4u : 0u) | ((px0 + 8 < fw && py0 + 4 < fy1) ? 8u : 0u);
+#if RX_OPAQUE >= 1
+        asm volatile("" : "+r"(px0), "+r"(py0));
+#endif
+#if RX_OPAQUE >= 2
+        asm volatile("" : "+f"(fx0), "+f"(fy0), "+r"(valid));
+#endif
 
         Vis4 V;  // z_buffer starts at 1.0 (rasterizer.rs:287)
         Opa4 O;  // z_buffer_opacity starts at 1.0, surface_id at None (:288-290)
