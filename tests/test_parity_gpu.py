@@ -389,3 +389,99 @@ def test_sky_cloud_layer_is_reported_unsupported():
     with pytest.raises(RxcError) as e:
         render_gpu(cfg.rasterizer(), cfg.scene, cfg.assets, 64, 64, 32)
     assert e.value.status == -3
+
+
+# ------------------------------------------------------------------------------------------------
+# edge cases and full-size configurations
+# ------------------------------------------------------------------------------------------------
+def _tri_batch(verts, tris, uvs=None, tile=0):
+    v = np.asarray(verts, dtype=np.float32)
+    uvs = uvs if uvs is not None else [(0.1 * i, 0.07 * i) for i in range(len(v))]
+    return Batch3D(v, tris, uvs).source(PixelSource.StaticTileIndex(tile)).cull_mode(CullMode.Off).with_computed_normals()
+
+
+def test_empty_scene_and_empty_batches():
+    """No batches at all, and batches without triangles or without vertices next to a drawn one."""
+    cfg = scenes.cube(200, 120, 40, logo_size=16)
+    cfg.scene.d3_static.clear()
+    cfg.scene.d2_static.clear()
+    st = _run(cfg, what="empty scene")
+    assert st["exact_frac"] == 1.0
+    cfg = scenes.cube(200, 120, 40, logo_size=16)
+    cfg.scene.d3_static.insert(0, _tri_batch([(0, 0, 0, 1), (1, 0, 0, 1), (0, 1, 0, 1)], []))     # vertices, no triangles
+    cfg.scene.d3_static.append(Batch3D(np.zeros((0, 4), np.float32), [], []).source(PixelSource.StaticTileIndex(0)))
+    cfg.scene.d2_static.append(Batch2D.new([], [], []))
+    _run(cfg, what="empty batches")
+
+
+def test_degenerate_and_non_finite_geometry():
+    """Zero-area and repeated-vertex triangles pass coverage but never the depth test (NaN z); NaN / Inf vertices and
+    a vertex on the camera plane (w = 0) follow the formulas instead of being culled (SURVEY T-edge, T-cast)."""
+    cfg = scenes.cube(320, 200, 40, logo_size=16)
+    nan, inf = float("nan"), float("inf")
+    verts = [(-0.9, -0.2, 0.3, 1), (0.9, -0.2, 0.3, 1), (0.0, 0.7, 0.3, 1),      # a plain triangle
+             (-0.5, 0.0, 0.6, 1), (0.5, 0.0, 0.6, 1), (0.0, 0.0, 0.6, 1),        # collinear (zero area)
+             (0.2, 0.2, 0.8, 1), (0.2, 0.2, 0.8, 1), (0.4, 0.5, 0.8, 1),         # repeated vertex
+             (nan, 0.1, 0.2, 1), (0.3, nan, 0.2, 1), (0.1, 0.3, inf, 1),         # non-finite
+             (0.0, 0.5, 0.0, 1), (-inf, 0.0, 0.5, 1)]
+    tris = [(0, 1, 2), (3, 4, 5), (6, 7, 8), (9, 0, 1), (10, 1, 2), (11, 2, 0), (0, 1, 13), (12, 0, 2), (0, 0, 0)]
+    cfg.scene.d3_static.append(_tri_batch(verts, tris))
+    _run(cfg, what="degenerate / non-finite")
+    # the camera sits exactly in the plane of a vertex: w = 0 after projection for the unclipped path
+    cfg.camera = scenes._firstp([0.0, 0.5, 0.0], [0.0, 0.5, 1.0])
+    _run(cfg, what="vertex at the eye")
+
+
+def test_huge_offscreen_and_subpixel_triangles():
+    cfg = scenes.cube(400, 300, 50, logo_size=16)
+    big = 1.0e6
+    verts = [(-big, -big, -3.0, 1), (big, -big, -3.0, 1), (0.0, big, -3.0, 1),           # covers the screen, far away
+             (50.0, 50.0, 0.0, 1), (51.0, 50.0, 0.0, 1), (50.0, 51.0, 0.0, 1),           # completely off screen
+             (0.1, 0.1, 0.55, 1), (0.1004, 0.1, 0.55, 1), (0.1, 0.1004, 0.55, 1),        # smaller than a pixel
+             (0.3, 0.1, 0.55, 1), (0.3, 0.1 + 1e-7, 0.55, 1), (0.9, 0.1, 0.55, 1)]       # a sliver
+    cfg.scene.d3_static.append(_tri_batch(verts, [(0, 1, 2), (3, 4, 5), (6, 7, 8), (9, 10, 11)]))
+    _run(cfg, what="huge / offscreen / subpixel")
+
+
+def test_frustum_rejected_batch_and_all_batches_behind_camera():
+    cfg = scenes.cube(256, 160, 40, logo_size=16)
+    behind = Batch3D.from_box(-0.5, -0.5, 5.0, 1.0, 1.0, 1.0).source(PixelSource.StaticTileIndex(0)).cull_mode(CullMode.Off).with_computed_normals()
+    cfg.scene.d3_static.append(behind)          # on the far side of the orbit camera's back: AABB reject (batch3d.rs:492-552)
+    _run(cfg, what="one rejected batch")
+    cfg.scene.d3_static = [behind]
+    cfg.scene.mark_dirty()
+    cfg.camera = scenes._firstp([0.0, 0.0, 0.0], [0.0, 0.0, -1.0])
+    _run(cfg, what="everything behind the camera")
+
+
+def test_dense_full_8k_owner_and_depth():
+    """BASELINE.json config D at its full size: 991,232 triangles, 7 lights, 7680x4320, Linear -- every pixel's
+    owner and depth bit for bit, colours within 1 LSB."""
+    st = _run(scenes.dense(7680, 4320, 40))
+    assert st["within1_frac"] > 0.9999
+
+
+def test_8k_bands_concatenate_to_the_full_frame():
+    """Config D's sharding: 8 row bands rendered separately are the full frame (pixels and owners)."""
+    from rusterix_b200 import mgpu
+    cfg = scenes.dense(7680, 4320, 40, patches=16)
+    r = cfg.rasterizer()
+    full = render_gpu(r, cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size)
+    for (y0, y1) in mgpu.all_bands(cfg.height, 8):
+        band = render_gpu(r, cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size, band=(y0, y1))
+        assert np.array_equal(band[0], full[0][y0:y1]) and np.array_equal(band[1], full[1][y0:y1])
+
+
+def test_sweep_of_256_frames_in_one_call_is_deterministic_and_matches_single_frames():
+    """Config E's unit of work: many cameras, one launch sequence (groups of frames share a workspace)."""
+    cfg = scenes.sweep(480, 270, 40, n_frames=4096, logo_size=64)
+    ids = list(range(0, 4096, 16))
+    rs = [cfg.rasterizer(i) for i in ids]
+    a = np.zeros((len(ids), cfg.height, cfg.width, 4), dtype=np.uint8)
+    b = np.zeros_like(a)
+    Rasterizer.rasterize_batch(rs, cfg.scene, a, cfg.width, cfg.height, cfg.tile_size, cfg.assets)
+    Rasterizer.rasterize_batch(rs, cfg.scene, b, cfg.width, cfg.height, cfg.tile_size, cfg.assets)
+    assert np.array_equal(a, b)
+    for k in (0, 97, 255):
+        single = render_gpu(rs[k], cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size, planes=False)
+        assert np.array_equal(a[k], single[0])
