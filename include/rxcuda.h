@@ -326,7 +326,7 @@ typedef struct rxc_frame {
 } rxc_frame;
 
 /* Counters filled by rxc_get_stats; times are device times from CUDA events (profiling on). */
-#define RXC_N_KERNELS 10
+#define RXC_N_KERNELS 11
 typedef struct rxc_stats {
     uint64_t frames;                       /* frames rasterized since create/reset           */
     uint64_t kernel_launches;              /* kernels launched since create/reset            */

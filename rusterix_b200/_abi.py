@@ -17,7 +17,7 @@ STATUS_NAMES = {
     -4: "RXC_ERR_OOM", -5: "RXC_ERR_INDEX", -6: "RXC_ERR_NO_DEVICE",
 }
 
-RXC_N_KERNELS = 10
+RXC_N_KERNELS = 11
 
 
 class rxc_texture(C.Structure):

@@ -195,6 +195,10 @@ __device__ __forceinline__ uint32_t tri_meta_flags(const DFrameBatch& FB) {
     return FB.alpha_test ? RX_META_ALPHA : 0u;
 }
 
+// virtual block coordinates: the front-end bodies run either as their own kernels (one CTA per block) or
+// back to back inside k_front_small (one CTA per frame walks the blocks)
+struct Blk { uint32_t x, y, nx; };
+
 struct MinMax {
     float mnx, mxx, mny, mxy;
     __device__ void init() { mnx = CUDART_INF_F; mxx = -CUDART_INF_F; mny = CUDART_INF_F; mxy = -CUDART_INF_F; }
@@ -229,12 +233,12 @@ __device__ void block_minmax_to_keys(MinMax m, uint32_t* kminx, uint32_t* kmaxx,
 // ---------------------------------------------------------------------------------------------
 // k_frame_setup
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_frame_setup(SceneDev S, Workspace Wk, uint32_t tiles_per_frame) {
-    const uint32_t f = blockIdx.y;
+__device__ __forceinline__ void d_frame_setup(const SceneDev& S, const Workspace& Wk, uint32_t tiles_per_frame, Blk bk) {
+    const uint32_t f = bk.y;
     const DFrame& F = Wk.frames[f];
     const uint32_t tid = threadIdx.x;
 
-    if (blockIdx.x == 0) {
+    if (bk.x == 0) {
         if (tid == 0) {
             DCounters z = {};
             Wk.counters[f] = z;
@@ -257,8 +261,8 @@ __global__ void __launch_bounds__(256) k_frame_setup(SceneDev S, Workspace Wk, u
         return;
     }
 
-    if (blockIdx.x <= S.n_b2) {  // one CTA per 2D batch: batch2d.rs:373-425
-        const uint32_t b = blockIdx.x - 1;
+    if (bk.x <= S.n_b2) {  // one CTA per 2D batch: batch2d.rs:373-425
+        const uint32_t b = bk.x - 1;
         const DBatch2& B = S.b2[b];
         Tri2D* recs = Wk.tri2d + (size_t)f * Wk.tri2d_stride + B.rec_off;
         const bool active = F.d2_active != 0;
@@ -349,7 +353,7 @@ __global__ void __launch_bounds__(256) k_frame_setup(SceneDev S, Workspace Wk, u
     }
 
     // remaining CTAs: per-batch frame state, and zeroing of the per-tile counters of this frame
-    const uint32_t zb = blockIdx.x - 1 - S.n_b2, nzb = gridDim.x - 1 - S.n_b2;
+    const uint32_t zb = bk.x - 1 - S.n_b2, nzb = bk.nx - 1 - S.n_b2;
     for (uint32_t b = zb * blockDim.x + tid; b < S.n_b3; b += nzb * blockDim.x) {  // per (frame, 3D batch) state
         const DBatch3& B = S.b3[b];
         DFrameBatch fb;
@@ -460,14 +464,14 @@ __device__ __forceinline__ void load_tri(const SceneDev& S, const DBatch3& B, co
     }
 }
 
-__global__ void __launch_bounds__(RX_CHUNK_TRIS) k_tri_setup(SceneDev S, Workspace Wk) {
-    const uint32_t f = blockIdx.y;
+__device__ __forceinline__ void d_tri_setup(const SceneDev& S, const Workspace& Wk, Blk bk) {
+    const uint32_t f = bk.y;
     const DFrame& F = Wk.frames[f];
-    const DChunk ch = S.chunks[blockIdx.x];
+    const DChunk ch = S.chunks[bk.x];
     const DBatch3& B = S.b3[ch.batch];
     DFrameBatch& FB = Wk.fb[(size_t)f * Wk.fb_stride + ch.batch];
     const uint32_t tid = threadIdx.x;
-    uint32_t* chunk_total = Wk.chunk_new_total + (size_t)f * Wk.chunk_stride + blockIdx.x;
+    uint32_t* chunk_total = Wk.chunk_new_total + (size_t)f * Wk.chunk_stride + bk.x;
 
     if (FB.rejected) {  // uniform for the CTA
         if (tid == 0) *chunk_total = 0u;
@@ -529,7 +533,7 @@ __global__ void __launch_bounds__(RX_CHUNK_TRIS) k_tri_setup(SceneDev S, Workspa
     }
 
     // vertices no triangle references still belong to projected_vertices (batch3d.rs:749-768)
-    if (blockIdx.x == B.chunk_first) {
+    if (bk.x == B.chunk_first) {
         for (uint32_t o = tid; o < B.n_orphans; o += blockDim.x) {
             const float4 p = __ldg(S.pos + S.orphans[B.orphan_off + o]);
             f4 vvv = rx_matvec4(FB.view_model, {p.x, p.y, p.z, p.w}, F.matvec_mode);
@@ -551,7 +555,7 @@ __global__ void __launch_bounds__(RX_CHUNK_TRIS) k_tri_setup(SceneDev S, Workspa
     if (n_new) {
         const uint32_t k = atomicAdd(&Wk.counters[f].n_clip, 1u);
         if (k < Wk.clip_stride) {
-            DClip c = {ch.first_tri + tid, blockIdx.x, base + wprefix, ch.batch};
+            DClip c = {ch.first_tri + tid, bk.x, base + wprefix, ch.batch};
             Wk.clip[(size_t)f * Wk.clip_stride + k] = c;
         } else {
             atomicOr(&Wk.counters[f].overflow, 4u);
@@ -566,9 +570,9 @@ __global__ void __launch_bounds__(RX_CHUNK_TRIS) k_tri_setup(SceneDev S, Workspa
 // ---------------------------------------------------------------------------------------------
 // k_batch_finalize : one warp per (frame, batch)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_batch_finalize(SceneDev S, Workspace Wk) {
-    const uint32_t f = blockIdx.y;
-    const uint32_t b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+__device__ __forceinline__ void d_batch_finalize(const SceneDev& S, const Workspace& Wk, Blk bk) {
+    const uint32_t f = bk.y;
+    const uint32_t b = bk.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint32_t lane = threadIdx.x & 31;
     if (b >= S.n_b3) return;
     const DFrame& F = Wk.frames[f];
@@ -607,13 +611,13 @@ __global__ void __launch_bounds__(256) k_batch_finalize(SceneDev S, Workspace Wk
 // ---------------------------------------------------------------------------------------------
 // k_clip_emit : grid-stride over the compact list of near-clipped triangles
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_clip_emit(SceneDev S, Workspace Wk) {
-    const uint32_t f = blockIdx.y;
+__device__ __forceinline__ void d_clip_emit(const SceneDev& S, const Workspace& Wk, Blk bk) {
+    const uint32_t f = bk.y;
     const DFrame& F = Wk.frames[f];
     DCounters& C = Wk.counters[f];
     const uint32_t n = min(C.n_clip, Wk.clip_stride);
     const uint32_t new_cap = Wk.bins_stride - S.n_tris;
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    for (uint32_t k = bk.x * blockDim.x + threadIdx.x; k < n; k += bk.nx * blockDim.x) {
         const DClip c = Wk.clip[(size_t)f * Wk.clip_stride + k];
         const DBatch3& B = S.b3[c.batch];
         const DFrameBatch& FB = Wk.fb[(size_t)f * Wk.fb_stride + c.batch];
@@ -658,15 +662,15 @@ __device__ __forceinline__ bool bin_tile_range(const DFrame& F, uint32_t bbx, ui
     return true;
 }
 
-__global__ void __launch_bounds__(256) k_bin_count(SceneDev S, Workspace Wk) {
-    const uint32_t f = blockIdx.y;
+__device__ __forceinline__ void d_bin_count(const SceneDev& S, const Workspace& Wk, Blk bk) {
+    const uint32_t f = bk.y;
     const DFrame& F = Wk.frames[f];
     DCounters& C = Wk.counters[f];
     const uint32_t new_cap = Wk.bins_stride - S.n_tris;
     const uint32_t total = S.n_tris + min(C.n_new_slots, new_cap);
     TriBin* bins = Wk.bins + (size_t)f * Wk.bins_stride;
     uint32_t* tc = Wk.tile_count + (size_t)f * Wk.tile_stride;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    for (uint32_t i = bk.x * blockDim.x + threadIdx.x; i < total; i += bk.nx * blockDim.x) {
         TriBin b = bins[i];
         int x0 = b.bbx & 0xFFFF, x1 = b.bbx >> 16, y0 = b.bby & 0xFFFF, y1 = b.bby >> 16;
         if (x0 >= x1 || y0 >= y1) continue;
@@ -693,10 +697,10 @@ __global__ void __launch_bounds__(256) k_bin_count(SceneDev S, Workspace Wk) {
     }
 }
 
-__global__ void __launch_bounds__(256) k_tile_alloc(Workspace Wk, uint32_t tiles_per_frame, int which, int pow2) {
-    const uint32_t f = blockIdx.y;
+__device__ __forceinline__ void d_tile_alloc(const Workspace& Wk, uint32_t tiles_per_frame, int which, int pow2, Blk bk) {
+    const uint32_t f = bk.y;
     DCounters& C = Wk.counters[f];
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = bk.x * blockDim.x + threadIdx.x;
     if (i >= tiles_per_frame) return;
     uint32_t* tc = (which ? Wk.tile_count2 : Wk.tile_count) + (size_t)f * Wk.tile_stride;
     uint32_t* tb = (which ? Wk.tile_base2 : Wk.tile_base) + (size_t)f * Wk.tile_stride;
@@ -712,8 +716,8 @@ __global__ void __launch_bounds__(256) k_tile_alloc(Workspace Wk, uint32_t tiles
     tb[i] = base;
 }
 
-__global__ void __launch_bounds__(256) k_bin_fill(SceneDev S, Workspace Wk) {
-    const uint32_t f = blockIdx.y;
+__device__ __forceinline__ void d_bin_fill(const SceneDev& S, const Workspace& Wk, Blk bk) {
+    const uint32_t f = bk.y;
     const DFrame& F = Wk.frames[f];
     DCounters& C = Wk.counters[f];
     const uint32_t new_cap = Wk.bins_stride - S.n_tris;
@@ -723,7 +727,7 @@ __global__ void __launch_bounds__(256) k_bin_fill(SceneDev S, Workspace Wk) {
     const uint32_t* tb = Wk.tile_base + (size_t)f * Wk.tile_stride;
     uint32_t* tf = Wk.tile_fill + (size_t)f * Wk.tile_stride;
     uint32_t* lists = Wk.lists + (size_t)f * Wk.list_stride;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    for (uint32_t i = bk.x * blockDim.x + threadIdx.x; i < total; i += bk.nx * blockDim.x) {
         const TriBin b = bins[i];
         if (b.batch & 0x80000000u) continue;
         int tx0, tx1, ty0, ty1;
@@ -736,6 +740,43 @@ __global__ void __launch_bounds__(256) k_bin_fill(SceneDev S, Workspace Wk) {
                 lists[tb[t] + pos] = b.slot;
             }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the front-end as kernels ...
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_frame_setup(SceneDev S, Workspace Wk, uint32_t tiles_per_frame) { d_frame_setup(S, Wk, tiles_per_frame, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
+__global__ void __launch_bounds__(RX_CHUNK_TRIS) k_tri_setup(SceneDev S, Workspace Wk) { d_tri_setup(S, Wk, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
+__global__ void __launch_bounds__(256) k_batch_finalize(SceneDev S, Workspace Wk) { d_batch_finalize(S, Wk, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
+__global__ void __launch_bounds__(128) k_clip_emit(SceneDev S, Workspace Wk) { d_clip_emit(S, Wk, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
+__global__ void __launch_bounds__(256) k_bin_count(SceneDev S, Workspace Wk) { d_bin_count(S, Wk, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
+__global__ void __launch_bounds__(256) k_tile_alloc(Workspace Wk, uint32_t tiles_per_frame, int which, int pow2) { d_tile_alloc(Wk, tiles_per_frame, which, pow2, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
+__global__ void __launch_bounds__(256) k_bin_fill(SceneDev S, Workspace Wk) { d_bin_fill(S, Wk, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
+
+// ... and fused for small scenes: one CTA per frame runs every front-end phase back to back (7 launches and
+// their gaps cost ~70 us per call, more than rasterising a 1080p frame of such a scene).  Phases communicate
+// through global memory written and read by this CTA only; __syncthreads orders them.
+__global__ void __launch_bounds__(256) k_front_small(SceneDev S, Workspace Wk, uint32_t tiles_per_frame, uint32_t n_frame_blocks) {
+    const uint32_t f = blockIdx.x;
+    for (uint32_t v = 0; v < n_frame_blocks; ++v) { d_frame_setup(S, Wk, tiles_per_frame, Blk{v, f, n_frame_blocks}); __syncthreads(); }
+    if (S.n_tris == 0u) return;
+    for (uint32_t v = 0; v < S.n_chunks; ++v) { d_tri_setup(S, Wk, Blk{v, f, S.n_chunks}); __syncthreads(); }
+    const uint32_t nfb = (S.n_b3 + 7u) / 8u;
+    for (uint32_t v = 0; v < nfb; ++v) d_batch_finalize(S, Wk, Blk{v, f, nfb});
+    __syncthreads();
+    d_clip_emit(S, Wk, Blk{0u, f, 1u});
+    __syncthreads();
+    d_bin_count(S, Wk, Blk{0u, f, 1u});
+    __syncthreads();
+    // nothing binned (every visible triangle went to the large list): all tile lists stay empty
+    if (Wk.counters[f].n_visible == Wk.counters[f].n_large) {
+        for (uint32_t i = threadIdx.x; i < tiles_per_frame; i += blockDim.x) Wk.tile_base[(size_t)f * Wk.tile_stride + i] = 0u;
+        return;
+    }
+    const uint32_t ntb = (tiles_per_frame + 255u) / 256u;
+    for (uint32_t v = 0; v < ntb; ++v) d_tile_alloc(Wk, tiles_per_frame, 0, 0, Blk{v, f, ntb});
+    __syncthreads();
+    d_bin_fill(S, Wk, Blk{0u, f, 1u});
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1998,6 +2039,10 @@ cudaError_t rxk_frame_setup(const SceneDev& S, const Workspace& W, uint32_t n_fr
     const uint32_t zero_blocks = max(max(1u, min(64u, (tiles_per_frame + 255u) / 256u)), min(64u, (S.n_b3 + 63u) / 64u));
     dim3 grid(1 + S.n_b2 + zero_blocks, n_frames);
     k_frame_setup<<<grid, 256, 0, st>>>(S, W, tiles_per_frame);
+    return cudaGetLastError();
+}
+cudaError_t rxk_front_small(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, cudaStream_t st) {
+    k_front_small<<<n_frames, 256, 0, st>>>(S, W, tiles_per_frame, 2u + S.n_b2);   // block 0, the 2D batches, one state/zeroing block
     return cudaGetLastError();
 }
 cudaError_t rxk_tri_setup(const SceneDev& S, const Workspace& W, uint32_t n_frames, cudaStream_t st) {

@@ -82,11 +82,14 @@ enum {
     RXK_BIN_FILL = 6,
     RXK_RASTER = 7,
     RXK_BIN2D = 8,
-    RXK_LIST_SORT = 9
+    RXK_LIST_SORT = 9,
+    RXK_FRONT_SMALL = 10
 };
 
 // Each returns the cudaError_t of the launch.  `n_frames` frames are processed by one launch.
 cudaError_t rxk_frame_setup(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, cudaStream_t st);
+// the whole front-end (frame setup .. bin fill) of a small non-general scene in one launch, one CTA per frame
+cudaError_t rxk_front_small(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, cudaStream_t st);
 cudaError_t rxk_tri_setup(const SceneDev& S, const Workspace& W, uint32_t n_frames, cudaStream_t st);
 cudaError_t rxk_batch_finalize(const SceneDev& S, const Workspace& W, uint32_t n_frames, cudaStream_t st);
 cudaError_t rxk_clip_emit(const SceneDev& S, const Workspace& W, uint32_t n_frames, int grid, cudaStream_t st);

@@ -25,4 +25,4 @@ for name in names:
     s = ctx.stats(); ctx.set_profiling(False)
     ms = [s.kernel_ms[i] / n for i in range(len(ctx.kernel_names()))]
     mpix = frames * cfg.width * cfg.height / 1e6
-    print(f"{name:12s} raster {ms[7]:.4f} ms  step {sum(ms):.4f} ms  {mpix / sum(ms) * 1e3:9.0f} Mpix/s  others " + " ".join(f"{m:.3f}" for m in ms[:7]))
+    print(f"{name:12s} raster {ms[7]:.4f} ms  step {sum(ms):.4f} ms  {mpix / sum(ms) * 1e3:9.0f} Mpix/s  others " + " ".join(f"{m:.3f}" for i, m in enumerate(ms) if i != 7))
