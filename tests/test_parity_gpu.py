@@ -485,3 +485,37 @@ def test_sweep_of_256_frames_in_one_call_is_deterministic_and_matches_single_fra
     for k in (0, 97, 255):
         single = render_gpu(rs[k], cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size, planes=False)
         assert np.array_equal(a[k], single[0])
+
+
+def test_one_context_many_scenes_in_any_order():
+    """The context keeps scene, textures, programs and a workspace resident: switching between scenes of different
+    size, kernel mode (fast / general / general + VM), frame size and light count must never leak state."""
+    order = [
+        lambda: scenes.shaded_config(320, 240, 40),
+        lambda: scenes.cube(200, 150, 40, logo_size=32),
+        lambda: scenes.dense(640, 360, 40, patches=6),
+        lambda: scenes.chunked_config(480, 270, 40),
+        lambda: scenes.sky_config(320, 180, 40),
+        lambda: scenes.game2d_config(240, 160),
+        lambda: scenes.map_config(1280, 720, 40, logo_size=64),
+        lambda: scenes.cube(64, 64, 200, logo_size=8),
+        lambda: scenes.shaded_config(160, 120, 16, emissive=False),
+        lambda: scenes.teapot(480, 270, 60, logo_size=64),
+    ]
+    for k, make in enumerate(order + order[::-1]):
+        cfg = make()
+        _run(cfg, frame=k % max(1, cfg.n_frames), what=f"#{k} {cfg.name}")
+
+
+def test_lights_can_change_without_a_scene_upload():
+    """examples/cube.rs:72-73 moves the light every frame: rxc_set_lights path, growing and shrinking lists."""
+    cfg = scenes.cube(240, 180, 60, logo_size=32)
+    base = cfg.scene.lights[0]
+    for n in (1, 3, 0, 2):
+        cfg.scene.lights = []
+        for i in range(n):
+            l = (Light.new(LightType.Point).with_intensity(1.0 + 0.3 * i).with_color([1.0, 0.9 - 0.2 * i, 0.6 + 0.1 * i])
+                 .with_position([2.0 * math.cos(0.9 * i + n), 0.8, 2.0 * math.sin(0.9 * i + n)]).with_start_distance(1.0).with_end_distance(4.0))
+            cfg.scene.lights.append(l.compile())
+        _run(cfg, what=f"{n} lights")
+    assert base is not None
