@@ -1648,6 +1648,10 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
 #if RX_OPAQUE >= 4
     asm volatile("" : "+r"(lx), "+r"(ly));
 #endif
+    int cbase = ly * RX_COLOR_STRIDE + lx;   // the thread's first pixel in s_color
+#if RX_OPAQUE >= 2
+    asm volatile("" : "+r"(cbase));
+#endif
     const uint32_t total = n_frames * tiles_per_frame;
     uint32_t cached_frame = 0xFFFFFFFFu, n_cached = 0;
     {
@@ -1788,7 +1792,7 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
 #pragma unroll 1
         for (int k = 0; k < 4; ++k) {
             const int px = px0 + ((k & 1) << 3), py = py0 + ((k >> 1) << 2);
-            const float fpx = (float)px + 0.5f, fpy = (float)py + 0.5f;
+            const float fpx = fx0 + ((k & 1) ? 8.0f : 0.0f), fpy = fy0 + ((k & 2) ? 4.0f : 0.0f);  // exact: small integers + 0.5
             const float4 st = s_state[k * RX_TILE_THREADS + tid];
             const uint32_t owner = __float_as_uint(st.y);
             uint32_t color;
@@ -1813,7 +1817,7 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                 color = F.has_bg_color ? F.bg_color : 0u;  // rasterizer.rs:277-282
                 if (!F.ignore_bg_shader && F.bg_shader != RXC_BG_NONE) color = shade_background(F, px, py);
             }
-            s_color[(py - ty0) * RX_COLOR_STRIDE + (px - tx0)] = color;
+            s_color[cbase + ((k & 1) << 3) + (k >> 1) * (4 * RX_COLOR_STRIDE)] = color;
             if (PLANES && px < fw && py < fy1) {
                 const size_t o = (size_t)(py - F.band_y0) * (size_t)fw + (size_t)px;
                 if (out.owner) out.owner[o] = owner;
@@ -1846,7 +1850,7 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
 #pragma unroll 1
                     for (int k = 0; k < 4; ++k) {
                         const int px = px0 + ((k & 1) << 3), py = py0 + ((k >> 1) << 2);
-                        uint32_t* c = &s_color[(py - ty0) * RX_COLOR_STRIDE + (px - tx0)];
+                        uint32_t* c = &s_color[cbase + ((k & 1) << 3) + (k >> 1) * (4 * RX_COLOR_STRIDE)];
                         *c = apply_2d<VM>(S, F, lights, fb2, T, px, py, smode, *c, &vm_fault);
                     }
                 }
