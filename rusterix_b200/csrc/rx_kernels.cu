@@ -1,18 +1,23 @@
 // rx_kernels.cu -- the sm_100a kernels of the rasterize path.
 //
-//   k_frame_setup     per (frame, batch) matrices, frustum-AABB reject, texture frame, light flicker,
-//                     2D batch projection + records, counter / tile-count zeroing
+//   k_frame_setup     per (frame, batch) matrices, frustum-AABB reject, texture frame, shade descriptor (source,
+//                     repeat flags, VM program), light flicker, 2D batch projection + records, counter zeroing
 //   k_tri_setup       per original triangle: view transform, early cull, near classification,
-//                     projection, cull/swap, edge equations, depth/uv reciprocals, pixel bbox;
+//                     projection, cull/swap, edge equations, depth/uv reciprocals, pixel bbox, flat-normal flag;
 //                     batch screen bbox by block reduction + atomics; near-clip counting + block scan
 //   k_batch_finalize  per batch: scan of the per-chunk clip counts, API-tile scissor from the bbox
 //   k_clip_emit       per near-clipped triangle: Sutherland-Hodgman, fan triangles at ordered slots
 //   k_bin_count       final (scissored) bbox, tile counts, large-triangle list
 //   k_tile_alloc      per tile: list space from an atomic arena cursor
 //   k_bin_fill        tile lists
-//   k_raster          persistent, one CTA per 16x16 tile at a time: staged triangle records in shared
-//                     memory, per-pixel exact edge/depth test, alpha test, deferred shading of the
-//                     owner, miss pass, 2D pass, 128-bit RGBA8 stores
+//   k_front_small     all of the above back to back in one CTA per frame (tiny scenes)
+//   k_bin_large, k_bin2d, k_list_sort   general mode: every triangle and every 2D record in per-tile lists sorted
+//                     by submission ordinal (chunk opacity layer, surface ids, many 2D records)
+//   k_raster          persistent, one CTA per 32x32 tile at a time, 2x2 pixels per thread: warp-private walk of the
+//                     triangle records, per-pixel exact edge/depth test, alpha test, deferred shading of the
+//                     owner (or the Rusteria VM program of its batch, rx_vm.cuh), miss pass (sky, brush preview),
+//                     opacity blend, 2D pass, 128-bit RGBA8 stores
+//   k_vm_execute, k_selftest_div   diagnostics
 //
 // Reference cites are to /root/reference (markusmoenig/Rusterix).
 #include "rx_kernels.cuh"
@@ -26,17 +31,6 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
-}
-
-// rasterizer.rs:199-207
-__device__ __forceinline__ uint32_t hash_u32(uint32_t seed) {
-    uint32_t state = seed;
-    state = (state ^ 61u) ^ (state >> 16);
-    state = state + (state << 3);
-    state ^= state >> 4;
-    state = state * 0x27d4eb2du;
-    state ^= state >> 15;
-    return state;
 }
 
 // The reference rejects a batch per API tile (rasterizer.rs:978-983 / :594-600).  Over one axis the

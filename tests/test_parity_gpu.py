@@ -519,3 +519,28 @@ def test_lights_can_change_without_a_scene_upload():
             cfg.scene.lights.append(l.compile())
         _run(cfg, what=f"{n} lights")
     assert base is not None
+
+
+def test_more_lights_than_the_shared_memory_table_and_more_large_triangles_than_the_cache():
+    """40 lights (the raster kernel stages 16 per frame in shared memory, the rest of such a list is read from global
+    memory) and 220 screen-filling triangles (160 large-triangle records are cached per frame, the two-level tile
+    selection runs above 32, the remainder is walked from the large list)."""
+    cfg = scenes.cube(384, 256, 64, logo_size=32)
+    rng = np.random.default_rng(5)
+    cfg.scene.lights = [Light.new(LightType(int(rng.choice([0, 3, 4])))).with_intensity(0.15).with_color(list(rng.random(3)))
+                        .with_position(list(rng.normal(0, 2.0, 3))).with_start_distance(0.5).with_end_distance(6.0).compile() for _ in range(40)]
+    verts, tris, uvs = [], [], []
+    for i in range(220):
+        z = -1.5 - 0.01 * i
+        a = 0.1 * i
+        base = len(verts)
+        for (x, y) in ((-6, -5), (6, -5), (0, 7)):
+            verts.append((x * math.cos(a) - y * math.sin(a), x * math.sin(a) + y * math.cos(a), z, 1.0))
+            uvs.append((x * 0.3, y * 0.3))
+        tris.append((base, base + 1, base + 2))
+    big = Batch3D(np.asarray(verts, dtype=np.float32), tris, uvs).source(PixelSource.StaticTileIndex(0)).cull_mode(CullMode.Off) \
+        .repeat_mode(RepeatMode.RepeatXY).with_computed_normals()
+    cfg.scene.d3_static.append(big)
+    st = _run(cfg, what="40 lights, 220 large triangles")
+    from rusterix_b200 import DeviceContext
+    assert DeviceContext.get(0).stats().last_large_tris > 160
