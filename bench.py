@@ -231,6 +231,8 @@ def main():
         raise SystemExit("bench.py needs a GPU: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from rusterix_b200 import mgpu
+    numa_cpus = mgpu.bind_to_gpu_numa_node(local_rank)  # before any pinned host allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -391,7 +393,8 @@ def main():
                        "l2": "256 MiB flush between timed steps; each step also writes %.0f MB of frames (> 126 MB L2)" % (F * frame_bytes / 1e6),
                        "timing": "CUDA events per step on the launching stream, summed over steps, max over ranks"},
             "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step),
-                    "ms_per_step": e2e_ms_step, "steps": e2e_steps, "api": "Rasterizer.rasterize_batch -> rxc_rasterize_batch, pinned host pixels"},
+                    "ms_per_step": e2e_ms_step, "steps": e2e_steps, "api": "Rasterizer.rasterize_batch -> rxc_rasterize_batch, pinned host pixels",
+                    "host_numa_binding": ("rank pinned to the %d cores next to its GPU" % len(numa_cpus)) if numa_cpus else "none"},
             "gpu_launches": int(gpu_launches), "launches_per_step": int(launches_per_step),
             "roofline": roofline, "clocks": clocks,
         }

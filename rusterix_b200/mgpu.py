@@ -2,12 +2,42 @@
 camera sweep or screen bands of one frame are independent units, so ranks render without any
 data-path collective; torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests) is used
 only to gather finished frames / bands to rank 0."""
-from typing import List, Tuple
+import os
+from typing import List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
 
 TILE_H = 32  # GPU tile height (csrc/rx_device.cuh RX_TILE_H): bands start on tile rows
+
+
+def bind_to_gpu_numa_node(device_index: int) -> Optional[List[int]]:
+    """Pins the calling process to the host cores next to GPU `device_index` (NVML's ideal CPU affinity,
+    i.e. the NUMA node its PCIe root port hangs off).  Host pixel buffers pinned afterwards are then
+    first-touched on that node, so the D2H of finished frames does not cross the socket interconnect
+    when 8 ranks drain their frames at once.  Returns the CPU list, or None when NVML or the topology
+    is unavailable (nothing is changed then)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = device_index
+        if visible:
+            ids = [v.strip() for v in visible.split(",") if v.strip()]
+            if device_index < len(ids) and ids[device_index].isdigit():
+                idx = int(ids[device_index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [w * 64 + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
 
 
 def shard_frames(n_frames: int, rank: int, world: int) -> List[int]:
