@@ -13,7 +13,7 @@ namespace {
 
 const char* const kKernelNames[RXC_N_KERNELS] = {"k_frame_setup", "k_tri_setup", "k_batch_finalize", "k_clip_emit", "k_bin_count",
                                                  "k_tile_alloc",  "k_bin_fill",  "k_raster",         "k_bin2d",     "k_list_sort",
-                                                 "k_front_small"};
+                                                 "k_front_fused"};  // k_front_small or k_front_cluster
 
 struct HChunk {  // host copy of what rxc_chunk carries besides its batches
     int32_t origin[2]; int32_t size;
@@ -76,6 +76,7 @@ struct rxc_ctx {
     DFrame* h_frames = nullptr;  size_t h_frames_cap = 0;      // pinned
     DCounters* h_counters = nullptr; size_t h_counters_cap = 0; // pinned
     int raster_blocks_per_sm = 1;
+    int front_cluster_max = 64;   // setup chunks up to which the front end runs as one cluster per frame (0 = never)
     // host-output pipelining: a copy stream and two staging halves so the D2H of one sub-group of
     // frames overlaps the kernels of the next
     cudaStream_t copy_stream = nullptr;
@@ -536,9 +537,13 @@ int32_t launch_group(rxc_ctx* ctx, const DFrame* h_frames, DCounters* h_counters
     // runs them back to back (measured: 22 us instead of ~70 us for the cube; from ~5 setup chunks on the serial
     // walk of one CTA loses against the parallel launches)
     const bool small_front = !S.general && S.n_chunks <= 2 && S.n_b2 <= 4 && tiles_per_frame <= 16384;
+    // mid-sized scenes: one cluster of CTAs per frame, cluster barriers instead of kernel boundaries
+    const bool cluster_front = !small_front && !S.general && ctx->front_cluster_max != 0 && S.n_chunks <= (uint32_t)ctx->front_cluster_max &&
+                               S.n_b2 <= 64 && tiles_per_frame <= 65536;
     if (small_front) { LaunchScope l(ctx, RXK_FRONT_SMALL); CK(rxk_front_small(S, ctx->W, n, tiles_per_frame, ctx->stream)); }
+    else if (cluster_front) { LaunchScope l(ctx, RXK_FRONT_SMALL); CK(rxk_front_cluster(S, ctx->W, n, tiles_per_frame, ctx->stream)); }
     else { LaunchScope l(ctx, RXK_FRAME_SETUP); CK(rxk_frame_setup(S, ctx->W, n, tiles_per_frame, ctx->stream)); }
-    if (S.n_tris && !small_front) {
+    if (S.n_tris && !small_front && !cluster_front) {
         { LaunchScope l(ctx, RXK_TRI_SETUP); CK(rxk_tri_setup(S, ctx->W, n, ctx->stream)); }
         { LaunchScope l(ctx, RXK_BATCH_FINALIZE); CK(rxk_batch_finalize(S, ctx->W, n, ctx->stream)); }
         { LaunchScope l(ctx, RXK_CLIP_EMIT); CK(rxk_clip_emit(S, ctx->W, n, grid_for(std::min<size_t>(S.n_tris, 65536), 128), ctx->stream)); }
@@ -758,6 +763,7 @@ int32_t rxc_create(int32_t device, rxc_ctx** out) {
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RXC_ERR_CUDA; }
     ctx->stream = ctx->own_stream;
     ctx->raster_blocks_per_sm = rxk_raster_blocks_per_sm();
+    if (const char* e = getenv("RXC_FRONT_CLUSTER_MAX")) ctx->front_cluster_max = atoi(e);  // tuning knob for experiments
     *out = ctx;
     return RXC_OK;
 }

@@ -11,6 +11,7 @@
 //   k_tile_alloc      per tile: list space from an atomic arena cursor
 //   k_bin_fill        tile lists
 //   k_front_small     all of the above back to back in one CTA per frame (tiny scenes)
+//   k_front_cluster   all of the above in one thread-block cluster per frame, cluster barriers between the phases
 //   k_bin_large, k_bin2d, k_list_sort   general mode: every triangle and every 2D record in per-tile lists sorted
 //                     by submission ordinal (chunk opacity layer, surface ids, many 2D records)
 //   k_raster          persistent, one CTA per 32x32 tile at a time, 2x2 pixels per thread: warp-private walk of the
@@ -24,6 +25,8 @@
 #include "rx_vm.cuh"
 
 #include <math_constants.h>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -771,6 +774,37 @@ __global__ void __launch_bounds__(256) k_front_small(SceneDev S, Workspace Wk, u
     for (uint32_t v = 0; v < ntb; ++v) d_tile_alloc(Wk, tiles_per_frame, 0, 0, Blk{v, f, ntb});
     __syncthreads();
     d_bin_fill(S, Wk, Blk{0u, f, 1u});
+}
+
+// ... and fused for mid-sized scenes: one thread-block CLUSTER per frame.  The CTAs of the cluster share out the
+// virtual blocks of every phase and meet at the hardware cluster barrier (barrier.cluster arrive.release /
+// wait.acquire, which also orders the global-memory hand-over between phases) instead of at a kernel boundary:
+// seven dependent launches (~10 us each of drain + launch + ramp) become six barriers of well under a microsecond.
+__global__ void __launch_bounds__(256) k_front_cluster(SceneDev S, Workspace Wk, uint32_t tiles_per_frame, uint32_t n_frame_blocks) {
+    cg::cluster_group cl = cg::this_cluster();
+    const uint32_t r = cl.block_rank(), R = cl.num_blocks();   // the cluster spans grid.x; grid.y = frames
+    const uint32_t f = blockIdx.y;
+    for (uint32_t v = r; v < n_frame_blocks; v += R) { d_frame_setup(S, Wk, tiles_per_frame, Blk{v, f, n_frame_blocks}); __syncthreads(); }
+    if (S.n_tris == 0u) return;                                 // uniform over the cluster
+    cl.sync();
+    for (uint32_t v = r; v < S.n_chunks; v += R) { d_tri_setup(S, Wk, Blk{v, f, S.n_chunks}); __syncthreads(); }
+    cl.sync();
+    const uint32_t nfb = (S.n_b3 + 7u) / 8u;
+    for (uint32_t v = r; v < nfb; v += R) d_batch_finalize(S, Wk, Blk{v, f, nfb});
+    cl.sync();
+    d_clip_emit(S, Wk, Blk{r, f, R});
+    cl.sync();
+    d_bin_count(S, Wk, Blk{r, f, R});
+    cl.sync();
+    // nothing binned (every visible triangle went to the large list): all tile lists stay empty
+    if (Wk.counters[f].n_visible == Wk.counters[f].n_large) {
+        for (uint32_t i = r * blockDim.x + threadIdx.x; i < tiles_per_frame; i += R * blockDim.x) Wk.tile_base[(size_t)f * Wk.tile_stride + i] = 0u;
+        return;
+    }
+    const uint32_t ntb = (tiles_per_frame + 255u) / 256u;
+    for (uint32_t v = r; v < ntb; v += R) d_tile_alloc(Wk, tiles_per_frame, 0, 0, Blk{v, f, ntb});
+    cl.sync();
+    d_bin_fill(S, Wk, Blk{r, f, R});
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -2042,6 +2076,18 @@ cudaError_t rxk_frame_setup(const SceneDev& S, const Workspace& W, uint32_t n_fr
 cudaError_t rxk_front_small(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, cudaStream_t st) {
     k_front_small<<<n_frames, 256, 0, st>>>(S, W, tiles_per_frame, 2u + S.n_b2);   // block 0, the 2D batches, one state/zeroing block
     return cudaGetLastError();
+}
+cudaError_t rxk_front_cluster(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, cudaStream_t st) {
+    const uint32_t zero_blocks = max(1u, min(64u, (tiles_per_frame + 255u) / 256u));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(RX_FRONT_CLUSTER, n_frames);
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = RX_FRONT_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_front_cluster, S, W, tiles_per_frame, 1u + S.n_b2 + zero_blocks);
 }
 cudaError_t rxk_tri_setup(const SceneDev& S, const Workspace& W, uint32_t n_frames, cudaStream_t st) {
     if (S.n_chunks == 0) return cudaSuccess;

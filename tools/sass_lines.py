@@ -14,36 +14,61 @@ import tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def disasm_lines(kernel):
+def disasm_functions(kernel):
+    """{mangled name: [source line of every instruction]} for the functions whose name contains `kernel`."""
     with tempfile.TemporaryDirectory() as td:
         subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "rusterix_b200", "librxcuda.so")], cwd=td, capture_output=True)
         cubin = [f for f in os.listdir(td) if f.startswith("rx_kernels")][0]
         txt = subprocess.run(["nvdisasm", "-g", "-c", cubin], cwd=td, capture_output=True, text=True).stdout
-    out, cur, on = [], None, False
+    funcs, cur, name = {}, None, None
     for line in txt.splitlines():
         if line.startswith("//---") and ".text." in line:
-            on = kernel in line
+            name = line.split(".text.")[1].split()[0]
+            if kernel not in name:
+                name = None
+            else:
+                funcs[name] = []
             continue
-        if not on:
+        if name is None:
             continue
         m = re.search(r'//## File "([^"]+)", line (\d+)', line)
         if m:
             cur = (os.path.basename(m.group(1)), int(m.group(2)))
             continue
         if re.match(r"\s+/\*[0-9a-f]{4,}\*/", line):
-            out.append(cur)
-    return out
+            funcs[name].append(cur)
+    return funcs
+
+
+def disasm_lines(kernel, n_profiled, profiled_name):
+    """The instantiation that was profiled: same instruction count, and the template arguments of the
+    demangled name in the report (`k_raster<0, 0, 1>`) in the same order as the mangled one (`ILi0ELb0ELi1E`)."""
+    funcs = disasm_functions(kernel)
+    args = re.findall(r"\d+", profiled_name[profiled_name.find("<"):profiled_name.find(">") + 1]) if "<" in profiled_name else []
+    cands = [n for n, l in funcs.items() if len(l) == n_profiled]
+    if args:
+        want = [n for n in cands if re.findall(r"L[ibjm](\d+)E", n) == args]
+        cands = want or cands
+    if len(cands) != 1:
+        print(f"warning: {len(cands)} disassembled functions match {profiled_name!r} ({n_profiled} instructions)", file=sys.stderr)
+    if not cands:
+        return max(funcs.values(), key=len)
+    print(f"joined with {cands[0]}", file=sys.stderr)
+    return funcs[cands[0]]
 
 
 def main():
     rep, kernel = sys.argv[1], sys.argv[2]
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-    lines = disasm_lines(kernel)
     page = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(page)))
     hdr = rows[1]
     ci, cs = hdr.index("Instructions Executed"), hdr.index("# Samples")
     body = rows[2:]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(io.StringIO(raw)))
+    pname = rr[2][rr[0].index("Kernel Name")] if len(rr) > 2 and "Kernel Name" in rr[0] else ""
+    lines = disasm_lines(kernel, len(body), pname)
     if len(body) != len(lines):
         print(f"warning: {len(body)} profiled instructions vs {len(lines)} disassembled", file=sys.stderr)
     inst, samp = collections.Counter(), collections.Counter()
