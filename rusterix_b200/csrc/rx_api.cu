@@ -76,11 +76,14 @@ struct rxc_ctx {
     DFrame* h_frames = nullptr;  size_t h_frames_cap = 0;      // pinned
     DCounters* h_counters = nullptr; size_t h_counters_cap = 0; // pinned
     int raster_blocks_per_sm = 1;
+    int piece_mb = 8;             // host output: small frames are rendered and drained in groups of about this size
+    int slice_mb = 4;             // host output: large frames are rendered and drained in slices of about this size (0 = whole frames)
     int front_cluster_max = 64;   // setup chunks up to which the front end runs as one cluster per frame (0 = never)
     // host-output pipelining: a copy stream and two staging halves so the D2H of one sub-group of
     // frames overlaps the kernels of the next
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_render[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
+    cudaEvent_t ev_slice[16] = {};   // one per slice of a large frame
 
     // stats / profiling
     rxc_stats stats = {};
@@ -286,7 +289,7 @@ int32_t ensure_workspace(rxc_ctx* ctx, uint32_t n_frames, uint32_t tiles_per_fra
     RES(w_fb, nf * std::max<size_t>(1, S.n_b3) * sizeof(DFrameBatch));
     RES(w_fb2, nf * std::max<size_t>(1, S.n_b2) * sizeof(DFrameBatch2));
     RES(w_lights, nf * std::max<size_t>(1, S.n_lights) * sizeof(DLight));
-    RES(w_counters, nf * sizeof(DCounters));
+    RES(w_counters, 2 * nf * sizeof(DCounters));   // two blocks: the pipelined host path alternates them with the staging halves
     RES(w_vis, nf * std::max<size_t>(1, 3 * T) * sizeof(TriVis));
     RES(w_shade, nf * std::max<size_t>(1, 3 * T) * sizeof(TriShade));
     RES(w_bins, nf * std::max<size_t>(1, 3 * T) * sizeof(TriBin));
@@ -303,7 +306,7 @@ int32_t ensure_workspace(rxc_ctx* ctx, uint32_t n_frames, uint32_t tiles_per_fra
     RES(w_tfill2, nf * (size_t)tiles_per_frame * 4);
     RES(w_lists2, nf * (size_t)want_list2 * 4);
     RES(w_tri2d, nf * std::max<size_t>(1, S.n_rec2d) * sizeof(Tri2D));
-    RES(w_rcounter, 16);
+    RES(w_rcounter, RX_RASTER_COUNTERS * 4);
 #undef RES
     W.frames = ctx->w_frames.as<DFrame>();
     W.fb = ctx->w_fb.as<DFrameBatch>(); W.fb_stride = std::max(1u, S.n_b3);
@@ -525,8 +528,12 @@ int32_t validate_sources(rxc_ctx* ctx) {
 }
 
 // Runs frames [first, first+n) of one group through the kernel sequence.
+// `slices` > 1 rasterises every frame as that many horizontal slices (ranges of GPU tile rows), one k_raster launch
+// each, and calls `after_slice(first_row, end_row)` (rows relative to the frame's band) once a slice has been
+// enqueued, so that the caller can start draining it while the next slice renders.
+template <class AfterSlice>
 int32_t launch_group(rxc_ctx* ctx, const DFrame* h_frames, DCounters* h_counters, uint32_t n, uint8_t* d_pixels, uint64_t stride,
-                     uint32_t* d_owner, float* d_depth) {
+                     uint32_t* d_owner, float* d_depth, uint32_t slices, AfterSlice after_slice) {
     SceneDev& S = ctx->S;
     const uint32_t tiles_per_frame = (uint32_t)h_frames[0].tiles_x * (uint32_t)h_frames[0].tiles_y;
     CK(cudaMemcpyAsync(ctx->W.frames, h_frames, n * sizeof(DFrame), cudaMemcpyHostToDevice, ctx->stream));
@@ -563,12 +570,22 @@ int32_t launch_group(rxc_ctx* ctx, const DFrame* h_frames, DCounters* h_counters
     RasterOut out;
     out.pixels = d_pixels; out.frame_stride = stride; out.owner = d_owner; out.depth = d_depth;
     out.vec_store = (((uintptr_t)d_pixels & 15) == 0 && (stride & 15) == 0 && ((h_frames[0].width * 4) & 15) == 0) ? 1u : 0u;
-    const size_t total_tiles = (size_t)n * tiles_per_frame;
-    const int grid = (int)std::max<size_t>(1, std::min<size_t>(total_tiles, (size_t)ctx->sm_count * ctx->raster_blocks_per_sm));
     int sample_mode = (int)h_frames[0].sample_mode;
     for (uint32_t i = 1; i < n; ++i) if ((int)h_frames[i].sample_mode != sample_mode) sample_mode = 2;
-    { LaunchScope l(ctx, RXK_RASTER); CK(rxk_raster(S, ctx->W, out, n, tiles_per_frame, sample_mode, grid, ctx->stream)); }
-    CK(cudaMemcpyAsync(h_counters, ctx->W.counters, n * sizeof(DCounters), cudaMemcpyDeviceToHost, ctx->stream));
+    const uint32_t tiles_x = (uint32_t)h_frames[0].tiles_x, tiles_y = (uint32_t)h_frames[0].tiles_y;
+    const uint32_t rows_total = (uint32_t)(h_frames[0].band_y1 - h_frames[0].band_y0);
+    slices = std::max(1u, std::min(std::min(slices, tiles_y), (uint32_t)RX_RASTER_COUNTERS));
+    const uint32_t rows_per_slice = (tiles_y + slices - 1) / slices;   // in tile rows
+    for (uint32_t k = 0, ty0 = 0; ty0 < tiles_y; ++k, ty0 += rows_per_slice) {
+        const uint32_t ty1 = std::min(tiles_y, ty0 + rows_per_slice);
+        const size_t slice_tiles = (size_t)(ty1 - ty0) * tiles_x;
+        const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)n * slice_tiles, (size_t)ctx->sm_count * ctx->raster_blocks_per_sm));
+        { LaunchScope l(ctx, RXK_RASTER); CK(rxk_raster(S, ctx->W, out, n, ty0 * tiles_x, (uint32_t)slice_tiles, k, sample_mode, grid, ctx->stream)); }
+        const int32_t st = after_slice(ty0 * (uint32_t)RX_TILE_H, std::min(rows_total, ty1 * (uint32_t)RX_TILE_H));
+        if (st != RXC_OK) return st;
+    }
+    // the counters follow the pixels: on the render stream, or (h_counters == nullptr) copied by the caller on its copy stream
+    if (h_counters) CK(cudaMemcpyAsync(h_counters, ctx->W.counters, n * sizeof(DCounters), cudaMemcpyDeviceToHost, ctx->stream));
     ctx->stats.frames += n;
     return RXC_OK;
 }
@@ -642,10 +659,18 @@ int32_t rasterize_impl(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames,
         ctx->h_frames_cap = group;
     }
 
-    // Host pixels, several frames: sub-groups of frames are rendered into alternating halves of the device
-    // staging buffer while the copy stream drains the previous half over PCIe.
-    if (!dev_px && sync && n_frames > 1 && !owner && !depth) {
-        const uint32_t sub = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(group, ((uint64_t)8 << 20) / std::max<uint64_t>(1, frame_bytes)));
+    // Host pixels: the frames are rendered in pieces of about 8 MB -- sub-groups of small frames, horizontal slices of
+    // large ones (one front-end pass per frame, one k_raster launch per slice) -- into alternating halves of the
+    // device staging buffer, while the copy stream drains the finished pieces over PCIe.  What stays exposed is the
+    // first piece: front end + one slice instead of a whole frame (or group of frames).
+    if (!dev_px && sync && !owner && !depth && (n_frames > 1 || frame_bytes >= ((uint64_t)2 << 20))) {
+        const uint64_t piece = (uint64_t)ctx->piece_mb << 20;
+        const uint32_t sub = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(group, piece / std::max<uint64_t>(1, frame_bytes)));
+        const uint64_t slice_bytes = (uint64_t)ctx->slice_mb << 20;
+        // slices only pay off from about 16 MB per frame on: every D2H copy carries ~10 us of fixed cost
+        const uint32_t slices = (sub > 1 || slice_bytes == 0 || frame_bytes < ((uint64_t)16 << 20)) ? 1u
+                                : (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(16, (frame_bytes + slice_bytes / 2) / slice_bytes));
+        const uint64_t row_bytes = (uint64_t)f0.width * 4;
         if (ctx->h_frames_cap < n_frames) {
             CK(cudaStreamSynchronize(ctx->stream));
             if (ctx->h_frames) cudaFreeHost(ctx->h_frames);
@@ -661,6 +686,7 @@ int32_t rasterize_impl(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames,
                 CK(cudaEventCreateWithFlags(&ctx->ev_render[i], cudaEventDisableTiming));
                 CK(cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
             }
+            for (int i = 0; i < 16; ++i) CK(cudaEventCreateWithFlags(&ctx->ev_slice[i], cudaEventDisableTiming));
         }
         CK(cudaStreamSynchronize(ctx->stream));  // the pinned frame block may still feed an earlier asynchronous call
         for (uint32_t i = 0; i < n_frames; ++i)
@@ -674,14 +700,29 @@ int32_t rasterize_impl(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames,
                 const int half = (int)(k & 1u);
                 uint8_t* d_px = ctx->d_out_px.as<uint8_t>() + (size_t)half * sub * frame_bytes;
                 if (k >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[half], 0));  // the half has been drained
-                if ((st = launch_group(ctx, ctx->h_frames + first, ctx->h_counters + first, n, d_px, frame_bytes, nullptr, nullptr)) != RXC_OK) return st;
-                CK(cudaEventRecord(ctx->ev_render[half], ctx->stream));
-                CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_render[half], 0));
-                if (stride == frame_bytes) {
-                    CK(cudaMemcpyAsync(pixels + (uint64_t)first * stride, d_px, (size_t)n * frame_bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
-                } else {
-                    CK(cudaMemcpy2DAsync(pixels + (uint64_t)first * stride, stride, d_px, frame_bytes, frame_bytes, n, cudaMemcpyDeviceToHost, ctx->copy_stream));
-                }
+                uint32_t slice_no = 0;
+                auto drain = [&](uint32_t row0, uint32_t row1) -> int32_t {
+                    cudaEvent_t ev = slices > 1 ? ctx->ev_slice[slice_no++ & 15u] : ctx->ev_render[half];
+                    CK(cudaEventRecord(ev, ctx->stream));
+                    CK(cudaStreamWaitEvent(ctx->copy_stream, ev, 0));
+                    if (slices > 1) {   // n == 1: rows [row0, row1) of the frame
+                        CK(cudaMemcpyAsync(pixels + (uint64_t)first * stride + row0 * row_bytes, d_px + row0 * row_bytes, (size_t)(row1 - row0) * row_bytes,
+                                           cudaMemcpyDeviceToHost, ctx->copy_stream));
+                    } else if (stride == frame_bytes) {
+                        CK(cudaMemcpyAsync(pixels + (uint64_t)first * stride, d_px, (size_t)n * frame_bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+                    } else {
+                        CK(cudaMemcpy2DAsync(pixels + (uint64_t)first * stride, stride, d_px, frame_bytes, frame_bytes, n, cudaMemcpyDeviceToHost, ctx->copy_stream));
+                    }
+                    return RXC_OK;
+                };
+                // the counter block alternates with the staging half, and is read back behind the pixels on the copy stream
+                // (a small D2H on the render stream would queue behind the pixel copies on the same DMA engine and stall it)
+                ctx->W.counters = ctx->w_counters.as<DCounters>() + (size_t)half * ctx->ws_frames;
+                st = launch_group(ctx, ctx->h_frames + first, nullptr, n, d_px, frame_bytes, nullptr, nullptr, slices, drain);
+                DCounters* d_counters = ctx->W.counters;
+                ctx->W.counters = ctx->w_counters.as<DCounters>();
+                if (st != RXC_OK) return st;
+                CK(cudaMemcpyAsync(ctx->h_counters + first, d_counters, n * sizeof(DCounters), cudaMemcpyDeviceToHost, ctx->copy_stream));
                 CK(cudaEventRecord(ctx->ev_copy[half], ctx->copy_stream));
                 ctx->stats.d2h_bytes += (uint64_t)n * frame_bytes;
             }
@@ -690,7 +731,7 @@ int32_t rasterize_impl(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames,
             if (ctx->profiling) drain_events(ctx);
             bool retry = false;
             if ((st = check_group(ctx, ctx->h_counters, n_frames, &retry)) != RXC_OK) return st;
-            if (!retry) return RXC_OK;  // else: a tile-list arena overflowed somewhere; it has been grown, run the call again
+            if (!retry) { ctx->lists_sized = true; return RXC_OK; }  // else: a tile-list arena overflowed somewhere; it has been grown, run the call again
         }
         return fail(ctx, RXC_ERR_OOM, "tile-list arena kept overflowing");
     }
@@ -712,7 +753,7 @@ int32_t rasterize_impl(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames,
             uint32_t* d_ow = owner; float* d_dp = depth;
             if (owner && !dev_owner) { if ((st = reserve(ctx, ctx->d_out_owner, frame_bytes)) != RXC_OK) return st; d_ow = ctx->d_out_owner.as<uint32_t>(); }
             if (depth && !dev_depth) { if ((st = reserve(ctx, ctx->d_out_depth, frame_bytes)) != RXC_OK) return st; d_dp = ctx->d_out_depth.as<float>(); }
-            if ((st = launch_group(ctx, ctx->h_frames, ctx->h_counters, n, d_px, d_stride, d_ow, d_dp)) != RXC_OK) return st;
+            if ((st = launch_group(ctx, ctx->h_frames, ctx->h_counters, n, d_px, d_stride, d_ow, d_dp, 1u, [](uint32_t, uint32_t) -> int32_t { return RXC_OK; })) != RXC_OK) return st;
             if (!sync && dev_px && ctx->lists_sized) break;  // truly asynchronous: counters are checked at the next synchronize
             CK(cudaStreamSynchronize(ctx->stream));
             if (ctx->profiling) drain_events(ctx);
@@ -763,6 +804,8 @@ int32_t rxc_create(int32_t device, rxc_ctx** out) {
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RXC_ERR_CUDA; }
     ctx->stream = ctx->own_stream;
     ctx->raster_blocks_per_sm = rxk_raster_blocks_per_sm();
+    if (const char* e = getenv("RXC_PIECE_MB")) ctx->piece_mb = std::max(1, atoi(e));
+    if (const char* e = getenv("RXC_SLICE_MB")) ctx->slice_mb = std::max(0, atoi(e));
     if (const char* e = getenv("RXC_FRONT_CLUSTER_MAX")) ctx->front_cluster_max = atoi(e);  // tuning knob for experiments
     *out = ctx;
     return RXC_OK;
@@ -787,6 +830,7 @@ void rxc_destroy(rxc_ctx* ctx) {
     if (ctx->copy_stream) {
         cudaStreamSynchronize(ctx->copy_stream);
         for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_render[i]); cudaEventDestroy(ctx->ev_copy[i]); }
+        for (int i = 0; i < 16; ++i) if (ctx->ev_slice[i]) cudaEventDestroy(ctx->ev_slice[i]);
         cudaStreamDestroy(ctx->copy_stream);
     }
     cudaStreamDestroy(ctx->own_stream);

@@ -239,8 +239,8 @@ __device__ __forceinline__ void d_frame_setup(const SceneDev& S, const Workspace
         if (tid == 0) {
             DCounters z = {};
             Wk.counters[f] = z;
-            if (f == 0) *Wk.raster_counter = 0u;
         }
+        if (f == 0 && tid < RX_RASTER_COUNTERS) Wk.raster_counter[tid] = 0u;
         // light flicker is a per-frame constant of the light (light.rs:656-672)
         for (uint32_t i = tid; i < S.n_lights; i += blockDim.x) {
             DLight l = S.lights[i];
@@ -1650,7 +1650,7 @@ __device__ __forceinline__ uint32_t apply_2d(const SceneDev& S, const DFrame& F,
 // MODE: 0 = fast path, 1 = general (below), 2 = general + Rusteria VM programs on batches.
 template <int SAMPLE, bool PLANES, int MODE>
 __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raster(SceneDev S, Workspace Wk, RasterOut out, uint32_t n_frames,
-                                                               uint32_t tiles_per_frame) {
+                                                               uint32_t tile0, uint32_t tiles_per_frame, uint32_t counter) {
     constexpr bool GENERAL = MODE >= 1, VM = MODE == 2;
     __shared__ __align__(16) TriVis s_large[GENERAL ? 1 : RX_LARGE_CACHE];
     __shared__ uint32_t s_large_slot[GENERAL ? 1 : RX_LARGE_CACHE];
@@ -1689,11 +1689,11 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
 
     for (;;) {
         if (tid == 0) {
-            const uint32_t work = atomicAdd(Wk.raster_counter, 1u);
+            const uint32_t work = atomicAdd(Wk.raster_counter + counter, 1u);
             if (work >= total) {
                 s_work[0] = -1;
             } else {
-                const uint32_t f = work / tiles_per_frame, tile = work - f * tiles_per_frame;
+                const uint32_t f = work / tiles_per_frame, tile = tile0 + (work - f * tiles_per_frame);
                 const uint32_t tiles_x = (uint32_t)Wk.frames[f].tiles_x;
                 const uint32_t ty = tile / tiles_x;
                 s_work[0] = (int32_t)f; s_work[1] = (int32_t)((tile - ty * tiles_x) * RX_TILE_W); s_work[2] = (int32_t)(ty * RX_TILE_H);
@@ -2144,10 +2144,10 @@ cudaError_t rxk_bin_fill(const SceneDev& S, const Workspace& W, uint32_t n_frame
     k_bin_fill<<<grid, 256, 0, st>>>(S, W);
     return cudaGetLastError();
 }
-cudaError_t rxk_raster(const SceneDev& S, const Workspace& W, const RasterOut& out, uint32_t n_frames, uint32_t tiles_per_frame,
-                       int sample_mode, int grid_x, cudaStream_t st) {
+cudaError_t rxk_raster(const SceneDev& S, const Workspace& W, const RasterOut& out, uint32_t n_frames, uint32_t tile0, uint32_t n_tiles,
+                       uint32_t counter, int sample_mode, int grid_x, cudaStream_t st) {
     const bool planes = out.owner || out.depth;
-#define RX_LAUNCH(SM, PL, MD) k_raster<SM, PL, MD><<<grid_x, RX_TILE_THREADS, 0, st>>>(S, W, out, n_frames, tiles_per_frame)
+#define RX_LAUNCH(SM, PL, MD) k_raster<SM, PL, MD><<<grid_x, RX_TILE_THREADS, 0, st>>>(S, W, out, n_frames, tile0, n_tiles, counter)
 #define RX_LAUNCH2(SM, PL) do { if (S.general && S.vm.n_programs) RX_LAUNCH(SM, PL, 2); else if (S.general) RX_LAUNCH(SM, PL, 1); else RX_LAUNCH(SM, PL, 0); } while (0)
     if (sample_mode == 0) { if (planes) RX_LAUNCH2(0, true); else RX_LAUNCH2(0, false); }
     else if (sample_mode == 1) { if (planes) RX_LAUNCH2(1, true); else RX_LAUNCH2(1, false); }

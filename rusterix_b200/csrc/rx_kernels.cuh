@@ -61,7 +61,7 @@ struct Workspace {
     uint32_t* tile_fill2;
     uint32_t* lists2;       uint32_t list2_stride;
     Tri2D* tri2d;           uint32_t tri2d_stride;
-    uint32_t* raster_counter;  // one work counter for the whole launch
+    uint32_t* raster_counter;  // RX_RASTER_COUNTERS work counters, one per k_raster launch of a call (zeroed by the frame setup)
 };
 
 struct RasterOut {
@@ -104,9 +104,12 @@ cudaError_t rxk_bin_large(const SceneDev& S, const Workspace& W, uint32_t n_fram
 cudaError_t rxk_bin2d(const SceneDev& S, const Workspace& W, uint32_t n_frames, int fill, cudaStream_t st);
 cudaError_t rxk_list_sort(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, int which, cudaStream_t st);
 cudaError_t rxk_bin_fill(const SceneDev& S, const Workspace& W, uint32_t n_frames, int grid, cudaStream_t st);
-// sample_mode: RXC_SAMPLE_* when every frame of the launch uses it, 2 = mixed (read per frame)
-cudaError_t rxk_raster(const SceneDev& S, const Workspace& W, const RasterOut& out, uint32_t n_frames, uint32_t tiles_per_frame,
-                       int sample_mode, int grid, cudaStream_t st);
+// sample_mode: RXC_SAMPLE_* when every frame of the launch uses it, 2 = mixed (read per frame).  The launch covers the
+// tiles [tile0, tile0 + n_tiles) of every frame (row-major tile index: a range of tile rows is a horizontal slice of
+// the frame) and hands them out through work counter `counter` (< RX_RASTER_COUNTERS).
+#define RX_RASTER_COUNTERS 64
+cudaError_t rxk_raster(const SceneDev& S, const Workspace& W, const RasterOut& out, uint32_t n_frames, uint32_t tile0, uint32_t n_tiles,
+                       uint32_t counter, int sample_mode, int grid, cudaStream_t st);
 int rxk_raster_blocks_per_sm();
 // diagnostics: program `program` of S.vm on n records (18 floats in, 24 floats out each)
 cudaError_t rxk_vm_execute(const SceneDev& S, uint32_t program, uint32_t n, const float* d_in, float* d_out, uint32_t* d_faults, cudaStream_t st);
