@@ -49,93 +49,144 @@ __device__ __forceinline__ f3 vm_pattern_sample(const VmDev& vm, const DPattern&
     return {__ldg(d), __ldg(d + 1), __ldg(d + 2)};
 }
 
+// Transcendental and other rarely executed component-wise ops live out of line: inlined three components at a time
+// they are most of the interpreter's code size, and the dispatch loop then no longer fits the instruction cache.
+__device__ __noinline__ f3 vm_math1(uint32_t op, f3 a) {
+    switch (op) {
+        case RXVM_SIN: return {sinf(a.x), sinf(a.y), sinf(a.z)};
+        case RXVM_SIN1: case RXVM_COS1: return {sinf(a.x), 0.0f, 0.0f};          // Cos1/Cos2 call sin (execution.rs:342-349)
+        case RXVM_SIN2: case RXVM_COS2: return {sinf(a.x), sinf(a.y), 0.0f};
+        case RXVM_COS: return {cosf(a.x), cosf(a.y), cosf(a.z)};
+        case RXVM_TAN: return {tanf(a.x), tanf(a.y), tanf(a.z)};
+        case RXVM_ATAN: return {atanf(a.x), atanf(a.y), atanf(a.z)};
+        case RXVM_SQRT: return {sqrtf(a.x), sqrtf(a.y), sqrtf(a.z)};
+        case RXVM_LOG: return {logf(a.x), logf(a.y), logf(a.z)};
+        case RXVM_ROUND: return {roundf(a.x), roundf(a.y), roundf(a.z)};
+        case RXVM_CEIL: return {ceilf(a.x), ceilf(a.y), ceilf(a.z)};
+        case RXVM_RADIANS: return {a.x * 0.017453292519943295f, a.y * 0.017453292519943295f, a.z * 0.017453292519943295f};
+        case RXVM_DEGREES: return {a.x * 57.29577951308232f, a.y * 57.29577951308232f, a.z * 57.29577951308232f};
+        case RXVM_LENGTH: { const float m = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); return {m, m, m}; }
+        case RXVM_LENGTH2: return {sqrtf(a.x * a.x + a.y * a.y), 0.0f, 0.0f};
+        case RXVM_LENGTH3: return {sqrtf(a.x * a.x + a.y * a.y + a.z * a.z), 0.0f, 0.0f};
+        case RXVM_NORMALIZE: { const float m = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); if (m > 0.0f) return {a.x / m, a.y / m, a.z / m}; return a; }
+        default: return a;
+    }
+}
+
+__device__ __noinline__ f3 vm_math2(uint32_t op, f3 a, f3 b) {
+    switch (op) {
+        case RXVM_ATAN2: return {atan2f(a.x, b.x), atan2f(a.y, b.y), atan2f(a.z, b.z)};
+        case RXVM_POW: return {powf(a.x, b.x), powf(a.y, b.y), powf(a.z, b.z)};
+        case RXVM_MOD: return {a.x - b.x * floorf(a.x / b.x), a.y - b.y * floorf(a.y / b.y), a.z - b.z * floorf(a.z / b.z)};
+        case RXVM_DIV: return {a.x / b.x, a.y / b.y, a.z / b.z};
+        case RXVM_ROTATE2D: {         // execution.rs:375-383: a = vector, b = angle in degrees
+            const float rad = b.x * 0.017453292519943295f;
+            float sn, cs;
+            sincosf(rad, &sn, &cs);
+            return {a.x * cs - a.y * sn, a.x * sn + a.y * cs, a.z};
+        }
+        case RXVM_CROSS: return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+        default: return a;
+    }
+}
+
 // Runs the shade function of program P on `io`.  Returns false when a device limit was hit (stack,
 // frames, op budget) or the code is malformed; the reference would have panicked or looped.
 __device__ __noinline__ bool vm_run(const VmDev& vm, const DProgram& P, VmIO& io) {
-    f3 stack[RXVM_STACK];
+    // The value stack keeps its top in registers (`t`): positions 1..sp-1 live in stack[1..sp-1], position sp in
+    // `t`; stack[0] is a dummy that absorbs the spill of an empty stack's top.  A unary op then touches no memory,
+    // a binary op loads one operand, a push stores one (half the local-memory traffic of a stack held in memory).
+    f3 stack[RXVM_STACK + 1];
     f3 locals[RXVM_LOCAL_POOL];
     f3 globals[RXVM_GLOBALS];
     uint32_t fr_pc[RXVM_FRAMES], fr_lb[RXVM_FRAMES], fr_sb[RXVM_FRAMES], fr_mk[RXVM_FRAMES], fr_nl[RXVM_FRAMES];
     uint32_t marks[RXVM_MARKS];
     const f3 zero = {0.0f, 0.0f, 0.0f};
-    if (P.n_words == 0u) return true;                     // shade_index is None
-    if (P.shade_locals > 32u || P.n_globals > RXVM_GLOBALS) return false;
-    for (uint32_t i = 0; i < P.n_globals; ++i) globals[i] = zero;
-    for (uint32_t i = 0; i < P.shade_locals; ++i) locals[i] = zero;
+    const uint32_t n_words = P.n_words, n_globals = P.n_globals, shade_locals = P.shade_locals;
+    if (n_words == 0u) return true;                       // shade_index is None
+    if (shade_locals > 32u || n_globals > RXVM_GLOBALS) return false;
+    for (uint32_t i = 0; i < n_globals; ++i) globals[i] = zero;
+    for (uint32_t i = 0; i < shade_locals; ++i) locals[i] = zero;
     const uint32_t* __restrict__ code = vm.code + P.code_off;
-    uint32_t pc = P.entry, sp = 0, lb = 0, nl = P.shade_locals, nf = 0, nm = 0;
+    uint32_t pc = P.entry, sp = 0, lb = 0, nl = shade_locals, nf = 0, nm = 0;
     bool have_ret = false;
-    f3 ret = zero;
+    f3 ret = zero, t = zero;
+    stack[0] = zero;
 
 #define VM_NEED(n) if (sp < (uint32_t)(n)) return false
 #define VM_ROOM() if (sp >= RXVM_STACK) return false
-#define VM_UN(expr) { VM_NEED(1); const f3 a = stack[sp - 1]; stack[sp - 1] = expr; break; }
-#define VM_BIN(expr) { VM_NEED(2); const f3 b = stack[sp - 1], a = stack[sp - 2]; --sp; stack[sp - 1] = expr; break; }
+#define VM_PUSH_RAW(v) { stack[sp] = t; ++sp; t = (v); }
+#define VM_POP_RAW(dst) { dst = t; --sp; t = stack[sp]; }
+#define VM_UN(expr) { VM_NEED(1); const f3 a = t; t = expr; break; }
+#define VM_BIN(expr) { VM_NEED(2); const f3 b = t, a = stack[sp - 1]; --sp; t = expr; break; }
 #define VM_MAP1(fn) VM_UN((f3{fn(a.x), fn(a.y), fn(a.z)}))
-#define VM_PUSHV(v) { VM_ROOM(); stack[sp++] = (v); break; }
-#define VM_POPTO(dst) { VM_NEED(1); dst = stack[--sp]; break; }
+#define VM_PUSHV(v) { VM_ROOM(); VM_PUSH_RAW(v); break; }
+#define VM_POPTO(dst) { VM_NEED(1); VM_POP_RAW(dst); break; }
 #define VM_B(x) ((x) ? f3{1.0f, 1.0f, 1.0f} : f3{0.0f, 0.0f, 0.0f})
 
     for (uint32_t budget = RXVM_BUDGET; budget != 0u; --budget) {
-        if (pc >= P.n_words) return false;
+        if (pc >= n_words) return false;
         const uint32_t w = __ldg(code + pc++);
-        const uint32_t a24 = w >> 8;
-        switch (w & 0xFFu) {
-            case RXVM_LOAD_GLOBAL: if (a24 >= P.n_globals) return false; VM_PUSHV(globals[a24]);
-            case RXVM_STORE_GLOBAL: if (a24 >= P.n_globals) return false; VM_POPTO(globals[a24]);
-            case RXVM_LOAD_LOCAL: if (a24 >= nl) return false; VM_PUSHV(locals[lb + a24]);
-            case RXVM_STORE_LOCAL: if (a24 >= nl) return false; VM_POPTO(locals[lb + a24]);
-            case RXVM_SWAP: { VM_NEED(2); const f3 t = stack[sp - 1]; stack[sp - 1] = stack[sp - 2]; stack[sp - 2] = t; break; }
+        const uint32_t a24 = w >> 8, op = w & 0xFFu;
+        // nvcc lowers the 100-way switch below to a compare tree (7 levels, ~23 instructions per op); the five ops that
+        // make up ~60 % of what shader programs execute are tested first, most frequent first
+        if (op == RXVM_PUSH) {
+            if (pc + 3u > n_words) return false;
+            VM_ROOM();
+            VM_PUSH_RAW((f3{__uint_as_float(__ldg(code + pc)), __uint_as_float(__ldg(code + pc + 1)), __uint_as_float(__ldg(code + pc + 2))}));
+            pc += 3u;
+            continue;
+        }
+        if (op == RXVM_LOAD_LOCAL) { if (a24 >= nl) return false; VM_ROOM(); VM_PUSH_RAW(locals[lb + a24]); continue; }
+        if (op == RXVM_MUL) { VM_NEED(2); const f3 a = stack[sp - 1]; --sp; t = {a.x * t.x, a.y * t.y, a.z * t.z}; continue; }
+        if (op == RXVM_ADD) { VM_NEED(2); const f3 a = stack[sp - 1]; --sp; t = {a.x + t.x, a.y + t.y, a.z + t.z}; continue; }
+        if (op == RXVM_STORE_LOCAL) { if (a24 >= nl) return false; VM_NEED(1); VM_POP_RAW(locals[lb + a24]); continue; }
+        switch (op) {
+            case RXVM_LOAD_GLOBAL: if (a24 >= n_globals) return false; VM_PUSHV(globals[a24]);
+            case RXVM_STORE_GLOBAL: if (a24 >= n_globals) return false; VM_POPTO(globals[a24]);
+            case RXVM_SWAP: { VM_NEED(2); const f3 x = stack[sp - 1]; stack[sp - 1] = t; t = x; break; }
             case RXVM_GET_COMPONENTS: {   // execution.rs:135-157
                 VM_NEED(1);
-                const f3 v = stack[sp - 1];
-                const float c[4] = {v.x, v.y, v.z, 0.0f};
+                const float c[4] = {t.x, t.y, t.z, 0.0f};
                 const uint32_t n = a24 & 7u, i0 = (a24 >> 3) & 3u, i1 = (a24 >> 5) & 3u, i2 = (a24 >> 7) & 3u;
                 f3 r = zero;
                 if (n == 1u) r = {c[i0], c[i0], c[i0]};
                 else if (n == 2u) r = {c[i0], c[i1], 0.0f};
                 else if (n == 3u) r = {c[i0], c[i1], c[i2]};
-                stack[sp - 1] = r;
+                t = r;
                 break;
             }
             case RXVM_SET_COMPONENTS: {   // execution.rs:158-183
                 VM_NEED(2);
-                const f3 value = stack[sp - 1];
-                f3 t = stack[sp - 2];
+                const f3 value = t;
+                f3 d = stack[sp - 1];
                 --sp;
                 const float c[3] = {value.x, value.y, value.z};
                 const uint32_t n = a24 & 7u;
                 for (uint32_t i = 0; i < n && i < 3u; ++i) {
                     const uint32_t idx = (a24 >> (3u + 2u * i)) & 3u;
-                    if (idx == 0u) t.x = c[i]; else if (idx == 1u) t.y = c[i]; else if (idx == 2u) t.z = c[i];
+                    if (idx == 0u) d.x = c[i]; else if (idx == 1u) d.y = c[i]; else if (idx == 2u) d.z = c[i];
                 }
-                stack[sp - 1] = t;
+                t = d;
                 break;
             }
-            case RXVM_PUSH: {
-                if (pc + 3u > P.n_words) return false;
-                VM_ROOM();
-                stack[sp++] = {__uint_as_float(__ldg(code + pc)), __uint_as_float(__ldg(code + pc + 1)), __uint_as_float(__ldg(code + pc + 2))};
-                pc += 3u;
-                break;
-            }
-            case RXVM_CLEAR: if (sp) --sp; break;
-            case RXVM_DUP: if (sp) { VM_ROOM(); stack[sp] = stack[sp - 1]; ++sp; } break;
+            case RXVM_CLEAR: if (sp) { --sp; t = stack[sp]; } break;
+            case RXVM_DUP: if (sp) { VM_ROOM(); stack[sp] = t; ++sp; } break;
             case RXVM_FUNCTION_CALL: {    // execution.rs:186-223
-                if (pc >= P.n_words || nf >= RXVM_FRAMES) return false;
+                if (pc >= n_words || nf >= RXVM_FRAMES) return false;
                 const uint32_t target = __ldg(code + pc++);
                 const uint32_t arity = a24 & 0xFFu, total = a24 >> 8;
                 const uint32_t nlb = lb + nl;
-                if (total > 32u || nlb + total > RXVM_LOCAL_POOL || target >= P.n_words) return false;
+                if (total > 32u || nlb + total > RXVM_LOCAL_POOL || target >= n_words) return false;
                 for (uint32_t i = 0; i < total; ++i) locals[nlb + i] = zero;
                 for (uint32_t i = arity; i-- > 0u;)
-                    if (sp) { const f3 v = stack[--sp]; if (i < total) locals[nlb + i] = v; else return false; }
+                    if (sp) { f3 v; VM_POP_RAW(v); if (i < total) locals[nlb + i] = v; else return false; }
                 fr_pc[nf] = pc; fr_lb[nf] = lb; fr_nl[nf] = nl; fr_sb[nf] = sp; fr_mk[nf] = nm; ++nf;
                 lb = nlb; nl = total; pc = target;
                 break;
             }
             case RXVM_RETURN:             // execution.rs:224-234
-                ret = sp ? stack[--sp] : zero;
+                if (sp) { VM_POP_RAW(ret); } else ret = zero;
                 have_ret = true;
                 // fall through: leave the function
             case RXVM_END: {
@@ -144,88 +195,62 @@ __device__ __noinline__ bool vm_run(const VmDev& vm, const DProgram& P, VmIO& io
                 const uint32_t base = fr_sb[nf];
                 f3 r = zero;
                 if (have_ret) { r = ret; have_ret = false; }
-                else if (sp > base) r = stack[--sp];
-                if (sp > base) sp = base;
+                else if (sp > base) { VM_POP_RAW(r); }
+                if (sp > base) { sp = base; t = stack[sp]; }
                 nm = fr_mk[nf]; lb = fr_lb[nf]; nl = fr_nl[nf]; pc = fr_pc[nf];
                 VM_ROOM();
-                stack[sp++] = r;
+                VM_PUSH_RAW(r);
                 break;
             }
-            case RXVM_JZ: { VM_NEED(1); const f3 v = stack[--sp]; if (v.x == 0.0f) { if (a24 > P.n_words) return false; pc = a24; } break; }
-            case RXVM_JMP: if (a24 > P.n_words) return false; pc = a24; break;
+            case RXVM_JZ: { VM_NEED(1); f3 v; VM_POP_RAW(v); if (v.x == 0.0f) { if (a24 > n_words) return false; pc = a24; } break; }
+            case RXVM_JMP: if (a24 > n_words) return false; pc = a24; break;
             case RXVM_MARK: if (nm >= RXVM_MARKS) return false; marks[nm++] = sp; break;
-            case RXVM_TRUNC: if (nm == 0u) return false; if (sp > marks[nm - 1]) sp = marks[nm - 1]; break;
+            case RXVM_TRUNC: if (nm == 0u) return false; if (sp > marks[nm - 1]) { sp = marks[nm - 1]; t = stack[sp]; } break;
             case RXVM_UNMARK: if (nm == 0u) return false; --nm; break;
-            case RXVM_PACK2: { VM_NEED(2); const f3 y = stack[sp - 1], x = stack[sp - 2]; --sp; stack[sp - 1] = {x.x, y.x, 0.0f}; break; }
-            case RXVM_PACK3: { VM_NEED(3); const f3 z = stack[sp - 1], y = stack[sp - 2], x = stack[sp - 3]; sp -= 2; stack[sp - 1] = {x.x, y.x, z.x}; break; }
-            case RXVM_ADD: VM_BIN((f3{a.x + b.x, a.y + b.y, a.z + b.z}))
+            case RXVM_PACK2: { VM_NEED(2); const f3 y = t, x = stack[sp - 1]; --sp; t = {x.x, y.x, 0.0f}; break; }
+            case RXVM_PACK3: { VM_NEED(3); const f3 z = t, y = stack[sp - 1], x = stack[sp - 2]; sp -= 2; t = {x.x, y.x, z.x}; break; }
             case RXVM_SUB: VM_BIN((f3{a.x - b.x, a.y - b.y, a.z - b.z}))
-            case RXVM_MUL: VM_BIN((f3{a.x * b.x, a.y * b.y, a.z * b.z}))
-            case RXVM_DIV: VM_BIN((f3{a.x / b.x, a.y / b.y, a.z / b.z}))
-            case RXVM_LENGTH: { VM_NEED(1); const f3 a = stack[sp - 1]; const float m = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); stack[sp - 1] = {m, m, m}; break; }
-            case RXVM_LENGTH2: VM_UN((f3{sqrtf(a.x * a.x + a.y * a.y), 0.0f, 0.0f}))
-            case RXVM_LENGTH3: VM_UN((f3{sqrtf(a.x * a.x + a.y * a.y + a.z * a.z), 0.0f, 0.0f}))
             case RXVM_ABS: VM_MAP1(fabsf)
-            case RXVM_SIN: VM_MAP1(sinf)
-            case RXVM_SIN1: case RXVM_COS1: VM_UN((f3{sinf(a.x), 0.0f, 0.0f}))          // Cos1/Cos2 call sin (execution.rs:342-349)
-            case RXVM_SIN2: case RXVM_COS2: VM_UN((f3{sinf(a.x), sinf(a.y), 0.0f}))
-            case RXVM_COS: VM_MAP1(cosf)
-            case RXVM_TAN: VM_MAP1(tanf)
-            case RXVM_ATAN: VM_MAP1(atanf)
-            case RXVM_ATAN2: VM_BIN((f3{atan2f(a.x, b.x), atan2f(a.y, b.y), atan2f(a.z, b.z)}))
-            case RXVM_ROTATE2D: {         // execution.rs:375-383
-                VM_NEED(2);
-                const f3 ang = stack[sp - 1], v = stack[sp - 2];
-                --sp;
-                const float rad = ang.x * 0.017453292519943295f;
-                float s, c;
-                sincosf(rad, &s, &c);
-                stack[sp - 1] = {v.x * c - v.y * s, v.x * s + v.y * c, v.z};
-                break;
+            case RXVM_SIN: case RXVM_SIN1: case RXVM_COS1: case RXVM_SIN2: case RXVM_COS2: case RXVM_COS: case RXVM_TAN: case RXVM_ATAN:
+            case RXVM_SQRT: case RXVM_LOG: case RXVM_ROUND: case RXVM_CEIL: case RXVM_RADIANS: case RXVM_DEGREES: case RXVM_LENGTH:
+            case RXVM_LENGTH2: case RXVM_LENGTH3: case RXVM_NORMALIZE:
+                VM_NEED(1); t = vm_math1(op, t); break;
+            case RXVM_ATAN2: case RXVM_POW: case RXVM_MOD: case RXVM_DIV: case RXVM_ROTATE2D: case RXVM_CROSS: {
+                VM_NEED(2); const f3 a = stack[sp - 1]; --sp; t = vm_math2(op, a, t); break;
             }
-            case RXVM_DOT: { VM_NEED(2); const f3 b = stack[sp - 1], a = stack[sp - 2]; --sp; const float d = a.x * b.x + a.y * b.y + a.z * b.z; stack[sp - 1] = {d, d, d}; break; }
+            case RXVM_DOT: { VM_NEED(2); const f3 b = t, a = stack[sp - 1]; --sp; const float d = a.x * b.x + a.y * b.y + a.z * b.z; t = {d, d, d}; break; }
             case RXVM_DOT2: VM_BIN((f3{a.x * b.x + a.y * b.y, 0.0f, 0.0f}))
             case RXVM_DOT3: VM_BIN((f3{a.x * b.x + a.y * b.y + a.z * b.z, 0.0f, 0.0f}))
-            case RXVM_CROSS: VM_BIN((f3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}))
-            case RXVM_NORMALIZE: { VM_NEED(1); const f3 a = stack[sp - 1]; const float m = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); if (m > 0.0f) stack[sp - 1] = {a.x / m, a.y / m, a.z / m}; break; }
             case RXVM_FLOOR: VM_MAP1(floorf)
-            case RXVM_CEIL: VM_MAP1(ceilf)
-            case RXVM_ROUND: VM_MAP1(roundf)
             case RXVM_FRACT: VM_UN((f3{a.x - floorf(a.x), a.y - floorf(a.y), a.z - floorf(a.z)}))
-            case RXVM_MOD: VM_BIN((f3{a.x - b.x * floorf(a.x / b.x), a.y - b.y * floorf(a.y / b.y), a.z - b.z * floorf(a.z / b.z)}))
-            case RXVM_RADIANS: VM_UN((f3{a.x * 0.017453292519943295f, a.y * 0.017453292519943295f, a.z * 0.017453292519943295f}))
-            case RXVM_DEGREES: VM_UN((f3{a.x * 57.29577951308232f, a.y * 57.29577951308232f, a.z * 57.29577951308232f}))
             case RXVM_MIN: VM_BIN((f3{fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)}))
             case RXVM_MAX: VM_BIN((f3{fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)}))
             case RXVM_MIX: {
                 VM_NEED(3);
-                const f3 c = stack[sp - 1], b = stack[sp - 2], a = stack[sp - 3];
+                const f3 c = t, b = stack[sp - 1], a = stack[sp - 2];
                 sp -= 2;
-                stack[sp - 1] = {a.x + (b.x - a.x) * c.x, a.y + (b.y - a.y) * c.y, a.z + (b.z - a.z) * c.z};
+                t = {a.x + (b.x - a.x) * c.x, a.y + (b.y - a.y) * c.y, a.z + (b.z - a.z) * c.z};
                 break;
             }
             case RXVM_SMOOTHSTEP: {       // execution.rs:458-476
                 VM_NEED(3);
-                const f3 c = stack[sp - 1], b = stack[sp - 2], a = stack[sp - 3];
+                const f3 c = t, b = stack[sp - 1], a = stack[sp - 2];
                 sp -= 2;
                 const float denom = b.x - a.x;
-                float t = denom != 0.0f ? (c.x - a.x) / denom : 0.0f;
-                if (t < 0.0f) t = 0.0f; else if (t > 1.0f) t = 1.0f;
-                const float s = t * t * (3.0f - 2.0f * t);
-                stack[sp - 1] = {s, s, s};
+                float u = denom != 0.0f ? (c.x - a.x) / denom : 0.0f;
+                if (u < 0.0f) u = 0.0f; else if (u > 1.0f) u = 1.0f;
+                const float sm = u * u * (3.0f - 2.0f * u);
+                t = {sm, sm, sm};
                 break;
             }
             case RXVM_STEP: VM_BIN((f3{b.x >= a.x ? 1.0f : 0.0f, b.y >= a.y ? 1.0f : 0.0f, b.z >= a.z ? 1.0f : 0.0f}))
             case RXVM_CLAMP: {
                 VM_NEED(3);
-                const f3 c = stack[sp - 1], b = stack[sp - 2], a = stack[sp - 3];
+                const f3 c = t, b = stack[sp - 1], a = stack[sp - 2];
                 sp -= 2;
-                stack[sp - 1] = {rx_clamp(a.x, b.x, c.x), rx_clamp(a.y, b.y, c.y), rx_clamp(a.z, b.z, c.z)};
+                t = {rx_clamp(a.x, b.x, c.x), rx_clamp(a.y, b.y, c.y), rx_clamp(a.z, b.z, c.z)};
                 break;
             }
-            case RXVM_SQRT: VM_MAP1(sqrtf)
-            case RXVM_LOG: VM_MAP1(logf)
-            case RXVM_POW: VM_BIN((f3{powf(a.x, b.x), powf(a.y, b.y), powf(a.z, b.z)}))
             case RXVM_EQ: VM_BIN(VM_B(a.x == b.x))
             case RXVM_NE: VM_BIN(VM_B(a.x != b.x))
             case RXVM_LT: VM_BIN(VM_B(a.x < b.x))
@@ -236,11 +261,11 @@ __device__ __noinline__ bool vm_run(const VmDev& vm, const DProgram& P, VmIO& io
             case RXVM_OR: VM_BIN(VM_B((a.x != 0.0f) | (b.x != 0.0f)))
             case RXVM_NOT: VM_UN(VM_B(a.x == 0.0f))
             case RXVM_NEG: VM_UN((f3{-a.x, -a.y, -a.z}))
-            case RXVM_PRINT: VM_NEED(1); --sp; break;
+            case RXVM_PRINT: { VM_NEED(1); --sp; t = stack[sp]; break; }
             case RXVM_UV: VM_PUSHV(io.uv)
             case RXVM_SET_UV: VM_POPTO(io.uv)
             case RXVM_NORMAL: VM_PUSHV(io.normal)
-            case RXVM_SET_NORMAL: { VM_NEED(1); io.normal = rx_normalize3(stack[--sp]); break; }   // .normalized(), execution.rs:583
+            case RXVM_SET_NORMAL: { VM_NEED(1); f3 v; VM_POP_RAW(v); io.normal = rx_normalize3(v); break; }   // .normalized(), execution.rs:583
             case RXVM_HITPOINT: VM_PUSHV(io.hitpoint)
             case RXVM_TIME: VM_PUSHV(io.time)
             case RXVM_COLOR: VM_PUSHV(io.color)
@@ -257,32 +282,32 @@ __device__ __noinline__ bool vm_run(const VmDev& vm, const DProgram& P, VmIO& io
             case RXVM_SET_BUMP: VM_POPTO(io.bump)
             case RXVM_SAMPLE: {           // execution.rs:625-633
                 VM_NEED(2);
-                const f3 b = stack[sp - 1], a = stack[sp - 2];
+                const f3 b = t, a = stack[sp - 1];
                 --sp;
                 const uint32_t i = vm_as_index(b.x);
-                stack[sp - 1] = i < vm.n_patterns ? vm_pattern_sample(vm, vm.patterns[i], a) : zero;
+                t = i < vm.n_patterns ? vm_pattern_sample(vm, vm.patterns[i], a) : zero;
                 break;
             }
             case RXVM_SAMPLE_NORMAL: {    // execution.rs:634-649
                 VM_NEED(2);
-                const f3 b = stack[sp - 1], a = stack[sp - 2];
+                const f3 b = t, a = stack[sp - 1];
                 --sp;
                 const uint32_t i = vm_as_index(b.x);
                 f3 r = zero;
                 if (i < vm.n_patterns_normal) {
-                    const f3 nm = vm_pattern_sample(vm, vm.patterns[vm.n_patterns + i], a);
-                    r = {nm.x * 2.0f - 1.0f, nm.y * 2.0f - 1.0f, nm.z * 2.0f - 1.0f};
+                    const f3 nm3 = vm_pattern_sample(vm, vm.patterns[vm.n_patterns + i], a);
+                    r = {nm3.x * 2.0f - 1.0f, nm3.y * 2.0f - 1.0f, nm3.z * 2.0f - 1.0f};
                 }
-                stack[sp - 1] = r;
+                t = r;
                 break;
             }
             case RXVM_PALETTE_INDEX: {    // execution.rs:735-742: nothing is pushed for a missing colour
                 VM_NEED(1);
-                const f3 a = stack[--sp];
+                f3 a; VM_POP_RAW(a);
                 const uint32_t i = vm_as_index(a.x);
                 if (i < vm.n_palette) {
                     const float4 c = __ldg(vm.palette + i);
-                    if (c.x != 0.0f) { VM_ROOM(); stack[sp++] = {c.y, c.z, c.w}; }
+                    if (c.x != 0.0f) { VM_ROOM(); VM_PUSH_RAW((f3{c.y, c.z, c.w})); }
                 }
                 break;
             }
@@ -292,6 +317,8 @@ __device__ __noinline__ bool vm_run(const VmDev& vm, const DProgram& P, VmIO& io
     return false;  // op budget exhausted
 #undef VM_NEED
 #undef VM_ROOM
+#undef VM_PUSH_RAW
+#undef VM_POP_RAW
 #undef VM_UN
 #undef VM_BIN
 #undef VM_MAP1

@@ -544,3 +544,29 @@ def test_more_lights_than_the_shared_memory_table_and_more_large_triangles_than_
     st = _run(cfg, what="40 lights, 220 large triangles")
     from rusterix_b200 import DeviceContext
     assert DeviceContext.get(0).stats().last_large_tris > 160
+
+
+@pytest.mark.parametrize("size", [(2600, 1700), (4099, 1031), (2048, 2176)])
+def test_sliced_host_output_matches_device_output(size):
+    """Host pixel buffers of large frames are rendered and drained as horizontal slices (rx_api.cu, pipelined host
+    path): same bytes as the device-resident render, for heights that are not a multiple of the GPU tile, for a
+    row band, and for a batch of frames."""
+    import torch
+
+    w, h = size
+    cfg = scenes.map_config(w, h, 40, logo_size=64)
+    r = cfg.rasterizer()
+    dev = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda:0")
+    r.rasterize(cfg.scene, dev, w, h, cfg.tile_size, cfg.assets)
+    ref = dev.cpu().numpy()
+    host = np.zeros((h, w, 4), dtype=np.uint8)
+    r.rasterize(cfg.scene, host, w, h, cfg.tile_size, cfg.assets)
+    assert np.array_equal(host, ref)
+    y0, y1 = 64, h - 37
+    band = np.zeros((y1 - y0, w, 4), dtype=np.uint8)
+    r.rasterize(cfg.scene, band, w, h, cfg.tile_size, cfg.assets, band=(y0, y1))
+    assert np.array_equal(band, ref[y0:y1])
+    out = np.zeros((3, h, w, 4), dtype=np.uint8)
+    Rasterizer.rasterize_batch([r, r, r], cfg.scene, out, w, h, cfg.tile_size, cfg.assets)
+    for k in range(3):
+        assert np.array_equal(out[k], ref)
