@@ -428,50 +428,71 @@ def main():
         dist.destroy_process_group()
 
 
-def band_split(rank, world, local_rank, dev, flush, barrier, steps=5, warmup=3):
+def band_split(rank, world, local_rank, dev, flush, barrier, steps=5, warmup=3, balance_iters=12):
     """BASELINE.json config D: one 7680x4320 frame of the 1M-triangle scene split by screen band over the ranks
-    (SURVEY 8e).  Every rank runs setup on the replicated geometry and bins / rasterises only its rows; strong
-    scaling of a single frame, time = max over ranks; the NCCL gather of the bands to rank 0 is timed separately."""
+    (SURVEY 8e).  Every rank runs setup on the replicated geometry (triangles outside its rows are dropped before
+    their records are written) and bins / rasterises only its rows; strong scaling of a single frame, time = max over
+    ranks; the NCCL gather of the bands to rank 0 is timed separately.  Band boundaries: equal heights first (reported
+    as `equal_bands_ms_per_frame`), then moved by `mgpu.BandBalancer` from the ranks' measured times (a few frames),
+    frozen at the best split found, and timed."""
     import torch
     import torch.distributed as dist
     from rusterix_b200 import Rasterizer, mgpu
 
     cfg, frame_ids, desc = build_workload("dense8k", 1, 0, 1)
     W, H = cfg.width, cfg.height
-    y0, y1 = mgpu.band_for_rank(H, rank, world, 32)
-    out = torch.empty((1, max(1, y1 - y0), W, 4), dtype=torch.uint8, device=dev)
-    batch = Rasterizer.prepare_batch([cfg.rasterizer(frame_ids[0]).on_device(local_rank)], cfg.scene, W, H, cfg.tile_size, cfg.assets,
-                                     band=(y0, y1), device=local_rank) if y1 > y0 else None
+    rast = cfg.rasterizer(frame_ids[0]).on_device(local_rank)
+    out = torch.empty((1, H, W, 4), dtype=torch.uint8, device=dev)   # any band of this rank fits
 
-    def step():
+    def prepare(band):
+        y0, y1 = band
+        return Rasterizer.prepare_batch([rast], cfg.scene, W, H, cfg.tile_size, cfg.assets, band=(y0, y1), device=local_rank) if y1 > y0 else None
+
+    def timed_frame(batch):
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record()
         if batch is not None:
             batch.run(out, sync=False)
-
-    for _ in range(warmup):
-        step(); flush.zero_()
-    barrier()
-    ms = 0.0
-    for _ in range(steps):
-        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-        a.record(); step(); b.record(); flush.zero_()
+        b.record(); flush.zero_()
         barrier()
-        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms += float(t.item())
-    ms /= steps
+        return a.elapsed_time(b)
+
+    def measure(batch):
+        for _ in range(warmup):
+            timed_frame(batch)
+        ms = 0.0
+        for _ in range(steps):
+            t = torch.tensor([timed_frame(batch)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms += float(t.item())
+        return ms / steps
+
+    bal = mgpu.BandBalancer(H, world, 32)
+    equal_ms = measure(prepare(bal.band(rank)))
+    for _ in range(balance_iters):
+        batch = prepare(bal.band(rank))
+        timed_frame(batch)                       # the first frame with new bands may regrow the tile-list arenas
+        bal.update(mgpu.all_gather_times(timed_frame(batch), device=dev))
+    bands = bal.use_best()
+    batch = prepare(bands[rank])
+    ms = measure(batch)
+    y0, y1 = bands[rank]
+    mine = out[0, :max(0, y1 - y0)]
     for _ in range(2):
-        mgpu.gather_bands_to_rank0(out[0, :max(0, y1 - y0)], H, W, rank, world, align=32)
+        mgpu.gather_ragged_bands_to_rank0(mine, bands, H, W, rank, world)
     barrier()
     g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
     g0.record()
-    mgpu.gather_bands_to_rank0(out[0, :max(0, y1 - y0)], H, W, rank, world, align=32)
+    mgpu.gather_ragged_bands_to_rank0(mine, bands, H, W, rank, world)
     g1.record()
     barrier()
     t = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return {"workload": desc + ", rows split into %d bands" % world, "scaling": "strong", "ms_per_frame": ms,
             "Mpixel_per_s": W * H / (ms * 1e-3) / 1e6, "frames_per_s": 1.0 / (ms * 1e-3), "gather_ms": float(t.item()),
-            "bytes_to_rank0": (H - (mgpu.band_for_rank(H, 0, world, 32)[1])) * W * 4}
+            "bytes_to_rank0": (H - bands[0][1]) * W * 4, "band_edges": [b[0] for b in bands] + [H],
+            "bands": "cost-balanced from the ranks' measured times (mgpu.BandBalancer, %d frames)" % balance_iters,
+            "equal_bands_ms_per_frame": equal_ms}
 
 
 def secondary(wname, local_rank, dev, flush, steps=5, warmup=3):

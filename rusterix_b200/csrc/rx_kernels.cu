@@ -512,6 +512,9 @@ __device__ __forceinline__ void d_tri_setup(const SceneDev& S, const Workspace& 
         const uint32_t meta = ch.batch | tri_meta_flags(FB);  // make_tri adds RX_META_FASTDIV
         TriVis tv; TriShade tsh;
         vis = make_tri(P, T.uv, T.nn, B.cull_mode, edge_vis, F.width, F.height, meta, &tv, &tsh, &bin.bbx, &bin.bby);
+        // band rendering (a rank of a row split): a triangle whose pixel rows miss the band is dropped before its
+        // 176 B of records are written; the batch bbox above still saw it, like the reference's projected_vertices
+        if (vis && ((int)(bin.bby >> 16) <= F.band_y0 || (int)(bin.bby & 0xFFFFu) >= F.band_y1)) { vis = false; bin.bbx = 0u; bin.bby = 0u; }
         if (vis) {
             Wk.vis[(size_t)f * Wk.slot_stride + slot] = tv;
             Wk.shade[(size_t)f * Wk.slot_stride + slot] = tsh;
@@ -633,7 +636,8 @@ __device__ __forceinline__ void d_clip_emit(const SceneDev& S, const Workspace& 
             const uint32_t slot = first + (uint32_t)(j - 1);
             TriBin bin = {0u, 0u, slot, c.batch};
             TriVis tv; TriShade tsh;
-            if (make_tri(P, uv, nn, B.cull_mode, true, F.width, F.height, meta, &tv, &tsh, &bin.bbx, &bin.bby)) {
+            if (make_tri(P, uv, nn, B.cull_mode, true, F.width, F.height, meta, &tv, &tsh, &bin.bbx, &bin.bby) &&
+                !((int)(bin.bby >> 16) <= F.band_y0 || (int)(bin.bby & 0xFFFFu) >= F.band_y1)) {
                 const uint32_t pos = atomicAdd(&C.n_new_slots, 1u);
                 if (pos < new_cap) {
                     Wk.vis[(size_t)f * Wk.slot_stride + slot] = tv;

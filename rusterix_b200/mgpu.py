@@ -94,3 +94,100 @@ def gather_frames_to_rank0(frames: torch.Tensor, rank: int, world: int):
         return stacked.reshape((-1,) + tuple(frames.shape[1:]))
     dist.gather(frames, None, dst=0)
     return None
+
+
+class BandBalancer:
+    """Cost-balanced row bands for the band split of one large frame.
+
+    Equal-height bands are badly unbalanced on real views (the horizon band of the 1M-triangle scene holds more than
+    half of all triangle references, the sky bands almost none), and a band split runs at the speed of its slowest
+    rank.  The balancer keeps the bands contiguous (one send per rank to gather them) and moves their boundaries
+    from the times the ranks measured for the previous frame.  It keeps a cost profile over the GPU tile rows of
+    the frame; every measured band time (minus the rank-independent front-end time) rescales the profile over the
+    rows of that band, so that boundaries that move from frame to frame resolve where the cost really sits (a band
+    straddling sky and terrain is not uniform).  The new boundaries cut the cumulative profile at k/world of its
+    total.  Successive frames of a camera path are coherent, so a few frames converge; `update` needs every rank's
+    time (`all_gather_times`), which is the only communication and is off the data path."""
+
+    def __init__(self, height: int, world: int, align: int = TILE_H):
+        self.height, self.world, self.align = int(height), int(world), int(align)
+        self.n_rows = (self.height + self.align - 1) // self.align          # tile rows
+        self.profile = [1.0] * self.n_rows                                   # relative cost per tile row
+        self.edges = [band_for_rank(height, r, world, align)[0] for r in range(world)] + [int(height)]
+        self.best = (float("inf"), list(self.edges))
+
+    def bands(self) -> List[Tuple[int, int]]:
+        return [(self.edges[r], self.edges[r + 1]) for r in range(self.world)]
+
+    def band(self, rank: int) -> Tuple[int, int]:
+        return self.edges[rank], self.edges[rank + 1]
+
+    def use_best(self) -> List[Tuple[int, int]]:
+        """Freeze the boundaries that gave the smallest slowest-rank time so far (static views, benchmarks)."""
+        self.edges = list(self.best[1])
+        return self.bands()
+
+    def update(self, times_ms: List[float]) -> List[Tuple[int, int]]:
+        """New boundaries from the per-rank times of the frame just rendered with the current ones."""
+        if len(times_ms) != self.world:
+            raise ValueError("one time per rank")
+        worst = max(times_ms)
+        if worst < self.best[0]:
+            self.best = (worst, list(self.edges))
+        fixed = 0.9 * min(times_ms)   # setup on the replicated geometry costs every rank about the same
+        measured = [max(t - fixed, 1e-6) for t in times_ms]
+        scale = sum(measured) / max(sum(self.profile), 1e-30)
+        for r in range(self.world):
+            a, b = self.edges[r] // self.align, (self.edges[r + 1] + self.align - 1) // self.align
+            if b <= a:
+                continue
+            predicted = sum(self.profile[a:b]) * scale
+            k = (measured[r] / max(predicted, 1e-30)) ** 0.6   # damped: the ranks' corrections interact through `scale`
+            for i in range(a, b):
+                self.profile[i] *= k
+        total = sum(self.profile)
+        new_edges, acc, i = [0], 0.0, 0
+        for k in range(1, self.world):
+            target = total * k / self.world
+            while i < self.n_rows and acc + self.profile[i] <= target:
+                acc += self.profile[i]
+                i += 1
+            # cut inside tile row i when it helps: boundaries stay on tile rows, so round to the nearer side
+            cut = i + (1 if i < self.n_rows and (target - acc) > 0.5 * self.profile[i] else 0)
+            y = min(cut * self.align, self.height)
+            new_edges.append(max(y, new_edges[-1]))
+        new_edges.append(self.height)
+        self.edges = new_edges
+        return self.bands()
+
+
+def all_gather_times(ms: float, device=None) -> List[float]:
+    """Every rank's time for the last frame (one small all_gather; NCCL on GPUs, gloo on CPU)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return [float(ms)]
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [float(x.item()) for x in out]
+
+
+def gather_ragged_bands_to_rank0(band: torch.Tensor, bands: List[Tuple[int, int]], height: int, width: int, rank: int, world: int):
+    """Like `gather_bands_to_rank0` for arbitrary contiguous bands (the balancer's)."""
+    if world == 1:
+        return band
+    if rank == 0:
+        full = torch.empty((height, width, 4), dtype=torch.uint8, device=band.device)
+        y0, y1 = bands[0]
+        full[y0:y1].copy_(band[: y1 - y0])
+        reqs = []
+        for r in range(1, world):
+            y0, y1 = bands[r]
+            if y1 > y0:
+                reqs.append(dist.irecv(full[y0:y1], src=r))
+        for q in reqs:
+            q.wait()
+        return full
+    y0, y1 = bands[rank]
+    if y1 > y0:
+        dist.send(band[: y1 - y0].contiguous(), dst=0)
+    return None

@@ -122,6 +122,21 @@ def _gloo_worker(rank, world, port, q):
             ids = mgpu.shard_frames(F * world, 0, world)
             for g in range(F * world):
                 ok = ok and int(allf[g, 0, 0, 0]) == 10 * (g // world) + (g % world)
+        # cost-balanced bands: both ranks see both times, compute the same boundaries, and the ragged gather
+        # reassembles the frame
+        bal = mgpu.BandBalancer(h, world, align=2)
+        for _ in range(3):
+            y0, y1 = bal.band(rank)
+            ms = 1.0 + 0.1 * sum(1 + 9 * (y >= 40) for y in range(y0, y1))   # rows 40.. are ten times as expensive
+            times = mgpu.all_gather_times(ms)
+            ok = ok and len(times) == world and abs(times[rank] - ms) < 1e-9
+            bal.update(times)
+        bands = bal.bands()
+        ok = ok and bands[0][1] == bands[1][0] and bands[0][1] > 25   # the boundary moved towards the expensive rows
+        y0, y1 = bands[rank]
+        got = mgpu.gather_ragged_bands_to_rank0(full[y0:y1].clone(), bands, h, w, rank, world)
+        if rank == 0:
+            ok = ok and torch.equal(got, full)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
@@ -140,6 +155,30 @@ def test_gather_to_rank0_world2_gloo():
     for p in ps:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_band_balancer_converges_on_a_skewed_cost_profile():
+    """mgpu.BandBalancer: contiguous, tile-aligned bands that cover the frame; on a profile like the 1M-triangle
+    view (cheap sky rows, an expensive horizon) the slowest rank ends close to the balanced optimum."""
+    H, align = 4320, 32
+    cost = np.full(H, 0.057e-3); cost[1632:2176] = 0.73e-3; cost[2176:2720] = 0.54e-3; cost[2720:3264] = 0.37e-3; cost[3264:] = 0.31e-3
+    for world in (1, 2, 3, 4, 8):
+        bal = mgpu.BandBalancer(H, world, align)
+        first = None
+        for _ in range(14):
+            bands = bal.bands()
+            assert bands[0][0] == 0 and bands[-1][1] == H
+            assert all(a[1] == b[0] for a, b in zip(bands, bands[1:])) and all(y0 <= y1 for y0, y1 in bands)
+            assert all(y % align == 0 for y0, y1 in bands[:-1] for y in (y0, y1))
+            times = [0.14 + float(cost[y0:y1].sum()) for y0, y1 in bands]
+            first = first if first is not None else max(times)
+            bal.update(times)
+        bands = bal.use_best()
+        worst = max(0.14 + float(cost[y0:y1].sum()) for y0, y1 in bands)
+        optimum = 0.14 + float(cost.sum()) / world
+        assert worst <= first + 1e-12 and worst <= 1.12 * optimum, (world, worst, optimum)
+    with pytest.raises(ValueError):
+        mgpu.BandBalancer(H, 4).update([1.0, 2.0])
 
 
 def test_bresenham_membership_closed_form_matches_the_serial_walk():
