@@ -820,6 +820,10 @@ __global__ void __launch_bounds__(256) k_front_cluster(SceneDev S, Workspace Wk,
 #ifndef RX_OPAQUE
 #define RX_OPAQUE 2
 #endif
+#ifndef RX_BULK_STORE
+#define RX_BULK_STORE 0   // 1: finished tiles leave shared memory through the bulk-copy (TMA) engine, 32 x cp.async.bulk of one
+                          // 128 B row per tile.  Measured slower than 256 x STG.128 (map 4K 1.41 -> 1.50 ms): off.
+#endif
 #define RX_LARGE_CACHE 160   // large-triangle records kept in shared memory across the tiles of a frame
 #define RX_COLOR_STRIDE 40   // words per tile row in shared memory: the 4 rows a warp writes hit disjoint banks
 
@@ -1661,7 +1665,7 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
     __shared__ uint16_t s_sel[GENERAL ? 1 : RX_LARGE_CACHE];
     __shared__ uint32_t s_nsel;
     __shared__ int32_t s_work[4];   // frame (-1 = done), tile x0, tile y0, tile index
-    __shared__ __align__(16) uint32_t s_color[RX_TILE_H * RX_COLOR_STRIDE];
+    __shared__ __align__(16) uint32_t s_color[(RX_BULK_STORE ? 2 : 1) * RX_TILE_H * RX_COLOR_STRIDE];  // bulk store: two tiles, one draining
     __shared__ float4 s_state[4 * RX_TILE_THREADS];  // (z, owner, alpha, beta) of pixel k of thread t at [k*256 + t]
     __shared__ float2 s_ostate[GENERAL ? 4 * RX_TILE_THREADS : 1];  // (z, owner) of the opacity layer
     __shared__ ShadeConst s_k;                       // frame constants of the deferred shade
@@ -1686,6 +1690,7 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
 #endif
     const uint32_t total = n_frames * tiles_per_frame;
     uint32_t cached_frame = 0xFFFFFFFFu, n_cached = 0;
+    uint32_t coff = 0;   // which half of s_color this tile uses (bulk store: the other half may still be draining)
     {
         const float x = (float)tid * (1.0f / 255.0f);
         s_kd[tid] = (__fmaf_rn(0.6975f, x * x, 0.3025f) * x) * (1.0f - 0.04f);  // visible after the first tile's barrier
@@ -1849,7 +1854,7 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                 color = F.has_bg_color ? F.bg_color : 0u;  // rasterizer.rs:277-282
                 if (!F.ignore_bg_shader && F.bg_shader != RXC_BG_NONE) color = shade_background(F, px, py);
             }
-            s_color[cbase + ((k & 1) << 3) + (k >> 1) * (4 * RX_COLOR_STRIDE)] = color;
+            s_color[coff + cbase + ((k & 1) << 3) + (k >> 1) * (4 * RX_COLOR_STRIDE)] = color;
             if (PLANES && px < fw && py < fy1) {
                 const size_t o = (size_t)(py - F.band_y0) * (size_t)fw + (size_t)px;
                 if (out.owner) out.owner[o] = owner;
@@ -1882,32 +1887,55 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
 #pragma unroll 1
                     for (int k = 0; k < 4; ++k) {
                         const int px = px0 + ((k & 1) << 3), py = py0 + ((k >> 1) << 2);
-                        uint32_t* c = &s_color[cbase + ((k & 1) << 3) + (k >> 1) * (4 * RX_COLOR_STRIDE)];
+                        uint32_t* c = &s_color[coff + cbase + ((k & 1) << 3) + (k >> 1) * (4 * RX_COLOR_STRIDE)];
                         *c = apply_2d<VM>(S, F, lights, fb2, T, px, py, smode, *c, &vm_fault);
                     }
                 }
             }
         }
         if (VM && vm_fault) atomicOr(&Wk.counters[f].overflow, 16u);  // a program hit a device limit
+#if RX_BULK_STORE
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the tile's pixels, written through the generic proxy, for the bulk-copy engine
+#endif
         __syncthreads();
 
-        // write back: RGBA8 rows of the tile, 128-bit stores when rows are 16 B aligned
+        // write back: RGBA8 rows of the tile.  Full tiles with 16 B aligned rows leave through the bulk-copy (TMA) engine,
+        // one 128 B row per lane of warp 0 (cp.async.bulk shared -> global); the warp only waits until shared memory has
+        // been read, the global writes complete asynchronously.
         uint8_t* frame_px = out.pixels + (size_t)f * out.frame_stride;
         const bool full_tile = (tx0 + RX_TILE_W <= fw) && (ty0 + RX_TILE_H <= fy1);
         if (out.vec_store && full_tile) {
+#if RX_BULK_STORE
+            if (warp == 0) {
+                const uint32_t src = (uint32_t)__cvta_generic_to_shared(&s_color[coff + lane * RX_COLOR_STRIDE]);
+                uint8_t* dst = frame_px + ((size_t)(ty0 - F.band_y0 + (int)lane) * (size_t)fw + (size_t)tx0) * 4;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" ::"l"(dst), "r"(src) : "memory");
+            }
+#else
             const int r = (int)tid >> 3, c4 = (int)tid & 7;   // 8 x 16 B per 32-pixel row
-            const uint4 v = *reinterpret_cast<const uint4*>(&s_color[r * RX_COLOR_STRIDE + c4 * 4]);
+            const uint4 v = *reinterpret_cast<const uint4*>(&s_color[coff + r * RX_COLOR_STRIDE + c4 * 4]);
             uint4* dst = reinterpret_cast<uint4*>(frame_px + ((size_t)(ty0 - F.band_y0 + r) * (size_t)fw + (size_t)tx0) * 4) + c4;
             *dst = v;
+#endif
         } else {
             for (int i = (int)tid; i < RX_TILE_W * RX_TILE_H; i += RX_TILE_THREADS) {
                 const int r = i >> 5, c = i & 31;
                 if (tx0 + c < fw && ty0 + r < fy1)
                     reinterpret_cast<uint32_t*>(frame_px)[(size_t)(ty0 - F.band_y0 + r) * (size_t)fw + (size_t)(tx0 + c)] =
-                        s_color[r * RX_COLOR_STRIDE + c];
+                        s_color[coff + r * RX_COLOR_STRIDE + c];
             }
         }
-        __syncthreads();  // s_color, s_work and s_nsel are rewritten by the next tile
+#if RX_BULK_STORE
+        // the next tile writes the other half: its previous drain (two tiles ago) must have read shared memory; at most
+        // this tile's group stays in flight
+        // (every tile commits a group, an empty one when it was stored directly, so "all but the latest" means the other half)
+        if (warp == 0) {
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        }
+        coff ^= (uint32_t)(RX_TILE_H * RX_COLOR_STRIDE);
+#endif
+        __syncthreads();  // s_color (its other half), s_work and s_nsel are rewritten by the next tile
     }
 }
 
