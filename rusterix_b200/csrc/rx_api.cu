@@ -545,8 +545,8 @@ int32_t launch_group(rxc_ctx* ctx, const DFrame* h_frames, DCounters* h_counters
     // walk of one CTA loses against the parallel launches)
     const bool small_front = !S.general && S.n_chunks <= 2 && S.n_b2 <= 4 && tiles_per_frame <= 16384;
     // mid-sized scenes: one cluster of CTAs per frame, cluster barriers instead of kernel boundaries
-    const bool cluster_front = !small_front && !S.general && ctx->front_cluster_max != 0 && S.n_chunks <= (uint32_t)ctx->front_cluster_max &&
-                               S.n_b2 <= 64 && tiles_per_frame <= 65536;
+    const bool cluster_front = !small_front && ctx->front_cluster_max != 0 && S.n_chunks <= (uint32_t)ctx->front_cluster_max &&
+                               S.n_b2 <= 64 && tiles_per_frame <= 65536 && (!S.general || S.n_rec2d <= 512);   // long sorted 2D lists want k_list_sort's CTA per tile (834 records: no gain)
     if (small_front) { LaunchScope l(ctx, RXK_FRONT_SMALL); CK(rxk_front_small(S, ctx->W, n, tiles_per_frame, ctx->stream)); }
     else if (cluster_front) { LaunchScope l(ctx, RXK_FRONT_SMALL); CK(rxk_front_cluster(S, ctx->W, n, tiles_per_frame, ctx->stream)); }
     else { LaunchScope l(ctx, RXK_FRAME_SETUP); CK(rxk_frame_setup(S, ctx->W, n, tiles_per_frame, ctx->stream)); }
@@ -561,7 +561,7 @@ int32_t launch_group(rxc_ctx* ctx, const DFrame* h_frames, DCounters* h_counters
         if (S.general) { LaunchScope l(ctx, RXK_BIN_FILL); CK(rxk_bin_large(S, ctx->W, n, 1, ctx->sm_count, ctx->stream)); }
         if (S.general) { LaunchScope l(ctx, RXK_LIST_SORT); CK(rxk_list_sort(S, ctx->W, n, tiles_per_frame, 0, ctx->stream)); }
     }
-    if (S.general && S.n_rec2d) {  // 2D records into sorted per-tile lists
+    if (S.general && S.n_rec2d && !cluster_front) {  // 2D records into sorted per-tile lists
         { LaunchScope l(ctx, RXK_BIN2D); CK(rxk_bin2d(S, ctx->W, n, 0, ctx->stream)); }
         { LaunchScope l(ctx, RXK_TILE_ALLOC); CK(rxk_tile_alloc(S, ctx->W, n, tiles_per_frame, 1, 1, ctx->stream)); }
         { LaunchScope l(ctx, RXK_BIN2D); CK(rxk_bin2d(S, ctx->W, n, 1, ctx->stream)); }

@@ -744,6 +744,109 @@ __device__ __forceinline__ void d_bin_fill(const SceneDev& S, const Workspace& W
 }
 
 // ---------------------------------------------------------------------------------------------
+// general mode: 2D record binning (one warp per record, lanes over the tiles of its bbox), binning of the large
+// triangles into the ordered lists (one warp per triangle, skipping tiles the conservative overlap test excludes),
+// and a warp-level list sort for the fused front end
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rect_overlaps(const TriVis& T, int tx0, int ty0, int tx1, int ty1);
+
+__device__ __forceinline__ void d_bin2d(const SceneDev& S, const Workspace& Wk, int fill, Blk bk) {
+    const uint32_t f = bk.y;
+    const DFrame& F = Wk.frames[f];
+    const uint32_t lane = threadIdx.x & 31, wpg = (bk.nx * blockDim.x) >> 5;
+    uint32_t* tc = Wk.tile_count2 + (size_t)f * Wk.tile_stride;
+    const uint32_t* tb = Wk.tile_base2 + (size_t)f * Wk.tile_stride;
+    uint32_t* tf = Wk.tile_fill2 + (size_t)f * Wk.tile_stride;
+    uint32_t* lists = Wk.lists2 + (size_t)f * Wk.list2_stride;
+    for (uint32_t r = (bk.x * blockDim.x + threadIdx.x) >> 5; r < S.n_rec2d; r += wpg) {
+        const Tri2D& T = Wk.tri2d[(size_t)f * Wk.tri2d_stride + r];
+        int tx0, tx1, ty0, ty1;
+        if (!bin_tile_range(F, T.bbx, T.bby, &tx0, &tx1, &ty0, &ty1)) continue;
+        const int w = tx1 - tx0 + 1, n = w * (ty1 - ty0 + 1);
+        for (int i = (int)lane; i < n; i += 32) {
+            const int t = (ty0 + i / w) * F.tiles_x + tx0 + i % w;
+            if (!fill) { atomicAdd(&tc[t], 1u); continue; }
+            if (tc[t] == 0u) continue;  // list dropped on arena overflow
+            lists[tb[t] + atomicAdd(&tf[t], 1u)] = r;
+        }
+    }
+}
+
+__device__ __forceinline__ void d_bin_large(const SceneDev& S, const Workspace& Wk, int fill, Blk bk) {
+    const uint32_t f = bk.y;
+    const DFrame& F = Wk.frames[f];
+    const DCounters& C = Wk.counters[f];
+    const uint32_t n_large = min(C.n_large, Wk.large_stride);
+    const uint32_t lane = threadIdx.x & 31, wpg = (bk.nx * blockDim.x) >> 5;
+    uint32_t* tc = Wk.tile_count + (size_t)f * Wk.tile_stride;
+    const uint32_t* tb = Wk.tile_base + (size_t)f * Wk.tile_stride;
+    uint32_t* tf = Wk.tile_fill + (size_t)f * Wk.tile_stride;
+    uint32_t* lists = Wk.lists + (size_t)f * Wk.list_stride;
+    for (uint32_t k = (bk.x * blockDim.x + threadIdx.x) >> 5; k < n_large; k += wpg) {
+        const uint32_t slot = Wk.large[(size_t)f * Wk.large_stride + k];
+        const TriVis& T = Wk.vis[(size_t)f * Wk.slot_stride + slot];
+        int tx0, tx1, ty0, ty1;
+        if (!bin_tile_range(F, T.bbx, T.bby, &tx0, &tx1, &ty0, &ty1)) continue;
+        const int w = tx1 - tx0 + 1, n = w * (ty1 - ty0 + 1);
+        for (int i = (int)lane; i < n; i += 32) {
+            const int tx = tx0 + i % w, ty = ty0 + i / w;
+            const int px0 = tx * RX_TILE_W, py0 = F.band_y0 + ty * RX_TILE_H;
+            if (rect_overlaps(T, px0, py0, min(px0 + RX_TILE_W, F.width), min(py0 + RX_TILE_H, F.band_y1)) == 0u) continue;
+            const int t = ty * F.tiles_x + tx;
+            if (!fill) { atomicAdd(&tc[t], 1u); continue; }
+            if (tc[t] == 0u) continue;  // list dropped on arena overflow
+            lists[tb[t] + atomicAdd(&tf[t], 1u)] = slot;
+        }
+    }
+}
+
+// One warp per tile, tiles strided over the warps of the (virtual) grid: lists of fewer than two entries are done,
+// the others are sorted ascending in place (bitonic over the power-of-two allocation, padded with 0xFFFFFFFF).  The
+// small scenes that take the fused front end have short lists; k_list_sort (a CTA per tile) serves the big ones.
+__device__ __forceinline__ void d_list_sort_warp(const Workspace& Wk, int which, uint32_t tiles_per_frame, Blk bk) {
+    const uint32_t f = bk.y, lane = threadIdx.x & 31, wpg = (bk.nx * blockDim.x) >> 5;
+    const uint32_t* tc = (which ? Wk.tile_count2 : Wk.tile_count) + (size_t)f * Wk.tile_stride;
+    const uint32_t* tb = (which ? Wk.tile_base2 : Wk.tile_base) + (size_t)f * Wk.tile_stride;
+    uint32_t* lists = which ? Wk.lists2 + (size_t)f * Wk.list2_stride : Wk.lists + (size_t)f * Wk.list_stride;
+    for (uint32_t t0 = ((bk.x * blockDim.x + threadIdx.x) >> 5) * 32u; t0 < tiles_per_frame; t0 += wpg * 32u) {
+        // 32 tiles per warp and round: one coalesced read of their counts, then the warp visits the ones with work
+        const uint32_t mine = t0 + lane < tiles_per_frame ? tc[t0 + lane] : 0u;
+        uint32_t todo = __ballot_sync(0xFFFFFFFFu, mine >= 2u);
+        while (todo) {
+            const int b = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const uint32_t n = __shfl_sync(0xFFFFFFFFu, mine, b);
+            uint32_t* d = lists + tb[t0 + b];
+            const uint32_t P = 1u << (32 - __clz(n - 1u));
+            if (P <= 32u) {   // in registers
+                uint32_t v = lane < n ? d[lane] : 0xFFFFFFFFu;
+                for (uint32_t k = 2; k <= P; k <<= 1)
+                    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                        const uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, v, j);
+                        const bool up = (lane & k) == 0u, low = (lane & j) == 0u;
+                        v = (low == up) ? min(v, o) : max(v, o);
+                    }
+                if (lane < n) d[lane] = v;
+            } else {          // in place, in global memory (L1 of this SM), warp-synchronous
+                for (uint32_t i = n + lane; i < P; i += 32) d[i] = 0xFFFFFFFFu;
+                __syncwarp();
+                for (uint32_t k = 2; k <= P; k <<= 1)
+                    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                        for (uint32_t i = lane; i < P; i += 32) {
+                            const uint32_t ixj = i ^ j;
+                            if (ixj > i) {
+                                const uint32_t a = d[i], c = d[ixj];
+                                if ((a > c) == ((i & k) == 0u)) { d[i] = c; d[ixj] = a; }
+                            }
+                        }
+                        __syncwarp();
+                    }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // the front-end as kernels ...
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_frame_setup(SceneDev S, Workspace Wk, uint32_t tiles_per_frame) { d_frame_setup(S, Wk, tiles_per_frame, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
@@ -753,6 +856,8 @@ __global__ void __launch_bounds__(128) k_clip_emit(SceneDev S, Workspace Wk) { d
 __global__ void __launch_bounds__(256) k_bin_count(SceneDev S, Workspace Wk) { d_bin_count(S, Wk, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
 __global__ void __launch_bounds__(256) k_tile_alloc(Workspace Wk, uint32_t tiles_per_frame, int which, int pow2) { d_tile_alloc(Wk, tiles_per_frame, which, pow2, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
 __global__ void __launch_bounds__(256) k_bin_fill(SceneDev S, Workspace Wk) { d_bin_fill(S, Wk, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
+__global__ void __launch_bounds__(256) k_bin2d(SceneDev S, Workspace Wk, int fill) { d_bin2d(S, Wk, fill, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
+__global__ void __launch_bounds__(256) k_bin_large(SceneDev S, Workspace Wk, int fill) { d_bin_large(S, Wk, fill, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
 
 // ... and fused for small scenes: one CTA per frame runs every front-end phase back to back (7 launches and
 // their gaps cost ~70 us per call, more than rasterising a 1080p frame of such a scene).  Phases communicate
@@ -788,27 +893,41 @@ __global__ void __launch_bounds__(256) k_front_cluster(SceneDev S, Workspace Wk,
     cg::cluster_group cl = cg::this_cluster();
     const uint32_t r = cl.block_rank(), R = cl.num_blocks();   // the cluster spans grid.x; grid.y = frames
     const uint32_t f = blockIdx.y;
+    const bool general = S.general != 0u, d2 = general && S.n_rec2d != 0u, d3 = S.n_tris != 0u;   // uniform over the grid
+    const uint32_t ntb = (tiles_per_frame + 255u) / 256u;
     for (uint32_t v = r; v < n_frame_blocks; v += R) { d_frame_setup(S, Wk, tiles_per_frame, Blk{v, f, n_frame_blocks}); __syncthreads(); }
-    if (S.n_tris == 0u) return;                                 // uniform over the cluster
+    if (!d3 && !d2) return;
     cl.sync();
-    for (uint32_t v = r; v < S.n_chunks; v += R) { d_tri_setup(S, Wk, Blk{v, f, S.n_chunks}); __syncthreads(); }
+    // the 2D chain of general mode (count, allocate, fill, sort) rides along with the first 3D phases
+    if (d3) for (uint32_t v = r; v < S.n_chunks; v += R) { d_tri_setup(S, Wk, Blk{v, f, S.n_chunks}); __syncthreads(); }
+    if (d2) d_bin2d(S, Wk, 0, Blk{r, f, R});
     cl.sync();
-    const uint32_t nfb = (S.n_b3 + 7u) / 8u;
-    for (uint32_t v = r; v < nfb; v += R) d_batch_finalize(S, Wk, Blk{v, f, nfb});
+    if (d3) { const uint32_t nfb = (S.n_b3 + 7u) / 8u; for (uint32_t v = r; v < nfb; v += R) d_batch_finalize(S, Wk, Blk{v, f, nfb}); }
+    if (d2) for (uint32_t v = r; v < ntb; v += R) d_tile_alloc(Wk, tiles_per_frame, 1, 1, Blk{v, f, ntb});
     cl.sync();
-    d_clip_emit(S, Wk, Blk{r, f, R});
+    if (d3) d_clip_emit(S, Wk, Blk{r, f, R});
+    if (d2) d_bin2d(S, Wk, 1, Blk{r, f, R});
     cl.sync();
-    d_bin_count(S, Wk, Blk{r, f, R});
+    if (d3) d_bin_count(S, Wk, Blk{r, f, R});
+    if (d2) d_list_sort_warp(Wk, 1, tiles_per_frame, Blk{r, f, R});
+    if (!d3) return;
     cl.sync();
-    // nothing binned (every visible triangle went to the large list): all tile lists stay empty
-    if (Wk.counters[f].n_visible == Wk.counters[f].n_large) {
+    if (general) {   // the ordered lists hold every triangle: the large ones are binned too
+        d_bin_large(S, Wk, 0, Blk{r, f, R});
+        cl.sync();
+    } else if (Wk.counters[f].n_visible == Wk.counters[f].n_large) {
+        // nothing binned (every visible triangle went to the large list): all tile lists stay empty
         for (uint32_t i = r * blockDim.x + threadIdx.x; i < tiles_per_frame; i += R * blockDim.x) Wk.tile_base[(size_t)f * Wk.tile_stride + i] = 0u;
         return;
     }
-    const uint32_t ntb = (tiles_per_frame + 255u) / 256u;
-    for (uint32_t v = r; v < ntb; v += R) d_tile_alloc(Wk, tiles_per_frame, 0, 0, Blk{v, f, ntb});
+    for (uint32_t v = r; v < ntb; v += R) d_tile_alloc(Wk, tiles_per_frame, 0, general ? 1 : 0, Blk{v, f, ntb});
     cl.sync();
     d_bin_fill(S, Wk, Blk{r, f, R});
+    if (general) {
+        d_bin_large(S, Wk, 1, Blk{r, f, R});
+        cl.sync();
+        d_list_sort_warp(Wk, 0, tiles_per_frame, Blk{r, f, R});
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1936,63 +2055,6 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
         coff ^= (uint32_t)(RX_TILE_H * RX_COLOR_STRIDE);
 #endif
         __syncthreads();  // s_color (its other half), s_work and s_nsel are rewritten by the next tile
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// 2D record binning (general mode): one warp per record, lanes over the tiles of its bbox
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_bin2d(SceneDev S, Workspace Wk, int fill) {
-    const uint32_t f = blockIdx.y;
-    const DFrame& F = Wk.frames[f];
-    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (r >= S.n_rec2d) return;
-    const Tri2D& T = Wk.tri2d[(size_t)f * Wk.tri2d_stride + r];
-    int tx0, tx1, ty0, ty1;
-    if (!bin_tile_range(F, T.bbx, T.bby, &tx0, &tx1, &ty0, &ty1)) return;
-    uint32_t* tc = Wk.tile_count2 + (size_t)f * Wk.tile_stride;
-    const uint32_t* tb = Wk.tile_base2 + (size_t)f * Wk.tile_stride;
-    uint32_t* tf = Wk.tile_fill2 + (size_t)f * Wk.tile_stride;
-    uint32_t* lists = Wk.lists2 + (size_t)f * Wk.list2_stride;
-    const int w = tx1 - tx0 + 1, n = w * (ty1 - ty0 + 1);
-    for (int i = (int)lane; i < n; i += 32) {
-        const int t = (ty0 + i / w) * F.tiles_x + tx0 + i % w;
-        if (!fill) { atomicAdd(&tc[t], 1u); continue; }
-        if (tc[t] == 0u) continue;  // list dropped on arena overflow
-        lists[tb[t] + atomicAdd(&tf[t], 1u)] = r;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// k_bin_large (general mode): the ordered tile lists hold every triangle, so the triangles k_bin_count put
-// on the large list are binned here, one warp per triangle, lanes over the tiles of the bbox, skipping tiles
-// the conservative overlap test excludes
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_bin_large(SceneDev S, Workspace Wk, int fill) {
-    const uint32_t f = blockIdx.y;
-    const DFrame& F = Wk.frames[f];
-    const DCounters& C = Wk.counters[f];
-    const uint32_t n_large = min(C.n_large, Wk.large_stride);
-    const uint32_t lane = threadIdx.x & 31, wpg = (gridDim.x * blockDim.x) >> 5;
-    uint32_t* tc = Wk.tile_count + (size_t)f * Wk.tile_stride;
-    const uint32_t* tb = Wk.tile_base + (size_t)f * Wk.tile_stride;
-    uint32_t* tf = Wk.tile_fill + (size_t)f * Wk.tile_stride;
-    uint32_t* lists = Wk.lists + (size_t)f * Wk.list_stride;
-    for (uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n_large; k += wpg) {
-        const uint32_t slot = Wk.large[(size_t)f * Wk.large_stride + k];
-        const TriVis& T = Wk.vis[(size_t)f * Wk.slot_stride + slot];
-        int tx0, tx1, ty0, ty1;
-        if (!bin_tile_range(F, T.bbx, T.bby, &tx0, &tx1, &ty0, &ty1)) continue;
-        const int w = tx1 - tx0 + 1, n = w * (ty1 - ty0 + 1);
-        for (int i = (int)lane; i < n; i += 32) {
-            const int tx = tx0 + i % w, ty = ty0 + i / w;
-            const int px0 = tx * RX_TILE_W, py0 = F.band_y0 + ty * RX_TILE_H;
-            if (rect_overlaps(T, px0, py0, min(px0 + RX_TILE_W, F.width), min(py0 + RX_TILE_H, F.band_y1)) == 0u) continue;
-            const int t = ty * F.tiles_x + tx;
-            if (!fill) { atomicAdd(&tc[t], 1u); continue; }
-            if (tc[t] == 0u) continue;  // list dropped on arena overflow
-            lists[tb[t] + atomicAdd(&tf[t], 1u)] = slot;
-        }
     }
 }
 
