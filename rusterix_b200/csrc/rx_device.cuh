@@ -81,7 +81,8 @@ struct DChunkInfo {      // what shading reads of a Chunk; entry [n_chunks] hold
 };
 
 struct DLight {          // rxc_light + the per-frame flicker factor (light.rs:656-672)
-    uint32_t light_type, emitting, from_linedef, pad;
+    uint32_t light_type, emitting, from_linedef;
+    float range2;   // per frame: squared distance from which the light contributes nothing (0: never, +inf: no range)
     float px, py, pz, intensity;
     float cr, cg, cb, flicker_factor;
     float start_distance, end_distance, cone_angle, width;

@@ -253,6 +253,11 @@ __device__ __forceinline__ void d_frame_setup(const SceneDev& S, const Workspace
             }
             l.flicker_factor = factor;
             l.inv_range = 1.0f / (l.start_distance - l.end_distance);
+            // early range cull of the deferred shade: radiance_at returns None from end_distance on (light.rs:536-653) for
+            // every positional type; the slack keeps the decision with the `dist >= end_distance` test behind it
+            if (!l.emitting) l.range2 = 0.0f;
+            else if (l.light_type == RXC_LIGHT_AMBIENT || l.light_type == RXC_LIGHT_AMBIENT_DAYLIGHT) l.range2 = CUDART_INF_F;
+            else l.range2 = l.end_distance > 0.0f ? l.end_distance * l.end_distance * 1.00001f : (l.end_distance <= 0.0f ? 0.0f : CUDART_INF_F);  // NaN: no cull
             Wk.lights[(size_t)f * Wk.lights_stride + i] = l;
         }
         return;
@@ -1232,13 +1237,13 @@ __device__ __forceinline__ uint32_t shade_owner(const SceneDev& S, const ShadeCo
         const DLight& L = lights[li];
         const f3 to_l = {L.px - world.x, L.py - world.y, L.pz - world.z};
         const float d2 = fdot3(to_l, to_l);
+        if (d2 >= L.range2) continue;   // out of range (or not emitting): before the normalisation and the type dispatch
         const float inv_d = fast_rsqrt(d2);
         const f3 ldir = {to_l.x * inv_d, to_l.y * inv_d, to_l.z * inv_d};
         const float n_dot_l = fmaxf(fdot3(normal, ldir), 0.0f);
+        if (!(n_dot_l > 0.0f)) continue;   // shade_fast_brdf adds nothing then (rasterizer.rs:1912-1951), whatever the radiance
         f3 radiance;
         if (!light_radiance_fast(L, n_dot_l, ldir, d2 * inv_d, &radiance)) continue;
-        // shade_fast_brdf, rasterizer.rs:1912-1951
-        if (!(n_dot_l > 0.0f)) continue;
         const f3 h = fnormalize3(rx_add3(ldir, view_dir));
         const float n_dot_h = fmaxf(fdot3(normal, h), 0.0f);
         const float h2 = n_dot_h * n_dot_h;
