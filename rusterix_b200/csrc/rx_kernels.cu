@@ -683,10 +683,15 @@ __device__ __forceinline__ void d_bin_count(const SceneDev& S, const Workspace& 
         const DFrameBatch& FB = Wk.fb[(size_t)f * Wk.fb_stride + b.batch];
         x0 = max(x0, FB.sc_x0); x1 = min(x1, FB.sc_x1); y0 = max(y0, FB.sc_y0); y1 = min(y1, FB.sc_y1);
         if (x0 >= x1 || y0 >= y1) { bins[i].bbx = 0u; bins[i].bby = 0u; continue; }
-        b.bbx = (uint32_t)x0 | ((uint32_t)x1 << 16);
-        b.bby = (uint32_t)y0 | ((uint32_t)y1 << 16);
-        TriVis* tv = Wk.vis + (size_t)f * Wk.slot_stride + b.slot;
-        tv->bbx = b.bbx; tv->bby = b.bby;
+        // the scissor almost never clips a triangle of its own batch (it is the union of the API tiles that overlap the
+        // batch bbox): the records are rewritten only when it, or the band, did
+        const uint32_t nbx = (uint32_t)x0 | ((uint32_t)x1 << 16), nby = (uint32_t)y0 | ((uint32_t)y1 << 16);
+        bool dirty = nbx != b.bbx || nby != b.bby;
+        if (dirty) {
+            b.bbx = nbx; b.bby = nby;
+            TriVis* tv = Wk.vis + (size_t)f * Wk.slot_stride + b.slot;
+            tv->bbx = nbx; tv->bby = nby;
+        }
         int tx0, tx1, ty0, ty1;
         bin_tile_range(F, b.bbx, b.bby, &tx0, &tx1, &ty0, &ty1);
         const int nt = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
@@ -695,11 +700,12 @@ __device__ __forceinline__ void d_bin_count(const SceneDev& S, const Workspace& 
             if (k < Wk.large_stride) Wk.large[(size_t)f * Wk.large_stride + k] = b.slot;
             else atomicOr(&C.overflow, 2u);
             b.batch |= 0x80000000u;
+            dirty = true;
         } else {
             for (int ty = ty0; ty <= ty1; ++ty)
                 for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(&tc[ty * F.tiles_x + tx], 1u);
         }
-        bins[i] = b;
+        if (dirty) bins[i] = b;
     }
 }
 
