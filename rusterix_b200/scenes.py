@@ -8,6 +8,7 @@ resolution, tile size, sampling) ready for `Rasterizer.setup(..).rasterize(..)`.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Callable, List, Optional
 
@@ -606,11 +607,14 @@ def pattern_bank(size=64):
 
 
 def shader_wood():
-    """examples/cube_shaded.rs:46-102, compiled by hand into the op sequence of its shade()."""
+    """rusteria/examples/wood.rusteria (= the shade() of examples/cube_shaded.rs:46-102), lowered by hand the way the
+    Rusteria compiler does it.  `vec2(1.5)` is (1.5, 0, 0): the parser pads a one-argument vec2 with a zero
+    (rusteria/src/parser.rs:880-896; vec3 broadcasts instead).  Rendered over uv like rsia does, the oracle's VM
+    reproduces the reference's own wood.png bit for bit (tests/test_rusteria_golden.py)."""
     from . import vm
     b = vm.Body()
     t = b.let(vm.time_ * 0.0)
-    uv2 = b.let(vm.uv / 3.0 - vm.vec2(1.5, 1.5))
+    uv2 = b.let(vm.uv / 3.0 - vm.vec2(1.5, 0.0))
     n1 = b.let(vm.sample(uv2 + vm.vec2(t.x, 0.0), "fbm_perlin"))
     n2 = b.let(vm.sample(uv2 * 2.0 + vm.vec2(0.0, (t * 0.7).x), "fbm_perlin"))
     turb = b.let(0.65 * n1 + 0.35 * n2)
@@ -629,6 +633,88 @@ def shader_wood():
     b.set("Color", vm.mix(vm.color, vm.color * 0.9, cathedral * 0.2))
     b.set("Roughness", 0.6 + cathedral * 0.3)
     return vm.Program([b.code], 0, b.n_locals, 0)
+
+
+def shader_marble():
+    """rusteria/examples/marble.rusteria lowered by hand (golden: the reference's marble.png)."""
+    from . import vm
+    b = vm.Body()
+    t = b.let(1.0)
+    uv2 = b.let(vm.uv * 1.0)
+    n1 = b.let(vm.sample(uv2 + vm.vec2(t, 0.0), "fbm_perlin"))
+    n2 = b.let(vm.sample(uv2 * 2.0 + vm.vec2(0.0, t), "fbm_perlin"))
+    turb = b.let(0.6 * n1 + 0.4 * n2)
+    bands = b.let(uv2.x + turb * 0.6)
+    s = b.let(vm.sin(bands * 8.0))
+    veins = b.let(vm.pow_(1.0 - vm.abs_(s), 3.0))
+    b.set("Color", vm.mix(vm.vec3(0.92, 0.93, 0.96), vm.vec3(0.18, 0.20, 0.24), veins))
+    m = b.let(vm.sample(uv2 * 0.5 + vm.vec2(0.0, 0.0), "value"))
+    b.set("Color", vm.color * (0.9 + 0.1 * m))
+    return vm.Program([b.code], 0, b.n_locals, 0)
+
+
+def shader_wood_ring():
+    """rusteria/examples/wood_ring.rusteria lowered by hand: a user function (`pdelta`, whose value is the expression
+    statement left on the stack), fract, nested vec2 (golden: the reference's wood_ring.png)."""
+    from . import vm
+    f = vm.Body(2)   # fn pdelta(a, c) { fract(a - c + 0.5) - 0.5; }
+    f.code += (vm.fract(f.param(0) - f.param(1) + 0.5) - 0.5).ops
+    b = vm.Body()
+    t = b.let(vm.time_ * 0.1)
+    uv0 = b.let(vm.fract(vm.uv))
+    cx = b.let(0.5)
+    cy = b.let(0.5)
+    dx = b.let(vm.call(0, 2, uv0.x, cx))
+    dy = b.let(vm.call(0, 2, uv0.y, cy))
+    r = b.let(vm.length(vm.vec2(dx, dy)))
+    w1 = b.let(vm.sample(vm.fract(uv0 * 2.0 + vm.vec2(t, 0.0)), "fbm_perlin"))
+    w2 = b.let(vm.sample(vm.fract(uv0 * 4.0 + vm.vec2(0.0, t)), "fbm_perlin"))
+    turb = b.let((0.6 * w1 + 0.4 * w2) - 0.5)
+    ring_freq = b.let(14.0)
+    ring_warp = b.let(0.05)
+    phase = b.let(r + ring_warp * turb)
+    waves = b.let(vm.sin(phase * ring_freq * 6.2831853))
+    rings_mask = b.let(vm.pow_(1.0 - vm.abs_(waves), 6.0))
+    grain_uv = b.let(vm.fract(vm.vec2(uv0.x * 8.0, uv0.y * 64.0)))
+    g = b.let(vm.sample(grain_uv + vm.vec2(0.0, vm.fract(t)), "value"))
+    grain = b.let((g - 0.5) * 2.0)
+    b.set("Color", vm.mix(vm.vec3(0.72, 0.52, 0.32), vm.vec3(0.45, 0.30, 0.16), rings_mask))
+    b.set("Color", vm.color * (1.0 + 0.05 * grain))
+    b.set("Roughness", 0.6)
+    return vm.Program([f.code, b.code], 1, b.n_locals, 0)
+
+
+def rusteria_pattern_bank(directory):
+    """rusteria's patterns() bank from its embedded PNGs (rusteria/src/textures/patterns.rs:136-175 via
+    TexStorage::from_png_bytes, textures/mod.rs:64-82: channel / 255).  Patterns whose PNG is not in `directory`
+    stay 1x1 zero textures, like an entry build_patterns() did not find."""
+    from PIL import Image
+    from . import vm
+    bank = [(1, 1, np.zeros((1, 3), np.float32)) for _ in range(7)]
+    for name, i in vm.PATTERN_INDEX.items():
+        path = os.path.join(directory, name + ".png")
+        if os.path.exists(path):
+            im = np.asarray(Image.open(path).convert("RGB"))
+            bank[i] = (im.shape[1], im.shape[0], (im.astype(np.float32) / np.float32(255.0)).reshape(-1, 3))
+    return bank
+
+
+def rsia_records(width, height, xs=None, ys=None):
+    """Execution inputs of `rsia file.rusteria` (Rusteria::shade, rusteria/src/lib.rs:161-206): uv = (x / w, 1 - y / h, 0),
+    everything else zero, for the pixels (xs, ys) or the whole image.  Returns [n, 18] float32 records."""
+    if xs is None:
+        ys, xs = np.mgrid[0:height, 0:width]
+    xs, ys = np.asarray(xs).ravel(), np.asarray(ys).ravel()
+    rec = np.zeros((xs.size, 18), np.float32)
+    rec[:, 0] = xs.astype(np.float32) / np.float32(width)
+    rec[:, 1] = np.float32(1.0) - ys.astype(np.float32) / np.float32(height)
+    return rec
+
+
+def rsia_pixels(colors):
+    """RenderBuffer::save (rusteria/src/renderbuffer.rs:166-182): `(c * 255.0) as u8`, a saturating truncation."""
+    c = np.nan_to_num(np.asarray(colors, np.float32) * np.float32(255.0), nan=0.0)
+    return np.clip(np.trunc(c), 0, 255).astype(np.uint8)
 
 
 def shader_holes():
