@@ -71,3 +71,23 @@ def test_product_package_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle_ffi" not in text and "librxoracle" not in text and "rx_oracle" not in text, f
+
+
+def test_rust_sys_crate_is_generated_from_the_checked_mirror():
+    """rust/rusterix-cuda-sys/src/lib.rs is what tools/gen_rust_sys.py prints from _abi.py (which the test above checks
+    against the header), names every entry point of the header, and mirrors every struct field in order."""
+    import re
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    want = subprocess.run([sys.executable, os.path.join(root, "tools", "gen_rust_sys.py")], capture_output=True, text=True, check=True).stdout
+    have = open(os.path.join(root, "rust", "rusterix-cuda-sys", "src", "lib.rs")).read()
+    assert have == want, "stale: run `python tools/gen_rust_sys.py --write`"
+    header = open(os.path.join(root, "include", "rxcuda.h")).read()
+    declared = set(re.findall(r"^\w[\w\s\*]*?\b(rxc_\w+)\s*\(", header, flags=re.M))
+    bound = set(re.findall(r"pub fn (rxc_\w+)\(", have))
+    assert declared and declared == bound, declared ^ bound
+    for s in (_abi.rxc_frame, _abi.rxc_scene, _abi.rxc_batch3d, _abi.rxc_light, _abi.rxc_stats):
+        body = re.search(r"pub struct %s \{(.*?)\n\}" % s.__name__, have, flags=re.S).group(1)
+        fields = re.findall(r"pub (\w+):", body)
+        assert fields == [("pass" if f == "pass_" else f) for f, _ in s._fields_]
