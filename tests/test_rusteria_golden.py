@@ -91,3 +91,79 @@ def test_device_vm_reproduces_the_reference_render(name):
     got = scenes.rsia_pixels(out[:, 3:6]).reshape(200, 200, 3)
     d = np.abs(got.astype(int) - _golden(name).astype(int)).max(axis=-1)
     assert (d == 0).mean() >= 0.995 and (d <= 1).mean() >= 0.999, ((d == 0).mean(), (d <= 1).mean(), d.max())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The pattern textures embedded in the rusteria crate are OUTPUTS of the reference VM: make_textures.rusteria (root of
+# the reference) generated them with iterate() / save().  tests/rusteria_programs.py holds its generator functions
+# lowered by hand; the goldens are the reference's PNGs (whole, or every 2nd pixel for fbm_value / perlin).
+# ---------------------------------------------------------------------------------------------------------------
+import rusteria_programs as rp  # noqa: E402
+
+GENERATORS = {"value": rp.make_value_noise, "fbm_value": rp.make_fbm_value_noise, "perlin": rp.make_perlin_noise,
+              "fbm_perlin": rp.make_perlin_fbm, "bricks": rp.make_bricks, "tiles": rp.make_tiles, "blocks": rp.make_blocks}
+SUBSAMPLED = {"fbm_value": 2, "perlin": 2}
+
+
+def _gen_golden(name):
+    step = SUBSAMPLED.get(name, 1)
+    path = os.path.join(GOLD, name + ("_every2nd.png" if step == 2 else ".png"))
+    im = np.asarray(Image.open(path).convert("RGB"))
+    ys, xs = np.mgrid[0:512:step, 0:512:step]
+    return im, rp.iterate_records(512, 512, xs, ys), xs, ys
+
+
+def _gen_scene():
+    s = types.Scene()
+    for make in GENERATORS.values():
+        s.add_shader(make())
+    return s
+
+
+def _gen_mask(name, xs, ys):
+    """Pixels a golden comparison may use.  perlin: grad2() hashes a lattice point with fract(sin(d) * 43758.5453) * 8;
+    at lattice point (6, 8) (d = 3256.2002) that is 1.969, one ulp of sin below the next bin, and the libm the
+    reference's author rendered with fell on the other side: the four cells around that point (5 % of the texture) show
+    another gradient.  Everything else is bit-exact."""
+    if name != "perlin":
+        return np.ones(xs.shape, bool)
+    cx, cy = np.floor(xs * (10.0 / 512.0)).astype(int), np.floor(ys * (10.0 / 512.0)).astype(int)
+    return ~(((cx == 5) | (cx == 6)) & ((cy == 7) | (cy == 8)))
+
+
+@pytest.mark.parametrize("name", list(GENERATORS))
+def test_oracle_vm_regenerates_the_embedded_pattern_textures(name):
+    oracle_ffi.set_programs(_gen_scene(), types.Assets())
+    gold, rec, xs, ys = _gen_golden(name)
+    out, faults = oracle_ffi.vm_execute(list(GENERATORS).index(name), rec)
+    assert faults == 0
+    got = rp.save_pixels(out[:, 3:6]).reshape(gold.shape)
+    same = (got == gold).all(axis=-1)
+    if name == "fbm_perlin":   # five octaves of the libm-sensitive lattice hash (see _gen_mask): most cells, not all
+        assert same.mean() > 0.85
+    else:
+        assert same[_gen_mask(name, xs, ys)].all(), (name, 1.0 - same.mean())
+        assert same.mean() > 0.94
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(GENERATORS))
+def test_device_vm_regenerates_the_embedded_pattern_textures(name):
+    """The flat code on the device: For / If / Return / nested calls / swizzled assignment.  sin, cos and pow come from
+    CUDA's libm: a lattice hash or a cell index can flip where the oracle's did not, so the bar is per pixel."""
+    from rusterix_b200 import Assets, DeviceContext
+
+    ctx = DeviceContext.get(0)
+    ctx.upload(_gen_scene(), Assets.default().textures([]))
+    gold, rec, xs, ys = _gen_golden(name)
+    out, faults = ctx.vm_execute(list(GENERATORS).index(name), rec)
+    assert faults == 0
+    got = rp.save_pixels(out[:, 3:6]).reshape(gold.shape)
+    oracle_ffi.set_programs(_gen_scene(), types.Assets())
+    want, _ = oracle_ffi.vm_execute(list(GENERATORS).index(name), rec)
+    same_gold = (got == gold).all(axis=-1)
+    same_oracle = (got == rp.save_pixels(want[:, 3:6]).reshape(gold.shape)).all(axis=-1)
+    if name in ("perlin", "fbm_perlin"):
+        assert same_oracle.mean() > 0.80 and same_gold.mean() > 0.80, (same_oracle.mean(), same_gold.mean())
+    else:
+        assert same_gold.mean() >= 0.995 and same_oracle.mean() >= 0.995, (same_gold.mean(), same_oracle.mean())
