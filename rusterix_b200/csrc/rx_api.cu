@@ -692,20 +692,27 @@ int32_t rasterize_impl(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames,
         for (uint32_t i = 0; i < n_frames; ++i)
             if ((st = fill_frame(ctx, frames[i], &ctx->h_frames[i])) != RXC_OK) return st;
         for (int attempt = 0; attempt < 4; ++attempt) {
-            if ((st = ensure_workspace(ctx, sub, tiles_per_frame)) != RXC_OK) return st;
-            if ((st = reserve(ctx, ctx->d_out_px, (size_t)2 * sub * frame_bytes)) != RXC_OK) return st;
+            // the first piece is small (its render is exposed), the later ones grow to four times its size (about 32 MB):
+            // they render while their predecessor drains, and every D2H copy carries a few microseconds of fixed cost
+            const uint32_t sub_big = (uint32_t)std::max<uint64_t>(sub, std::min<uint64_t>(group, (4 * piece) / std::max<uint64_t>(1, frame_bytes)));
+            if ((st = ensure_workspace(ctx, sub_big, tiles_per_frame)) != RXC_OK) return st;
+            if ((st = reserve(ctx, ctx->d_out_px, (size_t)2 * sub_big * frame_bytes)) != RXC_OK) return st;
             uint32_t k = 0;
-            for (uint32_t first = 0; first < n_frames; first += sub, ++k) {
-                const uint32_t n = std::min(sub, n_frames - first);
+            for (uint32_t first = 0, n = 0; first < n_frames; first += n, ++k) {
+                // doubling: a piece renders faster than it drains, so the next one may be twice as large without a bubble
+                n = std::min(std::min<uint32_t>(sub_big, k < 16 ? sub << k : sub_big), n_frames - first);
                 const int half = (int)(k & 1u);
-                uint8_t* d_px = ctx->d_out_px.as<uint8_t>() + (size_t)half * sub * frame_bytes;
+                uint8_t* d_px = ctx->d_out_px.as<uint8_t>() + (size_t)half * sub_big * frame_bytes;
                 if (k >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[half], 0));  // the half has been drained
+                // only the first frame of a call is sliced: it is the one whose render is exposed; the later ones render
+                // while their predecessor drains and leave as one copy (each D2H copy carries ~6 us of fixed cost)
+                const uint32_t slices_now = k == 0 ? slices : 1u;
                 uint32_t slice_no = 0;
                 auto drain = [&](uint32_t row0, uint32_t row1) -> int32_t {
-                    cudaEvent_t ev = slices > 1 ? ctx->ev_slice[slice_no++ & 15u] : ctx->ev_render[half];
+                    cudaEvent_t ev = slices_now > 1 ? ctx->ev_slice[slice_no++ & 15u] : ctx->ev_render[half];
                     CK(cudaEventRecord(ev, ctx->stream));
                     CK(cudaStreamWaitEvent(ctx->copy_stream, ev, 0));
-                    if (slices > 1) {   // n == 1: rows [row0, row1) of the frame
+                    if (slices_now > 1) {   // n == 1: rows [row0, row1) of the frame
                         CK(cudaMemcpyAsync(pixels + (uint64_t)first * stride + row0 * row_bytes, d_px + row0 * row_bytes, (size_t)(row1 - row0) * row_bytes,
                                            cudaMemcpyDeviceToHost, ctx->copy_stream));
                     } else if (stride == frame_bytes) {
@@ -718,7 +725,7 @@ int32_t rasterize_impl(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames,
                 // the counter block alternates with the staging half, and is read back behind the pixels on the copy stream
                 // (a small D2H on the render stream would queue behind the pixel copies on the same DMA engine and stall it)
                 ctx->W.counters = ctx->w_counters.as<DCounters>() + (size_t)half * ctx->ws_frames;
-                st = launch_group(ctx, ctx->h_frames + first, nullptr, n, d_px, frame_bytes, nullptr, nullptr, slices, drain);
+                st = launch_group(ctx, ctx->h_frames + first, nullptr, n, d_px, frame_bytes, nullptr, nullptr, slices_now, drain);
                 DCounters* d_counters = ctx->W.counters;
                 ctx->W.counters = ctx->w_counters.as<DCounters>();
                 if (st != RXC_OK) return st;
