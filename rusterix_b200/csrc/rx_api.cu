@@ -4,6 +4,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <exception>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -785,6 +787,24 @@ int32_t rasterize_impl(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames,
     return RXC_OK;
 }
 
+// C++ exceptions (std::bad_alloc from the host-side staging vectors, std::length_error ...) must not cross the C ABI:
+// a Rust or C host cannot catch them.  Every entry point runs inside this barrier and reports them as a status.
+template <class F>
+int32_t guarded(rxc_ctx* ctx, F&& f) noexcept {
+    try {
+        return f();
+    } catch (const std::bad_alloc&) {
+        if (ctx) { try { ctx->err = "out of host memory"; } catch (...) {} }
+        return RXC_ERR_OOM;
+    } catch (const std::exception& e) {
+        if (ctx) { try { ctx->err = std::string("internal error: ") + e.what(); } catch (...) {} }
+        return RXC_ERR_INVALID;
+    } catch (...) {
+        if (ctx) { try { ctx->err = "internal error"; } catch (...) {} }
+        return RXC_ERR_INVALID;
+    }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -797,6 +817,7 @@ uint32_t rxc_abi_version(void) { return RXC_ABI_VERSION; }
 const char* rxc_kernel_name(uint32_t k) { return k < RXC_N_KERNELS ? kKernelNames[k] : ""; }
 
 int32_t rxc_create(int32_t device, rxc_ctx** out) {
+    return guarded(nullptr, [&]() -> int32_t {
     if (!out) return RXC_ERR_INVALID;
     *out = nullptr;
     int n = 0;
@@ -816,6 +837,7 @@ int32_t rxc_create(int32_t device, rxc_ctx** out) {
     if (const char* e = getenv("RXC_FRONT_CLUSTER_MAX")) ctx->front_cluster_max = atoi(e);  // tuning knob for experiments
     *out = ctx;
     return RXC_OK;
+    });
 }
 
 void rxc_destroy(rxc_ctx* ctx) {
@@ -847,23 +869,28 @@ void rxc_destroy(rxc_ctx* ctx) {
 const char* rxc_last_error(const rxc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 int32_t rxc_set_stream(rxc_ctx* ctx, void* cuda_stream) {
+    return guarded(ctx, [&]() -> int32_t {
     if (!ctx) return RXC_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
     return RXC_OK;
+    });
 }
 
 int32_t rxc_set_assets(rxc_ctx* ctx, const rxc_tile* tiles, uint32_t n_tiles) {
+    return guarded(ctx, [&]() -> int32_t {
     if (!ctx || (n_tiles && !tiles)) return RXC_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     int32_t st = build_tiles(ctx, tiles, n_tiles, ctx->h_static_arena, ctx->h_static_tex, ctx->h_static_tiles);
     if (st != RXC_OK) return st;
     ctx->textures_dirty = true;
     return upload_textures(ctx);
+    });
 }
 
 int32_t rxc_set_lights(rxc_ctx* ctx, const rxc_light* lights, uint32_t n_lights) {
+    return guarded(ctx, [&]() -> int32_t {
     if (!ctx || (n_lights && !lights)) return RXC_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     const uint32_t before = ctx->S.n_lights;
@@ -871,9 +898,11 @@ int32_t rxc_set_lights(rxc_ctx* ctx, const rxc_light* lights, uint32_t n_lights)
     if (st != RXC_OK) return st;
     if (n_lights > before) ctx->ws_frames = 0;  // per-frame light slices must grow
     return RXC_OK;
+    });
 }
 
 int32_t rxc_set_mapmini(rxc_ctx* ctx, const rxc_mapmini* mm) {
+    return guarded(ctx, [&]() -> int32_t {
     if (!ctx) return RXC_ERR_INVALID;
     if (mm && ((mm->n_linedefs && !mm->linedefs) || (mm->n_occluded_sectors && !mm->occluded_sectors)))
         return fail(ctx, RXC_ERR_INVALID, "null array with non-zero count in rxc_mapmini");
@@ -890,9 +919,11 @@ int32_t rxc_set_mapmini(rxc_ctx* ctx, const rxc_mapmini* mm) {
         }
     }
     return upload_chunks(ctx, (uint32_t)ctx->h_static_tex.size());
+    });
 }
 
 int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
+    return guarded(ctx, [&]() -> int32_t {
     if (!ctx || !sc) return RXC_ERR_INVALID;
     if ((sc->n_batches3d && !sc->batches3d) || (sc->n_batches2d && !sc->batches2d) || (sc->n_lights && !sc->lights) ||
         (sc->n_dynamic_textures && !sc->dynamic_textures) || (sc->n_chunks && !sc->chunks) || (sc->n_actor_tiles && !sc->actor_tiles) ||
@@ -1097,22 +1128,32 @@ int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
     ctx->lists_sized = false;
     ctx->have_scene = true;
     return RXC_OK;
+    });
 }
 
 int32_t rxc_rasterize(rxc_ctx* ctx, const rxc_frame* frame, uint8_t* pixels, uint32_t* owner, float* depth) {
+    return guarded(ctx, [&]() -> int32_t {
     return rasterize_impl(ctx, frame, 1, pixels, 0, owner, depth, true);
+    });
 }
 int32_t rxc_rasterize_async(rxc_ctx* ctx, const rxc_frame* frame, uint8_t* pixels, uint32_t* owner, float* depth) {
+    return guarded(ctx, [&]() -> int32_t {
     return rasterize_impl(ctx, frame, 1, pixels, 0, owner, depth, false);
+    });
 }
 int32_t rxc_rasterize_batch(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames, uint8_t* pixels, uint64_t frame_stride_bytes) {
+    return guarded(ctx, [&]() -> int32_t {
     return rasterize_impl(ctx, frames, n_frames, pixels, frame_stride_bytes, nullptr, nullptr, true);
+    });
 }
 int32_t rxc_rasterize_batch_async(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames, uint8_t* pixels, uint64_t frame_stride_bytes) {
+    return guarded(ctx, [&]() -> int32_t {
     return rasterize_impl(ctx, frames, n_frames, pixels, frame_stride_bytes, nullptr, nullptr, false);
+    });
 }
 
 int32_t rxc_synchronize(rxc_ctx* ctx) {
+    return guarded(ctx, [&]() -> int32_t {
     if (!ctx) return RXC_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1124,15 +1165,19 @@ int32_t rxc_synchronize(rxc_ctx* ctx) {
         if (retry) return fail(ctx, RXC_ERR_OOM, "tile-list arena overflowed during an asynchronous frame; it has been grown, render the frame again");
     }
     return RXC_OK;
+    });
 }
 
 int32_t rxc_owner_base(const rxc_ctx* ctx, uint32_t batch, uint32_t* base) {
+    return guarded(nullptr, [&]() -> int32_t {
     if (!ctx || !base || batch >= ctx->owner_base.size()) return RXC_ERR_INVALID;
     *base = ctx->owner_base[batch];
     return RXC_OK;
+    });
 }
 
 int32_t rxc_selftest_div(rxc_ctx* ctx, uint64_t seed, uint64_t n_pairs, uint64_t* mismatches, uint32_t* bad_pair) {
+    return guarded(ctx, [&]() -> int32_t {
     if (!ctx || !mismatches) return RXC_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     unsigned long long* d = nullptr;
@@ -1149,9 +1194,11 @@ int32_t rxc_selftest_div(rxc_ctx* ctx, uint64_t seed, uint64_t n_pairs, uint64_t
     *mismatches = h[0];
     if (bad_pair) { bad_pair[0] = (uint32_t)(h[1] >> 32); bad_pair[1] = (uint32_t)h[1]; }
     return RXC_OK;
+    });
 }
 
 int32_t rxc_vm_execute(rxc_ctx* ctx, uint32_t program, uint32_t n, const float* in, float* out, uint32_t* faults) {
+    return guarded(ctx, [&]() -> int32_t {
     if (!ctx || !in || !out) return RXC_ERR_INVALID;
     if (!ctx->have_scene || program >= ctx->S.vm.n_programs) return fail(ctx, RXC_ERR_INDEX, "rxc_vm_execute: no such program in the current scene");
     if (n == 0) return RXC_OK;
@@ -1172,32 +1219,39 @@ int32_t rxc_vm_execute(rxc_ctx* ctx, uint32_t program, uint32_t n, const float* 
     if (e != cudaSuccess) { ctx->err = std::string("rxc_vm_execute: ") + cudaGetErrorString(e); return RXC_ERR_CUDA; }
     if (faults) *faults = h_f;
     return RXC_OK;
+    });
 }
 
 int32_t rxc_set_profiling(rxc_ctx* ctx, int32_t enabled) {
+    return guarded(ctx, [&]() -> int32_t {
     if (!ctx) return RXC_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     drain_events(ctx);
     ctx->profiling = enabled != 0;
     return RXC_OK;
+    });
 }
 
 int32_t rxc_get_stats(rxc_ctx* ctx, rxc_stats* out) {
+    return guarded(ctx, [&]() -> int32_t {
     if (!ctx || !out) return RXC_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     if (ctx->profiling) { CK(cudaStreamSynchronize(ctx->stream)); drain_events(ctx); }
     *out = ctx->stats;
     return RXC_OK;
+    });
 }
 
 int32_t rxc_reset_stats(rxc_ctx* ctx) {
+    return guarded(ctx, [&]() -> int32_t {
     if (!ctx) return RXC_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     drain_events(ctx);
     ctx->stats = rxc_stats{};
     return RXC_OK;
+    });
 }
 
 }  // extern "C"
