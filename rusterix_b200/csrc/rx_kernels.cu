@@ -1709,11 +1709,13 @@ __device__ __forceinline__ void process_record(const SceneDev& S, const DFrame& 
     const float4* q = reinterpret_cast<const float4*>(Tp);
     const float4 q5 = q[5];
     const uint32_t bbx = __float_as_uint(q5.y), bby = __float_as_uint(q5.z), meta = __float_as_uint(q5.w);
-    const int x0 = (int)(bbx & 0xFFFFu), x1 = (int)(bbx >> 16), y0 = (int)(bby & 0xFFFFu), y1 = (int)(bby >> 16);
-    const bool cx0 = px0 >= x0 && px0 < x1, cx1 = px0 + 8 >= x0 && px0 + 8 < x1;
-    const bool cy0 = py0 >= y0 && py0 < y1, cy1 = py0 + 4 >= y0 && py0 + 4 < y1;
-    uint32_t m = ((cx0 && cy0) ? 1u : 0u) | ((cx1 && cy0) ? 2u : 0u) | ((cx0 && cy1) ? 4u : 0u) | ((cx1 && cy1) ? 8u : 0u);
-    m &= valid;
+    uint32_t m = valid;   // `full` (uniform over the warp): the bbox contains the warp's region and every edge passes everywhere
+    if (!full) {
+        const int x0 = (int)(bbx & 0xFFFFu), x1 = (int)(bbx >> 16), y0 = (int)(bby & 0xFFFFu), y1 = (int)(bby >> 16);
+        const bool cx0 = px0 >= x0 && px0 < x1, cx1 = px0 + 8 >= x0 && px0 + 8 < x1;
+        const bool cy0 = py0 >= y0 && py0 < y1, cy1 = py0 + 4 >= y0 && py0 + 4 < y1;
+        m &= ((cx0 && cy0) ? 1u : 0u) | ((cx1 && cy0) ? 2u : 0u) | ((cx0 && cy1) ? 4u : 0u) | ((cx1 && cy1) ? 8u : 0u);
+    }
     if (!m) return;
     const float fx1 = fx0 + 8.0f, fy1 = fy0 + 4.0f;
     if (!full) {   // Edges::evaluate, edge.rs:28-36: (a*px + b*py) + c < 0 -> outside (a NaN result passes)
