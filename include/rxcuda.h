@@ -373,6 +373,12 @@ int32_t rxc_rasterize_batch_async(rxc_ctx* ctx, const rxc_frame* frames, uint32_
                                   uint64_t frame_stride_bytes);
 int32_t rxc_synchronize(rxc_ctx* ctx);
 
+/* Page-locks (cudaHostRegister) / releases a host pixel buffer the caller owns -- a Rust `Vec<u8>` that is reused for
+ * every frame, say -- so that the frames drain over PCIe by DMA at the pinned rate (about 2.5x the pageable one) and
+ * overlap with rendering.  Optional: rxc_rasterize works with pageable memory too.  Unpin before freeing the buffer. */
+int32_t rxc_pin_host(rxc_ctx* ctx, void* ptr, uint64_t bytes);
+int32_t rxc_unpin_host(rxc_ctx* ctx, void* ptr);
+
 /* Global submission ordinal of triangle 0 of 3D batch `batch` (owner ids are
  * base + index into the batch's clipped_indices; capacity 3*n_triangles per batch). */
 int32_t rxc_owner_base(const rxc_ctx* ctx, uint32_t batch, uint32_t* base);

@@ -237,6 +237,8 @@ EXPORTS = [
     ("rxc_rasterize_batch", C.c_int32, [C.c_void_p, C.POINTER(rxc_frame), C.c_uint32, C.c_void_p, C.c_uint64]),
     ("rxc_rasterize_batch_async", C.c_int32, [C.c_void_p, C.POINTER(rxc_frame), C.c_uint32, C.c_void_p, C.c_uint64]),
     ("rxc_synchronize", C.c_int32, [C.c_void_p]),
+    ("rxc_pin_host", C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    ("rxc_unpin_host", C.c_int32, [C.c_void_p, C.c_void_p]),
     ("rxc_owner_base", C.c_int32, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]),
     ("rxc_selftest_div", C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     ("rxc_vm_execute", C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]),

@@ -1168,6 +1168,30 @@ int32_t rxc_synchronize(rxc_ctx* ctx) {
     });
 }
 
+int32_t rxc_pin_host(rxc_ctx* ctx, void* ptr, uint64_t bytes) {
+    return guarded(ctx, [&]() -> int32_t {
+    if (!ctx) return RXC_ERR_INVALID;
+    if (!ptr || bytes == 0) return fail(ctx, RXC_ERR_INVALID, "rxc_pin_host: null pointer or empty range");
+    CK(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return RXC_OK; }
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, RXC_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e)); }
+    return RXC_OK;
+    });
+}
+
+int32_t rxc_unpin_host(rxc_ctx* ctx, void* ptr) {
+    return guarded(ctx, [&]() -> int32_t {
+    if (!ctx || !ptr) return RXC_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));   // nothing may still be draining into it
+    if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, RXC_ERR_CUDA, std::string("cudaHostUnregister: ") + cudaGetErrorString(e)); }
+    return RXC_OK;
+    });
+}
+
 int32_t rxc_owner_base(const rxc_ctx* ctx, uint32_t batch, uint32_t* base) {
     return guarded(nullptr, [&]() -> int32_t {
     if (!ctx || !base || batch >= ctx->owner_base.size()) return RXC_ERR_INVALID;

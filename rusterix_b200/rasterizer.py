@@ -96,6 +96,17 @@ class DeviceContext:
         self.check(self.lib.rxc_vm_execute(self.handle, int(program), len(rec), rec.ctypes.data, out.ctypes.data, C.byref(faults)))
         return out, int(faults.value)
 
+    def pin_host(self, buf):
+        """rxc_pin_host on a writable buffer (numpy array, bytearray ...): frames written into it then drain by DMA."""
+        p, keep = _buffer_pointer(buf, 1)
+        nbytes = keep.nbytes if hasattr(keep, "nbytes") else keep.numel() * keep.element_size()
+        self.check(self.lib.rxc_pin_host(self.handle, C.c_void_p(p), nbytes))
+        return buf
+
+    def unpin_host(self, buf):
+        p, _keep = _buffer_pointer(buf, 1)
+        self.check(self.lib.rxc_unpin_host(self.handle, C.c_void_p(p)))
+
     def stats(self) -> _abi.rxc_stats:
         s = _abi.rxc_stats()
         self.check(self.lib.rxc_get_stats(self.handle, C.byref(s)))

@@ -570,3 +570,27 @@ def test_sliced_host_output_matches_device_output(size):
     Rasterizer.rasterize_batch([r, r, r], cfg.scene, out, w, h, cfg.tile_size, cfg.assets)
     for k in range(3):
         assert np.array_equal(out[k], ref)
+
+
+def test_pin_host_buffer_same_frame_and_reusable():
+    """rxc_pin_host / rxc_unpin_host: a caller-owned host buffer page-locked through the ABI receives the same bytes as a
+    pageable one; pinning twice is harmless, unpinning makes the buffer pageable again."""
+    from rusterix_b200 import DeviceContext
+
+    cfg = scenes.map_config(1280, 720, 40, logo_size=64)
+    r = cfg.rasterizer()
+    pageable = np.zeros((720, 1280, 4), dtype=np.uint8)
+    r.rasterize(cfg.scene, pageable, 1280, 720, cfg.tile_size, cfg.assets)
+    ctx = DeviceContext.get(0)
+    pinned = np.zeros((720, 1280, 4), dtype=np.uint8)
+    ctx.pin_host(pinned)
+    ctx.pin_host(pinned)
+    try:
+        for _ in range(2):
+            pinned[:] = 0
+            r.rasterize(cfg.scene, pinned, 1280, 720, cfg.tile_size, cfg.assets)
+            assert np.array_equal(pinned, pageable)
+    finally:
+        ctx.unpin_host(pinned)
+    r.rasterize(cfg.scene, pinned, 1280, 720, cfg.tile_size, cfg.assets)
+    assert np.array_equal(pinned, pageable)

@@ -34,4 +34,17 @@ for spec in specs:
         batch.run(dev, sync=True)
     ms_dev = (time.perf_counter() - t0) / n * 1e3
     mb = host.numel() / 1e6
-    print(f"{name:11s} x{frames}: e2e {ms:7.3f} ms ({mb / ms:6.1f} GB/s to host, {mb / 4 / ms * 1e-3 * 1e3:8.0f} Mpix/s)  device-resident {ms_dev:7.3f} ms  identical={same}")
+    # the same call with a pageable buffer, and with that buffer page-locked through the ABI (rxc_pin_host)
+    import numpy as np
+    page = np.zeros(host.shape, dtype=np.uint8)
+    def wall(buf, n=10):
+        batch.run(buf, sync=True)
+        t = time.perf_counter()
+        for _ in range(n):
+            batch.run(buf, sync=True)
+        return (time.perf_counter() - t) / n * 1e3
+    ms_page = wall(page)
+    ctx.pin_host(page)
+    ms_reg = wall(page)
+    ctx.unpin_host(page)
+    print(f"{name:11s} x{frames}: e2e {ms:7.3f} ms ({mb / ms:6.1f} GB/s to host, {mb / 4 / ms * 1e-3 * 1e3:8.0f} Mpix/s)  device-resident {ms_dev:7.3f} ms  identical={same}  pageable {ms_page:7.3f} ms  rxc_pin_host {ms_reg:7.3f} ms")
