@@ -1803,6 +1803,8 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
     __shared__ ShadeConst s_k;                       // frame constants of the deferred shade
     __shared__ __align__(16) DLight s_lights[RX_SMEM_LIGHTS];
     __shared__ float s_kd[256];                      // srgb_to_linear_fast(c / 255) * (1 - 0.04), rasterizer.rs:20-25
+    __shared__ int s_union[8];                       // pixel bbox of the frame's cached large triangles [0..3] and of its 2D records [4..7]
+    __shared__ int s_can_be_empty;                   // per frame: some tile may be untouched (see the empty-tile path below)
 
     uint32_t tid = threadIdx.x;
 #if RX_OPAQUE >= 3
@@ -1877,6 +1879,35 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
             }
             cached_frame = f;
             __syncthreads();
+            if (!GENERAL && warp < 2u) {
+                // what an empty tile must not touch: the union of the cached large triangles' pixel boxes (warp 0) and
+                // of the (at most 32, in this mode) 2D records' (warp 1)
+                int x0 = 0x7FFFFFFF, y0 = 0x7FFFFFFF, x1 = 0, y1 = 0;
+                const uint32_t n = warp == 0u ? n_cached : ((F.d2_active && S.n_rec2d) ? S.n_rec2d : 0u);
+                const Tri2D* recs2 = Wk.tri2d + (size_t)f * Wk.tri2d_stride;
+                for (uint32_t i = lane; i < n; i += 32) {
+                    const uint32_t bx = warp == 0u ? s_large[i].bbx : recs2[i].bbx, by = warp == 0u ? s_large[i].bby : recs2[i].bby;
+                    if ((bx & 0xFFFFu) < (bx >> 16) && (by & 0xFFFFu) < (by >> 16)) {
+                        x0 = min(x0, (int)(bx & 0xFFFFu)); x1 = max(x1, (int)(bx >> 16));
+                        y0 = min(y0, (int)(by & 0xFFFFu)); y1 = max(y1, (int)(by >> 16));
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    x0 = min(x0, __shfl_xor_sync(0xFFFFFFFFu, x0, o)); y0 = min(y0, __shfl_xor_sync(0xFFFFFFFFu, y0, o));
+                    x1 = max(x1, __shfl_xor_sync(0xFFFFFFFFu, x1, o)); y1 = max(y1, __shfl_xor_sync(0xFFFFFFFFu, y1, o));
+                }
+                if (lane == 0) { int* u = s_union + 4 * warp; u[0] = x0; u[1] = y0; u[2] = x1; u[3] = y1; }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                // no tile of this frame can be empty when the large triangles' boxes already cover the band (a sky box,
+                // the walls of a room): then the per-tile test is skipped altogether
+                bool can = F.d3_active && !(F.has_sky | F.has_brush);
+                if (!GENERAL) can = can && n_large == n_cached && !(s_union[0] <= 0 && s_union[1] <= F.band_y0 && s_union[2] >= F.width && s_union[3] >= F.band_y1);
+                s_can_be_empty = can ? 1 : 0;
+            }
+            __syncthreads();
         }
         const DLight* lights = S.n_lights <= (uint32_t)RX_SMEM_LIGHTS ? s_lights : lights_g;
 
@@ -1884,6 +1915,35 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
         const int fw = F.width, fy1 = F.band_y1;
         const int tx0 = s_work[1], ty0 = F.band_y0 + s_work[2];
         const int tx1 = min(tx0 + RX_TILE_W, fw), ty1 = min(ty0 + RX_TILE_H, fy1);
+        if (!PLANES && s_can_be_empty) {
+            // Empty tile: no binned triangle, no large triangle and no 2D record can touch it -> every pixel is the miss
+            // colour vec4_to_pixel((0,0,0,1)) (rasterizer.rs:409-417).  Sparse scenes (an object in front of nothing) are
+            // mostly such tiles, and the full tile prologue + resolve costs them ~600 warp-instructions per warp.
+            bool empty = Wk.tile_count[(size_t)f * Wk.tile_stride + tile] == 0u;
+            if (GENERAL) {
+                empty = empty && !(F.d2_active && S.n_rec2d != 0u && Wk.tile_count2[(size_t)f * Wk.tile_stride + tile] != 0u);
+            } else {
+                empty = empty &&
+                        !(s_union[0] < tx1 && s_union[2] > tx0 && s_union[1] < ty1 && s_union[3] > ty0) &&
+                        !(s_union[4] < tx1 && s_union[6] > tx0 && s_union[5] < ty1 && s_union[7] > ty0);
+            }
+            if (empty) {   // uniform over the CTA
+                uint8_t* frame_px = out.pixels + (size_t)f * out.frame_stride;
+                if (out.vec_store && tx0 + RX_TILE_W <= fw && ty0 + RX_TILE_H <= fy1) {
+                    const int r = (int)tid >> 3, c4 = (int)tid & 7;
+                    reinterpret_cast<uint4*>(frame_px + ((size_t)(ty0 - F.band_y0 + r) * (size_t)fw + (size_t)tx0) * 4)[c4] =
+                        make_uint4(0xFF000000u, 0xFF000000u, 0xFF000000u, 0xFF000000u);
+                } else {
+                    for (int i = (int)tid; i < RX_TILE_W * RX_TILE_H; i += RX_TILE_THREADS) {
+                        const int r = i >> 5, c = i & 31;
+                        if (tx0 + c < fw && ty0 + r < fy1)
+                            reinterpret_cast<uint32_t*>(frame_px)[(size_t)(ty0 - F.band_y0 + r) * (size_t)fw + (size_t)(tx0 + c)] = 0xFF000000u;
+                    }
+                }
+                __syncthreads();  // s_work is rewritten by the next tile
+                continue;
+            }
+        }
         const int rx0 = tx0 + rbx, ry0 = ty0 + rby, rx1 = min(rx0 + RX_REGION_W, fw), ry1 = min(ry0 + RX_REGION_H, fy1);
         const bool region_ok = rx0 < rx1 && ry0 < ry1;
         int px0 = tx0 + lx, py0 = ty0 + ly;

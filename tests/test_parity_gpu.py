@@ -594,3 +594,25 @@ def test_pin_host_buffer_same_frame_and_reusable():
         ctx.unpin_host(pinned)
     r.rasterize(cfg.scene, pinned, 1280, 720, cfg.tile_size, cfg.assets)
     assert np.array_equal(pinned, pageable)
+
+
+@pytest.mark.parametrize("make", [
+    lambda: scenes.cube(800, 600, 200, logo_size=64), lambda: scenes.cube(333, 217, 40, logo_size=32),
+    lambda: scenes.teapot(960, 540, 60, logo_size=64), lambda: scenes.dense(1280, 720, 40, patches=8),
+    lambda: scenes.chunked_config(640, 360, 40), lambda: scenes.game2d_config(480, 320),
+    lambda: scenes.shaded_config(320, 240, 40), lambda: scenes.sky_config(320, 180, 40), lambda: scenes.map_config(640, 360, 40, logo_size=64),
+], ids=["cube", "cube_odd", "teapot", "dense", "chunked", "game2d", "shaded", "sky", "map"])
+def test_empty_tile_fast_path_matches_the_full_path(make):
+    """Tiles nothing can touch are filled with the miss colour without running the tile (k_raster, empty-tile path).  The
+    kernel variant that also writes the owner / depth planes never takes that path: both must give the same pixels, for
+    the whole frame, for a row band and for odd sizes with partial tiles."""
+    def render(frame, **kw):
+        cfg = make()   # a fresh scene per call: rasterize() appends the chunk lights to scene.dynamic_lights every time
+        return render_gpu(cfg.rasterizer(frame), cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size, **kw)[0]
+
+    height = make().height
+    for frame in (0, 3):
+        full = render(frame, planes=True)
+        assert np.array_equal(render(frame, planes=False), full)
+        y0, y1 = 32, height - 45
+        assert np.array_equal(render(frame, planes=False, band=(y0, y1)), full[y0:y1])
