@@ -410,7 +410,7 @@ def main():
         mpix, cores, sample, spf = cpu_port_time(cfg, frame_ids)
         line["cpu_baseline"] = {"value": mpix, "unit": "Mpixel/s", "cores": cores, "kind": "port", "sample": sample, "s_per_frame": spf}
         also = {}
-        for wname in ("teapot1080", "dense8k", "sweep1080", "chunked1080", "game2d1080", "shaded1080"):
+        for wname in ("cube800", "teapot1080", "dense8k", "sweep1080", "chunked1080", "game2d1080", "shaded1080"):
             if wname == args.workload:
                 continue
             try:
