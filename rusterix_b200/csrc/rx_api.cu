@@ -80,6 +80,7 @@ struct rxc_ctx {
     int raster_blocks_per_sm = 1;
     int piece_mb = 8;             // host output: small frames are rendered and drained in groups of about this size
     int slice_mb = 4;             // host output: large frames are rendered and drained in slices of about this size (0 = whole frames)
+    int front_stop = 0;           // profiling aid: k_front_cluster leaves after this many phases (RXC_FRONT_STOP)
     int front_cluster_max = 64;   // setup chunks up to which the front end runs as one cluster per frame (0 = never)
     // host-output pipelining: a copy stream and two staging halves so the D2H of one sub-group of
     // frames overlaps the kernels of the next
@@ -550,7 +551,7 @@ int32_t launch_group(rxc_ctx* ctx, const DFrame* h_frames, DCounters* h_counters
     const bool cluster_front = !small_front && ctx->front_cluster_max != 0 && S.n_chunks <= (uint32_t)ctx->front_cluster_max &&
                                S.n_b2 <= 64 && tiles_per_frame <= 65536 && (!S.general || S.n_rec2d <= 512);   // long sorted 2D lists want k_list_sort's CTA per tile (834 records: no gain)
     if (small_front) { LaunchScope l(ctx, RXK_FRONT_SMALL); CK(rxk_front_small(S, ctx->W, n, tiles_per_frame, ctx->stream)); }
-    else if (cluster_front) { LaunchScope l(ctx, RXK_FRONT_SMALL); CK(rxk_front_cluster(S, ctx->W, n, tiles_per_frame, ctx->stream)); }
+    else if (cluster_front) { LaunchScope l(ctx, RXK_FRONT_SMALL); CK(rxk_front_cluster(S, ctx->W, n, tiles_per_frame, (uint32_t)ctx->front_stop, ctx->stream)); }
     else { LaunchScope l(ctx, RXK_FRAME_SETUP); CK(rxk_frame_setup(S, ctx->W, n, tiles_per_frame, ctx->stream)); }
     if (S.n_tris && !small_front && !cluster_front) {
         { LaunchScope l(ctx, RXK_TRI_SETUP); CK(rxk_tri_setup(S, ctx->W, n, ctx->stream)); }
@@ -834,6 +835,7 @@ int32_t rxc_create(int32_t device, rxc_ctx** out) {
     ctx->raster_blocks_per_sm = rxk_raster_blocks_per_sm();
     if (const char* e = getenv("RXC_PIECE_MB")) ctx->piece_mb = std::max(1, atoi(e));
     if (const char* e = getenv("RXC_SLICE_MB")) ctx->slice_mb = std::max(0, atoi(e));
+    if (const char* e = getenv("RXC_FRONT_STOP")) ctx->front_stop = std::max(0, atoi(e));
     if (const char* e = getenv("RXC_FRONT_CLUSTER_MAX")) ctx->front_cluster_max = atoi(e);  // tuning knob for experiments
     *out = ctx;
     return RXC_OK;

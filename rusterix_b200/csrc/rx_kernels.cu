@@ -900,7 +900,7 @@ __global__ void __launch_bounds__(256) k_front_small(SceneDev S, Workspace Wk, u
 // virtual blocks of every phase and meet at the hardware cluster barrier (barrier.cluster arrive.release /
 // wait.acquire, which also orders the global-memory hand-over between phases) instead of at a kernel boundary:
 // seven dependent launches (~10 us each of drain + launch + ramp) become six barriers of well under a microsecond.
-__global__ void __launch_bounds__(256) k_front_cluster(SceneDev S, Workspace Wk, uint32_t tiles_per_frame, uint32_t n_frame_blocks) {
+__global__ void __launch_bounds__(256) k_front_cluster(SceneDev S, Workspace Wk, uint32_t tiles_per_frame, uint32_t n_frame_blocks, uint32_t stop_phase) {
     cg::cluster_group cl = cg::this_cluster();
     const uint32_t r = cl.block_rank(), R = cl.num_blocks();   // the cluster spans grid.x; grid.y = frames
     const uint32_t f = blockIdx.y;
@@ -909,23 +909,29 @@ __global__ void __launch_bounds__(256) k_front_cluster(SceneDev S, Workspace Wk,
     for (uint32_t v = r; v < n_frame_blocks; v += R) { d_frame_setup(S, Wk, tiles_per_frame, Blk{v, f, n_frame_blocks}); __syncthreads(); }
     if (!d3 && !d2) return;
     cl.sync();
+    if (stop_phase == 1u) return;   // profiling aid (RXC_FRONT_STOP): leave after this many phases
     // the 2D chain of general mode (count, allocate, fill, sort) rides along with the first 3D phases
     if (d3) for (uint32_t v = r; v < S.n_chunks; v += R) { d_tri_setup(S, Wk, Blk{v, f, S.n_chunks}); __syncthreads(); }
     if (d2) d_bin2d(S, Wk, 0, Blk{r, f, R});
     cl.sync();
+    if (stop_phase == 2u) return;   // profiling aid (RXC_FRONT_STOP): leave after this many phases
     if (d3) { const uint32_t nfb = (S.n_b3 + 7u) / 8u; for (uint32_t v = r; v < nfb; v += R) d_batch_finalize(S, Wk, Blk{v, f, nfb}); }
     if (d2) for (uint32_t v = r; v < ntb; v += R) d_tile_alloc(Wk, tiles_per_frame, 1, 1, Blk{v, f, ntb});
     cl.sync();
+    if (stop_phase == 3u) return;   // profiling aid (RXC_FRONT_STOP): leave after this many phases
     if (d3) d_clip_emit(S, Wk, Blk{r, f, R});
     if (d2) d_bin2d(S, Wk, 1, Blk{r, f, R});
     cl.sync();
+    if (stop_phase == 4u) return;   // profiling aid (RXC_FRONT_STOP): leave after this many phases
     if (d3) d_bin_count(S, Wk, Blk{r, f, R});
     if (d2) d_list_sort_warp(Wk, 1, tiles_per_frame, Blk{r, f, R});
     if (!d3) return;
     cl.sync();
+    if (stop_phase == 5u) return;   // profiling aid (RXC_FRONT_STOP): leave after this many phases
     if (general) {   // the ordered lists hold every triangle: the large ones are binned too
         d_bin_large(S, Wk, 0, Blk{r, f, R});
         cl.sync();
+    if (stop_phase == 6u) return;   // profiling aid (RXC_FRONT_STOP): leave after this many phases
     } else if (Wk.counters[f].n_visible == Wk.counters[f].n_large) {
         // nothing binned (every visible triangle went to the large list): all tile lists stay empty
         for (uint32_t i = r * blockDim.x + threadIdx.x; i < tiles_per_frame; i += R * blockDim.x) Wk.tile_base[(size_t)f * Wk.tile_stride + i] = 0u;
@@ -933,10 +939,12 @@ __global__ void __launch_bounds__(256) k_front_cluster(SceneDev S, Workspace Wk,
     }
     for (uint32_t v = r; v < ntb; v += R) d_tile_alloc(Wk, tiles_per_frame, 0, general ? 1 : 0, Blk{v, f, ntb});
     cl.sync();
+    if (stop_phase == 7u) return;   // profiling aid (RXC_FRONT_STOP): leave after this many phases
     d_bin_fill(S, Wk, Blk{r, f, R});
     if (general) {
         d_bin_large(S, Wk, 1, Blk{r, f, R});
         cl.sync();
+    if (stop_phase == 8u) return;   // profiling aid (RXC_FRONT_STOP): leave after this many phases
         d_list_sort_warp(Wk, 0, tiles_per_frame, Blk{r, f, R});
     }
 }
@@ -2244,7 +2252,7 @@ cudaError_t rxk_front_small(const SceneDev& S, const Workspace& W, uint32_t n_fr
     k_front_small<<<n_frames, 256, 0, st>>>(S, W, tiles_per_frame, 2u + S.n_b2);   // block 0, the 2D batches, one state/zeroing block
     return cudaGetLastError();
 }
-cudaError_t rxk_front_cluster(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, cudaStream_t st) {
+cudaError_t rxk_front_cluster(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, uint32_t stop_phase, cudaStream_t st) {
     const uint32_t zero_blocks = max(1u, min(64u, (tiles_per_frame + 255u) / 256u));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(RX_FRONT_CLUSTER, n_frames);
@@ -2254,7 +2262,7 @@ cudaError_t rxk_front_cluster(const SceneDev& S, const Workspace& W, uint32_t n_
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = RX_FRONT_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, k_front_cluster, S, W, tiles_per_frame, 1u + S.n_b2 + zero_blocks);
+    return cudaLaunchKernelEx(&cfg, k_front_cluster, S, W, tiles_per_frame, 1u + S.n_b2 + zero_blocks, stop_phase);
 }
 cudaError_t rxk_tri_setup(const SceneDev& S, const Workspace& W, uint32_t n_frames, cudaStream_t st) {
     if (S.n_chunks == 0) return cudaSuccess;

@@ -92,7 +92,8 @@ cudaError_t rxk_frame_setup(const SceneDev& S, const Workspace& W, uint32_t n_fr
 cudaError_t rxk_front_small(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, cudaStream_t st);
 // the same for mid-sized scenes: a cluster of RX_FRONT_CLUSTER CTAs per frame shares every phase, cluster barriers between them
 #define RX_FRONT_CLUSTER 8
-cudaError_t rxk_front_cluster(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, cudaStream_t st);
+// stop_phase: 0 = all phases; n = return after the n-th cluster barrier (profiling aid only, the frame is then incomplete)
+cudaError_t rxk_front_cluster(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, uint32_t stop_phase, cudaStream_t st);
 cudaError_t rxk_tri_setup(const SceneDev& S, const Workspace& W, uint32_t n_frames, cudaStream_t st);
 cudaError_t rxk_batch_finalize(const SceneDev& S, const Workspace& W, uint32_t n_frames, cudaStream_t st);
 cudaError_t rxk_clip_emit(const SceneDev& S, const Workspace& W, uint32_t n_frames, int grid, cudaStream_t st);
