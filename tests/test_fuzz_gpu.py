@@ -132,3 +132,7 @@ def test_random_scenes(block):
         o = render_oracle(r, scene, assets, w, h, ts)
         # tiny frames of random soups hold few pixels: a single texel flip of the +-1 LSB shading path is 0.1 %
         compare(g, o, f"fuzz seed {seed}", pixel_frac=0.99)
+        # the pixels-only kernel variant (empty-tile path, sliced host output for large frames) writes the same bytes
+        scene2, assets2, r2, _, _, _ = _scene(seed)   # a fresh scene: rasterize() appends the chunk lights on every call
+        fast = render_gpu(r2, scene2, assets2, w, h, ts, planes=False)[0]
+        assert np.array_equal(fast, g[0]), f"fuzz seed {seed}: pixels-only variant differs"
