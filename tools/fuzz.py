@@ -16,6 +16,9 @@ for seed in range(first, first + count):
     o = render_oracle(r, scene, assets, w, h, ts)
     if (g[1] != o[1]).any() or (g[2].view(np.uint32) != o[2].view(np.uint32)).any():
         bad.append(seed)
+    scene2, assets2, r2, _, _, _ = fz._scene(seed)   # pixels-only kernel variant (empty-tile path): same bytes
+    if not np.array_equal(render_gpu(r2, scene2, assets2, w, h, ts, planes=False)[0], g[0]):
+        bad.append(-seed)
     d = np.abs(g[0].astype(np.int16) - o[0].astype(np.int16)).max(axis=-1)
     npx += d.size; nexact += int((d == 0).sum()); n1 += int((d <= 1).sum()); worst = max(worst, int(d.max()))
 print(f"seeds {first}..{first + count - 1}: owner/depth mismatching seeds {bad}; pixels {npx}, exact {nexact / npx:.6f}, within 1 LSB {n1 / npx:.6f}, max diff {worst}")
