@@ -11,11 +11,16 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
 // this library.  The product (rusterix_b200/, include/rxcuda.h) never links or calls it.
 //
-// PARITY UNPINNED: the reference is pure Rust and cannot be built in this image (no cargo/rustc),
-// it ships no tests, golden images or fixtures for this path, and the
-// rounding of vek 0.17.2's Mat*Vec / Mat*Mat (Cargo.lock:3826) cannot be verified offline.  The
-// oracle is therefore pinned only by hand-derived known-answer tests (tests/test_oracle_kat.py)
-// and by the source text it restates; the Mat*Vec convention is selectable (frame.matvec_mode).
+// PARITY STATUS.  Rasterizer proper: UNPINNED.  The reference is pure Rust and cannot be built in this image (no
+// cargo/rustc), it ships no tests, golden images or fixtures for the rasterize path, and the
+// rounding of vek 0.17.2's Mat*Vec / Mat*Mat (Cargo.lock:3826) cannot be verified offline.  That part is pinned only
+// by hand-derived known-answer tests (tests/test_oracle_kat.py) and by the source text it restates; the Mat*Vec
+// convention is selectable (frame.matvec_mode).
+// Rusteria VM (the Execution::execute restatement below): PINNED by output of the reference itself.  The reference
+// repository ships ten images its own VM rendered together with the programs that rendered them
+// (rusteria/examples/*.png by the rsia CLI; rusteria/embedded/*.png by make_textures.rusteria); this interpreter
+// reproduces eight of them bit for bit and the two sin-hashed ones up to the platform libm
+// (tests/test_rusteria_golden.py, fixtures under tests/golden/rusteria/).
 //
 // Build: g++ -O2 -std=c++17 -ffp-contract=off -fno-fast-math -mfma -shared -fPIC (oracle/Makefile).
 // -ffp-contract=off matters: Rust never fuses a*b+c, GCC's default would.
