@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RXC_ABI_VERSION 3u
+#define RXC_ABI_VERSION 4u
 
 typedef struct rxc_ctx rxc_ctx;
 
@@ -306,6 +306,8 @@ typedef struct rxc_frame {
     uint32_t matvec_mode;         /* RXC_MATVEC_* */
     uint32_t band_y0;             /* multi-GPU band split: render rows [band_y0, band_y1);   */
     uint32_t band_y1;             /* both 0 = whole frame. `pixels` then holds only the band */
+    uint32_t band_x0;             /* ... and columns [band_x0, band_x1) (both 0 = every column): the output buffer */
+    uint32_t band_x1;             /* holds the rectangle, rows of (band_x1 - band_x0) pixels; band_x0 a multiple of 32 */
     /* Render graph (src/rasterizer.rs:227-253, :419-461; src/shapestack/shapefx.rs:935-1223).  The graph stays
      * on the host: it runs collect_nodes_from / render_setup / render_ambient_color (the latter lands in
      * `ambient`) and passes what the per-pixel code reads. */

@@ -2,7 +2,7 @@
 tests/test_abi.py checks sizes/offsets against a C probe compiled from the header."""
 import ctypes as C
 
-RXC_ABI_VERSION = 3
+RXC_ABI_VERSION = 4
 
 RXC_OK = 0
 RXC_ERR_INVALID = -1
@@ -193,6 +193,8 @@ class rxc_frame(C.Structure):
         ("matvec_mode", C.c_uint32),
         ("band_y0", C.c_uint32),
         ("band_y1", C.c_uint32),
+        ("band_x0", C.c_uint32),
+        ("band_x1", C.c_uint32),
         ("has_sun", C.c_uint32),
         ("sun_dir", C.c_float * 3),
         ("day_factor", C.c_float),

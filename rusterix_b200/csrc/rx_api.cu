@@ -362,6 +362,9 @@ int32_t fill_frame(rxc_ctx* ctx, const rxc_frame& f, DFrame* d) {
     uint32_t y0 = f.band_y0, y1 = f.band_y1;
     if (y0 == 0 && y1 == 0) y1 = f.height;
     if (y0 >= y1 || y1 > f.height) return fail(ctx, RXC_ERR_INVALID, "bad band");
+    uint32_t x0 = f.band_x0, x1 = f.band_x1;
+    if (x0 == 0 && x1 == 0) x1 = f.width;
+    if (x0 >= x1 || x1 > f.width) return fail(ctx, RXC_ERR_INVALID, "bad column band");
     memset(d, 0, sizeof(*d));
     memcpy(d->view, f.view, 64); memcpy(d->proj, f.projection, 64);
     memcpy(d->inv_view, f.inverse_view, 64); memcpy(d->inv_proj, f.inverse_projection, 64);
@@ -371,7 +374,8 @@ int32_t fill_frame(rxc_ctx* ctx, const rxc_frame& f, DFrame* d) {
     d->width_f = (float)f.width; d->height_f = (float)f.height;
     d->width = (int32_t)f.width; d->height = (int32_t)f.height;
     d->band_y0 = (int32_t)y0; d->band_y1 = (int32_t)y1;
-    d->tiles_x = (int32_t)((f.width + RX_TILE_W - 1) / RX_TILE_W);
+    d->band_x0 = (int32_t)x0; d->band_x1 = (int32_t)x1;
+    d->tiles_x = (int32_t)((x1 - x0 + RX_TILE_W - 1) / RX_TILE_W);
     d->tiles_y = (int32_t)((y1 - y0 + RX_TILE_H - 1) / RX_TILE_H);
     d->tile_size = std::min<uint32_t>(f.tile_size, std::max(f.width, f.height));  // one tile either way
     d->sample_mode = f.sample_mode;
@@ -572,7 +576,7 @@ int32_t launch_group(rxc_ctx* ctx, const DFrame* h_frames, DCounters* h_counters
     }
     RasterOut out;
     out.pixels = d_pixels; out.frame_stride = stride; out.owner = d_owner; out.depth = d_depth;
-    out.vec_store = (((uintptr_t)d_pixels & 15) == 0 && (stride & 15) == 0 && ((h_frames[0].width * 4) & 15) == 0) ? 1u : 0u;
+    out.vec_store = (((uintptr_t)d_pixels & 15) == 0 && (stride & 15) == 0 && (((h_frames[0].band_x1 - h_frames[0].band_x0) * 4) & 15) == 0) ? 1u : 0u;
     int sample_mode = (int)h_frames[0].sample_mode;
     for (uint32_t i = 1; i < n; ++i) if ((int)h_frames[i].sample_mode != sample_mode) sample_mode = 2;
     const uint32_t tiles_x = (uint32_t)h_frames[0].tiles_x, tiles_y = (uint32_t)h_frames[0].tiles_y;
@@ -634,12 +638,14 @@ int32_t rasterize_impl(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames,
     // all frames of a batch share the geometry of the output
     const rxc_frame& f0 = frames[0];
     for (uint32_t i = 1; i < n_frames; ++i)
-        if (frames[i].width != f0.width || frames[i].height != f0.height || frames[i].band_y0 != f0.band_y0 || frames[i].band_y1 != f0.band_y1)
+        if (frames[i].width != f0.width || frames[i].height != f0.height || frames[i].band_y0 != f0.band_y0 || frames[i].band_y1 != f0.band_y1 ||
+            frames[i].band_x0 != f0.band_x0 || frames[i].band_x1 != f0.band_x1)
             return fail(ctx, RXC_ERR_INVALID, "all frames of a batch must share width/height/band");
     DFrame probe;
     if ((st = fill_frame(ctx, f0, &probe)) != RXC_OK) return st;
     const uint32_t rows = (uint32_t)(probe.band_y1 - probe.band_y0);
-    const uint64_t frame_bytes = (uint64_t)f0.width * rows * 4;
+    const uint32_t cols = (uint32_t)(probe.band_x1 - probe.band_x0);
+    const uint64_t frame_bytes = (uint64_t)cols * rows * 4;
     if (n_frames > 1 && stride < frame_bytes) return fail(ctx, RXC_ERR_INVALID, "frame_stride_bytes smaller than a frame");
     const uint32_t tiles_per_frame = (uint32_t)probe.tiles_x * (uint32_t)probe.tiles_y;
 
@@ -673,7 +679,7 @@ int32_t rasterize_impl(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames,
         // slices only pay off from about 16 MB per frame on: every D2H copy carries ~10 us of fixed cost
         const uint32_t slices = (sub > 1 || slice_bytes == 0 || frame_bytes < ((uint64_t)16 << 20)) ? 1u
                                 : (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(16, (frame_bytes + slice_bytes / 2) / slice_bytes));
-        const uint64_t row_bytes = (uint64_t)f0.width * 4;
+        const uint64_t row_bytes = (uint64_t)cols * 4;
         if (ctx->h_frames_cap < n_frames) {
             CK(cudaStreamSynchronize(ctx->stream));
             if (ctx->h_frames) cudaFreeHost(ctx->h_frames);

@@ -206,7 +206,8 @@ struct DFrame {
     float width_f, height_f;
     int32_t width, height;        // full frame
     int32_t band_y0, band_y1;     // rows rendered
-    int32_t tiles_x, tiles_y;     // GPU tiles covering the band
+    int32_t band_x0, band_x1;     // columns rendered (the output buffer holds the rectangle, pitch band_x1 - band_x0)
+    int32_t tiles_x, tiles_y;     // GPU tiles covering the rectangle
     uint32_t tile_size;           // API tile size (scissor computation)
     uint32_t sample_mode;
     uint32_t has_bg_color, bg_color;

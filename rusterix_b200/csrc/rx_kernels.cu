@@ -289,6 +289,7 @@ __device__ __forceinline__ void d_frame_setup(const SceneDev& S, const Workspace
         scissor_1d(mnx, mxx - mnx, F.width, (int)F.tile_size, 0.5f, &sx0, &sx1);   // rasterizer.rs:594-600
         scissor_1d(mny, mxy - mny, F.height, (int)F.tile_size, 0.5f, &sy0, &sy1);
         sy0 = max(sy0, F.band_y0); sy1 = min(sy1, F.band_y1);
+        sx0 = max(sx0, F.band_x0); sx1 = min(sx1, F.band_x1);
         if (tid == 0) {
             DFrameBatch2 fb2;
             fb2.tex = 0xFFFFFFFFu; fb2.terrain = 0u; fb2.program = B.program;
@@ -519,7 +520,8 @@ __device__ __forceinline__ void d_tri_setup(const SceneDev& S, const Workspace& 
         vis = make_tri(P, T.uv, T.nn, B.cull_mode, edge_vis, F.width, F.height, meta, &tv, &tsh, &bin.bbx, &bin.bby);
         // band rendering (a rank of a row split): a triangle whose pixel rows miss the band is dropped before its
         // 176 B of records are written; the batch bbox above still saw it, like the reference's projected_vertices
-        if (vis && ((int)(bin.bby >> 16) <= F.band_y0 || (int)(bin.bby & 0xFFFFu) >= F.band_y1)) { vis = false; bin.bbx = 0u; bin.bby = 0u; }
+        if (vis && ((int)(bin.bby >> 16) <= F.band_y0 || (int)(bin.bby & 0xFFFFu) >= F.band_y1 || (int)(bin.bbx >> 16) <= F.band_x0 ||
+                    (int)(bin.bbx & 0xFFFFu) >= F.band_x1)) { vis = false; bin.bbx = 0u; bin.bby = 0u; }
         if (vis) {
             Wk.vis[(size_t)f * Wk.slot_stride + slot] = tv;
             Wk.shade[(size_t)f * Wk.slot_stride + slot] = tsh;
@@ -607,7 +609,7 @@ __device__ __forceinline__ void d_batch_finalize(const SceneDev& S, const Worksp
             int x0, x1, y0, y1;
             scissor_1d(mnx, mxx - mnx, F.width, (int)F.tile_size, 0.0f, &x0, &x1);  // rasterizer.rs:978-983
             scissor_1d(mny, mxy - mny, F.height, (int)F.tile_size, 0.0f, &y0, &y1);
-            FB.sc_x0 = x0; FB.sc_x1 = x1;
+            FB.sc_x0 = max(x0, F.band_x0); FB.sc_x1 = min(x1, F.band_x1);
             FB.sc_y0 = max(y0, F.band_y0); FB.sc_y1 = min(y1, F.band_y1);
         }
     }
@@ -642,7 +644,8 @@ __device__ __forceinline__ void d_clip_emit(const SceneDev& S, const Workspace& 
             TriBin bin = {0u, 0u, slot, c.batch};
             TriVis tv; TriShade tsh;
             if (make_tri(P, uv, nn, B.cull_mode, true, F.width, F.height, meta, &tv, &tsh, &bin.bbx, &bin.bby) &&
-                !((int)(bin.bby >> 16) <= F.band_y0 || (int)(bin.bby & 0xFFFFu) >= F.band_y1)) {
+                !((int)(bin.bby >> 16) <= F.band_y0 || (int)(bin.bby & 0xFFFFu) >= F.band_y1 || (int)(bin.bbx >> 16) <= F.band_x0 ||
+                  (int)(bin.bbx & 0xFFFFu) >= F.band_x1)) {
                 const uint32_t pos = atomicAdd(&C.n_new_slots, 1u);
                 if (pos < new_cap) {
                     Wk.vis[(size_t)f * Wk.slot_stride + slot] = tv;
@@ -663,7 +666,7 @@ __device__ __forceinline__ void d_clip_emit(const SceneDev& S, const Workspace& 
 __device__ __forceinline__ bool bin_tile_range(const DFrame& F, uint32_t bbx, uint32_t bby, int* tx0, int* tx1, int* ty0, int* ty1) {
     const int x0 = bbx & 0xFFFF, x1 = bbx >> 16, y0 = bby & 0xFFFF, y1 = bby >> 16;
     if (x0 >= x1 || y0 >= y1) return false;
-    *tx0 = x0 / RX_TILE_W; *tx1 = (x1 - 1) / RX_TILE_W;
+    *tx0 = (x0 - F.band_x0) / RX_TILE_W; *tx1 = (x1 - 1 - F.band_x0) / RX_TILE_W;
     *ty0 = (y0 - F.band_y0) / RX_TILE_H; *ty1 = (y1 - 1 - F.band_y0) / RX_TILE_H;
     return true;
 }
@@ -801,8 +804,8 @@ __device__ __forceinline__ void d_bin_large(const SceneDev& S, const Workspace& 
         const int w = tx1 - tx0 + 1, n = w * (ty1 - ty0 + 1);
         for (int i = (int)lane; i < n; i += 32) {
             const int tx = tx0 + i % w, ty = ty0 + i / w;
-            const int px0 = tx * RX_TILE_W, py0 = F.band_y0 + ty * RX_TILE_H;
-            if (rect_overlaps(T, px0, py0, min(px0 + RX_TILE_W, F.width), min(py0 + RX_TILE_H, F.band_y1)) == 0u) continue;
+            const int px0 = F.band_x0 + tx * RX_TILE_W, py0 = F.band_y0 + ty * RX_TILE_H;
+            if (rect_overlaps(T, px0, py0, min(px0 + RX_TILE_W, F.band_x1), min(py0 + RX_TILE_H, F.band_y1)) == 0u) continue;
             const int t = ty * F.tiles_x + tx;
             if (!fill) { atomicAdd(&tc[t], 1u); continue; }
             if (tc[t] == 0u) continue;  // list dropped on arena overflow
@@ -1912,7 +1915,7 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                 // no tile of this frame can be empty when the large triangles' boxes already cover the band (a sky box,
                 // the walls of a room): then the per-tile test is skipped altogether
                 bool can = F.d3_active && !(F.has_sky | F.has_brush);
-                if (!GENERAL) can = can && n_large == n_cached && !(s_union[0] <= 0 && s_union[1] <= F.band_y0 && s_union[2] >= F.width && s_union[3] >= F.band_y1);
+                if (!GENERAL) can = can && n_large == n_cached && !(s_union[0] <= F.band_x0 && s_union[1] <= F.band_y0 && s_union[2] >= F.band_x1 && s_union[3] >= F.band_y1);
                 s_can_be_empty = can ? 1 : 0;
             }
             __syncthreads();
@@ -1920,8 +1923,9 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
         const DLight* lights = S.n_lights <= (uint32_t)RX_SMEM_LIGHTS ? s_lights : lights_g;
 
         const uint32_t smode = SAMPLE == 2 ? F.sample_mode : (uint32_t)SAMPLE;
-        const int fw = F.width, fy1 = F.band_y1;
-        const int tx0 = s_work[1], ty0 = F.band_y0 + s_work[2];
+        const int fw = F.band_x1, fy1 = F.band_y1;   // right / bottom bound of the rendered rectangle
+        const int bx0 = F.band_x0, fpitch = F.band_x1 - F.band_x0;   // its left edge and the row pitch of the output buffer
+        const int tx0 = F.band_x0 + s_work[1], ty0 = F.band_y0 + s_work[2];
         const int tx1 = min(tx0 + RX_TILE_W, fw), ty1 = min(ty0 + RX_TILE_H, fy1);
         if (!PLANES && s_can_be_empty) {
             // Empty tile: no binned triangle, no large triangle and no 2D record can touch it -> every pixel is the miss
@@ -1939,13 +1943,13 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                 uint8_t* frame_px = out.pixels + (size_t)f * out.frame_stride;
                 if (out.vec_store && tx0 + RX_TILE_W <= fw && ty0 + RX_TILE_H <= fy1) {
                     const int r = (int)tid >> 3, c4 = (int)tid & 7;
-                    reinterpret_cast<uint4*>(frame_px + ((size_t)(ty0 - F.band_y0 + r) * (size_t)fw + (size_t)tx0) * 4)[c4] =
+                    reinterpret_cast<uint4*>(frame_px + ((size_t)(ty0 - F.band_y0 + r) * (size_t)fpitch + (size_t)(tx0 - bx0)) * 4)[c4] =
                         make_uint4(0xFF000000u, 0xFF000000u, 0xFF000000u, 0xFF000000u);
                 } else {
                     for (int i = (int)tid; i < RX_TILE_W * RX_TILE_H; i += RX_TILE_THREADS) {
                         const int r = i >> 5, c = i & 31;
                         if (tx0 + c < fw && ty0 + r < fy1)
-                            reinterpret_cast<uint32_t*>(frame_px)[(size_t)(ty0 - F.band_y0 + r) * (size_t)fw + (size_t)(tx0 + c)] = 0xFF000000u;
+                            reinterpret_cast<uint32_t*>(frame_px)[(size_t)(ty0 - F.band_y0 + r) * (size_t)fpitch + (size_t)(tx0 - bx0 + c)] = 0xFF000000u;
                     }
                 }
                 __syncthreads();  // s_work is rewritten by the next tile
@@ -2056,7 +2060,7 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
             }
             s_color[coff + cbase + ((k & 1) << 3) + (k >> 1) * (4 * RX_COLOR_STRIDE)] = color;
             if (PLANES && px < fw && py < fy1) {
-                const size_t o = (size_t)(py - F.band_y0) * (size_t)fw + (size_t)px;
+                const size_t o = (size_t)(py - F.band_y0) * (size_t)fpitch + (size_t)(px - bx0);
                 if (out.owner) out.owner[o] = owner;
                 if (out.depth) out.depth[o] = st.x;
             }
@@ -2108,20 +2112,20 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
 #if RX_BULK_STORE
             if (warp == 0) {
                 const uint32_t src = (uint32_t)__cvta_generic_to_shared(&s_color[coff + lane * RX_COLOR_STRIDE]);
-                uint8_t* dst = frame_px + ((size_t)(ty0 - F.band_y0 + (int)lane) * (size_t)fw + (size_t)tx0) * 4;
+                uint8_t* dst = frame_px + ((size_t)(ty0 - F.band_y0 + (int)lane) * (size_t)fpitch + (size_t)(tx0 - bx0)) * 4;
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" ::"l"(dst), "r"(src) : "memory");
             }
 #else
             const int r = (int)tid >> 3, c4 = (int)tid & 7;   // 8 x 16 B per 32-pixel row
             const uint4 v = *reinterpret_cast<const uint4*>(&s_color[coff + r * RX_COLOR_STRIDE + c4 * 4]);
-            uint4* dst = reinterpret_cast<uint4*>(frame_px + ((size_t)(ty0 - F.band_y0 + r) * (size_t)fw + (size_t)tx0) * 4) + c4;
+            uint4* dst = reinterpret_cast<uint4*>(frame_px + ((size_t)(ty0 - F.band_y0 + r) * (size_t)fpitch + (size_t)(tx0 - bx0)) * 4) + c4;
             *dst = v;
 #endif
         } else {
             for (int i = (int)tid; i < RX_TILE_W * RX_TILE_H; i += RX_TILE_THREADS) {
                 const int r = i >> 5, c = i & 31;
                 if (tx0 + c < fw && ty0 + r < fy1)
-                    reinterpret_cast<uint32_t*>(frame_px)[(size_t)(ty0 - F.band_y0 + r) * (size_t)fw + (size_t)(tx0 + c)] =
+                    reinterpret_cast<uint32_t*>(frame_px)[(size_t)(ty0 - F.band_y0 + r) * (size_t)fpitch + (size_t)(tx0 - bx0 + c)] =
                         s_color[coff + r * RX_COLOR_STRIDE + c];
             }
         }

@@ -298,6 +298,8 @@ def make_frame(rast, scene: Scene, width: int, height: int, tile_size: int, band
     f.matvec_mode = int(rast.matvec_mode)
     if band is not None:
         f.band_y0, f.band_y1 = int(band[0]), int(band[1])
+        if len(band) == 4:   # (y0, y1, x0, x1): a rectangle of the frame
+            f.band_x0, f.band_x1 = int(band[2]), int(band[3])
     # render graph results (Rasterizer.prepare_render_graph) and the brush preview
     if getattr(rast, "sun_dir", None) is not None:
         f.has_sun = 1

@@ -227,7 +227,8 @@ class Rasterizer:
         """Same positional arguments as the reference (src/rasterizer.rs:185-193).  `pixels` is a
         writable uint8 buffer of at least width*height*4 bytes: a numpy array, bytearray, or a torch
         tensor on the CPU or on the context's GPU.  `owner` (uint32) / `depth` (float32) are
-        optional parity outputs.  `band=(y0,y1)` renders only those rows into a band-sized buffer."""
+        optional parity outputs.  `band=(y0,y1)` renders only those rows into a band-sized buffer,
+        `band=(y0,y1,x0,x1)` only that rectangle (x0 a multiple of 32)."""
         self._check_supported()
         self.prepare_render_graph()
         self.width, self.height = float(width), float(height)
@@ -240,6 +241,7 @@ class Rasterizer:
         ctx.set_mapmini(self.mapmini)
         frame = marshal.make_frame(self, scene, width, height, tile_size, band)
         rows = height if band is None else band[1] - band[0]
+        width = width if band is None or len(band) < 4 else band[3] - band[2]   # the buffer holds the rendered rectangle
         p, _k1 = _buffer_pointer(pixels, width * rows * 4)
         if p is None:
             raise ValueError("pixels is required")
@@ -266,7 +268,8 @@ class Rasterizer:
             r.prepare_render_graph()
             frames[i] = marshal.make_frame(r, scene, width, height, tile_size, band)
         rows = height if band is None else band[1] - band[0]
-        return FrameBatch(ctx, frames, n, width * rows * 4)
+        cols = width if band is None or len(band) < 4 else band[3] - band[2]
+        return FrameBatch(ctx, frames, n, cols * rows * 4)
 
     @staticmethod
     def rasterize_batch(rasterizers, scene: Scene, pixels, width, height, tile_size, assets: Assets, band=None,

@@ -616,3 +616,30 @@ def test_empty_tile_fast_path_matches_the_full_path(make):
         assert np.array_equal(render(frame, planes=False), full)
         y0, y1 = 32, height - 45
         assert np.array_equal(render(frame, planes=False, band=(y0, y1)), full[y0:y1])
+
+
+@pytest.mark.parametrize("make", [lambda: scenes.map_config(640, 360, 40, logo_size=64), lambda: scenes.dense(1280, 720, 40, patches=8),
+                                  lambda: scenes.chunked_config(640, 360, 40), lambda: scenes.teapot(970, 543, 60, logo_size=64)],
+                         ids=["map", "dense", "chunked", "teapot_odd"])
+def test_column_bands_and_rectangles_match_the_full_frame(make):
+    """rxc_frame.band_x0/x1: a rank of a column split renders columns [x0, x1) (x0 on a GPU tile) into a buffer of that
+    width; rectangles combine both bands.  Pixels, owner ids and depth equal the full frame's, with and without planes."""
+    def render(**kw):
+        cfg = make()   # fresh scene per call (rasterize() appends the chunk lights every time)
+        return render_gpu(cfg.rasterizer(2), cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size, **kw)
+
+    cfg = make()
+    w, h = cfg.width, cfg.height
+    full = render(planes=True)
+    for (y0, y1, x0, x1) in ((0, h, 0, 96), (0, h, 96, 352), (0, h, 352, w), (64, h - 30, 160, w - 7), (32, 64, 32, 64)):
+        px = np.zeros((y1 - y0, x1 - x0, 4), dtype=np.uint8)
+        ow = np.zeros((y1 - y0, x1 - x0), dtype=np.uint32)
+        dp = np.zeros((y1 - y0, x1 - x0), dtype=np.float32)
+        c2 = make()
+        c2.rasterizer(2).rasterize(c2.scene, px, w, h, c2.tile_size, c2.assets, owner=ow, depth=dp, band=(y0, y1, x0, x1))
+        assert np.array_equal(px, full[0][y0:y1, x0:x1]) and np.array_equal(ow, full[1][y0:y1, x0:x1])
+        assert np.array_equal(dp.view(np.uint32), full[2][y0:y1, x0:x1].view(np.uint32))
+        c3 = make()
+        fast = np.zeros((y1 - y0, x1 - x0, 4), dtype=np.uint8)
+        c3.rasterizer(2).rasterize(c3.scene, fast, w, h, c3.tile_size, c3.assets, band=(y0, y1, x0, x1))
+        assert np.array_equal(fast, full[0][y0:y1, x0:x1])
