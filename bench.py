@@ -430,11 +430,11 @@ def main():
 
 def band_split(rank, world, local_rank, dev, flush, barrier, steps=5, warmup=3, balance_iters=12):
     """BASELINE.json config D: one 7680x4320 frame of the 1M-triangle scene split by screen band over the ranks
-    (SURVEY 8e).  Every rank runs setup on the replicated geometry (triangles outside its rows are dropped before
-    their records are written) and bins / rasterises only its rows; strong scaling of a single frame, time = max over
-    ranks; the NCCL gather of the bands to rank 0 is timed separately.  Band boundaries: equal heights first (reported
-    as `equal_bands_ms_per_frame`), then moved by `mgpu.BandBalancer` from the ranks' measured times (a few frames),
-    frozen at the best split found, and timed."""
+    (SURVEY 8e).  Every rank runs setup on the replicated geometry (triangles outside its band are dropped before
+    their records are written) and bins / rasterises only its band; strong scaling of a single frame, time = max over
+    ranks; the NCCL gather of the bands to rank 0 is timed separately.  Three splits are timed: equal-height row bands,
+    row bands whose boundaries `mgpu.BandBalancer` moved from the ranks' measured times (a few frames, frozen at the best
+    split found), and equal-width column bands; `ms_per_frame` is the best of them."""
     import torch
     import torch.distributed as dist
     from rusterix_b200 import Rasterizer, mgpu
@@ -475,24 +475,32 @@ def band_split(rank, world, local_rank, dev, flush, barrier, steps=5, warmup=3, 
         bal.update(mgpu.all_gather_times(timed_frame(batch), device=dev))
     bands = bal.use_best()
     batch = prepare(bands[rank])
-    ms = measure(batch)
-    y0, y1 = bands[rank]
-    mine = out[0, :max(0, y1 - y0)]
+    rows_ms = measure(batch)
+
+    # column bands (rxc_frame.band_x0/x1): every rank gets an equal-width slice of every tile row, the cheap sky rows and
+    # the expensive horizon rows alike, so the split is balanced by construction
+    x0, x1 = mgpu.column_band_for_rank(W, rank, world)
+    cbatch = Rasterizer.prepare_batch([rast], cfg.scene, W, H, cfg.tile_size, cfg.assets, band=(0, H, x0, x1), device=local_rank) if x1 > x0 else None
+    cols_ms = measure(cbatch)
+    mine = out.reshape(-1)[: H * max(0, x1 - x0) * 4].reshape(H, max(0, x1 - x0), 4)
     for _ in range(2):
-        mgpu.gather_ragged_bands_to_rank0(mine, bands, H, W, rank, world)
+        mgpu.gather_column_bands_to_rank0(mine, H, W, rank, world)
     barrier()
     g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
     g0.record()
-    mgpu.gather_ragged_bands_to_rank0(mine, bands, H, W, rank, world)
+    mgpu.gather_column_bands_to_rank0(mine, H, W, rank, world)
     g1.record()
     barrier()
     t = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return {"workload": desc + ", rows split into %d bands" % world, "scaling": "strong", "ms_per_frame": ms,
-            "Mpixel_per_s": W * H / (ms * 1e-3) / 1e6, "frames_per_s": 1.0 / (ms * 1e-3), "gather_ms": float(t.item()),
-            "bytes_to_rank0": (H - bands[0][1]) * W * 4, "band_edges": [b[0] for b in bands] + [H],
-            "bands": "cost-balanced from the ranks' measured times (mgpu.BandBalancer, %d frames)" % balance_iters,
-            "equal_bands_ms_per_frame": equal_ms}
+    ms = min(cols_ms, rows_ms)
+    return {"workload": desc + ", split into %d bands" % world, "scaling": "strong", "ms_per_frame": ms,
+            "Mpixel_per_s": W * H / (ms * 1e-3) / 1e6, "frames_per_s": 1.0 / (ms * 1e-3),
+            "split": "column bands" if cols_ms <= rows_ms else "cost-balanced row bands",
+            "column_bands_ms_per_frame": cols_ms, "balanced_row_bands_ms_per_frame": rows_ms, "equal_row_bands_ms_per_frame": equal_ms,
+            "row_band_edges": [b[0] for b in bands] + [H],
+            "row_bands": "cost-balanced from the ranks' measured times (mgpu.BandBalancer, %d frames)" % balance_iters,
+            "gather_ms": float(t.item()), "gather": "column bands to rank 0 (NCCL send/recv)", "bytes_to_rank0": (W - mgpu.column_band_for_rank(W, 0, world)[1]) * H * 4}
 
 
 def secondary(wname, local_rank, dev, flush, steps=5, warmup=3):

@@ -191,3 +191,35 @@ def gather_ragged_bands_to_rank0(band: torch.Tensor, bands: List[Tuple[int, int]
     if y1 > y0:
         dist.send(band[: y1 - y0].contiguous(), dst=0)
     return None
+
+
+def column_band_for_rank(width: int, rank: int, world: int, align: int = 32) -> Tuple[int, int]:
+    """Columns [x0, x1) of rank `rank` when a frame of `width` columns is split into `world` column bands whose left
+    edges are multiples of `align` (the GPU tile width).  Column bands cut every tile row -- the cheap sky rows and the
+    expensive horizon rows alike -- into `world` pieces, so equal widths are balanced without any measurement."""
+    cols_aligned = (width + align - 1) // align
+    per = (cols_aligned + world - 1) // world
+    return min(width, rank * per * align), min(width, (rank + 1) * per * align)
+
+
+def gather_column_bands_to_rank0(band: torch.Tensor, height: int, width: int, rank: int, world: int, align: int = 32):
+    """Each rank holds its column band [height, x1 - x0, 4] uint8; rank 0 returns the full [height, width, 4] frame."""
+    if world == 1:
+        return band
+    if rank == 0:
+        full = torch.empty((height, width, 4), dtype=torch.uint8, device=band.device)
+        x0, x1 = column_band_for_rank(width, 0, world, align)
+        full[:, x0:x1].copy_(band)
+        parts = []
+        for r in range(1, world):
+            x0, x1 = column_band_for_rank(width, r, world, align)
+            if x1 > x0:
+                buf = torch.empty((height, x1 - x0, 4), dtype=torch.uint8, device=band.device)
+                parts.append((x0, x1, buf, dist.irecv(buf, src=r)))
+        for x0, x1, buf, req in parts:
+            req.wait()
+            full[:, x0:x1].copy_(buf)
+        return full
+    if band.numel():
+        dist.send(band.contiguous(), dst=0)
+    return None

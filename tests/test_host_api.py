@@ -137,6 +137,12 @@ def _gloo_worker(rank, world, port, q):
         got = mgpu.gather_ragged_bands_to_rank0(full[y0:y1].clone(), bands, h, w, rank, world)
         if rank == 0:
             ok = ok and torch.equal(got, full)
+        # column bands: tile-aligned left edges, together the whole width, reassembled on rank 0
+        wide = (torch.arange(6 * 100 * 4, dtype=torch.int64) % 253).to(torch.uint8).reshape(6, 100, 4)
+        x0, x1 = mgpu.column_band_for_rank(100, rank, world)
+        got = mgpu.gather_column_bands_to_rank0(wide[:, x0:x1].clone(), 6, 100, rank, world)
+        if rank == 0:
+            ok = ok and torch.equal(got, wide)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
@@ -155,6 +161,13 @@ def test_gather_to_rank0_world2_gloo():
     for p in ps:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_column_bands_tile_the_width():
+    for width, world in ((7680, 8), (1920, 8), (100, 3), (33, 4), (3840, 1)):
+        bands = [mgpu.column_band_for_rank(width, r, world) for r in range(world)]
+        assert bands[0][0] == 0 and bands[-1][1] == width and all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
+        assert all(x0 % 32 == 0 for x0, x1 in bands if x1 > x0)   # ranks beyond the width get an empty band and idle
 
 
 def test_band_balancer_converges_on_a_skewed_cost_profile():
