@@ -1776,6 +1776,85 @@ __device__ __forceinline__ void process_record(const SceneDev& S, const DFrame& 
     }
 }
 
+// ---- small-triangle pass of long tile lists (fast mode) -------------------------------------------------
+// A tile at the horizon of a dense mesh holds thousands of triangles whose pixel boxes are a pixel or two wide.
+// Walked a record per warp (process_record: 128 pixel slots per record) such a tile is one long serial chain in the
+// one or two warps that own those pixels.  Here every THREAD takes one record of the list instead: a record whose
+// box, clipped to the tile, has at most RX_SMALL_MAX_PIX pixels is rasterised by that thread alone -- same edge,
+// barycentric, depth and alpha arithmetic as process_record / test_fragment -- and competes for its pixels with a
+// 64-bit shared-memory atomicMin on (order(z), slot).  That is the reference's sequential `z < zbuf` in submission
+// order (rasterizer.rs:1051-1060): the winner is the lexicographic minimum of (z, ordinal) over the fragments that
+// pass the alpha test, whatever the order they arrive in.  The other records are compacted into a shared list that
+// the warp walk then reads instead of the tile's whole list.
+#define RX_BIG_CAP 2048u        // compacted list of the other records (aliases the upper half of s_state)
+
+__device__ __forceinline__ uint32_t z_order_bits(float z) {   // monotone float -> uint map (z is never NaN here)
+    const uint32_t u = __float_as_uint(z);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float z_from_order_bits(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k); }
+#define RX_KEY_NONE ((((unsigned long long)0xBF800000u) << 32) | 0xFFFFFFFFull)   // (order(1.0f), RX_OWNER_NONE): z_buffer starts at 1.0
+
+// clipped pixel count of a record's box inside the tile; 0 = the record cannot touch the tile
+__device__ __forceinline__ int small_box(uint32_t bbx, uint32_t bby, int tx0, int ty0, int tx1, int ty1, int* x0, int* y0, int* x1, int* y1) {
+    *x0 = max((int)(bbx & 0xFFFFu), tx0); *x1 = min((int)(bbx >> 16), tx1);
+    *y0 = max((int)(bby & 0xFFFFu), ty0); *y1 = min((int)(bby >> 16), ty1);
+    const int w = *x1 - *x0, h = *y1 - *y0;
+    return (w <= 0 || h <= 0) ? 0 : w * h;
+}
+
+__device__ __noinline__ void small_triangle_pass(const SceneDev& S, const DFrame& F, const DFrameBatch* __restrict__ fbs,
+                                                 const TriVis* __restrict__ vis, const TriShade* __restrict__ shade,
+                                                 const uint32_t* __restrict__ list, uint32_t n_list, int tx0, int ty0, int tx1, int ty1,
+                                                 uint32_t sample_mode, int max_pix, unsigned long long* s_key, uint32_t* s_big, uint32_t* s_nbig) {
+    for (uint32_t i = threadIdx.x; i < n_list; i += RX_TILE_THREADS) {
+        const uint32_t slot = __ldg(list + i);
+        const float4* q = reinterpret_cast<const float4*>(vis + slot);
+        const float4 q5 = __ldg(q + 5);
+        const uint32_t meta = __float_as_uint(q5.w);
+        int x0, y0, x1, y1;
+        const int npix = small_box(__float_as_uint(q5.y), __float_as_uint(q5.z), tx0, ty0, tx1, ty1, &x0, &y0, &x1, &y1);
+        if (npix == 0) continue;
+        if (npix > max_pix) {
+            const uint32_t k = atomicAdd(s_nbig, 1u);
+            if (k < RX_BIG_CAP) s_big[k] = slot;
+            continue;
+        }
+        const float4 q3 = __ldg(q + 3), q4 = __ldg(q + 4);
+        const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+        // one loop over the box's pixels, row by row (lanes of a warp differ only in their pixel counts)
+        int x = x0, y = y0;
+        float fpy = (float)y + 0.5f;                 // rasterizer.rs:1022
+        float e0y = q3.w * fpy, e1y = q4.x * fpy, e2y = q4.y * fpy;
+#pragma unroll 1
+        for (int p = 0; p < npix; ++p) {
+            const float fpx = (float)x + 0.5f;
+            const int cx = x, cy = y;
+            const float fcy = fpy;
+            // Edges::evaluate, edge.rs:28-36: (a*px + b*py) + c < 0 -> outside
+            const bool in = !((q3.x * fpx + e0y) + q4.z < 0.0f) && !((q3.y * fpx + e1y) + q4.w < 0.0f) && !((q3.z * fpx + e2y) + q5.x < 0.0f);
+            if (++x == x1) {
+                x = x0; ++y;
+                fpy = (float)y + 0.5f;
+                e0y = q3.w * fpy; e1y = q4.x * fpy; e2y = q4.y * fpy;
+            }
+            if (!in) continue;
+            float al, be;
+            const float z = fragment_depth(q0, q1, q2, meta, fpx, fcy, &al, &be);
+            if (!(z < 1.0f)) continue;   // the first `z < zbuf` of a pixel is against 1.0; NaN fails
+            const unsigned long long key = ((unsigned long long)z_order_bits(z) << 32) | slot;
+            unsigned long long* cell = s_key + (cy - ty0) * RX_TILE_W + (cx - tx0);
+            if (key >= *reinterpret_cast<volatile unsigned long long*>(cell)) continue;
+            if (meta & RX_META_ALPHA) {  // alpha test: texel alpha must be 255 to write (:1408)
+                const uint32_t texel = alpha_test_texel<false>(S, S.arena, S.chunk_info, &F, fbs + (meta & RX_META_BATCH), shade + slot, al, be, z,
+                                                               fpx, fcy, sample_mode);
+                if ((texel >> 24) != 255u) continue;
+            }
+            atomicMin(cell, key);
+        }
+    }
+}
+
 // one 2D record against one pixel: triangle (rasterizer.rs:640-895) or Bresenham line (:901-955, :1777-1821)
 template <bool VM>
 __device__ __forceinline__ uint32_t apply_2d(const SceneDev& S, const DFrame& F, const DLight* __restrict__ lights,
@@ -1798,11 +1877,13 @@ __device__ __forceinline__ uint32_t apply_2d(const SceneDev& S, const DFrame& F,
 // SAMPLE: 0 nearest / 1 linear for every frame of the launch, 2 = read it per frame.  PLANES: owner/depth outputs.
 // GENERAL: the tile lists are sorted by submission ordinal and hold every triangle (no large list): chunk opacity
 // batches with their surface ids are evaluated sequentially, and 2D records come from sorted per-tile lists.
-// MODE: 0 = fast path, 1 = general (below), 2 = general + Rusteria VM programs on batches.
+// MODE: 0 = fast path, 1 = general (below), 2 = general + Rusteria VM programs on batches, 3 = fast path with the
+// thread-per-record pass of long tile lists (small_triangle_pass; its own instantiation because the extra code costs the
+// plain fast path 6 % on the map scene -- scenes with few triangles never have such lists and keep MODE 0).
 template <int SAMPLE, bool PLANES, int MODE>
 __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raster(SceneDev S, Workspace Wk, RasterOut out, uint32_t n_frames,
                                                                uint32_t tile0, uint32_t tiles_per_frame, uint32_t counter) {
-    constexpr bool GENERAL = MODE >= 1, VM = MODE == 2;
+    constexpr bool GENERAL = MODE == 1 || MODE == 2, VM = MODE == 2, SMALL = MODE == 3;
     __shared__ __align__(16) TriVis s_large[GENERAL ? 1 : RX_LARGE_CACHE];
     __shared__ uint32_t s_large_slot[GENERAL ? 1 : RX_LARGE_CACHE];
     __shared__ uint16_t s_sel[GENERAL ? 1 : RX_LARGE_CACHE];
@@ -1816,6 +1897,7 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
     __shared__ float s_kd[256];                      // srgb_to_linear_fast(c / 255) * (1 - 0.04), rasterizer.rs:20-25
     __shared__ int s_union[8];                       // pixel bbox of the frame's cached large triangles [0..3] and of its 2D records [4..7]
     __shared__ int s_can_be_empty;                   // per frame: some tile may be untouched (see the empty-tile path below)
+    __shared__ uint32_t s_nbig;                      // small-triangle pass: length of the compacted list of the other records
 
     uint32_t tid = threadIdx.x;
 #if RX_OPAQUE >= 3
@@ -1990,9 +2072,26 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
             }
             const uint32_t n_list = Wk.tile_count[(size_t)f * Wk.tile_stride + tile];
             const uint32_t* list = Wk.lists + (size_t)f * Wk.list_stride + Wk.tile_base[(size_t)f * Wk.tile_stride + tile];
+            // long list (uniform over the CTA): a thread per record for the small triangles, the others compacted (see
+            // small_triangle_pass).  s_key / s_big alias s_state, which is only written by the resolve below.
+            unsigned long long* s_key = reinterpret_cast<unsigned long long*>(s_state);
+            uint32_t* s_big = reinterpret_cast<uint32_t*>(s_state + 2 * RX_TILE_THREADS);
+            const bool small_pass = SMALL && n_list >= Wk.small_min_list;
+            if (small_pass) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) s_key[k * RX_TILE_THREADS + tid] = RX_KEY_NONE;
+                if (tid == 0) s_nbig = 0u;
+                __syncthreads();
+                small_triangle_pass(S, F, fbs, vis, shade, list, n_list, tx0, ty0, tx1, ty1, smode, (int)Wk.small_max_pix, s_key, s_big, &s_nbig);
+                __syncthreads();
+            }
 #pragma unroll 1
             for (int pass = GENERAL ? 2 : 0; pass < 3; ++pass) {
-                const uint32_t n_src = pass == 0 ? (n_cached > 32u ? s_nsel : n_cached) : pass == 1 ? n_large - n_cached : n_list;
+                // pass 2 after the small-triangle pass: the compacted list; if that overflowed, the whole list with the
+                // small records skipped
+                const bool from_big = SMALL && pass == 2 && small_pass && s_nbig <= RX_BIG_CAP;
+                const bool skip_small = SMALL && pass == 2 && small_pass && !from_big;
+                const uint32_t n_src = pass == 0 ? (n_cached > 32u ? s_nsel : n_cached) : pass == 1 ? n_large - n_cached : from_big ? s_nbig : n_list;
                 const uint32_t* src = pass == 1 ? large + n_cached : list;
 #pragma unroll 1
                 for (uint32_t base = 0; base < n_src; base += 32) {
@@ -2004,9 +2103,13 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                             const uint32_t r = n_cached > 32u ? (uint32_t)s_sel[i] : i;
                             rp = &s_large[r]; slot = s_large_slot[r];
                         } else {
-                            slot = __ldg(src + i); rp = vis + slot;
+                            slot = from_big ? s_big[i] : __ldg(src + i); rp = vis + slot;
                         }
                         if (region_ok) ov = rect_overlaps(*rp, rx0, ry0, rx1, ry1);
+                        if (skip_small) {
+                            int a0, b0, a1, b1;
+                            if (small_box(rp->bbx, rp->bby, tx0, ty0, tx1, ty1, &a0, &b0, &a1, &b1) <= (int)Wk.small_max_pix) ov = 0u;
+                        }
                     }
                     uint32_t mask = __ballot_sync(0xFFFFFFFFu, ov != 0u);
                     const uint32_t fullm = __ballot_sync(0xFFFFFFFFu, ov == 2u);
@@ -2018,6 +2121,23 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                         process_record<GENERAL, VM>(S, F, fbs, shade, Tp, rr, (fullm >> b) & 1u, px0, py0, fx0, fy0, valid, smode, V, O);
                     }
                 }
+            }
+            if (small_pass) {   // merge the small-triangle winners into the walk's state: the same (z, ordinal) rule as test_fragment
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned long long key = s_key[(ly + ((k >> 1) << 2)) * RX_TILE_W + lx + ((k & 1) << 3)];
+                    const uint32_t sslot = (uint32_t)key;
+                    if (sslot != RX_OWNER_NONE) {
+                        const float zs = z_from_order_bits((uint32_t)(key >> 32));
+                        if ((zs < V.z[k]) || (zs == V.z[k] && V.own[k] != RX_OWNER_NONE && sslot < V.own[k])) {
+                            const float4* q = reinterpret_cast<const float4*>(vis + sslot);
+                            V.z[k] = fragment_depth(__ldg(q), __ldg(q + 1), __ldg(q + 2), __float_as_uint(__ldg(q + 5).w),
+                                                    fx0 + ((k & 1) ? 8.0f : 0.0f), fy0 + ((k & 2) ? 4.0f : 0.0f), &V.al[k], &V.be[k]);
+                            V.own[k] = sslot;
+                        }
+                    }
+                }
+                __syncthreads();   // every key is read before s_state is written
             }
         }
 
@@ -2327,7 +2447,7 @@ cudaError_t rxk_raster(const SceneDev& S, const Workspace& W, const RasterOut& o
                        uint32_t counter, int sample_mode, int grid_x, cudaStream_t st) {
     const bool planes = out.owner || out.depth;
 #define RX_LAUNCH(SM, PL, MD) k_raster<SM, PL, MD><<<grid_x, RX_TILE_THREADS, 0, st>>>(S, W, out, n_frames, tile0, n_tiles, counter)
-#define RX_LAUNCH2(SM, PL) do { if (S.general && S.vm.n_programs) RX_LAUNCH(SM, PL, 2); else if (S.general) RX_LAUNCH(SM, PL, 1); else RX_LAUNCH(SM, PL, 0); } while (0)
+#define RX_LAUNCH2(SM, PL) do { if (S.general && S.vm.n_programs) RX_LAUNCH(SM, PL, 2); else if (S.general) RX_LAUNCH(SM, PL, 1); else if (S.n_tris >= W.small_min_tris) RX_LAUNCH(SM, PL, 3); else RX_LAUNCH(SM, PL, 0); } while (0)
     if (sample_mode == 0) { if (planes) RX_LAUNCH2(0, true); else RX_LAUNCH2(0, false); }
     else if (sample_mode == 1) { if (planes) RX_LAUNCH2(1, true); else RX_LAUNCH2(1, false); }
     else { if (planes) RX_LAUNCH2(2, true); else RX_LAUNCH2(2, false); }
@@ -2339,6 +2459,7 @@ int rxk_raster_blocks_per_sm() {
     int n = 0, best = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_raster<0, false, 0>, RX_TILE_THREADS, 0) == cudaSuccess) best = n;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_raster<1, false, 0>, RX_TILE_THREADS, 0) == cudaSuccess && n < best) best = n;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_raster<1, false, 3>, RX_TILE_THREADS, 0) == cudaSuccess && n < best) best = n;
     return best < 1 ? 1 : best;
 }
 cudaError_t rxk_vm_execute(const SceneDev& S, uint32_t program, uint32_t n, const float* d_in, float* d_out, uint32_t* d_faults, cudaStream_t st) {

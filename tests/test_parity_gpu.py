@@ -643,3 +643,40 @@ def test_column_bands_and_rectangles_match_the_full_frame(make):
         fast = np.zeros((y1 - y0, x1 - x0, 4), dtype=np.uint8)
         c3.rasterizer(2).rasterize(c3.scene, fast, w, h, c3.tile_size, c3.assets, band=(y0, y1, x0, x1))
         assert np.array_equal(fast, full[0][y0:y1, x0:x1])
+
+
+def test_small_triangle_pass_long_tile_lists():
+    """Tiles whose binned list holds >= 128 records take the thread-per-record pass of k_raster (small triangles through a
+    shared-memory atomicMin on (z, ordinal), the rest compacted for the warp walk): a quarter of a million triangles on a
+    640x360 frame (about a thousand per tile), then the same kind of frame with alpha-holed textures and with batches
+    drawn twice (exact depth ties: the first drawn must keep the pixel)."""
+    from rusterix_b200 import Assets, DeviceContext, Tile
+    st = _run(scenes.dense(640, 360, 40, patches=16), what="dense 16x16 patches on 640x360")
+    assert DeviceContext.get(0).stats().last_binned_refs > 128 * 200
+    cfg = scenes.dense(480, 270, 40, patches=10)
+    cfg.assets = Assets.default().textures([Tile.from_texture(scenes.tex_terrain(i, holes=True)) for i in range(16)])
+    cfg.sample_mode = SampleMode.Nearest
+    cfg.scene.d3_static.extend(cfg.scene.d3_static[:40])
+    cfg.scene.mark_dirty()
+    _run(cfg, what="dense, holed textures, duplicated batches")
+
+
+def test_small_triangle_pass_compacted_list_overflow():
+    """More than 2048 records that are NOT small in one tile: the compacted shared list overflows and the warp walk reads
+    the tile's whole list again, skipping the records the thread-per-record pass took."""
+    cfg = scenes.cube(160, 120, 40, logo_size=16)
+    rng = np.random.default_rng(11)
+    verts, tris = [], []
+    for i in range(18000):   # 16384 triangles and more select the kernel variant that has the pass
+        small = i % 5 == 0 or i >= 6000
+        cx, cy = rng.uniform(-0.12, 0.12, 2) if i < 6000 else rng.uniform(-1.0, 1.0, 2)
+        s = rng.uniform(0.004, 0.05) if small else rng.uniform(0.1, 0.2)
+        z = rng.uniform(-0.3, 0.3)
+        base = len(verts)
+        a = rng.uniform(0, 2 * math.pi)
+        for k in range(3):
+            verts.append((cx + s * math.cos(a + 2.1 * k), cy + s * math.sin(a + 2.1 * k), z, 1.0))
+        tris.append((base, base + 1, base + 2))
+    cfg.scene.d3_static.append(_tri_batch(verts, tris))
+    cfg.scene.mark_dirty()
+    _run(cfg, what="6000 overlapping triangles in a few tiles")
