@@ -81,7 +81,7 @@ struct rxc_ctx {
     int piece_mb = 8;             // host output: small frames are rendered and drained in groups of about this size
     int slice_mb = 4;             // host output: large frames are rendered and drained in slices of about this size (0 = whole frames)
     int front_stop = 0;           // profiling aid: k_front_cluster leaves after this many phases (RXC_FRONT_STOP)
-    int small_min_list = RX_SMALL_MIN_LIST, small_max_pix = RX_SMALL_MAX_PIX, small_min_tris = RX_SMALL_MIN_TRIS;   // k_raster: thread-per-record pass of tile lists at least this long, for boxes up to this many pixels
+    int small_min_list = RX_SMALL_MIN_LIST, small_max_pix = RX_SMALL_MAX_PIX, small_min_tris = RX_SMALL_MIN_TRIS, small_gshift = RX_SMALL_GSHIFT;   // k_raster: thread-per-record pass of tile lists at least this long, for boxes up to this many pixels
     int front_cluster_max = 64;   // setup chunks up to which the front end runs as one cluster per frame (0 = never)
     // host-output pipelining: a copy stream and two staging halves so the D2H of one sub-group of
     // frames overlaps the kernels of the next
@@ -324,6 +324,7 @@ int32_t ensure_workspace(rxc_ctx* ctx, uint32_t n_frames, uint32_t tiles_per_fra
     W.chunk_new_base = ctx->w_cbase.as<uint32_t>(); W.chunk_stride = std::max(1u, S.n_chunks);
     W.clip = ctx->w_clip.as<DClip>(); W.clip_stride = (uint32_t)std::max<size_t>(1, T);
     W.small_min_list = (uint32_t)std::max(1, ctx->small_min_list); W.small_max_pix = (uint32_t)ctx->small_max_pix;
+    W.small_gshift = (uint32_t)ctx->small_gshift;
     W.small_min_tris = ctx->small_min_list > 0 ? (uint32_t)std::max(0, ctx->small_min_tris) : 0xFFFFFFFFu;
     W.large = ctx->w_large.as<uint32_t>(); W.large_stride = (uint32_t)std::max<size_t>(1, 3 * T);
     W.tile_count = ctx->w_tcount.as<uint32_t>();
@@ -846,8 +847,9 @@ int32_t rxc_create(int32_t device, rxc_ctx** out) {
     if (const char* e = getenv("RXC_SLICE_MB")) ctx->slice_mb = std::max(0, atoi(e));
     if (const char* e = getenv("RXC_FRONT_STOP")) ctx->front_stop = std::max(0, atoi(e));
     if (const char* e = getenv("RXC_SMALL_MIN_LIST")) ctx->small_min_list = atoi(e);   // 0 = pass off
+    if (const char* e = getenv("RXC_SMALL_GSHIFT")) ctx->small_gshift = std::min(5, std::max(0, atoi(e)));
     if (const char* e = getenv("RXC_SMALL_MIN_TRIS")) ctx->small_min_tris = atoi(e);
-    if (const char* e = getenv("RXC_SMALL_MAX_PIX")) ctx->small_max_pix = std::max(1, atoi(e));
+    if (const char* e = getenv("RXC_SMALL_MAX_PIX")) ctx->small_max_pix = std::min(1024, std::max(1, atoi(e)));
     if (const char* e = getenv("RXC_FRONT_CLUSTER_MAX")) ctx->front_cluster_max = atoi(e);  // tuning knob for experiments
     *out = ctx;
     return RXC_OK;

@@ -1793,6 +1793,8 @@ __device__ __forceinline__ uint32_t z_order_bits(float z) {   // monotone float 
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 __device__ __forceinline__ float z_from_order_bits(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k); }
+// c_inv_w[w] = 65536 / w + 1: p / w == (p * c_inv_w[w]) >> 16 for p < 1024 and 1 <= w <= 32 (an integer division costs ~25 instructions)
+__constant__ uint32_t c_inv_w[33] = {0, 65537, 32769, 21846, 16385, 13108, 10923, 9363, 8193, 7282, 6554, 5958, 5462, 5042, 4682, 4370, 4097, 3856, 3641, 3450, 3277, 3121, 2979, 2850, 2731, 2622, 2521, 2428, 2341, 2260, 2185, 2115, 2049};
 #define RX_KEY_NONE ((((unsigned long long)0xBF800000u) << 32) | 0xFFFFFFFFull)   // (order(1.0f), RX_OWNER_NONE): z_buffer starts at 1.0
 
 // clipped pixel count of a record's box inside the tile; 0 = the record cannot touch the tile
@@ -1806,8 +1808,12 @@ __device__ __forceinline__ int small_box(uint32_t bbx, uint32_t bby, int tx0, in
 __device__ __noinline__ void small_triangle_pass(const SceneDev& S, const DFrame& F, const DFrameBatch* __restrict__ fbs,
                                                  const TriVis* __restrict__ vis, const TriShade* __restrict__ shade,
                                                  const uint32_t* __restrict__ list, uint32_t n_list, int tx0, int ty0, int tx1, int ty1,
-                                                 uint32_t sample_mode, int max_pix, unsigned long long* s_key, uint32_t* s_big, uint32_t* s_nbig) {
-    for (uint32_t i = threadIdx.x; i < n_list; i += RX_TILE_THREADS) {
+                                                 uint32_t sample_mode, int max_pix, uint32_t gshift, unsigned long long* s_key, uint32_t* s_big,
+                                                 uint32_t* s_nbig) {
+    // a group of 2^gshift neighbouring lanes per record: they read the same record (one transaction) and share out the
+    // pixels of its box, pixel p = sub + j * group -> (x0 + p % w, y0 + p / w)
+    const uint32_t group = 1u << gshift, sub = threadIdx.x & (group - 1u), per_round = RX_TILE_THREADS >> gshift;
+    for (uint32_t i = threadIdx.x >> gshift; i < n_list; i += per_round) {
         const uint32_t slot = __ldg(list + i);
         const float4* q = reinterpret_cast<const float4*>(vis + slot);
         const float4 q5 = __ldg(q + 5);
@@ -1816,38 +1822,34 @@ __device__ __noinline__ void small_triangle_pass(const SceneDev& S, const DFrame
         const int npix = small_box(__float_as_uint(q5.y), __float_as_uint(q5.z), tx0, ty0, tx1, ty1, &x0, &y0, &x1, &y1);
         if (npix == 0) continue;
         if (npix > max_pix) {
-            const uint32_t k = atomicAdd(s_nbig, 1u);
-            if (k < RX_BIG_CAP) s_big[k] = slot;
+            if (sub == 0u) {
+                const uint32_t k = atomicAdd(s_nbig, 1u);
+                if (k < RX_BIG_CAP) s_big[k] = slot;
+            }
             continue;
         }
         const float4 q3 = __ldg(q + 3), q4 = __ldg(q + 4);
         const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
-        // one loop over the box's pixels, row by row (lanes of a warp differ only in their pixel counts)
-        int x = x0, y = y0;
-        float fpy = (float)y + 0.5f;                 // rasterizer.rs:1022
-        float e0y = q3.w * fpy, e1y = q4.x * fpy, e2y = q4.y * fpy;
+        const uint32_t w = (uint32_t)(x1 - x0);
+        const uint32_t iw = c_inv_w[w];
 #pragma unroll 1
-        for (int p = 0; p < npix; ++p) {
-            const float fpx = (float)x + 0.5f;
-            const int cx = x, cy = y;
-            const float fcy = fpy;
+        for (uint32_t p = sub; p < (uint32_t)npix; p += group) {
+            const uint32_t row = (p * iw) >> 16;
+            const int x = x0 + (int)(p - row * w), y = y0 + (int)row;
+            const float fpx = (float)x + 0.5f, fpy = (float)y + 0.5f;   // rasterizer.rs:1022
             // Edges::evaluate, edge.rs:28-36: (a*px + b*py) + c < 0 -> outside
-            const bool in = !((q3.x * fpx + e0y) + q4.z < 0.0f) && !((q3.y * fpx + e1y) + q4.w < 0.0f) && !((q3.z * fpx + e2y) + q5.x < 0.0f);
-            if (++x == x1) {
-                x = x0; ++y;
-                fpy = (float)y + 0.5f;
-                e0y = q3.w * fpy; e1y = q4.x * fpy; e2y = q4.y * fpy;
-            }
-            if (!in) continue;
+            if ((q3.x * fpx + q3.w * fpy) + q4.z < 0.0f) continue;
+            if ((q3.y * fpx + q4.x * fpy) + q4.w < 0.0f) continue;
+            if ((q3.z * fpx + q4.y * fpy) + q5.x < 0.0f) continue;
             float al, be;
-            const float z = fragment_depth(q0, q1, q2, meta, fpx, fcy, &al, &be);
+            const float z = fragment_depth(q0, q1, q2, meta, fpx, fpy, &al, &be);
             if (!(z < 1.0f)) continue;   // the first `z < zbuf` of a pixel is against 1.0; NaN fails
             const unsigned long long key = ((unsigned long long)z_order_bits(z) << 32) | slot;
-            unsigned long long* cell = s_key + (cy - ty0) * RX_TILE_W + (cx - tx0);
+            unsigned long long* cell = s_key + (y - ty0) * RX_TILE_W + (x - tx0);
             if (key >= *reinterpret_cast<volatile unsigned long long*>(cell)) continue;
             if (meta & RX_META_ALPHA) {  // alpha test: texel alpha must be 255 to write (:1408)
                 const uint32_t texel = alpha_test_texel<false>(S, S.arena, S.chunk_info, &F, fbs + (meta & RX_META_BATCH), shade + slot, al, be, z,
-                                                               fpx, fcy, sample_mode);
+                                                               fpx, fpy, sample_mode);
                 if ((texel >> 24) != 255u) continue;
             }
             atomicMin(cell, key);
@@ -2082,7 +2084,7 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                 for (int k = 0; k < 4; ++k) s_key[k * RX_TILE_THREADS + tid] = RX_KEY_NONE;
                 if (tid == 0) s_nbig = 0u;
                 __syncthreads();
-                small_triangle_pass(S, F, fbs, vis, shade, list, n_list, tx0, ty0, tx1, ty1, smode, (int)Wk.small_max_pix, s_key, s_big, &s_nbig);
+                small_triangle_pass(S, F, fbs, vis, shade, list, n_list, tx0, ty0, tx1, ty1, smode, (int)Wk.small_max_pix, Wk.small_gshift, s_key, s_big, &s_nbig);
                 __syncthreads();
             }
 #pragma unroll 1

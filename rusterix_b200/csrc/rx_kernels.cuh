@@ -39,9 +39,10 @@ struct SceneDev {
 };
 
 // Per-frame workspace: every array holds `n_frames` slices of the given stride (in elements)
-#define RX_SMALL_MIN_LIST 128   // tiles whose binned list is at least this long take the pass
+#define RX_SMALL_MIN_LIST 64    // tiles whose binned list is at least this long take the pass
 #define RX_SMALL_MIN_TRIS 16384 // scenes with fewer triangles run the plain fast-path kernel (no tile list can be long enough to matter)
-#define RX_SMALL_MAX_PIX 64     // pixel count of the clipped box up to which a record is "small"
+#define RX_SMALL_GSHIFT 3       // 8 lanes share a record's pixels
+#define RX_SMALL_MAX_PIX 256    // pixel count of the clipped box up to which a record is "small"
 struct Workspace {
     DFrame* frames;
     DFrameBatch* fb;        uint32_t fb_stride;
@@ -66,6 +67,7 @@ struct Workspace {
     Tri2D* tri2d;           uint32_t tri2d_stride;
     uint32_t* raster_counter;  // RX_RASTER_COUNTERS work counters, one per k_raster launch of a call (zeroed by the frame setup)
     uint32_t small_min_list, small_max_pix;  // k_raster's thread-per-record pass of long tile lists
+    uint32_t small_gshift;                   // log2 of the lanes that share one record in the pass
     uint32_t small_min_tris;                 // scenes with at least this many triangles run the k_raster variant that has the pass (0xFFFFFFFF = never)
 };
 
