@@ -1009,7 +1009,8 @@ __device__ __forceinline__ uint32_t sample_nearest_fast(const uint32_t* __restri
     return __ldg(tex + ty * W + tx);
 }
 // Texture::sample_linear (texture.rs:414-460) for shading: same taps and weights, FMA lerps, channels
-// rounded by the saturating conversion
+// rounded by the saturating conversion.  Only the owner of a pixel is shaded, and a fragment owns a pixel only if
+// its exactly sampled texel has alpha 255 (rasterizer.rs:1408): the alpha channel is not filtered again, it is 255.
 __device__ __forceinline__ uint32_t sample_linear_fast(const uint32_t* __restrict__ tex, int W, int H, float u, float v,
                                                        bool repeat_x, bool repeat_y) {
     u = fast_wrap(u, repeat_x);
@@ -1021,9 +1022,9 @@ __device__ __forceinline__ uint32_t sample_linear_fast(const uint32_t* __restric
     const float dx = x - fx, dy = y - fy;
     const uint32_t c00 = __ldg(tex + y0 * W + x0), c10 = __ldg(tex + y0 * W + x1);
     const uint32_t c01 = __ldg(tex + y1 * W + x0), c11 = __ldg(tex + y1 * W + x1);
-    uint32_t out = 0;
+    uint32_t out = 0xFF000000u;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 3; ++i) {
         const float v00 = (float)((c00 >> (8 * i)) & 0xFF), v10 = (float)((c10 >> (8 * i)) & 0xFF);
         const float v01 = (float)((c01 >> (8 * i)) & 0xFF), v11 = (float)((c11 >> (8 * i)) & 0xFF);
         const float a = __fmaf_rn(dx, v10 - v00, v00), b = __fmaf_rn(dx, v11 - v01, v01);
