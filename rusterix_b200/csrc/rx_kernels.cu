@@ -1179,9 +1179,12 @@ __device__ __forceinline__ uint32_t shade_owner(const SceneDev& S, const ShadeCo
     if (flags & RX_SD_TEXTURED) {
         // perspective-correct UV, rasterizer.rs:1062-1076.  The owner is decided; the quotients are
         // faithful (rcp + one residual correction) instead of div.rn.
-        const float iu = __fmaf_rn(s1.x, gamma, __fmaf_rn(s0.z, beta, s0.x * alpha));
-        const float iv = __fmaf_rn(s1.y, gamma, __fmaf_rn(s0.w, beta, s0.y * alpha));
-        const float irw = __fmaf_rn(s2.x, gamma, __fmaf_rn(s1.w, beta, s1.z * alpha));
+        // The three sums are the reference's own unfused operations: on a triangle that crosses the near plane the terms
+        // cancel, and a fused sum then differs from the reference's by far more than an ulp -- on a minified noise texture
+        // that is another texel (fuzz seed 20675: 32 % of the frame).
+        const float iu = s0.x * alpha + s0.z * beta + s1.x * gamma;
+        const float iv = s0.y * alpha + s0.w * beta + s1.y * gamma;
+        const float irw = s1.z * alpha + s1.w * beta + s2.x * gamma;
         const float rr = fast_rcp(irw);
         float u = iu * rr, v = iv * rr;
         u = __fmaf_rn(__fmaf_rn(-irw, u, iu), rr, u);
