@@ -508,7 +508,8 @@ def secondary(wname, local_rank, dev, flush, steps=5, warmup=3):
     import torch
     from rusterix_b200 import DeviceContext, Rasterizer
 
-    F = 1 if wname == "dense8k" else 8
+    # config E is a 4096-frame batch: 32 cameras per call (265 MB of frames) amortise the per-call front end
+    F = 1 if wname == "dense8k" else 32 if wname == "sweep1080" else 8
     cfg, frame_ids, desc = build_workload(wname, F, 0, 1)
     rasts = [cfg.rasterizer(i).on_device(local_rank) for i in frame_ids]
     out = torch.empty((F, cfg.height, cfg.width, 4), dtype=torch.uint8, device=dev)
