@@ -258,6 +258,10 @@ __device__ __forceinline__ void d_frame_setup(const SceneDev& S, const Workspace
             if (!l.emitting) l.range2 = 0.0f;
             else if (l.light_type == RXC_LIGHT_AMBIENT || l.light_type == RXC_LIGHT_AMBIENT_DAYLIGHT) l.range2 = CUDART_INF_F;
             else l.range2 = l.end_distance > 0.0f ? l.end_distance * l.end_distance * 1.00001f : (l.end_distance <= 0.0f ? 0.0f : CUDART_INF_F);  // NaN: no cull
+            // spot lights: the per-frame copy carries cos(cone_angle) in `width` (an area light's field) for the deferred shade's
+            // cone test; < 0 rejects every direction, > pi none, NaN none (light.rs:566-569 compares acos(..) > cone_angle)
+            if (l.light_type == RXC_LIGHT_SPOT)
+                l.width = l.cone_angle < 0.0f ? CUDART_INF_F : l.cone_angle > 3.14159274f ? -CUDART_INF_F : cosf(l.cone_angle);
             Wk.lights[(size_t)f * Wk.lights_stride + i] = l;
         }
         return;
@@ -1130,7 +1134,8 @@ __device__ __forceinline__ bool light_radiance_fast(const DLight& l, float n_dot
             const float a = (dist <= l.start_distance) ? 1.0f : __fmaf_rn(dist - l.start_distance, l.inv_range, 1.0f);
             // direction_to_point = -ldir; angle = acos(dir . direction_to_point) > cone_angle -> None
             const float c = -(l.dx * ldir.x + l.dy * ldir.y + l.dz * ldir.z);
-            if (acosf(c) > l.cone_angle) return false;
+            // acos(c) > cone_angle  <=>  c < cos(cone_angle) for c in [-1, 1]; outside, acos is NaN and the light passes
+            if (c < l.width && c >= -1.0f && c <= 1.0f) return false;
             att = l.intensity * a * l.flicker_factor;
             break;
         }
