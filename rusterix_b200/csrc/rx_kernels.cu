@@ -708,6 +708,12 @@ __device__ __forceinline__ void d_bin_count(const SceneDev& S, const Workspace& 
             else atomicOr(&C.overflow, 2u);
             b.batch |= 0x80000000u;
             dirty = true;
+        } else if (nt == 1) {
+            // warp-aggregated: neighbouring triangles of a mesh fall into the same tile, and at the horizon of a dense mesh
+            // thousands of them into the same few tiles -- one atomic per tile and warp instead of one per triangle
+            const int t = ty0 * F.tiles_x + tx0;
+            const unsigned peers = __match_any_sync(__activemask(), t);
+            if ((uint32_t)(__ffs(peers) - 1) == (threadIdx.x & 31u)) atomicAdd(&tc[t], (uint32_t)__popc(peers));
         } else {
             for (int ty = ty0; ty <= ty1; ++ty)
                 for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(&tc[ty * F.tiles_x + tx], 1u);
@@ -751,6 +757,17 @@ __device__ __forceinline__ void d_bin_fill(const SceneDev& S, const Workspace& W
         if (b.batch & 0x80000000u) continue;
         int tx0, tx1, ty0, ty1;
         if (!bin_tile_range(F, b.bbx, b.bby, &tx0, &tx1, &ty0, &ty1)) continue;
+        if (tx0 == tx1 && ty0 == ty1) {   // single tile: one atomic per tile and warp (see d_bin_count)
+            const int t = ty0 * F.tiles_x + tx0;
+            if (tc[t] == 0u) continue;  // list dropped on arena overflow
+            const unsigned peers = __match_any_sync(__activemask(), t);
+            const uint32_t lane = threadIdx.x & 31u, leader = (uint32_t)(__ffs(peers) - 1);
+            uint32_t pos = 0u;
+            if (lane == leader) pos = atomicAdd(&tf[t], (uint32_t)__popc(peers));
+            pos = __shfl_sync(peers, pos, (int)leader) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+            lists[tb[t] + pos] = b.slot;
+            continue;
+        }
         for (int ty = ty0; ty <= ty1; ++ty)
             for (int tx = tx0; tx <= tx1; ++tx) {
                 const int t = ty * F.tiles_x + tx;
