@@ -675,6 +675,22 @@ __device__ __forceinline__ bool bin_tile_range(const DFrame& F, uint32_t bbx, ui
     return true;
 }
 
+// Warp-aggregated tile counters: the lanes that are at the same tile in the same step share one atomic
+// (`__match_any_sync` over whoever is converged here).  Neighbouring triangles of a mesh fall into the same tiles, and at
+// the horizon of a dense mesh thousands of them into the same few -- one atomic per tile and warp instead of one per
+// triangle and tile.  tile_slot() returns the caller's own entry of the group's reservation.
+__device__ __forceinline__ void tile_count(uint32_t* tc, int t) {
+    const unsigned peers = __match_any_sync(__activemask(), t);
+    if ((uint32_t)(__ffs(peers) - 1) == (threadIdx.x & 31u)) atomicAdd(&tc[t], (uint32_t)__popc(peers));
+}
+__device__ __forceinline__ uint32_t tile_slot(uint32_t* tf, int t) {
+    const unsigned peers = __match_any_sync(__activemask(), t);
+    const uint32_t lane = threadIdx.x & 31u, leader = (uint32_t)(__ffs(peers) - 1);
+    uint32_t pos = 0u;
+    if (lane == leader) pos = atomicAdd(&tf[t], (uint32_t)__popc(peers));
+    return __shfl_sync(peers, pos, (int)leader) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+}
+
 __device__ __forceinline__ void d_bin_count(const SceneDev& S, const Workspace& Wk, Blk bk) {
     const uint32_t f = bk.y;
     const DFrame& F = Wk.frames[f];
@@ -709,14 +725,10 @@ __device__ __forceinline__ void d_bin_count(const SceneDev& S, const Workspace& 
             b.batch |= 0x80000000u;
             dirty = true;
         } else if (nt == 1) {
-            // warp-aggregated: neighbouring triangles of a mesh fall into the same tile, and at the horizon of a dense mesh
-            // thousands of them into the same few tiles -- one atomic per tile and warp instead of one per triangle
-            const int t = ty0 * F.tiles_x + tx0;
-            const unsigned peers = __match_any_sync(__activemask(), t);
-            if ((uint32_t)(__ffs(peers) - 1) == (threadIdx.x & 31u)) atomicAdd(&tc[t], (uint32_t)__popc(peers));
+            tile_count(tc, ty0 * F.tiles_x + tx0);
         } else {
             for (int ty = ty0; ty <= ty1; ++ty)
-                for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(&tc[ty * F.tiles_x + tx], 1u);
+                for (int tx = tx0; tx <= tx1; ++tx) tile_count(tc, ty * F.tiles_x + tx);
         }
         if (dirty) bins[i] = b;
     }
@@ -757,23 +769,17 @@ __device__ __forceinline__ void d_bin_fill(const SceneDev& S, const Workspace& W
         if (b.batch & 0x80000000u) continue;
         int tx0, tx1, ty0, ty1;
         if (!bin_tile_range(F, b.bbx, b.bby, &tx0, &tx1, &ty0, &ty1)) continue;
-        if (tx0 == tx1 && ty0 == ty1) {   // single tile: one atomic per tile and warp (see d_bin_count)
+        if (tx0 == tx1 && ty0 == ty1) {   // single tile, the common case of a dense mesh
             const int t = ty0 * F.tiles_x + tx0;
             if (tc[t] == 0u) continue;  // list dropped on arena overflow
-            const unsigned peers = __match_any_sync(__activemask(), t);
-            const uint32_t lane = threadIdx.x & 31u, leader = (uint32_t)(__ffs(peers) - 1);
-            uint32_t pos = 0u;
-            if (lane == leader) pos = atomicAdd(&tf[t], (uint32_t)__popc(peers));
-            pos = __shfl_sync(peers, pos, (int)leader) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-            lists[tb[t] + pos] = b.slot;
+            lists[tb[t] + tile_slot(tf, t)] = b.slot;
             continue;
         }
         for (int ty = ty0; ty <= ty1; ++ty)
             for (int tx = tx0; tx <= tx1; ++tx) {
                 const int t = ty * F.tiles_x + tx;
                 if (tc[t] == 0u) continue;  // list dropped on arena overflow
-                const uint32_t pos = atomicAdd(&tf[t], 1u);
-                lists[tb[t] + pos] = b.slot;
+                lists[tb[t] + tile_slot(tf, t)] = b.slot;
             }
     }
 }
