@@ -136,3 +136,14 @@ def test_random_scenes(block):
         scene2, assets2, r2, _, _, _ = _scene(seed)   # a fresh scene: rasterize() appends the chunk lights on every call
         fast = render_gpu(r2, scene2, assets2, w, h, ts, planes=False)[0]
         assert np.array_equal(fast, g[0]), f"fuzz seed {seed}: pixels-only variant differs"
+
+
+@pytest.mark.parametrize("seed", [20675, 20522])
+def test_uv_of_triangles_crossing_the_near_plane(seed):
+    """Regression: with fused multiply-adds in the deferred shade's perspective-correct UV sums these two scenes (a huge
+    triangle crossing the near plane under a minified noise texture) had 32 % / 2.5 % of their pixels on another texel
+    although owner and depth were exact.  The sums are the reference's unfused operations now: the full colour bar holds."""
+    scene, assets, r, w, h, ts = _scene(seed)
+    g = render_gpu(r, scene, assets, w, h, ts)
+    o = render_oracle(r, scene, assets, w, h, ts)
+    compare(g, o, f"fuzz seed {seed}", pixel_frac=0.999)
