@@ -1931,6 +1931,7 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
     __shared__ float s_kd[256];                      // srgb_to_linear_fast(c / 255) * (1 - 0.04), rasterizer.rs:20-25
     __shared__ int s_union[8];                       // pixel bbox of the frame's cached large triangles [0..3] and of its 2D records [4..7]
     __shared__ int s_can_be_empty;                   // per frame: some tile may be untouched (see the empty-tile path below)
+    __shared__ struct { const DFrame* F; const DLight* lights_g; const TriVis* vis; const TriShade* shade; const DFrameBatch* fbs; const uint32_t* large; uint32_t n_large; } s_p;
     __shared__ uint32_t s_nbig;                      // small-triangle pass: length of the compacted list of the other records
 
     uint32_t tid = threadIdx.x;
@@ -1974,32 +1975,33 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
         __syncthreads();
         if (s_work[0] < 0) break;
         const uint32_t f = (uint32_t)s_work[0], tile = (uint32_t)s_work[3];
-        const DFrame& F = Wk.frames[f];
-        const DCounters& C = Wk.counters[f];
-        const DLight* lights_g = Wk.lights + (size_t)f * Wk.lights_stride;
-        const TriVis* vis = Wk.vis + (size_t)f * Wk.slot_stride;
-        const TriShade* shade = Wk.shade + (size_t)f * Wk.slot_stride;
-        const DFrameBatch* fbs = Wk.fb + (size_t)f * Wk.fb_stride;
-        const uint32_t n_large = (GENERAL || !F.d3_active) ? 0u : min(C.n_large, Wk.large_stride);
-        const uint32_t* large = Wk.large + (size_t)f * Wk.large_stride;
-
+        // per-frame base pointers, staged below when the frame changes (f is uniform, but the compiler cannot know)
         if (f != cached_frame) {  // uniform for the CTA: stage what every tile of this frame reads
-            if (tid < 16) s_k.s2w[tid] = F.s2w[tid];
-            else if (tid < 19) s_k.cam[tid - 16] = F.cam[tid - 16];
-            else if (tid == 19) s_k.has_ambient = F.has_ambient;
-            else if (tid < 23) s_k.ambient[tid - 20] = F.ambient[tid - 20];
+            const DFrame& Fg = Wk.frames[f];
+            const DLight* lights_gg = Wk.lights + (size_t)f * Wk.lights_stride;
+            const TriVis* visg = Wk.vis + (size_t)f * Wk.slot_stride;
+            const uint32_t n_largeg = (GENERAL || !Fg.d3_active) ? 0u : min(Wk.counters[f].n_large, Wk.large_stride);
+            const uint32_t* largeg = Wk.large + (size_t)f * Wk.large_stride;
+            if (tid == 32) {   // the frame's base pointers: one shared-memory load per tile instead of the 64-bit index arithmetic
+                s_p.F = &Fg; s_p.lights_g = lights_gg; s_p.vis = visg; s_p.shade = Wk.shade + (size_t)f * Wk.slot_stride;
+                s_p.fbs = Wk.fb + (size_t)f * Wk.fb_stride; s_p.large = largeg; s_p.n_large = n_largeg;
+            }
+            if (tid < 16) s_k.s2w[tid] = Fg.s2w[tid];
+            else if (tid < 19) s_k.cam[tid - 16] = Fg.cam[tid - 16];
+            else if (tid == 19) s_k.has_ambient = Fg.has_ambient;
+            else if (tid < 23) s_k.ambient[tid - 20] = Fg.ambient[tid - 20];
             else if (tid == 23) s_k.n_lights = S.n_lights;
-            else if (tid < 27) s_k.sun_l[tid - 24] = F.sun_l[tid - 24];
-            else if (tid == 27) s_k.sun_radiance = F.sun_radiance;
+            else if (tid < 27) s_k.sun_l[tid - 24] = Fg.sun_l[tid - 24];
+            else if (tid == 27) s_k.sun_radiance = Fg.sun_radiance;
             for (uint32_t i = tid; i < min(S.n_lights, (uint32_t)RX_SMEM_LIGHTS) * (uint32_t)(sizeof(DLight) / 4); i += RX_TILE_THREADS)
-                reinterpret_cast<uint32_t*>(s_lights)[i] = __ldg(reinterpret_cast<const uint32_t*>(lights_g) + i);
-            if (!GENERAL) {  // large-triangle records of the frame
-                n_cached = min(n_large, (uint32_t)RX_LARGE_CACHE);
-                const float4* g = reinterpret_cast<const float4*>(vis);
+                reinterpret_cast<uint32_t*>(s_lights)[i] = __ldg(reinterpret_cast<const uint32_t*>(lights_gg) + i);
+            if (!GENERAL) {  // largeg-triangle records of the frame
+                n_cached = min(n_largeg, (uint32_t)RX_LARGE_CACHE);
+                const float4* g = reinterpret_cast<const float4*>(visg);
                 float4* sq = reinterpret_cast<float4*>(s_large);
                 for (uint32_t i = tid; i < n_cached * 6u; i += RX_TILE_THREADS) {
                     const uint32_t r = i / 6u, q = i - r * 6u;
-                    const uint32_t slot = __ldg(large + r);
+                    const uint32_t slot = __ldg(largeg + r);
                     if (q == 0) s_large_slot[r] = slot;
                     sq[i] = __ldg(g + (size_t)slot * 6u + q);
                 }
@@ -2007,10 +2009,10 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
             cached_frame = f;
             __syncthreads();
             if (!GENERAL && warp < 2u) {
-                // what an empty tile must not touch: the union of the cached large triangles' pixel boxes (warp 0) and
+                // what an empty tile must not touch: the union of the cached largeg triangles' pixel boxes (warp 0) and
                 // of the (at most 32, in this mode) 2D records' (warp 1)
                 int x0 = 0x7FFFFFFF, y0 = 0x7FFFFFFF, x1 = 0, y1 = 0;
-                const uint32_t n = warp == 0u ? n_cached : ((F.d2_active && S.n_rec2d) ? S.n_rec2d : 0u);
+                const uint32_t n = warp == 0u ? n_cached : ((Fg.d2_active && S.n_rec2d) ? S.n_rec2d : 0u);
                 const Tri2D* recs2 = Wk.tri2d + (size_t)f * Wk.tri2d_stride;
                 for (uint32_t i = lane; i < n; i += 32) {
                     const uint32_t bx = warp == 0u ? s_large[i].bbx : recs2[i].bbx, by = warp == 0u ? s_large[i].bby : recs2[i].bby;
@@ -2028,14 +2030,21 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
             }
             __syncthreads();
             if (tid == 0) {
-                // no tile of this frame can be empty when the large triangles' boxes already cover the band (a sky box,
+                // no tile of this frame can be empty when the largeg triangles' boxes already cover the band (a sky box,
                 // the walls of a room): then the per-tile test is skipped altogether
-                bool can = F.d3_active && !(F.has_sky | F.has_brush);
-                if (!GENERAL) can = can && n_large == n_cached && !(s_union[0] <= F.band_x0 && s_union[1] <= F.band_y0 && s_union[2] >= F.band_x1 && s_union[3] >= F.band_y1);
+                bool can = Fg.d3_active && !(Fg.has_sky | Fg.has_brush);
+                if (!GENERAL) can = can && n_largeg == n_cached && !(s_union[0] <= Fg.band_x0 && s_union[1] <= Fg.band_y0 && s_union[2] >= Fg.band_x1 && s_union[3] >= Fg.band_y1);
                 s_can_be_empty = can ? 1 : 0;
             }
             __syncthreads();
         }
+        const DFrame& F = *s_p.F;
+        const DLight* lights_g = s_p.lights_g;
+        const TriVis* vis = s_p.vis;
+        const TriShade* shade = s_p.shade;
+        const DFrameBatch* fbs = s_p.fbs;
+        const uint32_t n_large = s_p.n_large;
+        const uint32_t* large = s_p.large;
         const DLight* lights = S.n_lights <= (uint32_t)RX_SMEM_LIGHTS ? s_lights : lights_g;
 
         const uint32_t smode = SAMPLE == 2 ? F.sample_mode : (uint32_t)SAMPLE;
