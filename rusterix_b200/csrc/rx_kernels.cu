@@ -1931,7 +1931,7 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
     __shared__ float s_kd[256];                      // srgb_to_linear_fast(c / 255) * (1 - 0.04), rasterizer.rs:20-25
     __shared__ int s_union[8];                       // pixel bbox of the frame's cached large triangles [0..3] and of its 2D records [4..7]
     __shared__ int s_can_be_empty;                   // per frame: some tile may be untouched (see the empty-tile path below)
-    __shared__ struct { const DFrame* F; const DLight* lights_g; const TriVis* vis; const TriShade* shade; const DFrameBatch* fbs; const uint32_t* large; uint32_t n_large; } s_p;
+    __shared__ struct { const DFrame* F; const DLight* lights_g; const TriVis* vis; const TriShade* shade; const DFrameBatch* fbs; const uint32_t* large; const uint32_t* tile_count; const uint32_t* tile_base; const uint32_t* lists; uint32_t n_large; } s_p;
     __shared__ uint32_t s_nbig;                      // small-triangle pass: length of the compacted list of the other records
 
     uint32_t tid = threadIdx.x;
@@ -1985,6 +1985,8 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
             if (tid == 32) {   // the frame's base pointers: one shared-memory load per tile instead of the 64-bit index arithmetic
                 s_p.F = &Fg; s_p.lights_g = lights_gg; s_p.vis = visg; s_p.shade = Wk.shade + (size_t)f * Wk.slot_stride;
                 s_p.fbs = Wk.fb + (size_t)f * Wk.fb_stride; s_p.large = largeg; s_p.n_large = n_largeg;
+                s_p.tile_count = Wk.tile_count + (size_t)f * Wk.tile_stride; s_p.tile_base = Wk.tile_base + (size_t)f * Wk.tile_stride;
+                s_p.lists = Wk.lists + (size_t)f * Wk.list_stride;
             }
             if (tid < 16) s_k.s2w[tid] = Fg.s2w[tid];
             else if (tid < 19) s_k.cam[tid - 16] = Fg.cam[tid - 16];
@@ -2056,7 +2058,7 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
             // Empty tile: no binned triangle, no large triangle and no 2D record can touch it -> every pixel is the miss
             // colour vec4_to_pixel((0,0,0,1)) (rasterizer.rs:409-417).  Sparse scenes (an object in front of nothing) are
             // mostly such tiles, and the full tile prologue + resolve costs them ~600 warp-instructions per warp.
-            bool empty = Wk.tile_count[(size_t)f * Wk.tile_stride + tile] == 0u;
+            bool empty = s_p.tile_count[tile] == 0u;
             if (GENERAL) {
                 empty = empty && !(F.d2_active && S.n_rec2d != 0u && Wk.tile_count2[(size_t)f * Wk.tile_stride + tile] != 0u);
             } else {
@@ -2113,8 +2115,8 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                 if (tid < n_cached && rect_overlaps(s_large[tid], tx0, ty0, tx1, ty1) != 0u) s_sel[atomicAdd(&s_nsel, 1u)] = (uint16_t)tid;
                 __syncthreads();
             }
-            const uint32_t n_list = Wk.tile_count[(size_t)f * Wk.tile_stride + tile];
-            const uint32_t* list = Wk.lists + (size_t)f * Wk.list_stride + Wk.tile_base[(size_t)f * Wk.tile_stride + tile];
+            const uint32_t n_list = s_p.tile_count[tile];
+            const uint32_t* list = s_p.lists + s_p.tile_base[tile];
             // long list (uniform over the CTA): a thread per record for the small triangles, the others compacted (see
             // small_triangle_pass).  s_key / s_big alias s_state, which is only written by the resolve below.
             unsigned long long* s_key = reinterpret_cast<unsigned long long*>(s_state);
