@@ -2040,11 +2040,12 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
             }
             __syncthreads();
         }
-        const DFrame& F = *s_p.F;
-        const DLight* lights_g = s_p.lights_g;
-        const TriVis* vis = s_p.vis;
-        const TriShade* shade = s_p.shade;
-        const DFrameBatch* fbs = s_p.fbs;
+        // (the VM variant, far over its register budget already, is faster recomputing them: 3.50 vs 3.64 ms on the batch-shader scene)
+        const DFrame& F = VM ? Wk.frames[f] : *s_p.F;
+        const DLight* lights_g = VM ? Wk.lights + (size_t)f * Wk.lights_stride : s_p.lights_g;
+        const TriVis* vis = VM ? Wk.vis + (size_t)f * Wk.slot_stride : s_p.vis;
+        const TriShade* shade = VM ? Wk.shade + (size_t)f * Wk.slot_stride : s_p.shade;
+        const DFrameBatch* fbs = VM ? Wk.fb + (size_t)f * Wk.fb_stride : s_p.fbs;
         const uint32_t n_large = s_p.n_large;
         const uint32_t* large = s_p.large;
         const DLight* lights = S.n_lights <= (uint32_t)RX_SMEM_LIGHTS ? s_lights : lights_g;
@@ -2115,8 +2116,8 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                 if (tid < n_cached && rect_overlaps(s_large[tid], tx0, ty0, tx1, ty1) != 0u) s_sel[atomicAdd(&s_nsel, 1u)] = (uint16_t)tid;
                 __syncthreads();
             }
-            const uint32_t n_list = s_p.tile_count[tile];
-            const uint32_t* list = s_p.lists + s_p.tile_base[tile];
+            const uint32_t n_list = VM ? Wk.tile_count[(size_t)f * Wk.tile_stride + tile] : s_p.tile_count[tile];
+            const uint32_t* list = VM ? Wk.lists + (size_t)f * Wk.list_stride + Wk.tile_base[(size_t)f * Wk.tile_stride + tile] : s_p.lists + s_p.tile_base[tile];
             // long list (uniform over the CTA): a thread per record for the small triangles, the others compacted (see
             // small_triangle_pass).  s_key / s_big alias s_state, which is only written by the resolve below.
             unsigned long long* s_key = reinterpret_cast<unsigned long long*>(s_state);
