@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RXC_ABI_VERSION 4u
+#define RXC_ABI_VERSION 5u
 
 typedef struct rxc_ctx rxc_ctx;
 
@@ -398,6 +398,54 @@ int32_t rxc_selftest_div(rxc_ctx* ctx, uint64_t seed, uint64_t n_pairs, uint64_t
  * (uv, color, normal, roughness, metallic, emissive, opacity, bump).  Roughness starts at 0.5, the rest of
  * Execution at zero (execution.rs:58-77).  faults (optional) counts records that hit a device limit. */
 int32_t rxc_vm_execute(rxc_ctx* ctx, uint32_t program, uint32_t n, const float* in, float* out, uint32_t* faults);
+
+/* ---- multi-GPU delivery to rank 0 ------------------------------------------------------------------
+ * The path shards by frame (camera sweeps) and by screen band (one large frame) with no exchange step; what is left
+ * is getting the finished pixels into ONE buffer.  In the reference that is the serial compose of the tile buffers
+ * into `pixels` (src/rasterizer.rs:560-579); here it is one process and one context per GPU, and
+ *   - rank 0 owns the delivery buffer (rxc_mgpu_target), every other rank maps it (cudaIpc: NVLink / NVSwitch peer
+ *     access) and rxc_mgpu_rasterize makes the raster kernel's tile write-back store straight into the mapping --
+ *     no gather follows the render;
+ *   - rxc_mgpu_deliver marks the step complete: ranks > 0 raise a flag in rank 0's memory behind their kernels,
+ *     rank 0's stream waits for all flags; rxc_mgpu_release is the reverse hand-shake (rank 0 is done with the
+ *     buffer, the other ranks' streams wait for that before they overwrite it);
+ *   - where a peer mapping cannot be had, ranks render into local staging and the regions move as ONE ncclGroup of
+ *     send/recv pairs on a second stream (RXC_MGPU_NCCL).
+ * NCCL (libnccl.so.2, resolved at run time) carries the set-up and the fallback; the host only has to get the 128
+ * bytes of rxc_mgpu_unique_id from rank 0 to the other ranks (MPI, a socket, a file, torch.distributed ...).
+ * rxc_mgpu_init, rxc_mgpu_target and rxc_mgpu_shutdown are collective: every rank calls them, in the same order
+ * (rxc_destroy alone tears the rank's state down without waiting for anyone). */
+#define RXC_MGPU_ID_BYTES 128
+enum { RXC_MGPU_LOCAL = 0,  /* this rank writes the delivery buffer directly (rank 0; world == 1)        */
+       RXC_MGPU_PEER = 1,   /* this rank writes rank 0's buffer through its peer mapping                 */
+       RXC_MGPU_NCCL = 2 }; /* no peer mapping: local staging + grouped ncclSend/ncclRecv                */
+/* What one rank contributes to a step: `rows` rows of `row_bytes` bytes, `pitch_bytes` apart (0 = contiguous), the
+ * first at `offset` of the delivery buffer.  Only read in RXC_MGPU_NCCL mode (every rank passes the same list). */
+typedef struct rxc_mgpu_region {
+    uint32_t rank;
+    uint32_t rows;
+    uint64_t offset;
+    uint64_t row_bytes;
+    uint64_t pitch_bytes;
+} rxc_mgpu_region;
+int32_t rxc_mgpu_unique_id(uint8_t* id /* RXC_MGPU_ID_BYTES, an ncclUniqueId */);
+int32_t rxc_mgpu_init(rxc_ctx* ctx, const uint8_t* id, uint32_t rank, uint32_t world);
+int32_t rxc_mgpu_shutdown(rxc_ctx* ctx);
+/* (Re)allocates the delivery buffer of `bytes` bytes on rank 0 and maps it on the other ranks.  rank0_ptr (optional)
+ * receives its device address on rank 0 (NULL elsewhere), mode (optional) this rank's RXC_MGPU_* mode. */
+int32_t rxc_mgpu_target(rxc_ctx* ctx, uint64_t bytes, void** rank0_ptr, uint32_t* mode);
+/* rxc_rasterize_batch_async into the delivery buffer: frame i at offset_bytes + i * frame_stride_bytes.  pitch_bytes
+ * = 0: rows of the rendered rectangle are contiguous; else the distance between rows, so that a band (rxc_frame.band_*)
+ * lands in place inside a full frame (offset_bytes = (band_y0 * width + band_x0) * 4, pitch_bytes = width * 4). */
+int32_t rxc_mgpu_rasterize(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames, uint64_t offset_bytes,
+                           uint64_t frame_stride_bytes, uint64_t pitch_bytes);
+/* Every rank, once per step, after its rxc_mgpu_rasterize calls.  When rank 0's stream has passed it, the step's
+ * pixels of every rank are in the delivery buffer.  Asynchronous (stream-ordered) on every rank. */
+int32_t rxc_mgpu_deliver(rxc_ctx* ctx, const rxc_mgpu_region* regions, uint32_t n_regions);
+/* Every rank, once per step (or once per ring slot): rank 0 is done reading, the others may overwrite. */
+int32_t rxc_mgpu_release(rxc_ctx* ctx);
+/* mode of this rank, deliveries issued so far, and (rank 0, synchronizes) how many waits timed out on a dead peer */
+int32_t rxc_mgpu_status(rxc_ctx* ctx, uint32_t* mode, uint32_t* deliveries, uint32_t* timeouts);
 
 int32_t rxc_set_profiling(rxc_ctx* ctx, int32_t enabled);
 int32_t rxc_get_stats(rxc_ctx* ctx, rxc_stats* out);

@@ -1117,8 +1117,19 @@ struct Raster {
                 break;
             }
             case RXC_SRC_TERRAIN:
-                if (batch.chunk >= 0) sample_terrain_texture(batch.chunk, {world.x, world.z}, texel);
-                else { texel[0] = 255; texel[1] = 0; texel[2] = 0; texel[3] = 255; }
+                if (batch.chunk >= 0) {
+                    sample_terrain_texture(batch.chunk, {world.x, world.z}, texel);
+                    if (f->has_brush_preview) {   // :1193-1212 (and :1601-1620): the texel goes towards white inside the brush
+                        float dist = magnitude(world - V3{f->brush_position[0], f->brush_position[1], f->brush_position[2]});
+                        if (dist < f->brush_radius) {
+                            float normalized_d = dist / f->brush_radius;
+                            float falloff = rclamp(f->brush_falloff, 0.001f, 1.0f);
+                            float fade = rclamp((1.0f - normalized_d) / falloff, 0.0f, 1.0f);
+                            float blend = 0.2f + 0.6f * fade;
+                            for (int i = 0; i < 3; ++i) texel[i] = as_u8(rmin((float)texel[i] * (1.0f - blend) + 255.0f * blend, 255.0f));
+                        }
+                    }
+                } else { texel[0] = 255; texel[1] = 0; texel[2] = 0; texel[3] = 255; }
                 break;
             default: texel[0] = texel[1] = texel[2] = 0; texel[3] = 255; break;
         }

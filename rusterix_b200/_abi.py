@@ -2,7 +2,7 @@
 tests/test_abi.py checks sizes/offsets against a C probe compiled from the header."""
 import ctypes as C
 
-RXC_ABI_VERSION = 4
+RXC_ABI_VERSION = 5
 
 RXC_OK = 0
 RXC_ERR_INVALID = -1
@@ -223,6 +223,14 @@ class rxc_stats(C.Structure):
     ]
 
 
+RXC_MGPU_ID_BYTES = 128
+RXC_MGPU_LOCAL, RXC_MGPU_PEER, RXC_MGPU_NCCL = 0, 1, 2
+
+
+class rxc_mgpu_region(C.Structure):
+    _fields_ = [("rank", C.c_uint32), ("rows", C.c_uint32), ("offset", C.c_uint64), ("row_bytes", C.c_uint64), ("pitch_bytes", C.c_uint64)]
+
+
 # every symbol include/rxcuda.h declares: (name, restype, argtypes)
 EXPORTS = [
     ("rxc_abi_version", C.c_uint32, []),
@@ -244,6 +252,14 @@ EXPORTS = [
     ("rxc_owner_base", C.c_int32, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]),
     ("rxc_selftest_div", C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     ("rxc_vm_execute", C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]),
+    ("rxc_mgpu_unique_id", C.c_int32, [C.POINTER(C.c_uint8)]),
+    ("rxc_mgpu_init", C.c_int32, [C.c_void_p, C.POINTER(C.c_uint8), C.c_uint32, C.c_uint32]),
+    ("rxc_mgpu_shutdown", C.c_int32, [C.c_void_p]),
+    ("rxc_mgpu_target", C.c_int32, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]),
+    ("rxc_mgpu_rasterize", C.c_int32, [C.c_void_p, C.POINTER(rxc_frame), C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64]),
+    ("rxc_mgpu_deliver", C.c_int32, [C.c_void_p, C.POINTER(rxc_mgpu_region), C.c_uint32]),
+    ("rxc_mgpu_release", C.c_int32, [C.c_void_p]),
+    ("rxc_mgpu_status", C.c_int32, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     ("rxc_set_profiling", C.c_int32, [C.c_void_p, C.c_int32]),
     ("rxc_get_stats", C.c_int32, [C.c_void_p, C.POINTER(rxc_stats)]),
     ("rxc_reset_stats", C.c_int32, [C.c_void_p]),

@@ -38,19 +38,42 @@ def cuda_sources():
 
 
 def build_cuda(force=False, verbose=False):
+    """One object per .cu (compiled in parallel, only when the source or a header is newer), then one link."""
+    from concurrent.futures import ThreadPoolExecutor
+
     srcs = cuda_sources()
-    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    deps.append(os.path.join(ROOT, "include", "rxcuda.h"))
-    if not force and not _newer(LIB, deps):
-        return LIB
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(ROOT, "include", "rxcuda.h"))
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     extra = os.environ.get("RX_NVCC_EXTRA", "").split()  # experiments only, e.g. -DRX_RASTER_MIN_BLOCKS=4
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-I", os.path.join(ROOT, "include"), "-o", LIB] + srcs
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    objdir = os.path.join(CSRC, "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    tag = os.path.join(objdir, "flags.txt")   # objects built with other flags are stale
+    flags_now = " ".join(NVCC_FLAGS + extra)
+    if not os.path.exists(tag) or open(tag).read() != flags_now:
+        force = True
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        if not force and not _newer(obj, [src] + headers):
+            return obj, ""
+        cmd = [nvcc] + compile_flags + extra + (["-Xptxas", "-v"] if verbose else []) + ["-I", os.path.join(ROOT, "include"), "-c", "-o", obj, src]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        return obj, r.stdout + r.stderr
+
+    with ThreadPoolExecutor(max_workers=max(1, len(srcs))) as ex:
+        results = list(ex.map(compile_one, srcs))
+    objs = [o for o, _ in results]
     if verbose:
-        print(r.stdout + r.stderr)
+        print("".join(t for _, t in results))
+    if force or _newer(LIB, objs):
+        r = subprocess.run([nvcc] + NVCC_FLAGS + ["-o", LIB] + objs + ["-ldl"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    open(tag, "w").write(flags_now)
     return LIB
 
 

@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 
+#include "rx_internal.h"
 #include "rx_kernels.cuh"
 
 namespace {
@@ -94,7 +95,8 @@ struct rxc_ctx {
     bool profiling = false;
     std::vector<PendingEvent> pending;
     std::vector<cudaEvent_t> free_events;
-    bool async_overflow = false;
+    RxMgpu* mgpu = nullptr;       // rxc_mgpu_* state (rx_mgpu.cu)
+    uint32_t async_pending = 0;   // frames of the last asynchronous group whose counters (ctx->h_counters) nobody has looked at yet
 };
 
 namespace {
@@ -544,7 +546,7 @@ int32_t validate_sources(rxc_ctx* ctx) {
 // enqueued, so that the caller can start draining it while the next slice renders.
 template <class AfterSlice>
 int32_t launch_group(rxc_ctx* ctx, const DFrame* h_frames, DCounters* h_counters, uint32_t n, uint8_t* d_pixels, uint64_t stride,
-                     uint32_t* d_owner, float* d_depth, uint32_t slices, AfterSlice after_slice) {
+                     uint32_t pitch_px, uint32_t* d_owner, float* d_depth, uint32_t slices, AfterSlice after_slice) {
     SceneDev& S = ctx->S;
     const uint32_t tiles_per_frame = (uint32_t)h_frames[0].tiles_x * (uint32_t)h_frames[0].tiles_y;
     CK(cudaMemcpyAsync(ctx->W.frames, h_frames, n * sizeof(DFrame), cudaMemcpyHostToDevice, ctx->stream));
@@ -580,7 +582,8 @@ int32_t launch_group(rxc_ctx* ctx, const DFrame* h_frames, DCounters* h_counters
     }
     RasterOut out;
     out.pixels = d_pixels; out.frame_stride = stride; out.owner = d_owner; out.depth = d_depth;
-    out.vec_store = (((uintptr_t)d_pixels & 15) == 0 && (stride & 15) == 0 && (((h_frames[0].band_x1 - h_frames[0].band_x0) * 4) & 15) == 0) ? 1u : 0u;
+    out.pitch = pitch_px ? pitch_px : (uint32_t)(h_frames[0].band_x1 - h_frames[0].band_x0);
+    out.vec_store = (((uintptr_t)d_pixels & 15) == 0 && (stride & 15) == 0 && ((out.pitch * 4) & 15) == 0) ? 1u : 0u;
     int sample_mode = (int)h_frames[0].sample_mode;
     for (uint32_t i = 1; i < n; ++i) if ((int)h_frames[i].sample_mode != sample_mode) sample_mode = 2;
     const uint32_t tiles_x = (uint32_t)h_frames[0].tiles_x, tiles_y = (uint32_t)h_frames[0].tiles_y;
@@ -628,8 +631,21 @@ int32_t check_group(rxc_ctx* ctx, const DCounters* h_counters, uint32_t n, bool*
     return RXC_OK;
 }
 
+// The counters of the last asynchronous group, if nobody has looked at them yet (the stream must be synchronized).
+// Reported once: a tile-list overflow there means geometry was dropped from those frames.
+int32_t check_async(rxc_ctx* ctx) {
+    const uint32_t n = ctx->async_pending;
+    ctx->async_pending = 0;
+    if (!n || !ctx->h_counters) return RXC_OK;
+    bool retry = false;
+    const int32_t st = check_group(ctx, ctx->h_counters, n, &retry);
+    if (st != RXC_OK) return st;
+    if (retry) return fail(ctx, RXC_ERR_OOM, "a tile-list arena overflowed during an asynchronous call (its frames are incomplete); the arena has been grown, render them again");
+    return RXC_OK;
+}
+
 int32_t rasterize_impl(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames, uint8_t* pixels, uint64_t stride, uint32_t* owner,
-                       float* depth, bool sync) {
+                       float* depth, bool sync, uint64_t pitch_bytes = 0) {
     if (!ctx) return RXC_ERR_INVALID;
     if (!frames || n_frames == 0 || !pixels) return fail(ctx, RXC_ERR_INVALID, "frames and pixels are required");
     if (!ctx->have_scene) return fail(ctx, RXC_ERR_INVALID, "rxc_set_scene has not been called");
@@ -651,6 +667,9 @@ int32_t rasterize_impl(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames,
     const uint32_t cols = (uint32_t)(probe.band_x1 - probe.band_x0);
     const uint64_t frame_bytes = (uint64_t)cols * rows * 4;
     if (n_frames > 1 && stride < frame_bytes) return fail(ctx, RXC_ERR_INVALID, "frame_stride_bytes smaller than a frame");
+    if (pitch_bytes && ((pitch_bytes & 3) || pitch_bytes < (uint64_t)cols * 4 || pitch_bytes > ((uint64_t)1 << 20)))
+        return fail(ctx, RXC_ERR_INVALID, "row pitch must be a multiple of 4 bytes and at least one row of the rendered rectangle");
+    const uint32_t pitch_px = (uint32_t)(pitch_bytes / 4);   // 0 = tight rows
     const uint32_t tiles_per_frame = (uint32_t)probe.tiles_x * (uint32_t)probe.tiles_y;
 
     // frames are processed in groups sized to a workspace budget
@@ -660,11 +679,13 @@ int32_t rasterize_impl(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames,
     group = std::min(group, 1024u);
 
     const bool dev_px = is_device_pointer(pixels);
+    if (pitch_px && !dev_px) return fail(ctx, RXC_ERR_INVALID, "a row pitch needs a device pixel buffer");
     const bool dev_owner = owner && is_device_pointer(owner);
     const bool dev_depth = depth && is_device_pointer(depth);
-    if (!sync && ctx->async_overflow) { /* reported at the next synchronize */ }
 
     if (ctx->h_frames_cap < group) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if ((st = check_async(ctx)) != RXC_OK) return st;
         if (ctx->h_frames) cudaFreeHost(ctx->h_frames);
         if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
         CK(cudaMallocHost((void**)&ctx->h_frames, group * sizeof(DFrame)));
@@ -686,6 +707,7 @@ int32_t rasterize_impl(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames,
         const uint64_t row_bytes = (uint64_t)cols * 4;
         if (ctx->h_frames_cap < n_frames) {
             CK(cudaStreamSynchronize(ctx->stream));
+            if ((st = check_async(ctx)) != RXC_OK) return st;
             if (ctx->h_frames) cudaFreeHost(ctx->h_frames);
             if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
             ctx->h_frames = nullptr; ctx->h_counters = nullptr; ctx->h_frames_cap = 0;
@@ -702,6 +724,7 @@ int32_t rasterize_impl(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames,
             for (int i = 0; i < 16; ++i) CK(cudaEventCreateWithFlags(&ctx->ev_slice[i], cudaEventDisableTiming));
         }
         CK(cudaStreamSynchronize(ctx->stream));  // the pinned frame block may still feed an earlier asynchronous call
+        if ((st = check_async(ctx)) != RXC_OK) return st;
         for (uint32_t i = 0; i < n_frames; ++i)
             if ((st = fill_frame(ctx, frames[i], &ctx->h_frames[i])) != RXC_OK) return st;
         for (int attempt = 0; attempt < 4; ++attempt) {
@@ -738,7 +761,7 @@ int32_t rasterize_impl(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames,
                 // the counter block alternates with the staging half, and is read back behind the pixels on the copy stream
                 // (a small D2H on the render stream would queue behind the pixel copies on the same DMA engine and stall it)
                 ctx->W.counters = ctx->w_counters.as<DCounters>() + (size_t)half * ctx->ws_frames;
-                st = launch_group(ctx, ctx->h_frames + first, nullptr, n, d_px, frame_bytes, nullptr, nullptr, slices_now, drain);
+                st = launch_group(ctx, ctx->h_frames + first, nullptr, n, d_px, frame_bytes, 0u, nullptr, nullptr, slices_now, drain);
                 DCounters* d_counters = ctx->W.counters;
                 ctx->W.counters = ctx->w_counters.as<DCounters>();
                 if (st != RXC_OK) return st;
@@ -760,8 +783,11 @@ int32_t rasterize_impl(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames,
         const uint32_t n = std::min(group, n_frames - first);
         for (int attempt = 0; attempt < 4; ++attempt) {
             if ((st = ensure_workspace(ctx, n, tiles_per_frame)) != RXC_OK) return st;
-            // the pinned frame block is reused per group: the previous group's copy must have been consumed
-            if (first != 0 || attempt != 0 || !sync) CK(cudaStreamSynchronize(ctx->stream));
+            // the pinned frame and counter blocks are reused per group and per call: whatever was enqueued before (an
+            // earlier asynchronous call included) must have consumed / filled them, and an asynchronous group's
+            // counters are looked at before the next group overwrites them
+            CK(cudaStreamSynchronize(ctx->stream));
+            if ((st = check_async(ctx)) != RXC_OK) return st;
             for (uint32_t i = 0; i < n; ++i)
                 if ((st = fill_frame(ctx, frames[first + i], &ctx->h_frames[i])) != RXC_OK) return st;
             uint8_t* d_px = pixels + (uint64_t)first * stride;
@@ -773,8 +799,8 @@ int32_t rasterize_impl(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames,
             uint32_t* d_ow = owner; float* d_dp = depth;
             if (owner && !dev_owner) { if ((st = reserve(ctx, ctx->d_out_owner, frame_bytes)) != RXC_OK) return st; d_ow = ctx->d_out_owner.as<uint32_t>(); }
             if (depth && !dev_depth) { if ((st = reserve(ctx, ctx->d_out_depth, frame_bytes)) != RXC_OK) return st; d_dp = ctx->d_out_depth.as<float>(); }
-            if ((st = launch_group(ctx, ctx->h_frames, ctx->h_counters, n, d_px, d_stride, d_ow, d_dp, 1u, [](uint32_t, uint32_t) -> int32_t { return RXC_OK; })) != RXC_OK) return st;
-            if (!sync && dev_px && ctx->lists_sized) break;  // truly asynchronous: counters are checked at the next synchronize
+            if ((st = launch_group(ctx, ctx->h_frames, ctx->h_counters, n, d_px, d_stride, pitch_px, d_ow, d_dp, 1u, [](uint32_t, uint32_t) -> int32_t { return RXC_OK; })) != RXC_OK) return st;
+            if (!sync && dev_px && ctx->lists_sized) { ctx->async_pending = n; break; }  // truly asynchronous: the counters are checked before they are reused, or at the next synchronize
             CK(cudaStreamSynchronize(ctx->stream));
             if (ctx->profiling) drain_events(ctx);
             bool retry = false;
@@ -819,6 +845,18 @@ int32_t guarded(rxc_ctx* ctx, F&& f) noexcept {
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
+// internal interface (rx_internal.h)
+// ---------------------------------------------------------------------------------------------
+cudaStream_t rxi_stream(rxc_ctx* ctx) { return ctx->stream; }
+int rxi_device(rxc_ctx* ctx) { return ctx->device; }
+int32_t rxi_fail(rxc_ctx* ctx, int32_t code, const std::string& msg) { return fail(ctx, code, msg); }
+RxMgpu** rxi_mgpu_slot(rxc_ctx* ctx) { return &ctx->mgpu; }
+void rxi_count_launch(rxc_ctx* ctx, uint32_t n) { ctx->stats.kernel_launches += n; }
+int32_t rxi_rasterize_device(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames, uint8_t* d_pixels, uint64_t stride, uint64_t pitch_bytes) {
+    return rasterize_impl(ctx, frames, n_frames, d_pixels, stride, nullptr, nullptr, false, pitch_bytes);
+}
+
+// ---------------------------------------------------------------------------------------------
 // exported C ABI
 // ---------------------------------------------------------------------------------------------
 extern "C" {
@@ -860,6 +898,7 @@ void rxc_destroy(rxc_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    rxi_mgpu_destroy(ctx);
     DevBuf* bufs[] = {&ctx->d_arena, &ctx->d_tex, &ctx->d_tiles, &ctx->d_pos, &ctx->d_uv, &ctx->d_nrm, &ctx->d_idx, &ctx->d_b3,
                       &ctx->d_chunks, &ctx->d_orphans, &ctx->d_pos2, &ctx->d_uv2, &ctx->d_idx2, &ctx->d_b2, &ctx->d_lights,
                       &ctx->w_frames, &ctx->w_fb, &ctx->w_fb2, &ctx->w_lights, &ctx->w_counters, &ctx->w_vis, &ctx->w_shade,
@@ -1174,13 +1213,7 @@ int32_t rxc_synchronize(rxc_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->profiling) drain_events(ctx);
-    if (ctx->h_counters && ctx->ws_frames) {
-        bool retry = false;
-        int32_t st = check_group(ctx, ctx->h_counters, 1, &retry);
-        if (st != RXC_OK) return st;
-        if (retry) return fail(ctx, RXC_ERR_OOM, "tile-list arena overflowed during an asynchronous frame; it has been grown, render the frame again");
-    }
-    return RXC_OK;
+    return check_async(ctx);
     });
 }
 

@@ -1072,6 +1072,10 @@ struct __align__(16) ShadeConst {
     uint32_t n_lights;
     float sun_l[3];          // unit vector towards the sun
     float sun_radiance;      // 0 = no sun
+    float brush[4];          // brush preview: position, radius (rasterizer.rs:13-17)
+    float brush_falloff;
+    uint32_t has_brush;
+    uint32_t pad[2];
 };
 #define RX_SMEM_LIGHTS 16   // lights of the frame staged in shared memory (more: read from global memory)
 
@@ -1097,6 +1101,23 @@ __device__ __forceinline__ uint32_t terrain_sample(const uint8_t* __restrict__ a
     const uint32_t py = rx_as_u32(rx_clamp(floorf(pixel_y), 0.0f, (float)H - 1.0f));
     const uint32_t x = min(px, (uint32_t)(W - 1)), y = min(py, (uint32_t)(H - 1));
     return __ldg(reinterpret_cast<const uint32_t*>(arena) + tex_word + y * (uint32_t)W + x);
+}
+
+// Brush preview on a terrain texel (rasterizer.rs:1193-1212 in d3_rasterize, :1601-1620 in d3_rasterize_opacity): inside
+// the brush radius the RGB channels go 20..80 % of the way to white, `as u8` truncation.  Alpha is untouched, so the
+// alpha test (ownership) never sees it.  bp = brush position xyz, radius.
+__device__ __forceinline__ uint32_t brush_terrain(uint32_t texel, f3 world, const float* bp, float brush_falloff) {
+    const f3 dv = {world.x - bp[0], world.y - bp[1], world.z - bp[2]};
+    const float dist = sqrtf(rx_dot3(dv, dv));
+    if (!(dist < bp[3])) return texel;
+    const float nd = dist / bp[3];
+    const float fade = rx_clamp((1.0f - nd) / rx_clamp(brush_falloff, 0.001f, 1.0f), 0.0f, 1.0f);
+    const float blend = 0.2f + 0.6f * fade;
+    uint32_t out = texel & 0xFF000000u;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        out |= rx_as_u8(fminf((float)((texel >> (8 * i)) & 0xFFu) * (1.0f - blend) + 255.0f * blend, 255.0f)) << (8 * i);
+    return out;
 }
 
 // first sector containing the point (chunk.rs:154-161, mini.rs:58-65, bbox.rs:35-40); chunk < 0 = the mapmini
@@ -1235,7 +1256,10 @@ __device__ __forceinline__ uint32_t shade_owner(const SceneDev& S, const ShadeCo
     const f3 world = {hx * ihw, hy * ihw, hz * ihw};
     const f3 view_dir = fnormalize3({kc.x - world.x, kc.y - world.y, kc.z - world.z});
 
-    if (flags & RX_SD_TERRAIN) texel = terrain_sample(S.arena, d0.x, d0.y, S.chunk_info[__float_as_int(d1.w)], world.x, world.z);
+    if (flags & RX_SD_TERRAIN) {
+        texel = terrain_sample(S.arena, d0.x, d0.y, S.chunk_info[__float_as_int(d1.w)], world.x, world.z);
+        if (K.has_brush) texel = brush_terrain(texel, world, K.brush, K.brush_falloff);
+    }
 
     f3 normal = {0.0f, 0.0f, 0.0f};
     if (flags & RX_SD_NORMALS) {  // rasterizer.rs:1083-1099
@@ -1373,7 +1397,10 @@ __device__ __noinline__ bool vm_fragment_3d(const SceneDev& S, const DFrame& F, 
     }
     uint32_t texel = FB.sd_pixel;
     if (FB.sd_flags & RX_SD_TEXTURED) texel = sample_desc(S.arena, FB.sd_tex_word, FB.sd_wh, FB.sd_flags, u, v, sample_mode);
-    else if (FB.sd_flags & RX_SD_TERRAIN) texel = terrain_sample(S.arena, FB.sd_tex_word, FB.sd_wh, S.chunk_info[FB.sd_chunk], world.x, world.z);
+    else if (FB.sd_flags & RX_SD_TERRAIN) {
+        texel = terrain_sample(S.arena, FB.sd_tex_word, FB.sd_wh, S.chunk_info[FB.sd_chunk], world.x, world.z);
+        if (F.has_brush) { const float bp[4] = {F.brush_pos[0], F.brush_pos[1], F.brush_pos[2], F.brush_radius}; texel = brush_terrain(texel, world, bp, F.brush_falloff); }
+    }
     const float inv255 = 1.0f / 255.0f;  // pixel_to_vec4, lib.rs:55-62
     vm_io_reset(*io);
     io->color = {srgb_to_linear_exact((float)(texel & 0xFFu) * inv255), srgb_to_linear_exact((float)((texel >> 8) & 0xFFu) * inv255),
@@ -1466,6 +1493,11 @@ __device__ __forceinline__ uint32_t shade_opacity(const SceneDev& S, const DFram
         const float hz = __fmaf_rn(F.s2w[10], z, __fmaf_rn(F.s2w[9], fpy, __fmaf_rn(F.s2w[8], fpx, F.s2w[11])));
         const float hw = __fmaf_rn(F.s2w[14], z, __fmaf_rn(F.s2w[13], fpy, __fmaf_rn(F.s2w[12], fpx, F.s2w[15])));
         texel = terrain_sample(S.arena, FB.sd_tex_word, FB.sd_wh, S.chunk_info[FB.sd_chunk], hx / hw, hz / hw);
+        if (F.has_brush) {
+            const float hy = __fmaf_rn(F.s2w[6], z, __fmaf_rn(F.s2w[5], fpy, __fmaf_rn(F.s2w[4], fpx, F.s2w[7])));
+            const float bp[4] = {F.brush_pos[0], F.brush_pos[1], F.brush_pos[2], F.brush_radius};
+            texel = brush_terrain(texel, {hx / hw, hy / hw, hz / hw}, bp, F.brush_falloff);
+        }
     }
     auto rt = [](uint32_t c) {  // linear_to_srgb_fast(srgb_to_linear_fast(c / 255)), rasterizer.rs:19-33
         const float x = (float)c * (1.0f / 255.0f);
@@ -1995,6 +2027,10 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
             else if (tid == 23) s_k.n_lights = S.n_lights;
             else if (tid < 27) s_k.sun_l[tid - 24] = Fg.sun_l[tid - 24];
             else if (tid == 27) s_k.sun_radiance = Fg.sun_radiance;
+            else if (tid < 31) s_k.brush[tid - 28] = Fg.brush_pos[tid - 28];
+            else if (tid == 31) s_k.brush[3] = Fg.brush_radius;
+            else if (tid == 32) s_k.brush_falloff = Fg.brush_falloff;
+            else if (tid == 33) s_k.has_brush = Fg.has_brush;
             for (uint32_t i = tid; i < min(S.n_lights, (uint32_t)RX_SMEM_LIGHTS) * (uint32_t)(sizeof(DLight) / 4); i += RX_TILE_THREADS)
                 reinterpret_cast<uint32_t*>(s_lights)[i] = __ldg(reinterpret_cast<const uint32_t*>(lights_gg) + i);
             if (!GENERAL) {  // largeg-triangle records of the frame
@@ -2052,7 +2088,8 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
 
         const uint32_t smode = SAMPLE == 2 ? F.sample_mode : (uint32_t)SAMPLE;
         const int fw = F.band_x1, fy1 = F.band_y1;   // right / bottom bound of the rendered rectangle
-        const int bx0 = F.band_x0, fpitch = F.band_x1 - F.band_x0;   // its left edge and the row pitch of the output buffer
+        const int bx0 = F.band_x0, fpitch = F.band_x1 - F.band_x0;   // its left edge and the row pitch of the owner / depth planes
+        const int ppitch = (int)out.pitch;   // row pitch of the pixel buffer in pixels: the rectangle's width, or the full frame's when a band is written in place (rxc_mgpu_rasterize)
         const int tx0 = F.band_x0 + s_work[1], ty0 = F.band_y0 + s_work[2];
         const int tx1 = min(tx0 + RX_TILE_W, fw), ty1 = min(ty0 + RX_TILE_H, fy1);
         if (!PLANES && s_can_be_empty) {
@@ -2071,13 +2108,13 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                 uint8_t* frame_px = out.pixels + (size_t)f * out.frame_stride;
                 if (out.vec_store && tx0 + RX_TILE_W <= fw && ty0 + RX_TILE_H <= fy1) {
                     const int r = (int)tid >> 3, c4 = (int)tid & 7;
-                    reinterpret_cast<uint4*>(frame_px + ((size_t)(ty0 - F.band_y0 + r) * (size_t)fpitch + (size_t)(tx0 - bx0)) * 4)[c4] =
+                    reinterpret_cast<uint4*>(frame_px + ((size_t)(ty0 - F.band_y0 + r) * (size_t)ppitch + (size_t)(tx0 - bx0)) * 4)[c4] =
                         make_uint4(0xFF000000u, 0xFF000000u, 0xFF000000u, 0xFF000000u);
                 } else {
                     for (int i = (int)tid; i < RX_TILE_W * RX_TILE_H; i += RX_TILE_THREADS) {
                         const int r = i >> 5, c = i & 31;
                         if (tx0 + c < fw && ty0 + r < fy1)
-                            reinterpret_cast<uint32_t*>(frame_px)[(size_t)(ty0 - F.band_y0 + r) * (size_t)fpitch + (size_t)(tx0 - bx0 + c)] = 0xFF000000u;
+                            reinterpret_cast<uint32_t*>(frame_px)[(size_t)(ty0 - F.band_y0 + r) * (size_t)ppitch + (size_t)(tx0 - bx0 + c)] = 0xFF000000u;
                     }
                 }
                 __syncthreads();  // s_work is rewritten by the next tile
@@ -2278,20 +2315,20 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
 #if RX_BULK_STORE
             if (warp == 0) {
                 const uint32_t src = (uint32_t)__cvta_generic_to_shared(&s_color[coff + lane * RX_COLOR_STRIDE]);
-                uint8_t* dst = frame_px + ((size_t)(ty0 - F.band_y0 + (int)lane) * (size_t)fpitch + (size_t)(tx0 - bx0)) * 4;
+                uint8_t* dst = frame_px + ((size_t)(ty0 - F.band_y0 + (int)lane) * (size_t)ppitch + (size_t)(tx0 - bx0)) * 4;
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" ::"l"(dst), "r"(src) : "memory");
             }
 #else
             const int r = (int)tid >> 3, c4 = (int)tid & 7;   // 8 x 16 B per 32-pixel row
             const uint4 v = *reinterpret_cast<const uint4*>(&s_color[coff + r * RX_COLOR_STRIDE + c4 * 4]);
-            uint4* dst = reinterpret_cast<uint4*>(frame_px + ((size_t)(ty0 - F.band_y0 + r) * (size_t)fpitch + (size_t)(tx0 - bx0)) * 4) + c4;
+            uint4* dst = reinterpret_cast<uint4*>(frame_px + ((size_t)(ty0 - F.band_y0 + r) * (size_t)ppitch + (size_t)(tx0 - bx0)) * 4) + c4;
             *dst = v;
 #endif
         } else {
             for (int i = (int)tid; i < RX_TILE_W * RX_TILE_H; i += RX_TILE_THREADS) {
                 const int r = i >> 5, c = i & 31;
                 if (tx0 + c < fw && ty0 + r < fy1)
-                    reinterpret_cast<uint32_t*>(frame_px)[(size_t)(ty0 - F.band_y0 + r) * (size_t)fpitch + (size_t)(tx0 - bx0 + c)] =
+                    reinterpret_cast<uint32_t*>(frame_px)[(size_t)(ty0 - F.band_y0 + r) * (size_t)ppitch + (size_t)(tx0 - bx0 + c)] =
                         s_color[coff + r * RX_COLOR_STRIDE + c];
             }
         }

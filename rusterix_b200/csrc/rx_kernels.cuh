@@ -77,6 +77,7 @@ struct RasterOut {
     uint32_t* owner;       // optional, only for single-frame calls
     float* depth;
     uint32_t vec_store;    // rows are 16 B aligned -> 128-bit stores
+    uint32_t pitch;        // pixels per row of the pixel buffer (the rendered rectangle's width unless a band is written in place)
 };
 
 enum {

@@ -2,11 +2,14 @@
 camera sweep or screen bands of one frame are independent units, so ranks render without any
 data-path collective; torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests) is used
 only to gather finished frames / bands to rank 0."""
+import ctypes as C
 import os
-from typing import List, Optional, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
+
+from . import _abi
 
 TILE_H = 32  # GPU tile height (csrc/rx_device.cuh RX_TILE_H): bands start on tile rows
 
@@ -223,3 +226,92 @@ def gather_column_bands_to_rank0(band: torch.Tensor, height: int, width: int, ra
     if band.numel():
         dist.send(band.contiguous(), dst=0)
     return None
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# rxc_mgpu_*: delivery to rank 0 inside the library (include/rxcuda.h).  The raster kernel of every rank writes its
+# tiles straight into rank 0's buffer over NVLink (cudaIpc peer mapping); torch.distributed only carries the 128-byte
+# ncclUniqueId from rank 0 to the others once.
+# ---------------------------------------------------------------------------------------------------------------------
+class _DevicePointer:
+    """Lets torch wrap a raw device address (rank 0's delivery buffer) without copying."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 3, "strides": None}
+
+
+def frame_regions(world: int, frames_per_rank: int, frame_bytes: int, base_offset: int = 0):
+    """The regions of a frame-sharded step: rank r's `frames_per_rank` frames sit back to back at
+    base_offset + r * frames_per_rank * frame_bytes (contiguous blocks per rank)."""
+    arr = (_abi.rxc_mgpu_region * world)()
+    for r in range(world):
+        arr[r].rank, arr[r].rows = r, 1
+        arr[r].offset = base_offset + r * frames_per_rank * frame_bytes
+        arr[r].row_bytes = frames_per_rank * frame_bytes
+        arr[r].pitch_bytes = 0
+    return arr
+
+
+def band_regions(bands: Sequence[Tuple[int, int, int, int]], width: int, base_offset: int = 0):
+    """The regions of a band split: bands[r] = (y0, y1, x0, x1) of rank r inside a frame `width` pixels wide."""
+    arr = (_abi.rxc_mgpu_region * len(bands))()
+    for r, (y0, y1, x0, x1) in enumerate(bands):
+        arr[r].rank = r
+        arr[r].rows = max(0, y1 - y0) if x1 > x0 else 0
+        arr[r].offset = base_offset + (y0 * width + x0) * 4
+        arr[r].row_bytes = max(0, x1 - x0) * 4
+        arr[r].pitch_bytes = width * 4
+        if x0 == 0 and x1 == width:   # full rows: one contiguous block
+            arr[r].row_bytes, arr[r].rows, arr[r].pitch_bytes = max(0, y1 - y0) * width * 4, 1 if y1 > y0 else 0, 0
+    return arr
+
+
+class Delivery:
+    """One rxc_mgpu session of a DeviceContext: `Delivery(ctx, rank, world)` on every rank (collective), then per
+    step `render(...)` any number of times, `deliver(regions)` once, and `release()` when rank 0 is done reading."""
+
+    def __init__(self, ctx, rank: int, world: int, id_bytes: Optional[bytes] = None):
+        self.ctx, self.rank, self.world = ctx, int(rank), int(world)
+        self.lib = ctx.lib
+        ident = (C.c_uint8 * _abi.RXC_MGPU_ID_BYTES)()
+        if world > 1:
+            if id_bytes is None:
+                box = [None]
+                if rank == 0:
+                    ctx.check_static(self.lib.rxc_mgpu_unique_id(ident))
+                    box[0] = bytes(ident)
+                dist.broadcast_object_list(box, src=0)
+                id_bytes = box[0]
+            C.memmove(ident, id_bytes, _abi.RXC_MGPU_ID_BYTES)
+        ctx.check(self.lib.rxc_mgpu_init(ctx.handle, ident, self.rank, self.world))
+        self.bytes, self.ptr, self.mode = 0, None, _abi.RXC_MGPU_LOCAL
+
+    def target(self, nbytes: int):
+        """Collective: (re)allocates the delivery buffer on rank 0 and maps it everywhere.  Returns a uint8 tensor view
+        of it on rank 0, None on the other ranks."""
+        p, mode = C.c_void_p(), C.c_uint32()
+        self.ctx.check(self.lib.rxc_mgpu_target(self.ctx.handle, int(nbytes), C.byref(p), C.byref(mode)))
+        self.bytes, self.ptr, self.mode = int(nbytes), p.value, int(mode.value)
+        if self.rank == 0:
+            return torch.as_tensor(_DevicePointer(p.value, nbytes), device=torch.device("cuda", self.ctx.device))
+        return None
+
+    def render(self, batch, offset_bytes: int, frame_stride_bytes: Optional[int] = None, pitch_bytes: int = 0):
+        """rxc_mgpu_rasterize of a prepared FrameBatch (asynchronous)."""
+        stride = batch.stride if frame_stride_bytes is None else int(frame_stride_bytes)
+        self.ctx.check(self.lib.rxc_mgpu_rasterize(self.ctx.handle, batch.frames, batch.n, int(offset_bytes), stride, int(pitch_bytes)))
+
+    def deliver(self, regions=None):
+        n = len(regions) if regions is not None else 0
+        self.ctx.check(self.lib.rxc_mgpu_deliver(self.ctx.handle, regions, n))
+
+    def release(self):
+        self.ctx.check(self.lib.rxc_mgpu_release(self.ctx.handle))
+
+    def status(self):
+        mode, deliveries, timeouts = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self.ctx.check(self.lib.rxc_mgpu_status(self.ctx.handle, C.byref(mode), C.byref(deliveries), C.byref(timeouts)))
+        return {"mode": ("local", "peer", "nccl")[mode.value], "deliveries": int(deliveries.value), "timeouts": int(timeouts.value)}
+
+    def close(self):
+        self.ctx.check(self.lib.rxc_mgpu_shutdown(self.ctx.handle))

@@ -37,6 +37,10 @@ class DeviceContext:
         if st != 0:
             raise _lib.RxcError(st, self.lib.rxc_last_error(self.handle).decode())
 
+    def check_static(self, st):
+        if st != 0:
+            raise _lib.RxcError(st, "call without a context failed")
+
     def close(self):
         if self.handle:
             self.lib.rxc_destroy(self.handle)
