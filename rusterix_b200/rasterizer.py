@@ -57,7 +57,7 @@ class DeviceContext:
             self.check(self.lib.rxc_set_assets(self.handle, m.struct, len(assets.tile_list)))
             self._assets_key = akey
             self._scene_key = None
-        skey = (scene._uid, scene._generation, index_bytes)
+        skey = (scene._uid, scene._generation, index_bytes, scene.structure_key())
         lights = scene.all_lights()
         lkey = tuple(
             (int(l.light_type), tuple(l.position), tuple(l.color), l.intensity, l.emitting, l.start_distance,
@@ -153,6 +153,23 @@ def _buffer_pointer(buf, nbytes):
     return arr.ctypes.data, arr
 
 
+def _check_band(band, width, height):
+    """`band` = (y0, y1) or (y0, y1, x0, x1).  In the C ABI a band of 0/0 means "the whole frame", so an EMPTY band
+    must never reach it (it would render the full frame into a band-sized buffer): callers skip the render for a
+    rank whose band is empty, and anything else that is not a proper sub-rectangle is an error here."""
+    if band is None:
+        return
+    if len(band) not in (2, 4):
+        raise ValueError("band is (y0, y1) or (y0, y1, x0, x1)")
+    y0, y1 = int(band[0]), int(band[1])
+    if not (0 <= y0 < y1 <= height):
+        raise ValueError(f"empty or out-of-range row band {band} for a frame of {height} rows (skip the render for an empty band)")
+    if len(band) == 4:
+        x0, x1 = int(band[2]), int(band[3])
+        if not (0 <= x0 < x1 <= width):
+            raise ValueError(f"empty or out-of-range column band {band} for a frame of {width} columns")
+
+
 class Rasterizer:
     def __init__(self, projection_matrix_2d, view_matrix, projection_matrix):
         self.render_mode_ = RenderMode.render_all()
@@ -211,7 +228,12 @@ class Rasterizer:
         return self
 
     def _check_supported(self):
-        pass
+        """What the device path does not do is reported by the library (RXC_ERR_UNSUPPORTED from rxc_set_scene /
+        rxc_rasterize: the Sky node's cloud layer, texture-baking VM ops, device VM limits); the only host-side
+        check is the one the library cannot make, a render graph holding something other than the mirrored nodes."""
+        g = self.render_graph
+        if g is not None and not hasattr(g, "miss_nodes"):
+            raise _lib.RxcError(_abi.RXC_ERR_UNSUPPORTED, "render_graph must be a rusterix_b200.types.RenderGraph")
 
     def prepare_render_graph(self):
         """src/rasterizer.rs:227-253: collect the miss nodes, render_setup them (the last Sky node's sun wins) and
@@ -243,6 +265,7 @@ class Rasterizer:
         ctx = DeviceContext.get(self.device)
         ctx.upload(scene, assets, self.index_bytes)
         ctx.set_mapmini(self.mapmini)
+        _check_band(band, width, height)
         frame = marshal.make_frame(self, scene, width, height, tile_size, band)
         rows = height if band is None else band[1] - band[0]
         width = width if band is None or len(band) < 4 else band[3] - band[2]   # the buffer holds the rendered rectangle
@@ -265,6 +288,7 @@ class Rasterizer:
         ctx.upload(scene, assets, 4)
         if rasterizers:
             ctx.set_mapmini(rasterizers[0].mapmini)
+        _check_band(band, width, height)
         n = len(rasterizers)
         frames = (_abi.rxc_frame * n)()
         for i, r in enumerate(rasterizers):

@@ -542,8 +542,25 @@ class Scene:
         self.animation_frame = (self.animation_frame + 1) & 0xFFFFFFFFFFFFFFFF
 
     def mark_dirty(self):
-        """Tell the device cache that geometry / dynamic textures changed."""
+        """Tell the device cache that geometry / dynamic textures changed IN PLACE (a vertex array edited, a texture
+        repainted).  Structural changes -- batches or tiles appended, removed or replaced, the usual per-frame
+        `scene.d3_dynamic = ...` of the reference's callers -- are seen without it (structure_key)."""
         self._generation += 1
+
+    def structure_key(self):
+        """Cheap identity of what the scene currently holds: which batch objects (and which vertex / index arrays
+        inside them) sit in which list, how many dynamic tiles and shaders there are.  The reference re-projects
+        `&mut scene` on every rasterize() call; the device cache is re-uploaded when this key or the generation
+        changes."""
+        def bkey(b):
+            return (id(b), id(b.vertices), id(b.indices), len(b.vertices), len(b.indices), id(getattr(b, "source_", None)))
+        key = [tuple(bkey(b) for b in lst) for lst in (self.d2_static, self.d2_dynamic, self.d3_static, self.d3_dynamic, self.d3_overlay)]
+        for ck, ch in self.chunks.items():
+            key.append((ck, id(ch), tuple(bkey(b) for b in ch.batches2d), tuple(bkey(b) for b in ch.batches3d_opacity),
+                        tuple(bkey(b) for b in ch.batches3d), id(ch.terrain_batch2d), id(ch.terrain_batch3d), id(ch.terrain_texture),
+                        len(ch.occluded_sectors), len(ch.shaders)))
+        key.append((len(self.dynamic_textures), tuple(id(t) for t in self.dynamic_textures), len(self.shaders)))
+        return tuple(key)
 
     def all_lights(self) -> List[CompiledLight]:
         return list(self.lights) + list(self.dynamic_lights)

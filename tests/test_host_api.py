@@ -291,3 +291,35 @@ def test_oracle_opacity_layer_and_surface_ids():
     assert owner[H // 2, W // 2] == 3 * 4 and owner[H // 2, W // 2 + 12] == 3 * 2   # slots: batch2 tri0 / batch1 tri0 (+3 per tri capacity)
     assert side[1] > 150 and side[2] == 0
     assert centre[1] < 80 and centre[2] > 60 and centre[0] > 60 and centre[3] == 255
+
+
+def test_empty_or_bad_bands_never_reach_the_abi_sentinel():
+    """rxc_frame.band_y0 = band_y1 = 0 means "whole frame": an empty band must be an error on the host side, not a
+    full-frame render into a band-sized buffer (a balancer may hand rank 0 an empty band)."""
+    from rusterix_b200.rasterizer import _check_band
+
+    _check_band(None, 640, 360); _check_band((0, 360), 640, 360); _check_band((32, 64, 0, 640), 640, 360)
+    for bad in ((0, 0), (64, 64), (64, 32), (0, 361), (0, 32, 0, 0), (0, 32, 64, 64), (0, 32, 0, 641), (0,), (0, 1, 2)):
+        with pytest.raises(ValueError):
+            _check_band(bad, 640, 360)
+
+
+def test_structural_scene_changes_invalidate_the_device_cache_key():
+    """The reference re-projects `&mut scene` on every call; the device cache must notice batches that were appended,
+    replaced or removed and dynamic tiles that were added, without an explicit mark_dirty()."""
+    from rusterix_b200 import Batch2D, Batch3D, scenes
+
+    scene = scenes.map_scene()
+    k0 = scene.structure_key()
+    assert k0 == scene.structure_key()
+    scene.d3_dynamic.append(Batch3D.from_box(0, 0, 0, 1, 1, 1))
+    k1 = scene.structure_key()
+    assert k1 != k0
+    scene.d3_dynamic = [Batch3D.from_box(0, 0, 0, 1, 1, 1)]          # the reference's per-frame reassignment
+    k2 = scene.structure_key()
+    assert k2 != k1
+    scene.d2_dynamic.append(Batch2D.from_rectangle(0, 0, 4, 4))
+    assert scene.structure_key() != k2
+    k3 = scene.structure_key()
+    scene.dynamic_textures.append(scenes.map_assets(16).tile_list[0])
+    assert scene.structure_key() != k3

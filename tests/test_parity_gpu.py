@@ -229,6 +229,26 @@ def test_chunk_path_opacity_surface_ids_terrain_occlusion(frame):
     assert st["within1_frac"] >= 0.999
 
 
+@pytest.mark.parametrize("frame", [0, 5])
+def test_brush_preview_highlights_terrain_texels(frame):
+    """brush_preview over Terrain batches: the sampled terrain texel goes towards white inside the brush radius, in
+    d3_rasterize (rasterizer.rs:1193-1212) and in d3_rasterize_opacity (:1601-1620; one pane is given the Terrain source)."""
+    from rusterix_b200.types import BrushPreview
+
+    cfg = scenes.chunked_config(960, 540)
+    cfg.brush_preview = BrushPreview((8.0, 0.0, 8.0), 3.5, 0.5)
+    ch = cfg.scene.chunks[(0, 0)]
+    ch.batches3d_opacity[0] = ch.batches3d_opacity[0].source(PixelSource.Terrain)
+    cfg.scene.mark_dirty()
+    st = _run(cfg, frame)
+    assert st["within1_frac"] >= 0.999
+    cfg.brush_preview = None
+    plain = render_gpu(cfg.rasterizer(frame), cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size)[0]
+    cfg.brush_preview = BrushPreview((8.0, 0.0, 8.0), 3.5, 0.5)
+    lit = render_gpu(cfg.rasterizer(frame), cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size)[0]
+    assert (plain != lit).any()
+
+
 def test_chunk_path_linear_odd_size_and_preserve_transparency():
     cfg = scenes.chunked_config(1001, 563)
     cfg.sample_mode = SampleMode.Linear

@@ -128,6 +128,36 @@ def test_oracle_brush_preview_blends_towards_white_on_the_ground_plane():
     assert not changed[:20].any()                                              # rays above the horizon never hit y = 0
 
 
+def test_oracle_brush_preview_whitens_terrain_texels_only():
+    """rasterizer.rs:1193-1212: with a brush preview the terrain texel is blended towards white inside the brush radius
+    before it is shaded.  Pixels owned by other batches keep their colour; terrain pixels change only near the brush."""
+    from rusterix_b200 import marshal
+    from rusterix_b200.types import BrushPreview
+
+    cfg = scenes.chunked_config(320, 180)
+    cfg.scene.d2_static.clear(); cfg.scene.d2_dynamic.clear()
+    for ch in cfg.scene.chunks.values():
+        ch.batches2d.clear(); ch.terrain_batch2d = None; ch.batches3d_opacity.clear()
+    without, owner, depth = oracle_ffi.rasterize(cfg.rasterizer(0), cfg.scene, cfg.assets, 320, 180, 40)
+    cfg.brush_preview = BrushPreview((8.0, 0.0, 8.0), 2.5, 0.5)
+    with_brush, owner2, _ = oracle_ffi.rasterize(cfg.rasterizer(0), cfg.scene, cfg.assets, 320, 180, 40)
+    assert np.array_equal(owner, owner2)                     # alpha is untouched: ownership does not move
+    # owner id ranges of the terrain batches: 3 slots per triangle, in submission order
+    b3, _b2 = marshal.submission_order(cfg.scene)
+    terrain = np.zeros(owner.shape, dtype=bool)
+    base = 0
+    for entry in b3:
+        batch = entry[0]
+        n = 3 * len(batch.indices)
+        if batch.source_.name == "Terrain":
+            terrain |= (owner >= base) & (owner < base + n)
+        base += n
+    changed = (with_brush.astype(int) != without.astype(int)).any(axis=-1)
+    assert changed.sum() > 50 and not changed[~terrain].any()
+    assert (with_brush[changed][:, :3].astype(int) >= without[changed][:, :3].astype(int)).all()
+    assert (terrain & ~changed).sum() > 50                   # terrain outside the radius is untouched
+
+
 def test_sun_lights_the_scene_and_clouds_are_rejected():
     cfg = scenes.sky_config(120, 80, 40, hour=13.0)
     lit = oracle_ffi.rasterize(cfg.rasterizer(0), cfg.scene, cfg.assets, 120, 80, 40)
