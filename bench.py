@@ -12,8 +12,15 @@ Default workload: BASELINE.json's textured map scene at 3840x2160 (the config it
   cpu_baseline  the CPU oracle (a port of the reference algorithm) on this box's host cores
 
 `--impl reference` times only the CPU port on the same workload (rank 0 only).
-Multi-GPU: frames are sharded across ranks (one process per GPU, torchrun), no data-path collective;
-the NCCL gather of the frames to rank 0 is timed separately and reported under "gather".
+Multi-GPU: frames are sharded across ranks (one process per GPU, torchrun), no data-path collective.
+  value              render-only: every rank's frames stay in its own HBM (weak scaling, F frames per GPU and step)
+  value_with_gather  the same step with every rank's raster kernel writing its tiles straight into rank 0's
+                     buffer over NVLink (rxc_mgpu_*: peer mapping, completion flags; no copy or collective after
+                     the render), timed until rank 0's stream has seen every rank's flag
+  sweep4096          BASELINE.json config E as specified: 4096 frames of the map scene at 1920x1080 in contiguous
+                     blocks per rank, STRONG scaling, total-job seconds render-only and delivered to rank 0
+  band_split         config D: one 7680x4320 frame of the 1M-triangle scene split into bands, render-only and
+                     written in place into rank 0's frame
 """
 import argparse
 import json
@@ -32,11 +39,12 @@ import numpy as np  # noqa: E402
 
 WORKLOADS = {
     # name: (builder, kwargs, description)
-    "map4k": ("sweep", dict(width=3840, height=2160, tile_size=40), "minigame map scene (walls/floor/fence/sky, 1 point light, logo rect), 3840x2160, Nearest, tile 40"),
-    "teapot1080": ("teapot", dict(width=1920, height=1080, tile_size=60), "teapot-like lathe mesh 2256 tris, 1920x1080, Linear, tile 60, orbit sweep"),
-    "sweep1080": ("sweep", dict(width=1920, height=1080, tile_size=40), "camera sweep of the map scene, 1920x1080, Nearest, tile 40"),
+    "map4k": ("sweep", dict(width=3840, height=2160, tile_size=40, real=True), "minigame map scene (world.rxm walls/floor/fence/sky with the minigame's own PNG tiles, 1 point light, logo rect), 3840x2160, Nearest, tile 40"),
+    "teapot1080": ("teapot", dict(width=1920, height=1080, tile_size=60, real=True), "examples/teapot.obj (1202 vertices, 2256 triangles) textured with images/logo.png, 1920x1080, Linear, tile 60, orbit sweep"),
+    "sweep1080": ("sweep", dict(width=1920, height=1080, tile_size=40, real=True), "camera sweep of the map scene, 1920x1080, Nearest, tile 40"),
     "dense8k": ("dense", dict(width=7680, height=4320, tile_size=40), "991,232-triangle heightfield in 1024 batches, 7 lights, 7680x4320, Linear"),
-    "cube800": ("cube", dict(width=800, height=600, tile_size=200), "textured cube, 800x600, Nearest, tile 200"),
+    "cube800": ("cube", dict(width=800, height=600, tile_size=200, real=True), "cube textured with images/logo.png, 800x600, Nearest, tile 200"),
+    "cube2000": ("cube", dict(width=2000, height=2000, tile_size=40, real=True), "cube textured with images/logo.png, 2000x2000, tile 40 (the shape of benches/rasterize_cube.rs)"),
     # the rows SURVEY 8f marks "next", measured like the others
     "chunked1080": ("chunked", dict(width=1920, height=1080, tile_size=40), "chunked map (4 chunks: opacity panes with surface ids, terrain textures, occluded sectors, chunk lights, entity/item tiles, 2D overlay with lines), 1920x1080, Nearest"),
     "shaded1080": ("shaded", dict(width=1920, height=1080, tile_size=40), "batch shaders (Rusteria VM programs on 3D, chunk, opacity-pass and 2D batches; one program cuts holes through opacity), 1920x1080, Nearest"),
@@ -119,6 +127,12 @@ def build_workload(name, frames_per_step, rank, world):
     return cfg, frame_ids, desc
 
 
+def make_config(desc, cfg, world):
+    """The `config` object of the JSON line: the same keys and values in the native and the reference arm."""
+    return {"workload": desc, "width": cfg.width, "height": cfg.height, "triangles": cfg.counts()[1], "tile_size": cfg.tile_size,
+            "sample_mode": str(cfg.sample_mode).split(".")[-1], "lights": len(cfg.scene.all_lights())}
+
+
 def cpu_port_time(cfg, frame_ids, budget_s=20.0, max_frames=10, warm=1):
     """Times the oracle (CPU port of the reference algorithm, all host threads) on whole frames of the
     same workload.  Returns (Mpixel/s, cores, sample description, seconds per frame)."""
@@ -171,8 +185,9 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "Mpixels/s shaded", "value": val, "unit": "Mpixel/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "frames_per_s": args.steps / dt,
-        "config": {"workload": desc, "step": "1 frame (bounded sample of the GPU arm's multi-frame step)",
-                   "note": "the Rust reference cannot be built in this image (no cargo); this is the C++ port of its algorithm (oracle/rx_oracle.cpp), all host threads"},
+        "config": make_config(desc, cfg, 1),
+        "step": "1 frame (a bounded sample of the GPU arm's multi-frame step; the metric is a rate)",
+        "note": "the Rust reference cannot be built in this image (no cargo); this is the C++ port of its algorithm (oracle/rx_oracle.cpp), all host threads",
         "cpu_baseline": {"value": val, "unit": "Mpixel/s", "cores": cores, "kind": "port", "sample": f"{args.steps} frames, 1 per step"},
         "e2e": {"value": val, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -365,22 +380,33 @@ def main():
                              "profile_version": ncu_row.get("version")},
                 "note": "the kernel is SM-issue bound, not HBM bound: about 640 thread-instructions per pixel (exact divisions, no FMA contraction, per-light BRDF) keep the issue slots ~80 % busy; see DESIGN.md section 5"}
 
-    # ---- optional NCCL gather of the step's frames to rank 0 (timed separately, not part of value)
-    gather = None
+    # ---- the same step with delivery to rank 0 fused into the raster kernel's write-back (rxc_mgpu_*)
+    delivered = None
+    dl = None
     if world > 1:
-        from rusterix_b200 import mgpu
+        dl = mgpu.Delivery(ctx, rank, world)
+        slots = 2
+        dl.target(slots * world * F * frame_bytes)
+        regions = [mgpu.frame_regions(world, F, frame_bytes, s_ * world * F * frame_bytes) for s_ in range(slots)]
+        k_step = [0]
 
-        for _ in range(2):
-            mgpu.gather_frames_to_rank0(out_dev, rank, world)
-        barrier()
-        g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
-        g0.record()
-        mgpu.gather_frames_to_rank0(out_dev, rank, world)
-        g1.record()
-        barrier()
-        t = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        gather = {"ms_per_step": float(t.item()), "bytes_to_rank0": (world - 1) * F * frame_bytes}
+        def step_delivered():
+            k = k_step[0]; k_step[0] += 1
+            slot = k % slots
+            if k >= slots:
+                dl.release()                    # rank 0 is done with what this slot held two steps ago
+            dl.render(batch, (slot * world + rank) * F * frame_bytes)
+            dl.deliver(regions[slot])           # ranks > 0: flag behind the raster kernel; rank 0: wait for every flag
+
+        ms_del, _ = timed(step_delivered, args.steps, args.warmup)
+        ms_del /= args.steps
+        stt = dl.status()
+        nv_bytes = (world - 1) * F * frame_bytes
+        delivered = {"value": pixels_per_step / (ms_del * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": ms_del,
+                     "bytes_to_rank0_per_step": nv_bytes, "rank0_ingest_GBps": nv_bytes / (ms_del * 1e-3) / 1e9,
+                     "mode": "peer writes over NVLink from k_raster's tile write-back (cudaIpc mapping of rank 0's buffer), completion flags" if stt["mode"] != "nccl" else "local staging + one ncclGroup of send/recv (no peer mapping)",
+                     "timeouts": stt["timeouts"] if rank == 0 else None,
+                     "timing": "CUDA events around render + deliver (+ release) on every rank's stream, max over ranks; rank 0's end event sits behind its wait for every rank's flag"}
 
     line = None
     if rank == 0:
@@ -388,20 +414,26 @@ def main():
             "metric": "Mpixels/s shaded", "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "frames_per_s": F * world / (ms_per_step * 1e-3),
-            "config": {"workload": desc, "frames_per_step_per_gpu": F, "width": W, "height": H, "triangles": cfg.counts()[1],
-                       "sharding": "frames sharded across ranks, no data-path collective" if world > 1 else "single GPU",
-                       "l2": "256 MiB flush between timed steps; each step also writes %.0f MB of frames (> 126 MB L2)" % (F * frame_bytes / 1e6),
-                       "timing": "CUDA events per step on the launching stream, summed over steps, max over ranks"},
+            "config": make_config(desc, cfg, world),
+            "frames_per_step_per_gpu": F,
+            "notes": {"sharding": "frames sharded across ranks, no data-path collective" if world > 1 else "single GPU",
+                      "l2": "256 MiB flush between timed steps; each step also writes %.0f MB of frames (> 126 MB L2)" % (F * frame_bytes / 1e6),
+                      "timing": "CUDA events per step on the launching stream, summed over steps, max over ranks"},
             "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step),
                     "ms_per_step": e2e_ms_step, "steps": e2e_steps, "api": "Rasterizer.rasterize_batch -> rxc_rasterize_batch, pinned host pixels",
                     "host_numa_binding": ("rank pinned to the %d cores next to its GPU" % len(numa_cpus)) if numa_cpus else "none"},
             "gpu_launches": int(gpu_launches), "launches_per_step": int(launches_per_step),
             "roofline": roofline, "clocks": clocks,
         }
-        if gather:
-            line["gather"] = gather
+        if delivered:
+            line["value_with_gather"] = delivered["value"]
+            line["delivered"] = delivered
+    if not args.no_extras:
+        sw = sweep4096(rank, world, local_rank, dev, barrier, dl)
+        if rank == 0:
+            line["sweep4096"] = sw
     if world > 1 and not args.no_extras:
-        bs = band_split(rank, world, local_rank, dev, flush, barrier)
+        bs = band_split(rank, world, local_rank, dev, flush, barrier, dl)
         if rank == 0:
             line["band_split"] = bs
 
@@ -410,7 +442,7 @@ def main():
         mpix, cores, sample, spf = cpu_port_time(cfg, frame_ids)
         line["cpu_baseline"] = {"value": mpix, "unit": "Mpixel/s", "cores": cores, "kind": "port", "sample": sample, "s_per_frame": spf}
         also = {}
-        for wname in ("cube800", "teapot1080", "dense8k", "sweep1080", "chunked1080", "game2d1080", "shaded1080"):
+        for wname in ("cube800", "cube2000", "teapot1080", "dense8k", "sweep1080", "chunked1080", "game2d1080", "shaded1080"):
             if wname == args.workload:
                 continue
             try:
@@ -423,18 +455,99 @@ def main():
 
     if rank == 0:
         emit_line(line)
+    if dl is not None:
+        ctx.synchronize()
+        dl.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def band_split(rank, world, local_rank, dev, flush, barrier, steps=5, warmup=3, balance_iters=12):
+def sweep4096(rank, world, local_rank, dev, barrier, dl, total_frames=4096, per_launch=32):
+    """BASELINE.json config E as specified: 4096 frames of the map scene at 1920x1080, sharded by frame across the
+    ranks in contiguous blocks -- STRONG scaling (the job is the same 4096 frames at every N).  A rank renders its
+    block `per_launch` frames per launch sequence (265 MB of frames: more than the L2 holds, so no flush is needed
+    between launches).  Two totals: render-only (frames stay in the rank's HBM, a ring of one launch) and delivered
+    (every launch written straight into a two-slot ring in rank 0's memory, rxc_mgpu_*, release hand-shake included)."""
+    import torch
+    import torch.distributed as dist
+    from rusterix_b200 import DeviceContext, Rasterizer, mgpu
+
+    cfg, _ids, desc = build_workload("sweep1080", 1, 0, 1)
+    W, H = cfg.width, cfg.height
+    fb = W * H * 4
+    per_rank = total_frames // world
+    first = rank * per_rank
+    n_launch = (per_rank + per_launch - 1) // per_launch
+    t_prep = time.perf_counter()
+    batches = []
+    for k in range(n_launch):
+        ids = range(first + k * per_launch, min(first + (k + 1) * per_launch, first + per_rank))
+        batches.append(Rasterizer.prepare_batch([cfg.rasterizer(i).on_device(local_rank) for i in ids], cfg.scene, W, H, cfg.tile_size, cfg.assets, device=local_rank))
+    t_prep = time.perf_counter() - t_prep
+    ctx = DeviceContext.get(local_rank)
+    out = torch.empty((per_launch, H, W, 4), dtype=torch.uint8, device=dev)
+
+    def job_render():
+        for b in batches:
+            b.run(out, sync=False)
+
+    own = None
+    if dl is None:   # one GPU: the delivery buffer is local memory, the path through rxc_mgpu_* is the same
+        own = dl = mgpu.Delivery(ctx, rank, world)
+    slots = 2
+    dl.target(slots * world * per_launch * fb)
+    regions = [mgpu.frame_regions(world, per_launch, fb, s_ * world * per_launch * fb) for s_ in range(slots)]
+
+    def job_delivered():
+        for k, b in enumerate(batches):
+            slot = k % slots
+            if k >= slots:
+                dl.release()
+            dl.render(b, (slot * world + rank) * per_launch * fb)
+            dl.deliver(regions[slot])
+        for _ in range(min(slots, len(batches))):   # leave the ring drained for the next job
+            dl.release()
+
+    def timed_job(job):
+        for b in batches[:3]:
+            b.run(out, sync=False)          # warm-up: scene upload, workspace, clocks
+        barrier()
+        a = torch.cuda.Event(enable_timing=True); z = torch.cuda.Event(enable_timing=True)
+        a.record(); job(); z.record()
+        barrier()
+        ms = a.elapsed_time(z)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    ms_r = min(timed_job(job_render) for _ in range(2))
+    ms_d = min(timed_job(job_delivered) for _ in range(2))
+    st = dl.status()
+    if own is not None:
+        ctx.synchronize()
+        own.close()
+    pix = per_rank * world * W * H
+    return {"workload": "camera sweep: %d frames of the map scene at %dx%d, contiguous blocks of %d frames per rank, %d frames per launch" % (per_rank * world, W, H, per_rank, per_launch),
+            "scaling": "strong", "frames": per_rank * world, "n_gpus": world,
+            "render_only": {"total_job_s": ms_r * 1e-3, "frames_per_s": per_rank * world / (ms_r * 1e-3), "Mpixel_per_s": pix / (ms_r * 1e-3) / 1e6},
+            "delivered_to_rank0": {"total_job_s": ms_d * 1e-3, "frames_per_s": per_rank * world / (ms_d * 1e-3), "Mpixel_per_s": pix / (ms_d * 1e-3) / 1e6,
+                                   "bytes_to_rank0": (world - 1) * per_rank * fb, "rank0_ingest_GBps": (world - 1) * per_rank * fb / (ms_d * 1e-3) / 1e9 if world > 1 else None,
+                                   "mode": ("peer writes over NVLink (ranks > 0), local stores (rank 0)" if st["mode"] != "nccl" else "nccl send/recv") if world > 1 else "local", "timeouts": st["timeouts"] if rank == 0 else None},
+            "host_prepare_s": t_prep,
+            "timing": "one pair of CUDA events around the whole job on every rank's stream (best of 2 jobs after a 3-launch warm-up), max over ranks; every launch writes 265 MB of frames (> L2)"}
+
+
+def band_split(rank, world, local_rank, dev, flush, barrier, dl, steps=5, warmup=3, balance_iters=12):
     """BASELINE.json config D: one 7680x4320 frame of the 1M-triangle scene split by screen band over the ranks
-    (SURVEY 8e).  Every rank runs setup on the replicated geometry (triangles outside its band are dropped before
-    their records are written) and bins / rasterises only its band; strong scaling of a single frame, time = max over
-    ranks; the NCCL gather of the bands to rank 0 is timed separately.  Three splits are timed: equal-height row bands,
-    row bands whose boundaries `mgpu.BandBalancer` moved from the ranks' measured times (a few frames, frozen at the best
-    split found), and equal-width column bands; `ms_per_frame` is the best of them."""
+    (SURVEY 8e).  Strong scaling of a single frame, time = max over ranks.  Every rank drops the batches that cannot
+    touch its rectangle before it loads a vertex of them (k_frame_setup), so the front end is sharded too.  Three splits
+    are timed render-only (the band stays in the rank's HBM): equal-height row bands, row bands whose boundaries
+    `mgpu.BandBalancer` moved from the ranks' measured times, and equal-width column bands.  The two best are then timed
+    DELIVERED: every rank's raster kernel writes its band in place into the full frame in rank 0's memory
+    (rxc_mgpu_rasterize with the frame's row pitch), until rank 0 has seen every rank's completion flag."""
     import torch
     import torch.distributed as dist
     from rusterix_b200 import Rasterizer, mgpu
@@ -445,62 +558,82 @@ def band_split(rank, world, local_rank, dev, flush, barrier, steps=5, warmup=3, 
     out = torch.empty((1, H, W, 4), dtype=torch.uint8, device=dev)   # any band of this rank fits
 
     def prepare(band):
-        y0, y1 = band
-        return Rasterizer.prepare_batch([rast], cfg.scene, W, H, cfg.tile_size, cfg.assets, band=(y0, y1), device=local_rank) if y1 > y0 else None
+        y0, y1 = band[0], band[1]
+        x0, x1 = (band[2], band[3]) if len(band) == 4 else (0, W)
+        return Rasterizer.prepare_batch([rast], cfg.scene, W, H, cfg.tile_size, cfg.assets, band=(y0, y1, x0, x1), device=local_rank) if (y1 > y0 and x1 > x0) else None
 
-    def timed_frame(batch):
+    def timed_frame(run):
         a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
         a.record()
-        if batch is not None:
-            batch.run(out, sync=False)
+        run()
         b.record(); flush.zero_()
         barrier()
         return a.elapsed_time(b)
 
-    def measure(batch):
+    def measure(run):
         for _ in range(warmup):
-            timed_frame(batch)
+            timed_frame(run)
         ms = 0.0
         for _ in range(steps):
-            t = torch.tensor([timed_frame(batch)], dtype=torch.float64, device=dev)
+            t = torch.tensor([timed_frame(run)], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms += float(t.item())
         return ms / steps
 
+    def local_run(batch):
+        return (lambda: batch.run(out, sync=False)) if batch is not None else (lambda: None)
+
     bal = mgpu.BandBalancer(H, world, 32)
-    equal_ms = measure(prepare(bal.band(rank)))
+    equal_ms = measure(local_run(prepare(bal.band(rank))))
     for _ in range(balance_iters):
-        batch = prepare(bal.band(rank))
-        timed_frame(batch)                       # the first frame with new bands may regrow the tile-list arenas
-        bal.update(mgpu.all_gather_times(timed_frame(batch), device=dev))
-    bands = bal.use_best()
-    batch = prepare(bands[rank])
-    rows_ms = measure(batch)
+        run = local_run(prepare(bal.band(rank)))
+        timed_frame(run)                       # the first frame with new bands may regrow the tile-list arenas
+        bal.update(mgpu.all_gather_times(timed_frame(run), device=dev))
+    row_bands = bal.use_best()
+    rbatch = prepare(row_bands[rank])
+    rows_ms = measure(local_run(rbatch))
 
     # column bands (rxc_frame.band_x0/x1): every rank gets an equal-width slice of every tile row, the cheap sky rows and
     # the expensive horizon rows alike, so the split is balanced by construction
-    x0, x1 = mgpu.column_band_for_rank(W, rank, world)
-    cbatch = Rasterizer.prepare_batch([rast], cfg.scene, W, H, cfg.tile_size, cfg.assets, band=(0, H, x0, x1), device=local_rank) if x1 > x0 else None
-    cols_ms = measure(cbatch)
-    mine = out.reshape(-1)[: H * max(0, x1 - x0) * 4].reshape(H, max(0, x1 - x0), 4)
-    for _ in range(2):
-        mgpu.gather_column_bands_to_rank0(mine, H, W, rank, world)
-    barrier()
-    g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
-    g0.record()
-    mgpu.gather_column_bands_to_rank0(mine, H, W, rank, world)
-    g1.record()
-    barrier()
-    t = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    col_bands = [(0, H) + mgpu.column_band_for_rank(W, r, world) for r in range(world)]
+    cbatch = prepare(col_bands[rank])
+    cols_ms = measure(local_run(cbatch))
+
+    # delivered: the band written in place into rank 0's full frame
+    dl.target(W * H * 4)
+
+    def delivered_run(batch, band, regions):
+        y0, y1 = band[0], band[1]
+        x0 = band[2] if len(band) == 4 else 0
+
+        def run():
+            if batch is not None:
+                dl.render(batch, (y0 * W + x0) * 4, pitch_bytes=W * 4)
+            dl.deliver(regions)
+            dl.release()
+        return run
+
+    row_regions = mgpu.band_regions([(y0, y1, 0, W) for y0, y1 in row_bands], W)
+    col_regions = mgpu.band_regions(col_bands, W)
+    rows_del = measure(delivered_run(rbatch, row_bands[rank], row_regions))
+    cols_del = measure(delivered_run(cbatch, col_bands[rank], col_regions))
+    st = dl.status()
     ms = min(cols_ms, rows_ms)
+    ms_del = min(cols_del, rows_del)
+    nv_bytes = (W * H - (col_bands[0][3] - col_bands[0][2]) * H) * 4 if cols_del <= rows_del else (H - (row_bands[0][1] - row_bands[0][0])) * W * 4
     return {"workload": desc + ", split into %d bands" % world, "scaling": "strong", "ms_per_frame": ms,
             "Mpixel_per_s": W * H / (ms * 1e-3) / 1e6, "frames_per_s": 1.0 / (ms * 1e-3),
             "split": "column bands" if cols_ms <= rows_ms else "cost-balanced row bands",
             "column_bands_ms_per_frame": cols_ms, "balanced_row_bands_ms_per_frame": rows_ms, "equal_row_bands_ms_per_frame": equal_ms,
-            "row_band_edges": [b[0] for b in bands] + [H],
+            "row_band_edges": [b[0] for b in row_bands] + [H],
             "row_bands": "cost-balanced from the ranks' measured times (mgpu.BandBalancer, %d frames)" % balance_iters,
-            "gather_ms": float(t.item()), "gather": "column bands to rank 0 (NCCL send/recv)", "bytes_to_rank0": (W - mgpu.column_band_for_rank(W, 0, world)[1]) * H * 4}
+            "delivered": {"ms_per_frame": ms_del, "Mpixel_per_s": W * H / (ms_del * 1e-3) / 1e6, "frames_per_s": 1.0 / (ms_del * 1e-3),
+                          "split": "column bands" if cols_del <= rows_del else "cost-balanced row bands",
+                          "column_bands_ms_per_frame": cols_del, "balanced_row_bands_ms_per_frame": rows_del,
+                          "bytes_to_rank0": nv_bytes, "rank0_ingest_GBps": nv_bytes / (ms_del * 1e-3) / 1e9,
+                          "mode": "peer writes over NVLink (ranks > 0), local stores (rank 0)" if st["mode"] != "nccl" else "nccl send/recv",
+                          "timeouts": st["timeouts"] if rank == 0 else None,
+                          "what": "every rank's k_raster writes its band in place into the 7680x4320 frame in rank 0's memory over NVLink; timed on every rank from the first front-end kernel to its completion flag (rank 0: until it has seen all flags), max over ranks"}}
 
 
 def secondary(wname, local_rank, dev, flush, steps=5, warmup=3):

@@ -375,6 +375,32 @@ int32_t rxc_rasterize_batch_async(rxc_ctx* ctx, const rxc_frame* frames, uint32_
                                   uint64_t frame_stride_bytes);
 int32_t rxc_synchronize(rxc_ctx* ctx);
 
+/* Pre-projected entry (the escape hatch for third-party arithmetic).  Coverage at triangle borders
+ * depends on the exact bits of the projected vertices, i.e. on how vek 0.17 rounds Mat4 * Vec4 -- a crate that is not part
+ * of the reference's sources.  A Rust host can run its own `Scene::project` (src/scene.rs:154-200, i.e.
+ * Batch3D::clip_and_project, src/batch/batch3d.rs:482-740) and hand over what that leaves in every Batch3D; the device then
+ * skips its own view transform / cull / near clip / projection and builds its triangle records from these values verbatim
+ * (edge equations and visibility included), so that ownership is decided by the host's own vertex bits.
+ * One entry per 3D batch of the current scene, in the order of rxc_scene.batches3d.  Owner ids stay comparable: triangle i
+ * of clipped_indices of batch b is rxc_owner_base(b) + i (n_clipped <= 3 * n_triangles of the batch). */
+typedef struct rxc_projected3d {
+    const float* projected_vertices; /* n_projected * [screen x, screen y, z_ndc, w_clip]  (batch3d.rs:689-700)      */
+    const float* clipped_uvs;        /* n_projected * [u, v]                                (batch3d.rs:602-607)      */
+    const float* clipped_normals;    /* n_projected * [x, y, z], or NULL when the batch has no normals                */
+    uint32_t n_projected;
+    uint32_t n_clipped;
+    const void* clipped_indices;     /* n_clipped * 3 indices into projected_vertices, index_bytes wide each          */
+    uint32_t index_bytes;            /* 4 or 8 (Rust usize triples)                                                   */
+    uint32_t has_bounding_box;       /* bounding_box.is_some(); None = the batch is skipped (rasterizer.rs:976-977)   */
+    const float* edges;              /* n_clipped * 9: Edges.a[3], Edges.b[3], Edges.c[3]   (src/edge.rs:3-8)         */
+    const uint8_t* visible;          /* n_clipped: Edges.visible                                                      */
+    float bounding_box[4];           /* Rect x, y, width, height                            (batch3d.rs:762-767)      */
+} rxc_projected3d;
+/* rxc_rasterize with the 3D front end replaced by the host's projection results (2D batches are projected on the device
+ * as usual).  Single frame, synchronous. */
+int32_t rxc_rasterize_projected(rxc_ctx* ctx, const rxc_frame* frame, const rxc_projected3d* batches, uint32_t n_batches,
+                                uint8_t* pixels, uint32_t* owner, float* depth);
+
 /* Page-locks (cudaHostRegister) / releases a host pixel buffer the caller owns -- a Rust `Vec<u8>` that is reused for
  * every frame, say -- so that the frames drain over PCIe by DMA at the pinned rate (about 2.5x the pageable one) and
  * overlap with rendering.  Optional: rxc_rasterize works with pageable memory too.  Unpin before freeing the buffer. */

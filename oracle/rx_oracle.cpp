@@ -1792,6 +1792,25 @@ int32_t rxo_clip_and_project(const rxc_batch3d* batch, const rxc_frame* f, float
     return RXC_OK;
 }
 
+// The attributes clip_and_project leaves next to projected_vertices (batch3d.rs:602-607, :648-681): clipped_uvs and
+// clipped_normals, n_projected entries each (normals: zeros when the batch has none -- the reference would have panicked).
+// Call after rxo_clip_and_project with the same arguments; capacities as there.
+int32_t rxo_clip_and_project_attrs(const rxc_batch3d* batch, const rxc_frame* f, float* clipped_uvs, float* clipped_normals) {
+    Batch3DState s;
+    s.b = batch;
+    M4 view, proj;
+    std::memcpy(view.m, f->view, sizeof(view.m));
+    std::memcpy(proj.m, f->projection, sizeof(proj.m));
+    clip_and_project(s, view, proj, (float)f->width, (float)f->height, f->matvec_mode);
+    for (size_t i = 0; i < s.projected_vertices.size(); ++i) {
+        V2 uv = i < s.clipped_uvs.size() ? s.clipped_uvs[i] : V2{0.0f, 0.0f};
+        V3 n = i < s.clipped_normals.size() ? s.clipped_normals[i] : V3{0.0f, 0.0f, 0.0f};
+        clipped_uvs[i * 2] = uv.x; clipped_uvs[i * 2 + 1] = uv.y;
+        clipped_normals[i * 3] = n.x; clipped_normals[i * 3 + 1] = n.y; clipped_normals[i * 3 + 2] = n.z;
+    }
+    return RXC_OK;
+}
+
 // ---- known-answer-test hooks: each exposes one reference function unchanged ---------------------
 void rxo_edges_new(const float v0[6], const float v1[6], float out_abc[9]) {
     float a[3][2], b[3][2];

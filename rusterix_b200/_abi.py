@@ -223,6 +223,22 @@ class rxc_stats(C.Structure):
     ]
 
 
+class rxc_projected3d(C.Structure):
+    _fields_ = [
+        ("projected_vertices", C.c_void_p),
+        ("clipped_uvs", C.c_void_p),
+        ("clipped_normals", C.c_void_p),
+        ("n_projected", C.c_uint32),
+        ("n_clipped", C.c_uint32),
+        ("clipped_indices", C.c_void_p),
+        ("index_bytes", C.c_uint32),
+        ("has_bounding_box", C.c_uint32),
+        ("edges", C.c_void_p),
+        ("visible", C.c_void_p),
+        ("bounding_box", C.c_float * 4),
+    ]
+
+
 RXC_MGPU_ID_BYTES = 128
 RXC_MGPU_LOCAL, RXC_MGPU_PEER, RXC_MGPU_NCCL = 0, 1, 2
 
@@ -246,6 +262,7 @@ EXPORTS = [
     ("rxc_rasterize_async", C.c_int32, [C.c_void_p, C.POINTER(rxc_frame), C.c_void_p, C.c_void_p, C.c_void_p]),
     ("rxc_rasterize_batch", C.c_int32, [C.c_void_p, C.POINTER(rxc_frame), C.c_uint32, C.c_void_p, C.c_uint64]),
     ("rxc_rasterize_batch_async", C.c_int32, [C.c_void_p, C.POINTER(rxc_frame), C.c_uint32, C.c_void_p, C.c_uint64]),
+    ("rxc_rasterize_projected", C.c_int32, [C.c_void_p, C.POINTER(rxc_frame), C.POINTER(rxc_projected3d), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("rxc_synchronize", C.c_int32, [C.c_void_p]),
     ("rxc_pin_host", C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64]),
     ("rxc_unpin_host", C.c_int32, [C.c_void_p, C.c_void_p]),

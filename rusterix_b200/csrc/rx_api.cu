@@ -96,6 +96,9 @@ struct rxc_ctx {
     std::vector<PendingEvent> pending;
     std::vector<cudaEvent_t> free_events;
     RxMgpu* mgpu = nullptr;       // rxc_mgpu_* state (rx_mgpu.cu)
+    bool pj_active = false;       // rxc_rasterize_projected is running: the front end reads `pj` instead of the geometry
+    ProjectedDev pj = {};
+    DevBuf d_pj_pv, d_pj_uv, d_pj_nrm, d_pj_idx, d_pj_edges, d_pj_info, d_pj_bbox;
     uint32_t async_pending = 0;   // frames of the last asynchronous group whose counters (ctx->h_counters) nobody has looked at yet
 };
 
@@ -410,6 +413,7 @@ int32_t fill_frame(rxc_ctx* ctx, const rxc_frame& f, DFrame* d) {
     }
     d->has_sky = f.has_sky ? 1u : 0u;
     memcpy(d->sky, f.sky, sizeof(d->sky));
+    d->preprojected = ctx->pj_active ? 1u : 0u;
     d->has_brush = f.has_brush_preview ? 1u : 0u;
     memcpy(d->brush_pos, f.brush_position, 12);
     d->brush_radius = f.brush_radius; d->brush_falloff = f.brush_falloff;
@@ -556,17 +560,22 @@ int32_t launch_group(rxc_ctx* ctx, const DFrame* h_frames, DCounters* h_counters
     // tiny scenes (a couple of batches): the seven front-end launches cost more than their work, one CTA per frame
     // runs them back to back (measured: 22 us instead of ~70 us for the cube; from ~5 setup chunks on the serial
     // walk of one CTA loses against the parallel launches)
-    const bool small_front = !S.general && S.n_chunks <= 2 && S.n_b2 <= 4 && tiles_per_frame <= 16384;
+    const bool pj = ctx->pj_active;   // host-projected 3D batches: always the separate kernels
+    const bool small_front = !pj && !S.general && S.n_chunks <= 2 && S.n_b2 <= 4 && tiles_per_frame <= 16384;
     // mid-sized scenes: one cluster of CTAs per frame, cluster barriers instead of kernel boundaries
-    const bool cluster_front = !small_front && ctx->front_cluster_max != 0 && S.n_chunks <= (uint32_t)ctx->front_cluster_max &&
+    const bool cluster_front = !pj && !small_front && ctx->front_cluster_max != 0 && S.n_chunks <= (uint32_t)ctx->front_cluster_max &&
                                S.n_b2 <= 64 && tiles_per_frame <= 65536 && (!S.general || S.n_rec2d <= 512);   // long sorted 2D lists want k_list_sort's CTA per tile (834 records: no gain)
     if (small_front) { LaunchScope l(ctx, RXK_FRONT_SMALL); CK(rxk_front_small(S, ctx->W, n, tiles_per_frame, ctx->stream)); }
     else if (cluster_front) { LaunchScope l(ctx, RXK_FRONT_SMALL); CK(rxk_front_cluster(S, ctx->W, n, tiles_per_frame, (uint32_t)ctx->front_stop, ctx->stream)); }
     else { LaunchScope l(ctx, RXK_FRAME_SETUP); CK(rxk_frame_setup(S, ctx->W, n, tiles_per_frame, ctx->stream)); }
     if (S.n_tris && !small_front && !cluster_front) {
-        { LaunchScope l(ctx, RXK_TRI_SETUP); CK(rxk_tri_setup(S, ctx->W, n, ctx->stream)); }
-        { LaunchScope l(ctx, RXK_BATCH_FINALIZE); CK(rxk_batch_finalize(S, ctx->W, n, ctx->stream)); }
-        { LaunchScope l(ctx, RXK_CLIP_EMIT); CK(rxk_clip_emit(S, ctx->W, n, grid_for(std::min<size_t>(S.n_tris, 65536), 128), ctx->stream)); }
+        if (pj) {
+            LaunchScope l(ctx, RXK_TRI_SETUP); CK(rxk_tri_setup_projected(S, ctx->W, ctx->pj, ctx->stream));
+        } else {
+            { LaunchScope l(ctx, RXK_TRI_SETUP); CK(rxk_tri_setup(S, ctx->W, n, ctx->stream)); }
+            { LaunchScope l(ctx, RXK_BATCH_FINALIZE); CK(rxk_batch_finalize(S, ctx->W, n, ctx->stream)); }
+            { LaunchScope l(ctx, RXK_CLIP_EMIT); CK(rxk_clip_emit(S, ctx->W, n, grid_for(std::min<size_t>(S.n_tris, 65536), 128), ctx->stream)); }
+        }
         { LaunchScope l(ctx, RXK_BIN_COUNT); CK(rxk_bin_count(S, ctx->W, n, grid_for((size_t)S.n_tris + S.n_tris / 8, 256), ctx->stream)); }
         if (S.general) { LaunchScope l(ctx, RXK_BIN_COUNT); CK(rxk_bin_large(S, ctx->W, n, 0, ctx->sm_count, ctx->stream)); }
         { LaunchScope l(ctx, RXK_TILE_ALLOC); CK(rxk_tile_alloc(S, ctx->W, n, tiles_per_frame, 0, S.general ? 1 : 0, ctx->stream)); }
@@ -905,7 +914,8 @@ void rxc_destroy(rxc_ctx* ctx) {
                       &ctx->w_bins, &ctx->w_ctot, &ctx->w_cbase, &ctx->w_clip, &ctx->w_large, &ctx->w_tcount, &ctx->w_tbase,
                       &ctx->w_tfill, &ctx->w_lists, &ctx->w_tri2d, &ctx->w_rcounter, &ctx->d_out_px, &ctx->d_out_owner, &ctx->d_out_depth,
                       &ctx->w_tcount2, &ctx->w_tbase2, &ctx->w_tfill2, &ctx->w_lists2, &ctx->d_sectors, &ctx->d_chunkinfo, &ctx->d_linedefs,
-                      &ctx->d_vm_code, &ctx->d_vm_programs, &ctx->d_vm_patdata, &ctx->d_vm_patterns, &ctx->d_vm_palette};
+                      &ctx->d_vm_code, &ctx->d_vm_programs, &ctx->d_vm_patdata, &ctx->d_vm_patterns, &ctx->d_vm_palette,
+                      &ctx->d_pj_pv, &ctx->d_pj_uv, &ctx->d_pj_nrm, &ctx->d_pj_idx, &ctx->d_pj_edges, &ctx->d_pj_info, &ctx->d_pj_bbox};
     for (DevBuf* b : bufs) free_buf(*b);
     if (ctx->h_frames) cudaFreeHost(ctx->h_frames);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -1069,8 +1079,12 @@ int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
             if (b.normals) memcpy(&nrm[vo * 3], b.normals, (size_t)b.n_vertices * 12);
         }
         float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-        for (uint32_t v = 0; v < b.n_vertices; ++v)
+        bool unit_w = b.n_vertices != 0;
+        for (uint32_t v = 0; v < b.n_vertices; ++v) {
             for (int k = 0; k < 3; ++k) { mn[k] = std::fmin(mn[k], b.vertices[v * 4 + k]); mx[k] = std::fmax(mx[k], b.vertices[v * 4 + k]); }
+            unit_w = unit_w && b.vertices[v * 4 + 3] == 1.0f && std::isfinite(b.vertices[v * 4]) && std::isfinite(b.vertices[v * 4 + 1]) && std::isfinite(b.vertices[v * 4 + 2]);
+        }
+        if (unit_w) d.bflags |= RX_BF_UNIT_W;   // the band reject of whole batches (k_frame_setup) relies on it
         memcpy(d.aabb_min, mn, 12); memcpy(d.aabb_max, mx, 12);
         std::vector<uint8_t> used(b.n_vertices, 0);
         for (size_t k = 0; k < (size_t)b.n_triangles * 3; ++k) {
@@ -1204,6 +1218,69 @@ int32_t rxc_rasterize_batch(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_fr
 int32_t rxc_rasterize_batch_async(rxc_ctx* ctx, const rxc_frame* frames, uint32_t n_frames, uint8_t* pixels, uint64_t frame_stride_bytes) {
     return guarded(ctx, [&]() -> int32_t {
     return rasterize_impl(ctx, frames, n_frames, pixels, frame_stride_bytes, nullptr, nullptr, false);
+    });
+}
+
+int32_t rxc_rasterize_projected(rxc_ctx* ctx, const rxc_frame* frame, const rxc_projected3d* batches, uint32_t n_batches, uint8_t* pixels,
+                                uint32_t* owner, float* depth) {
+    return guarded(ctx, [&]() -> int32_t {
+    if (!ctx) return RXC_ERR_INVALID;
+    if (!frame || !pixels || (n_batches && !batches)) return fail(ctx, RXC_ERR_INVALID, "frame, batches and pixels are required");
+    if (!ctx->have_scene) return fail(ctx, RXC_ERR_INVALID, "rxc_set_scene has not been called");
+    if (n_batches != ctx->h_b3.size()) return fail(ctx, RXC_ERR_INVALID, "rxc_rasterize_projected: one rxc_projected3d per 3D batch of the scene");
+    CK(cudaSetDevice(ctx->device));
+    // ---- validate + flatten (host memory is only borrowed for the call)
+    size_t NP = 0, NC = 0;
+    for (uint32_t b = 0; b < n_batches; ++b) {
+        const rxc_projected3d& q = batches[b];
+        const std::string who = "projected batch " + std::to_string(b) + ": ";
+        if (!q.has_bounding_box) continue;   // skipped altogether, whatever else it holds
+        if (q.index_bytes != 4 && q.index_bytes != 8) return fail(ctx, RXC_ERR_INVALID, who + "index_bytes must be 4 or 8");
+        if ((q.n_projected && (!q.projected_vertices || !q.clipped_uvs)) || (q.n_clipped && (!q.clipped_indices || !q.edges || !q.visible)))
+            return fail(ctx, RXC_ERR_INVALID, who + "null array with non-zero count");
+        if (q.n_clipped > 3ull * ctx->h_b3[b].n_tris) return fail(ctx, RXC_ERR_INVALID, who + "more clipped triangles than 3 per input triangle (batch3d.rs:625-681 emits at most 2 per clipped one)");
+        if ((ctx->h_b3[b].has_normals != 0) != (q.clipped_normals != nullptr) && q.n_projected)
+            return fail(ctx, RXC_ERR_INVALID, who + "clipped_normals must be given exactly when the batch has normals");
+        for (size_t k = 0; k < (size_t)q.n_clipped * 3; ++k)
+            if (idx_at(q.clipped_indices, q.index_bytes, k) >= q.n_projected) return fail(ctx, RXC_ERR_INDEX, who + "clipped index out of range (reference panics)");
+        NP += q.n_projected; NC += q.n_clipped;
+    }
+    std::vector<float> pv(NP * 4), uv(NP * 2), nrm(NP * 3, 0.0f), edges(NC * 9), bbox((size_t)n_batches * 5, 0.0f);
+    std::vector<uint32_t> idx(NC * 3), info(NC * 2);
+    size_t po = 0, co = 0;
+    for (uint32_t b = 0; b < n_batches; ++b) {
+        const rxc_projected3d& q = batches[b];
+        if (!q.has_bounding_box) continue;
+        bbox[(size_t)b * 5] = 1.0f;
+        memcpy(&bbox[(size_t)b * 5 + 1], q.bounding_box, 16);
+        if (q.n_projected) {
+            memcpy(&pv[po * 4], q.projected_vertices, (size_t)q.n_projected * 16);
+            memcpy(&uv[po * 2], q.clipped_uvs, (size_t)q.n_projected * 8);
+            if (q.clipped_normals) memcpy(&nrm[po * 3], q.clipped_normals, (size_t)q.n_projected * 12);
+        }
+        if (q.n_clipped) memcpy(&edges[co * 9], q.edges, (size_t)q.n_clipped * 36);
+        for (uint32_t i = 0; i < q.n_clipped; ++i) {
+            for (int k = 0; k < 3; ++k) idx[(co + i) * 3 + k] = (uint32_t)(po + idx_at(q.clipped_indices, q.index_bytes, (size_t)i * 3 + k));
+            info[(co + i) * 2] = b | (q.visible[i] ? 0x80000000u : 0u);
+            info[(co + i) * 2 + 1] = ctx->owner_base[b] + i;
+        }
+        po += q.n_projected; co += q.n_clipped;
+    }
+    int32_t st;
+    if ((st = upload(ctx, ctx->d_pj_pv, pv.data(), pv.size() * 4)) != RXC_OK) return st;
+    if ((st = upload(ctx, ctx->d_pj_uv, uv.data(), uv.size() * 4)) != RXC_OK) return st;
+    if ((st = upload(ctx, ctx->d_pj_nrm, nrm.data(), nrm.size() * 4)) != RXC_OK) return st;
+    if ((st = upload(ctx, ctx->d_pj_idx, idx.data(), idx.size() * 4)) != RXC_OK) return st;
+    if ((st = upload(ctx, ctx->d_pj_edges, edges.data(), edges.size() * 4)) != RXC_OK) return st;
+    if ((st = upload(ctx, ctx->d_pj_info, info.data(), info.size() * 4)) != RXC_OK) return st;
+    if ((st = upload(ctx, ctx->d_pj_bbox, bbox.data(), bbox.size() * 4)) != RXC_OK) return st;
+    ctx->pj.pv = ctx->d_pj_pv.as<float4>(); ctx->pj.uv = ctx->d_pj_uv.as<float2>(); ctx->pj.nrm = ctx->d_pj_nrm.as<float>();
+    ctx->pj.idx = ctx->d_pj_idx.as<uint32_t>(); ctx->pj.edges = ctx->d_pj_edges.as<float>(); ctx->pj.info = ctx->d_pj_info.as<uint32_t>();
+    ctx->pj.bbox = ctx->d_pj_bbox.as<float>(); ctx->pj.n_clipped = (uint32_t)NC;
+    ctx->pj_active = true;
+    st = rasterize_impl(ctx, frame, 1, pixels, 0, owner, depth, true);
+    ctx->pj_active = false;
+    return st;
     });
 }
 

@@ -52,6 +52,7 @@ struct DBatch3 {         // static per 3D batch (uploaded by rxc_set_scene)
 };
 #define RX_BF_HAS_PROFILE 1u
 #define RX_BF_OPACITY 2u         // a chunk.batches3d_opacity batch (rasterizer.rs:1425-1690)
+#define RX_BF_UNIT_W 4u          // every vertex has w == 1 and finite coordinates: the vertices lie inside the object AABB's hull
 
 struct DBatch2 {         // static per 2D batch
     uint32_t v_off, n_verts;
@@ -230,7 +231,7 @@ struct DFrame {
     uint32_t has_sky, has_brush;
     float sky[6][4];
     float brush_pos[3], brush_radius, brush_falloff;
-    uint32_t pad_t[1];
+    uint32_t preprojected;        // rxc_rasterize_projected: the host's own Scene::project results replace the device front end
 };
 
 // per-frame counters (zeroed by k_frame_setup)

@@ -117,23 +117,11 @@ __device__ int clip_polygon(const f4 vv[3], const float2 uv[3], const f3 nn[3], 
     return n;
 }
 
-// batch3d.rs:706-739 + the per-triangle constants of rasterizer.rs:989-1076.
-// Returns visibility; fills the records and the raw pixel bbox when visible.
-__device__ bool make_tri(const f4 P[3], const float2 uv[3], const f3 nn[3], uint32_t cull_mode, bool edge_vis, int W, int H,
-                         uint32_t meta, TriVis* tv, TriShade* ts, uint32_t* bbx, uint32_t* bby) {
-    const f4 v0 = P[0];
-    f4 v1 = P[1], v2 = P[2];
-    const float orientation = (v1.x - v0.x) * (v2.y - v0.y) - (v1.y - v0.y) * (v2.x - v0.x);  // batch3d.rs:743-746
-    const bool front = orientation > 0.0f;
-    bool visible;
-    bool swap = false;
-    if (cull_mode == RXC_CULL_OFF) { swap = front; visible = true; }
-    else if (cull_mode == RXC_CULL_FRONT) { visible = !front; }
-    else { swap = front; visible = front; }
-    visible = visible && edge_vis;
-    if (!visible) return false;
-    if (swap) { f4 t = v1; v1 = v2; v2 = t; }
-
+// The records of a visible triangle from its unswapped projected vertices and its final edge equations
+// (rasterizer.rs:989-1076: pixel range, barycentric constants, 1/z, uv/w, 1/w).  Returns false when no pixel centre
+// can be visited.
+__device__ bool tri_records(const f4 P[3], const float2 uv[3], const f3 nn[3], const float ea[3], const float eb[3], const float ec[3],
+                            int W, int H, uint32_t meta, TriVis* tv, TriShade* ts, uint32_t* bbx, uint32_t* bby) {
     int x0, x1, y0, y1;
     pixel_range(fminf(P[0].x, fminf(P[1].x, P[2].x)), fmaxf(P[0].x, fmaxf(P[1].x, P[2].x)), W, &x0, &x1);
     pixel_range(fminf(P[0].y, fminf(P[1].y, P[2].y)), fmaxf(P[0].y, fmaxf(P[1].y, P[2].y)), H, &y0, &y1);
@@ -142,9 +130,8 @@ __device__ bool make_tri(const f4 P[3], const float2 uv[3], const f3 nn[3], uint
     *bby = (uint32_t)y0 | ((uint32_t)y1 << 16);
 
     TriVis r;
-    edge_eq(v0.x, v0.y, v1.x, v1.y, &r.ea[0], &r.eb[0], &r.ec[0]);
-    edge_eq(v1.x, v1.y, v2.x, v2.y, &r.ea[1], &r.eb[1], &r.ec[1]);
-    edge_eq(v2.x, v2.y, v0.x, v0.y, &r.ea[2], &r.eb[2], &r.ec[2]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { r.ea[i] = ea[i]; r.eb[i] = eb[i]; r.ec[i] = ec[i]; }
     r.ax = P[0].x; r.ay = P[0].y; r.bx = P[1].x; r.by = P[1].y; r.cx = P[2].x; r.cy = P[2].y;
     const float acx = P[2].x - P[0].x, acy = P[2].y - P[0].y;
     const float abx = P[1].x - P[0].x, aby = P[1].y - P[0].y;
@@ -184,6 +171,30 @@ __device__ bool make_tri(const f4 P[3], const float2 uv[3], const f3 nn[3], uint
     }
     *ts = s;
     return true;
+}
+
+// batch3d.rs:706-739 + the per-triangle constants of rasterizer.rs:989-1076.
+// Returns visibility; fills the records and the raw pixel bbox when visible.
+__device__ bool make_tri(const f4 P[3], const float2 uv[3], const f3 nn[3], uint32_t cull_mode, bool edge_vis, int W, int H,
+                         uint32_t meta, TriVis* tv, TriShade* ts, uint32_t* bbx, uint32_t* bby) {
+    const f4 v0 = P[0];
+    f4 v1 = P[1], v2 = P[2];
+    const float orientation = (v1.x - v0.x) * (v2.y - v0.y) - (v1.y - v0.y) * (v2.x - v0.x);  // batch3d.rs:743-746
+    const bool front = orientation > 0.0f;
+    bool visible;
+    bool swap = false;
+    if (cull_mode == RXC_CULL_OFF) { swap = front; visible = true; }
+    else if (cull_mode == RXC_CULL_FRONT) { visible = !front; }
+    else { swap = front; visible = front; }
+    visible = visible && edge_vis;
+    if (!visible) return false;
+    if (swap) { f4 t = v1; v1 = v2; v2 = t; }
+
+    float ea[3], eb[3], ec[3];
+    edge_eq(v0.x, v0.y, v1.x, v1.y, &ea[0], &eb[0], &ec[0]);
+    edge_eq(v1.x, v1.y, v2.x, v2.y, &ea[1], &eb[1], &ec[1]);
+    edge_eq(v2.x, v2.y, v0.x, v0.y, &ea[2], &eb[2], &ec[2]);
+    return tri_records(P, uv, nn, ea, eb, ec, W, H, meta, tv, ts, bbx, bby);
 }
 
 // record flags of every triangle of a batch: the opacity layer never alpha-tests (rasterizer.rs:1647-1651)
@@ -369,7 +380,7 @@ __device__ __forceinline__ void d_frame_setup(const SceneDev& S, const Workspace
         rx_matmat4(pv, B.transform, mvp, F.matvec_mode);
         rx_matmat4(F.view, B.transform, fb.view_model, F.matvec_mode);  // batch3d.rs:555
         bool rejected = false;
-        if (B.n_verts != 0) {  // batch3d.rs:493-552
+        if (B.n_verts != 0 && !F.preprojected) {  // batch3d.rs:493-552 (pre-projected frames: the host's bounding_box decides, k_tri_setup_projected)
             bool ol = true, orr = true, ob = true, ot = true, on = true, of = true;
             for (int c = 0; c < 8; ++c) {
                 f4 v = {(c & 4) ? B.aabb_max[0] : B.aabb_min[0], (c & 2) ? B.aabb_max[1] : B.aabb_min[1],
@@ -379,6 +390,30 @@ __device__ __forceinline__ void d_frame_setup(const SceneDev& S, const Workspace
                 ol &= r.x < -w; orr &= r.x > w; ob &= r.y < -w; ot &= r.y > w; on &= r.z < -w; of &= r.z > w;
             }
             rejected = ol || orr || ob || ot || on || of;
+        }
+        // Band / rectangle rendering (one rank of a band split): a batch none of whose triangles can touch the rectangle
+        // is dropped here, before k_tri_setup loads a single vertex of it -- this is what shards the front end of a band
+        // split across the ranks.  Conservative: every vertex has w = 1 and lies inside the object AABB (RX_BF_UNIT_W),
+        // all eight corners are in front of the near-clip plane (view z < -0.11: no triangle of the batch is clipped, every
+        // clip w is positive), so every projected vertex is a convex combination of the projected corners; the bounds get
+        // a margin for the rounding of the two different matrix chains.  Only pixels outside the rectangle can differ.
+        const bool sub_rect = F.band_y0 > 0 || F.band_y1 < F.height || F.band_x0 > 0 || F.band_x1 < F.width;
+        if (sub_rect && !rejected && !F.preprojected && (B.bflags & RX_BF_UNIT_W)) {
+            bool front = true;
+            float sx0 = CUDART_INF_F, sx1 = -CUDART_INF_F, sy0 = CUDART_INF_F, sy1 = -CUDART_INF_F;
+            for (int c = 0; c < 8; ++c) {
+                const f4 v = {(c & 4) ? B.aabb_max[0] : B.aabb_min[0], (c & 2) ? B.aabb_max[1] : B.aabb_min[1],
+                              (c & 1) ? B.aabb_max[2] : B.aabb_min[2], 1.0f};
+                const f4 vv = rx_matvec4(fb.view_model, v, F.matvec_mode);
+                const f4 r = rx_matvec4(mvp, v, F.matvec_mode);
+                front = front && vv.z < -0.11f && r.w > 1e-3f;
+                const float x = ((r.x / r.w) * 0.5f + 0.5f) * F.width_f, y = ((-r.y / r.w) * 0.5f + 0.5f) * F.height_f;
+                sx0 = fminf(sx0, x); sx1 = fmaxf(sx1, x); sy0 = fminf(sy0, y); sy1 = fmaxf(sy1, y);
+            }
+            if (front && sx0 == sx0 && sx1 == sx1 && sy0 == sy0 && sy1 == sy1) {
+                const float mx = 2.0f + 1e-4f * fmaxf(fabsf(sx0), fabsf(sx1)), my = 2.0f + 1e-4f * fmaxf(fabsf(sy0), fabsf(sy1));
+                if (sy1 + my < (float)F.band_y0 || sy0 - my > (float)F.band_y1 || sx1 + mx < (float)F.band_x0 || sx0 - mx > (float)F.band_x1) rejected = true;
+            }
         }
         fb.tex = 0xFFFFFFFFu;
         fb.alpha_test = 0;
@@ -576,6 +611,62 @@ __device__ __forceinline__ void d_tri_setup(const SceneDev& S, const Workspace& 
     if (lane == 0 && nvis) atomicAdd(&Wk.counters[f].n_visible, nvis);
 
     block_minmax_to_keys(mm, &FB.bb_minx, &FB.bb_maxx, &FB.bb_miny, &FB.bb_maxy);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_tri_setup_projected : rxc_rasterize_projected.  The host ran Scene::project itself (its own vek arithmetic) and hands
+// over projected_vertices / clipped_indices / clipped_uvs / clipped_normals / edges / bounding_box per batch; one thread
+// per clipped triangle builds the same records k_tri_setup / k_clip_emit build, with the host's edge equations and
+// visibility verbatim; one thread per batch turns bounding_box into the scissor of rasterizer.rs:978-983.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_tri_setup_projected(SceneDev S, Workspace Wk, ProjectedDev Pj) {
+    const DFrame& F = Wk.frames[0];
+    DCounters& C = Wk.counters[0];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < S.n_b3) {
+        DFrameBatch& FB = Wk.fb[i];
+        const float* bb = Pj.bbox + (size_t)i * 5;
+        if (bb[0] == 0.0f) FB.rejected = 1u;   // bounding_box == None: d3_rasterize returns at once (rasterizer.rs:976-977)
+        if (!FB.rejected) {
+            int x0, x1, y0, y1;
+            scissor_1d(bb[1], bb[3], F.width, (int)F.tile_size, 0.0f, &x0, &x1);  // rasterizer.rs:978-983
+            scissor_1d(bb[2], bb[4], F.height, (int)F.tile_size, 0.0f, &y0, &y1);
+            FB.sc_x0 = max(x0, F.band_x0); FB.sc_x1 = min(x1, F.band_x1);
+            FB.sc_y0 = max(y0, F.band_y0); FB.sc_y1 = min(y1, F.band_y1);
+        }
+    }
+    const uint32_t total = max(S.n_tris, Pj.n_clipped);   // k_bin_count streams bins [0, max(n_tris, n_clipped))
+    if (i == 0) C.n_new_slots = Pj.n_clipped > S.n_tris ? Pj.n_clipped - S.n_tris : 0u;
+    if (i >= total) return;
+    TriBin bin = {0u, 0u, 0u, 0u};
+    if (i < Pj.n_clipped) {
+        const uint32_t w0 = Pj.info[2 * i], slot = Pj.info[2 * i + 1];
+        const uint32_t b = w0 & 0x7FFFFFFFu;
+        bin.slot = slot; bin.batch = b;
+        const DFrameBatch& FB = Wk.fb[b];
+        const float* bb = Pj.bbox + (size_t)b * 5;
+        if ((w0 >> 31) && bb[0] != 0.0f && F.d3_active) {
+            const uint32_t i0 = Pj.idx[3 * i], i1 = Pj.idx[3 * i + 1], i2 = Pj.idx[3 * i + 2];
+            const float4 p0 = Pj.pv[i0], p1 = Pj.pv[i1], p2 = Pj.pv[i2];
+            const f4 P[3] = {{p0.x, p0.y, p0.z, p0.w}, {p1.x, p1.y, p1.z, p1.w}, {p2.x, p2.y, p2.z, p2.w}};
+            const float2 uv[3] = {Pj.uv[i0], Pj.uv[i1], Pj.uv[i2]};
+            const f3 nn[3] = {{Pj.nrm[3 * i0], Pj.nrm[3 * i0 + 1], Pj.nrm[3 * i0 + 2]}, {Pj.nrm[3 * i1], Pj.nrm[3 * i1 + 1], Pj.nrm[3 * i1 + 2]},
+                              {Pj.nrm[3 * i2], Pj.nrm[3 * i2 + 1], Pj.nrm[3 * i2 + 2]}};
+            const float* e = Pj.edges + (size_t)i * 9;
+            const float ea[3] = {e[0], e[1], e[2]}, eb[3] = {e[3], e[4], e[5]}, ec[3] = {e[6], e[7], e[8]};
+            TriVis tv; TriShade tsh;
+            uint32_t bbx = 0u, bby = 0u;
+            // a batch whose constant texel can never be written was already marked by k_frame_setup (FB.rejected)
+            if (!FB.rejected && tri_records(P, uv, nn, ea, eb, ec, F.width, F.height, b | tri_meta_flags(FB), &tv, &tsh, &bbx, &bby) &&
+                !((int)(bby >> 16) <= F.band_y0 || (int)(bby & 0xFFFFu) >= F.band_y1 || (int)(bbx >> 16) <= F.band_x0 || (int)(bbx & 0xFFFFu) >= F.band_x1)) {
+                bin.bbx = bbx; bin.bby = bby;
+                Wk.vis[slot] = tv;
+                Wk.shade[slot] = tsh;
+                atomicAdd(&C.n_visible, 1u);
+            }
+        }
+    }
+    Wk.bins[i] = bin;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -2477,6 +2568,13 @@ cudaError_t rxk_tri_setup(const SceneDev& S, const Workspace& W, uint32_t n_fram
     k_tri_setup<<<grid, RX_CHUNK_TRIS, 0, st>>>(S, W);
     return cudaGetLastError();
 }
+cudaError_t rxk_tri_setup_projected(const SceneDev& S, const Workspace& W, const ProjectedDev& P, cudaStream_t st) {
+    const uint32_t n = max(max(S.n_tris, P.n_clipped), S.n_b3);
+    if (n == 0) return cudaSuccess;
+    k_tri_setup_projected<<<(n + 255) / 256, 256, 0, st>>>(S, W, P);
+    return cudaGetLastError();
+}
+
 cudaError_t rxk_batch_finalize(const SceneDev& S, const Workspace& W, uint32_t n_frames, cudaStream_t st) {
     if (S.n_b3 == 0) return cudaSuccess;
     dim3 grid((S.n_b3 + 7) / 8, n_frames);

@@ -71,6 +71,18 @@ struct Workspace {
     uint32_t small_min_tris;                 // scenes with at least this many triangles run the k_raster variant that has the pass (0xFFFFFFFF = never)
 };
 
+// rxc_rasterize_projected: the outputs of the host's own Scene::project (batch3d.rs:482-740), flattened over the batches
+struct ProjectedDev {
+    const float4* pv;        // [NP] projected_vertices (sx, sy, z, w)
+    const float2* uv;        // [NP] clipped_uvs
+    const float* nrm;        // [NP*3] clipped_normals (zeros for batches without normals)
+    const uint32_t* idx;     // [NC*3] clipped_indices, global into pv
+    const float* edges;      // [NC*9] Edges a[3], b[3], c[3]
+    const uint32_t* info;    // [NC*2] batch | visible << 31, record slot (= owner id)
+    const float* bbox;       // [n_b3*5] has_bounding_box, Rect x, y, width, height
+    uint32_t n_clipped;      // NC
+};
+
 struct RasterOut {
     uint8_t* pixels;       // frame f at pixels + f*frame_stride
     uint64_t frame_stride; // bytes
@@ -103,6 +115,8 @@ cudaError_t rxk_front_small(const SceneDev& S, const Workspace& W, uint32_t n_fr
 // stop_phase: 0 = all phases; n = return after the n-th cluster barrier (profiling aid only, the frame is then incomplete)
 cudaError_t rxk_front_cluster(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, uint32_t stop_phase, cudaStream_t st);
 cudaError_t rxk_tri_setup(const SceneDev& S, const Workspace& W, uint32_t n_frames, cudaStream_t st);
+// frame 0 only: records, bins and batch scissors from host-projected data instead of k_tri_setup / k_batch_finalize / k_clip_emit
+cudaError_t rxk_tri_setup_projected(const SceneDev& S, const Workspace& W, const ProjectedDev& P, cudaStream_t st);
 cudaError_t rxk_batch_finalize(const SceneDev& S, const Workspace& W, uint32_t n_frames, cudaStream_t st);
 cudaError_t rxk_clip_emit(const SceneDev& S, const Workspace& W, uint32_t n_frames, int grid, cudaStream_t st);
 cudaError_t rxk_bin_count(const SceneDev& S, const Workspace& W, uint32_t n_frames, int grid, cudaStream_t st);

@@ -317,3 +317,38 @@ def make_frame(rast, scene: Scene, width: int, height: int, tile_size: int, band
         f.brush_position[:] = [float(c) for c in bp.position]
         f.brush_radius, f.brush_falloff = float(bp.radius), float(bp.falloff)
     return f
+
+
+def marshal_projected(projected, index_bytes: int = 4):
+    """rxc_projected3d array from a list (one entry per 3D batch, submission order) of dicts / objects holding what
+    `Scene::project` leaves in a Batch3D: projected_vertices [n,4], clipped_uvs [n,2], clipped_normals [n,3] or None,
+    clipped_indices [m,3], edges [m,9] (a[3], b[3], c[3]), visible [m], bounding_box (x, y, width, height) or None."""
+    n = len(projected)
+    arr = (_abi.rxc_projected3d * max(1, n))()
+    keep = []
+
+    def get(p, k):
+        return p[k] if isinstance(p, dict) else getattr(p, k)
+
+    for i, p in enumerate(projected):
+        pv = np.ascontiguousarray(get(p, "projected_vertices"), dtype=np.float32).reshape(-1, 4)
+        uv = np.ascontiguousarray(get(p, "clipped_uvs"), dtype=np.float32).reshape(-1, 2)
+        nr = get(p, "clipped_normals")
+        nr = None if nr is None else np.ascontiguousarray(nr, dtype=np.float32).reshape(-1, 3)
+        ci = np.ascontiguousarray(get(p, "clipped_indices"), dtype=np.uint64 if index_bytes == 8 else np.uint32).reshape(-1, 3)
+        ed = np.ascontiguousarray(get(p, "edges"), dtype=np.float32).reshape(-1, 9)
+        vi = np.ascontiguousarray(get(p, "visible"), dtype=np.uint8).reshape(-1)
+        bb = get(p, "bounding_box")
+        if len(uv) != len(pv) or (nr is not None and len(nr) != len(pv)) or len(ed) != len(ci) or len(vi) != len(ci):
+            raise ValueError(f"projected batch {i}: array lengths disagree")
+        keep += [pv, uv, nr, ci, ed, vi]
+        a = arr[i]
+        a.projected_vertices, a.clipped_uvs = pv.ctypes.data, uv.ctypes.data
+        a.clipped_normals = nr.ctypes.data if nr is not None else None
+        a.n_projected, a.n_clipped = len(pv), len(ci)
+        a.clipped_indices, a.index_bytes = ci.ctypes.data, index_bytes
+        a.edges, a.visible = ed.ctypes.data, vi.ctypes.data
+        a.has_bounding_box = 0 if bb is None else 1
+        if bb is not None:
+            a.bounding_box[:] = [float(c) for c in bb]
+    return Marshalled(arr, keep)

@@ -278,6 +278,28 @@ class Rasterizer:
         ctx.check(fn(ctx.handle, C.byref(frame), C.c_void_p(p), C.c_void_p(o or 0), C.c_void_p(d or 0)))
         return pixels
 
+    def rasterize_projected(self, scene: Scene, projected, pixels, width: int, height: int, tile_size: int, assets: Assets,
+                            owner=None, depth=None):
+        """The pre-projected entry (rxc_rasterize_projected): like rasterize(), but the 3D batches arrive the way the
+        host's own `Scene::project` left them (src/scene.rs:154-200) -- `projected` holds, per 3D batch in submission
+        order, projected_vertices / clipped_uvs / clipped_normals / clipped_indices / edges / visible / bounding_box
+        (marshal.marshal_projected) -- and the device uses those bits verbatim instead of projecting itself."""
+        self._check_supported()
+        self.prepare_render_graph()
+        self.width, self.height = float(width), float(height)
+        for chunk in scene.chunks.values():
+            scene.dynamic_lights.extend(chunk.lights)
+        ctx = DeviceContext.get(self.device)
+        ctx.upload(scene, assets, self.index_bytes)
+        ctx.set_mapmini(self.mapmini)
+        frame = marshal.make_frame(self, scene, width, height, tile_size, None)
+        m = marshal.marshal_projected(projected)
+        p, _k1 = _buffer_pointer(pixels, width * height * 4)
+        o, _k2 = _buffer_pointer(owner, width * height * 4)
+        d, _k3 = _buffer_pointer(depth, width * height * 4)
+        ctx.check(ctx.lib.rxc_rasterize_projected(ctx.handle, C.byref(frame), m.struct, len(projected), C.c_void_p(p), C.c_void_p(o or 0), C.c_void_p(d or 0)))
+        return pixels
+
     @staticmethod
     def prepare_batch(rasterizers, scene: Scene, width, height, tile_size, assets: Assets, band=None, device=0):
         """Marshal a camera sweep once: uploads the scene if needed and returns a FrameBatch that

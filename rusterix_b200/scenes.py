@@ -21,6 +21,19 @@ from .types import (Assets, BBox, Batch2D, Batch3D, Chunk, CompiledLinedef, Cull
 from . import vekmath
 
 SEED = 0x52555354
+# the reference's own input fixtures (mesh, textures), vendored under tests/golden/reference_assets with their provenance
+REFERENCE_ASSETS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "reference_assets")
+
+
+def reference_asset(name: str) -> str:
+    p = os.path.join(REFERENCE_ASSETS, name)
+    if not os.path.exists(p):
+        raise FileNotFoundError(f"{p}: the vendored reference fixtures are missing")
+    return p
+
+
+def have_reference_assets() -> bool:
+    return os.path.exists(os.path.join(REFERENCE_ASSETS, "teapot.obj"))
 
 
 def splitmix64(n: int, seed: int = SEED) -> np.ndarray:
@@ -179,13 +192,14 @@ def _example_light():
     return Light.new(LightType.Point).with_intensity(1.0).with_color([1.0, 1.0, 0.95]).with_position([2.0, 0.8, 0.0]).compile()
 
 
-def cube(width=800, height=600, tile_size=200, logo_size=1024) -> Config:
-    """Config A (examples/cube.rs:27-90): textured box, CullMode::Off, 1 point light, 200x200 2D rect."""
+def cube(width=800, height=600, tile_size=200, logo_size=1024, real=False) -> Config:
+    """Config A (examples/cube.rs:27-90): textured box, CullMode::Off, 1 point light, 200x200 2D rect.
+    real=True: the texture is the reference's images/logo.png (examples/cube.rs:36) instead of the procedural logo."""
     scene = Scene.from_static(
         [Batch2D.from_rectangle(0.0, 0.0, 200.0, 200.0)],
         [Batch3D.from_box(-0.5, -0.5, -0.5, 1.0, 1.0, 1.0).source(PixelSource.StaticTileIndex(0)).cull_mode(CullMode.Off).with_computed_normals()],
     ).lights_([_example_light()]).background_(VGrayGradientShader())
-    assets = Assets.default().textures([Tile.from_texture(tex_logo(logo_size))])
+    assets = Assets.default().textures([Tile.from_texture(Texture.from_image(reference_asset("logo.png")) if real else tex_logo(logo_size))])
     cam = D3OrbitCamera.new()
     cam.set_parameter_f32("distance", 1.5)
     return Config("cube", scene, assets, width, height, tile_size, SampleMode.Nearest, (0.1,) * 4, cam)
@@ -217,13 +231,17 @@ def lathe_teapot(segs=47, bands=24) -> Batch3D:
     return Batch3D(v, idx, v[:, :2].copy())  # UV defaults to (x, y): src/wavefront.rs:91-101
 
 
-def teapot(width=1920, height=1080, tile_size=60, obj_path=None, logo_size=1024, n_frames=64) -> Config:
-    """Config B (examples/obj.rs:28-83): OBJ mesh, RepeatXY, scaling(.35,-.35,.35), Linear, orbit sweep."""
+def teapot(width=1920, height=1080, tile_size=60, obj_path=None, logo_size=1024, n_frames=64, real=False) -> Config:
+    """Config B (examples/obj.rs:28-83): OBJ mesh, RepeatXY, scaling(.35,-.35,.35), Linear, orbit sweep.
+    real=True: the reference's examples/teapot.obj (1202 vertices, 2256 triangles) and images/logo.png; otherwise a
+    lathe body with the same triangle count and the procedural logo."""
+    if real and obj_path is None:
+        obj_path = reference_asset("teapot.obj")
     mesh = Batch3D.from_obj(obj_path) if obj_path else lathe_teapot()
     mesh = (mesh.source(PixelSource.StaticTileIndex(0)).repeat_mode(RepeatMode.RepeatXY)
             .transform(vekmath.scaling_3d(0.35, -0.35, 0.35)).with_computed_normals())
     scene = Scene.from_static([Batch2D.from_rectangle(0.0, 0.0, 200.0, 200.0)], [mesh]).lights_([_example_light()]).background_(VGrayGradientShader())
-    assets = Assets.default().textures([Tile.from_texture(tex_logo(logo_size))])
+    assets = Assets.default().textures([Tile.from_texture(Texture.from_image(reference_asset("logo.png")) if real else tex_logo(logo_size))])
     cam = D3OrbitCamera.new()
     cam.set_parameter_f32("distance", 1.5)
 
@@ -256,7 +274,12 @@ def _quads_batch(quads):
 MAP_TILES = ["logo", "brickwall", "lightpanel", "fence", "brickfloor", "sky"]
 
 
-def map_assets(logo_size=1024) -> Assets:
+def map_assets(logo_size=1024, real=False) -> Assets:
+    """Tiles of the map scene in the order map_scene() indexes them: logo, brickwall, lightpanel, fence, brickfloor, sky.
+    real=True: the reference's own PNGs (images/logo.png, minigame/*.png) instead of the procedural stand-ins."""
+    if real:
+        return Assets.default().textures([Tile.from_texture(Texture.from_image(reference_asset(n)))
+                                          for n in ("logo.png", "brickwall.png", "lightpanel.png", "fence.png", "brickfloor.png", "sky.png")])
     return Assets.default().textures([
         Tile.from_texture(tex_logo(logo_size)),
         Tile.from_texture(tex_brick(SEED + 2)),
@@ -301,20 +324,20 @@ def _firstp(pos, center):
     return c
 
 
-def map_config(width=3840, height=2160, tile_size=40, logo_size=1024) -> Config:
+def map_config(width=3840, height=2160, tile_size=40, logo_size=1024, real=False) -> Config:
     """Config C (examples/map.rs:62-125): first-person camera inside the room, Nearest, ambient 1."""
     pos = np.array([6.0600824, 1.0, 4.5524735], dtype=np.float32)
     cam = _firstp(pos, pos + np.array([0.03489969, 0.0, 0.99939084], dtype=np.float32))
-    return Config("map", map_scene(), map_assets(logo_size), width, height, tile_size, SampleMode.Nearest, (1.0,) * 4, cam)
+    return Config("map", map_scene(), map_assets(logo_size, real), width, height, tile_size, SampleMode.Nearest, (1.0,) * 4, cam)
 
 
-def sweep(width=1920, height=1080, tile_size=40, n_frames=4096, logo_size=1024) -> Config:
+def sweep(width=1920, height=1080, tile_size=40, n_frames=4096, logo_size=1024, real=False) -> Config:
     """Config E: n_frames views of the map scene on a circle of radius 4 around the room centre."""
     def cams(i):
         th = 2.0 * math.pi * i / n_frames
         return _firstp([7.5 + 4.0 * math.cos(th), 1.0, 7.5 + 4.0 * math.sin(th)], [7.5, 1.0, 7.5])
 
-    return Config("sweep", map_scene(), map_assets(logo_size), width, height, tile_size, SampleMode.Nearest, (1.0,) * 4,
+    return Config("sweep", map_scene(), map_assets(logo_size, real), width, height, tile_size, SampleMode.Nearest, (1.0,) * 4,
                   cams(0), cams, n_frames)
 
 

@@ -33,6 +33,8 @@ def load():
         lib.rxo_clip_and_project.argtypes = [C.POINTER(_abi.rxc_batch3d), C.POINTER(_abi.rxc_frame), C.c_void_p,
                                              C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.POINTER(C.c_uint32), C.c_void_p, C.POINTER(C.c_uint32)]
+        lib.rxo_clip_and_project_attrs.restype = C.c_int32
+        lib.rxo_clip_and_project_attrs.argtypes = [C.POINTER(_abi.rxc_batch3d), C.POINTER(_abi.rxc_frame), C.c_void_p, C.c_void_p]
         lib.rxo_hash_u32.restype = C.c_uint32
         lib.rxo_hash_u32.argtypes = [C.c_uint32]
         lib.rxo_edges_evaluate.restype = C.c_int32
@@ -139,3 +141,33 @@ def clip_and_project(rast, scene, batch_index, width, height):
                              edges.ctypes.data, visible.ctypes.data, C.byref(n_clip), bbox.ctypes.data, C.byref(has_bbox))
     return dict(projected=projected[:n_proj.value], clipped_indices=cidx[:n_clip.value], edges=edges[:n_clip.value],
                 visible=visible[:n_clip.value], bbox=bbox if has_bbox.value else None)
+
+
+def project_scene(rast, scene, assets, width, height, tile_size=40):
+    """What the reference's `Scene::project` (src/scene.rs:154-200) leaves in every 3D batch, computed by the oracle's
+    clip_and_project: a list (submission order) of dicts with projected_vertices, clipped_uvs, clipped_normals (None
+    when the batch has no normals), clipped_indices, edges, visible and bounding_box (None = Option::None).  This is
+    the host-side input of the pre-projected entry (Rasterizer.rasterize_projected)."""
+    lib = load()
+    sc = marshal.marshal_scene(scene, 4, assets)
+    frame = marshal.make_frame(rast, scene, width, height, tile_size)
+    out = []
+    for bi in range(sc.struct.n_batches3d):
+        b = sc.struct.batches3d[bi]
+        nv, nt = b.n_vertices, b.n_triangles
+        projected = np.zeros((nv + 4 * nt + 1, 4), dtype=np.float32)
+        cidx = np.zeros((3 * nt + 1, 3), dtype=np.uint32)
+        edges = np.zeros((3 * nt + 1, 9), dtype=np.float32)
+        visible = np.zeros(3 * nt + 1, dtype=np.uint8)
+        bbox = np.zeros(4, dtype=np.float32)
+        uvs = np.zeros((nv + 4 * nt + 1, 2), dtype=np.float32)
+        nrm = np.zeros((nv + 4 * nt + 1, 3), dtype=np.float32)
+        n_proj, n_clip, has_bbox = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        lib.rxo_clip_and_project(C.byref(b), C.byref(frame), projected.ctypes.data, C.byref(n_proj), cidx.ctypes.data,
+                                 edges.ctypes.data, visible.ctypes.data, C.byref(n_clip), bbox.ctypes.data, C.byref(has_bbox))
+        lib.rxo_clip_and_project_attrs(C.byref(b), C.byref(frame), uvs.ctypes.data, nrm.ctypes.data)
+        out.append(dict(projected_vertices=projected[:n_proj.value].copy(), clipped_uvs=uvs[:n_proj.value].copy(),
+                        clipped_normals=nrm[:n_proj.value].copy() if b.normals else None,
+                        clipped_indices=cidx[:n_clip.value].copy(), edges=edges[:n_clip.value].copy(), visible=visible[:n_clip.value].copy(),
+                        bounding_box=bbox.copy() if has_bbox.value else None))
+    return out

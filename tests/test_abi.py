@@ -28,7 +28,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 
 def test_struct_layout_matches_header():
-    structs = ["rxc_texture", "rxc_tile", "rxc_light", "rxc_batch3d", "rxc_batch2d", "rxc_sector", "rxc_chunk", "rxc_linedef", "rxc_mapmini", "rxc_scene", "rxc_frame", "rxc_stats", "rxc_mgpu_region"]
+    structs = ["rxc_texture", "rxc_tile", "rxc_light", "rxc_batch3d", "rxc_batch2d", "rxc_sector", "rxc_chunk", "rxc_linedef", "rxc_mapmini", "rxc_scene", "rxc_frame", "rxc_stats", "rxc_mgpu_region", "rxc_projected3d"]
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for s in structs:
         cls = getattr(_abi, s)

@@ -27,6 +27,101 @@ def test_cube_800x600_nearest():
     assert st["exact_frac"] > 0.99
 
 
+# ---- the BASELINE.json configs at their full sizes on the reference's own mesh and textures (tests/golden/reference_assets)
+def test_config_a_cube_800x600_tile200_reference_logo():
+    """Config A as the north star words it: 800x600, tile 200, Nearest, images/logo.png at 1024x1024."""
+    st = _run(scenes.cube(800, 600, 200, real=True))
+    assert st["exact_frac"] > 0.99
+
+
+def test_config_a_cube_2000x2000_tile40_as_the_bench_file():
+    """Config A in the shape of the reference's own bench (benches/rasterize_cube.rs:13-14,30): 2000x2000, tile 40."""
+    st = _run(scenes.cube(2000, 2000, 40, real=True))
+    assert st["exact_frac"] > 0.99
+
+
+@pytest.mark.parametrize("frame", [0, 21, 47])
+def test_config_b_teapot_obj_1920x1080_linear(frame):
+    """Config B on examples/teapot.obj itself (1202 vertices, 2256 triangles, UV = (x, y), RepeatXY,
+    scaling(.35, -.35, .35), bilinear sampling of images/logo.png) at 1920x1080, orbit camera."""
+    cfg = scenes.teapot(1920, 1080, 60, real=True)
+    assert cfg.counts() == (1202, 2256)
+    _run(cfg, frame=frame)
+
+
+def test_config_c_map_4k_reference_textures():
+    """Config C with the minigame's own PNGs (brickwall, lightpanel, fence with its alpha holes, brickfloor, sky)."""
+    st = _run(scenes.map_config(3840, 2160, 40, real=True))
+    assert st["within1_frac"] >= 0.999
+
+
+# ---- the pre-projected entry (rxc_rasterize_projected): the host's own Scene::project results, used verbatim --------------
+def _run_projected(cfg, frame=0, host_mode=None, **kw):
+    import oracle_ffi
+
+    r = cfg.rasterizer(frame)
+    for k, v in kw.items():
+        setattr(r, k, v)
+    host = cfg.rasterizer(frame)          # the "host" that ran Scene::project, possibly with another Mat4*Vec4 rounding
+    if host_mode is not None:
+        host.matvec_mode = host_mode
+    proj = oracle_ffi.project_scene(host, cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size)
+    px = np.zeros((cfg.height, cfg.width, 4), dtype=np.uint8)
+    ow = np.zeros((cfg.height, cfg.width), dtype=np.uint32)
+    dp = np.zeros((cfg.height, cfg.width), dtype=np.float32)
+    r.rasterize_projected(cfg.scene, proj, px, cfg.width, cfg.height, cfg.tile_size, cfg.assets, owner=ow, depth=dp)
+    o = render_oracle(host, cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size)
+    return compare((px, ow, dp), o, cfg.name + " (pre-projected)"), (px, ow, dp)
+
+
+@pytest.mark.parametrize("name", ["cube", "teapot", "map", "sweep", "dense", "chunked"])
+def test_preprojected_entry_reproduces_the_oracle_from_its_own_projection(name):
+    """Feed the device what the oracle's clip_and_project produced (projected_vertices, clipped_*, edges, bounding_box):
+    the frame must equal the oracle's own, owner and depth bit for bit -- and the frame the device renders when it
+    projects itself."""
+    cfg = {"cube": lambda: scenes.cube(800, 600, 200, logo_size=256), "teapot": lambda: scenes.teapot(960, 540, 60, real=True),
+           "map": lambda: scenes.map_config(960, 540, 40, logo_size=256), "sweep": lambda: scenes.sweep(640, 360, 40, logo_size=128),
+           "dense": lambda: scenes.dense(1280, 720, 40, patches=8), "chunked": lambda: scenes.chunked_config(960, 540)}[name]()
+    frame = 1024 if name == "sweep" else 3 if name in ("teapot", "chunked") else 0   # the sweep's walls cross the near plane
+    st, got = _run_projected(cfg, frame)
+    own = render_gpu(cfg.rasterizer(frame), cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size)
+    assert np.array_equal(got[1], own[1]) and np.array_equal(got[2].view(np.uint32), own[2].view(np.uint32))
+    if not cfg.scene.chunks:   # every rasterize() call appends the chunk lights again (rasterizer.rs:219-223): colours drift by design
+        assert np.array_equal(got[0], own[0])
+
+
+def test_preprojected_entry_follows_the_hosts_vertex_bits_not_its_own_convention():
+    """The point of the entry: the host projected with ANOTHER Mat4*Vec4 rounding (plain rows) than the device would
+    have used (fused columns, the frame's matvec_mode).  Ownership must follow the host's bits."""
+    cfg = scenes.teapot(960, 540, 60, real=True)
+    a = render_oracle(cfg.rasterizer(7), cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size)
+    host = cfg.rasterizer(7); host.matvec_mode = MatVecMode.PlainRows
+    b = render_oracle(host, cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size)
+    assert (a[2].view(np.uint32) != b[2].view(np.uint32)).any()      # the two conventions do differ on this frame
+    _run_projected(cfg, 7, host_mode=MatVecMode.PlainRows)
+
+
+def test_preprojected_entry_rejects_what_the_reference_would_panic_on():
+    import oracle_ffi
+    from rusterix_b200 import RxcError
+
+    cfg = scenes.cube(320, 240, 40, logo_size=64)
+    r = cfg.rasterizer(0)
+    proj = oracle_ffi.project_scene(r, cfg.scene, cfg.assets, 320, 240, 40)
+    px = np.zeros((240, 320, 4), dtype=np.uint8)
+    with pytest.raises(RxcError):
+        r.rasterize_projected(cfg.scene, proj + proj, px, 320, 240, 40, cfg.assets)       # one entry per 3D batch
+    bad = [dict(p) for p in proj]
+    bad[0]["clipped_indices"] = bad[0]["clipped_indices"].copy(); bad[0]["clipped_indices"][0, 0] = 10 ** 6
+    with pytest.raises(RxcError):
+        r.rasterize_projected(cfg.scene, bad, px, 320, 240, 40, cfg.assets)
+    none = [dict(p, bounding_box=None) for p in proj]                                      # bounding_box None: batch skipped
+    r.rasterize_projected(cfg.scene, none, px, 320, 240, 40, cfg.assets)
+    ow = np.zeros((240, 320), dtype=np.uint32)
+    r.rasterize_projected(cfg.scene, none, px, 320, 240, 40, cfg.assets, owner=ow)
+    assert (ow == 0xFFFFFFFF).all()
+
+
 def test_cube_odd_size_partial_tiles():
     _run(scenes.cube(333, 217, 40, logo_size=128))
 
