@@ -1855,6 +1855,11 @@ void rxo_mat4_mul_vec4(const float m[16], const float v[4], uint32_t mode, float
     V4 r = mat4_mul_vec4(M, {v[0], v[1], v[2], v[3]}, mode);
     std::memcpy(out, &r, 16);
 }
+void rxo_mat4_mul_mat4(const float a[16], const float b[16], uint32_t mode, float out[16]) {
+    M4 A, B; std::memcpy(A.m, a, 64); std::memcpy(B.m, b, 64);
+    M4 R = mat4_mul_mat4(A, B, mode);
+    std::memcpy(out, R.m, 64);
+}
 uint32_t rxo_hardware_threads(void) { return std::max(1u, std::thread::hardware_concurrency()); }
 
 }  // extern "C"

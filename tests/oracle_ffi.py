@@ -47,6 +47,7 @@ def load():
         lib.rxo_shade_background.argtypes = [C.POINTER(_abi.rxc_frame), C.c_float, C.c_float, C.c_void_p]
         lib.rxo_shade_fast_brdf.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.rxo_mat4_mul_vec4.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        lib.rxo_mat4_mul_mat4.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         lib.rxo_hardware_threads.restype = C.c_uint32
         lib.rxo_set_programs.restype = C.c_int32
         lib.rxo_set_programs.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_uint32, C.POINTER(_abi.rxc_pattern), C.c_uint32,
