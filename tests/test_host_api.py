@@ -323,3 +323,101 @@ def test_structural_scene_changes_invalidate_the_device_cache_key():
     k3 = scene.structure_key()
     scene.dynamic_textures.append(scenes.map_assets(16).tile_list[0])
     assert scene.structure_key() != k3
+
+
+def test_marshalling_against_an_independent_walk_of_the_host_objects():
+    """The oracle and the device both receive rxc_scene from marshal.py; a flattening / ordering mistake there would be
+    invisible to every parity test.  This walks the chunked scene a second, deliberately dumb way -- nested loops
+    written straight from src/rasterizer.rs:314-405 (3D), :501-553 (2D) and :219-223 (lights), no helper of marshal.py
+    -- and compares what rxc_scene actually holds: batch order, pass tags, chunk indices, geometry pointers' contents,
+    profile ids, resolved EntityTile / ItemTile sources and the light order after the per-call chunk-light append."""
+    import ctypes as C
+
+    from rusterix_b200 import marshal, scenes
+
+    cfg = scenes.chunked_config(320, 180)
+    scene, assets = cfg.scene, cfg.assets
+    # what Rasterizer::rasterize does before anything else: chunk lights appended to dynamic_lights (:219-223)
+    n_dyn_before = len(scene.dynamic_lights)
+    for chunk in scene.chunks.values():
+        scene.dynamic_lights.extend(chunk.lights)
+
+    expect3, expect2 = [], []          # (batch object, pass tag, chunk index)
+    ci = 0
+    for _key, chunk in scene.chunks.items():
+        for b in chunk.batches3d_opacity:
+            expect3.append((b, 4, ci))                      # :318-329  d3_rasterize_opacity
+        for b in chunk.batches3d:
+            expect3.append((b, 3, ci))                      # :331-343
+        if chunk.terrain_batch3d is not None:
+            expect3.append((chunk.terrain_batch3d, 3, ci))  # :345-356
+        ci += 1
+    for b in scene.d3_static:
+        expect3.append((b, 0, -1))                          # :359-371
+    for b in scene.d3_dynamic:
+        expect3.append((b, 1, -1))                          # :373-385
+    for b in scene.d3_overlay:
+        expect3.append((b, 2, -1))                          # :387-405
+    ci = 0
+    for _key, chunk in scene.chunks.items():
+        for b in chunk.batches2d:
+            expect2.append((b, ci))                         # :503-517
+        if chunk.terrain_batch2d is not None:
+            expect2.append((chunk.terrain_batch2d, ci))     # :519-531
+        ci += 1
+    for b in scene.d2_static:
+        expect2.append((b, -1))                             # :534-543
+    for b in scene.d2_dynamic:
+        expect2.append((b, -1))                             # :545-553
+    expect_lights = list(scene.lights) + list(scene.dynamic_lights)
+
+    m = marshal.marshal_scene(scene, 4, assets)
+    s = m.struct
+    assert s.n_batches3d == len(expect3) and s.n_batches2d == len(expect2) and s.n_chunks == len(scene.chunks)
+    assert len(scene.dynamic_lights) == n_dyn_before + sum(len(c.lights) for c in scene.chunks.values())
+
+    def floats(ptr, n):
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), (n,)).copy() if n else np.zeros(0, np.float32)
+
+    def actor_bytes(index):
+        t = s.actor_tiles[index].textures[0]
+        return bytes(C.string_at(t.data, t.width * t.height * 4)), t.width, t.height
+
+    for i, (b, tag, chunk_index) in enumerate(expect3):
+        o = s.batches3d[i]
+        assert (o.pass_, o.chunk) == (tag, chunk_index), i
+        assert o.n_vertices == len(b.vertices) and o.n_triangles == len(b.indices), i
+        assert np.array_equal(floats(o.vertices, o.n_vertices * 4), np.asarray(b.vertices, np.float32).reshape(-1)), i
+        assert np.array_equal(floats(o.uvs, o.n_vertices * 2), np.asarray(b.uvs, np.float32).reshape(-1)), i
+        assert (o.has_profile_id, o.profile_id) == ((0, 0) if b.profile_id_ is None else (1, b.profile_id_)), i
+        assert np.array_equal(np.asarray(list(o.transform), np.float32).reshape(4, 4).T, np.asarray(b.transform_3d, np.float32)), i   # column-major
+        src = b.source_
+        assert o.source_kind == int(src.kind), i
+        if src.name in ("EntityTile", "ItemTile"):       # resolved on the host: assets.entity_tiles[id].get_index(index) (:1130-1177)
+            table = assets.entity_tiles if src.name == "EntityTile" else assets.item_tiles
+            seq = table.get(src.ident)
+            if seq is None or not (0 <= src.index < len(seq)):
+                assert o.source_index == 0xFFFFFFFF, i
+            else:
+                tex = seq[src.index][1].textures[0]
+                assert actor_bytes(o.source_index) == (tex.data.tobytes(), tex.width, tex.height), i
+        elif src.name in ("StaticTileIndex", "DynamicTileIndex"):
+            assert o.source_index == src.index, i
+    for i, (b, chunk_index) in enumerate(expect2):
+        o = s.batches2d[i]
+        assert o.chunk == chunk_index and o.mode == int(b.mode) and o.n_vertices == len(b.vertices), i
+        assert np.array_equal(floats(o.vertices, o.n_vertices * 2), np.asarray(b.vertices, np.float32).reshape(-1)), i
+    assert s.n_lights == len(expect_lights)
+    for i, l in enumerate(expect_lights):
+        o = s.lights[i]
+        assert o.light_type == int(l.light_type) and tuple(o.position) == tuple(np.float32(c) for c in l.position), i
+        assert o.intensity == np.float32(l.intensity) and o.end_distance == np.float32(l.end_distance), i
+    # chunk members: origin, size, sectors in order, terrain texture bytes
+    for k, chunk in enumerate(scene.chunks.values()):
+        c = s.chunks[k]
+        assert tuple(c.origin) == tuple(chunk.origin) and c.size == chunk.size and c.n_occluded_sectors == len(chunk.occluded_sectors)
+        for j, (bbox, occ) in enumerate(chunk.occluded_sectors):
+            q = c.occluded_sectors[j]
+            assert (tuple(q.min), tuple(q.max), q.occlusion) == (tuple(np.float32(v) for v in bbox.min), tuple(np.float32(v) for v in bbox.max), np.float32(occ))
+        tt = c.terrain_texture.contents
+        assert bytes(C.string_at(tt.data, tt.width * tt.height * 4)) == chunk.terrain_texture.data.tobytes()
