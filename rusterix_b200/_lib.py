@@ -7,7 +7,7 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librxcuda.so")
+LIB_PATH = os.environ.get("RXC_LIB") or os.path.join(_HERE, "librxcuda.so")   # RXC_LIB: an experiment build (build.py, RX_BUILD_TAG)
 _lib = None
 
 

@@ -8,7 +8,10 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
-LIB = os.path.join(_HERE, "librxcuda.so")
+# experiments: RX_BUILD_TAG=tma RX_NVCC_EXTRA=-DRX_TMA_STORE=1 builds librxcuda_tma.so next to the shipped library
+# (load it with RXC_LIB=<path>, rusterix_b200/_lib.py)
+_TAG = os.environ.get("RX_BUILD_TAG", "")
+LIB = os.path.join(_HERE, "librxcuda%s.so" % (("_" + _TAG) if _TAG else ""))
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -46,7 +49,7 @@ def build_cuda(force=False, verbose=False):
     headers.append(os.path.join(ROOT, "include", "rxcuda.h"))
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     extra = os.environ.get("RX_NVCC_EXTRA", "").split()  # experiments only, e.g. -DRX_RASTER_MIN_BLOCKS=4
-    objdir = os.path.join(CSRC, "_obj")
+    objdir = os.path.join(CSRC, "_obj" + (("_" + _TAG) if _TAG else ""))
     os.makedirs(objdir, exist_ok=True)
     tag = os.path.join(objdir, "flags.txt")   # objects built with other flags are stale
     flags_now = " ".join(NVCC_FLAGS + extra)

@@ -81,6 +81,7 @@ struct rxc_ctx {
     int raster_blocks_per_sm = 1;
     int piece_mb = 8;             // host output: small frames are rendered and drained in groups of about this size
     int slice_mb = 4;             // host output: large frames are rendered and drained in slices of about this size (0 = whole frames)
+    int tma_store = 1;            // RX_TMA_STORE builds: tiles leave through the tensor-map store (RXC_TMA_STORE=0 switches back to STG.128)
     int front_stop = 0;           // profiling aid: k_front_cluster leaves after this many phases (RXC_FRONT_STOP)
     int small_min_list = RX_SMALL_MIN_LIST, small_max_pix = RX_SMALL_MAX_PIX, small_min_tris = RX_SMALL_MIN_TRIS, small_gshift = RX_SMALL_GSHIFT;   // k_raster: thread-per-record pass of tile lists at least this long, for boxes up to this many pixels
     int front_cluster_max = 64;   // setup chunks up to which the front end runs as one cluster per frame (0 = never)
@@ -112,6 +113,33 @@ namespace {
             return RXC_ERR_CUDA;                                                                   \
         }                                                                                          \
     } while (0)
+
+#if RX_TMA_STORE
+// The pixel buffer of a launch as a 3-D tensor (x, y, frame) of 32-bit pixels, tiled 32 x 32 x 1 with the 128 B shared-memory
+// swizzle k_raster writes its tile in.  cuTensorMapEncodeTiled is a driver entry point: resolved through the runtime, so
+// the library keeps no link-time dependency on libcuda.
+bool encode_pixel_tensor_map(CUtensorMap* map, uint8_t* d_pixels, uint32_t cols, uint32_t rows, uint32_t pitch_px, uint32_t n_frames, uint64_t frame_stride) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) encode = (EncodeFn)fn;
+        else cudaGetLastError();
+    }
+    if (!encode) return false;
+    if (n_frames > 1 && (frame_stride & 15)) return false;
+    const cuuint64_t dims[3] = {cols, rows, n_frames};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch_px * 4, n_frames > 1 ? frame_stride : (cuuint64_t)pitch_px * 4 * rows};
+    const cuuint32_t box[3] = {RX_TILE_W, RX_TILE_H, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, d_pixels, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+#endif
 
 int32_t fail(rxc_ctx* ctx, int32_t code, const std::string& msg) {
     ctx->err = msg;
@@ -330,6 +358,7 @@ int32_t ensure_workspace(rxc_ctx* ctx, uint32_t n_frames, uint32_t tiles_per_fra
     W.clip = ctx->w_clip.as<DClip>(); W.clip_stride = (uint32_t)std::max<size_t>(1, T);
     W.small_min_list = (uint32_t)std::max(1, ctx->small_min_list); W.small_max_pix = (uint32_t)ctx->small_max_pix;
     W.small_gshift = (uint32_t)ctx->small_gshift;
+    W.neg_zero = -0.0f;
     W.small_min_tris = ctx->small_min_list > 0 ? (uint32_t)std::max(0, ctx->small_min_tris) : 0xFFFFFFFFu;
     W.large = ctx->w_large.as<uint32_t>(); W.large_stride = (uint32_t)std::max<size_t>(1, 3 * T);
     W.tile_count = ctx->w_tcount.as<uint32_t>();
@@ -593,6 +622,13 @@ int32_t launch_group(rxc_ctx* ctx, const DFrame* h_frames, DCounters* h_counters
     out.pixels = d_pixels; out.frame_stride = stride; out.owner = d_owner; out.depth = d_depth;
     out.pitch = pitch_px ? pitch_px : (uint32_t)(h_frames[0].band_x1 - h_frames[0].band_x0);
     out.vec_store = (((uintptr_t)d_pixels & 15) == 0 && (stride & 15) == 0 && ((out.pitch * 4) & 15) == 0) ? 1u : 0u;
+    out.tma_store = 0u;
+    memset(&out.tmap, 0, sizeof(out.tmap));
+#if RX_TMA_STORE
+    if (ctx->tma_store && out.vec_store && !d_owner && !d_depth)
+        out.tma_store = encode_pixel_tensor_map(&out.tmap, d_pixels, (uint32_t)(h_frames[0].band_x1 - h_frames[0].band_x0),
+                                                (uint32_t)(h_frames[0].band_y1 - h_frames[0].band_y0), out.pitch, n, stride) ? 1u : 0u;
+#endif
     int sample_mode = (int)h_frames[0].sample_mode;
     for (uint32_t i = 1; i < n; ++i) if ((int)h_frames[i].sample_mode != sample_mode) sample_mode = 2;
     const uint32_t tiles_x = (uint32_t)h_frames[0].tiles_x, tiles_y = (uint32_t)h_frames[0].tiles_y;
@@ -892,6 +928,7 @@ int32_t rxc_create(int32_t device, rxc_ctx** out) {
     ctx->raster_blocks_per_sm = rxk_raster_blocks_per_sm();
     if (const char* e = getenv("RXC_PIECE_MB")) ctx->piece_mb = std::max(1, atoi(e));
     if (const char* e = getenv("RXC_SLICE_MB")) ctx->slice_mb = std::max(0, atoi(e));
+    if (const char* e = getenv("RXC_TMA_STORE")) ctx->tma_store = atoi(e);
     if (const char* e = getenv("RXC_FRONT_STOP")) ctx->front_stop = std::max(0, atoi(e));
     if (const char* e = getenv("RXC_SMALL_MIN_LIST")) ctx->small_min_list = atoi(e);   // 0 = pass off
     if (const char* e = getenv("RXC_SMALL_GSHIFT")) ctx->small_gshift = std::min(5, std::max(0, atoi(e)));

@@ -12,6 +12,12 @@
 #define RX_TILE_W 32             // screen tile of one raster CTA
 #define RX_TILE_H 32
 #define RX_TILE_THREADS 256       // 8 warps; warp w owns a 16x8 region, every thread 2x2 pixels of it (stride 8, 4)
+#ifndef RX_DX
+#define RX_DX 8            // a thread's 2x2 pixels: (x, x + RX_DX) x (y, y + 4).  8: at a given k the 32 lanes of a warp cover a compact
+                           // 8x4 block (coherent coverage, textures and light culls).  1 (horizontally adjacent pairs, which the
+                           // packed pair shade needs) was measured: teapot +50 %, dense 8K +23 %, map 4K +10 % -- a small triangle's
+                           // footprint then spreads over twice the k iterations at half the lane utilisation
+#endif
 #define RX_REGION_W 16
 #define RX_REGION_H 8
 #define RX_CHUNK_TRIS 256          // triangles of one batch handled by one setup CTA
@@ -332,6 +338,34 @@ __device__ __forceinline__ float rx_div_by(float a, float b, float rb) {
     q = __fmaf_rn(r, rb, q);
     r = __fmaf_rn(-b, q, a);
     return __fmaf_rn(r, rb, q);
+}
+
+// ---- packed fp32 (sm_100 FFMA2 / FMUL2 / FADD2: one issue slot for two lanes of fp32) -------------------------------
+// The coverage / depth arithmetic is one rounded IEEE operation per reference operation, never contracted.  For the
+// scalar code -fmad=false guarantees that.  ptxas does NOT extend the guarantee to packed operations: a mul.rn.f32x2
+// followed by an add.rn.f32x2 (or an fma.rn.f32x2 it recognises as one of those) is contracted into FFMA2 whatever
+// --fmad says (checked in SASS).  So every packed PRODUCT that feeds a sum is issued as a true fused multiply-add with
+// the addend -0.0 held in a register the compiler cannot see through (a kernel argument): RN(a*b + (-0)) == RN(a*b)
+// bit for bit (a zero product keeps its sign: (+0) + (-0) = +0, (-0) + (-0) = -0), and an FFMA2 cannot be contracted
+// with the FADD2 that consumes it.  Sums and differences are fma(a, +-1, b), exact by construction.
+__device__ __forceinline__ float2 rx_fma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{\n .reg .b64 ra, rb, rc, rd;\n mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n mov.b64 rc, {%6, %7};\n fma.rn.f32x2 rd, ra, rb, rc;\n mov.b64 {%0, %1}, rd;\n}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 rx_bc2(float s) { return make_float2(s, s); }
+__device__ __forceinline__ float2 rx_mul2(float2 a, float2 b, float nz) { return rx_fma2(a, b, rx_bc2(nz)); }       // RN(a*b), nz = -0.0f (opaque)
+__device__ __forceinline__ float2 rx_add2(float2 a, float2 b) { return rx_fma2(a, rx_bc2(1.0f), b); }                // RN(a+b)
+__device__ __forceinline__ float2 rx_sub2(float2 a, float2 b) { return rx_fma2(b, rx_bc2(-1.0f), a); }               // RN(a-b)
+__device__ __forceinline__ float rx_mul1(float a, float b, float nz) { return __fmaf_rn(a, b, nz); }                 // scalar product that may feed a packed sum
+// rx_div_by on two numerators
+__device__ __forceinline__ float2 rx_div_by2(float2 a, float b, float rb, float nz) {
+    float2 q = rx_mul2(a, rx_bc2(rb), nz);
+    float2 r = rx_fma2(q, rx_bc2(-b), a);
+    q = rx_fma2(r, rx_bc2(rb), q);
+    r = rx_fma2(q, rx_bc2(-b), a);
+    return rx_fma2(r, rx_bc2(rb), q);
 }
 
 __device__ __forceinline__ float rx_clamp(float x, float lo, float hi) {  // Rust f32::clamp (NaN stays)

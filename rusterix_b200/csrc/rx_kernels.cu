@@ -1083,10 +1083,21 @@ __global__ void __launch_bounds__(256) k_front_cluster(SceneDev S, Workspace Wk,
 #define RX_BULK_STORE 0   // 1: finished tiles leave shared memory through the bulk-copy (TMA) engine, 32 x cp.async.bulk of one
                           // 128 B row per tile.  Measured slower than 256 x STG.128 (map 4K 1.41 -> 1.50 ms): off.
 #endif
+#ifndef RX_PACKED_SHADE
+#define RX_PACKED_SHADE 0       // deferred shade of two adjacent pixels of one triangle per packed fp32 instruction (shade_owner_pair, needs
+                                // RX_DX = 1).  Measured and rejected: the instruction count did not move (map 4K 1.173e9 vs 1.178e9 warp
+                                // instructions) and the kernel slowed down 11 % on top of the RX_DX = 1 layout's own loss
+#endif
+#ifndef RX_PACKED_FRAGMENTS
+#define RX_PACKED_FRAGMENTS 0   // barycentrics / depth of two pixels per packed fp32 instruction (test_fragment_pair: FFMA2 / FADD2, bit-exact --
+                                // all GPU parity tests pass with it).  Measured and rejected: -3.7 % instructions but only -1.9 % time on map 4K
+                                // when every covered pair takes it (teapot +3 %, dense 8K +2 %: half-covered pairs do double work), and
+                                // +8 % on map 4K when half-covered pairs fall back to the scalar test (two code paths, 32 B more spills)
+#endif
 #define RX_LARGE_CACHE 160   // large-triangle records kept in shared memory across the tiles of a frame
 #define RX_COLOR_STRIDE 40   // words per tile row in shared memory: the 4 rows a warp writes hit disjoint banks
 
-// Visibility state of the 2x2 pixels of a thread: pixel k is (px0 + 8*(k&1), py0 + 4*(k>>1)).
+// Visibility state of the 2x2 pixels of a thread: pixel k is (px0 + RX_DX*(k&1), py0 + 4*(k>>1)).
 struct Vis4 {
     float z[4];
     uint32_t own[4];     // owner slot
@@ -1419,6 +1430,137 @@ __device__ __forceinline__ uint32_t shade_owner(const SceneDev& S, const ShadeCo
     const uint32_t a8 = texel >> 24;  // f32_to_u8_saturated(a / 255) == a for every u8 a
     return fast_u8(l2s(lit.x)) | (fast_u8(l2s(lit.y)) << 8) | (fast_u8(l2s(lit.z)) << 16) | (a8 << 24);
 }
+
+// shade_owner for TWO horizontally adjacent pixels (fpx, fpx + 1; same y) owned by the SAME triangle, in packed fp32
+// (FFMA2 / FMUL2 / FADD2: one issue slot per two pixels): the same formulas in the same order as shade_owner, lane by
+// lane; only the texel fetches, the table look-ups, the SFU calls and the per-light radiance stay scalar.  The caller
+// takes this path for lit, textured-or-constant, non-terrain owners with vertex normals when neither the sun nor sector
+// occlusion is in play (everything else goes through shade_owner pixel by pixel).  nz = -0.0f (see rx_mul2).
+#if RX_PACKED_SHADE
+__device__ __forceinline__ uint2 shade_owner_pair(const SceneDev& S, const ShadeConst& K, const DLight* lights, const float* kd_lut,
+                                                  const DFrameBatch& FB, const TriShade* __restrict__ shp, float2 alpha, float2 beta, float2 z,
+                                                  float fpx, float fpy, uint32_t sample_mode, float nz) {
+    const float4* sq = reinterpret_cast<const float4*>(shp);
+    const float4 s0 = __ldg(sq), s1 = __ldg(sq + 1), s2 = __ldg(sq + 2);
+    const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(&FB.sd_tex_word));
+    const float4 d1 = __ldg(reinterpret_cast<const float4*>(&FB.sd_ambient[0]));
+    const uint32_t flags = d0.z;
+    const float2 gamma = rx_sub2(rx_sub2(rx_bc2(1.0f), alpha), beta);
+    const float2 X = make_float2(fpx, fpx + 1.0f);
+
+    uint32_t texel0 = d0.w, texel1 = d0.w;
+    if (flags & RX_SD_TEXTURED) {   // the reference's own unfused sums (see shade_owner), two pixels per instruction
+        const float2 iu = rx_add2(rx_add2(rx_mul2(alpha, rx_bc2(s0.x), nz), rx_mul2(beta, rx_bc2(s0.z), nz)), rx_mul2(gamma, rx_bc2(s1.x), nz));
+        const float2 iv = rx_add2(rx_add2(rx_mul2(alpha, rx_bc2(s0.y), nz), rx_mul2(beta, rx_bc2(s0.w), nz)), rx_mul2(gamma, rx_bc2(s1.y), nz));
+        const float2 irw = rx_add2(rx_add2(rx_mul2(alpha, rx_bc2(s1.z), nz), rx_mul2(beta, rx_bc2(s1.w), nz)), rx_mul2(gamma, rx_bc2(s2.x), nz));
+        const float2 rr = make_float2(fast_rcp(irw.x), fast_rcp(irw.y));
+        const float2 nirw = make_float2(-irw.x, -irw.y);
+        float2 u = rx_fma2(iu, rr, rx_bc2(-0.0f)), v = rx_fma2(iv, rr, rx_bc2(-0.0f));
+        u = rx_fma2(rx_fma2(nirw, u, iu), rr, u);
+        v = rx_fma2(rx_fma2(nirw, v, iv), rr, v);
+        const uint32_t* tex = reinterpret_cast<const uint32_t*>(S.arena) + d0.x;
+        const int W = (int)(d0.y & 0xFFFFu), H = (int)(d0.y >> 16);
+        const bool rpx = (flags & RX_SD_REPEAT_X) != 0u, rpy = (flags & RX_SD_REPEAT_Y) != 0u;
+        if (sample_mode == RXC_SAMPLE_NEAREST) { texel0 = sample_nearest_fast(tex, W, H, u.x, v.x, rpx, rpy); texel1 = sample_nearest_fast(tex, W, H, u.y, v.y, rpx, rpy); }
+        else { texel0 = sample_linear_fast(tex, W, H, u.x, v.x, rpx, rpy); texel1 = sample_linear_fast(tex, W, H, u.y, v.y, rpx, rpy); }
+    }
+
+    // screen_to_world folded into one projective map (DFrame::s2w)
+    const float4 m0 = *reinterpret_cast<const float4*>(&K.s2w[0]), m1 = *reinterpret_cast<const float4*>(&K.s2w[4]);
+    const float4 m2 = *reinterpret_cast<const float4*>(&K.s2w[8]), m3 = *reinterpret_cast<const float4*>(&K.s2w[12]);
+    const float4 kc = *reinterpret_cast<const float4*>(&K.cam[0]), ka = *reinterpret_cast<const float4*>(&K.ambient[0]);
+    const float2 Y = rx_bc2(fpy);
+    const float2 hx = rx_fma2(rx_bc2(m0.z), z, rx_fma2(rx_bc2(m0.y), Y, rx_fma2(rx_bc2(m0.x), X, rx_bc2(m0.w))));
+    const float2 hy = rx_fma2(rx_bc2(m1.z), z, rx_fma2(rx_bc2(m1.y), Y, rx_fma2(rx_bc2(m1.x), X, rx_bc2(m1.w))));
+    const float2 hz = rx_fma2(rx_bc2(m2.z), z, rx_fma2(rx_bc2(m2.y), Y, rx_fma2(rx_bc2(m2.x), X, rx_bc2(m2.w))));
+    const float2 hw = rx_fma2(rx_bc2(m3.z), z, rx_fma2(rx_bc2(m3.y), Y, rx_fma2(rx_bc2(m3.x), X, rx_bc2(m3.w))));
+    const float2 ihw = make_float2(fast_rcp(hw.x), fast_rcp(hw.y));
+    const float2 zero2 = rx_bc2(-0.0f);
+    const float2 wx = rx_fma2(hx, ihw, zero2), wy = rx_fma2(hy, ihw, zero2), wz = rx_fma2(hz, ihw, zero2);
+    // view_dir = normalize(cam - world)
+    float2 vx = rx_sub2(rx_bc2(kc.x), wx), vy = rx_sub2(rx_bc2(kc.y), wy), vz = rx_sub2(rx_bc2(kc.z), wz);
+    {
+        const float2 dd = rx_fma2(vx, vx, rx_fma2(vy, vy, rx_fma2(vz, vz, zero2)));
+        const float2 iv2 = make_float2(fast_rsqrt(dd.x), fast_rsqrt(dd.y));
+        vx = rx_fma2(vx, iv2, zero2); vy = rx_fma2(vy, iv2, zero2); vz = rx_fma2(vz, iv2, zero2);
+    }
+    // normal (rasterizer.rs:1083-1099); the caller guarantees RX_SD_NORMALS
+    float2 nx, ny, nzv;
+    {
+        const float4 s4 = __ldg(sq + 4);
+        if (__float_as_uint(s4.z) != 0u) {
+            nx = rx_bc2(s2.y); ny = rx_bc2(s2.z); nzv = rx_bc2(s2.w);
+        } else {
+            const float4 s3 = __ldg(sq + 3);
+            nx = rx_fma2(rx_bc2(s3.w), gamma, rx_fma2(rx_bc2(s3.x), beta, rx_fma2(alpha, rx_bc2(s2.y), zero2)));
+            ny = rx_fma2(rx_bc2(s4.x), gamma, rx_fma2(rx_bc2(s3.y), beta, rx_fma2(alpha, rx_bc2(s2.z), zero2)));
+            nzv = rx_fma2(rx_bc2(s4.y), gamma, rx_fma2(rx_bc2(s3.z), beta, rx_fma2(alpha, rx_bc2(s2.w), zero2)));
+            const float2 nn = rx_fma2(nx, nx, rx_fma2(ny, ny, rx_fma2(nzv, nzv, zero2)));
+            const float2 inn = make_float2(fast_rsqrt(nn.x), fast_rsqrt(nn.y));
+            nx = rx_fma2(nx, inn, zero2); ny = rx_fma2(ny, inn, zero2); nzv = rx_fma2(nzv, inn, zero2);
+        }
+        const float2 ndv = rx_fma2(nx, vx, rx_fma2(ny, vy, rx_fma2(nzv, vz, zero2)));
+        const float2 sg = make_float2(ndv.x < 0.0f ? -1.0f : 1.0f, ndv.y < 0.0f ? -1.0f : 1.0f);   // face the camera
+        nx = rx_fma2(nx, sg, zero2); ny = rx_fma2(ny, sg, zero2); nzv = rx_fma2(nzv, sg, zero2);
+    }
+    const float2 kdr = make_float2(kd_lut[texel0 & 0xFFu], kd_lut[texel1 & 0xFFu]);
+    const float2 kdg = make_float2(kd_lut[(texel0 >> 8) & 0xFFu], kd_lut[(texel1 >> 8) & 0xFFu]);
+    const float2 kdb = make_float2(kd_lut[(texel0 >> 16) & 0xFFu], kd_lut[(texel1 >> 16) & 0xFFu]);
+    const float2 hemi = rx_fma2(rx_bc2(0.5f), ny, rx_bc2(0.5f));
+    f3 amb = {d1.x, d1.y, d1.z};
+    if (K.has_ambient) amb = {ka.x + amb.x, ka.y + amb.y, ka.z + amb.z};   // occlusion is 1 on this path
+    float2 lr = rx_fma2(rx_fma2(kdr, rx_bc2(amb.x), zero2), hemi, zero2);
+    float2 lg = rx_fma2(rx_fma2(kdg, rx_bc2(amb.y), zero2), hemi, zero2);
+    float2 lb = rx_fma2(rx_fma2(kdb, rx_bc2(amb.z), zero2), hemi, zero2);
+
+    float2 fr;
+    {
+        const float2 d = rx_fma2(nx, vx, rx_fma2(ny, vy, rx_fma2(nzv, vz, zero2)));
+        const float2 om = make_float2(1.0f - fminf(fmaxf(d.x, 0.0f), 1.0f), 1.0f - fminf(fmaxf(d.y, 0.0f), 1.0f));
+        const float2 om2 = rx_fma2(om, om, zero2);
+        fr = rx_fma2(rx_bc2(1.0f - 0.04f), rx_fma2(rx_fma2(om2, om2, zero2), om, zero2), rx_bc2(0.04f));
+    }
+    const uint32_t n_lights = __float_as_uint(ka.w);
+    for (uint32_t li = 0; li < n_lights; ++li) {  // rasterizer.rs:1373-1391
+        const DLight& L = lights[li];
+        const float2 tx = rx_sub2(rx_bc2(L.px), wx), ty = rx_sub2(rx_bc2(L.py), wy), tz = rx_sub2(rx_bc2(L.pz), wz);
+        const float2 d2 = rx_fma2(tx, tx, rx_fma2(ty, ty, rx_fma2(tz, tz, zero2)));
+        const float range2 = L.range2;
+        bool a0 = d2.x < range2, a1 = d2.y < range2;
+        if (!(a0 || a1)) continue;
+        const float2 inv_d = make_float2(fast_rsqrt(d2.x), fast_rsqrt(d2.y));
+        const float2 lx = rx_fma2(tx, inv_d, zero2), ly = rx_fma2(ty, inv_d, zero2), lz = rx_fma2(tz, inv_d, zero2);
+        const float2 ndl_raw = rx_fma2(nx, lx, rx_fma2(ny, ly, rx_fma2(nzv, lz, zero2)));
+        const float2 ndl = make_float2(fmaxf(ndl_raw.x, 0.0f), fmaxf(ndl_raw.y, 0.0f));
+        a0 = a0 && ndl.x > 0.0f; a1 = a1 && ndl.y > 0.0f;
+        if (!(a0 || a1)) continue;
+        f3 r0 = {0.0f, 0.0f, 0.0f}, r1 = {0.0f, 0.0f, 0.0f};   // a pixel the light does not reach adds exactly nothing
+        const float2 dist = rx_fma2(d2, inv_d, zero2);
+        if (a0 && !light_radiance_fast(L, ndl.x, {lx.x, ly.x, lz.x}, dist.x, &r0)) r0 = {0.0f, 0.0f, 0.0f};
+        if (a1 && !light_radiance_fast(L, ndl.y, {lx.y, ly.y, lz.y}, dist.y, &r1)) r1 = {0.0f, 0.0f, 0.0f};
+        float2 hx2 = rx_add2(lx, vx), hy2 = rx_add2(ly, vy), hz2 = rx_add2(lz, vz);
+        const float2 hh = rx_fma2(hx2, hx2, rx_fma2(hy2, hy2, rx_fma2(hz2, hz2, zero2)));
+        const float2 ih = make_float2(fast_rsqrt(hh.x), fast_rsqrt(hh.y));
+        hx2 = rx_fma2(hx2, ih, zero2); hy2 = rx_fma2(hy2, ih, zero2); hz2 = rx_fma2(hz2, ih, zero2);
+        const float2 ndh_raw = rx_fma2(nx, hx2, rx_fma2(ny, hy2, rx_fma2(nzv, hz2, zero2)));
+        const float2 ndh = make_float2(fmaxf(ndh_raw.x, 0.0f), fmaxf(ndh_raw.y, 0.0f));
+        const float2 h2 = rx_fma2(ndh, ndh, zero2);
+        const float2 spec = rx_fma2(fr, rx_fma2(rx_fma2(h2, h2, zero2), h2, zero2), zero2);
+        lr = rx_fma2(rx_fma2(rx_add2(kdr, spec), ndl, zero2), make_float2(r0.x, r1.x), lr);
+        lg = rx_fma2(rx_fma2(rx_add2(kdg, spec), ndl, zero2), make_float2(r0.y, r1.y), lg);
+        lb = rx_fma2(rx_fma2(rx_add2(kdb, spec), ndl, zero2), make_float2(r0.z, r1.z), lb);
+    }
+    auto l2s2 = [&](float2 x) {   // linear_to_srgb_fast, rasterizer.rs:28-33, then * 255 for the saturating conversion
+        const float2 sq2 = make_float2(fast_sqrt(x.x), fast_sqrt(x.y));
+        const float2 r = rx_fma2(rx_fma2(sq2, rx_bc2(-0.055f), zero2), sq2, rx_fma2(sq2, rx_bc2(1.055f), zero2));
+        return rx_fma2(r, rx_bc2(255.0f), zero2);
+    };
+    const float2 cr = l2s2(lr), cg = l2s2(lg), cb = l2s2(lb);
+    auto u8 = [](float x) { uint32_t r; asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; };
+    return make_uint2(u8(cr.x) | (u8(cg.x) << 8) | (u8(cb.x) << 16) | (texel0 & 0xFF000000u),
+                      u8(cr.y) | (u8(cg.y) << 8) | (u8(cb.y) << 16) | (texel1 & 0xFF000000u));
+}
+#endif
 
 // ---- Rusteria VM batch shaders (general mode) -------------------------------------------------------
 // Everything a program can observe is derived with the reference's own arithmetic (exact divisions, no
@@ -1866,24 +2008,60 @@ __device__ __forceinline__ void test_fragment(const SceneDev& S, const DFrame& F
     best_z = z; best = slot; best_al = alpha; best_be = beta;
 }
 
+// The same for the two pixels of a row of the thread's 2x2 (x = fxa and fxb, same y): the barycentric and depth
+// arithmetic of both in packed fp32 (rx_fma2: FFMA2 / FMUL2 / FADD2, one issue slot for two pixels), every operation
+// the same single rounding as in test_fragment.  `pm` = which of the two are covered (bit 0: a, bit 1: b).
+template <bool VM>
+__device__ __forceinline__ void test_fragment_pair(const SceneDev& S, const DFrame& F, const DFrameBatch* __restrict__ fbs,
+                                                   const TriShade* __restrict__ shade, const float4 q0, const float4 q1, const float4 q2,
+                                                   uint32_t meta, uint32_t slot, float fxa, float fxb, float fpy, uint32_t sample_mode, float nz,
+                                                   float& bz0, uint32_t& bo0, float& bal0, float& bbe0, float& bz1, uint32_t& bo1, float& bal1, float& bbe1) {
+    const float2 X = make_float2(fxa, fxb);
+    const float acx = q1.x - q0.x, acy = q1.y - q0.y;
+    const float apy = fpy - q0.y, pcy = q1.y - fpy, pby = q0.w - fpy;
+    const float2 apx = rx_add2(X, rx_bc2(-q0.x));          // fpx - a.x
+    const float2 pcx = rx_sub2(rx_bc2(q1.x), X);           // c.x - fpx
+    const float2 pbx = rx_sub2(rx_bc2(q0.z), X);           // b.x - fpx
+    const float2 na = rx_sub2(rx_mul2(pcx, rx_bc2(pby), nz), rx_mul2(pbx, rx_bc2(pcy), nz));   // pcx*pby - pcy*pbx
+    const float2 nb = rx_sub2(rx_bc2(rx_mul1(acx, apy, nz)), rx_mul2(apx, rx_bc2(acy), nz));   // acx*apy - acy*apx
+    float2 alpha, beta;
+    if (meta & RX_META_FASTDIV) { alpha = rx_div_by2(na, q2.x, q1.z, nz); beta = rx_div_by2(nb, q2.x, q1.z, nz); }
+    else { alpha = make_float2(na.x / q2.x, na.y / q2.x); beta = make_float2(nb.x / q2.x, nb.y / q2.x); }
+    const float2 gamma = rx_sub2(rx_sub2(rx_bc2(1.0f), alpha), beta);
+    const float2 ooz = rx_add2(rx_add2(rx_mul2(alpha, rx_bc2(q2.y), nz), rx_mul2(beta, rx_bc2(q2.z), nz)), rx_mul2(gamma, rx_bc2(q2.w), nz));  // :1054-1056
+    // sequential `z < zbuf` in submission order == lexicographic min of (z, ordinal); alpha test (:1408)
+    auto commit = [&](float z, float al, float be, float fx, float& bz, uint32_t& bo, float& bal, float& bbe) {
+        const bool pass_z = (z < bz) || (z == bz && bo != RX_OWNER_NONE && slot < bo);
+        if (!pass_z) return;
+        if (meta & RX_META_ALPHA) {
+            const uint32_t texel = alpha_test_texel<VM>(S, S.arena, S.chunk_info, &F, fbs + (meta & RX_META_BATCH), shade + slot, al, be, z, fx, fpy,
+                                                             sample_mode);
+            if ((texel >> 24) != 255u) return;
+        }
+        bz = z; bo = slot; bal = al; bbe = be;
+    };
+    commit(1.0f / ooz.x, alpha.x, beta.x, fxa, bz0, bo0, bal0, bbe0);
+    commit(1.0f / ooz.y, alpha.y, beta.y, fxb, bz1, bo1, bal1, bbe1);
+}
+
 // coverage of one staged triangle over the thread's 2x2 pixels (rasterizer.rs:1020-1036), then the
 // depth test of the covered ones.  `valid` masks pixels outside the frame.
 template <bool GENERAL, bool VM>
 __device__ __forceinline__ void process_record(const SceneDev& S, const DFrame& F, const DFrameBatch* __restrict__ fbs,
                                                const TriShade* __restrict__ shade, const TriVis* Tp, uint32_t slot, bool full, int px0,
-                                               int py0, float fx0, float fy0, uint32_t valid, uint32_t sample_mode, Vis4& V, Opa4& O) {
+                                               int py0, float fx0, float fy0, uint32_t valid, uint32_t sample_mode, float nz, Vis4& V, Opa4& O) {
     const float4* q = reinterpret_cast<const float4*>(Tp);
     const float4 q5 = q[5];
     const uint32_t bbx = __float_as_uint(q5.y), bby = __float_as_uint(q5.z), meta = __float_as_uint(q5.w);
     uint32_t m = valid;   // `full` (uniform over the warp): the bbox contains the warp's region and every edge passes everywhere
     if (!full) {
         const int x0 = (int)(bbx & 0xFFFFu), x1 = (int)(bbx >> 16), y0 = (int)(bby & 0xFFFFu), y1 = (int)(bby >> 16);
-        const bool cx0 = px0 >= x0 && px0 < x1, cx1 = px0 + 8 >= x0 && px0 + 8 < x1;
+        const bool cx0 = px0 >= x0 && px0 < x1, cx1 = px0 + RX_DX >= x0 && px0 + RX_DX < x1;
         const bool cy0 = py0 >= y0 && py0 < y1, cy1 = py0 + 4 >= y0 && py0 + 4 < y1;
         m &= ((cx0 && cy0) ? 1u : 0u) | ((cx1 && cy0) ? 2u : 0u) | ((cx0 && cy1) ? 4u : 0u) | ((cx1 && cy1) ? 8u : 0u);
     }
     if (!m) return;
-    const float fx1 = fx0 + 8.0f, fy1 = fy0 + 4.0f;
+    const float fx1 = fx0 + (float)RX_DX, fy1 = fy0 + 4.0f;
     if (!full) {   // Edges::evaluate, edge.rs:28-36: (a*px + b*py) + c < 0 -> outside (a NaN result passes)
         const float4 q3 = q[3], q4 = q[4];
         const float ea[3] = {q3.x, q3.y, q3.z}, eb[3] = {q3.w, q4.x, q4.y}, ec[3] = {q4.z, q4.w, q5.x};
@@ -1923,12 +2101,30 @@ __device__ __forceinline__ void process_record(const SceneDev& S, const DFrame& 
                 if ((O.some & (1u << k)) && O.sid[k] == profile) m &= ~(1u << k);
         }
     }
+#if RX_PACKED_FRAGMENTS
+    // pixels 0,1 share y = fy0 and pixels 2,3 y = fy1: each covered pair goes through the packed test
+#pragma unroll
+    for (int pr = 0; pr < 2; ++pr) {
+        const uint32_t pm = (m >> (2 * pr)) & 3u;
+        const float fy = pr ? fy1 : fy0;
+        if (pm == 3u) {
+            test_fragment_pair<VM>(S, F, fbs, shade, q0, q1, q2, meta, slot, fx0, fx1, fy, sample_mode, nz, V.z[2 * pr], V.own[2 * pr], V.al[2 * pr],
+                                   V.be[2 * pr], V.z[2 * pr + 1], V.own[2 * pr + 1], V.al[2 * pr + 1], V.be[2 * pr + 1]);
+        } else if (pm == 1u) {   // one pixel of the pair: the scalar test (small triangles mostly come this way)
+            test_fragment<VM>(S, F, fbs, shade, q0, q1, q2, meta, slot, fx0, fy, sample_mode, V.z[2 * pr], V.own[2 * pr], V.al[2 * pr], V.be[2 * pr]);
+        } else if (pm == 2u) {
+            test_fragment<VM>(S, F, fbs, shade, q0, q1, q2, meta, slot, fx1, fy, sample_mode, V.z[2 * pr + 1], V.own[2 * pr + 1], V.al[2 * pr + 1],
+                              V.be[2 * pr + 1]);
+        }
+    }
+#else
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         if (m & (1u << k))
             test_fragment<VM>(S, F, fbs, shade, q0, q1, q2, meta, slot, (k & 1) ? fx1 : fx0, (k & 2) ? fy1 : fy0, sample_mode, V.z[k],
                           V.own[k], V.al[k], V.be[k]);
     }
+#endif
 }
 
 // ---- small-triangle pass of long tile lists (fast mode) -------------------------------------------------
@@ -2038,7 +2234,7 @@ __device__ __forceinline__ uint32_t apply_2d(const SceneDev& S, const DFrame& F,
 // thread-per-record pass of long tile lists (small_triangle_pass; its own instantiation because the extra code costs the
 // plain fast path 6 % on the map scene -- scenes with few triangles never have such lists and keep MODE 0).
 template <int SAMPLE, bool PLANES, int MODE>
-__global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raster(SceneDev S, Workspace Wk, RasterOut out, uint32_t n_frames,
+__global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raster(SceneDev S, Workspace Wk, const __grid_constant__ RasterOut out, uint32_t n_frames,
                                                                uint32_t tile0, uint32_t tiles_per_frame, uint32_t counter) {
     constexpr bool GENERAL = MODE == 1 || MODE == 2, VM = MODE == 2, SMALL = MODE == 3;
     __shared__ __align__(16) TriVis s_large[GENERAL ? 1 : RX_LARGE_CACHE];
@@ -2046,7 +2242,14 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
     __shared__ uint16_t s_sel[GENERAL ? 1 : RX_LARGE_CACHE];
     __shared__ uint32_t s_nsel;
     __shared__ int32_t s_work[4];   // frame (-1 = done), tile x0, tile y0, tile index
+#if RX_TMA_STORE
+    // two dense 32x32 tiles in the tensor map's 128 B swizzle (16 B chunk c of row r sits at chunk c ^ (r & 7)), one draining
+    __shared__ __align__(1024) uint32_t s_color[2 * RX_TILE_H * RX_TILE_W];
+#define RX_CIDX(row, col) ((row) * RX_TILE_W + (((((col) >> 2) ^ ((row) & 7)) << 2) | ((col) & 3)))
+#else
     __shared__ __align__(16) uint32_t s_color[(RX_BULK_STORE ? 2 : 1) * RX_TILE_H * RX_COLOR_STRIDE];  // bulk store: two tiles, one draining
+#define RX_CIDX(row, col) ((row) * RX_COLOR_STRIDE + (col))
+#endif
     __shared__ float4 s_state[4 * RX_TILE_THREADS];  // (z, owner, alpha, beta) of pixel k of thread t at [k*256 + t]
     __shared__ float2 s_ostate[GENERAL ? 4 * RX_TILE_THREADS : 1];  // (z, owner) of the opacity layer
     __shared__ ShadeConst s_k;                       // frame constants of the deferred shade
@@ -2056,6 +2259,7 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
     __shared__ int s_can_be_empty;                   // per frame: some tile may be untouched (see the empty-tile path below)
     __shared__ struct { const DFrame* F; const DLight* lights_g; const TriVis* vis; const TriShade* shade; const DFrameBatch* fbs; const uint32_t* large; const uint32_t* tile_count; const uint32_t* tile_base; const uint32_t* lists; uint32_t n_large; } s_p;
     __shared__ uint32_t s_nbig;                      // small-triangle pass: length of the compacted list of the other records
+    __shared__ __align__(8) unsigned long long s_mbar;   // completion of the bulk copies that stage the frame's large-triangle records
 
     uint32_t tid = threadIdx.x;
 #if RX_OPAQUE >= 3
@@ -2063,18 +2267,35 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
 #endif
     const uint32_t lane = tid & 31, warp = tid >> 5;
     // warp w covers a 16x8 region (2 across, 4 down); lane (lx, ly) of the 8x4 lane grid owns the
-    // pixels (lx + 8i, ly + 4j) of the region
+    // pixels (lx + RX_DX*i, ly + 4j) of the region (RX_DX = 1: lx is even, the thread owns two horizontally adjacent pairs)
     const int rbx = (int)(warp & 1) * RX_REGION_W, rby = (int)(warp >> 1) * RX_REGION_H;
-    int lx = (int)(lane & 7) + rbx, ly = (int)(lane >> 3) + rby;   // pixel offset of the thread inside the tile
+    int lx = (int)(lane & 7) * (RX_DX == 1 ? 2 : 1) + rbx, ly = (int)(lane >> 3) + rby;   // pixel offset of the thread inside the tile
 #if RX_OPAQUE >= 4
     asm volatile("" : "+r"(lx), "+r"(ly));
 #endif
+#if RX_TMA_STORE
+    // the thread's first pixel in the swizzled tile; with RX_DX = 8 pixel k of its 2x2 sits at (cbase ^ (k&1)<<3 ^ (k>>1)<<4) + (k>>1)*128:
+    // +8 columns flips chunk bit 1, +4 rows flips bit 2 of (row & 7) and with it chunk bit 2
+    int cbase = ly * RX_TILE_W + ((((lx >> 2) ^ (ly & 7)) << 2) | (lx & 3));
+#if RX_DX == 1
+#define RX_CPIX(k) (((cbase + ((k) & 1)) ^ (((k) >> 1) << 4)) + ((k) >> 1) * (4 * RX_TILE_W))   // lx is even: the neighbour shares the 16 B chunk
+#else
+#define RX_CPIX(k) ((cbase ^ (((k) & 1) << 3) ^ (((k) >> 1) << 4)) + ((k) >> 1) * (4 * RX_TILE_W))
+#endif
+#else
     int cbase = ly * RX_COLOR_STRIDE + lx;   // the thread's first pixel in s_color
+#define RX_CPIX(k) (cbase + ((k) & 1) * RX_DX + ((k) >> 1) * (4 * RX_COLOR_STRIDE))
+#endif
 #if RX_OPAQUE >= 2
     asm volatile("" : "+r"(cbase));
 #endif
     const uint32_t total = n_frames * tiles_per_frame;
     uint32_t cached_frame = 0xFFFFFFFFu, n_cached = 0;
+    uint32_t mbar_phase = 0u;
+    if (!GENERAL && tid == 0) {   // visible to everybody (and to the async proxy) after the first tile's barrier
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     uint32_t coff = 0;   // which half of s_color this tile uses (bulk store: the other half may still be draining)
     {
         const float x = (float)tid * (1.0f / 255.0f);
@@ -2124,15 +2345,26 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
             else if (tid == 33) s_k.has_brush = Fg.has_brush;
             for (uint32_t i = tid; i < min(S.n_lights, (uint32_t)RX_SMEM_LIGHTS) * (uint32_t)(sizeof(DLight) / 4); i += RX_TILE_THREADS)
                 reinterpret_cast<uint32_t*>(s_lights)[i] = __ldg(reinterpret_cast<const uint32_t*>(lights_gg) + i);
-            if (!GENERAL) {  // largeg-triangle records of the frame
+            if (!GENERAL) {
+                // The frame's large-triangle records are staged in shared memory by the bulk-copy (TMA) engine: one
+                // cp.async.bulk of a 96 B record per lane, completion counted in bytes on an mbarrier the CTA then waits on
+                // (every thread of the previous tile is past its reads of s_large: the barrier after the work fetch).
                 n_cached = min(n_largeg, (uint32_t)RX_LARGE_CACHE);
-                const float4* g = reinterpret_cast<const float4*>(visg);
-                float4* sq = reinterpret_cast<float4*>(s_large);
-                for (uint32_t i = tid; i < n_cached * 6u; i += RX_TILE_THREADS) {
-                    const uint32_t r = i / 6u, q = i - r * 6u;
-                    const uint32_t slot = __ldg(largeg + r);
-                    if (q == 0) s_large_slot[r] = slot;
-                    sq[i] = __ldg(g + (size_t)slot * 6u + q);
+                if (n_cached) {
+                    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+                    if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(n_cached * (uint32_t)sizeof(TriVis)) : "memory");
+                    for (uint32_t r = tid; r < n_cached; r += RX_TILE_THREADS) {
+                        const uint32_t slot = __ldg(largeg + r);
+                        s_large_slot[r] = slot;
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"((uint32_t)__cvta_generic_to_shared(&s_large[r])), "l"(visg + slot), "r"((uint32_t)sizeof(TriVis)), "r"(mbar) : "memory");
+                    }
+                    uint32_t done = 0u;
+                    while (!done) {
+                        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                                     : "=r"(done) : "r"(mbar), "r"(mbar_phase) : "memory");
+                    }
+                    mbar_phase ^= 1u;
                 }
             }
             cached_frame = f;
@@ -2216,8 +2448,8 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
         const bool region_ok = rx0 < rx1 && ry0 < ry1;
         int px0 = tx0 + lx, py0 = ty0 + ly;
         float fx0 = (float)px0 + 0.5f, fy0 = (float)py0 + 0.5f;  // rasterizer.rs:1022
-        uint32_t valid = ((px0 < fw && py0 < fy1) ? 1u : 0u) | ((px0 + 8 < fw && py0 < fy1) ? 2u : 0u) |
-                         ((px0 < fw && py0 + 4 < fy1) ? 4u : 0u) | ((px0 + 8 < fw && py0 + 4 < fy1) ? 8u : 0u);
+        uint32_t valid = ((px0 < fw && py0 < fy1) ? 1u : 0u) | ((px0 + RX_DX < fw && py0 < fy1) ? 2u : 0u) |
+                         ((px0 < fw && py0 + 4 < fy1) ? 4u : 0u) | ((px0 + RX_DX < fw && py0 + 4 < fy1) ? 8u : 0u);
 #if RX_OPAQUE >= 1
         asm volatile("" : "+r"(px0), "+r"(py0));
 #endif
@@ -2292,21 +2524,21 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                         mask &= mask - 1u;
                         const uint32_t rr = __shfl_sync(0xFFFFFFFFu, slot, b);
                         const TriVis* Tp = reinterpret_cast<const TriVis*>(__shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(rp), b));
-                        process_record<GENERAL, VM>(S, F, fbs, shade, Tp, rr, (fullm >> b) & 1u, px0, py0, fx0, fy0, valid, smode, V, O);
+                        process_record<GENERAL, VM>(S, F, fbs, shade, Tp, rr, (fullm >> b) & 1u, px0, py0, fx0, fy0, valid, smode, Wk.neg_zero, V, O);
                     }
                 }
             }
             if (small_pass) {   // merge the small-triangle winners into the walk's state: the same (z, ordinal) rule as test_fragment
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const unsigned long long key = s_key[(ly + ((k >> 1) << 2)) * RX_TILE_W + lx + ((k & 1) << 3)];
+                    const unsigned long long key = s_key[(ly + ((k >> 1) << 2)) * RX_TILE_W + lx + (k & 1) * RX_DX];
                     const uint32_t sslot = (uint32_t)key;
                     if (sslot != RX_OWNER_NONE) {
                         const float zs = z_from_order_bits((uint32_t)(key >> 32));
                         if ((zs < V.z[k]) || (zs == V.z[k] && V.own[k] != RX_OWNER_NONE && sslot < V.own[k])) {
                             const float4* q = reinterpret_cast<const float4*>(vis + sslot);
                             V.z[k] = fragment_depth(__ldg(q), __ldg(q + 1), __ldg(q + 2), __float_as_uint(__ldg(q + 5).w),
-                                                    fx0 + ((k & 1) ? 8.0f : 0.0f), fy0 + ((k & 2) ? 4.0f : 0.0f), &V.al[k], &V.be[k]);
+                                                    fx0 + ((k & 1) ? (float)RX_DX : 0.0f), fy0 + ((k & 2) ? 4.0f : 0.0f), &V.al[k], &V.be[k]);
                             V.own[k] = sslot;
                         }
                     }
@@ -2326,11 +2558,41 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
         }
 #pragma unroll 1
         for (int k = 0; k < 4; ++k) {
-            const int px = px0 + ((k & 1) << 3), py = py0 + ((k >> 1) << 2);
-            const float fpx = fx0 + ((k & 1) ? 8.0f : 0.0f), fpy = fy0 + ((k & 2) ? 4.0f : 0.0f);  // exact: small integers + 0.5
+            const int px = px0 + (k & 1) * RX_DX, py = py0 + ((k >> 1) << 2);
+            const float fpx = fx0 + ((k & 1) ? (float)RX_DX : 0.0f), fpy = fy0 + ((k & 2) ? 4.0f : 0.0f);  // exact: small integers + 0.5
             const float4 st = s_state[k * RX_TILE_THREADS + tid];
             const uint32_t owner = __float_as_uint(st.y);
             uint32_t color;
+#if RX_PACKED_SHADE && RX_DX == 1
+            if (!GENERAL && !(k & 1) && owner != RX_OWNER_NONE && F.d3_active) {
+                // the horizontally adjacent pixel has the same owner (it mostly does): both are shaded in packed arithmetic
+                const float4 st1 = s_state[(k + 1) * RX_TILE_THREADS + tid];
+                if (__float_as_uint(st1.y) == owner) {
+                    const uint32_t b = __ldg(&vis[owner].meta) & RX_META_BATCH;
+                    const uint32_t fl = fbs[b].sd_flags;
+                    if ((fl & (RX_SD_NORMALS | RX_SD_TERRAIN)) == RX_SD_NORMALS && s_k.sun_radiance <= 0.0f && (S.n_sectors == 0u || !s_k.has_ambient)) {
+                        const uint2 c2 = shade_owner_pair(S, s_k, lights, s_kd, fbs[b], shade + owner, make_float2(st.z, st1.z), make_float2(st.w, st1.w),
+                                                          make_float2(st.x, st1.x), fpx, fpy, smode, Wk.neg_zero);
+                        s_color[coff + RX_CPIX(k)] = c2.x;
+                        s_color[coff + RX_CPIX(k + 1)] = c2.y;
+                        if (PLANES) {
+                            if (px < fw && py < fy1) {
+                                const size_t o = (size_t)(py - F.band_y0) * (size_t)fpitch + (size_t)(px - bx0);
+                                if (out.owner) out.owner[o] = owner;
+                                if (out.depth) out.depth[o] = st.x;
+                            }
+                            if (px + 1 < fw && py < fy1) {
+                                const size_t o = (size_t)(py - F.band_y0) * (size_t)fpitch + (size_t)(px + 1 - bx0);
+                                if (out.owner) out.owner[o] = owner;
+                                if (out.depth) out.depth[o] = st1.x;
+                            }
+                        }
+                        ++k;   // the pair is done
+                        continue;
+                    }
+                }
+            }
+#endif
             if (F.d3_active) {
                 if (owner != RX_OWNER_NONE) {
                     const uint32_t b = __ldg(&vis[owner].meta) & RX_META_BATCH;
@@ -2352,7 +2614,7 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                 color = F.has_bg_color ? F.bg_color : 0u;  // rasterizer.rs:277-282
                 if (!F.ignore_bg_shader && F.bg_shader != RXC_BG_NONE) color = shade_background(F, px, py);
             }
-            s_color[coff + cbase + ((k & 1) << 3) + (k >> 1) * (4 * RX_COLOR_STRIDE)] = color;
+            s_color[coff + RX_CPIX(k)] = color;
             if (PLANES && px < fw && py < fy1) {
                 const size_t o = (size_t)(py - F.band_y0) * (size_t)fpitch + (size_t)(px - bx0);
                 if (out.owner) out.owner[o] = owner;
@@ -2384,15 +2646,15 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                     const Tri2D& T = recs[__shfl_sync(0xFFFFFFFFu, r, b)];
 #pragma unroll 1
                     for (int k = 0; k < 4; ++k) {
-                        const int px = px0 + ((k & 1) << 3), py = py0 + ((k >> 1) << 2);
-                        uint32_t* c = &s_color[coff + cbase + ((k & 1) << 3) + (k >> 1) * (4 * RX_COLOR_STRIDE)];
+                        const int px = px0 + (k & 1) * RX_DX, py = py0 + ((k >> 1) << 2);
+                        uint32_t* c = &s_color[coff + RX_CPIX(k)];
                         *c = apply_2d<VM>(S, F, lights, fb2, T, px, py, smode, *c, &vm_fault);
                     }
                 }
             }
         }
         if (VM && vm_fault) atomicOr(&Wk.counters[f].overflow, 16u);  // a program hit a device limit
-#if RX_BULK_STORE
+#if RX_BULK_STORE || RX_TMA_STORE
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the tile's pixels, written through the generic proxy, for the bulk-copy engine
 #endif
         __syncthreads();
@@ -2402,6 +2664,17 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
         // been read, the global writes complete asynchronously.
         uint8_t* frame_px = out.pixels + (size_t)f * out.frame_stride;
         const bool full_tile = (tx0 + RX_TILE_W <= fw) && (ty0 + RX_TILE_H <= fy1);
+#if RX_TMA_STORE
+        if (out.tma_store) {
+            // ONE bulk tensor store per tile, issued by one thread: the TMA engine reads the swizzled 4 KB tile from shared
+            // memory and writes the 32 rows; rows / columns beyond the buffer (partial tiles) are clipped by the engine
+            if (tid == 0) {
+                const uint32_t src = (uint32_t)__cvta_generic_to_shared(&s_color[coff]);
+                asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                             ::"l"(&out.tmap), "r"(src), "r"(tx0 - bx0), "r"(ty0 - F.band_y0), "r"((int)f) : "memory");
+            }
+        } else
+#endif
         if (out.vec_store && full_tile) {
 #if RX_BULK_STORE
             if (warp == 0) {
@@ -2411,7 +2684,7 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
             }
 #else
             const int r = (int)tid >> 3, c4 = (int)tid & 7;   // 8 x 16 B per 32-pixel row
-            const uint4 v = *reinterpret_cast<const uint4*>(&s_color[coff + r * RX_COLOR_STRIDE + c4 * 4]);
+            const uint4 v = *reinterpret_cast<const uint4*>(&s_color[coff + RX_CIDX(r, c4 * 4)]);
             uint4* dst = reinterpret_cast<uint4*>(frame_px + ((size_t)(ty0 - F.band_y0 + r) * (size_t)ppitch + (size_t)(tx0 - bx0)) * 4) + c4;
             *dst = v;
 #endif
@@ -2420,9 +2693,17 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                 const int r = i >> 5, c = i & 31;
                 if (tx0 + c < fw && ty0 + r < fy1)
                     reinterpret_cast<uint32_t*>(frame_px)[(size_t)(ty0 - F.band_y0 + r) * (size_t)ppitch + (size_t)(tx0 - bx0 + c)] =
-                        s_color[coff + r * RX_COLOR_STRIDE + c];
+                        s_color[coff + RX_CIDX(r, c)];
             }
         }
+#if RX_TMA_STORE
+        // the next tile writes the other half: its previous store (two tiles ago) must have read shared memory
+        if (tid == 0) {
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        }
+        coff ^= (uint32_t)(RX_TILE_H * RX_TILE_W);
+#endif
 #if RX_BULK_STORE
         // the next tile writes the other half: its previous drain (two tiles ago) must have read shared memory; at most
         // this tile's group stays in flight
@@ -2435,6 +2716,11 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
 #endif
         __syncthreads();  // s_color (its other half), s_work and s_nsel are rewritten by the next tile
     }
+#if RX_TMA_STORE
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory stays valid until the engine has read it
+#endif
+#undef RX_CIDX
+#undef RX_CPIX
 }
 
 // ---------------------------------------------------------------------------------------------

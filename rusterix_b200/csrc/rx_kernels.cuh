@@ -1,6 +1,12 @@
 // rx_kernels.cuh -- launch interface between the host API (rx_api.cu) and the kernels (rx_kernels.cu)
 #pragma once
+#include <cuda.h>   // CUtensorMap (type only: the driver entry point is resolved at run time)
+
 #include "rx_device.cuh"
+
+#ifndef RX_TMA_STORE
+#define RX_TMA_STORE 0   // 1: finished tiles leave shared memory as ONE 2-D tensor-map bulk store (cp.async.bulk.tensor, UTMASTG)
+#endif
 
 struct TriBin {           // 16 B per triangle: what the binning kernels stream
     uint32_t bbx, bby;    // raw pixel bbox from setup; final (scissored) bbox after k_bin_count
@@ -69,6 +75,7 @@ struct Workspace {
     uint32_t small_min_list, small_max_pix;  // k_raster's thread-per-record pass of long tile lists
     uint32_t small_gshift;                   // log2 of the lanes that share one record in the pass
     uint32_t small_min_tris;                 // scenes with at least this many triangles run the k_raster variant that has the pass (0xFFFFFFFF = never)
+    float neg_zero;                          // -0.0f, as a run-time value the compiler cannot see through (rx_mul2 in rx_device.cuh)
 };
 
 // rxc_rasterize_projected: the outputs of the host's own Scene::project (batch3d.rs:482-740), flattened over the batches
@@ -90,6 +97,8 @@ struct RasterOut {
     float* depth;
     uint32_t vec_store;    // rows are 16 B aligned -> 128-bit stores
     uint32_t pitch;        // pixels per row of the pixel buffer (the rendered rectangle's width unless a band is written in place)
+    uint32_t tma_store;    // tmap describes the pixel buffer as (x, y, frame) of u32: tiles are stored through it (RX_TMA_STORE builds)
+    alignas(64) CUtensorMap tmap;
 };
 
 enum {

@@ -19,7 +19,7 @@ for name in names:
     for _ in range(3):
         batch.run(out, sync=True)
     ctx.reset_stats(); ctx.set_profiling(True)
-    n = 10
+    n = 30
     for _ in range(n):
         batch.run(out, sync=True)
     s = ctx.stats(); ctx.set_profiling(False)
