@@ -91,3 +91,12 @@ def test_rust_sys_crate_is_generated_from_the_checked_mirror():
         body = re.search(r"pub struct %s \{(.*?)\n\}" % s.__name__, have, flags=re.S).group(1)
         fields = re.findall(r"pub (\w+):", body)
         assert fields == [("pass" if f == "pass_" else f) for f, _ in s._fields_]
+
+
+def test_rust_wrapper_sources_agree_with_the_sys_crate_and_the_header():
+    """rust/rusterix-cuda/src/{cuda,lower}.rs cannot be compiled here (no rustc); tools/check_rust_wrapper.py checks what
+    can be: call arities, struct-literal field sets, constants, and the NodeOp opcode table against vm.OPS and the
+    reference's enum order."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_rust_wrapper.py")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "MISMATCH" not in r.stdout

@@ -602,6 +602,44 @@ def test_sweep_of_256_frames_in_one_call_is_deterministic_and_matches_single_fra
         assert np.array_equal(a[k], single[0])
 
 
+def test_config_e_sweep_of_1024_frames_in_contiguous_blocks_through_the_delivery_buffer():
+    """Config E the way bench.py's sweep4096 block runs it: contiguous blocks of frames, 32 cameras per launch sequence,
+    rendered straight into the rxc_mgpu delivery buffer (two-slot ring, release hand-shake; world 1 here, the multi-rank
+    legs are in test_mgpu_gpu.py).  1024 frames of the 4096-frame path; every 37th is compared byte for byte with a
+    single-frame render, and with the oracle for a few."""
+    import torch
+    from rusterix_b200 import DeviceContext, mgpu
+
+    W, H, per_launch, n = 320, 180, 32, 1024
+    cfg = scenes.sweep(W, H, 40, n_frames=4096, logo_size=64)
+    fb = W * H * 4
+    ctx = DeviceContext.get(0)
+    dl = mgpu.Delivery(ctx, 0, 1)
+    buf = dl.target(2 * per_launch * fb)
+    first = 1536                                   # the block of "rank 3 of 8": frames 1536 .. 2559
+    got = torch.empty((n, H, W, 4), dtype=torch.uint8, device="cuda:0")
+    for k in range(n // per_launch):
+        ids = range(first + k * per_launch, first + (k + 1) * per_launch)
+        batch = Rasterizer.prepare_batch([cfg.rasterizer(i) for i in ids], cfg.scene, W, H, cfg.tile_size, cfg.assets)
+        slot = k % 2
+        if k >= 2:
+            dl.release()
+        dl.render(batch, slot * per_launch * fb)
+        dl.deliver(mgpu.frame_regions(1, per_launch, fb, slot * per_launch * fb))
+        ctx.synchronize()
+        got[k * per_launch:(k + 1) * per_launch] = buf[slot * per_launch * fb:(slot + 1) * per_launch * fb].reshape(per_launch, H, W, 4)
+    dl.close()
+    got = got.cpu().numpy()
+    assert len({got[i].tobytes() for i in range(0, n, 8)}) == n // 8          # the camera really moves
+    for i in range(0, n, 37):
+        single = render_gpu(cfg.rasterizer(first + i), cfg.scene, cfg.assets, W, H, cfg.tile_size, planes=False)
+        assert np.array_equal(got[i], single[0]), i
+    for i in (0, 511, 1023):
+        o = render_oracle(cfg.rasterizer(first + i), cfg.scene, cfg.assets, W, H, cfg.tile_size, planes=False)
+        diff = np.abs(got[i].astype(np.int16) - o[0].astype(np.int16)).max(axis=-1)
+        assert (diff <= 1).mean() >= 0.999
+
+
 def test_one_context_many_scenes_in_any_order():
     """The context keeps scene, textures, programs and a workspace resident: switching between scenes of different
     size, kernel mode (fast / general / general + VM), frame size and light count must never leak state."""

@@ -62,6 +62,28 @@ def rust_type(t, owner=None, field=None):
     raise TypeError(t)
 
 
+def header_enums():
+    """(name, value) of every enumerator of the anonymous enums of include/rxcuda.h (RXC_MODE_*, RXC_SRC_*, RXVM_* ...)."""
+    import re
+    text = open(os.path.join(ROOT, "include", "rxcuda.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    out = []
+    for body in re.findall(r"\benum\s*\{(.*?)\}\s*;", text, flags=re.S):
+        nxt = 0
+        for item in body.split(","):
+            item = item.strip()
+            if not item:
+                continue
+            if "=" in item:
+                name, val = [x.strip() for x in item.split("=")]
+                nxt = int(val.rstrip("u"), 0)
+            else:
+                name = item
+            out.append((name, nxt))
+            nxt += 1
+    return out
+
+
 def generate():
     out = ["// GENERATED by tools/gen_rust_sys.py from rusterix_b200/_abi.py (the ctypes mirror that tests/test_abi.py checks",
            "// against include/rxcuda.h).  Do not edit: regenerate with `python tools/gen_rust_sys.py --write`.",
@@ -71,6 +93,10 @@ def generate():
            "pub const RXC_ABI_VERSION: u32 = %d;" % _abi.RXC_ABI_VERSION, "pub const RXC_N_KERNELS: usize = %d;" % _abi.RXC_N_KERNELS]
     for code, name in sorted(_abi.STATUS_NAMES.items(), reverse=True):
         out.append("pub const %s: i32 = %d;" % (name, code))
+    out.append("pub const RXC_MGPU_ID_BYTES: usize = %d;" % _abi.RXC_MGPU_ID_BYTES)
+    out.append("// enumerators of include/rxcuda.h")
+    for name, val in header_enums():
+        out.append("pub const %s: u32 = %d;" % (name, val))
     out += ["", "#[repr(C)]", "pub struct rxc_ctx {", "    _private: [u8; 0],", "}"]
     for s in STRUCTS:
         out += ["", "#[repr(C)]", "#[derive(Clone, Copy)]", "pub struct %s {" % s.__name__]
