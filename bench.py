@@ -130,7 +130,7 @@ def build_workload(name, frames_per_step, rank, world):
 def make_config(desc, cfg, world):
     """The `config` object of the JSON line: the same keys and values in the native and the reference arm."""
     return {"workload": desc, "width": cfg.width, "height": cfg.height, "triangles": cfg.counts()[1], "tile_size": cfg.tile_size,
-            "sample_mode": str(cfg.sample_mode).split(".")[-1], "lights": len(cfg.scene.all_lights())}
+            "sample_mode": getattr(cfg.sample_mode, "name", str(cfg.sample_mode)), "lights": len(cfg.scene.all_lights())}
 
 
 def cpu_port_time(cfg, frame_ids, budget_s=20.0, max_frames=10, warm=1):
