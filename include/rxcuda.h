@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RXC_ABI_VERSION 5u
+#define RXC_ABI_VERSION 6u
 
 typedef struct rxc_ctx rxc_ctx;
 
@@ -472,6 +472,26 @@ int32_t rxc_mgpu_deliver(rxc_ctx* ctx, const rxc_mgpu_region* regions, uint32_t 
 int32_t rxc_mgpu_release(rxc_ctx* ctx);
 /* mode of this rank, deliveries issued so far, and (rank 0, synchronizes) how many waits timed out on a dead peer */
 int32_t rxc_mgpu_status(rxc_ctx* ctx, uint32_t* mode, uint32_t* deliveries, uint32_t* timeouts);
+
+/* Batch shaders without the interpreter: rxc_set_scene translates the programs it can verify (static
+ * stack heights, no run-time fault possible) to straight-line C++ and the VM variant of the raster kernel is recompiled with
+ * NVRTC (libnvrtc.so.12, resolved at run time) in a background thread, cached on disk ($RXC_JIT_CACHE, else
+ * $XDG_CACHE_HOME/rusterix_b200); frames use the interpreter until the kernel is ready and whenever NVRTC is missing.
+ * Environment: RXC_VM_JIT = 0 (off) / 1 (background, default) / 2 (compile synchronously); rxc_set_vm_jit changes it for
+ * the scenes set afterwards.
+ * rxc_vm_translate (no context, no GPU): the generated source for a program table; jit_index[i] = i when program i was
+ * accepted, 0xFFFFFFFF when it stays with the interpreter.  Returns the length of the source (written up to `cap` bytes).
+ * rxc_vm_jit_compile (no context, no GPU): runs the NVRTC compilation of k_raster<sample_mode, planes, VM> (sample_mode -1: of the
+ * rxc_vm_execute kernel) for a program
+ * table and returns the size of the cubin (0 = no program accepted, RXC_ERR_UNSUPPORTED = NVRTC missing or the compilation
+ * failed; the compiler's messages in `log`).
+ * rxc_vm_jit_info: programs translated for the current scene, kernels loaded so far, whether a requested kernel is still
+ * being compiled (pending: a kernel is requested by the first frame that needs it), raster launches that used one,
+ * and the last compiler / loader message (up to log_cap bytes). */
+int64_t rxc_vm_translate(const rxc_program* programs, uint32_t n_programs, char* source, uint64_t cap, uint32_t* jit_index);
+int64_t rxc_vm_jit_compile(const rxc_program* programs, uint32_t n_programs, int32_t sample_mode, int32_t planes, char* log, uint32_t log_cap);
+int32_t rxc_set_vm_jit(rxc_ctx* ctx, int32_t mode);
+int32_t rxc_vm_jit_info(rxc_ctx* ctx, uint32_t* n_translated, uint32_t* kernels_compiled, uint32_t* pending, uint64_t* jit_launches, char* log, uint32_t log_cap);
 
 int32_t rxc_set_profiling(rxc_ctx* ctx, int32_t enabled);
 int32_t rxc_get_stats(rxc_ctx* ctx, rxc_stats* out);

@@ -2,7 +2,7 @@
 tests/test_abi.py checks sizes/offsets against a C probe compiled from the header."""
 import ctypes as C
 
-RXC_ABI_VERSION = 5
+RXC_ABI_VERSION = 6
 
 RXC_OK = 0
 RXC_ERR_INVALID = -1
@@ -277,6 +277,10 @@ EXPORTS = [
     ("rxc_mgpu_deliver", C.c_int32, [C.c_void_p, C.POINTER(rxc_mgpu_region), C.c_uint32]),
     ("rxc_mgpu_release", C.c_int32, [C.c_void_p]),
     ("rxc_mgpu_status", C.c_int32, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    ("rxc_vm_translate", C.c_int64, [C.POINTER(rxc_program), C.c_uint32, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint32)]),
+    ("rxc_vm_jit_compile", C.c_int64, [C.POINTER(rxc_program), C.c_uint32, C.c_int32, C.c_int32, C.c_char_p, C.c_uint32]),
+    ("rxc_set_vm_jit", C.c_int32, [C.c_void_p, C.c_int32]),
+    ("rxc_vm_jit_info", C.c_int32, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.c_char_p, C.c_uint32]),
     ("rxc_set_profiling", C.c_int32, [C.c_void_p, C.c_int32]),
     ("rxc_get_stats", C.c_int32, [C.c_void_p, C.POINTER(rxc_stats)]),
     ("rxc_reset_stats", C.c_int32, [C.c_void_p]),

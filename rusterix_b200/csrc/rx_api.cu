@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "rx_internal.h"
+#include "rx_jit.h"
 #include "rx_kernels.cuh"
 
 namespace {
@@ -97,6 +98,10 @@ struct rxc_ctx {
     std::vector<PendingEvent> pending;
     std::vector<cudaEvent_t> free_events;
     RxMgpu* mgpu = nullptr;       // rxc_mgpu_* state (rx_mgpu.cu)
+    RxJit* jit = nullptr;         // batch shaders compiled to straight-line code (rx_jit.cu); nullptr = interpreter only
+    int vm_jit = 1;               // RXC_VM_JIT: 0 off, 1 compile in the background, 2 compile synchronously
+    std::string jit_note;         // last compiler log / load failure (diagnostics)
+    uint32_t jit_translated = 0;  // programs of the current scene the translator accepted
     bool pj_active = false;       // rxc_rasterize_projected is running: the front end reads `pj` instead of the geometry
     ProjectedDev pj = {};
     DevBuf d_pj_pv, d_pj_uv, d_pj_nrm, d_pj_idx, d_pj_edges, d_pj_info, d_pj_bbox;
@@ -500,8 +505,21 @@ int32_t upload_vm(rxc_ctx* ctx, const rxc_scene* sc) {
         DProgram d = {};
         d.code_off = (uint32_t)code.size(); d.n_words = p.n_words; d.entry = p.entry; d.shade_locals = p.shade_locals;
         d.n_globals = p.n_globals; d.sets_opacity = p.sets_opacity ? 1u : 0u;
+        d.jit_index = 0xFFFFFFFFu;
         code.insert(code.end(), p.code, p.code + p.n_words);
         progs[i] = d;
+    }
+    // the programs as straight-line C++ for the JIT-compiled kernel variant (the interpreter runs what the translator declines)
+    if (ctx->jit) { rxj_destroy(ctx->jit); ctx->jit = nullptr; }
+    ctx->jit_translated = 0;
+    if (ctx->vm_jit && sc->n_shaders) {
+        std::string generated;
+        std::vector<uint32_t> jit_index;
+        if (rxj_generate(sc->shaders, sc->n_shaders, &generated, &jit_index)) {
+            ctx->jit_translated = 0;
+            for (uint32_t i = 0; i < sc->n_shaders; ++i) { progs[i].jit_index = jit_index[i]; if (jit_index[i] != 0xFFFFFFFFu) ++ctx->jit_translated; }
+            ctx->jit = rxj_create(generated, ctx->vm_jit);
+        }
     }
     std::vector<float> patdata;
     std::vector<DPattern> pats;
@@ -639,7 +657,13 @@ int32_t launch_group(rxc_ctx* ctx, const DFrame* h_frames, DCounters* h_counters
         const uint32_t ty1 = std::min(tiles_y, ty0 + rows_per_slice);
         const size_t slice_tiles = (size_t)(ty1 - ty0) * tiles_x;
         const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)n * slice_tiles, (size_t)ctx->sm_count * ctx->raster_blocks_per_sm));
-        { LaunchScope l(ctx, RXK_RASTER); CK(rxk_raster(S, ctx->W, out, n, ty0 * tiles_x, (uint32_t)slice_tiles, k, sample_mode, grid, ctx->stream)); }
+        void* jit_kernel = nullptr;
+        if (ctx->jit && S.general && S.vm.n_programs) {
+            std::string note;
+            jit_kernel = rxj_kernel(ctx->jit, sample_mode, d_owner || d_depth, &note);
+            if (!note.empty()) ctx->jit_note = note;
+        }
+        { LaunchScope l(ctx, RXK_RASTER); CK(rxk_raster(S, ctx->W, out, n, ty0 * tiles_x, (uint32_t)slice_tiles, k, sample_mode, grid, ctx->stream, jit_kernel)); }
         const int32_t st = after_slice(ty0 * (uint32_t)RX_TILE_H, std::min(rows_total, ty1 * (uint32_t)RX_TILE_H));
         if (st != RXC_OK) return st;
     }
@@ -929,6 +953,7 @@ int32_t rxc_create(int32_t device, rxc_ctx** out) {
     if (const char* e = getenv("RXC_PIECE_MB")) ctx->piece_mb = std::max(1, atoi(e));
     if (const char* e = getenv("RXC_SLICE_MB")) ctx->slice_mb = std::max(0, atoi(e));
     if (const char* e = getenv("RXC_TMA_STORE")) ctx->tma_store = atoi(e);
+    if (const char* e = getenv("RXC_VM_JIT")) ctx->vm_jit = std::min(2, std::max(0, atoi(e)));
     if (const char* e = getenv("RXC_FRONT_STOP")) ctx->front_stop = std::max(0, atoi(e));
     if (const char* e = getenv("RXC_SMALL_MIN_LIST")) ctx->small_min_list = atoi(e);   // 0 = pass off
     if (const char* e = getenv("RXC_SMALL_GSHIFT")) ctx->small_gshift = std::min(5, std::max(0, atoi(e)));
@@ -945,6 +970,7 @@ void rxc_destroy(rxc_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     rxi_mgpu_destroy(ctx);
+    if (ctx->jit) { rxj_destroy(ctx->jit); ctx->jit = nullptr; }
     DevBuf* bufs[] = {&ctx->d_arena, &ctx->d_tex, &ctx->d_tiles, &ctx->d_pos, &ctx->d_uv, &ctx->d_nrm, &ctx->d_idx, &ctx->d_b3,
                       &ctx->d_chunks, &ctx->d_orphans, &ctx->d_pos2, &ctx->d_uv2, &ctx->d_idx2, &ctx->d_b2, &ctx->d_lights,
                       &ctx->w_frames, &ctx->w_fb, &ctx->w_fb2, &ctx->w_lights, &ctx->w_counters, &ctx->w_vis, &ctx->w_shade,
@@ -1397,7 +1423,13 @@ int32_t rxc_vm_execute(rxc_ctx* ctx, uint32_t program, uint32_t n, const float* 
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_f, 4);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, in, (size_t)n * 18 * 4, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_f, 0, 4, ctx->stream);
-    if (e == cudaSuccess) { ctx->stats.kernel_launches++; e = rxk_vm_execute(ctx->S, program, n, d_in, d_out, d_f, ctx->stream); }
+    void* jit_kernel = nullptr;
+    if (ctx->jit) {
+        std::string note;
+        jit_kernel = rxj_kernel(ctx->jit, -1, false, &note);
+        if (!note.empty()) ctx->jit_note = note;
+    }
+    if (e == cudaSuccess) { ctx->stats.kernel_launches++; e = rxk_vm_execute(ctx->S, program, n, d_in, d_out, d_f, ctx->stream, jit_kernel); }
     uint32_t h_f = 0;
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)n * 24 * 4, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(&h_f, d_f, 4, cudaMemcpyDeviceToHost, ctx->stream);
@@ -1405,6 +1437,56 @@ int32_t rxc_vm_execute(rxc_ctx* ctx, uint32_t program, uint32_t n, const float* 
     cudaFree(d_in); cudaFree(d_out); cudaFree(d_f);
     if (e != cudaSuccess) { ctx->err = std::string("rxc_vm_execute: ") + cudaGetErrorString(e); return RXC_ERR_CUDA; }
     if (faults) *faults = h_f;
+    return RXC_OK;
+    });
+}
+
+int64_t rxc_vm_translate(const rxc_program* programs, uint32_t n_programs, char* source, uint64_t cap, uint32_t* jit_index) {
+    try {
+        if (n_programs && !programs) return RXC_ERR_INVALID;
+        std::string src;
+        std::vector<uint32_t> idx;
+        rxj_generate(programs, n_programs, &src, &idx);
+        if (jit_index) for (uint32_t i = 0; i < n_programs; ++i) jit_index[i] = idx[i];
+        if (source && cap) { const size_t n = std::min<size_t>(src.size(), (size_t)cap - 1); memcpy(source, src.data(), n); source[n] = 0; }
+        return (int64_t)src.size();
+    } catch (...) {
+        return RXC_ERR_OOM;
+    }
+}
+
+int64_t rxc_vm_jit_compile(const rxc_program* programs, uint32_t n_programs, int32_t sample_mode, int32_t planes, char* log, uint32_t log_cap) {
+    try {
+        if ((n_programs && !programs) || sample_mode < -1 || sample_mode > 2) return RXC_ERR_INVALID;
+        std::string src, msg;
+        std::vector<uint32_t> idx;
+        if (!rxj_generate(programs, n_programs, &src, &idx)) return 0;
+        const size_t bytes = rxj_compile_offline(src, sample_mode, planes != 0, &msg);
+        if (log && log_cap) { const size_t n = std::min<size_t>(msg.size(), log_cap - 1); memcpy(log, msg.data(), n); log[n] = 0; }
+        return bytes ? (int64_t)bytes : (int64_t)RXC_ERR_UNSUPPORTED;
+    } catch (...) {
+        return RXC_ERR_OOM;
+    }
+}
+
+int32_t rxc_set_vm_jit(rxc_ctx* ctx, int32_t mode) {
+    return guarded(ctx, [&]() -> int32_t {
+    if (!ctx || mode < 0 || mode > 2) return RXC_ERR_INVALID;
+    ctx->vm_jit = mode;
+    return RXC_OK;
+    });
+}
+
+int32_t rxc_vm_jit_info(rxc_ctx* ctx, uint32_t* n_translated, uint32_t* kernels_compiled, uint32_t* pending, uint64_t* jit_launches, char* log, uint32_t log_cap) {
+    return guarded(ctx, [&]() -> int32_t {
+    if (!ctx) return RXC_ERR_INVALID;
+    uint64_t compiled = 0, used = 0;
+    rxj_stats(ctx->jit, &compiled, &used);
+    if (n_translated) *n_translated = ctx->jit_translated;
+    if (kernels_compiled) *kernels_compiled = (uint32_t)compiled;
+    if (pending) *pending = rxj_idle(ctx->jit) ? 0u : 1u;
+    if (jit_launches) *jit_launches = used;
+    if (log && log_cap) { const size_t n = std::min<size_t>(ctx->jit_note.size(), log_cap - 1); memcpy(log, ctx->jit_note.data(), n); log[n] = 0; }
     return RXC_OK;
     });
 }

@@ -101,7 +101,8 @@ struct DLight {          // rxc_light + the per-frame flicker factor (light.rs:6
 struct DProgram {
     uint32_t code_off, n_words;  // words of this program inside VmDev::code
     uint32_t entry, shade_locals, n_globals, sets_opacity;
-    uint32_t pad[2];
+    uint32_t jit_index;          // which generated function runs this program in a JIT-compiled kernel, 0xFFFFFFFF = the interpreter
+    uint32_t pad;
 };
 struct DPattern {
     uint32_t off;                // first Value (3 floats) inside VmDev::pattern_data

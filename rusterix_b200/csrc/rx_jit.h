@@ -1,0 +1,22 @@
+// rx_jit.h -- interface of the batch-shader JIT (rx_jit.cu) towards rx_api.cu.  Not part of the C ABI.
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "rxcuda.h"
+
+struct RxJit;
+// C++ for the programs the translator accepts (vm_run_jit + one function per program); jit_index[i] = i or 0xFFFFFFFF.
+// Returns false when no program was accepted.
+bool rxj_generate(const rxc_program* progs, uint32_t n, std::string* source, std::vector<uint32_t>* jit_index);
+// mode: 0 off, 1 compile in the background (frames use the interpreter until the kernel is ready), 2 compile synchronously
+RxJit* rxj_create(const std::string& generated, int mode);
+void rxj_destroy(RxJit* j);
+// cudaKernel_t of k_raster<sample_mode, planes, 2> (sample_mode -1: of k_vm_execute) compiled with the generated code, or
+// nullptr (not ready / failed / off)
+void* rxj_kernel(RxJit* j, int sample_mode, bool planes, std::string* failed);
+int rxj_idle(RxJit* j);
+size_t rxj_compile_offline(const std::string& generated, int sample_mode, bool planes, std::string* log);
+void rxj_stats(RxJit* j, uint64_t* compiled, uint64_t* used);

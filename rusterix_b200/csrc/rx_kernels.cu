@@ -613,6 +613,7 @@ __device__ __forceinline__ void d_tri_setup(const SceneDev& S, const Workspace& 
     block_minmax_to_keys(mm, &FB.bb_minx, &FB.bb_maxx, &FB.bb_miny, &FB.bb_maxy);
 }
 
+#ifndef __CUDACC_RTC__   // (the JIT build recompiles k_raster only)
 // ---------------------------------------------------------------------------------------------
 // k_tri_setup_projected : rxc_rasterize_projected.  The host ran Scene::project itself (its own vek arithmetic) and hands
 // over projected_vertices / clipped_indices / clipped_uvs / clipped_normals / edges / bounding_box per batch; one thread
@@ -668,6 +669,8 @@ __global__ void __launch_bounds__(256) k_tri_setup_projected(SceneDev S, Workspa
     }
     Wk.bins[i] = bin;
 }
+
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // k_batch_finalize : one warp per (frame, batch)
@@ -981,6 +984,7 @@ __device__ __forceinline__ void d_list_sort_warp(const Workspace& Wk, int which,
 // ---------------------------------------------------------------------------------------------
 // the front-end as kernels ...
 // ---------------------------------------------------------------------------------------------
+#ifndef __CUDACC_RTC__
 __global__ void __launch_bounds__(256) k_frame_setup(SceneDev S, Workspace Wk, uint32_t tiles_per_frame) { d_frame_setup(S, Wk, tiles_per_frame, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
 __global__ void __launch_bounds__(RX_CHUNK_TRIS) k_tri_setup(SceneDev S, Workspace Wk) { d_tri_setup(S, Wk, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
 __global__ void __launch_bounds__(256) k_batch_finalize(SceneDev S, Workspace Wk) { d_batch_finalize(S, Wk, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
@@ -1069,6 +1073,8 @@ __global__ void __launch_bounds__(256) k_front_cluster(SceneDev S, Workspace Wk,
         d_list_sort_warp(Wk, 0, tiles_per_frame, Blk{r, f, R});
     }
 }
+
+#endif  // !__CUDACC_RTC__
 
 // ---------------------------------------------------------------------------------------------
 // k_raster
@@ -2724,6 +2730,27 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_vm_execute (diagnostics): one thread per record runs a program outside the rasterizer
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_vm_execute(VmDev vm, uint32_t program, uint32_t n, const float* __restrict__ in, float* __restrict__ out,
+                                                    uint32_t* faults) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* r = in + (size_t)i * 18;
+    VmIO io;
+    vm_io_reset(io);
+    io.uv = {r[0], r[1], r[2]}; io.color = {r[3], r[4], r[5]}; io.normal = {r[6], r[7], r[8]};
+    io.hitpoint = {r[9], r[10], r[11]}; io.time = {r[12], r[13], r[14]}; io.opacity = {r[15], r[16], r[17]};
+    if (!vm_run(vm, vm.programs[program], io)) atomicAdd(faults, 1u);
+    float* o = out + (size_t)i * 24;
+    const f3 v[8] = {io.uv, io.color, io.normal, io.roughness, io.metallic, io.emissive, io.opacity, io.bump};
+    for (int k = 0; k < 8; ++k) { o[3 * k] = v[k].x; o[3 * k + 1] = v[k].y; o[3 * k + 2] = v[k].z; }
+}
+
+#ifdef __CUDACC_RTC__
+}  // namespace
+#else
+// ---------------------------------------------------------------------------------------------
 // k_list_sort (general mode): one CTA per tile sorts its list ascending (= submission order).  The
 // allocation of a list is a power of two (k_tile_alloc), the tail is padded with 0xFFFFFFFF.
 // ---------------------------------------------------------------------------------------------
@@ -2801,24 +2828,6 @@ __global__ void __launch_bounds__(256) k_selftest_div(uint64_t seed, uint32_t it
         }
     }
     if (bad) atomicAdd(mismatches, (unsigned long long)bad);
-}
-
-// ---------------------------------------------------------------------------------------------
-// k_vm_execute (diagnostics): one thread per record runs a program outside the rasterizer
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_vm_execute(VmDev vm, uint32_t program, uint32_t n, const float* __restrict__ in, float* __restrict__ out,
-                                                    uint32_t* faults) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float* r = in + (size_t)i * 18;
-    VmIO io;
-    vm_io_reset(io);
-    io.uv = {r[0], r[1], r[2]}; io.color = {r[3], r[4], r[5]}; io.normal = {r[6], r[7], r[8]};
-    io.hitpoint = {r[9], r[10], r[11]}; io.time = {r[12], r[13], r[14]}; io.opacity = {r[15], r[16], r[17]};
-    if (!vm_run(vm, vm.programs[program], io)) atomicAdd(faults, 1u);
-    float* o = out + (size_t)i * 24;
-    const f3 v[8] = {io.uv, io.color, io.normal, io.roughness, io.metallic, io.emissive, io.opacity, io.bump};
-    for (int k = 0; k < 8; ++k) { o[3 * k] = v[k].x; o[3 * k + 1] = v[k].y; o[3 * k + 2] = v[k].z; }
 }
 
 }  // namespace
@@ -2911,8 +2920,14 @@ cudaError_t rxk_bin_fill(const SceneDev& S, const Workspace& W, uint32_t n_frame
     return cudaGetLastError();
 }
 cudaError_t rxk_raster(const SceneDev& S, const Workspace& W, const RasterOut& out, uint32_t n_frames, uint32_t tile0, uint32_t n_tiles,
-                       uint32_t counter, int sample_mode, int grid_x, cudaStream_t st) {
+                       uint32_t counter, int sample_mode, int grid_x, cudaStream_t st, void* jit_kernel) {
     const bool planes = out.owner || out.depth;
+    if (jit_kernel && S.general && S.vm.n_programs) {
+        // the batch-shader variant recompiled with the scene's programs as straight-line code (rx_jit.cu): same arguments
+        SceneDev s = S; Workspace w = W; RasterOut o = out;
+        void* args[] = {&s, &w, &o, &n_frames, &tile0, &n_tiles, &counter};
+        return cudaLaunchKernel((const void*)jit_kernel, dim3(grid_x), dim3(RX_TILE_THREADS), args, 0, st);
+    }
 #define RX_LAUNCH(SM, PL, MD) k_raster<SM, PL, MD><<<grid_x, RX_TILE_THREADS, 0, st>>>(S, W, out, n_frames, tile0, n_tiles, counter)
 #define RX_LAUNCH2(SM, PL) do { if (S.general && S.vm.n_programs) RX_LAUNCH(SM, PL, 2); else if (S.general) RX_LAUNCH(SM, PL, 1); else if (S.n_tris >= W.small_min_tris) RX_LAUNCH(SM, PL, 3); else RX_LAUNCH(SM, PL, 0); } while (0)
     if (sample_mode == 0) { if (planes) RX_LAUNCH2(0, true); else RX_LAUNCH2(0, false); }
@@ -2929,7 +2944,12 @@ int rxk_raster_blocks_per_sm() {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_raster<1, false, 3>, RX_TILE_THREADS, 0) == cudaSuccess && n < best) best = n;
     return best < 1 ? 1 : best;
 }
-cudaError_t rxk_vm_execute(const SceneDev& S, uint32_t program, uint32_t n, const float* d_in, float* d_out, uint32_t* d_faults, cudaStream_t st) {
+cudaError_t rxk_vm_execute(const SceneDev& S, uint32_t program, uint32_t n, const float* d_in, float* d_out, uint32_t* d_faults, cudaStream_t st, void* jit_kernel) {
+    if (jit_kernel) {
+        VmDev vm = S.vm;
+        void* args[] = {&vm, &program, &n, &d_in, &d_out, &d_faults};
+        return cudaLaunchKernel((const void*)jit_kernel, dim3((n + 127) / 128), dim3(128), args, 0, st);
+    }
     k_vm_execute<<<(n + 127) / 128, 128, 0, st>>>(S.vm, program, n, d_in, d_out, d_faults);
     return cudaGetLastError();
 }
@@ -2937,3 +2957,4 @@ cudaError_t rxk_selftest_div(uint64_t seed, uint32_t blocks, uint32_t iters, uns
     k_selftest_div<<<blocks, 256, 0, st>>>(seed, iters, d_mismatches);
     return cudaGetLastError();
 }
+#endif  // !__CUDACC_RTC__

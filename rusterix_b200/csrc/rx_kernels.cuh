@@ -115,12 +115,15 @@ enum {
     RXK_FRONT_SMALL = 10
 };
 
+#define RX_FRONT_CLUSTER 8       // CTAs of the cluster that runs a mid-sized scene's front end
+#define RX_RASTER_COUNTERS 64    // work counters of k_raster launches per call
+
+#ifndef __CUDACC_RTC__   // host-side launch interface (the JIT recompiles the device code only)
 // Each returns the cudaError_t of the launch.  `n_frames` frames are processed by one launch.
 cudaError_t rxk_frame_setup(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, cudaStream_t st);
 // the whole front-end (frame setup .. bin fill) of a small non-general scene in one launch, one CTA per frame
 cudaError_t rxk_front_small(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, cudaStream_t st);
 // the same for mid-sized scenes: a cluster of RX_FRONT_CLUSTER CTAs per frame shares every phase, cluster barriers between them
-#define RX_FRONT_CLUSTER 8
 // stop_phase: 0 = all phases; n = return after the n-th cluster barrier (profiling aid only, the frame is then incomplete)
 cudaError_t rxk_front_cluster(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, uint32_t stop_phase, cudaStream_t st);
 cudaError_t rxk_tri_setup(const SceneDev& S, const Workspace& W, uint32_t n_frames, cudaStream_t st);
@@ -139,11 +142,11 @@ cudaError_t rxk_bin_fill(const SceneDev& S, const Workspace& W, uint32_t n_frame
 // sample_mode: RXC_SAMPLE_* when every frame of the launch uses it, 2 = mixed (read per frame).  The launch covers the
 // tiles [tile0, tile0 + n_tiles) of every frame (row-major tile index: a range of tile rows is a horizontal slice of
 // the frame) and hands them out through work counter `counter` (< RX_RASTER_COUNTERS).
-#define RX_RASTER_COUNTERS 64
 cudaError_t rxk_raster(const SceneDev& S, const Workspace& W, const RasterOut& out, uint32_t n_frames, uint32_t tile0, uint32_t n_tiles,
-                       uint32_t counter, int sample_mode, int grid, cudaStream_t st);
+                       uint32_t counter, int sample_mode, int grid, cudaStream_t st, void* jit_kernel = nullptr);
 int rxk_raster_blocks_per_sm();
 // diagnostics: program `program` of S.vm on n records (18 floats in, 24 floats out each)
-cudaError_t rxk_vm_execute(const SceneDev& S, uint32_t program, uint32_t n, const float* d_in, float* d_out, uint32_t* d_faults, cudaStream_t st);
+cudaError_t rxk_vm_execute(const SceneDev& S, uint32_t program, uint32_t n, const float* d_in, float* d_out, uint32_t* d_faults, cudaStream_t st, void* jit_kernel = nullptr);
 // diagnostics: rx_div_by vs div.rn on blocks*256*iters random operand pairs; adds the mismatch count
 cudaError_t rxk_selftest_div(uint64_t seed, uint32_t blocks, uint32_t iters, unsigned long long* d_mismatches, cudaStream_t st);
+#endif  // !__CUDACC_RTC__

@@ -90,12 +90,106 @@ __device__ __noinline__ f3 vm_math2(uint32_t op, f3 a, f3 b) {
     }
 }
 
+// ---- op semantics shared by the interpreter below and by the code the JIT generates (rx_jit.cpp) ---------------------
+// One function per arity; `op` is a compile-time constant in generated code (the switch folds away) and a run-time
+// value in the interpreter.  Everything is the reference's arithmetic, op by op (execution.rs:296-742).
+#define VM_BOOL3(x) ((x) ? f3{1.0f, 1.0f, 1.0f} : f3{0.0f, 0.0f, 0.0f})
+__device__ __forceinline__ f3 vm_un(uint32_t op, f3 a) {
+    switch (op) {
+        case RXVM_ABS: return {fabsf(a.x), fabsf(a.y), fabsf(a.z)};
+        case RXVM_FLOOR: return {floorf(a.x), floorf(a.y), floorf(a.z)};
+        case RXVM_FRACT: return {a.x - floorf(a.x), a.y - floorf(a.y), a.z - floorf(a.z)};
+        case RXVM_NOT: return VM_BOOL3(a.x == 0.0f);
+        case RXVM_NEG: return {-a.x, -a.y, -a.z};
+        default: return vm_math1(op, a);   // the transcendental / rarely executed ones, out of line
+    }
+}
+__device__ __forceinline__ f3 vm_bin(uint32_t op, f3 a, f3 b) {
+    switch (op) {
+        case RXVM_ADD: return {a.x + b.x, a.y + b.y, a.z + b.z};
+        case RXVM_SUB: return {a.x - b.x, a.y - b.y, a.z - b.z};
+        case RXVM_MUL: return {a.x * b.x, a.y * b.y, a.z * b.z};
+        case RXVM_PACK2: return {a.x, b.x, 0.0f};
+        case RXVM_DOT: { const float d = a.x * b.x + a.y * b.y + a.z * b.z; return {d, d, d}; }
+        case RXVM_DOT2: return {a.x * b.x + a.y * b.y, 0.0f, 0.0f};
+        case RXVM_DOT3: return {a.x * b.x + a.y * b.y + a.z * b.z, 0.0f, 0.0f};
+        case RXVM_MIN: return {fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)};
+        case RXVM_MAX: return {fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)};
+        case RXVM_STEP: return {b.x >= a.x ? 1.0f : 0.0f, b.y >= a.y ? 1.0f : 0.0f, b.z >= a.z ? 1.0f : 0.0f};
+        case RXVM_EQ: return VM_BOOL3(a.x == b.x);
+        case RXVM_NE: return VM_BOOL3(a.x != b.x);
+        case RXVM_LT: return VM_BOOL3(a.x < b.x);
+        case RXVM_LE: return VM_BOOL3(a.x <= b.x);
+        case RXVM_GT: return VM_BOOL3(a.x > b.x);
+        case RXVM_GE: return VM_BOOL3(a.x >= b.x);
+        case RXVM_AND: return VM_BOOL3((a.x != 0.0f) & (b.x != 0.0f));
+        case RXVM_OR: return VM_BOOL3((a.x != 0.0f) | (b.x != 0.0f));
+        default: return vm_math2(op, a, b);   // Atan2, Pow, Mod, Div, Rotate2D, Cross
+    }
+}
+__device__ __forceinline__ f3 vm_tern(uint32_t op, f3 a, f3 b, f3 c) {
+    switch (op) {
+        case RXVM_PACK3: return {a.x, b.x, c.x};
+        case RXVM_MIX: return {a.x + (b.x - a.x) * c.x, a.y + (b.y - a.y) * c.y, a.z + (b.z - a.z) * c.z};
+        case RXVM_SMOOTHSTEP: {       // execution.rs:458-476
+            const float denom = b.x - a.x;
+            float u = denom != 0.0f ? (c.x - a.x) / denom : 0.0f;
+            if (u < 0.0f) u = 0.0f; else if (u > 1.0f) u = 1.0f;
+            const float sm = u * u * (3.0f - 2.0f * u);
+            return {sm, sm, sm};
+        }
+        case RXVM_CLAMP: return {rx_clamp(a.x, b.x, c.x), rx_clamp(a.y, b.y, c.y), rx_clamp(a.z, b.z, c.z)};
+        default: return a;
+    }
+}
+__device__ __forceinline__ f3 vm_get_components(uint32_t a24, f3 t) {   // execution.rs:135-157
+    const float c[4] = {t.x, t.y, t.z, 0.0f};
+    const uint32_t n = a24 & 7u, i0 = (a24 >> 3) & 3u, i1 = (a24 >> 5) & 3u, i2 = (a24 >> 7) & 3u;
+    if (n == 1u) return {c[i0], c[i0], c[i0]};
+    if (n == 2u) return {c[i0], c[i1], 0.0f};
+    if (n == 3u) return {c[i0], c[i1], c[i2]};
+    return {0.0f, 0.0f, 0.0f};
+}
+__device__ __forceinline__ f3 vm_set_components(uint32_t a24, f3 d, f3 value) {   // execution.rs:158-183
+    const float c[3] = {value.x, value.y, value.z};
+    const uint32_t n = a24 & 7u;
+    for (uint32_t i = 0; i < n && i < 3u; ++i) {
+        const uint32_t idx = (a24 >> (3u + 2u * i)) & 3u;
+        if (idx == 0u) d.x = c[i]; else if (idx == 1u) d.y = c[i]; else if (idx == 2u) d.z = c[i];
+    }
+    return d;
+}
+__device__ __forceinline__ f3 vm_sample_op(const VmDev& vm, bool normal_bank, f3 a, f3 b) {   // execution.rs:625-649
+    const uint32_t i = vm_as_index(b.x);
+    if (!normal_bank) return i < vm.n_patterns ? vm_pattern_sample(vm, vm.patterns[i], a) : f3{0.0f, 0.0f, 0.0f};
+    if (i >= vm.n_patterns_normal) return {0.0f, 0.0f, 0.0f};
+    const f3 nm3 = vm_pattern_sample(vm, vm.patterns[vm.n_patterns + i], a);
+    return {nm3.x * 2.0f - 1.0f, nm3.y * 2.0f - 1.0f, nm3.z * 2.0f - 1.0f};
+}
+
+#ifdef RXVM_JIT
+// Straight-line C++ generated from the scene's programs (rx_jit.cpp), compiled with NVRTC into its own copy of the VM
+// kernels: vm_run_jit(vm, jit_index, io) runs program `jit_index` without fetching or dispatching a single op
+// (returns 1 = done, 0 = device limit hit, 2 = hand over to the interpreter).
+#include "rx_vm_generated.inc"
+#endif
+
 // Runs the shade function of program P on `io`.  Returns false when a device limit was hit (stack,
 // frames, op budget) or the code is malformed; the reference would have panicked or looped.
 __device__ __noinline__ bool vm_run(const VmDev& vm, const DProgram& P, VmIO& io) {
     // The value stack keeps its top in registers (`t`): positions 1..sp-1 live in stack[1..sp-1], position sp in
     // `t`; stack[0] is a dummy that absorbs the spill of an empty stack's top.  A unary op then touches no memory,
     // a binary op loads one operand, a push stores one (half the local-memory traffic of a stack held in memory).
+#ifdef RXVM_JIT
+    if (P.jit_index != 0xFFFFFFFFu) {   // the program as straight-line code; 2 = its stack took a shape the translator did not verify
+        const bool may_bail = vm_jit_may_bail(P.jit_index);
+        VmIO saved;
+        if (may_bail) saved = io;
+        const int st = vm_run_jit(vm, P.jit_index, io);
+        if (st != 2) return st == 1;
+        if (may_bail) io = saved;          // ... so the interpreter runs it from the start
+    }
+#endif
     f3 stack[RXVM_STACK + 1];
     f3 locals[RXVM_LOCAL_POOL];
     f3 globals[RXVM_GLOBALS];
@@ -145,31 +239,8 @@ __device__ __noinline__ bool vm_run(const VmDev& vm, const DProgram& P, VmIO& io
             case RXVM_LOAD_GLOBAL: if (a24 >= n_globals) return false; VM_PUSHV(globals[a24]);
             case RXVM_STORE_GLOBAL: if (a24 >= n_globals) return false; VM_POPTO(globals[a24]);
             case RXVM_SWAP: { VM_NEED(2); const f3 x = stack[sp - 1]; stack[sp - 1] = t; t = x; break; }
-            case RXVM_GET_COMPONENTS: {   // execution.rs:135-157
-                VM_NEED(1);
-                const float c[4] = {t.x, t.y, t.z, 0.0f};
-                const uint32_t n = a24 & 7u, i0 = (a24 >> 3) & 3u, i1 = (a24 >> 5) & 3u, i2 = (a24 >> 7) & 3u;
-                f3 r = zero;
-                if (n == 1u) r = {c[i0], c[i0], c[i0]};
-                else if (n == 2u) r = {c[i0], c[i1], 0.0f};
-                else if (n == 3u) r = {c[i0], c[i1], c[i2]};
-                t = r;
-                break;
-            }
-            case RXVM_SET_COMPONENTS: {   // execution.rs:158-183
-                VM_NEED(2);
-                const f3 value = t;
-                f3 d = stack[sp - 1];
-                --sp;
-                const float c[3] = {value.x, value.y, value.z};
-                const uint32_t n = a24 & 7u;
-                for (uint32_t i = 0; i < n && i < 3u; ++i) {
-                    const uint32_t idx = (a24 >> (3u + 2u * i)) & 3u;
-                    if (idx == 0u) d.x = c[i]; else if (idx == 1u) d.y = c[i]; else if (idx == 2u) d.z = c[i];
-                }
-                t = d;
-                break;
-            }
+            case RXVM_GET_COMPONENTS: VM_NEED(1); t = vm_get_components(a24, t); break;
+            case RXVM_SET_COMPONENTS: { VM_NEED(2); const f3 d = stack[sp - 1]; --sp; t = vm_set_components(a24, d, t); break; }
             case RXVM_CLEAR: if (sp) { --sp; t = stack[sp]; } break;
             case RXVM_DUP: if (sp) { VM_ROOM(); stack[sp] = t; ++sp; } break;
             case RXVM_FUNCTION_CALL: {    // execution.rs:186-223
@@ -207,60 +278,23 @@ __device__ __noinline__ bool vm_run(const VmDev& vm, const DProgram& P, VmIO& io
             case RXVM_MARK: if (nm >= RXVM_MARKS) return false; marks[nm++] = sp; break;
             case RXVM_TRUNC: if (nm == 0u) return false; if (sp > marks[nm - 1]) { sp = marks[nm - 1]; t = stack[sp]; } break;
             case RXVM_UNMARK: if (nm == 0u) return false; --nm; break;
-            case RXVM_PACK2: { VM_NEED(2); const f3 y = t, x = stack[sp - 1]; --sp; t = {x.x, y.x, 0.0f}; break; }
-            case RXVM_PACK3: { VM_NEED(3); const f3 z = t, y = stack[sp - 1], x = stack[sp - 2]; sp -= 2; t = {x.x, y.x, z.x}; break; }
-            case RXVM_SUB: VM_BIN((f3{a.x - b.x, a.y - b.y, a.z - b.z}))
-            case RXVM_ABS: VM_MAP1(fabsf)
+            case RXVM_PACK3: case RXVM_MIX: case RXVM_SMOOTHSTEP: case RXVM_CLAMP: {
+                VM_NEED(3);
+                const f3 c = t, b = stack[sp - 1], a = stack[sp - 2];
+                sp -= 2;
+                t = vm_tern(op, a, b, c);
+                break;
+            }
+            case RXVM_ABS: case RXVM_FLOOR: case RXVM_FRACT: case RXVM_NOT: case RXVM_NEG:
             case RXVM_SIN: case RXVM_SIN1: case RXVM_COS1: case RXVM_SIN2: case RXVM_COS2: case RXVM_COS: case RXVM_TAN: case RXVM_ATAN:
             case RXVM_SQRT: case RXVM_LOG: case RXVM_ROUND: case RXVM_CEIL: case RXVM_RADIANS: case RXVM_DEGREES: case RXVM_LENGTH:
             case RXVM_LENGTH2: case RXVM_LENGTH3: case RXVM_NORMALIZE:
-                VM_NEED(1); t = vm_math1(op, t); break;
+                VM_NEED(1); t = vm_un(op, t); break;
+            case RXVM_PACK2: case RXVM_SUB: case RXVM_DOT: case RXVM_DOT2: case RXVM_DOT3: case RXVM_MIN: case RXVM_MAX: case RXVM_STEP:
+            case RXVM_EQ: case RXVM_NE: case RXVM_LT: case RXVM_LE: case RXVM_GT: case RXVM_GE: case RXVM_AND: case RXVM_OR:
             case RXVM_ATAN2: case RXVM_POW: case RXVM_MOD: case RXVM_DIV: case RXVM_ROTATE2D: case RXVM_CROSS: {
-                VM_NEED(2); const f3 a = stack[sp - 1]; --sp; t = vm_math2(op, a, t); break;
+                VM_NEED(2); const f3 a = stack[sp - 1]; --sp; t = vm_bin(op, a, t); break;
             }
-            case RXVM_DOT: { VM_NEED(2); const f3 b = t, a = stack[sp - 1]; --sp; const float d = a.x * b.x + a.y * b.y + a.z * b.z; t = {d, d, d}; break; }
-            case RXVM_DOT2: VM_BIN((f3{a.x * b.x + a.y * b.y, 0.0f, 0.0f}))
-            case RXVM_DOT3: VM_BIN((f3{a.x * b.x + a.y * b.y + a.z * b.z, 0.0f, 0.0f}))
-            case RXVM_FLOOR: VM_MAP1(floorf)
-            case RXVM_FRACT: VM_UN((f3{a.x - floorf(a.x), a.y - floorf(a.y), a.z - floorf(a.z)}))
-            case RXVM_MIN: VM_BIN((f3{fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)}))
-            case RXVM_MAX: VM_BIN((f3{fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)}))
-            case RXVM_MIX: {
-                VM_NEED(3);
-                const f3 c = t, b = stack[sp - 1], a = stack[sp - 2];
-                sp -= 2;
-                t = {a.x + (b.x - a.x) * c.x, a.y + (b.y - a.y) * c.y, a.z + (b.z - a.z) * c.z};
-                break;
-            }
-            case RXVM_SMOOTHSTEP: {       // execution.rs:458-476
-                VM_NEED(3);
-                const f3 c = t, b = stack[sp - 1], a = stack[sp - 2];
-                sp -= 2;
-                const float denom = b.x - a.x;
-                float u = denom != 0.0f ? (c.x - a.x) / denom : 0.0f;
-                if (u < 0.0f) u = 0.0f; else if (u > 1.0f) u = 1.0f;
-                const float sm = u * u * (3.0f - 2.0f * u);
-                t = {sm, sm, sm};
-                break;
-            }
-            case RXVM_STEP: VM_BIN((f3{b.x >= a.x ? 1.0f : 0.0f, b.y >= a.y ? 1.0f : 0.0f, b.z >= a.z ? 1.0f : 0.0f}))
-            case RXVM_CLAMP: {
-                VM_NEED(3);
-                const f3 c = t, b = stack[sp - 1], a = stack[sp - 2];
-                sp -= 2;
-                t = {rx_clamp(a.x, b.x, c.x), rx_clamp(a.y, b.y, c.y), rx_clamp(a.z, b.z, c.z)};
-                break;
-            }
-            case RXVM_EQ: VM_BIN(VM_B(a.x == b.x))
-            case RXVM_NE: VM_BIN(VM_B(a.x != b.x))
-            case RXVM_LT: VM_BIN(VM_B(a.x < b.x))
-            case RXVM_LE: VM_BIN(VM_B(a.x <= b.x))
-            case RXVM_GT: VM_BIN(VM_B(a.x > b.x))
-            case RXVM_GE: VM_BIN(VM_B(a.x >= b.x))
-            case RXVM_AND: VM_BIN(VM_B((a.x != 0.0f) & (b.x != 0.0f)))
-            case RXVM_OR: VM_BIN(VM_B((a.x != 0.0f) | (b.x != 0.0f)))
-            case RXVM_NOT: VM_UN(VM_B(a.x == 0.0f))
-            case RXVM_NEG: VM_UN((f3{-a.x, -a.y, -a.z}))
             case RXVM_PRINT: { VM_NEED(1); --sp; t = stack[sp]; break; }
             case RXVM_UV: VM_PUSHV(io.uv)
             case RXVM_SET_UV: VM_POPTO(io.uv)
@@ -280,26 +314,8 @@ __device__ __noinline__ bool vm_run(const VmDev& vm, const DProgram& P, VmIO& io
             case RXVM_SET_OPACITY: VM_POPTO(io.opacity)
             case RXVM_BUMP: VM_PUSHV(io.bump)
             case RXVM_SET_BUMP: VM_POPTO(io.bump)
-            case RXVM_SAMPLE: {           // execution.rs:625-633
-                VM_NEED(2);
-                const f3 b = t, a = stack[sp - 1];
-                --sp;
-                const uint32_t i = vm_as_index(b.x);
-                t = i < vm.n_patterns ? vm_pattern_sample(vm, vm.patterns[i], a) : zero;
-                break;
-            }
-            case RXVM_SAMPLE_NORMAL: {    // execution.rs:634-649
-                VM_NEED(2);
-                const f3 b = t, a = stack[sp - 1];
-                --sp;
-                const uint32_t i = vm_as_index(b.x);
-                f3 r = zero;
-                if (i < vm.n_patterns_normal) {
-                    const f3 nm3 = vm_pattern_sample(vm, vm.patterns[vm.n_patterns + i], a);
-                    r = {nm3.x * 2.0f - 1.0f, nm3.y * 2.0f - 1.0f, nm3.z * 2.0f - 1.0f};
-                }
-                t = r;
-                break;
+            case RXVM_SAMPLE: case RXVM_SAMPLE_NORMAL: {
+                VM_NEED(2); const f3 a = stack[sp - 1]; --sp; t = vm_sample_op(vm, op == RXVM_SAMPLE_NORMAL, a, t); break;
             }
             case RXVM_PALETTE_INDEX: {    // execution.rs:735-742: nothing is pushed for a missing colour
                 VM_NEED(1);

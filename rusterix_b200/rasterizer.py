@@ -100,6 +100,19 @@ class DeviceContext:
         self.check(self.lib.rxc_vm_execute(self.handle, int(program), len(rec), rec.ctypes.data, out.ctypes.data, C.byref(faults)))
         return out, int(faults.value)
 
+    def set_vm_jit(self, mode: int):
+        """rxc_set_vm_jit: 0 = interpreter only, 1 = batch-shader kernels compiled in the background, 2 = compiled before
+        the first frame that needs them.  Applies to scenes uploaded afterwards (the resident one is uploaded again)."""
+        self.check(self.lib.rxc_set_vm_jit(self.handle, int(mode)))
+        self._scene_key = None
+
+    def vm_jit_info(self) -> dict:
+        nt, nk, pend, used = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0), C.c_uint64(0)
+        log = C.create_string_buffer(1 << 14)
+        self.check(self.lib.rxc_vm_jit_info(self.handle, C.byref(nt), C.byref(nk), C.byref(pend), C.byref(used), log, len(log)))
+        return {"translated": int(nt.value), "kernels": int(nk.value), "pending": bool(pend.value), "launches": int(used.value),
+                "log": log.value.decode(errors="replace")}
+
     def pin_host(self, buf):
         """rxc_pin_host on a writable buffer (numpy array, bytearray ...): frames written into it then drain by DMA."""
         p, keep = _buffer_pointer(buf, 1)

@@ -480,6 +480,91 @@ def test_shaded_scene_with_emissive_against_per_fragment_oracle():
 
 
 # ------------------------------------------------------------------------------------------------
+# batch shaders compiled at run time (rx_jit.cu): the same programs as straight-line code, NVRTC-compiled
+# ------------------------------------------------------------------------------------------------
+class _JitMode:
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __enter__(self):
+        DeviceContext.get(0).set_vm_jit(self.mode)
+        return DeviceContext.get(0)
+
+    def __exit__(self, *exc):
+        import os
+        DeviceContext.get(0).set_vm_jit(int(os.environ.get("RXC_VM_JIT", "1")))
+
+
+def test_vm_jit_kernel_equals_the_interpreter_on_every_op():
+    """Every NodeOp program, 4096 random Execution states each: the generated code and the interpreter agree bit for bit
+    (they call the same vm_un / vm_bin / vm_tern functions), and the generated code is what ran."""
+    progs, scene, assets = _vm_scene()
+    recs = vm_programs.records(4096, seed=23)
+    with _JitMode(0) as ctx:
+        ctx.upload(scene, assets)
+        want = [ctx.vm_execute(k, recs) for k in range(len(progs))]
+        assert ctx.vm_jit_info()["launches"] == 0
+    with _JitMode(2) as ctx:
+        ctx.upload(scene, assets)
+        got = [ctx.vm_execute(k, recs) for k in range(len(progs))]
+        info = ctx.vm_jit_info()
+    assert info["translated"] == len(progs) and info["kernels"] == 1 and info["launches"] == len(progs), info
+    for name, (g, gf), (w, wf) in zip(progs, got, want):
+        assert gf == wf == 0, name
+        assert np.array_equal(g.view(np.uint32), w.view(np.uint32)), (name, np.abs(g - w).max())
+
+
+@pytest.mark.parametrize("sample_mode", [SampleMode.Nearest, SampleMode.Linear])
+def test_shaded_scene_jit_equals_interpreter(sample_mode):
+    """The whole batch-shader scene (3D, chunk, opacity pane, 2D programs) through the recompiled raster kernel:
+    pixels, owner and depth identical to the interpreter's frame; and parity with the oracle as before."""
+    cfg = scenes.shaded_config(640, 480, 40)
+    cfg.sample_mode = sample_mode
+    with _JitMode(0):
+        a = render_gpu(cfg.rasterizer(4), cfg.scene, cfg.assets, 640, 480, 40)
+    with _JitMode(2) as ctx:
+        b = render_gpu(cfg.rasterizer(4), cfg.scene, cfg.assets, 640, 480, 40)
+        info = ctx.vm_jit_info()
+        assert info["launches"] >= 1 and info["kernels"] >= 1 and info["translated"] >= 4, info
+        st = _run(cfg, frame=4)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2].view(np.uint32), b[2].view(np.uint32))
+    assert st["within1_frac"] > 0.999
+
+
+def test_vm_jit_background_compile_switches_kernels_between_frames():
+    """Default mode: the first frames run the interpreter while the worker thread compiles; once the kernel is there the
+    next frame uses it -- and is the same frame."""
+    import time
+    cfg = scenes.shaded_config(320, 240, 40, emissive=True)    # a program set no other test compiles
+    with _JitMode(1) as ctx:
+        first = render_gpu(cfg.rasterizer(1), cfg.scene, cfg.assets, 320, 240, 40, planes=False)
+        t0 = time.time()
+        while ctx.vm_jit_info()["pending"] and time.time() - t0 < 120:
+            time.sleep(0.2)
+        before = ctx.vm_jit_info()
+        second = render_gpu(cfg.rasterizer(1), cfg.scene, cfg.assets, 320, 240, 40, planes=False)
+        after = ctx.vm_jit_info()
+    assert not before["pending"], before
+    assert after["launches"] > before["launches"], (before, after)
+    assert np.array_equal(first[0], second[0])
+
+
+def test_vm_jit_declined_program_still_faults_through_the_interpreter():
+    from rusterix_b200 import RxcError
+    deep = [("Push", (1.0, 1.0, 1.0))] * 40 + [("Add",)] * 39 + [("SetColor",)]
+    with _JitMode(2) as ctx:
+        s = Scene()
+        s.add_shader(rvm.Program([deep], 0, 0, 0))
+        s.add_shader(rvm.Program([[("UV",), ("SetColor",)]], 0, 0, 0))
+        a = Assets.default().textures([])
+        ctx.upload(s, a)
+        _, faults = ctx.vm_execute(0, vm_programs.records(8))
+        assert faults == 8
+        out, faults = ctx.vm_execute(1, vm_programs.records(8))
+        assert faults == 0 and ctx.vm_jit_info()["translated"] == 1
+
+
+# ------------------------------------------------------------------------------------------------
 # render graph: Sky node on uncovered pixels, directional sun, brush preview (SURVEY 8f f4)
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("frame,hour", [(0, 16.5), (3, 7.0), (5, 12.0), (6, 22.0)])

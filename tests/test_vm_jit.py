@@ -1,0 +1,103 @@
+"""Batch-shader JIT (rusterix_b200/csrc/rx_jit.cu): the translator and the NVRTC compilation, no GPU needed.
+The GPU half (JIT kernel == interpreter kernel, bit for bit) is in test_parity_gpu.py."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import vm_programs
+from rusterix_b200 import _abi, _lib, scenes
+from rusterix_b200 import vm as rvm
+
+NO_JIT = 0xFFFFFFFF
+
+
+def _table(programs):
+    flat = [p.flatten() for p in programs]
+    arr = (_abi.rxc_program * max(1, len(flat)))()
+    for i, fp in enumerate(flat):
+        arr[i].code = fp.words.ctypes.data if len(fp.words) else None
+        arr[i].n_words = len(fp.words)
+        arr[i].entry, arr[i].shade_locals, arr[i].n_globals = fp.entry, fp.shade_locals, fp.n_globals
+        arr[i].sets_opacity = 1 if fp.sets_opacity else 0
+    return arr, flat
+
+
+def _translate(programs):
+    lib = _lib.load()
+    arr, flat = _table(programs)
+    idx = (C.c_uint32 * max(1, len(flat)))()
+    n = lib.rxc_vm_translate(arr, len(flat), None, 0, idx)
+    assert n > 0
+    buf = C.create_string_buffer(int(n) + 1)
+    assert lib.rxc_vm_translate(arr, len(flat), buf, len(buf), idx) == n
+    return buf.value.decode(), list(idx)[:len(flat)]
+
+
+def test_every_test_program_is_translated():
+    progs = vm_programs.all_programs()
+    src, idx = _translate(list(progs.values()))
+    assert idx == list(range(len(progs)))
+    for i in range(len(progs)):
+        assert "vmj_p%d(" % i in src
+    assert "vm_run_jit" in src and "vm_jit_may_bail" in src
+    # straight-line code: no opcode fetch, every op is a compile-time constant
+    assert "vm.code" not in src
+
+
+def test_scene_shaders_are_translated():
+    shaders = [scenes.shader_wood(), scenes.shader_marble(), scenes.shader_wood_ring(), scenes.shader_holes(),
+               scenes.shader_control_flow(), scenes.shader_control_flow(True), scenes.shader_glass_tint(), scenes.shader_2d_scanlines()]
+    _src, idx = _translate(shaders)
+    assert idx == list(range(len(shaders)))
+
+
+def test_programs_that_can_fault_stay_with_the_interpreter():
+    """What the reference would panic on (or what has no static stack shape) is not translated: the interpreter keeps
+    reporting it as a fault."""
+    deep = [("Push", (1.0, 1.0, 1.0))] * 40 + [("Add",)] * 39 + [("SetColor",)]                  # value stack deeper than 32
+    underflow = [("Add",), ("SetColor",)]                                                          # pops an empty stack
+    uneven = [("UV",), ("If", [("Push", (1.0, 1.0, 1.0))], None), ("SetColor",)]                   # stack height differs at the merge
+    good = [("UV",), ("SetColor",)]
+    progs = [rvm.Program([deep], 0, 0, 0), rvm.Program([underflow], 0, 0, 0), rvm.Program([uneven], 0, 0, 0), rvm.Program([good], 0, 0, 0)]
+    src, idx = _translate(progs)
+    assert idx == [NO_JIT, NO_JIT, NO_JIT, 3]
+    assert "vmj_p0(" not in src and "vmj_p3(" in src
+
+
+def test_palette_lookup_can_hand_over_to_the_interpreter():
+    """PaletteIndex pushes nothing for a missing colour (execution.rs:735-742): the generated code returns 2 there."""
+    progs = vm_programs.all_programs()
+    name = next((n for n, p in progs.items() if any(op[0] == "PaletteIndex" for body in p.user_functions for op in _walk(body))), None)
+    if name is None:
+        pytest.skip("no test program uses PaletteIndex")
+    src, idx = _translate([progs[name]])
+    assert idx == [0] and "return 2;" in src and "case 0u: return true;" in src
+
+
+def _walk(body):
+    for op in body:
+        yield op
+        if op[0] in ("If", "For"):
+            for arg in op[1:]:
+                if isinstance(arg, list):
+                    yield from _walk(arg)
+
+
+def test_nvrtc_compiles_the_generated_kernel(tmp_path, monkeypatch):
+    """The diagnostics kernel (k_vm_execute) with every test program as straight-line code, compiled for sm_100a here."""
+    if not any(os.path.exists(os.path.join(d, "libnvrtc.so.12")) for d in ("/usr/local/cuda/lib64", "/usr/lib/x86_64-linux-gnu")):
+        pytest.skip("libnvrtc.so.12 not installed")
+    monkeypatch.setenv("RXC_JIT_CACHE", str(tmp_path))
+    lib = _lib.load()
+    arr, flat = _table(list(vm_programs.all_programs().values()))
+    log = C.create_string_buffer(1 << 16)
+    n = lib.rxc_vm_jit_compile(arr, len(flat), -1, 0, log, len(log))
+    assert n > 0, log.value.decode()
+    cached = [f for f in os.listdir(tmp_path) if f.endswith(".cubin")]
+    assert len(cached) == 1
+    # the second request is served from the disk cache
+    assert lib.rxc_vm_jit_compile(arr, len(flat), -1, 0, log, len(log)) == n
+    # an empty table has nothing to compile
+    assert lib.rxc_vm_jit_compile(None, 0, -1, 0, log, len(log)) == 0

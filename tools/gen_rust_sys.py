@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from rusterix_b200 import _abi  # noqa: E402
 
-SCALARS = {C.c_uint8: "u8", C.c_int32: "i32", C.c_uint32: "u32", C.c_uint64: "u64", C.c_float: "f32", C.c_double: "f64"}
+SCALARS = {C.c_uint8: "u8", C.c_int32: "i32", C.c_uint32: "u32", C.c_uint64: "u64", C.c_int64: "i64", C.c_float: "f32", C.c_double: "f64"}
 STRUCTS = [v for v in vars(_abi).values() if isinstance(v, type) and issubclass(v, C.Structure) and v is not C.Structure]
 # what the void pointers of the ABI point at (the header's declared pointee types)
 VOID_FIELDS = {
@@ -36,6 +36,10 @@ ARG_NAMES = {
     "rxc_mgpu_target": ["ctx", "bytes", "rank0_ptr", "mode"],
     "rxc_mgpu_rasterize": ["ctx", "frames", "n_frames", "offset_bytes", "frame_stride_bytes", "pitch_bytes"],
     "rxc_mgpu_deliver": ["ctx", "regions", "n_regions"], "rxc_mgpu_release": ["ctx"], "rxc_mgpu_status": ["ctx", "mode", "deliveries", "timeouts"],
+    "rxc_vm_translate": ["programs", "n_programs", "source", "cap", "jit_index"],
+    "rxc_vm_jit_compile": ["programs", "n_programs", "sample_mode", "planes", "log", "log_cap"],
+    "rxc_set_vm_jit": ["ctx", "mode"],
+    "rxc_vm_jit_info": ["ctx", "n_translated", "kernels_compiled", "pending", "jit_launches", "log", "log_cap"],
     "rxc_get_stats": ["ctx", "out"], "rxc_pin_host": ["ctx", "ptr", "bytes"], "rxc_unpin_host": ["ctx", "ptr"], "rxc_reset_stats": ["ctx"], "rxc_kernel_name": ["kernel_class"],
 }
 # pointer arguments that are not the context handle: their Rust types
@@ -44,7 +48,7 @@ ARG_TYPES = {
     ("rxc_rasterize", 3): "*mut u32", ("rxc_rasterize", 4): "*mut f32", ("rxc_rasterize_projected", 4): "*mut u8",
     ("rxc_rasterize_projected", 5): "*mut u32", ("rxc_rasterize_projected", 6): "*mut f32", ("rxc_rasterize_async", 2): "*mut u8",
     ("rxc_rasterize_async", 3): "*mut u32", ("rxc_rasterize_async", 4): "*mut f32", ("rxc_rasterize_batch", 3): "*mut u8",
-    ("rxc_rasterize_batch_async", 3): "*mut u8", ("rxc_mgpu_init", 1): "*const u8", ("rxc_mgpu_target", 2): "*mut *mut c_void", ("rxc_pin_host", 1): "*mut c_void", ("rxc_unpin_host", 1): "*mut c_void", ("rxc_vm_execute", 3): "*const f32", ("rxc_vm_execute", 4): "*mut f32",
+    ("rxc_rasterize_batch_async", 3): "*mut u8", ("rxc_vm_translate", 2): "*mut c_char", ("rxc_vm_jit_info", 5): "*mut c_char", ("rxc_vm_jit_compile", 4): "*mut c_char", ("rxc_mgpu_init", 1): "*const u8", ("rxc_mgpu_target", 2): "*mut *mut c_void", ("rxc_pin_host", 1): "*mut c_void", ("rxc_unpin_host", 1): "*mut c_void", ("rxc_vm_execute", 3): "*const f32", ("rxc_vm_execute", 4): "*mut f32",
 }
 
 
