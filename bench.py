@@ -647,6 +647,9 @@ def secondary(wname, local_rank, dev, flush, steps=5, warmup=3):
     rasts = [cfg.rasterizer(i).on_device(local_rank) for i in frame_ids]
     out = torch.empty((F, cfg.height, cfg.width, 4), dtype=torch.uint8, device=dev)
     ctx = DeviceContext.get(local_rank)
+    jit = wname == "shaded1080" and os.environ.get("RXC_VM_JIT", "1") != "0"
+    if jit:
+        ctx.set_vm_jit(2)   # the scene's programs as straight-line code, compiled (NVRTC, seconds) before the first frame instead of behind it
 
     batch = Rasterizer.prepare_batch(rasts, cfg.scene, cfg.width, cfg.height, cfg.tile_size, cfg.assets, device=local_rank)
 
@@ -667,7 +670,14 @@ def secondary(wname, local_rank, dev, flush, steps=5, warmup=3):
     step(); ctx.synchronize()
     s = ctx.stats(); ctx.set_profiling(False)
     names = ctx.kernel_names()
-    return {"workload": desc, "frames_per_step": F, "ms_per_step": ms, "Mpixel_per_s": F * cfg.width * cfg.height / (ms * 1e-3) / 1e6,
+    extra = {}
+    if wname == "shaded1080":
+        info = ctx.vm_jit_info()
+        extra["vm"] = {"programs_translated": info["translated"], "jit_kernels": info["kernels"], "jit_launches": info["launches"],
+                       "mode": "NVRTC-compiled straight-line programs" if info["launches"] else "interpreter" + (": " + info["log"][:200] if info["log"] else "")}
+        if jit:
+            ctx.set_vm_jit(int(os.environ.get("RXC_VM_JIT", "1")))
+    return {**extra, "workload": desc, "frames_per_step": F, "ms_per_step": ms, "Mpixel_per_s": F * cfg.width * cfg.height / (ms * 1e-3) / 1e6,
             "frames_per_s": F / (ms * 1e-3), "triangles": cfg.counts()[1],
             "kernel_ms": {names[i]: s.kernel_ms[i] for i in range(len(names)) if s.launches[i]},
             "binned_refs": int(s.last_binned_refs), "large_tris": int(s.last_large_tris), "visible_tris": int(s.last_visible_tris)}

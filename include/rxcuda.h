@@ -475,8 +475,10 @@ int32_t rxc_mgpu_status(rxc_ctx* ctx, uint32_t* mode, uint32_t* deliveries, uint
 
 /* Batch shaders without the interpreter: rxc_set_scene translates the programs it can verify (static
  * stack heights, no run-time fault possible) to straight-line C++ and the VM variant of the raster kernel is recompiled with
- * NVRTC (libnvrtc.so.12, resolved at run time) in a background thread, cached on disk ($RXC_JIT_CACHE, else
- * $XDG_CACHE_HOME/rusterix_b200); frames use the interpreter until the kernel is ready and whenever NVRTC is missing.
+ * NVRTC.  The compiler runs in a child process (`rxjitc`, installed next to the library; libnvrtc.so.12 is resolved there, at
+ * run time) driven by a worker thread, results are cached on disk ($RXC_JIT_CACHE, else $XDG_CACHE_HOME/rusterix_b200); frames
+ * use the interpreter until the kernel is ready and whenever rxjitc / NVRTC is missing.  Exiting or unloading the library
+ * while a compilation is running kills that process.
  * Environment: RXC_VM_JIT = 0 (off) / 1 (background, default) / 2 (compile synchronously); rxc_set_vm_jit changes it for
  * the scenes set afterwards.
  * rxc_vm_translate (no context, no GPU): the generated source for a program table; jit_index[i] = i when program i was

@@ -18,5 +18,6 @@ void rxj_destroy(RxJit* j);
 // nullptr (not ready / failed / off)
 void* rxj_kernel(RxJit* j, int sample_mode, bool planes, std::string* failed);
 int rxj_idle(RxJit* j);
+void rxj_shutdown();
 size_t rxj_compile_offline(const std::string& generated, int sample_mode, bool planes, std::string* log);
 void rxj_stats(RxJit* j, uint64_t* compiled, uint64_t* used);

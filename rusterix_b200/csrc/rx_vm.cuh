@@ -49,9 +49,10 @@ __device__ __forceinline__ f3 vm_pattern_sample(const VmDev& vm, const DPattern&
     return {__ldg(d), __ldg(d + 1), __ldg(d + 2)};
 }
 
-// Transcendental and other rarely executed component-wise ops live out of line: inlined three components at a time
-// they are most of the interpreter's code size, and the dispatch loop then no longer fits the instruction cache.
-__device__ __noinline__ f3 vm_math1(uint32_t op, f3 a) {
+// Transcendental and other rarely executed component-wise ops.  The interpreter calls them out of line (vm_math1 / vm_math2):
+// inlined three components at a time they are most of its code size, and the dispatch loop then no longer fits the instruction
+// cache.  Generated code (rx_jit.cu) inlines them: `op` is a constant there and only that op's arithmetic remains.
+__device__ __forceinline__ f3 vm_math1_inline(uint32_t op, f3 a) {
     switch (op) {
         case RXVM_SIN: return {sinf(a.x), sinf(a.y), sinf(a.z)};
         case RXVM_SIN1: case RXVM_COS1: return {sinf(a.x), 0.0f, 0.0f};          // Cos1/Cos2 call sin (execution.rs:342-349)
@@ -73,7 +74,7 @@ __device__ __noinline__ f3 vm_math1(uint32_t op, f3 a) {
     }
 }
 
-__device__ __noinline__ f3 vm_math2(uint32_t op, f3 a, f3 b) {
+__device__ __forceinline__ f3 vm_math2_inline(uint32_t op, f3 a, f3 b) {
     switch (op) {
         case RXVM_ATAN2: return {atan2f(a.x, b.x), atan2f(a.y, b.y), atan2f(a.z, b.z)};
         case RXVM_POW: return {powf(a.x, b.x), powf(a.y, b.y), powf(a.z, b.z)};
@@ -90,10 +91,14 @@ __device__ __noinline__ f3 vm_math2(uint32_t op, f3 a, f3 b) {
     }
 }
 
+__device__ __noinline__ f3 vm_math1(uint32_t op, f3 a) { return vm_math1_inline(op, a); }
+__device__ __noinline__ f3 vm_math2(uint32_t op, f3 a, f3 b) { return vm_math2_inline(op, a, b); }
+
 // ---- op semantics shared by the interpreter below and by the code the JIT generates (rx_jit.cpp) ---------------------
 // One function per arity; `op` is a compile-time constant in generated code (the switch folds away) and a run-time
 // value in the interpreter.  Everything is the reference's arithmetic, op by op (execution.rs:296-742).
 #define VM_BOOL3(x) ((x) ? f3{1.0f, 1.0f, 1.0f} : f3{0.0f, 0.0f, 0.0f})
+template <bool INL = false>
 __device__ __forceinline__ f3 vm_un(uint32_t op, f3 a) {
     switch (op) {
         case RXVM_ABS: return {fabsf(a.x), fabsf(a.y), fabsf(a.z)};
@@ -101,9 +106,10 @@ __device__ __forceinline__ f3 vm_un(uint32_t op, f3 a) {
         case RXVM_FRACT: return {a.x - floorf(a.x), a.y - floorf(a.y), a.z - floorf(a.z)};
         case RXVM_NOT: return VM_BOOL3(a.x == 0.0f);
         case RXVM_NEG: return {-a.x, -a.y, -a.z};
-        default: return vm_math1(op, a);   // the transcendental / rarely executed ones, out of line
+        default: return INL ? vm_math1_inline(op, a) : vm_math1(op, a);   // the transcendental / rarely executed ones
     }
 }
+template <bool INL = false>
 __device__ __forceinline__ f3 vm_bin(uint32_t op, f3 a, f3 b) {
     switch (op) {
         case RXVM_ADD: return {a.x + b.x, a.y + b.y, a.z + b.z};
@@ -124,7 +130,7 @@ __device__ __forceinline__ f3 vm_bin(uint32_t op, f3 a, f3 b) {
         case RXVM_GE: return VM_BOOL3(a.x >= b.x);
         case RXVM_AND: return VM_BOOL3((a.x != 0.0f) & (b.x != 0.0f));
         case RXVM_OR: return VM_BOOL3((a.x != 0.0f) | (b.x != 0.0f));
-        default: return vm_math2(op, a, b);   // Atan2, Pow, Mod, Div, Rotate2D, Cross
+        default: return INL ? vm_math2_inline(op, a, b) : vm_math2(op, a, b);   // Atan2, Pow, Mod, Div, Rotate2D, Cross
     }
 }
 __device__ __forceinline__ f3 vm_tern(uint32_t op, f3 a, f3 b, f3 c) {
@@ -174,6 +180,10 @@ __device__ __forceinline__ f3 vm_sample_op(const VmDev& vm, bool normal_bank, f3
 #include "rx_vm_generated.inc"
 #endif
 
+#if defined(RXVM_JIT) && RXVM_JIT_COMPLETE
+// every program of the scene is generated code: no interpreter in this kernel
+__device__ __forceinline__ bool vm_run(const VmDev& vm, const DProgram& P, VmIO& io) { return vm_run_jit(vm, P.jit_index, io) == 1; }
+#else
 // Runs the shade function of program P on `io`.  Returns false when a device limit was hit (stack,
 // frames, op budget) or the code is malformed; the reference would have panicked or looped.
 __device__ __noinline__ bool vm_run(const VmDev& vm, const DProgram& P, VmIO& io) {
@@ -342,3 +352,4 @@ __device__ __noinline__ bool vm_run(const VmDev& vm, const DProgram& P, VmIO& io
 #undef VM_POPTO
 #undef VM_B
 }
+#endif  // !(RXVM_JIT && RXVM_JIT_COMPLETE)

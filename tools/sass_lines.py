@@ -17,8 +17,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def disasm_functions(kernel):
     """{mangled name: [source line of every instruction]} for the functions whose name contains `kernel`."""
     with tempfile.TemporaryDirectory() as td:
-        subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "rusterix_b200", "librxcuda.so")], cwd=td, capture_output=True)
-        cubin = [f for f in os.listdir(td) if f.startswith("rx_kernels")][0]
+        jit = os.environ.get("RX_SASS_CUBIN")   # a kernel the batch-shader JIT compiled (cache file: u32 name length, name, cubin)
+        if jit:
+            data = open(jit, "rb").read()
+            n = int.from_bytes(data[:4], "little")
+            cubin = "jit.cubin"
+            open(os.path.join(td, cubin), "wb").write(data[4 + n:] if n < 512 and data[4 + n:8 + n] == b"\x7fELF" else data)
+        else:
+            subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "rusterix_b200", "librxcuda.so")], cwd=td, capture_output=True)
+            cubin = [f for f in os.listdir(td) if f.startswith("rx_kernels")][0]
         txt = subprocess.run(["nvdisasm", "-g", "-c", cubin], cwd=td, capture_output=True, text=True).stdout
     funcs, cur, name = {}, None, None
     for line in txt.splitlines():
