@@ -98,8 +98,12 @@ struct rxc_ctx {
     std::vector<PendingEvent> pending;
     std::vector<cudaEvent_t> free_events;
     RxMgpu* mgpu = nullptr;       // rxc_mgpu_* state (rx_mgpu.cu)
-    RxJit* jit = nullptr;         // batch shaders compiled to straight-line code (rx_jit.cu); nullptr = interpreter only
+    RxJit* jit = nullptr;         // kernels recompiled for the current scene (rx_jit.cu): batch shaders as straight-line code, scene constants folded
     int vm_jit = 1;               // RXC_VM_JIT: 0 off, 1 compile in the background, 2 compile synchronously
+    int kernel_spec = 1;          // RXC_KERNEL_SPEC: 1 = the raster kernel is also recompiled with the scene's / frame's constants folded in
+    std::string spec_scene;       // -D switches of the current scene's batches (set_scene), of its lights (set_lights)
+    std::string spec_lights;
+    bool spec_mismatch = false;   // a specialised kernel found a scene it was not compiled for (a bug): specialisation stays off
     std::string jit_note;         // last compiler log / load failure (diagnostics)
     uint32_t jit_translated = 0;  // programs of the current scene the translator accepted
     bool pj_active = false;       // rxc_rasterize_projected is running: the front end reads `pj` instead of the geometry
@@ -257,6 +261,40 @@ int32_t upload_textures(rxc_ctx* ctx) {
     return upload_chunks(ctx, toff);
 }
 
+// What a kernel recompiled for this scene may treat as constants (k_raster's RX_SPEC_* switches): the
+// shade-descriptor flag bits k_frame_setup derives from static batch state and that are the same on every 3D batch, and
+// whether any fragment can be alpha-tested at all.  Mirrors d_frame_setup (rx_kernels.cu); the specialised kernel re-checks it.
+std::string scene_signature(rxc_ctx* ctx, bool any_vm_opacity) {
+    if (ctx->h_b3.empty()) return std::string();
+    uint32_t all = 0xFFFFFFFFu, any = 0u, unknown = 0u;
+    for (const DBatch3& B : ctx->h_b3) {
+        uint32_t f = B.has_normals ? RX_SD_NORMALS : 0u;
+        if (B.repeat_mode == RXC_REPEAT_REPEAT_XY || B.repeat_mode == RXC_REPEAT_REPEAT_X) f |= RX_SD_REPEAT_X;
+        if (B.repeat_mode == RXC_REPEAT_REPEAT_XY || B.repeat_mode == RXC_REPEAT_REPEAT_Y) f |= RX_SD_REPEAT_Y;
+        if (B.source_kind == RXC_SRC_STATIC_TILE || B.source_kind == RXC_SRC_DYNAMIC_TILE) f |= RX_SD_TEXTURED;   // validated: they resolve
+        else if (B.source_kind == RXC_SRC_ENTITY_TILE || B.source_kind == RXC_SRC_ITEM_TILE) unknown |= RX_SD_TEXTURED;   // may not resolve
+        else if (B.source_kind == RXC_SRC_TERRAIN) unknown |= RX_SD_TERRAIN;   // depends on the chunk's terrain texture
+        all &= f; any |= f;
+    }
+    const uint32_t bits = RX_SD_TEXTURED | RX_SD_REPEAT_X | RX_SD_REPEAT_Y | RX_SD_NORMALS | RX_SD_TERRAIN;
+    const uint32_t known = bits & ~unknown & ~(all ^ any);   // the same on every batch
+    std::string d = "-DRX_SPEC_FLAGS_KNOWN=" + std::to_string(known) + "u -DRX_SPEC_FLAGS_VALUE=" + std::to_string(all & known) + "u";
+    bool opaque = !any_vm_opacity;
+    for (const DTex& t : ctx->h_static_tex) opaque = opaque && t.all_opaque;
+    for (const DTex& t : ctx->h_dyn_tex) opaque = opaque && t.all_opaque;
+    if (opaque) d += " -DRX_SPEC_NO_ALPHA=1";
+    return d;
+}
+
+std::string lights_signature(const std::vector<DLight>& h) {
+    std::string d;
+    if (h.size() <= 4) d = "-DRX_SPEC_NLIGHTS=" + std::to_string(h.size());   // unrolled; more (or a count that keeps changing) stay a loop
+    bool one_type = !h.empty();
+    for (const DLight& l : h) one_type = one_type && l.light_type == h[0].light_type;
+    if (one_type) d += std::string(d.empty() ? "" : " ") + "-DRX_SPEC_LIGHT_TYPE=" + std::to_string(h[0].light_type);
+    return d;
+}
+
 int32_t upload_lights(rxc_ctx* ctx, const rxc_light* lights, uint32_t n) {
     std::vector<DLight> h(n);
     for (uint32_t i = 0; i < n; ++i) {
@@ -277,6 +315,7 @@ int32_t upload_lights(rxc_ctx* ctx, const rxc_light* lights, uint32_t n) {
     if (st != RXC_OK) return st;
     ctx->S.lights = ctx->d_lights.as<DLight>();
     ctx->S.n_lights = n;
+    ctx->spec_lights = lights_signature(h);
     return RXC_OK;
 }
 
@@ -510,16 +549,24 @@ int32_t upload_vm(rxc_ctx* ctx, const rxc_scene* sc) {
         progs[i] = d;
     }
     // the programs as straight-line C++ for the JIT-compiled kernel variant (the interpreter runs what the translator declines)
-    if (ctx->jit) { rxj_destroy(ctx->jit); ctx->jit = nullptr; }
     ctx->jit_translated = 0;
-    if (ctx->vm_jit && sc->n_shaders) {
+    if (ctx->vm_jit) {
         std::string generated;
         std::vector<uint32_t> jit_index;
-        if (rxj_generate(sc->shaders, sc->n_shaders, &generated, &jit_index)) {
-            ctx->jit_translated = 0;
+        if (sc->n_shaders && rxj_generate(sc->shaders, sc->n_shaders, &generated, &jit_index)) {
             for (uint32_t i = 0; i < sc->n_shaders; ++i) { progs[i].jit_index = jit_index[i]; if (jit_index[i] != 0xFFFFFFFFu) ++ctx->jit_translated; }
-            ctx->jit = rxj_create(generated, ctx->vm_jit);
+        } else {
+            generated.clear();
         }
+        if (ctx->jit) rxj_set_programs(ctx->jit, generated, ctx->vm_jit);
+        else if (!generated.empty() || ctx->kernel_spec) ctx->jit = rxj_create(generated, ctx->vm_jit);
+    } else if (ctx->jit) {
+        rxj_set_programs(ctx->jit, std::string(), 0);
+    }
+    {
+        bool any_vm_opacity = false;
+        for (uint32_t i = 0; i < sc->n_shaders; ++i) any_vm_opacity = any_vm_opacity || sc->shaders[i].sets_opacity;
+        ctx->spec_scene = scene_signature(ctx, any_vm_opacity);
     }
     std::vector<float> patdata;
     std::vector<DPattern> pats;
@@ -658,9 +705,23 @@ int32_t launch_group(rxc_ctx* ctx, const DFrame* h_frames, DCounters* h_counters
         const size_t slice_tiles = (size_t)(ty1 - ty0) * tiles_x;
         const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)n * slice_tiles, (size_t)ctx->sm_count * ctx->raster_blocks_per_sm));
         void* jit_kernel = nullptr;
-        if (ctx->jit && S.general && S.vm.n_programs) {
-            std::string note;
-            jit_kernel = rxj_kernel(ctx->jit, sample_mode, d_owner || d_depth, &note);
+        const int raster_mode = rxk_raster_mode(S, ctx->W);
+        const bool spec = ctx->kernel_spec && !ctx->spec_mismatch;
+        if (ctx->jit && (raster_mode == 2 || spec)) {
+            std::string defines, note;
+            if (spec) {
+                // what all frames of this launch agree on (RX_FS_* of rx_kernels.cu)
+                uint32_t known = 63u, value = 0u;
+                auto bits = [&](const DFrame& F) {
+                    return (F.has_ambient ? 1u : 0u) | (F.sun_radiance > 0.0f ? 2u : 0u) | ((F.has_sky | F.has_brush) ? 4u : 0u) | (F.d3_active ? 8u : 0u) |
+                           ((F.d2_active && S.n_rec2d != 0u) ? 16u : 0u) | (S.n_sectors ? 32u : 0u);
+                };
+                value = bits(h_frames[0]);
+                for (uint32_t i = 1; i < n; ++i) known &= ~(bits(h_frames[i]) ^ value);
+                defines = "-DRX_SPEC_ACTIVE=1" + (ctx->spec_scene.empty() ? "" : " " + ctx->spec_scene) + (ctx->spec_lights.empty() ? "" : " " + ctx->spec_lights) +
+                          " -DRX_SPEC_FRAME_KNOWN=" + std::to_string(known) + "u -DRX_SPEC_FRAME_VALUE=" + std::to_string(value & known) + "u";
+            }
+            jit_kernel = rxj_kernel(ctx->jit, sample_mode, d_owner || d_depth, raster_mode, defines, &note);
             if (!note.empty()) ctx->jit_note = note;
         }
         { LaunchScope l(ctx, RXK_RASTER); CK(rxk_raster(S, ctx->W, out, n, ty0 * tiles_x, (uint32_t)slice_tiles, k, sample_mode, grid, ctx->stream, jit_kernel)); }
@@ -696,6 +757,10 @@ int32_t check_group(rxc_ctx* ctx, const DCounters* h_counters, uint32_t n, bool*
         *retry = true;
     }
     if (ov & 6u) return fail(ctx, RXC_ERR_OOM, "internal list overflow (large/clip); this is a bug");
+    if (ov & 32u) {
+        ctx->spec_mismatch = true;   // never expected: the library's generic kernels from here on
+        return fail(ctx, RXC_ERR_CUDA, "a scene-specialised raster kernel ran on a scene or frame it was not compiled for (internal error; specialisation is now off for this context, render the frame again)");
+    }
     if (ov & 16u) return fail(ctx, RXC_ERR_UNSUPPORTED, "a batch shader exceeded a device VM limit (stack 32, call depth 8, 2^20 ops) or popped an empty stack");
     return RXC_OK;
 }
@@ -954,6 +1019,7 @@ int32_t rxc_create(int32_t device, rxc_ctx** out) {
     if (const char* e = getenv("RXC_SLICE_MB")) ctx->slice_mb = std::max(0, atoi(e));
     if (const char* e = getenv("RXC_TMA_STORE")) ctx->tma_store = atoi(e);
     if (const char* e = getenv("RXC_VM_JIT")) ctx->vm_jit = std::min(2, std::max(0, atoi(e)));
+    if (const char* e = getenv("RXC_KERNEL_SPEC")) ctx->kernel_spec = atoi(e) != 0;
     if (const char* e = getenv("RXC_FRONT_STOP")) ctx->front_stop = std::max(0, atoi(e));
     if (const char* e = getenv("RXC_SMALL_MIN_LIST")) ctx->small_min_list = atoi(e);   // 0 = pass off
     if (const char* e = getenv("RXC_SMALL_GSHIFT")) ctx->small_gshift = std::min(5, std::max(0, atoi(e)));
@@ -1426,7 +1492,7 @@ int32_t rxc_vm_execute(rxc_ctx* ctx, uint32_t program, uint32_t n, const float* 
     void* jit_kernel = nullptr;
     if (ctx->jit) {
         std::string note;
-        jit_kernel = rxj_kernel(ctx->jit, -1, false, &note);
+        jit_kernel = ctx->jit_translated ? rxj_kernel(ctx->jit, -1, false, 2, std::string(), &note) : nullptr;
         if (!note.empty()) ctx->jit_note = note;
     }
     if (e == cudaSuccess) { ctx->stats.kernel_launches++; e = rxk_vm_execute(ctx->S, program, n, d_in, d_out, d_f, ctx->stream, jit_kernel); }
@@ -1461,7 +1527,7 @@ int64_t rxc_vm_jit_compile(const rxc_program* programs, uint32_t n_programs, int
         std::string src, msg;
         std::vector<uint32_t> idx;
         if (!rxj_generate(programs, n_programs, &src, &idx)) return 0;
-        const size_t bytes = rxj_compile_offline(src, sample_mode, planes != 0, &msg);
+        const size_t bytes = rxj_compile_offline(src, sample_mode, planes != 0, 2, std::string(), &msg);
         if (log && log_cap) { const size_t n = std::min<size_t>(msg.size(), log_cap - 1); memcpy(log, msg.data(), n); log[n] = 0; }
         return bytes ? (int64_t)bytes : (int64_t)RXC_ERR_UNSUPPORTED;
     } catch (...) {

@@ -12,12 +12,13 @@ struct RxJit;
 // Returns false when no program was accepted.
 bool rxj_generate(const rxc_program* progs, uint32_t n, std::string* source, std::vector<uint32_t>* jit_index);
 // mode: 0 off, 1 compile in the background (frames use the interpreter until the kernel is ready), 2 compile synchronously
-RxJit* rxj_create(const std::string& generated, int mode);
+RxJit* rxj_create(const std::string& generated, int mode);   // one per context; the kernels it loads outlive the scenes
+void rxj_set_programs(RxJit* j, const std::string& generated, int mode);   // a new scene's programs (may be empty)
 void rxj_destroy(RxJit* j);
-// cudaKernel_t of k_raster<sample_mode, planes, 2> (sample_mode -1: of k_vm_execute) compiled with the generated code, or
-// nullptr (not ready / failed / off)
-void* rxj_kernel(RxJit* j, int sample_mode, bool planes, std::string* failed);
+// cudaKernel_t of k_raster<sample_mode, planes, raster_mode> compiled with `defines` (space-separated -D switches: the scene's
+// constants) and, for raster mode 2, the generated code -- sample_mode -1: of k_vm_execute -- or nullptr (not ready / failed / off)
+void* rxj_kernel(RxJit* j, int sample_mode, bool planes, int raster_mode, const std::string& defines, std::string* failed);
 int rxj_idle(RxJit* j);
 void rxj_shutdown();
-size_t rxj_compile_offline(const std::string& generated, int sample_mode, bool planes, std::string* log);
+size_t rxj_compile_offline(const std::string& generated, int sample_mode, bool planes, int raster_mode, const std::string& defines, std::string* log);
 void rxj_stats(RxJit* j, uint64_t* compiled, uint64_t* used);

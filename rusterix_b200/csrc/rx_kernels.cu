@@ -1106,6 +1106,41 @@ __global__ void __launch_bounds__(256) k_front_cluster(SceneDev S, Workspace Wk,
                                 // (128 GPU parity tests, owner and depth bit for bit) and measured slower: the bounds cost every record what the
                                 // culled sky fragments save -- map 4K 1.312 -> 1.320 ms, dense 8K 0.828 -> 0.839, teapot 0.213 -> 0.210
 #endif
+// ---- scene / frame specialisation (rx_jit.cu): a kernel recompiled for one scene knows these as constants ------------------
+// RX_SPEC_FLAGS_KNOWN / _VALUE: shade-descriptor flag bits that are the same on every batch; RX_SPEC_NLIGHTS; RX_SPEC_LIGHT_TYPE
+// (every light has this type); RX_SPEC_FRAME_KNOWN / _VALUE over the RX_FS_* bits below.  Undefined = read at run time.
+#define RX_FS_AMBIENT 1u
+#define RX_FS_SUN 2u
+#define RX_FS_SKY_OR_BRUSH 4u
+#define RX_FS_D3 8u
+#define RX_FS_D2 16u
+#define RX_FS_SECTORS 32u
+#ifndef RX_SPEC_FLAGS_KNOWN
+#define RX_SPEC_FLAGS_KNOWN 0u
+#define RX_SPEC_FLAGS_VALUE 0u
+#endif
+#ifndef RX_SPEC_FRAME_KNOWN
+#define RX_SPEC_FRAME_KNOWN 0u
+#define RX_SPEC_FRAME_VALUE 0u
+#endif
+#ifdef RX_SPEC_NO_ALPHA           // no texture of the scene has a texel with alpha < 255 and no program writes opacity: no alpha test anywhere
+#define RX_K_META_ALPHA(m) 0u
+#else
+#define RX_K_META_ALPHA(m) ((m) & RX_META_ALPHA)
+#endif
+#define RX_K_FLAGS(x) (((x) & ~RX_SPEC_FLAGS_KNOWN) | RX_SPEC_FLAGS_VALUE)
+#define RX_K_FS(bit, x) ((RX_SPEC_FRAME_KNOWN & (bit)) ? ((RX_SPEC_FRAME_VALUE & (bit)) != 0u) : (bool)(x))
+#ifdef RX_SPEC_NLIGHTS
+#define RX_K_NLIGHTS(x) ((uint32_t)RX_SPEC_NLIGHTS)
+#else
+#define RX_K_NLIGHTS(x) (x)
+#endif
+#ifdef RX_SPEC_LIGHT_TYPE
+#define RX_K_LIGHT_TYPE(x) ((uint32_t)RX_SPEC_LIGHT_TYPE)
+#else
+#define RX_K_LIGHT_TYPE(x) (x)
+#endif
+
 #define RX_LARGE_CACHE 160   // large-triangle records kept in shared memory across the tiles of a frame
 #define RX_COLOR_STRIDE 40   // words per tile row in shared memory: the 4 rows a warp writes hit disjoint banks
 
@@ -1275,7 +1310,7 @@ __device__ __forceinline__ bool light_radiance_fast(const DLight& l, float n_dot
     if (!l.emitting) return false;
     float att;      // scalar applied to the light colour
     bool lambert = true;
-    switch (l.light_type) {
+    switch (RX_K_LIGHT_TYPE(l.light_type)) {
         case RXC_LIGHT_POINT:
             if (dist >= l.end_distance) return false;
             att = l.intensity * l.flicker_factor;
@@ -1335,7 +1370,7 @@ __device__ __forceinline__ uint32_t shade_owner(const SceneDev& S, const ShadeCo
     const float4 s0 = __ldg(sq), s1 = __ldg(sq + 1), s2 = __ldg(sq + 2);
     const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(&FB.sd_tex_word));
     const float4 d1 = __ldg(reinterpret_cast<const float4*>(&FB.sd_ambient[0]));
-    const uint32_t flags = d0.z;
+    const uint32_t flags = RX_K_FLAGS(d0.z);
     const float gamma = 1.0f - alpha - beta;
 
     uint32_t texel = d0.w;
@@ -1372,7 +1407,7 @@ __device__ __forceinline__ uint32_t shade_owner(const SceneDev& S, const ShadeCo
 
     if (flags & RX_SD_TERRAIN) {
         texel = terrain_sample(S.arena, d0.x, d0.y, S.chunk_info[__float_as_int(d1.w)], world.x, world.z);
-        if (K.has_brush) texel = brush_terrain(texel, world, K.brush, K.brush_falloff);
+        if (RX_K_FS(RX_FS_SKY_OR_BRUSH, K.has_brush) && K.has_brush) texel = brush_terrain(texel, world, K.brush, K.brush_falloff);
     }
 
     f3 normal = {0.0f, 0.0f, 0.0f};
@@ -1399,15 +1434,16 @@ __device__ __forceinline__ uint32_t shade_owner(const SceneDev& S, const ShadeCo
     f3 amb = {d1.x, d1.y, d1.z};                                                        // :1368-1370
     const float4 ks = *reinterpret_cast<const float4*>(&K.sun_l[0]);
     float occ = 1.0f;  // :1327-1365: the sky and sun terms are scaled by the sector occlusion (0 when it is not > 0)
-    if ((K.has_ambient || ks.w > 0.0f) && S.n_sectors) { const float o = sector_occlusion(S, __float_as_int(d1.w), world.x, world.z); occ = o > 0.0f ? o : 0.0f; }
-    if (K.has_ambient) amb = {__fmaf_rn(ka.x, occ, amb.x), __fmaf_rn(ka.y, occ, amb.y), __fmaf_rn(ka.z, occ, amb.z)};
+    const bool has_ambient = RX_K_FS(RX_FS_AMBIENT, K.has_ambient), has_sun = RX_K_FS(RX_FS_SUN, ks.w > 0.0f);
+    if ((has_ambient || has_sun) && RX_K_FS(RX_FS_SECTORS, S.n_sectors)) { const float o = sector_occlusion(S, __float_as_int(d1.w), world.x, world.z); occ = o > 0.0f ? o : 0.0f; }
+    if (has_ambient) amb = {__fmaf_rn(ka.x, occ, amb.x), __fmaf_rn(ka.y, occ, amb.y), __fmaf_rn(ka.z, occ, amb.z)};
     f3 lit = {amb.x * kd.x * hemi, amb.y * kd.y * hemi, amb.z * kd.z * hemi};
 
     const float n_dot_v = fmaxf(fdot3(normal, view_dir), 0.0f);
     const float om = 1.0f - fminf(n_dot_v, 1.0f);
     const float om2 = om * om;
     const float fr = __fmaf_rn(1.0f - 0.04f, om2 * om2 * om, 0.04f);  // schlick_fresnel with f0 = 0.04 (:1882-1887)
-    if (ks.w > 0.0f) {  // directional sun, rasterizer.rs:1342-1361
+    if (has_sun) {  // directional sun, rasterizer.rs:1342-1361
         const f3 ldir = {ks.x, ks.y, ks.z};
         const float n_dot_l = fmaxf(fdot3(normal, ldir), 0.0f);
         if (n_dot_l > 0.0f) {
@@ -1419,7 +1455,7 @@ __device__ __forceinline__ uint32_t shade_owner(const SceneDev& S, const ShadeCo
             lit = {__fmaf_rn(kd.x + spec, w, lit.x), __fmaf_rn(kd.y + spec, w, lit.y), __fmaf_rn(kd.z + spec, w, lit.z)};
         }
     }
-    const uint32_t n_lights = __float_as_uint(ka.w);
+    const uint32_t n_lights = RX_K_NLIGHTS(__float_as_uint(ka.w));
     for (uint32_t li = 0; li < n_lights; ++li) {  // rasterizer.rs:1373-1391
         const DLight& L = lights[li];
         const f3 to_l = {L.px - world.x, L.py - world.y, L.pz - world.z};
@@ -2014,7 +2050,7 @@ __device__ __forceinline__ void test_fragment(const SceneDev& S, const DFrame& F
     // sequential `z < zbuf` in submission order == lexicographic min of (z, ordinal)
     const bool pass_z = (z < best_z) || (z == best_z && best != RX_OWNER_NONE && slot < best);
     if (!pass_z) return;
-    if (meta & RX_META_ALPHA) {  // alpha test: texel alpha must be 255 to write (:1408)
+    if (RX_K_META_ALPHA(meta)) {  // alpha test: texel alpha must be 255 to write (:1408)
         const uint32_t texel = alpha_test_texel<VM>(S, S.arena, S.chunk_info, &F, fbs + (meta & RX_META_BATCH), shade + slot, alpha, beta, z,
                                                          fpx, fpy, sample_mode);
         if ((texel >> 24) != 255u) return;
@@ -2224,7 +2260,7 @@ __device__ __noinline__ void small_triangle_pass(const SceneDev& S, const DFrame
             const unsigned long long key = ((unsigned long long)z_order_bits(z) << 32) | slot;
             unsigned long long* cell = s_key + (y - ty0) * RX_TILE_W + (x - tx0);
             if (key >= *reinterpret_cast<volatile unsigned long long*>(cell)) continue;
-            if (meta & RX_META_ALPHA) {  // alpha test: texel alpha must be 255 to write (:1408)
+            if (RX_K_META_ALPHA(meta)) {  // alpha test: texel alpha must be 255 to write (:1408)
                 const uint32_t texel = alpha_test_texel<false>(S, S.arena, S.chunk_info, &F, fbs + (meta & RX_META_BATCH), shade + slot, al, be, z,
                                                                fpx, fpy, sample_mode);
                 if ((texel >> 24) != 255u) continue;
@@ -2393,6 +2429,32 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                     mbar_phase ^= 1u;
                 }
             }
+#ifdef RX_SPEC_ACTIVE
+            // A kernel compiled for one scene / frame signature (rx_jit.cu) checks, once per frame and CTA, that what it was told is
+            // what it finds: a mismatch would render silently wrong pixels, so it is reported like an overflow (bit 5) instead.
+            {
+                bool bad = false;
+                const DFrameBatch* fbg = Wk.fb + (size_t)f * Wk.fb_stride;
+                for (uint32_t b = tid; b < S.n_b3; b += RX_TILE_THREADS) {
+                    bad = bad || (fbg[b].sd_flags & RX_SPEC_FLAGS_KNOWN) != RX_SPEC_FLAGS_VALUE;
+#ifdef RX_SPEC_NO_ALPHA
+                    bad = bad || fbg[b].alpha_test != 0u;
+#endif
+                }
+#ifdef RX_SPEC_LIGHT_TYPE
+                for (uint32_t i = tid; i < S.n_lights; i += RX_TILE_THREADS) bad = bad || lights_gg[i].light_type != (uint32_t)RX_SPEC_LIGHT_TYPE;
+#endif
+                if (tid == 0) {
+#ifdef RX_SPEC_NLIGHTS
+                    bad = bad || S.n_lights != (uint32_t)RX_SPEC_NLIGHTS;
+#endif
+                    const uint32_t fs = (Fg.has_ambient ? RX_FS_AMBIENT : 0u) | (Fg.sun_radiance > 0.0f ? RX_FS_SUN : 0u) | ((Fg.has_sky | Fg.has_brush) ? RX_FS_SKY_OR_BRUSH : 0u) |
+                                        (Fg.d3_active ? RX_FS_D3 : 0u) | ((Fg.d2_active && S.n_rec2d != 0u) ? RX_FS_D2 : 0u) | (S.n_sectors ? RX_FS_SECTORS : 0u);
+                    bad = bad || (fs & RX_SPEC_FRAME_KNOWN) != RX_SPEC_FRAME_VALUE;
+                }
+                if (bad) atomicOr(&Wk.counters[f].overflow, 32u);
+            }
+#endif
             cached_frame = f;
             __syncthreads();
             if (!GENERAL && warp < 2u) {
@@ -2492,7 +2554,7 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
         }
         O.some = 0u;
 
-        if (F.d3_active) {
+        if (RX_K_FS(RX_FS_D3, F.d3_active)) {
             // Three sources of triangle records, one walk: (0) the large triangles cached in shared memory (culled
             // per tile by the CTA when there are many), (1) the rest of the large list, (2) the tile's binned list.
             // Warp-private: every lane fetches one record and tests it against the warp's region, the survivors are
@@ -2641,7 +2703,7 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                 }
             }
 #endif
-            if (F.d3_active) {
+            if (RX_K_FS(RX_FS_D3, F.d3_active)) {
                 if (owner != RX_OWNER_NONE) {
                     const uint32_t b = __ldg(&vis[owner].meta) & RX_META_BATCH;
                     if (VM && (fbs[b].sd_flags & RX_SD_SHADER))
@@ -2650,7 +2712,7 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
                         color = shade_owner(S, s_k, lights, s_kd, fbs[b], shade + owner, st.z, st.w, st.x, fpx, fpy, smode);
                 } else {
                     color = 0xFF000000u;  // vec4_to_pixel((0,0,0,1))
-                    if (F.has_sky | F.has_brush) color = miss_color(&F, px, py);
+                    if (RX_K_FS(RX_FS_SKY_OR_BRUSH, F.has_sky | F.has_brush)) color = miss_color(&F, px, py);
                 }
                 if (GENERAL) {
                     const float2 os = s_ostate[k * RX_TILE_THREADS + tid];
@@ -2671,7 +2733,7 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
         }
 
         // 2D pass in submission order (rasterizer.rs:501-553) over the thread's own pixels in s_color
-        if (F.d2_active && S.n_rec2d != 0u && region_ok) {
+        if (RX_K_FS(RX_FS_D2, F.d2_active && S.n_rec2d != 0u) && region_ok) {
             const Tri2D* recs = Wk.tri2d + (size_t)f * Wk.tri2d_stride;
             const DFrameBatch2* fb2 = Wk.fb2 + (size_t)f * Wk.fb2_stride;
             const uint32_t n2 = GENERAL ? Wk.tile_count2[(size_t)f * Wk.tile_stride + tile] : S.n_rec2d;
@@ -2963,11 +3025,14 @@ cudaError_t rxk_bin_fill(const SceneDev& S, const Workspace& W, uint32_t n_frame
     k_bin_fill<<<grid, 256, 0, st>>>(S, W);
     return cudaGetLastError();
 }
+int rxk_raster_mode(const SceneDev& S, const Workspace& W) {
+    return (S.general && S.vm.n_programs) ? 2 : S.general ? 1 : S.n_tris >= W.small_min_tris ? 3 : 0;
+}
 cudaError_t rxk_raster(const SceneDev& S, const Workspace& W, const RasterOut& out, uint32_t n_frames, uint32_t tile0, uint32_t n_tiles,
                        uint32_t counter, int sample_mode, int grid_x, cudaStream_t st, void* jit_kernel) {
     const bool planes = out.owner || out.depth;
-    if (jit_kernel && S.general && S.vm.n_programs) {
-        // the batch-shader variant recompiled with the scene's programs as straight-line code (rx_jit.cu): same arguments
+    if (jit_kernel) {
+        // the same kernel recompiled for this scene (rx_jit.cu: its programs as straight-line code, its constants folded): same arguments
         SceneDev s = S; Workspace w = W; RasterOut o = out;
         void* args[] = {&s, &w, &o, &n_frames, &tile0, &n_tiles, &counter};
         return cudaLaunchKernel((const void*)jit_kernel, dim3(grid_x), dim3(RX_TILE_THREADS), args, 0, st);

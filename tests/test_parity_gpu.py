@@ -505,10 +505,11 @@ def test_vm_jit_kernel_equals_the_interpreter_on_every_op():
         want = [ctx.vm_execute(k, recs) for k in range(len(progs))]
         assert ctx.vm_jit_info()["launches"] == 0
     with _JitMode(2) as ctx:
+        before = ctx.vm_jit_info()
         ctx.upload(scene, assets)
         got = [ctx.vm_execute(k, recs) for k in range(len(progs))]
         info = ctx.vm_jit_info()
-    assert info["translated"] == len(progs) and info["kernels"] == 1 and info["launches"] == len(progs), info
+    assert info["translated"] == len(progs) and info["launches"] - before["launches"] == len(progs), (before, info)
     for name, (g, gf), (w, wf) in zip(progs, got, want):
         assert gf == wf == 0, name
         assert np.array_equal(g.view(np.uint32), w.view(np.uint32)), (name, np.abs(g - w).max())
@@ -523,9 +524,10 @@ def test_shaded_scene_jit_equals_interpreter(sample_mode):
     with _JitMode(0):
         a = render_gpu(cfg.rasterizer(4), cfg.scene, cfg.assets, 640, 480, 40)
     with _JitMode(2) as ctx:
+        before = ctx.vm_jit_info()
         b = render_gpu(cfg.rasterizer(4), cfg.scene, cfg.assets, 640, 480, 40)
         info = ctx.vm_jit_info()
-        assert info["launches"] >= 1 and info["kernels"] >= 1 and info["translated"] >= 4, info
+        assert info["launches"] > before["launches"] and info["kernels"] >= 1 and info["translated"] >= 4, (before, info)
         st = _run(cfg, frame=4)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2].view(np.uint32), b[2].view(np.uint32))
     assert st["within1_frac"] > 0.999
@@ -562,6 +564,69 @@ def test_vm_jit_declined_program_still_faults_through_the_interpreter():
         assert faults == 8
         out, faults = ctx.vm_execute(1, vm_programs.records(8))
         assert faults == 0 and ctx.vm_jit_info()["translated"] == 1
+
+
+# ------------------------------------------------------------------------------------------------
+# raster kernels recompiled for the scene (rx_jit.cu): the scene's and the frame's constants folded in
+# ------------------------------------------------------------------------------------------------
+def _spec_cases():
+    yield "cube", lambda: scenes.cube(800, 600, 200, logo_size=256), 0
+    yield "teapot-linear", lambda: scenes.teapot(960, 540, 60, logo_size=256, n_frames=8), 3
+    yield "map", lambda: scenes.map_config(1280, 720, 40, logo_size=256), 0
+    yield "sweep", lambda: scenes.sweep(960, 540, 40, n_frames=64, logo_size=256), 17
+    yield "dense", lambda: scenes.dense(1280, 720, 40, patches=8, patch_verts=23), 0
+    yield "dense-long-lists", lambda: scenes.dense(640, 360, 40, patches=12, patch_verts=30), 0
+    yield "chunked", lambda: scenes.chunked_config(640, 360, 40), 2
+    yield "game2d", lambda: scenes.game2d_config(480, 320), 0
+    yield "sky", lambda: scenes.sky_config(480, 270, 40, hour=16.5), 1
+
+
+@pytest.mark.parametrize("name,make,frame", list(_spec_cases()), ids=[c[0] for c in _spec_cases()])
+def test_scene_specialised_kernel_equals_the_generic_kernel(name, make, frame):
+    """k_raster recompiled with the scene's constants (shade-descriptor bits shared by all batches, light count and type,
+    ambient / sun / sky / 2D presence, no alpha test anywhere) renders the frame of the library's generic kernel bit for
+    bit -- pixels, owner ids and depth -- with and without the owner / depth planes, and it is the kernel that ran."""
+    cfg = make()
+    base_lights = list(cfg.scene.dynamic_lights)
+
+    def render(planes):
+        cfg.scene.dynamic_lights = list(base_lights)   # rasterize() appends the chunks' lights on every call (src/rasterizer.rs:219-223)
+        return render_gpu(cfg.rasterizer(frame), cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size, planes=planes)
+
+    with _JitMode(0):
+        a, a2 = render(True), render(False)
+    with _JitMode(2) as ctx:
+        before = ctx.vm_jit_info()
+        b, b2 = render(True), render(False)
+        after = ctx.vm_jit_info()
+    assert after["launches"] - before["launches"] >= 2, (before, after)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2].view(np.uint32), b[2].view(np.uint32))
+    assert np.array_equal(a2[0], b2[0]) and np.array_equal(a[0], a2[0])
+
+
+def test_scene_specialised_kernel_follows_light_and_frame_changes():
+    """The signature is per launch: another light count, another light type, ambient switched off -- each picks (compiles)
+    its own kernel; a kernel is never run on a frame it was not compiled for (the kernel checks and would report it)."""
+    from rusterix_b200 import Light, LightType
+    cfg = scenes.map_config(640, 360, 40, logo_size=64)
+    extra = (Light.new(LightType.Spot).with_position([7.0, 1.8, 7.0]).with_color([0.6, 0.8, 1.0]).with_intensity(1.5)
+             .with_start_distance(1.0).with_end_distance(9.0).with_direction([0.0, -1.0, 0.2]).with_cone_angle(0.9).compile())
+    frames = {}
+    for mode in (0, 2):
+        with _JitMode(mode):
+            out = []
+            cfg.scene.dynamic_lights = []
+            out.append(render_gpu(cfg.rasterizer(0), cfg.scene, cfg.assets, 640, 360, 40))
+            cfg.scene.dynamic_lights = [extra]                       # two lights of two types
+            out.append(render_gpu(cfg.rasterizer(0), cfg.scene, cfg.assets, 640, 360, 40))
+            r = cfg.rasterizer(0)
+            r.ambient_color = None                                    # frame signature: no ambient term
+            out.append(render_gpu(r, cfg.scene, cfg.assets, 640, 360, 40))
+            cfg.scene.dynamic_lights = []
+            frames[mode] = out
+    for a, b in zip(frames[0], frames[2]):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2].view(np.uint32), b[2].view(np.uint32))
+    assert not np.array_equal(frames[0][0][0], frames[0][1][0]) and not np.array_equal(frames[0][1][0], frames[0][2][0])
 
 
 # ------------------------------------------------------------------------------------------------
