@@ -127,6 +127,13 @@ def build_workload(name, frames_per_step, rank, world):
     return cfg, frame_ids, desc
 
 
+def kernels_note(ctx):
+    """Which k_raster ran: the library's generic instantiation or the one recompiled for the scene (rx_jit.cu)."""
+    info = ctx.vm_jit_info()
+    return {"k_raster": "recompiled for the scene with NVRTC (scene / frame constants folded in, rx_jit.cu)" if info["launches"] else "generic instantiation of librxcuda.so",
+            "scene_kernels_loaded": info["kernels"], "launches_of_scene_kernels": info["launches"], "compile_log": info["log"][:300]}
+
+
 def make_config(desc, cfg, world):
     """The `config` object of the JSON line: the same keys and values in the native and the reference arm."""
     return {"workload": desc, "width": cfg.width, "height": cfg.height, "triangles": cfg.counts()[1], "tile_size": cfg.tile_size,
@@ -260,6 +267,11 @@ def main():
     frame_bytes = W * H * 4
     rasts = [cfg.rasterizer(i).on_device(local_rank) for i in frame_ids]
     ctx = DeviceContext.get(local_rank)
+    # The raster kernel is recompiled for the scene (NVRTC: its constants folded in, batch shaders as straight-line code;
+    # rusterix_b200/csrc/rx_jit.cu).  The library does that in the background and renders with its generic kernel meanwhile; the
+    # bench asks for the compilation BEFORE the first frame (a few seconds inside the warm-up), so that the timed steps measure
+    # the kernel a running application ends up with.  RXC_VM_JIT=0 benches the generic kernels.
+    ctx.set_vm_jit(int(os.environ.get("RXC_VM_JIT", "2")))
     # a dedicated (non-default) torch stream: the kernels, the L2 flush and the torch.cuda.Events
     # all live on it, so the events bracket exactly the launches of a step
     stream = torch.cuda.Stream(device=dev)
@@ -424,6 +436,7 @@ def main():
                     "host_numa_binding": ("rank pinned to the %d cores next to its GPU" % len(numa_cpus)) if numa_cpus else "none"},
             "gpu_launches": int(gpu_launches), "launches_per_step": int(launches_per_step),
             "roofline": roofline, "clocks": clocks,
+            "kernels": kernels_note(ctx),
         }
         if delivered:
             line["value_with_gather"] = delivered["value"]
@@ -647,9 +660,6 @@ def secondary(wname, local_rank, dev, flush, steps=5, warmup=3):
     rasts = [cfg.rasterizer(i).on_device(local_rank) for i in frame_ids]
     out = torch.empty((F, cfg.height, cfg.width, 4), dtype=torch.uint8, device=dev)
     ctx = DeviceContext.get(local_rank)
-    jit = wname == "shaded1080" and os.environ.get("RXC_VM_JIT", "1") != "0"
-    if jit:
-        ctx.set_vm_jit(2)   # the scene's programs as straight-line code, compiled (NVRTC, seconds) before the first frame instead of behind it
 
     batch = Rasterizer.prepare_batch(rasts, cfg.scene, cfg.width, cfg.height, cfg.tile_size, cfg.assets, device=local_rank)
 
@@ -675,8 +685,6 @@ def secondary(wname, local_rank, dev, flush, steps=5, warmup=3):
         info = ctx.vm_jit_info()
         extra["vm"] = {"programs_translated": info["translated"], "jit_kernels": info["kernels"], "jit_launches": info["launches"],
                        "mode": "NVRTC-compiled straight-line programs" if info["launches"] else "interpreter" + (": " + info["log"][:200] if info["log"] else "")}
-        if jit:
-            ctx.set_vm_jit(int(os.environ.get("RXC_VM_JIT", "1")))
     return {**extra, "workload": desc, "frames_per_step": F, "ms_per_step": ms, "Mpixel_per_s": F * cfg.width * cfg.height / (ms * 1e-3) / 1e6,
             "frames_per_s": F / (ms * 1e-3), "triangles": cfg.counts()[1],
             "kernel_ms": {names[i]: s.kernel_ms[i] for i in range(len(names)) if s.launches[i]},

@@ -101,8 +101,9 @@ struct rxc_ctx {
     RxJit* jit = nullptr;         // kernels recompiled for the current scene (rx_jit.cu): batch shaders as straight-line code, scene constants folded
     int vm_jit = 1;               // RXC_VM_JIT: 0 off, 1 compile in the background, 2 compile synchronously
     int kernel_spec = 1;          // RXC_KERNEL_SPEC: 1 = the raster kernel is also recompiled with the scene's / frame's constants folded in
-    std::string spec_scene;       // -D switches of the current scene's batches (set_scene), of its lights (set_lights)
+    std::string spec_scene;       // -D switches of the current scene's batches and textures (recomputed when spec_dirty), of its lights (set_lights)
     std::string spec_lights;
+    bool spec_dirty = true, spec_vm_opacity = false;
     bool spec_mismatch = false;   // a specialised kernel found a scene it was not compiled for (a bug): specialisation stays off
     std::string jit_note;         // last compiler log / load failure (diagnostics)
     uint32_t jit_translated = 0;  // programs of the current scene the translator accepted
@@ -288,7 +289,8 @@ std::string scene_signature(rxc_ctx* ctx, bool any_vm_opacity) {
 
 std::string lights_signature(const std::vector<DLight>& h) {
     std::string d;
-    if (h.size() <= 4) d = "-DRX_SPEC_NLIGHTS=" + std::to_string(h.size());   // unrolled; more (or a count that keeps changing) stay a loop
+    static const size_t cap = getenv("RXC_SPEC_MAX_LIGHTS") ? (size_t)atoi(getenv("RXC_SPEC_MAX_LIGHTS")) : 4;
+    if (h.size() <= cap) d = "-DRX_SPEC_NLIGHTS=" + std::to_string(h.size());   // a constant trip count; more (or a count that keeps changing) stay a run-time loop
     bool one_type = !h.empty();
     for (const DLight& l : h) one_type = one_type && l.light_type == h[0].light_type;
     if (one_type) d += std::string(d.empty() ? "" : " ") + "-DRX_SPEC_LIGHT_TYPE=" + std::to_string(h[0].light_type);
@@ -563,11 +565,9 @@ int32_t upload_vm(rxc_ctx* ctx, const rxc_scene* sc) {
     } else if (ctx->jit) {
         rxj_set_programs(ctx->jit, std::string(), 0);
     }
-    {
-        bool any_vm_opacity = false;
-        for (uint32_t i = 0; i < sc->n_shaders; ++i) any_vm_opacity = any_vm_opacity || sc->shaders[i].sets_opacity;
-        ctx->spec_scene = scene_signature(ctx, any_vm_opacity);
-    }
+    ctx->spec_vm_opacity = false;
+    for (uint32_t i = 0; i < sc->n_shaders; ++i) ctx->spec_vm_opacity = ctx->spec_vm_opacity || sc->shaders[i].sets_opacity;
+    ctx->spec_dirty = true;
     std::vector<float> patdata;
     std::vector<DPattern> pats;
     auto add_patterns = [&](const rxc_pattern* list, uint32_t n) -> int32_t {
@@ -707,6 +707,7 @@ int32_t launch_group(rxc_ctx* ctx, const DFrame* h_frames, DCounters* h_counters
         void* jit_kernel = nullptr;
         const int raster_mode = rxk_raster_mode(S, ctx->W);
         const bool spec = ctx->kernel_spec && !ctx->spec_mismatch;
+        if (spec && ctx->spec_dirty) { ctx->spec_scene = scene_signature(ctx, ctx->spec_vm_opacity); ctx->spec_dirty = false; }
         if (ctx->jit && (raster_mode == 2 || spec)) {
             std::string defines, note;
             if (spec) {
@@ -1079,6 +1080,7 @@ int32_t rxc_set_assets(rxc_ctx* ctx, const rxc_tile* tiles, uint32_t n_tiles) {
     int32_t st = build_tiles(ctx, tiles, n_tiles, ctx->h_static_arena, ctx->h_static_tex, ctx->h_static_tiles);
     if (st != RXC_OK) return st;
     ctx->textures_dirty = true;
+    ctx->spec_dirty = true;
     return upload_textures(ctx);
     });
 }
