@@ -2733,7 +2733,9 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
         }
 
         // 2D pass in submission order (rasterizer.rs:501-553) over the thread's own pixels in s_color
-        if (RX_K_FS(RX_FS_D2, F.d2_active && S.n_rec2d != 0u) && region_ok) {
+        // (fast mode: the union of the 2D records' pixel boxes, staged per frame, keeps the tiles they cannot touch out of the loop)
+        if (RX_K_FS(RX_FS_D2, F.d2_active && S.n_rec2d != 0u) && region_ok &&
+            (GENERAL || (s_union[4] < tx1 && s_union[6] > tx0 && s_union[5] < ty1 && s_union[7] > ty0))) {
             const Tri2D* recs = Wk.tri2d + (size_t)f * Wk.tri2d_stride;
             const DFrameBatch2* fb2 = Wk.fb2 + (size_t)f * Wk.fb2_stride;
             const uint32_t n2 = GENERAL ? Wk.tile_count2[(size_t)f * Wk.tile_stride + tile] : S.n_rec2d;

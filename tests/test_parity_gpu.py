@@ -501,9 +501,10 @@ def test_vm_jit_kernel_equals_the_interpreter_on_every_op():
     progs, scene, assets = _vm_scene()
     recs = vm_programs.records(4096, seed=23)
     with _JitMode(0) as ctx:
+        launches = ctx.vm_jit_info()["launches"]
         ctx.upload(scene, assets)
         want = [ctx.vm_execute(k, recs) for k in range(len(progs))]
-        assert ctx.vm_jit_info()["launches"] == 0
+        assert ctx.vm_jit_info()["launches"] == launches
     with _JitMode(2) as ctx:
         before = ctx.vm_jit_info()
         ctx.upload(scene, assets)
