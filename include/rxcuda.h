@@ -493,6 +493,15 @@ int32_t rxc_mgpu_status(rxc_ctx* ctx, uint32_t* mode, uint32_t* deliveries, uint
 int64_t rxc_vm_translate(const rxc_program* programs, uint32_t n_programs, char* source, uint64_t cap, uint32_t* jit_index);
 int64_t rxc_vm_jit_compile(const rxc_program* programs, uint32_t n_programs, int32_t sample_mode, int32_t planes, char* log, uint32_t log_cap);
 int32_t rxc_set_vm_jit(rxc_ctx* ctx, int32_t mode);
+/* The one documented deviation of batch shaders: the reference keeps ONE Execution per screen tile and never
+ * resets it (src/rasterizer.rs:310), so state a fragment's program leaves behind (emissive, globals, the .yz of roughness ...) is
+ * seen by the next fragment of the tile; the device starts every fragment from Execution::new().  A static analysis says which
+ * programs can observe the difference: report[i] = 0 cannot (device == reference on this program), 1 can (writes `emissive`, reads a
+ * channel the rasterizer does not fully reset and some program writes, reads a global / local before writing it), 2 not analysable.
+ * rxc_vm_state_report: for a program table; usage[i] bit 0 = bound to a 3D batch, bit 1 = to a 2D batch (NULL: both).
+ * rxc_vm_scene_state_report: for the current scene with its real bindings (programs no batch uses report 0). */
+int32_t rxc_vm_state_report(const rxc_program* programs, uint32_t n_programs, const uint8_t* usage, int32_t scene_has_3d, uint32_t* report);
+int32_t rxc_vm_scene_state_report(rxc_ctx* ctx, uint32_t* report, uint32_t cap, uint32_t* n_programs);
 int32_t rxc_vm_jit_info(rxc_ctx* ctx, uint32_t* n_translated, uint32_t* kernels_compiled, uint32_t* pending, uint64_t* jit_launches, char* log, uint32_t log_cap);
 
 int32_t rxc_set_profiling(rxc_ctx* ctx, int32_t enabled);

@@ -104,6 +104,7 @@ struct rxc_ctx {
     std::string spec_scene;       // -D switches of the current scene's batches and textures (recomputed when spec_dirty), of its lights (set_lights)
     std::string spec_lights;
     bool spec_dirty = true, spec_vm_opacity = false;
+    std::vector<uint32_t> vm_state_report;   // per program of the current scene: rxj_state_report with the batches' bindings
     bool spec_mismatch = false;   // a specialised kernel found a scene it was not compiled for (a bug): specialisation stays off
     std::string jit_note;         // last compiler log / load failure (diagnostics)
     uint32_t jit_translated = 0;  // programs of the current scene the translator accepted
@@ -721,6 +722,7 @@ int32_t launch_group(rxc_ctx* ctx, const DFrame* h_frames, DCounters* h_counters
                 for (uint32_t i = 1; i < n; ++i) known &= ~(bits(h_frames[i]) ^ value);
                 defines = "-DRX_SPEC_ACTIVE=1" + (ctx->spec_scene.empty() ? "" : " " + ctx->spec_scene) + (ctx->spec_lights.empty() ? "" : " " + ctx->spec_lights) +
                           " -DRX_SPEC_FRAME_KNOWN=" + std::to_string(known) + "u -DRX_SPEC_FRAME_VALUE=" + std::to_string(value & known) + "u";
+                if (const char* e = getenv("RXC_JIT_EXTRA")) defines += std::string(" ") + e;   // experiments: further -D switches for the recompiled kernel
             }
             jit_kernel = rxj_kernel(ctx->jit, sample_mode, d_owner || d_depth, raster_mode, defines, &note);
             if (!note.empty()) ctx->jit_note = note;
@@ -1016,6 +1018,7 @@ int32_t rxc_create(int32_t device, rxc_ctx** out) {
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RXC_ERR_CUDA; }
     ctx->stream = ctx->own_stream;
     ctx->raster_blocks_per_sm = rxk_raster_blocks_per_sm();
+    if (const char* e = getenv("RXC_RASTER_BLOCKS")) ctx->raster_blocks_per_sm = std::max(1, atoi(e));   // experiments (with RXC_JIT_EXTRA=-DRX_RASTER_MIN_BLOCKS=n)
     if (const char* e = getenv("RXC_PIECE_MB")) ctx->piece_mb = std::max(1, atoi(e));
     if (const char* e = getenv("RXC_SLICE_MB")) ctx->slice_mb = std::max(0, atoi(e));
     if (const char* e = getenv("RXC_TMA_STORE")) ctx->tma_store = atoi(e);
@@ -1312,6 +1315,14 @@ int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
     if ((st = upload(ctx, ctx->d_b2, ctx->h_b2.data(), ctx->h_b2.size() * sizeof(DBatch2))) != RXC_OK) return st;
     if ((st = upload_lights(ctx, sc->lights, sc->n_lights)) != RXC_OK) return st;
     if ((st = upload_vm(ctx, sc)) != RXC_OK) return st;
+    {   // which programs could tell the reference's per-tile Execution from the device's fresh one
+        std::vector<uint8_t> usage(sc->n_shaders, 0);
+        for (const DBatch3& b : ctx->h_b3) if (b.program >= 0 && (uint32_t)b.program < sc->n_shaders) usage[b.program] |= 1u;
+        for (const DBatch2& b : ctx->h_b2) if (b.program >= 0 && (uint32_t)b.program < sc->n_shaders) usage[b.program] |= 2u;
+        ctx->vm_state_report.assign(sc->n_shaders, 0u);
+        if (sc->n_shaders) rxj_state_report(sc->shaders, sc->n_shaders, usage.data(), !ctx->h_b3.empty(), ctx->vm_state_report.data());
+        for (uint32_t i = 0; i < sc->n_shaders; ++i) if (!usage[i]) ctx->vm_state_report[i] = 0u;   // bound to no batch: never runs
+    }
 
     SceneDev& S = ctx->S;
     S.pos = ctx->d_pos.as<float4>(); S.uv = ctx->d_uv.as<float2>(); S.nrm = ctx->d_nrm.as<float>(); S.idx = ctx->d_idx.as<uint32_t>();
@@ -1535,6 +1546,25 @@ int64_t rxc_vm_jit_compile(const rxc_program* programs, uint32_t n_programs, int
     } catch (...) {
         return RXC_ERR_OOM;
     }
+}
+
+int32_t rxc_vm_state_report(const rxc_program* programs, uint32_t n_programs, const uint8_t* usage, int32_t scene_has_3d, uint32_t* report) {
+    try {
+        if ((n_programs && (!programs || !report))) return RXC_ERR_INVALID;
+        if (n_programs) rxj_state_report(programs, n_programs, usage, scene_has_3d != 0, report);
+        return RXC_OK;
+    } catch (...) {
+        return RXC_ERR_OOM;
+    }
+}
+
+int32_t rxc_vm_scene_state_report(rxc_ctx* ctx, uint32_t* report, uint32_t cap, uint32_t* n_programs) {
+    return guarded(ctx, [&]() -> int32_t {
+    if (!ctx) return RXC_ERR_INVALID;
+    if (n_programs) *n_programs = (uint32_t)ctx->vm_state_report.size();
+    for (uint32_t i = 0; report && i < cap && i < ctx->vm_state_report.size(); ++i) report[i] = ctx->vm_state_report[i];
+    return RXC_OK;
+    });
 }
 
 int32_t rxc_set_vm_jit(rxc_ctx* ctx, int32_t mode) {

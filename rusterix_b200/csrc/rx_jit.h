@@ -11,6 +11,9 @@ struct RxJit;
 // C++ for the programs the translator accepts (vm_run_jit + one function per program); jit_index[i] = i or 0xFFFFFFFF.
 // Returns false when no program was accepted.
 bool rxj_generate(const rxc_program* progs, uint32_t n, std::string* source, std::vector<uint32_t>* jit_index);
+// out[i]: 0 = program i cannot tell the reference's per-tile Execution from the device's fresh one, 1 = it can (see rx_jit.cu),
+// 2 = not analysable.  usage[i]: bit 0 = bound to a 3D batch, bit 1 = to a 2D batch (nullptr: both).
+void rxj_state_report(const rxc_program* progs, uint32_t n, const uint8_t* usage, bool scene_has_3d, uint32_t* out);
 // mode: 0 off, 1 compile in the background (frames use the interpreter until the kernel is ready), 2 compile synchronously
 RxJit* rxj_create(const std::string& generated, int mode);   // one per context; the kernels it loads outlive the scenes
 void rxj_set_programs(RxJit* j, const std::string& generated, int mode);   // a new scene's programs (may be empty)

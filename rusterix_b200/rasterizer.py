@@ -113,6 +113,15 @@ class DeviceContext:
         return {"translated": int(nt.value), "kernels": int(nk.value), "pending": bool(pend.value), "launches": int(used.value),
                 "log": log.value.decode(errors="replace")}
 
+    def vm_state_report(self):
+        """rxc_vm_scene_state_report: per program of the resident scene 0 = the device and the reference (one Execution per
+        tile, never reset) compute the same thing, 1 = the program can observe the difference, 2 = not analysable."""
+        n = C.c_uint32(0)
+        self.check(self.lib.rxc_vm_scene_state_report(self.handle, None, 0, C.byref(n)))
+        out = (C.c_uint32 * max(1, n.value))()
+        self.check(self.lib.rxc_vm_scene_state_report(self.handle, out, n.value, C.byref(n)))
+        return list(out)[:n.value]
+
     def pin_host(self, buf):
         """rxc_pin_host on a writable buffer (numpy array, bytearray ...): frames written into it then drain by DMA."""
         p, keep = _buffer_pointer(buf, 1)

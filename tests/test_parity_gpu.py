@@ -567,6 +567,22 @@ def test_vm_jit_declined_program_still_faults_through_the_interpreter():
         assert faults == 0 and ctx.vm_jit_info()["translated"] == 1
 
 
+def test_vm_state_report_names_the_scene_whose_frames_depend_on_the_tile_execution():
+    """rxc_vm_scene_state_report: the batch-shader scene's programs cannot observe the reference's never-reset per-tile
+    Execution (so the frame is compared with the FAITHFUL oracle, test_shaded_scene_parity); its `emissive` variant can --
+    that is the one scene checked against the oracle in per-fragment-state mode."""
+    ctx = DeviceContext.get(0)
+    cfg = scenes.shaded_config(160, 120, 40)
+    render_gpu(cfg.rasterizer(0), cfg.scene, cfg.assets, 160, 120, 40)
+    plain = ctx.vm_state_report()
+    cfg2 = scenes.shaded_config(160, 120, 40, emissive=True)
+    render_gpu(cfg2.rasterizer(0), cfg2.scene, cfg2.assets, 160, 120, 40)
+    leaky = ctx.vm_state_report()
+    assert len(plain) == len(leaky) >= 4
+    assert plain == [0] * len(plain), plain
+    assert 1 in leaky and 2 not in leaky, leaky
+
+
 # ------------------------------------------------------------------------------------------------
 # raster kernels recompiled for the scene (rx_jit.cu, DESIGN.md 5b): the scene's and the frame's constants folded in
 # ------------------------------------------------------------------------------------------------

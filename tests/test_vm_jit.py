@@ -101,3 +101,44 @@ def test_nvrtc_compiles_the_generated_kernel(tmp_path, monkeypatch):
     assert lib.rxc_vm_jit_compile(arr, len(flat), -1, 0, log, len(log)) == n
     # an empty table has nothing to compile
     assert lib.rxc_vm_jit_compile(None, 0, -1, 0, log, len(log)) == 0
+
+
+# ---- which programs can observe the reference's per-tile Execution (rxc_vm_state_report) ----
+def _state_report(programs, usage=None, scene_has_3d=True):
+    lib = _lib.load()
+    arr, flat = _table(programs)
+    out = (C.c_uint32 * max(1, len(flat)))()
+    use = None if usage is None else (C.c_uint8 * len(flat))(*usage)
+    assert lib.rxc_vm_state_report(arr, len(flat), use, 1 if scene_has_3d else 0, out) == 0
+    return list(out)[:len(flat)]
+
+
+def test_state_report_passes_the_self_contained_shaders():
+    """The example shaders assign everything they read: on them a fresh Execution per fragment and the reference's
+    never-reset per-tile Execution compute the same pixels."""
+    shaders = [scenes.shader_wood(), scenes.shader_marble(), scenes.shader_wood_ring(), scenes.shader_holes(),
+               scenes.shader_control_flow(), scenes.shader_glass_tint()]
+    assert _state_report(shaders, usage=[1] * len(shaders)) == [0] * len(shaders)
+
+
+def test_state_report_flags_what_leaks_between_fragments():
+    emissive = scenes.shader_control_flow(True)                                        # writes `emissive` on one path: every later fragment of the tile is lit by it
+    stale_global = rvm.Program([[("LoadGlobal", 0), ("SetColor",), ("UV",), ("StoreGlobal", 0)]], 0, 0, 1)   # reads the global the previous fragment stored
+    fresh_global = rvm.Program([[("UV",), ("StoreGlobal", 0), ("LoadGlobal", 0), ("SetColor",)]], 0, 0, 1)
+    stale_local = rvm.Program([[("UV",), ("If", [("UV",), ("StoreLocal", 0)], None), ("LoadLocal", 0), ("SetColor",)]], 0, 1, 0)   # written on one path only
+    writes_uvz = rvm.Program([[("Push", (0.0, 0.0, 7.0)), ("SetUV",)]], 0, 0, 0)       # leaves uv.z = 7 behind ...
+    reads_uv = rvm.Program([[("UV",), ("SetColor",)]], 0, 0, 0)                        # ... where this one can see it
+    assert _state_report([emissive]) == [1]
+    assert _state_report([stale_global, fresh_global, stale_local]) == [1, 0, 1]
+    assert _state_report([reads_uv]) == [0]
+    assert _state_report([writes_uvz, reads_uv]) == [0, 1]
+    # a 2D program reading the hit point sees the z the 3D pass left there -- unless the scene has no 3D batches
+    reads_hit = rvm.Program([[("Hitpoint",), ("SetColor",)]], 0, 0, 0)
+    assert _state_report([reads_hit], usage=[2], scene_has_3d=True) == [1]
+    assert _state_report([reads_hit], usage=[2], scene_has_3d=False) == [0]
+    assert _state_report([reads_hit], usage=[1], scene_has_3d=True) == [0]
+    reads_hit_x = rvm.Program([[("Hitpoint",), ("GetComponents", [0]), ("SetColor",)]], 0, 0, 0)   # hitpoint.x is assigned in 2D too
+    assert _state_report([reads_hit_x], usage=[2], scene_has_3d=True) == [0]
+    # what the verifier declines is not analysable
+    underflow = rvm.Program([[("Add",), ("SetColor",)]], 0, 0, 0)
+    assert _state_report([underflow]) == [2]

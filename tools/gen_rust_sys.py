@@ -39,6 +39,8 @@ ARG_NAMES = {
     "rxc_vm_translate": ["programs", "n_programs", "source", "cap", "jit_index"],
     "rxc_vm_jit_compile": ["programs", "n_programs", "sample_mode", "planes", "log", "log_cap"],
     "rxc_set_vm_jit": ["ctx", "mode"],
+    "rxc_vm_state_report": ["programs", "n_programs", "usage", "scene_has_3d", "report"],
+    "rxc_vm_scene_state_report": ["ctx", "report", "cap", "n_programs"],
     "rxc_vm_jit_info": ["ctx", "n_translated", "kernels_compiled", "pending", "jit_launches", "log", "log_cap"],
     "rxc_get_stats": ["ctx", "out"], "rxc_pin_host": ["ctx", "ptr", "bytes"], "rxc_unpin_host": ["ctx", "ptr"], "rxc_reset_stats": ["ctx"], "rxc_kernel_name": ["kernel_class"],
 }
@@ -48,7 +50,7 @@ ARG_TYPES = {
     ("rxc_rasterize", 3): "*mut u32", ("rxc_rasterize", 4): "*mut f32", ("rxc_rasterize_projected", 4): "*mut u8",
     ("rxc_rasterize_projected", 5): "*mut u32", ("rxc_rasterize_projected", 6): "*mut f32", ("rxc_rasterize_async", 2): "*mut u8",
     ("rxc_rasterize_async", 3): "*mut u32", ("rxc_rasterize_async", 4): "*mut f32", ("rxc_rasterize_batch", 3): "*mut u8",
-    ("rxc_rasterize_batch_async", 3): "*mut u8", ("rxc_vm_translate", 2): "*mut c_char", ("rxc_vm_jit_info", 5): "*mut c_char", ("rxc_vm_jit_compile", 4): "*mut c_char", ("rxc_mgpu_init", 1): "*const u8", ("rxc_mgpu_target", 2): "*mut *mut c_void", ("rxc_pin_host", 1): "*mut c_void", ("rxc_unpin_host", 1): "*mut c_void", ("rxc_vm_execute", 3): "*const f32", ("rxc_vm_execute", 4): "*mut f32",
+    ("rxc_rasterize_batch_async", 3): "*mut u8", ("rxc_vm_translate", 2): "*mut c_char", ("rxc_vm_jit_info", 5): "*mut c_char", ("rxc_vm_state_report", 2): "*const u8", ("rxc_vm_jit_compile", 4): "*mut c_char", ("rxc_mgpu_init", 1): "*const u8", ("rxc_mgpu_target", 2): "*mut *mut c_void", ("rxc_pin_host", 1): "*mut c_void", ("rxc_unpin_host", 1): "*mut c_void", ("rxc_vm_execute", 3): "*const f32", ("rxc_vm_execute", 4): "*mut f32",
 }
 
 
