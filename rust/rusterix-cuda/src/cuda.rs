@@ -327,4 +327,23 @@ fn scene_key(scene: &Scene) -> u64 {
 impl CudaRasterizer {
     /// Forget what is resident (call after editing vertex or texture data in place).
     pub fn invalidate(&mut self) { self.scene_key = 0; self.assets_key = (0, 0); }
+
+    /// How the library recompiles its raster kernel for the scene (NVRTC): 0 = never (generic kernels, batch shaders
+    /// interpreted), 1 = in the background (default), 2 = before the first frame that needs the kernel (offline renderers, benchmarks).
+    /// Takes effect with the next scene upload.
+    pub fn set_kernel_jit(&mut self, mode: i32) {
+        let st = unsafe { rxc_set_vm_jit(self.ctx, mode) };
+        self.check(st, "rxc_set_vm_jit");
+        self.scene_key = 0;
+    }
+
+    /// Per shader program of the resident scene: 0 = device and reference agree by construction, 1 = the program can observe the
+    /// reference's never-reset per-tile `Execution` (src/rasterizer.rs:310), 2 = not analysable.
+    pub fn shader_state_report(&self) -> Vec<u32> {
+        let mut n: u32 = 0;
+        unsafe { rxc_vm_scene_state_report(self.ctx, std::ptr::null_mut(), 0, &mut n) };
+        let mut out = vec![0u32; n as usize];
+        unsafe { rxc_vm_scene_state_report(self.ctx, out.as_mut_ptr(), n, &mut n) };
+        out
+    }
 }
