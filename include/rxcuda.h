@@ -355,6 +355,14 @@ int32_t rxc_set_assets(rxc_ctx* ctx, const rxc_tile* tiles, uint32_t n_tiles);
 /* Geometry, lights and dynamic textures of a Scene: uploaded once, kept on device. */
 int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* scene);
 /* Replace only the light list (lights animate per frame in examples/cube.rs:72-73). */
+/* The same for a scene that differs from the resident one only behind its first `keep_batches3d` 3D batches (an engine's frame
+ * loop: the world stays, the entities' dynamic batches change -- the reference re-projects `&mut scene` every call, src/scene.rs:154-200).
+ * `scene` describes the WHOLE scene as for rxc_set_scene; of the kept batches only the per-batch state (source, shader, transform,
+ * ambient, modes ...) is read -- their vertex / uv / normal / index arrays are not touched (the pointers may dangle), their flattened
+ * copies, bounding boxes and setup chunks stay on the device and only the rest is validated, flattened and uploaded.  A kept batch
+ * must have the vertex and triangle count it had (else RXC_ERR_INVALID).  Everything else (2D batches, textures, chunks, lights,
+ * programs) is taken from `scene` as usual. */
+int32_t rxc_update_scene(rxc_ctx* ctx, const rxc_scene* scene, uint32_t keep_batches3d);
 int32_t rxc_set_lights(rxc_ctx* ctx, const rxc_light* lights, uint32_t n_lights);
 /* Rasterizer.mapmini; NULL or all-empty = MapMini::default() (everything visible, occlusion 1). */
 int32_t rxc_set_mapmini(rxc_ctx* ctx, const rxc_mapmini* mapmini);

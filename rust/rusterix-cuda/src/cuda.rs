@@ -14,6 +14,7 @@ pub struct CudaRasterizer {
     assets_key: (usize, usize),          // (tile_list.as_ptr(), len): re-upload when the list was rebuilt
     scene_key: u64,                      // structural hash of the scene (batch pointers / lengths)
     lights_key: u64,
+    geometry_keys: Vec<(usize, usize, usize, usize)>,   // per 3D batch in submission order: (vertices, indices, counts) at the last upload
     pinned: Vec<(*mut u8, usize)>,
 }
 unsafe impl Send for CudaRasterizer {}   // one context per (thread, GPU): Send, not Sync -- like &mut Rasterizer
@@ -24,7 +25,7 @@ impl CudaRasterizer {
         let st = unsafe { rxc_create(device, &mut ctx) };
         if st != RXC_OK { return Err(format!("rxc_create failed with status {st} (no sm_100 GPU visible?)")); }
         if unsafe { rxc_abi_version() } != RXC_ABI_VERSION { unsafe { rxc_destroy(ctx) }; return Err("librxcuda ABI version mismatch".into()); }
-        Ok(Self { ctx, assets_key: (0, 0), scene_key: 0, lights_key: 0, pinned: Vec::new() })
+        Ok(Self { ctx, assets_key: (0, 0), scene_key: 0, lights_key: 0, geometry_keys: Vec::new(), pinned: Vec::new() })
     }
 
     pub fn last_error(&self) -> String { unsafe { CStr::from_ptr(rxc_last_error(self.ctx)) }.to_string_lossy().into_owned() }
@@ -124,9 +125,14 @@ impl CudaRasterizer {
             patterns: pats.as_ptr(), n_patterns: pats.len() as u32, patterns_normal: pats_n.as_ptr(), n_patterns_normal: pats_n.len() as u32,
             palette: palette.as_ptr() as *const f32, n_palette: palette.len() as u32,
         };
-        let st = unsafe { rxc_set_scene(self.ctx, &s) };
+        // An engine's frame loop replaces the dynamic batches and keeps the world: the leading 3D batches whose arrays are the ones
+        // already resident (same pointers and lengths as at the last upload) are not validated, flattened or uploaded again.
+        let gkeys: Vec<(usize, usize, usize, usize)> = b3.iter().map(|b| (b.vertices as usize, b.indices as usize, b.n_vertices as usize, b.n_triangles as usize)).collect();
+        let keep = if self.scene_key != 0 { gkeys.iter().zip(self.geometry_keys.iter()).take_while(|(a, b)| a == b).count() } else { 0 };
+        let st = if keep > 0 { unsafe { rxc_update_scene(self.ctx, &s, keep as u32) } } else { unsafe { rxc_set_scene(self.ctx, &s) } };
         if st == RXC_ERR_UNSUPPORTED { return false; }
         self.check(st, "rxc_set_scene");
+        self.geometry_keys = gkeys;
         self.scene_key = skey;
         self.lights_key = lkey;
         true
@@ -326,7 +332,7 @@ fn scene_key(scene: &Scene) -> u64 {
 
 impl CudaRasterizer {
     /// Forget what is resident (call after editing vertex or texture data in place).
-    pub fn invalidate(&mut self) { self.scene_key = 0; self.assets_key = (0, 0); }
+    pub fn invalidate(&mut self) { self.scene_key = 0; self.assets_key = (0, 0); self.geometry_keys.clear(); }
 
     /// How the library recompiles its raster kernel for the scene (NVRTC): 0 = never (generic kernels, batch shaders
     /// interpreted), 1 = in the background (default), 2 = before the first frame that needs the kernel (offline renderers, benchmarks).

@@ -256,6 +256,7 @@ EXPORTS = [
     ("rxc_set_stream", C.c_int32, [C.c_void_p, C.c_void_p]),
     ("rxc_set_assets", C.c_int32, [C.c_void_p, C.POINTER(rxc_tile), C.c_uint32]),
     ("rxc_set_scene", C.c_int32, [C.c_void_p, C.POINTER(rxc_scene)]),
+    ("rxc_update_scene", C.c_int32, [C.c_void_p, C.POINTER(rxc_scene), C.c_uint32]),
     ("rxc_set_lights", C.c_int32, [C.c_void_p, C.POINTER(rxc_light), C.c_uint32]),
     ("rxc_set_mapmini", C.c_int32, [C.c_void_p, C.POINTER(rxc_mapmini)]),
     ("rxc_rasterize", C.c_int32, [C.c_void_p, C.POINTER(rxc_frame), C.c_void_p, C.c_void_p, C.c_void_p]),

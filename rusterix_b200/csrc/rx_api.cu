@@ -63,6 +63,11 @@ struct rxc_ctx {
     // scene
     std::vector<DBatch3> h_b3;
     std::vector<DBatch2> h_b2;
+    // the flattened 3D geometry of the current scene, kept on the host so that rxc_update_scene can reuse the part of it that did not change
+    std::vector<float> h_pos, h_uv, h_nrm;
+    std::vector<uint32_t> h_idx, h_orphans;
+    std::vector<DChunk> h_setup_chunks;
+    bool h_geometry_valid = false;
     std::vector<uint32_t> owner_base;
     DevBuf d_pos, d_uv, d_nrm, d_idx, d_b3, d_chunks, d_orphans, d_pos2, d_uv2, d_idx2, d_b2, d_lights;
     SceneDev S = {};
@@ -176,6 +181,17 @@ int32_t upload(rxc_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
         CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));  // the source is only borrowed for the call
         ctx->stats.h2d_bytes += bytes;
+    }
+    return RXC_OK;
+}
+
+// the same when the first `from` bytes on the device are already what `src` holds (rxc_update_scene); a buffer that has to grow is uploaded whole
+int32_t upload_from(rxc_ctx* ctx, DevBuf& b, const void* src, size_t bytes, size_t from) {
+    if (from == 0 || from > bytes || std::max<size_t>(bytes, 16) > b.cap) return upload(ctx, b, src, bytes);
+    if (bytes > from) {
+        CK(cudaMemcpyAsync((uint8_t*)b.p + from, (const uint8_t*)src + from, bytes - from, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->stats.h2d_bytes += bytes - from;
     }
     return RXC_OK;
 }
@@ -1121,8 +1137,10 @@ int32_t rxc_set_mapmini(rxc_ctx* ctx, const rxc_mapmini* mm) {
     });
 }
 
-int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
-    return guarded(ctx, [&]() -> int32_t {
+namespace {
+// rxc_set_scene (keep3d = 0) and rxc_update_scene: the first keep3d 3D batches have the geometry (vertex / uv / normal / index arrays)
+// of the previous call -- their flattened copies, bounding boxes, orphan lists and setup chunks are reused and their pointers not read
+int32_t set_scene_impl(rxc_ctx* ctx, const rxc_scene* sc, uint32_t keep3d) {
     if (!ctx || !sc) return RXC_ERR_INVALID;
     if ((sc->n_batches3d && !sc->batches3d) || (sc->n_batches2d && !sc->batches2d) || (sc->n_lights && !sc->lights) ||
         (sc->n_dynamic_textures && !sc->dynamic_textures) || (sc->n_chunks && !sc->chunks) || (sc->n_actor_tiles && !sc->actor_tiles) ||
@@ -1130,7 +1148,17 @@ int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
         (sc->n_palette && !sc->palette) || sc->n_scene_shaders > sc->n_shaders)
         return fail(ctx, RXC_ERR_INVALID, "null array with non-zero count in rxc_scene");
     CK(cudaSetDevice(ctx->device));
+    const std::vector<DBatch3> old_b3 = ctx->h_b3;   // geometry-derived fields of the batches that are kept
+    if (keep3d) {
+        if (!ctx->have_scene || !ctx->h_geometry_valid || keep3d > old_b3.size() || keep3d > sc->n_batches3d)
+            return fail(ctx, RXC_ERR_INVALID, "rxc_update_scene: keep_batches3d exceeds the batches of the resident scene (or there is none)");
+        for (uint32_t i = 0; i < keep3d; ++i)
+            if (old_b3[i].n_verts != sc->batches3d[i].n_vertices || old_b3[i].n_tris != sc->batches3d[i].n_triangles ||
+                (old_b3[i].has_normals != 0u) != (sc->batches3d[i].normals != nullptr))
+                return fail(ctx, RXC_ERR_INVALID, "rxc_update_scene: 3D batch " + std::to_string(i) + " is not the batch of the resident scene (vertex / triangle count, normals)");
+    }
     ctx->have_scene = false;
+    ctx->h_geometry_valid = false;
     for (uint32_t i = 0; i < sc->n_chunks; ++i)
         if ((uint64_t)sc->chunks[i].shader_base + sc->chunks[i].n_shaders > sc->n_shaders)
             return fail(ctx, RXC_ERR_INDEX, "chunk " + std::to_string(i) + ": shader range outside rxc_scene.shaders");
@@ -1148,9 +1176,11 @@ int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
             return fail(ctx, RXC_ERR_INDEX, who + "terrain chunk of size 0 (reference divides by chunk.size)");
         if (b.index_bytes != 4 && b.index_bytes != 8) return fail(ctx, RXC_ERR_INVALID, who + "index_bytes must be 4 or 8");
         if (b.cull_mode > RXC_CULL_BACK || b.repeat_mode > RXC_REPEAT_REPEAT_Y) return fail(ctx, RXC_ERR_INVALID, who + "bad enum value");
-        if ((b.n_vertices && (!b.vertices || !b.uvs)) || (b.n_triangles && !b.indices)) return fail(ctx, RXC_ERR_INVALID, who + "null geometry pointer");
-        for (size_t k = 0; k < (size_t)b.n_triangles * 3; ++k)
-            if (idx_at(b.indices, b.index_bytes, k) >= b.n_vertices) return fail(ctx, RXC_ERR_INDEX, who + "vertex index out of range (reference panics)");
+        if (i >= keep3d) {   // (a kept batch was checked when it was uploaded; its arrays are not read again)
+            if ((b.n_vertices && (!b.vertices || !b.uvs)) || (b.n_triangles && !b.indices)) return fail(ctx, RXC_ERR_INVALID, who + "null geometry pointer");
+            for (size_t k = 0; k < (size_t)b.n_triangles * 3; ++k)
+                if (idx_at(b.indices, b.index_bytes, k) >= b.n_vertices) return fail(ctx, RXC_ERR_INDEX, who + "vertex index out of range (reference panics)");
+        }
         V += b.n_vertices; T += b.n_triangles;
     }
     for (uint32_t i = 0; i < sc->n_batches2d; ++i) {
@@ -1174,9 +1204,19 @@ int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
     if (3 * T >= 0x7FFFFFFFull || V >= 0xFFFFFFFFull) return fail(ctx, RXC_ERR_UNSUPPORTED, "scene too large for 32-bit slots");
 
     // ---- flatten 3D
-    std::vector<float> pos(V * 4), uv(V * 2), nrm(V * 3, 0.0f);
-    std::vector<uint32_t> idx(T * 3), orphans;
-    std::vector<DChunk> chunks;
+    // (the vectors live in the context: what the kept batches put there stays, the rest is rewritten)
+    size_t keep_v = 0, keep_t = 0, keep_orphans = 0, keep_chunks = 0;
+    if (keep3d) {
+        const DBatch3& last = old_b3[keep3d - 1];
+        keep_v = (size_t)last.v_off + last.n_verts; keep_t = (size_t)last.t_off + last.n_tris;
+        keep_orphans = (size_t)last.orphan_off + last.n_orphans; keep_chunks = (size_t)last.chunk_first + last.n_chunks;
+    }
+    std::vector<float>&pos = ctx->h_pos, &uv = ctx->h_uv, &nrm = ctx->h_nrm;
+    std::vector<uint32_t>&idx = ctx->h_idx, &orphans = ctx->h_orphans;
+    std::vector<DChunk>& chunks = ctx->h_setup_chunks;
+    pos.resize(V * 4); uv.resize(V * 2); nrm.resize(V * 3); idx.resize(T * 3);
+    std::fill(nrm.begin() + keep_v * 3, nrm.end(), 0.0f);   // batches without normals read zeros
+    orphans.resize(keep_orphans); chunks.resize(keep_chunks);
     ctx->h_b3.assign(sc->n_batches3d, DBatch3{});
     ctx->owner_base.assign(sc->n_batches3d, 0);
     size_t vo = 0, to = 0;
@@ -1207,6 +1247,14 @@ int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
         if (b.pass == RXC_PASS_CHUNK_OPACITY) any_opacity = true;
         memcpy(d.ambient, b.ambient_color, 12);
         memcpy(d.transform, b.transform, 64);
+        if (i < keep3d) {   // geometry of the previous call: flattened arrays, bounding box, orphans and setup chunks stand
+            const DBatch3& o = old_b3[i];
+            d.bflags |= o.bflags & RX_BF_UNIT_W;
+            memcpy(d.aabb_min, o.aabb_min, 12); memcpy(d.aabb_max, o.aabb_max, 12);
+            d.orphan_off = o.orphan_off; d.n_orphans = o.n_orphans; d.chunk_first = o.chunk_first; d.n_chunks = o.n_chunks;
+            vo += b.n_vertices; to += b.n_triangles;
+            continue;
+        }
         if (b.n_vertices) {
             memcpy(&pos[vo * 4], b.vertices, (size_t)b.n_vertices * 16);
             memcpy(&uv[vo * 2], b.uvs, (size_t)b.n_vertices * 8);
@@ -1302,13 +1350,13 @@ int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
     }
     ctx->textures_dirty = true;
     if ((st = upload_textures(ctx)) != RXC_OK) return st;
-    if ((st = upload(ctx, ctx->d_pos, pos.data(), pos.size() * 4)) != RXC_OK) return st;
-    if ((st = upload(ctx, ctx->d_uv, uv.data(), uv.size() * 4)) != RXC_OK) return st;
-    if ((st = upload(ctx, ctx->d_nrm, nrm.data(), nrm.size() * 4)) != RXC_OK) return st;
-    if ((st = upload(ctx, ctx->d_idx, idx.data(), idx.size() * 4)) != RXC_OK) return st;
+    if ((st = upload_from(ctx, ctx->d_pos, pos.data(), pos.size() * 4, keep_v * 16)) != RXC_OK) return st;
+    if ((st = upload_from(ctx, ctx->d_uv, uv.data(), uv.size() * 4, keep_v * 8)) != RXC_OK) return st;
+    if ((st = upload_from(ctx, ctx->d_nrm, nrm.data(), nrm.size() * 4, keep_v * 12)) != RXC_OK) return st;
+    if ((st = upload_from(ctx, ctx->d_idx, idx.data(), idx.size() * 4, keep_t * 12)) != RXC_OK) return st;
     if ((st = upload(ctx, ctx->d_b3, ctx->h_b3.data(), ctx->h_b3.size() * sizeof(DBatch3))) != RXC_OK) return st;
-    if ((st = upload(ctx, ctx->d_chunks, chunks.data(), chunks.size() * sizeof(DChunk))) != RXC_OK) return st;
-    if ((st = upload(ctx, ctx->d_orphans, orphans.data(), orphans.size() * 4)) != RXC_OK) return st;
+    if ((st = upload_from(ctx, ctx->d_chunks, chunks.data(), chunks.size() * sizeof(DChunk), keep_chunks * sizeof(DChunk))) != RXC_OK) return st;
+    if ((st = upload_from(ctx, ctx->d_orphans, orphans.data(), orphans.size() * 4, keep_orphans * 4)) != RXC_OK) return st;
     if ((st = upload(ctx, ctx->d_pos2, pos2.data(), pos2.size() * 4)) != RXC_OK) return st;
     if ((st = upload(ctx, ctx->d_uv2, uv2.data(), uv2.size() * 4)) != RXC_OK) return st;
     if ((st = upload(ctx, ctx->d_idx2, idx2.data(), idx2.size() * 4)) != RXC_OK) return st;
@@ -1338,8 +1386,17 @@ int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
     ctx->list2_cap_min = 0;
     ctx->lists_sized = false;
     ctx->have_scene = true;
+    ctx->h_geometry_valid = true;
     return RXC_OK;
-    });
+}
+}  // namespace
+
+int32_t rxc_set_scene(rxc_ctx* ctx, const rxc_scene* sc) {
+    return guarded(ctx, [&]() -> int32_t { return set_scene_impl(ctx, sc, 0u); });
+}
+
+int32_t rxc_update_scene(rxc_ctx* ctx, const rxc_scene* sc, uint32_t keep_batches3d) {
+    return guarded(ctx, [&]() -> int32_t { return set_scene_impl(ctx, sc, keep_batches3d); });
 }
 
 int32_t rxc_rasterize(rxc_ctx* ctx, const rxc_frame* frame, uint8_t* pixels, uint32_t* owner, float* depth) {

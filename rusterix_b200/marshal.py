@@ -101,6 +101,13 @@ def submission_order(scene: Scene):
     return b3, b2
 
 
+def geometry_keys(scene: Scene):
+    """Per 3D batch in submission order: the identity of its vertex / uv / normal / index arrays (DeviceContext.upload keeps
+    the leading batches whose arrays are the ones already on the device)."""
+    b3, _b2 = submission_order(scene)
+    return [(id(b), id(b.vertices), id(b.uvs), id(getattr(b, "normals", None)), id(b.indices), len(b.vertices), len(b.indices)) for b, _p, _c in b3]
+
+
 class _ActorTiles:
     """EntityTile / ItemTile sources are resolved on the host (the id -> IndexMap lookup of
     src/rasterizer.rs:1130-1177) to indices into one `actor_tiles` array."""

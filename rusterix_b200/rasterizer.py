@@ -26,6 +26,8 @@ class DeviceContext:
         self._scene_key = None
         self._lights_key = None
         self._mapmini_key = ((), ())
+        self._geometry_keys = None      # per 3D batch in submission order: identity of its arrays at the last upload
+        self.last_upload_kept = 0       # leading 3D batches the last scene upload reused (rxc_update_scene)
 
     @classmethod
     def get(cls, device=0) -> "DeviceContext":
@@ -65,7 +67,21 @@ class DeviceContext:
              l.from_linedef) for l in lights)
         if skey != self._scene_key:
             m = marshal.marshal_scene(scene, index_bytes, assets)
-            self.check(self.lib.rxc_set_scene(self.handle, C.byref(m.struct)))
+            # an engine's frame loop replaces the dynamic batches and keeps the world: the leading 3D batches whose arrays are the
+            # ones already resident are not uploaded again (rxc_update_scene)
+            gkeys = marshal.geometry_keys(scene)
+            keep = 0
+            prev = self._scene_key
+            if prev is not None and prev[:3] == skey[:3] and self._geometry_keys:
+                while keep < min(len(gkeys), len(self._geometry_keys)) and gkeys[keep] == self._geometry_keys[keep]:
+                    keep += 1
+            self._geometry_keys = None
+            if keep:
+                self.check(self.lib.rxc_update_scene(self.handle, C.byref(m.struct), keep))
+            else:
+                self.check(self.lib.rxc_set_scene(self.handle, C.byref(m.struct)))
+            self._geometry_keys = gkeys
+            self.last_upload_kept = keep
             self._scene_key = skey
             self._lights_key = lkey
         elif lkey != self._lights_key:

@@ -390,6 +390,7 @@ import oracle_ffi
 import vm_programs
 from rusterix_b200 import Assets, DeviceContext
 from rusterix_b200 import vm as rvm
+from rusterix_b200 import marshal as marshal_mod
 
 # ops whose results go through libm (sin, cos, tan, atan, atan2, pow, ln, sincos): CUDA and glibc agree to a few ulp
 _LIBM_PROGRAMS = {"libm", "wood", "control_flow", "glass", "scanlines"}
@@ -581,6 +582,64 @@ def test_vm_state_report_names_the_scene_whose_frames_depend_on_the_tile_executi
     assert len(plain) == len(leaky) >= 4
     assert plain == [0] * len(plain), plain
     assert 1 in leaky and 2 not in leaky, leaky
+
+
+# ------------------------------------------------------------------------------------------------
+# rxc_update_scene: the frame loop of an engine (the world stays, the dynamic batches change)
+# ------------------------------------------------------------------------------------------------
+def _entity_box(x, tile=0, y=0.2, z=6.0, size=0.8):
+    return (Batch3D.from_box(x, y, z, size, 1.5 * size, size).source(PixelSource.StaticTileIndex(tile)).cull_mode(CullMode.Off)
+            .with_computed_normals())
+
+
+@pytest.mark.parametrize("name", ["map", "chunked", "dense"])
+def test_update_scene_reuses_the_resident_world(name):
+    """Replacing scene.d3_dynamic re-uploads only what follows the unchanged batches (chunks' and static batches' geometry stays
+    on the device): the frame equals the one after a full rxc_set_scene, bit for bit, and far fewer bytes cross PCIe."""
+    cfg = {"map": lambda: scenes.map_config(640, 360, 40, logo_size=64), "chunked": lambda: scenes.chunked_config(480, 270, 40),
+           "dense": lambda: scenes.dense(640, 360, 40, patches=8, patch_verts=23)}[name]()
+    ctx = DeviceContext.get(0)
+    base_lights = list(cfg.scene.dynamic_lights)
+
+    def render():
+        cfg.scene.dynamic_lights = list(base_lights)
+        return render_gpu(cfg.rasterizer(0), cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size)
+
+    kw = dict(y=2.0, z=10.0, size=3.0) if name == "dense" else {}
+    off = 26.0 if name == "dense" else 0.0
+    cfg.scene.d3_dynamic = [_entity_box(off + 5.0, **kw)]
+    a = render()
+    n_before = len(marshal_mod.submission_order(cfg.scene)[0]) - 1 - len(cfg.scene.d3_overlay)
+    h0 = ctx.stats().h2d_bytes
+    cfg.scene.d3_dynamic = [_entity_box(off + 6.5, **kw), _entity_box(off + 3.0, tile=1, **kw)]     # the entities moved, one more appeared
+    b = render()
+    updated_bytes = ctx.stats().h2d_bytes - h0
+    assert ctx.last_upload_kept == n_before, (ctx.last_upload_kept, n_before)
+    ctx._scene_key = None                                                    # the same scene through a full rxc_set_scene
+    h1 = ctx.stats().h2d_bytes
+    c = render()
+    full_bytes = ctx.stats().h2d_bytes - h1
+    assert ctx.last_upload_kept == 0
+    assert np.array_equal(b[0], c[0]) and np.array_equal(b[1], c[1]) and np.array_equal(b[2].view(np.uint32), c[2].view(np.uint32))
+    assert not np.array_equal(a[0], b[0])
+    if name == "dense":
+        assert updated_bytes * 4 < full_bytes, (updated_bytes, full_bytes)
+    compare(b, render_oracle(cfg.rasterizer(0), cfg.scene, cfg.assets, cfg.width, cfg.height, cfg.tile_size), name + " after rxc_update_scene")
+
+
+def test_update_scene_rejects_a_prefix_that_is_not_resident():
+    from rusterix_b200 import RxcError, marshal as m
+    cfg = scenes.cube(64, 64, 40, logo_size=16)
+    ctx = DeviceContext.get(0)
+    render_gpu(cfg.rasterizer(), cfg.scene, cfg.assets, 64, 64, 40)
+    ms = m.marshal_scene(cfg.scene, 4, cfg.assets)
+    import ctypes as C
+    assert ctx.lib.rxc_update_scene(ctx.handle, C.byref(ms.struct), 5) == -1          # more batches than the scene has
+    ctx._scene_key = None
+    other = scenes.teapot(64, 64, 40, logo_size=16, n_frames=2)
+    ms2 = m.marshal_scene(other.scene, 4, other.assets)
+    assert ctx.lib.rxc_update_scene(ctx.handle, C.byref(ms2.struct), 1) == -1         # another batch (vertex count differs)
+    render_gpu(cfg.rasterizer(), cfg.scene, cfg.assets, 64, 64, 40)                   # the context is still usable
 
 
 # ------------------------------------------------------------------------------------------------
