@@ -717,32 +717,33 @@ int32_t launch_group(rxc_ctx* ctx, const DFrame* h_frames, DCounters* h_counters
     const uint32_t rows_total = (uint32_t)(h_frames[0].band_y1 - h_frames[0].band_y0);
     slices = std::max(1u, std::min(std::min(slices, tiles_y), (uint32_t)RX_RASTER_COUNTERS));
     const uint32_t rows_per_slice = (tiles_y + slices - 1) / slices;   // in tile rows
+    // which k_raster: the library's generic instantiation, or the one recompiled for this scene and these frames (rx_jit.cu) once it is there
+    void* jit_kernel = nullptr;
+    const int raster_mode = rxk_raster_mode(S, ctx->W);
+    const bool spec = ctx->kernel_spec && !ctx->spec_mismatch;
+    if (spec && ctx->spec_dirty) { ctx->spec_scene = scene_signature(ctx, ctx->spec_vm_opacity); ctx->spec_dirty = false; }
+    if (ctx->jit && (raster_mode == 2 || spec)) {
+        std::string defines, note;
+        if (spec) {
+            // what all frames of this launch agree on (RX_FS_* of rx_kernels.cu)
+            uint32_t known = 63u, value = 0u;
+            auto bits = [&](const DFrame& F) {
+                return (F.has_ambient ? 1u : 0u) | (F.sun_radiance > 0.0f ? 2u : 0u) | ((F.has_sky | F.has_brush) ? 4u : 0u) | (F.d3_active ? 8u : 0u) |
+                       ((F.d2_active && S.n_rec2d != 0u) ? 16u : 0u) | (S.n_sectors ? 32u : 0u);
+            };
+            value = bits(h_frames[0]);
+            for (uint32_t i = 1; i < n; ++i) known &= ~(bits(h_frames[i]) ^ value);
+            defines = "-DRX_SPEC_ACTIVE=1" + (ctx->spec_scene.empty() ? "" : " " + ctx->spec_scene) + (ctx->spec_lights.empty() ? "" : " " + ctx->spec_lights) +
+                      " -DRX_SPEC_FRAME_KNOWN=" + std::to_string(known) + "u -DRX_SPEC_FRAME_VALUE=" + std::to_string(value & known) + "u";
+            if (const char* e = getenv("RXC_JIT_EXTRA")) defines += std::string(" ") + e;   // experiments: further -D switches for the recompiled kernel
+        }
+        jit_kernel = rxj_kernel(ctx->jit, sample_mode, d_owner || d_depth, raster_mode, defines, &note);
+        if (!note.empty()) ctx->jit_note = note;
+    }
     for (uint32_t k = 0, ty0 = 0; ty0 < tiles_y; ++k, ty0 += rows_per_slice) {
         const uint32_t ty1 = std::min(tiles_y, ty0 + rows_per_slice);
         const size_t slice_tiles = (size_t)(ty1 - ty0) * tiles_x;
         const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)n * slice_tiles, (size_t)ctx->sm_count * ctx->raster_blocks_per_sm));
-        void* jit_kernel = nullptr;
-        const int raster_mode = rxk_raster_mode(S, ctx->W);
-        const bool spec = ctx->kernel_spec && !ctx->spec_mismatch;
-        if (spec && ctx->spec_dirty) { ctx->spec_scene = scene_signature(ctx, ctx->spec_vm_opacity); ctx->spec_dirty = false; }
-        if (ctx->jit && (raster_mode == 2 || spec)) {
-            std::string defines, note;
-            if (spec) {
-                // what all frames of this launch agree on (RX_FS_* of rx_kernels.cu)
-                uint32_t known = 63u, value = 0u;
-                auto bits = [&](const DFrame& F) {
-                    return (F.has_ambient ? 1u : 0u) | (F.sun_radiance > 0.0f ? 2u : 0u) | ((F.has_sky | F.has_brush) ? 4u : 0u) | (F.d3_active ? 8u : 0u) |
-                           ((F.d2_active && S.n_rec2d != 0u) ? 16u : 0u) | (S.n_sectors ? 32u : 0u);
-                };
-                value = bits(h_frames[0]);
-                for (uint32_t i = 1; i < n; ++i) known &= ~(bits(h_frames[i]) ^ value);
-                defines = "-DRX_SPEC_ACTIVE=1" + (ctx->spec_scene.empty() ? "" : " " + ctx->spec_scene) + (ctx->spec_lights.empty() ? "" : " " + ctx->spec_lights) +
-                          " -DRX_SPEC_FRAME_KNOWN=" + std::to_string(known) + "u -DRX_SPEC_FRAME_VALUE=" + std::to_string(value & known) + "u";
-                if (const char* e = getenv("RXC_JIT_EXTRA")) defines += std::string(" ") + e;   // experiments: further -D switches for the recompiled kernel
-            }
-            jit_kernel = rxj_kernel(ctx->jit, sample_mode, d_owner || d_depth, raster_mode, defines, &note);
-            if (!note.empty()) ctx->jit_note = note;
-        }
         { LaunchScope l(ctx, RXK_RASTER); CK(rxk_raster(S, ctx->W, out, n, ty0 * tiles_x, (uint32_t)slice_tiles, k, sample_mode, grid, ctx->stream, jit_kernel)); }
         const int32_t st = after_slice(ty0 * (uint32_t)RX_TILE_H, std::min(rows_total, ty1 * (uint32_t)RX_TILE_H));
         if (st != RXC_OK) return st;
