@@ -508,6 +508,14 @@ int32_t rxc_set_vm_jit(rxc_ctx* ctx, int32_t mode);
  * channel the rasterizer does not fully reset and some program writes, reads a global / local before writing it), 2 not analysable.
  * rxc_vm_state_report: for a program table; usage[i] bit 0 = bound to a 3D batch, bit 1 = to a 2D batch (NULL: both).
  * rxc_vm_scene_state_report: for the current scene with its real bindings (programs no batch uses report 0). */
+/* rxc_set_vm_state_mode: how batch-shader scenes are rendered.  0 (default) = a fresh Execution per fragment, the fast tiled kernel;
+ * 1 = the reference's own order and ONE never-reset Execution per screen tile of `tile_size` pixels (src/rasterizer.rs:310) for every
+ * scene with programs: forward shading in submission order, one GPU thread per tile (k_raster_ordered) -- the reference's frame for
+ * state-dependent programs too, at a fraction of the speed; 2 = that kernel only for the scenes whose report (below) flags a program,
+ * the fast one otherwise: every frame then equals the reference's.  Whole frames only (no band, no row pitch), tile_size <= 224.
+ * rxc_get_vm_state_mode: the mode and how many frames the reference-order kernel has rendered. */
+int32_t rxc_set_vm_state_mode(rxc_ctx* ctx, int32_t mode);
+int32_t rxc_get_vm_state_mode(rxc_ctx* ctx, int32_t* mode, uint64_t* ordered_frames);
 int32_t rxc_vm_state_report(const rxc_program* programs, uint32_t n_programs, const uint8_t* usage, int32_t scene_has_3d, uint32_t* report);
 int32_t rxc_vm_scene_state_report(rxc_ctx* ctx, uint32_t* report, uint32_t cap, uint32_t* n_programs);
 int32_t rxc_vm_jit_info(rxc_ctx* ctx, uint32_t* n_translated, uint32_t* kernels_compiled, uint32_t* pending, uint64_t* jit_launches, char* log, uint32_t log_cap);

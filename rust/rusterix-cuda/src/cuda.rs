@@ -343,6 +343,13 @@ impl CudaRasterizer {
         self.scene_key = 0;
     }
 
+    /// 0 = a fresh `Execution` per fragment (fast, default); 1 = the reference's order and never-reset per-tile `Execution` for every
+    /// scene with shader programs; 2 = for the scenes whose `shader_state_report` flags a program (every frame then equals the reference's).
+    pub fn set_shader_state_mode(&mut self, mode: i32) {
+        let st = unsafe { rxc_set_vm_state_mode(self.ctx, mode) };
+        self.check(st, "rxc_set_vm_state_mode");
+    }
+
     /// Per shader program of the resident scene: 0 = device and reference agree by construction, 1 = the program can observe the
     /// reference's never-reset per-tile `Execution` (src/rasterizer.rs:310), 2 = not analysable.
     pub fn shader_state_report(&self) -> Vec<u32> {

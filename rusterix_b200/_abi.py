@@ -281,6 +281,8 @@ EXPORTS = [
     ("rxc_vm_translate", C.c_int64, [C.POINTER(rxc_program), C.c_uint32, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint32)]),
     ("rxc_vm_jit_compile", C.c_int64, [C.POINTER(rxc_program), C.c_uint32, C.c_int32, C.c_int32, C.c_char_p, C.c_uint32]),
     ("rxc_set_vm_jit", C.c_int32, [C.c_void_p, C.c_int32]),
+    ("rxc_set_vm_state_mode", C.c_int32, [C.c_void_p, C.c_int32]),
+    ("rxc_get_vm_state_mode", C.c_int32, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]),
     ("rxc_vm_state_report", C.c_int32, [C.POINTER(rxc_program), C.c_uint32, C.POINTER(C.c_uint8), C.c_int32, C.POINTER(C.c_uint32)]),
     ("rxc_vm_scene_state_report", C.c_int32, [C.c_void_p, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint32)]),
     ("rxc_vm_jit_info", C.c_int32, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.c_char_p, C.c_uint32]),

@@ -110,6 +110,10 @@ struct rxc_ctx {
     std::string spec_lights;
     bool spec_dirty = true, spec_vm_opacity = false;
     std::vector<uint32_t> vm_state_report;   // per program of the current scene: rxj_state_report with the batches' bindings
+    int vm_state_mode = 0;        // rxc_set_vm_state_mode: 0 = a fresh Execution per fragment (k_raster), 1 = the reference's per-tile Execution
+                                  // for every scene with programs (k_raster_ordered), 2 = for the scenes whose report says it can be observed
+    DevBuf d_ordered;             // scratch planes of k_raster_ordered
+    uint64_t ordered_frames = 0;  // frames rendered by it
     bool spec_mismatch = false;   // a specialised kernel found a scene it was not compiled for (a bug): specialisation stays off
     std::string jit_note;         // last compiler log / load failure (diagnostics)
     uint32_t jit_translated = 0;  // programs of the current scene the translator accepted
@@ -717,6 +721,39 @@ int32_t launch_group(rxc_ctx* ctx, const DFrame* h_frames, DCounters* h_counters
     const uint32_t rows_total = (uint32_t)(h_frames[0].band_y1 - h_frames[0].band_y0);
     slices = std::max(1u, std::min(std::min(slices, tiles_y), (uint32_t)RX_RASTER_COUNTERS));
     const uint32_t rows_per_slice = (tiles_y + slices - 1) / slices;   // in tile rows
+    // the reference's order and per-tile Execution instead (k_raster_ordered), when asked for and the scene has programs to observe it
+    bool ordered = false;
+    if (ctx->vm_state_mode && S.general && S.vm.n_programs) {
+        ordered = ctx->vm_state_mode == 1;
+        for (uint32_t r : ctx->vm_state_report) ordered = ordered || r == 1u;
+    }
+    if (ordered) {
+        const DFrame& F0 = h_frames[0];
+        for (uint32_t i = 0; i < n; ++i) {
+            const DFrame& F = h_frames[i];
+            if (F.band_x0 != 0 || F.band_y0 != 0 || F.band_x1 != F.width || F.band_y1 != F.height || pitch_px)
+                return fail(ctx, RXC_ERR_UNSUPPORTED, "reference-order mode (rxc_set_vm_state_mode) renders whole frames only (no band, no row pitch)");
+            if (F.tile_size != F0.tile_size || F.width != F0.width || F.height != F0.height)
+                return fail(ctx, RXC_ERR_UNSUPPORTED, "reference-order mode: the frames of a batch must share width, height and tile_size");
+        }
+        const uint32_t ts = std::max<uint32_t>(1u, (uint32_t)F0.tile_size);
+        if (ts > 224u) return fail(ctx, RXC_ERR_UNSUPPORTED, "reference-order mode: tile_size above 224");
+        const size_t px = (size_t)F0.width * (size_t)F0.height;
+        int32_t st = reserve(ctx, ctx->d_ordered, (size_t)n * px * 24);
+        if (st != RXC_OK) return st;
+        uint8_t* base = ctx->d_ordered.as<uint8_t>();
+        const size_t plane = (size_t)n * px * 4;
+        const uint32_t api_tiles = ((uint32_t)F0.width + ts - 1) / ts * (((uint32_t)F0.height + ts - 1) / ts);
+        { LaunchScope l(ctx, RXK_RASTER);
+          CK(rxk_raster_ordered(S, ctx->W, out, n, api_tiles, (float*)base, (float*)(base + plane), (uint32_t*)(base + 2 * plane), (uint32_t*)(base + 3 * plane),
+                                (uint32_t*)(base + 4 * plane), (uint32_t*)(base + 5 * plane), px, ctx->stream)); }
+        const int32_t sa = after_slice(0u, rows_total);
+        if (sa != RXC_OK) return sa;
+        if (h_counters) CK(cudaMemcpyAsync(h_counters, ctx->W.counters, n * sizeof(DCounters), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->stats.frames += n;
+        ctx->ordered_frames += n;
+        return RXC_OK;
+    }
     // which k_raster: the library's generic instantiation, or the one recompiled for this scene and these frames (rx_jit.cu) once it is there
     void* jit_kernel = nullptr;
     const int raster_mode = rxk_raster_mode(S, ctx->W);
@@ -1058,7 +1095,7 @@ void rxc_destroy(rxc_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     rxi_mgpu_destroy(ctx);
     if (ctx->jit) { rxj_destroy(ctx->jit); ctx->jit = nullptr; }
-    DevBuf* bufs[] = {&ctx->d_arena, &ctx->d_tex, &ctx->d_tiles, &ctx->d_pos, &ctx->d_uv, &ctx->d_nrm, &ctx->d_idx, &ctx->d_b3,
+    DevBuf* bufs[] = {&ctx->d_ordered, &ctx->d_arena, &ctx->d_tex, &ctx->d_tiles, &ctx->d_pos, &ctx->d_uv, &ctx->d_nrm, &ctx->d_idx, &ctx->d_b3,
                       &ctx->d_chunks, &ctx->d_orphans, &ctx->d_pos2, &ctx->d_uv2, &ctx->d_idx2, &ctx->d_b2, &ctx->d_lights,
                       &ctx->w_frames, &ctx->w_fb, &ctx->w_fb2, &ctx->w_lights, &ctx->w_counters, &ctx->w_vis, &ctx->w_shade,
                       &ctx->w_bins, &ctx->w_ctot, &ctx->w_cbase, &ctx->w_clip, &ctx->w_large, &ctx->w_tcount, &ctx->w_tbase,
@@ -1621,6 +1658,23 @@ int32_t rxc_vm_scene_state_report(rxc_ctx* ctx, uint32_t* report, uint32_t cap, 
     if (!ctx) return RXC_ERR_INVALID;
     if (n_programs) *n_programs = (uint32_t)ctx->vm_state_report.size();
     for (uint32_t i = 0; report && i < cap && i < ctx->vm_state_report.size(); ++i) report[i] = ctx->vm_state_report[i];
+    return RXC_OK;
+    });
+}
+
+int32_t rxc_set_vm_state_mode(rxc_ctx* ctx, int32_t mode) {
+    return guarded(ctx, [&]() -> int32_t {
+    if (!ctx || mode < 0 || mode > 2) return RXC_ERR_INVALID;
+    ctx->vm_state_mode = mode;
+    return RXC_OK;
+    });
+}
+
+int32_t rxc_get_vm_state_mode(rxc_ctx* ctx, int32_t* mode, uint64_t* ordered_frames) {
+    return guarded(ctx, [&]() -> int32_t {
+    if (!ctx) return RXC_ERR_INVALID;
+    if (mode) *mode = ctx->vm_state_mode;
+    if (ordered_frames) *ordered_frames = ctx->ordered_frames;
     return RXC_OK;
     });
 }

@@ -1621,17 +1621,18 @@ __device__ __forceinline__ uint32_t pack_pixel(float r, float g, float b, float 
     return rx_f32_to_u8_saturated(r) | (rx_f32_to_u8_saturated(g) << 8) | (rx_f32_to_u8_saturated(b) << 16) | (rx_f32_to_u8_saturated(a) << 24);
 }
 
-// A 3D fragment of a batch with a VM program, up to and including the program (rasterizer.rs:1062-1317 for the
-// opaque pass, :1500-1637 for the opacity pass).  Returns false when the program hit a device limit.
-__device__ __noinline__ bool vm_fragment_3d(const SceneDev& S, const DFrame& F, const DFrameBatch& FB, const TriShade& sh, float alpha, float beta,
-                                            float z, float fpx, float fpy, uint32_t sample_mode, bool opacity_pass, VmIO* io, f3* world_out) {
+// What a 3D fragment hands to its program, derived with the reference's own arithmetic (rasterizer.rs:1062-1222 for the opaque
+// pass, :1500-1600 for the opacity pass): perspective-correct uv, world position, interpolated / flipped normal, texel.
+struct Frag3D { float u, v; f3 world, normal; uint32_t texel; };
+__device__ __forceinline__ Frag3D vm_inputs_3d(const SceneDev& S, const DFrame& F, const DFrameBatch& FB, const TriShade& sh, float alpha, float beta,
+                                               float z, float fpx, float fpy, uint32_t sample_mode, bool opacity_pass) {
+    Frag3D g;
     const float gamma = 1.0f - alpha - beta;
     float u = sh.uw0 * alpha + sh.uw1 * beta + sh.uw2 * gamma;
     float v = sh.vw0 * alpha + sh.vw1 * beta + sh.vw2 * gamma;
     const float irw = sh.rw0 * alpha + sh.rw1 * beta + sh.rw2 * gamma;
     u = u / irw; v = v / irw;
     const f3 world = screen_to_world_exact(F, fpx, fpy, z);
-    *world_out = world;
     f3 normal = {0.0f, 0.0f, 0.0f};
     if (!opacity_pass && (FB.sd_flags & RX_SD_NORMALS)) {  // :1083-1099
         if (__float_as_uint(sh.pad0) != 0u) {
@@ -1649,14 +1650,27 @@ __device__ __noinline__ bool vm_fragment_3d(const SceneDev& S, const DFrame& F, 
         texel = terrain_sample(S.arena, FB.sd_tex_word, FB.sd_wh, S.chunk_info[FB.sd_chunk], world.x, world.z);
         if (F.has_brush) { const float bp[4] = {F.brush_pos[0], F.brush_pos[1], F.brush_pos[2], F.brush_radius}; texel = brush_terrain(texel, world, bp, F.brush_falloff); }
     }
-    const float inv255 = 1.0f / 255.0f;  // pixel_to_vec4, lib.rs:55-62
+    g.u = u; g.v = v; g.world = world; g.normal = normal; g.texel = texel;
+    return g;
+}
+__device__ __forceinline__ f3 texel_linear_exact(uint32_t texel) {   // pixel_to_vec4 (lib.rs:55-62) + srgb_to_linear_fast
+    const float inv255 = 1.0f / 255.0f;
+    return {srgb_to_linear_exact((float)(texel & 0xFFu) * inv255), srgb_to_linear_exact((float)((texel >> 8) & 0xFFu) * inv255),
+            srgb_to_linear_exact((float)((texel >> 16) & 0xFFu) * inv255)};
+}
+
+// A 3D fragment of a batch with a VM program, up to and including the program (rasterizer.rs:1062-1317 for the
+// opaque pass, :1500-1637 for the opacity pass).  Returns false when the program hit a device limit.
+__device__ __noinline__ bool vm_fragment_3d(const SceneDev& S, const DFrame& F, const DFrameBatch& FB, const TriShade& sh, float alpha, float beta,
+                                            float z, float fpx, float fpy, uint32_t sample_mode, bool opacity_pass, VmIO* io, f3* world_out) {
+    const Frag3D g = vm_inputs_3d(S, F, FB, sh, alpha, beta, z, fpx, fpy, sample_mode, opacity_pass);
+    *world_out = g.world;
     vm_io_reset(*io);
-    io->color = {srgb_to_linear_exact((float)(texel & 0xFFu) * inv255), srgb_to_linear_exact((float)((texel >> 8) & 0xFFu) * inv255),
-                 srgb_to_linear_exact((float)((texel >> 16) & 0xFFu) * inv255)};
-    io->opacity.x = (float)(texel >> 24) / 255.0f;
-    io->normal = normal;
-    io->uv = {u / 4.0f, v / 4.0f, 0.0f};
-    io->hitpoint = world;
+    io->color = texel_linear_exact(g.texel);
+    io->opacity.x = (float)(g.texel >> 24) / 255.0f;
+    io->normal = g.normal;
+    io->uv = {g.u / 4.0f, g.v / 4.0f, 0.0f};
+    io->hitpoint = g.world;
     io->time = {F.time, F.time, F.time};
     if (FB.sd_program < 0 || (uint32_t)FB.sd_program >= S.vm.n_programs) return true;
     return vm_run(S.vm, S.vm.programs[FB.sd_program], *io);
@@ -1666,11 +1680,7 @@ __device__ __noinline__ bool vm_fragment_3d(const SceneDev& S, const DFrame& F, 
 // What the program READS is exact (vm_fragment_3d); what happens to its outputs afterwards only feeds the pixel's RGBA8 and is
 // continuous in them, so it runs in the shading-only fast arithmetic of shade_owner (rsqrt / ex2 / lg2 approximations, FMAs;
 // +-1 LSB): shade_fast_brdf (:1912-1951) with the per-fragment terms (f0, kd, shininess, Fresnel) hoisted out of the light loop.
-__device__ __noinline__ uint32_t shade_owner_vm(const SceneDev& S, const DFrame& F, const DLight* lights, const DFrameBatch& FB, const TriShade& sh,
-                                                float alpha, float beta, float z, float fpx, float fpy, uint32_t sample_mode, uint32_t* fault) {
-    VmIO io;
-    f3 world;
-    if (!vm_fragment_3d(S, F, FB, sh, alpha, beta, z, fpx, fpy, sample_mode, false, &io, &world)) *fault = 1u;
+__device__ __forceinline__ uint32_t vm_light_3d(const SceneDev& S, const DFrame& F, const DLight* lights, const DFrameBatch& FB, const VmIO& io, f3 world) {
     const f3 base = io.color;
     const f3 normal = fnormalize3(io.normal);
     const float rough = rx_clamp(io.roughness.x, 0.0f, 1.0f), metal = rx_clamp(io.metallic.x, 0.0f, 1.0f);
@@ -1729,19 +1739,33 @@ __device__ __noinline__ uint32_t shade_owner_vm(const SceneDev& S, const DFrame&
     auto l2s = [](float x) { const float s = fast_sqrt(x); return __fmaf_rn(-0.055f * s, s, 1.055f * s); };  // rasterizer.rs:28-33
     return fast_u8(l2s(lit.x)) | (fast_u8(l2s(lit.y)) << 8) | (fast_u8(l2s(lit.z)) << 16) | (rx_f32_to_u8_saturated(io.opacity.x) << 24);
 }
+__device__ __noinline__ uint32_t shade_owner_vm(const SceneDev& S, const DFrame& F, const DLight* lights, const DFrameBatch& FB, const TriShade& sh,
+                                                float alpha, float beta, float z, float fpx, float fpy, uint32_t sample_mode, uint32_t* fault) {
+    VmIO io;
+    f3 world;
+    if (!vm_fragment_3d(S, F, FB, sh, alpha, beta, z, fpx, fpy, sample_mode, false, &io, &world)) *fault = 1u;
+    return vm_light_3d(S, F, lights, FB, io, world);
+}
 
 // 2D fragment behind a program (rasterizer.rs:760-797): sRGB texel in, colour out, alpha forced to 1
 __device__ __noinline__ uint32_t shade_2d_vm(const SceneDev& S, const DFrame& F, int program, uint32_t texel, float u, float v, float wx, float wy,
-                                             uint32_t* fault) {
+                                             uint32_t* fault, VmIO* carried = nullptr, VmPersist* ps = nullptr) {
     if (program < 0 || (uint32_t)program >= S.vm.n_programs || S.vm.programs[program].n_words == 0u) return texel;
-    VmIO io;
-    vm_io_reset(io);
+    VmIO fresh;
+    VmIO& io = carried ? *carried : fresh;   // carried: the tile's never-reset Execution (k_raster_ordered); the assignments below are the reference's
+    if (!carried) vm_io_reset(io);
     const float inv255 = 1.0f / 255.0f;
     io.color = {(float)(texel & 0xFFu) * inv255, (float)((texel >> 8) & 0xFFu) * inv255, (float)((texel >> 16) & 0xFFu) * inv255};
-    io.uv = {u / 4.0f, v / 4.0f, 0.0f};
-    io.hitpoint = {wx, wy, 0.0f};
+    io.uv.x = u / 4.0f; io.uv.y = v / 4.0f;
+    io.hitpoint.x = wx; io.hitpoint.y = wy;
     io.time = {F.time, F.time, F.time};
-    if (!vm_run(S.vm, S.vm.programs[program], io)) *fault = 1u;
+    io.roughness.x = 0.5f; io.metallic.x = 0.0f;
+#ifdef __CUDACC_RTC__   // (kernels recompiled for a scene never carry state: that is k_raster_ordered, which lives in the library only)
+    const bool ok = vm_run(S.vm, S.vm.programs[program], io);
+#else
+    const bool ok = ps ? vm_run_t<true>(S.vm, S.vm.programs[program], io, ps) : vm_run(S.vm, S.vm.programs[program], io);
+#endif
+    if (!ok) *fault = 1u;
     return pack_pixel(io.color.x, io.color.y, io.color.z, 1.0f);
 }
 
@@ -1904,7 +1928,7 @@ __device__ __forceinline__ bool los_visible(const SceneDev& S, float fx, float f
 template <bool VM>
 __device__ __forceinline__ uint32_t shade_2d(const SceneDev& S, const DFrame& F, const DLight* __restrict__ lights, const Tri2D& T,
                                              const DBatch2& B, const DFrameBatch2& FB, int px, int py, float fpx, float fpy,
-                                             uint32_t sample_mode, uint32_t color, uint32_t* fault) {
+                                             uint32_t sample_mode, uint32_t color, uint32_t* fault, VmIO* carried = nullptr, VmPersist* ps = nullptr) {
     // barycentric_weights_2d, rasterizer.rs:1731-1750
     const float acx = T.cx - T.ax, acy = T.cy - T.ay, abx = T.bx - T.ax, aby = T.by - T.ay;
     const float apx = fpx - T.ax, apy = fpy - T.ay, pcx = T.cx - fpx, pcy = T.cy - fpy, pbx = T.bx - fpx, pby = T.by - fpy;
@@ -1928,7 +1952,7 @@ __device__ __forceinline__ uint32_t shade_2d(const SceneDev& S, const DFrame& F,
         texel = B.source_pixel;
     }
 
-    if (VM && FB.program >= 0) texel = shade_2d_vm(S, F, FB.program, texel, u, v, wx, wy, fault);  // rasterizer.rs:760-797
+    if (VM && FB.program >= 0) texel = shade_2d_vm(S, F, FB.program, texel, u, v, wx, wy, fault, carried, ps);  // rasterizer.rs:760-797
 
     if (FB.lit) {  // rasterizer.rs:799-873
         float acc[3] = {0.0f, 0.0f, 0.0f};
@@ -2274,7 +2298,7 @@ __device__ __noinline__ void small_triangle_pass(const SceneDev& S, const DFrame
 template <bool VM>
 __device__ __forceinline__ uint32_t apply_2d(const SceneDev& S, const DFrame& F, const DLight* __restrict__ lights,
                                             const DFrameBatch2* __restrict__ fb2, const Tri2D& T, int px, int py, uint32_t sample_mode,
-                                            uint32_t color, uint32_t* fault) {
+                                            uint32_t color, uint32_t* fault, VmIO* carried = nullptr, VmPersist* ps = nullptr) {
     const int x0 = T.bbx & 0xFFFF, x1 = T.bbx >> 16, y0 = T.bby & 0xFFFF, y1 = T.bby >> 16;
     if (px < x0 || px >= x1 || py < y0 || py >= y1) return color;
     const DBatch2& B = S.b2[T.batch];
@@ -2286,7 +2310,7 @@ __device__ __forceinline__ uint32_t apply_2d(const SceneDev& S, const DFrame& F,
     if ((T.ea[0] * fpx + T.eb[0] * fpy + T.ec[0]) < 0.0f) return color;
     if ((T.ea[1] * fpx + T.eb[1] * fpy + T.ec[1]) < 0.0f) return color;
     if ((T.ea[2] * fpx + T.eb[2] * fpy + T.ec[2]) < 0.0f) return color;
-    return shade_2d<VM>(S, F, lights, T, B, fb2[T.batch], px, py, fpx, fpy, sample_mode, color, fault);
+    return shade_2d<VM>(S, F, lights, T, B, fb2[T.batch], px, py, fpx, fpy, sample_mode, color, fault, carried, ps);
 }
 
 // SAMPLE: 0 nearest / 1 linear for every frame of the launch, 2 = read it per frame.  PLANES: owner/depth outputs.
@@ -2859,6 +2883,185 @@ __global__ void __launch_bounds__(128) k_vm_execute(VmDev vm, uint32_t program, 
 }  // namespace
 #else
 // ---------------------------------------------------------------------------------------------
+// k_raster_ordered : the reference's order, for scenes whose batch-shader programs can observe it.
+//
+// The reference shades FORWARD -- every fragment that passes the depth test is shaded at once, in submission order, triangle by
+// triangle, row by row -- and keeps ONE Execution per API tile (tile_size x tile_size pixels) that is never reset
+// (src/rasterizer.rs:310): what a program leaves in it (emissive, globals, the .yz of roughness ...) is seen by the fragments shaded
+// after it in that tile, with or without a program of their own.  k_raster decides the owner of a pixel first
+// and shades only the owner, so it cannot carry that state; this kernel can: one thread (a warp's lane 0) per API tile walks the tile exactly like
+// rasterize()'s closure does (:310-553) -- the 3D records of the tile in submission order (the sorted lists of the 32x32 device tiles
+// the API tile touches, merged), each over its pixel box row by row, depth test, surface-id skip, the fragment's program and
+// lighting with the carried Execution, the write when the result is opaque; the opacity layer likewise; then the miss pass and the
+// opacity blend; then the 2D records in submission order -- with the same per-fragment device functions as k_raster.  It is the slow
+// path by construction (a thread per tile): rxc_set_vm_state_mode selects it, by default nothing does.
+// ---------------------------------------------------------------------------------------------
+struct OrderedScratch {   // per frame `stride` entries each (one per pixel)
+    float* z; float* zop; uint32_t* cop; uint32_t* sid; uint32_t* some; uint32_t* own;
+    size_t stride;
+};
+#define RX_ORDERED_MAX_LISTS 64   // device tiles one API tile may touch (tile_size <= 224)
+
+// the sorted lists of several device tiles as one ascending sequence without repeats
+struct ListMerge {
+    const uint32_t* p[RX_ORDERED_MAX_LISTS];
+    uint32_t n[RX_ORDERED_MAX_LISTS], i[RX_ORDERED_MAX_LISTS];
+    int k;
+    __device__ bool next(uint32_t* out) {
+        uint32_t best = 0xFFFFFFFFu;
+        for (int c = 0; c < k; ++c) if (i[c] < n[c]) best = min(best, p[c][i[c]]);
+        if (best == 0xFFFFFFFFu) return false;   // (the padding of a sorted list is 0xFFFFFFFF too)
+        for (int c = 0; c < k; ++c) while (i[c] < n[c] && p[c][i[c]] == best) ++i[c];
+        *out = best;
+        return true;
+    }
+};
+
+__global__ void __launch_bounds__(128) k_raster_ordered(SceneDev S, Workspace Wk, RasterOut out, uint32_t n_frames, OrderedScratch Q) {
+    const uint32_t f = blockIdx.y;
+    if (f >= n_frames) return;
+    // one tile per WARP, walked by its lane 0: the walk is one serial chain of data-dependent work (32 tiles sharing a warp would
+    // take turns at every divergent branch: 79 ms per 1080p frame of the batch-shader scene instead of the 5 ms a warp each takes)
+    if (threadIdx.x & 31u) return;
+    const DFrame& F = Wk.frames[f];
+    const int W = F.width, H = F.height, ts = max(1, (int)F.tile_size);
+    const int atx = (W + ts - 1) / ts, aty = (H + ts - 1) / ts;
+    const int at = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+    if (at >= atx * aty) return;
+    const int ax0 = (at % atx) * ts, ay0 = (at / atx) * ts, ax1 = min(ax0 + ts, W), ay1 = min(ay0 + ts, H);
+    const DLight* lights = Wk.lights + (size_t)f * Wk.lights_stride;
+    const TriVis* vis = Wk.vis + (size_t)f * Wk.slot_stride;
+    const TriShade* shade = Wk.shade + (size_t)f * Wk.slot_stride;
+    const DFrameBatch* fbs = Wk.fb + (size_t)f * Wk.fb_stride;
+    const uint32_t smode = F.sample_mode;
+    float* zb = Q.z + (size_t)f * Q.stride; float* zop = Q.zop + (size_t)f * Q.stride;
+    uint32_t* cop = Q.cop + (size_t)f * Q.stride; uint32_t* sid = Q.sid + (size_t)f * Q.stride;
+    uint32_t* some = Q.some + (size_t)f * Q.stride; uint32_t* own = Q.own + (size_t)f * Q.stride;
+    uint32_t* px_out = reinterpret_cast<uint32_t*>(out.pixels + (size_t)f * out.frame_stride);
+    const int pitch = (int)out.pitch;
+    uint32_t fault = 0u;
+
+    VmIO io;             // `let mut execution = Execution::new(0)` of this tile (:310)
+    VmPersist ps;
+    vm_io_reset(io);
+    ps.n_globals = 0u; ps.n_locals = 0u;
+
+    for (int y = ay0; y < ay1; ++y)
+        for (int x = ax0; x < ax1; ++x) {
+            const size_t i = (size_t)y * W + x;
+            zb[i] = 1.0f; zop[i] = 1.0f; some[i] = 0u; sid[i] = 0u; cop[i] = 0u; own[i] = RX_OWNER_NONE;   // :287-290
+        }
+
+    // the device tiles under this API tile
+    const int dx0 = ax0 / RX_TILE_W, dx1 = (ax1 - 1) / RX_TILE_W, dy0 = ay0 / RX_TILE_H, dy1 = (ay1 - 1) / RX_TILE_H;
+    ListMerge M;
+    if (F.d3_active) {
+        M.k = 0;
+        for (int dy = dy0; dy <= dy1; ++dy)
+            for (int dx = dx0; dx <= dx1; ++dx) {
+                const size_t t = (size_t)f * Wk.tile_stride + (size_t)dy * F.tiles_x + dx;
+                M.p[M.k] = Wk.lists + (size_t)f * Wk.list_stride + Wk.tile_base[t]; M.n[M.k] = Wk.tile_count[t]; M.i[M.k] = 0u;
+                ++M.k;
+            }
+        uint32_t slot;
+        while (M.next(&slot)) {
+            const float4* q = reinterpret_cast<const float4*>(vis + slot);
+            const float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4], q5 = q[5];
+            const uint32_t bbx = __float_as_uint(q5.y), bby = __float_as_uint(q5.z), meta = __float_as_uint(q5.w);
+            const int x0 = max(ax0, (int)(bbx & 0xFFFFu)), x1 = min(ax1, (int)(bbx >> 16)), y0 = max(ay0, (int)(bby & 0xFFFFu)), y1 = min(ay1, (int)(bby >> 16));
+            if (x0 >= x1 || y0 >= y1) continue;
+            const DFrameBatch& FB = fbs[meta & RX_META_BATCH];
+            const TriShade& sh = shade[slot];
+            const float ea[3] = {q3.x, q3.y, q3.z}, eb[3] = {q3.w, q4.x, q4.y}, ec[3] = {q4.z, q4.w, q5.x};
+            const bool opacity = (meta & RX_META_OPACITY) != 0u, has_profile = (FB.sd_flags & RX_SD_HAS_PROFILE) != 0u;
+            const bool program = (FB.sd_flags & RX_SD_SHADER) && FB.sd_program >= 0 && (uint32_t)FB.sd_program < S.vm.n_programs;
+            for (int y = y0; y < y1; ++y)            // rasterizer.rs:1018-1020: rows, then columns
+                for (int x = x0; x < x1; ++x) {
+                    const float fpx = (float)x + 0.5f, fpy = (float)y + 0.5f;   // :1022
+                    if ((ea[0] * fpx + eb[0] * fpy) + ec[0] < 0.0f || (ea[1] * fpx + eb[1] * fpy) + ec[1] < 0.0f || (ea[2] * fpx + eb[2] * fpy) + ec[2] < 0.0f) continue;   // edge.rs:28-36
+                    float al, be;
+                    const float z = fragment_depth(q0, q1, q2, meta, fpx, fpy, &al, &be);
+                    const size_t i = (size_t)y * W + x;
+                    if (opacity) {   // d3_rasterize_opacity, :1425-1690
+                        if (!(z < zop[i])) continue;
+                        const Frag3D g = vm_inputs_3d(S, F, FB, sh, al, be, z, fpx, fpy, smode, true);
+                        io.color = texel_linear_exact(g.texel);
+                        io.opacity.x = (float)(g.texel >> 24) / 255.0f;
+                        if (program && S.vm.programs[FB.sd_program].n_words != 0u) {   // :1643-1668
+                            io.normal = {0.0f, 0.0f, 0.0f};
+                            io.uv.x = g.u / 4.0f; io.uv.y = g.v / 4.0f;
+                            io.hitpoint = g.world;
+                            io.time = {F.time, F.time, F.time};
+                            io.roughness.x = 0.5f; io.metallic.x = 0.0f;
+                            if (!vm_run_t<true>(S.vm, S.vm.programs[FB.sd_program], io, &ps)) fault = 1u;
+                        }
+                        cop[i] = pack_pixel(linear_to_srgb_exact(io.color.x), linear_to_srgb_exact(io.color.y), linear_to_srgb_exact(io.color.z), io.opacity.x);
+                        zop[i] = z; sid[i] = FB.sd_profile; some[i] = has_profile ? 1u : 0u;
+                        continue;
+                    }
+                    if (has_profile && some[i] && sid[i] == FB.sd_profile) continue;   // :1041-1047
+                    if (!(z < zb[i])) continue;                                        // :1051-1060
+                    const Frag3D g = vm_inputs_3d(S, F, FB, sh, al, be, z, fpx, fpy, smode, false);
+                    io.color = texel_linear_exact(g.texel);                            // :1259-1281 / :1310-1316: every branch assigns these
+                    io.opacity.x = (float)(g.texel >> 24) / 255.0f;
+                    io.normal = g.normal;
+                    io.roughness.x = 0.5f; io.metallic.x = 0.0f;
+                    if (program && S.vm.programs[FB.sd_program].n_words != 0u) {       // :1284-1301
+                        io.uv.x = g.u / 4.0f; io.uv.y = g.v / 4.0f;
+                        io.hitpoint = g.world;
+                        io.time = {F.time, F.time, F.time};
+                        if (!vm_run_t<true>(S.vm, S.vm.programs[FB.sd_program], io, &ps)) fault = 1u;
+                    }
+                    const uint32_t color = vm_light_3d(S, F, lights, FB, io, g.world);  // :1319-1404, emissive of the carried Execution included
+                    if ((color >> 24) == 255u) { px_out[(size_t)y * pitch + x] = color; zb[i] = z; own[i] = slot; }   // :1408-1412
+                }
+        }
+    }
+
+    // miss pass (:409-461), opacity blend (:464-495), or the 2D-only background (:277-307)
+    for (int y = ay0; y < ay1; ++y)
+        for (int x = ax0; x < ax1; ++x) {
+            const size_t i = (size_t)y * W + x;
+            uint32_t color;
+            if (F.d3_active) {
+                if (own[i] != RX_OWNER_NONE) color = px_out[(size_t)y * pitch + x];
+                else { color = 0xFF000000u; if (F.has_sky | F.has_brush) color = miss_color(&F, x, y); }
+                if (zop[i] < 1.0f && zb[i] > zop[i]) color = blend_opacity(cop[i], color, F.preserve_transparency != 0u);
+            } else {
+                color = F.has_bg_color ? F.bg_color : 0u;
+                if (!F.ignore_bg_shader && F.bg_shader != RXC_BG_NONE) color = shade_background(F, x, y);
+            }
+            px_out[(size_t)y * pitch + x] = color;
+            if (out.owner) out.owner[i] = own[i];
+            if (out.depth) out.depth[i] = zb[i];
+        }
+
+    // 2D batches in submission order (:501-553, :584-959) with the same Execution
+    if (F.d2_active && S.n_rec2d != 0u) {
+        const Tri2D* recs = Wk.tri2d + (size_t)f * Wk.tri2d_stride;
+        const DFrameBatch2* fb2 = Wk.fb2 + (size_t)f * Wk.fb2_stride;
+        M.k = 0;
+        for (int dy = dy0; dy <= dy1; ++dy)
+            for (int dx = dx0; dx <= dx1; ++dx) {
+                const size_t t = (size_t)f * Wk.tile_stride + (size_t)dy * F.tiles_x + dx;
+                M.p[M.k] = Wk.lists2 + (size_t)f * Wk.list2_stride + Wk.tile_base2[t]; M.n[M.k] = Wk.tile_count2[t]; M.i[M.k] = 0u;
+                ++M.k;
+            }
+        uint32_t r;
+        while (M.next(&r)) {
+            const Tri2D& T = recs[r];
+            const int x0 = max(ax0, (int)(T.bbx & 0xFFFFu)), x1 = min(ax1, (int)(T.bbx >> 16)), y0 = max(ay0, (int)(T.bby & 0xFFFFu)), y1 = min(ay1, (int)(T.bby >> 16));
+            for (int y = y0; y < y1; ++y)
+                for (int x = x0; x < x1; ++x) {
+                    uint32_t* c = px_out + (size_t)y * pitch + x;
+                    *c = apply_2d<true>(S, F, lights, fb2, T, x, y, smode, *c, &fault, &io, &ps);
+                }
+        }
+    }
+    if (fault) atomicOr(&Wk.counters[f].overflow, 16u);
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_list_sort (general mode): one CTA per tile sorts its list ascending (= submission order).  The
 // allocation of a list is a power of two (k_tile_alloc), the tail is padded with 0xFFFFFFFF.
 // ---------------------------------------------------------------------------------------------
@@ -3025,6 +3228,13 @@ cudaError_t rxk_bin_fill(const SceneDev& S, const Workspace& W, uint32_t n_frame
     if (S.n_tris == 0) return cudaSuccess;
     dim3 grid(grid_x, n_frames);
     k_bin_fill<<<grid, 256, 0, st>>>(S, W);
+    return cudaGetLastError();
+}
+cudaError_t rxk_raster_ordered(const SceneDev& S, const Workspace& W, const RasterOut& out, uint32_t n_frames, uint32_t api_tiles, float* z, float* zop,
+                               uint32_t* cop, uint32_t* sid, uint32_t* some, uint32_t* own, size_t stride, cudaStream_t st) {
+    OrderedScratch q = {z, zop, cop, sid, some, own, stride};
+    dim3 grid((api_tiles + 3u) / 4u, n_frames);
+    k_raster_ordered<<<grid, 128, 0, st>>>(S, W, out, n_frames, q);
     return cudaGetLastError();
 }
 int rxk_raster_mode(const SceneDev& S, const Workspace& W) {

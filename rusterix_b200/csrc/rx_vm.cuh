@@ -23,6 +23,14 @@
 struct VmIO {   // the Execution fields the rasterizer reads and writes (execution.rs:27-55)
     f3 uv, color, normal, hitpoint, time, opacity, roughness, metallic, emissive, bump;
 };
+// What else an Execution carries from one shade() to the next when it is never reset (the reference's per-tile Execution,
+// src/rasterizer.rs:310; only the reference-order kernel k_raster_ordered keeps one): `reset` and `shade` RESIZE the globals and
+// the locals of shade()'s frame (execution.rs:103-107, :773), they do not clear them.
+struct VmPersist {
+    f3 globals[16];
+    f3 locals[32];
+    uint32_t n_globals, n_locals;
+};
 
 __device__ __forceinline__ void vm_io_reset(VmIO& io) {  // Execution::new, execution.rs:58-77
     const f3 z = {0.0f, 0.0f, 0.0f};
@@ -186,12 +194,14 @@ __device__ __forceinline__ bool vm_run(const VmDev& vm, const DProgram& P, VmIO&
 #else
 // Runs the shade function of program P on `io`.  Returns false when a device limit was hit (stack,
 // frames, op budget) or the code is malformed; the reference would have panicked or looped.
-__device__ __noinline__ bool vm_run(const VmDev& vm, const DProgram& P, VmIO& io) {
+// PERSIST: globals and shade()'s locals start from `ps` and are left there (see VmPersist); always interpreted.
+template <bool PERSIST>
+__device__ __noinline__ bool vm_run_t(const VmDev& vm, const DProgram& P, VmIO& io, VmPersist* ps) {
     // The value stack keeps its top in registers (`t`): positions 1..sp-1 live in stack[1..sp-1], position sp in
     // `t`; stack[0] is a dummy that absorbs the spill of an empty stack's top.  A unary op then touches no memory,
     // a binary op loads one operand, a push stores one (half the local-memory traffic of a stack held in memory).
 #ifdef RXVM_JIT
-    if (P.jit_index != 0xFFFFFFFFu) {   // the program as straight-line code; 2 = its stack took a shape the translator did not verify
+    if (!PERSIST && P.jit_index != 0xFFFFFFFFu) {   // the program as straight-line code; 2 = its stack took a shape the translator did not verify
         const bool may_bail = vm_jit_may_bail(P.jit_index);
         VmIO saved;
         if (may_bail) saved = io;
@@ -209,8 +219,8 @@ __device__ __noinline__ bool vm_run(const VmDev& vm, const DProgram& P, VmIO& io
     const uint32_t n_words = P.n_words, n_globals = P.n_globals, shade_locals = P.shade_locals;
     if (n_words == 0u) return true;                       // shade_index is None
     if (shade_locals > 32u || n_globals > RXVM_GLOBALS) return false;
-    for (uint32_t i = 0; i < n_globals; ++i) globals[i] = zero;
-    for (uint32_t i = 0; i < shade_locals; ++i) locals[i] = zero;
+    for (uint32_t i = 0; i < n_globals; ++i) globals[i] = (PERSIST && i < ps->n_globals) ? ps->globals[i] : zero;
+    for (uint32_t i = 0; i < shade_locals; ++i) locals[i] = (PERSIST && i < ps->n_locals) ? ps->locals[i] : zero;
     const uint32_t* __restrict__ code = vm.code + P.code_off;
     uint32_t pc = P.entry, sp = 0, lb = 0, nl = shade_locals, nf = 0, nm = 0;
     bool have_ret = false;
@@ -271,7 +281,14 @@ __device__ __noinline__ bool vm_run(const VmDev& vm, const DProgram& P, VmIO& io
                 have_ret = true;
                 // fall through: leave the function
             case RXVM_END: {
-                if (nf == 0u) return true;
+                if (nf == 0u) {
+                    if (PERSIST) {   // (at the outermost frame lb is 0: locals[0 .. shade_locals) are shade()'s)
+                        for (uint32_t i = 0; i < n_globals; ++i) ps->globals[i] = globals[i];
+                        for (uint32_t i = 0; i < shade_locals; ++i) ps->locals[i] = locals[i];
+                        ps->n_globals = n_globals; ps->n_locals = shade_locals;
+                    }
+                    return true;
+                }
                 --nf;
                 const uint32_t base = fr_sb[nf];
                 f3 r = zero;
@@ -352,4 +369,5 @@ __device__ __noinline__ bool vm_run(const VmDev& vm, const DProgram& P, VmIO& io
 #undef VM_POPTO
 #undef VM_B
 }
+__device__ __forceinline__ bool vm_run(const VmDev& vm, const DProgram& P, VmIO& io) { return vm_run_t<false>(vm, P, io, nullptr); }
 #endif  // !(RXVM_JIT && RXVM_JIT_COMPLETE)

@@ -129,6 +129,16 @@ class DeviceContext:
         return {"translated": int(nt.value), "kernels": int(nk.value), "pending": bool(pend.value), "launches": int(used.value),
                 "log": log.value.decode(errors="replace")}
 
+    def set_vm_state_mode(self, mode: int):
+        """rxc_set_vm_state_mode: 0 = a fresh Execution per fragment (fast, default), 1 = the reference's order and per-tile
+        Execution for every scene with programs, 2 = for the scenes whose state report flags a program."""
+        self.check(self.lib.rxc_set_vm_state_mode(self.handle, int(mode)))
+
+    def ordered_frames(self) -> int:
+        mode, n = C.c_int32(0), C.c_uint64(0)
+        self.check(self.lib.rxc_get_vm_state_mode(self.handle, C.byref(mode), C.byref(n)))
+        return int(n.value)
+
     def vm_state_report(self):
         """rxc_vm_scene_state_report: per program of the resident scene 0 = the device and the reference (one Execution per
         tile, never reset) compute the same thing, 1 = the program can observe the difference, 2 = not analysable."""

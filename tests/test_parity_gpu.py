@@ -585,6 +585,77 @@ def test_vm_state_report_names_the_scene_whose_frames_depend_on_the_tile_executi
 
 
 # ------------------------------------------------------------------------------------------------
+# rxc_set_vm_state_mode: the reference's order and per-tile Execution on the device (k_raster_ordered)
+# ------------------------------------------------------------------------------------------------
+class _StateMode:
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __enter__(self):
+        DeviceContext.get(0).set_vm_state_mode(self.mode)
+        return DeviceContext.get(0)
+
+    def __exit__(self, *exc):
+        DeviceContext.get(0).set_vm_state_mode(0)
+
+
+@pytest.mark.parametrize("tile_size", [40, 16, 64])
+def test_reference_order_mode_reproduces_the_state_leak(tile_size):
+    """The `emissive` variant of the batch-shader scene: one branch of a program writes `emissive`, the reference never resets its
+    per-tile Execution, so every fragment shaded later in that tile glows -- a frame that depends on tile_size and on the order of
+    the triangles.  In reference-order mode the device renders THAT frame: compared with the FAITHFUL oracle (no per-fragment
+    switch), owner and depth bit for bit, colours within the bar.  The fast mode renders something else."""
+    cfg = scenes.shaded_config(480, 360, tile_size, emissive=True)
+    with _StateMode(1) as ctx:
+        n0 = ctx.ordered_frames()
+        st = _run(cfg, frame=1)
+        assert ctx.ordered_frames() == n0 + 1
+        ordered = render_gpu(cfg.rasterizer(1), cfg.scene, cfg.assets, 480, 360, tile_size)
+    assert st["within1_frac"] > 0.999
+    fast = render_gpu(cfg.rasterizer(1), cfg.scene, cfg.assets, 480, 360, tile_size)
+    assert np.array_equal(fast[1], ordered[1]) and np.array_equal(fast[2].view(np.uint32), ordered[2].view(np.uint32))   # same owners, same depth
+    leak = np.abs(fast[0].astype(np.int16) - ordered[0].astype(np.int16)).max(axis=-1) > 1
+    assert leak.mean() > 0.01, leak.mean()                                                                                 # ... other colours
+
+
+def test_reference_order_mode_equals_the_fast_mode_where_nothing_leaks():
+    """The plain batch-shader scene (3D, chunk, opacity pane and 2D programs that assign what they read): both kernels render the
+    reference's frame -- same owners and depth, colours within 1 LSB of each other and of the oracle."""
+    cfg = scenes.shaded_config(480, 360, 40)
+    fast = render_gpu(cfg.rasterizer(2), cfg.scene, cfg.assets, 480, 360, 40)
+    with _StateMode(1):
+        ordered = render_gpu(cfg.rasterizer(2), cfg.scene, cfg.assets, 480, 360, 40)
+        st = _run(cfg, frame=2)
+    assert st["within1_frac"] > 0.999
+    assert np.array_equal(fast[1], ordered[1]) and np.array_equal(fast[2].view(np.uint32), ordered[2].view(np.uint32))
+    d = np.abs(fast[0].astype(np.int16) - ordered[0].astype(np.int16)).max(axis=-1)
+    assert (d <= 1).mean() > 0.999, (d <= 1).mean()
+
+
+def test_state_mode_auto_takes_the_reference_order_only_where_the_report_asks_for_it():
+    with _StateMode(2) as ctx:
+        n0 = ctx.ordered_frames()
+        plain = scenes.shaded_config(160, 120, 40)
+        _run(plain, frame=0)
+        assert ctx.ordered_frames() == n0                       # nothing to observe: the fast kernel
+        leaky = scenes.shaded_config(160, 120, 40, emissive=True)
+        _run(leaky, frame=0)                                    # ... compared with the faithful oracle
+        assert ctx.ordered_frames() == n0 + 1
+        cube = scenes.cube(160, 120, 40, logo_size=16)
+        _run(cube)
+        assert ctx.ordered_frames() == n0 + 1                   # no programs at all
+
+
+def test_reference_order_mode_refuses_bands():
+    from rusterix_b200 import RxcError
+    cfg = scenes.shaded_config(160, 128, 40, emissive=True)
+    with _StateMode(1):
+        with pytest.raises(RxcError) as e:
+            render_gpu(cfg.rasterizer(0), cfg.scene, cfg.assets, 160, 128, 40, band=(32, 96))
+        assert e.value.status == -3
+
+
+# ------------------------------------------------------------------------------------------------
 # rxc_update_scene: the frame loop of an engine (the world stays, the dynamic batches change)
 # ------------------------------------------------------------------------------------------------
 def _entity_box(x, tile=0, y=0.2, z=6.0, size=0.8):

@@ -39,6 +39,7 @@ ARG_NAMES = {
     "rxc_vm_translate": ["programs", "n_programs", "source", "cap", "jit_index"],
     "rxc_vm_jit_compile": ["programs", "n_programs", "sample_mode", "planes", "log", "log_cap"],
     "rxc_set_vm_jit": ["ctx", "mode"], "rxc_update_scene": ["ctx", "scene", "keep_batches3d"],
+    "rxc_set_vm_state_mode": ["ctx", "mode"], "rxc_get_vm_state_mode": ["ctx", "mode", "ordered_frames"],
     "rxc_vm_state_report": ["programs", "n_programs", "usage", "scene_has_3d", "report"],
     "rxc_vm_scene_state_report": ["ctx", "report", "cap", "n_programs"],
     "rxc_vm_jit_info": ["ctx", "n_translated", "kernels_compiled", "pending", "jit_launches", "log", "log_cap"],
