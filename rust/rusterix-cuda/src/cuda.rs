@@ -129,7 +129,8 @@ impl CudaRasterizer {
         // already resident (same pointers and lengths as at the last upload) are not validated, flattened or uploaded again.
         let gkeys: Vec<(usize, usize, usize, usize)> = b3.iter().map(|b| (b.vertices as usize, b.indices as usize, b.n_vertices as usize, b.n_triangles as usize)).collect();
         let keep = if self.scene_key != 0 { gkeys.iter().zip(self.geometry_keys.iter()).take_while(|(a, b)| a == b).count() } else { 0 };
-        let st = if keep > 0 { unsafe { rxc_update_scene(self.ctx, &s, keep as u32) } } else { unsafe { rxc_set_scene(self.ctx, &s) } };
+        let mut st = if keep > 0 { unsafe { rxc_update_scene(self.ctx, &s, keep as u32) } } else { RXC_ERR_INVALID };
+        if st == RXC_ERR_INVALID { st = unsafe { rxc_set_scene(self.ctx, &s) }; }   // nothing to keep, or the library no longer holds that prefix
         if st == RXC_ERR_UNSUPPORTED { return false; }
         self.check(st, "rxc_set_scene");
         self.geometry_keys = gkeys;

@@ -76,10 +76,11 @@ class DeviceContext:
                 while keep < min(len(gkeys), len(self._geometry_keys)) and gkeys[keep] == self._geometry_keys[keep]:
                     keep += 1
             self._geometry_keys = None
-            if keep:
-                self.check(self.lib.rxc_update_scene(self.handle, C.byref(m.struct), keep))
-            else:
-                self.check(self.lib.rxc_set_scene(self.handle, C.byref(m.struct)))
+            st = self.lib.rxc_update_scene(self.handle, C.byref(m.struct), keep) if keep else _abi.RXC_ERR_INVALID
+            if st == _abi.RXC_ERR_INVALID:   # nothing to keep, or the library no longer holds that prefix (an earlier upload failed): everything
+                keep = 0
+                st = self.lib.rxc_set_scene(self.handle, C.byref(m.struct))
+            self.check(st)
             self._geometry_keys = gkeys
             self.last_upload_kept = keep
             self._scene_key = skey
