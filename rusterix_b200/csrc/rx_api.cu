@@ -737,7 +737,11 @@ int32_t launch_group(rxc_ctx* ctx, const DFrame* h_frames, DCounters* h_counters
                 return fail(ctx, RXC_ERR_UNSUPPORTED, "reference-order mode: the frames of a batch must share width, height and tile_size");
         }
         const uint32_t ts = std::max<uint32_t>(1u, (uint32_t)F0.tile_size);
-        if (ts > 224u) return fail(ctx, RXC_ERR_UNSUPPORTED, "reference-order mode: tile_size above 224");
+        {   // an API tile may lie over at most 64 of the 32x32 device tiles whose lists the kernel merges
+            const uint32_t sx = std::min<uint32_t>(ts, (uint32_t)F0.width), sy = std::min<uint32_t>(ts, (uint32_t)F0.height);
+            if (((sx + 30u) / 32u + 1u) * ((sy + 30u) / 32u + 1u) > 64u)
+                return fail(ctx, RXC_ERR_UNSUPPORTED, "reference-order mode: tile_size too large (an API tile may span at most 64 device tiles: up to 224 x 224 pixels)");
+        }
         const size_t px = (size_t)F0.width * (size_t)F0.height;
         int32_t st = reserve(ctx, ctx->d_ordered, (size_t)n * px * 24);
         if (st != RXC_OK) return st;
