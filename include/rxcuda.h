@@ -508,11 +508,13 @@ int32_t rxc_set_vm_jit(rxc_ctx* ctx, int32_t mode);
  * channel the rasterizer does not fully reset and some program writes, reads a global / local before writing it), 2 not analysable.
  * rxc_vm_state_report: for a program table; usage[i] bit 0 = bound to a 3D batch, bit 1 = to a 2D batch (NULL: both).
  * rxc_vm_scene_state_report: for the current scene with its real bindings (programs no batch uses report 0). */
-/* rxc_set_vm_state_mode: how batch-shader scenes are rendered.  0 (default) = a fresh Execution per fragment, the fast tiled kernel;
+/* rxc_set_vm_state_mode: how batch-shader scenes are rendered.  0 = a fresh Execution per fragment, the fast tiled kernel, always;
  * 1 = the reference's own order and ONE never-reset Execution per screen tile of `tile_size` pixels (src/rasterizer.rs:310) for every
- * scene with programs: forward shading in submission order, one GPU thread per tile (k_raster_ordered) -- the reference's frame for
- * state-dependent programs too, at a fraction of the speed; 2 = that kernel only for the scenes whose report (below) flags a program,
- * the fast one otherwise: every frame then equals the reference's.  Whole frames only (no band, no row pitch), tile_size <= 224.
+ * scene with programs: forward shading in submission order, one GPU warp per tile (k_raster_ordered) -- the reference's frame for
+ * state-dependent programs too, at a fraction of the speed; 2 (the default; environment RXC_VM_STATE_MODE) = that kernel only for
+ * the scenes whose report (below) flags a program, the fast one otherwise: every frame equals the reference's and only the scenes
+ * that need it pay for it.  The kernel renders whole frames (no band, no row pitch) with API tiles up to 224 x 224 pixels: what it
+ * cannot render is RXC_ERR_UNSUPPORTED in mode 1 and goes to the fast kernel in mode 2.
  * rxc_get_vm_state_mode: the mode and how many frames the reference-order kernel has rendered. */
 int32_t rxc_set_vm_state_mode(rxc_ctx* ctx, int32_t mode);
 int32_t rxc_get_vm_state_mode(rxc_ctx* ctx, int32_t* mode, uint64_t* ordered_frames);

@@ -110,8 +110,8 @@ struct rxc_ctx {
     std::string spec_lights;
     bool spec_dirty = true, spec_vm_opacity = false;
     std::vector<uint32_t> vm_state_report;   // per program of the current scene: rxj_state_report with the batches' bindings
-    int vm_state_mode = 0;        // rxc_set_vm_state_mode: 0 = a fresh Execution per fragment (k_raster), 1 = the reference's per-tile Execution
-                                  // for every scene with programs (k_raster_ordered), 2 = for the scenes whose report says it can be observed
+    int vm_state_mode = 2;        // rxc_set_vm_state_mode: 0 = a fresh Execution per fragment (k_raster), 1 = the reference's per-tile Execution
+                                  // for every scene with programs (k_raster_ordered), 2 (default) = for the scenes whose report says it can be observed
     DevBuf d_ordered;             // scratch planes of k_raster_ordered
     uint64_t ordered_frames = 0;  // frames rendered by it
     bool spec_mismatch = false;   // a specialised kernel found a scene it was not compiled for (a bug): specialisation stays off
@@ -728,20 +728,29 @@ int32_t launch_group(rxc_ctx* ctx, const DFrame* h_frames, DCounters* h_counters
         for (uint32_t r : ctx->vm_state_report) ordered = ordered || r == 1u;
     }
     if (ordered) {
+        // whole frames of one size, API tiles over at most 64 of the 32x32 device tiles whose lists the kernel merges; what it cannot
+        // render is an error when the mode was forced (1) and goes to the fast kernel (a fresh Execution per fragment) in auto mode (2)
         const DFrame& F0 = h_frames[0];
-        for (uint32_t i = 0; i < n; ++i) {
+        const char* why = nullptr;
+        for (uint32_t i = 0; i < n && !why; ++i) {
             const DFrame& F = h_frames[i];
             if (F.band_x0 != 0 || F.band_y0 != 0 || F.band_x1 != F.width || F.band_y1 != F.height || pitch_px)
-                return fail(ctx, RXC_ERR_UNSUPPORTED, "reference-order mode (rxc_set_vm_state_mode) renders whole frames only (no band, no row pitch)");
-            if (F.tile_size != F0.tile_size || F.width != F0.width || F.height != F0.height)
-                return fail(ctx, RXC_ERR_UNSUPPORTED, "reference-order mode: the frames of a batch must share width, height and tile_size");
+                why = "reference-order mode (rxc_set_vm_state_mode) renders whole frames only (no band, no row pitch)";
+            else if (F.tile_size != F0.tile_size || F.width != F0.width || F.height != F0.height)
+                why = "reference-order mode: the frames of a batch must share width, height and tile_size";
         }
+        const uint32_t ts_probe = std::max<uint32_t>(1u, (uint32_t)F0.tile_size);
+        const uint32_t sx = std::min<uint32_t>(ts_probe, (uint32_t)F0.width), sy = std::min<uint32_t>(ts_probe, (uint32_t)F0.height);
+        if (!why && ((sx + 30u) / 32u + 1u) * ((sy + 30u) / 32u + 1u) > 64u)
+            why = "reference-order mode: tile_size too large (an API tile may span at most 64 device tiles: up to 224 x 224 pixels)";
+        if (why) {
+            if (ctx->vm_state_mode == 1) return fail(ctx, RXC_ERR_UNSUPPORTED, why);
+            ordered = false;
+        }
+    }
+    if (ordered) {
+        const DFrame& F0 = h_frames[0];
         const uint32_t ts = std::max<uint32_t>(1u, (uint32_t)F0.tile_size);
-        {   // an API tile may lie over at most 64 of the 32x32 device tiles whose lists the kernel merges
-            const uint32_t sx = std::min<uint32_t>(ts, (uint32_t)F0.width), sy = std::min<uint32_t>(ts, (uint32_t)F0.height);
-            if (((sx + 30u) / 32u + 1u) * ((sy + 30u) / 32u + 1u) > 64u)
-                return fail(ctx, RXC_ERR_UNSUPPORTED, "reference-order mode: tile_size too large (an API tile may span at most 64 device tiles: up to 224 x 224 pixels)");
-        }
         const size_t px = (size_t)F0.width * (size_t)F0.height;
         int32_t st = reserve(ctx, ctx->d_ordered, (size_t)n * px * 24);
         if (st != RXC_OK) return st;
@@ -1082,6 +1091,7 @@ int32_t rxc_create(int32_t device, rxc_ctx** out) {
     if (const char* e = getenv("RXC_TMA_STORE")) ctx->tma_store = atoi(e);
     if (const char* e = getenv("RXC_VM_JIT")) ctx->vm_jit = std::min(2, std::max(0, atoi(e)));
     if (const char* e = getenv("RXC_KERNEL_SPEC")) ctx->kernel_spec = atoi(e) != 0;
+    if (const char* e = getenv("RXC_VM_STATE_MODE")) ctx->vm_state_mode = std::min(2, std::max(0, atoi(e)));
     if (const char* e = getenv("RXC_FRONT_STOP")) ctx->front_stop = std::max(0, atoi(e));
     if (const char* e = getenv("RXC_SMALL_MIN_LIST")) ctx->small_min_list = atoi(e);   // 0 = pass off
     if (const char* e = getenv("RXC_SMALL_GSHIFT")) ctx->small_gshift = std::min(5, std::max(0, atoi(e)));

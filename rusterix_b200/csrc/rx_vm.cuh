@@ -6,7 +6,9 @@
 // Deviations from the reference, all documented in DESIGN.md:
 //  * `Execution` is created once per screen tile and never reset (src/rasterizer.rs:310), so globals,
 //    locals, emissive, bump, uv.z ... written by one fragment leak into the next fragment shaded in the same
-//    tile.  Here every fragment starts from Execution::new(): the state is per fragment.
+//    tile.  In k_raster every fragment starts from Execution::new(): the state is per fragment.  Scenes whose programs
+//    can observe the difference (rxj_state_report) are rendered by k_raster_ordered instead, which carries one
+//    Execution per tile like the reference (rxc_set_vm_state_mode, on by default).
 //  * a `Return` inside a `For` leaves the function (the reference pops the loop condition from an
 //    empty or foreign stack after it: a panic or garbage).
 //  * sin/cos/tan/atan/atan2/pow/ln come from CUDA's libm instead of the host's (<= 2 ulp apart).

@@ -396,6 +396,19 @@ from rusterix_b200 import marshal as marshal_mod
 _LIBM_PROGRAMS = {"libm", "wood", "control_flow", "glass", "scanlines"}
 
 
+class _StateMode:
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __enter__(self):
+        DeviceContext.get(0).set_vm_state_mode(self.mode)
+        return DeviceContext.get(0)
+
+    def __exit__(self, *exc):
+        import os
+        DeviceContext.get(0).set_vm_state_mode(int(os.environ.get("RXC_VM_STATE_MODE", "2")))
+
+
 def _vm_scene():
     progs = vm_programs.all_programs()
     s = Scene()
@@ -475,7 +488,8 @@ def test_shaded_scene_with_emissive_against_per_fragment_oracle():
     cfg = scenes.shaded_config(480, 360, 40, emissive=True)
     oracle_ffi.set_vm_state_mode(True)
     try:
-        _run(cfg, frame=1)
+        with _StateMode(0):      # the fast kernel (by default such a scene is rendered in the reference's order, see below)
+            _run(cfg, frame=1)
     finally:
         oracle_ffi.set_vm_state_mode(False)
 
@@ -540,7 +554,7 @@ def test_vm_jit_background_compile_switches_kernels_between_frames():
     next frame uses it -- and is the same frame."""
     import time
     cfg = scenes.shaded_config(320, 240, 40, emissive=True)    # a program set no other test compiles
-    with _JitMode(1) as ctx:
+    with _StateMode(0), _JitMode(1) as ctx:                     # (the fast kernel: in auto mode this scene goes to the reference-order kernel)
         first = render_gpu(cfg.rasterizer(1), cfg.scene, cfg.assets, 320, 240, 40, planes=False)
         t0 = time.time()
         while ctx.vm_jit_info()["pending"] and time.time() - t0 < 120:
@@ -587,18 +601,6 @@ def test_vm_state_report_names_the_scene_whose_frames_depend_on_the_tile_executi
 # ------------------------------------------------------------------------------------------------
 # rxc_set_vm_state_mode: the reference's order and per-tile Execution on the device (k_raster_ordered)
 # ------------------------------------------------------------------------------------------------
-class _StateMode:
-    def __init__(self, mode):
-        self.mode = mode
-
-    def __enter__(self):
-        DeviceContext.get(0).set_vm_state_mode(self.mode)
-        return DeviceContext.get(0)
-
-    def __exit__(self, *exc):
-        DeviceContext.get(0).set_vm_state_mode(0)
-
-
 @pytest.mark.parametrize("tile_size", [40, 16, 64])
 def test_reference_order_mode_reproduces_the_state_leak(tile_size):
     """The `emissive` variant of the batch-shader scene: one branch of a program writes `emissive`, the reference never resets its
@@ -612,7 +614,8 @@ def test_reference_order_mode_reproduces_the_state_leak(tile_size):
         assert ctx.ordered_frames() == n0 + 1
         ordered = render_gpu(cfg.rasterizer(1), cfg.scene, cfg.assets, 480, 360, tile_size)
     assert st["within1_frac"] > 0.999
-    fast = render_gpu(cfg.rasterizer(1), cfg.scene, cfg.assets, 480, 360, tile_size)
+    with _StateMode(0):
+        fast = render_gpu(cfg.rasterizer(1), cfg.scene, cfg.assets, 480, 360, tile_size)
     assert np.array_equal(fast[1], ordered[1]) and np.array_equal(fast[2].view(np.uint32), ordered[2].view(np.uint32))   # same owners, same depth
     leak = np.abs(fast[0].astype(np.int16) - ordered[0].astype(np.int16)).max(axis=-1) > 1
     assert leak.mean() > 0.01, leak.mean()                                                                                 # ... other colours
@@ -622,7 +625,8 @@ def test_reference_order_mode_equals_the_fast_mode_where_nothing_leaks():
     """The plain batch-shader scene (3D, chunk, opacity pane and 2D programs that assign what they read): both kernels render the
     reference's frame -- same owners and depth, colours within 1 LSB of each other and of the oracle."""
     cfg = scenes.shaded_config(480, 360, 40)
-    fast = render_gpu(cfg.rasterizer(2), cfg.scene, cfg.assets, 480, 360, 40)
+    with _StateMode(0):
+        fast = render_gpu(cfg.rasterizer(2), cfg.scene, cfg.assets, 480, 360, 40)
     with _StateMode(1):
         ordered = render_gpu(cfg.rasterizer(2), cfg.scene, cfg.assets, 480, 360, 40)
         st = _run(cfg, frame=2)
