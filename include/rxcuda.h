@@ -492,7 +492,7 @@ int32_t rxc_mgpu_status(rxc_ctx* ctx, uint32_t* mode, uint32_t* deliveries, uint
  * rxc_vm_translate (no context, no GPU): the generated source for a program table; jit_index[i] = i when program i was
  * accepted, 0xFFFFFFFF when it stays with the interpreter.  Returns the length of the source (written up to `cap` bytes).
  * rxc_vm_jit_compile (no context, no GPU): runs the NVRTC compilation of k_raster<sample_mode, planes, VM> (sample_mode -1: of the
- * rxc_vm_execute kernel) for a program
+ * rxc_vm_execute kernel, -2: of the reference-order kernel) for a program
  * table and returns the size of the cubin (0 = no program accepted, RXC_ERR_UNSUPPORTED = NVRTC missing or the compilation
  * failed; the compiler's messages in `log`).
  * rxc_vm_jit_info: programs translated for the current scene, kernels loaded so far, whether a requested kernel is still

@@ -757,9 +757,15 @@ int32_t launch_group(rxc_ctx* ctx, const DFrame* h_frames, DCounters* h_counters
         uint8_t* base = ctx->d_ordered.as<uint8_t>();
         const size_t plane = (size_t)n * px * 4;
         const uint32_t api_tiles = ((uint32_t)F0.width + ts - 1) / ts * (((uint32_t)F0.height + ts - 1) / ts);
+        void* ordered_kernel = nullptr;   // the kernel with the scene's programs compiled instead of interpreted, once it is there
+        if (ctx->jit && ctx->jit_translated) {
+            std::string note;
+            ordered_kernel = rxj_kernel(ctx->jit, -2, false, 2, std::string(), &note);
+            if (!note.empty()) ctx->jit_note = note;
+        }
         { LaunchScope l(ctx, RXK_RASTER);
           CK(rxk_raster_ordered(S, ctx->W, out, n, api_tiles, (float*)base, (float*)(base + plane), (uint32_t*)(base + 2 * plane), (uint32_t*)(base + 3 * plane),
-                                (uint32_t*)(base + 4 * plane), (uint32_t*)(base + 5 * plane), px, ctx->stream)); }
+                                (uint32_t*)(base + 4 * plane), (uint32_t*)(base + 5 * plane), px, ctx->stream, ordered_kernel)); }
         const int32_t sa = after_slice(0u, rows_total);
         if (sa != RXC_OK) return sa;
         if (h_counters) CK(cudaMemcpyAsync(h_counters, ctx->W.counters, n * sizeof(DCounters), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1645,7 +1651,7 @@ int64_t rxc_vm_translate(const rxc_program* programs, uint32_t n_programs, char*
 
 int64_t rxc_vm_jit_compile(const rxc_program* programs, uint32_t n_programs, int32_t sample_mode, int32_t planes, char* log, uint32_t log_cap) {
     try {
-        if ((n_programs && !programs) || sample_mode < -1 || sample_mode > 2) return RXC_ERR_INVALID;
+        if ((n_programs && !programs) || sample_mode < -2 || sample_mode > 2) return RXC_ERR_INVALID;
         std::string src, msg;
         std::vector<uint32_t> idx;
         if (!rxj_generate(programs, n_programs, &src, &idx)) return 0;

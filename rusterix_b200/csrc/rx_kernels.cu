@@ -1760,11 +1760,7 @@ __device__ __noinline__ uint32_t shade_2d_vm(const SceneDev& S, const DFrame& F,
     io.hitpoint.x = wx; io.hitpoint.y = wy;
     io.time = {F.time, F.time, F.time};
     io.roughness.x = 0.5f; io.metallic.x = 0.0f;
-#ifdef __CUDACC_RTC__   // (kernels recompiled for a scene never carry state: that is k_raster_ordered, which lives in the library only)
-    const bool ok = vm_run(S.vm, S.vm.programs[program], io);
-#else
     const bool ok = ps ? vm_run_t<true>(S.vm, S.vm.programs[program], io, ps) : vm_run(S.vm, S.vm.programs[program], io);
-#endif
     if (!ok) *fault = 1u;
     return pack_pixel(io.color.x, io.color.y, io.color.z, 1.0f);
 }
@@ -2879,9 +2875,7 @@ __global__ void __launch_bounds__(128) k_vm_execute(VmDev vm, uint32_t program, 
 }
 #endif
 
-#ifdef __CUDACC_RTC__
-}  // namespace
-#else
+#if !defined(__CUDACC_RTC__) || RXVM_JIT_ORDERED   // (a JIT build of k_raster leaves it out)
 // ---------------------------------------------------------------------------------------------
 // k_raster_ordered : the reference's order, for scenes whose batch-shader programs can observe it.
 //
@@ -2918,16 +2912,22 @@ struct ListMerge {
 };
 
 __global__ void __launch_bounds__(128) k_raster_ordered(SceneDev S, Workspace Wk, RasterOut out, uint32_t n_frames, OrderedScratch Q) {
+    // One API tile per WARP.  The tile's Execution lives in shared memory; everything that does not touch it is done by the 32 lanes
+    // side by side -- the coverage and depth tests of a record's row (a record visits a pixel once, so the depth tests of one row do not
+    // depend on each other), the exact derivation of the fragments' program inputs, and the lighting of what the programs returned --
+    // and what does (the assignments to the Execution and the program run, in pixel order) is done one fragment at a time by the lane
+    // that owns the pixel.  (A thread per tile, 32 tiles sharing a warp: 79 ms per 1080p frame of the batch-shader scene; a warp per
+    // tile with one working lane: 36 ms.)
+    __shared__ VmIO s_io[4];
+    __shared__ VmPersist s_ps[4];
     const uint32_t f = blockIdx.y;
     if (f >= n_frames) return;
-    // one tile per WARP, walked by its lane 0: the walk is one serial chain of data-dependent work (32 tiles sharing a warp would
-    // take turns at every divergent branch: 79 ms per 1080p frame of the batch-shader scene instead of the 5 ms a warp each takes)
-    if (threadIdx.x & 31u) return;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const DFrame& F = Wk.frames[f];
     const int W = F.width, H = F.height, ts = max(1, (int)F.tile_size);
     const int atx = (W + ts - 1) / ts, aty = (H + ts - 1) / ts;
-    const int at = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
-    if (at >= atx * aty) return;
+    const int at = (int)(blockIdx.x * (blockDim.x >> 5) + warp);
+    if (at >= atx * aty) return;   // (the whole warp)
     const int ax0 = (at % atx) * ts, ay0 = (at / atx) * ts, ax1 = min(ax0 + ts, W), ay1 = min(ay0 + ts, H);
     const DLight* lights = Wk.lights + (size_t)f * Wk.lights_stride;
     const TriVis* vis = Wk.vis + (size_t)f * Wk.slot_stride;
@@ -2940,21 +2940,21 @@ __global__ void __launch_bounds__(128) k_raster_ordered(SceneDev S, Workspace Wk
     uint32_t* px_out = reinterpret_cast<uint32_t*>(out.pixels + (size_t)f * out.frame_stride);
     const int pitch = (int)out.pitch;
     uint32_t fault = 0u;
+    const uint32_t FULL = 0xFFFFFFFFu;
 
-    VmIO io;             // `let mut execution = Execution::new(0)` of this tile (:310)
-    VmPersist ps;
-    vm_io_reset(io);
-    ps.n_globals = 0u; ps.n_locals = 0u;
-
-    for (int y = ay0; y < ay1; ++y)
-        for (int x = ax0; x < ax1; ++x) {
-            const size_t i = (size_t)y * W + x;
-            zb[i] = 1.0f; zop[i] = 1.0f; some[i] = 0u; sid[i] = 0u; cop[i] = 0u; own[i] = RX_OWNER_NONE;   // :287-290
-        }
+    VmIO& io = s_io[warp];             // `let mut execution = Execution::new(0)` of this tile (:310)
+    VmPersist& ps = s_ps[warp];
+    if (lane == 0u) { vm_io_reset(io); ps.n_globals = 0u; ps.n_locals = 0u; }
+    const int tw = ax1 - ax0, th = ay1 - ay0;
+    for (int p = (int)lane; p < tw * th; p += 32) {
+        const size_t i = (size_t)(ay0 + p / tw) * W + (ax0 + p % tw);
+        zb[i] = 1.0f; zop[i] = 1.0f; some[i] = 0u; sid[i] = 0u; cop[i] = 0u; own[i] = RX_OWNER_NONE;   // :287-290
+    }
+    __syncwarp();
 
     // the device tiles under this API tile
     const int dx0 = ax0 / RX_TILE_W, dx1 = (ax1 - 1) / RX_TILE_W, dy0 = ay0 / RX_TILE_H, dy1 = (ay1 - 1) / RX_TILE_H;
-    ListMerge M;
+    ListMerge M;   // (every lane walks the same lists: uniform)
     if (F.d3_active) {
         M.k = 0;
         for (int dy = dy0; dy <= dy1; ++dy)
@@ -2974,69 +2974,91 @@ __global__ void __launch_bounds__(128) k_raster_ordered(SceneDev S, Workspace Wk
             const TriShade& sh = shade[slot];
             const float ea[3] = {q3.x, q3.y, q3.z}, eb[3] = {q3.w, q4.x, q4.y}, ec[3] = {q4.z, q4.w, q5.x};
             const bool opacity = (meta & RX_META_OPACITY) != 0u, has_profile = (FB.sd_flags & RX_SD_HAS_PROFILE) != 0u;
-            const bool program = (FB.sd_flags & RX_SD_SHADER) && FB.sd_program >= 0 && (uint32_t)FB.sd_program < S.vm.n_programs;
+            const bool program = (FB.sd_flags & RX_SD_SHADER) && FB.sd_program >= 0 && (uint32_t)FB.sd_program < S.vm.n_programs &&
+                                 S.vm.programs[FB.sd_program].n_words != 0u;
             for (int y = y0; y < y1; ++y)            // rasterizer.rs:1018-1020: rows, then columns
-                for (int x = x0; x < x1; ++x) {
+                for (int xs = x0; xs < x1; xs += 32) {
+                    const int x = xs + (int)lane;
                     const float fpx = (float)x + 0.5f, fpy = (float)y + 0.5f;   // :1022
-                    if ((ea[0] * fpx + eb[0] * fpy) + ec[0] < 0.0f || (ea[1] * fpx + eb[1] * fpy) + ec[1] < 0.0f || (ea[2] * fpx + eb[2] * fpy) + ec[2] < 0.0f) continue;   // edge.rs:28-36
-                    float al, be;
-                    const float z = fragment_depth(q0, q1, q2, meta, fpx, fpy, &al, &be);
-                    const size_t i = (size_t)y * W + x;
-                    if (opacity) {   // d3_rasterize_opacity, :1425-1690
-                        if (!(z < zop[i])) continue;
-                        const Frag3D g = vm_inputs_3d(S, F, FB, sh, al, be, z, fpx, fpy, smode, true);
-                        io.color = texel_linear_exact(g.texel);
-                        io.opacity.x = (float)(g.texel >> 24) / 255.0f;
-                        if (program && S.vm.programs[FB.sd_program].n_words != 0u) {   // :1643-1668
-                            io.normal = {0.0f, 0.0f, 0.0f};
-                            io.uv.x = g.u / 4.0f; io.uv.y = g.v / 4.0f;
-                            io.hitpoint = g.world;
-                            io.time = {F.time, F.time, F.time};
-                            io.roughness.x = 0.5f; io.metallic.x = 0.0f;
-                            if (!vm_run_t<true>(S.vm, S.vm.programs[FB.sd_program], io, &ps)) fault = 1u;
+                    const size_t i = (size_t)y * W + min(x, x1 - 1);
+                    bool pass = x < x1 && !((ea[0] * fpx + eb[0] * fpy) + ec[0] < 0.0f || (ea[1] * fpx + eb[1] * fpy) + ec[1] < 0.0f ||
+                                            (ea[2] * fpx + eb[2] * fpy) + ec[2] < 0.0f);   // edge.rs:28-36
+                    float al = 0.0f, be = 0.0f, z = 1.0f;
+                    if (pass) {
+                        z = fragment_depth(q0, q1, q2, meta, fpx, fpy, &al, &be);
+                        if (opacity) pass = z < zop[i];                                                   // d3_rasterize_opacity, :1425-1690
+                        else pass = !(has_profile && some[i] && sid[i] == FB.sd_profile) && z < zb[i];     // :1041-1047, :1051-1060
+                    }
+                    Frag3D g = {};
+                    if (pass) g = vm_inputs_3d(S, F, FB, sh, al, be, z, fpx, fpy, smode, opacity);
+                    const uint32_t mask = __ballot_sync(FULL, pass);
+                    if (!mask) continue;
+                    VmIO snap;   // the Execution as the rasterizer reads it back for THIS fragment
+                    if (program) {
+                        // in pixel order, one fragment at a time: the assignments of :1259-1298 (:1633-1661 in the opacity pass) and the program
+                        for (uint32_t m = mask; m; m &= m - 1u) {
+                            if (lane == (uint32_t)(__ffs(m) - 1)) {
+                                io.color = texel_linear_exact(g.texel);
+                                io.opacity.x = (float)(g.texel >> 24) / 255.0f;
+                                io.normal = opacity ? f3{0.0f, 0.0f, 0.0f} : g.normal;
+                                io.roughness.x = 0.5f; io.metallic.x = 0.0f;
+                                io.uv.x = g.u / 4.0f; io.uv.y = g.v / 4.0f;
+                                io.hitpoint = g.world;
+                                io.time = {F.time, F.time, F.time};
+                                if (!vm_run_t<true>(S.vm, S.vm.programs[FB.sd_program], io, &ps)) fault = 1u;
+                                snap = io;
+                            }
+                            __syncwarp();
                         }
-                        cop[i] = pack_pixel(linear_to_srgb_exact(io.color.x), linear_to_srgb_exact(io.color.y), linear_to_srgb_exact(io.color.z), io.opacity.x);
-                        zop[i] = z; sid[i] = FB.sd_profile; some[i] = has_profile ? 1u : 0u;
-                        continue;
+                    } else {
+                        // no program: a fragment assigns color, opacity.x (and, opaque pass, normal, roughness.x, metallic.x; :1310-1316) and reads
+                        // nothing another fragment of this row wrote -- the row's last fragment is what stays in the Execution
+                        snap = io;
+                        snap.color = texel_linear_exact(g.texel);
+                        snap.opacity.x = (float)(g.texel >> 24) / 255.0f;
+                        if (!opacity) { snap.normal = g.normal; snap.roughness.x = 0.5f; snap.metallic.x = 0.0f; }
+                        __syncwarp();
+                        if (lane == (uint32_t)(31 - __clz(mask))) {
+                            io.color = snap.color; io.opacity.x = snap.opacity.x;
+                            if (!opacity) { io.normal = snap.normal; io.roughness.x = 0.5f; io.metallic.x = 0.0f; }
+                        }
+                        __syncwarp();
                     }
-                    if (has_profile && some[i] && sid[i] == FB.sd_profile) continue;   // :1041-1047
-                    if (!(z < zb[i])) continue;                                        // :1051-1060
-                    const Frag3D g = vm_inputs_3d(S, F, FB, sh, al, be, z, fpx, fpy, smode, false);
-                    io.color = texel_linear_exact(g.texel);                            // :1259-1281 / :1310-1316: every branch assigns these
-                    io.opacity.x = (float)(g.texel >> 24) / 255.0f;
-                    io.normal = g.normal;
-                    io.roughness.x = 0.5f; io.metallic.x = 0.0f;
-                    if (program && S.vm.programs[FB.sd_program].n_words != 0u) {       // :1284-1301
-                        io.uv.x = g.u / 4.0f; io.uv.y = g.v / 4.0f;
-                        io.hitpoint = g.world;
-                        io.time = {F.time, F.time, F.time};
-                        if (!vm_run_t<true>(S.vm, S.vm.programs[FB.sd_program], io, &ps)) fault = 1u;
+                    if (pass) {
+                        if (opacity) {   // :1670-1685: the layer's pixel, its depth, the surface id
+                            cop[i] = pack_pixel(linear_to_srgb_exact(snap.color.x), linear_to_srgb_exact(snap.color.y), linear_to_srgb_exact(snap.color.z), snap.opacity.x);
+                            zop[i] = z; sid[i] = FB.sd_profile; some[i] = has_profile ? 1u : 0u;
+                        } else {
+                            const uint32_t color = vm_light_3d(S, F, lights, FB, snap, g.world);   // :1319-1404, emissive of the carried Execution included
+                            if ((color >> 24) == 255u) { px_out[(size_t)y * pitch + x] = color; zb[i] = z; own[i] = slot; }   // :1408-1412
+                        }
                     }
-                    const uint32_t color = vm_light_3d(S, F, lights, FB, io, g.world);  // :1319-1404, emissive of the carried Execution included
-                    if ((color >> 24) == 255u) { px_out[(size_t)y * pitch + x] = color; zb[i] = z; own[i] = slot; }   // :1408-1412
+                    __syncwarp();   // the next record's lanes read what these lanes wrote
                 }
         }
     }
 
     // miss pass (:409-461), opacity blend (:464-495), or the 2D-only background (:277-307)
-    for (int y = ay0; y < ay1; ++y)
-        for (int x = ax0; x < ax1; ++x) {
-            const size_t i = (size_t)y * W + x;
-            uint32_t color;
-            if (F.d3_active) {
-                if (own[i] != RX_OWNER_NONE) color = px_out[(size_t)y * pitch + x];
-                else { color = 0xFF000000u; if (F.has_sky | F.has_brush) color = miss_color(&F, x, y); }
-                if (zop[i] < 1.0f && zb[i] > zop[i]) color = blend_opacity(cop[i], color, F.preserve_transparency != 0u);
-            } else {
-                color = F.has_bg_color ? F.bg_color : 0u;
-                if (!F.ignore_bg_shader && F.bg_shader != RXC_BG_NONE) color = shade_background(F, x, y);
-            }
-            px_out[(size_t)y * pitch + x] = color;
-            if (out.owner) out.owner[i] = own[i];
-            if (out.depth) out.depth[i] = zb[i];
+    __syncwarp();
+    for (int p = (int)lane; p < tw * th; p += 32) {
+        const int x = ax0 + p % tw, y = ay0 + p / tw;
+        const size_t i = (size_t)y * W + x;
+        uint32_t color;
+        if (F.d3_active) {
+            if (own[i] != RX_OWNER_NONE) color = px_out[(size_t)y * pitch + x];
+            else { color = 0xFF000000u; if (F.has_sky | F.has_brush) color = miss_color(&F, x, y); }
+            if (zop[i] < 1.0f && zb[i] > zop[i]) color = blend_opacity(cop[i], color, F.preserve_transparency != 0u);
+        } else {
+            color = F.has_bg_color ? F.bg_color : 0u;
+            if (!F.ignore_bg_shader && F.bg_shader != RXC_BG_NONE) color = shade_background(F, x, y);
         }
+        px_out[(size_t)y * pitch + x] = color;
+        if (out.owner) out.owner[i] = own[i];
+        if (out.depth) out.depth[i] = zb[i];
+    }
+    __syncwarp();
 
-    // 2D batches in submission order (:501-553, :584-959) with the same Execution
+    // 2D batches in submission order (:501-553, :584-959) with the same Execution: records without a program do not touch it (:760)
     if (F.d2_active && S.n_rec2d != 0u) {
         const Tri2D* recs = Wk.tri2d + (size_t)f * Wk.tri2d_stride;
         const DFrameBatch2* fb2 = Wk.fb2 + (size_t)f * Wk.fb2_stride;
@@ -3051,16 +3073,31 @@ __global__ void __launch_bounds__(128) k_raster_ordered(SceneDev S, Workspace Wk
         while (M.next(&r)) {
             const Tri2D& T = recs[r];
             const int x0 = max(ax0, (int)(T.bbx & 0xFFFFu)), x1 = min(ax1, (int)(T.bbx >> 16)), y0 = max(ay0, (int)(T.bby & 0xFFFFu)), y1 = min(ay1, (int)(T.bby >> 16));
+            const bool program = T.kind == 0u && fb2[T.batch].program >= 0;
             for (int y = y0; y < y1; ++y)
-                for (int x = x0; x < x1; ++x) {
-                    uint32_t* c = px_out + (size_t)y * pitch + x;
-                    *c = apply_2d<true>(S, F, lights, fb2, T, x, y, smode, *c, &fault, &io, &ps);
+                for (int xs = x0; xs < x1; xs += 32) {
+                    const int x = xs + (int)lane;
+                    uint32_t* c = px_out + (size_t)y * pitch + min(x, x1 - 1);
+                    if (!program) {
+                        if (x < x1) *c = apply_2d<true>(S, F, lights, fb2, T, x, y, smode, *c, &fault);
+                    } else {
+                        for (uint32_t m = __ballot_sync(FULL, x < x1); m; m &= m - 1u) {   // pixel order through the Execution
+                            if (lane == (uint32_t)(__ffs(m) - 1)) *c = apply_2d<true>(S, F, lights, fb2, T, x, y, smode, *c, &fault, &io, &ps);
+                            __syncwarp();
+                        }
+                    }
+                    __syncwarp();
                 }
         }
     }
-    if (fault) atomicOr(&Wk.counters[f].overflow, 16u);
+    if (__any_sync(FULL, fault != 0u) && lane == 0u) atomicOr(&Wk.counters[f].overflow, 16u);
 }
 
+#endif
+
+#ifdef __CUDACC_RTC__
+}  // namespace
+#else
 // ---------------------------------------------------------------------------------------------
 // k_list_sort (general mode): one CTA per tile sorts its list ascending (= submission order).  The
 // allocation of a list is a power of two (k_tile_alloc), the tail is padded with 0xFFFFFFFF.
@@ -3231,9 +3268,14 @@ cudaError_t rxk_bin_fill(const SceneDev& S, const Workspace& W, uint32_t n_frame
     return cudaGetLastError();
 }
 cudaError_t rxk_raster_ordered(const SceneDev& S, const Workspace& W, const RasterOut& out, uint32_t n_frames, uint32_t api_tiles, float* z, float* zop,
-                               uint32_t* cop, uint32_t* sid, uint32_t* some, uint32_t* own, size_t stride, cudaStream_t st) {
+                               uint32_t* cop, uint32_t* sid, uint32_t* some, uint32_t* own, size_t stride, cudaStream_t st, void* jit_kernel) {
     OrderedScratch q = {z, zop, cop, sid, some, own, stride};
     dim3 grid((api_tiles + 3u) / 4u, n_frames);
+    if (jit_kernel) {   // the same kernel with the scene's programs compiled (rx_jit.cu)
+        SceneDev s = S; Workspace w = W; RasterOut o = out;
+        void* args[] = {&s, &w, &o, &n_frames, &q};
+        return cudaLaunchKernel((const void*)jit_kernel, grid, dim3(128), args, 0, st);
+    }
     k_raster_ordered<<<grid, 128, 0, st>>>(S, W, out, n_frames, q);
     return cudaGetLastError();
 }

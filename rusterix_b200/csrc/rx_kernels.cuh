@@ -147,7 +147,7 @@ cudaError_t rxk_raster(const SceneDev& S, const Workspace& W, const RasterOut& o
 // the reference-order kernel (k_raster_ordered: one thread per API tile, the tile's Execution carried from fragment to fragment):
 // general-mode scenes, whole frames only; the six scratch planes hold `stride` (= width * height) entries per frame
 cudaError_t rxk_raster_ordered(const SceneDev& S, const Workspace& W, const RasterOut& out, uint32_t n_frames, uint32_t api_tiles, float* z, float* zop,
-                               uint32_t* cop, uint32_t* sid, uint32_t* some, uint32_t* own, size_t stride, cudaStream_t st);
+                               uint32_t* cop, uint32_t* sid, uint32_t* some, uint32_t* own, size_t stride, cudaStream_t st, void* jit_kernel = nullptr);
 int rxk_raster_mode(const SceneDev& S, const Workspace& W);   // the MODE template argument rxk_raster picks (0 fast, 1 general, 2 general + VM, 3 fast + small-triangle pass)
 int rxk_raster_blocks_per_sm();
 // diagnostics: program `program` of S.vm on n records (18 floats in, 24 floats out each)

@@ -193,6 +193,10 @@ __device__ __forceinline__ f3 vm_sample_op(const VmDev& vm, bool normal_bank, f3
 #if defined(RXVM_JIT) && RXVM_JIT_COMPLETE
 // every program of the scene is generated code: no interpreter in this kernel
 __device__ __forceinline__ bool vm_run(const VmDev& vm, const DProgram& P, VmIO& io) { return vm_run_jit(vm, P.jit_index, io) == 1; }
+template <bool PERSIST>
+__device__ __forceinline__ bool vm_run_t(const VmDev& vm, const DProgram& P, VmIO& io, VmPersist* ps) {
+    return (PERSIST ? vm_run_jit_ps(vm, P.jit_index, io, *ps) : vm_run_jit(vm, P.jit_index, io)) == 1;
+}
 #else
 // Runs the shade function of program P on `io`.  Returns false when a device limit was hit (stack,
 // frames, op budget) or the code is malformed; the reference would have panicked or looped.
@@ -203,11 +207,11 @@ __device__ __noinline__ bool vm_run_t(const VmDev& vm, const DProgram& P, VmIO& 
     // `t`; stack[0] is a dummy that absorbs the spill of an empty stack's top.  A unary op then touches no memory,
     // a binary op loads one operand, a push stores one (half the local-memory traffic of a stack held in memory).
 #ifdef RXVM_JIT
-    if (!PERSIST && P.jit_index != 0xFFFFFFFFu) {   // the program as straight-line code; 2 = its stack took a shape the translator did not verify
+    if (P.jit_index != 0xFFFFFFFFu) {   // the program as straight-line code; 2 = its stack took a shape the translator did not verify
         const bool may_bail = vm_jit_may_bail(P.jit_index);
         VmIO saved;
         if (may_bail) saved = io;
-        const int st = vm_run_jit(vm, P.jit_index, io);
+        const int st = PERSIST ? vm_run_jit_ps(vm, P.jit_index, io, *ps) : vm_run_jit(vm, P.jit_index, io);   // (ps is only written when the program ends)
         if (st != 2) return st == 1;
         if (may_bail) io = saved;          // ... so the interpreter runs it from the start
     }

@@ -621,6 +621,19 @@ def test_reference_order_mode_reproduces_the_state_leak(tile_size):
     assert leak.mean() > 0.01, leak.mean()                                                                                 # ... other colours
 
 
+def test_reference_order_mode_with_compiled_programs_equals_the_interpreted_one():
+    """k_raster_ordered recompiled with the scene's programs as straight-line code (carried globals / locals included): the same
+    frame as with the interpreter, bit for bit, and it is the kernel that ran."""
+    cfg = scenes.shaded_config(320, 240, 40, emissive=True)
+    with _StateMode(1), _JitMode(0):
+        a = render_gpu(cfg.rasterizer(3), cfg.scene, cfg.assets, 320, 240, 40)
+    with _StateMode(1), _JitMode(2) as ctx:
+        before = ctx.vm_jit_info()["launches"]
+        b = render_gpu(cfg.rasterizer(3), cfg.scene, cfg.assets, 320, 240, 40)
+        assert ctx.vm_jit_info()["launches"] == before + 1, ctx.vm_jit_info()
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2].view(np.uint32), b[2].view(np.uint32))
+
+
 def test_reference_order_mode_equals_the_fast_mode_where_nothing_leaks():
     """The plain batch-shader scene (3D, chunk, opacity pane and 2D programs that assign what they read): both kernels render the
     reference's frame -- same owners and depth, colours within 1 LSB of each other and of the oracle."""

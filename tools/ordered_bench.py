@@ -4,9 +4,9 @@ import torch
 import bench
 from rusterix_b200 import DeviceContext, Rasterizer
 ctx = DeviceContext.get(0)
-for mode in (0, 1):
+for mode, jit in ((0, 2), (1, 0), (1, 2)):
     ctx.set_vm_state_mode(mode)
-    ctx.set_vm_jit(2)
+    ctx.set_vm_jit(jit)
     cfg, frame_ids, desc = bench.build_workload("shaded1080", 8, 0, 1)
     rasts = [cfg.rasterizer(i) for i in frame_ids]
     out = torch.empty((8, cfg.height, cfg.width, 4), dtype=torch.uint8, device="cuda:0")
@@ -18,4 +18,4 @@ for mode in (0, 1):
     for _ in range(n):
         batch.run(out, sync=True)
     torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / n
-    print(f"state mode {mode}: {dt * 1e3:8.3f} ms per 8-frame 1080p step ({8 * cfg.width * cfg.height / dt / 1e6:9.0f} Mpixel/s), ordered frames so far {ctx.ordered_frames()}")
+    print(f"state mode {mode} jit {jit}: {dt * 1e3:8.3f} ms per 8-frame 1080p step ({8 * cfg.width * cfg.height / dt / 1e6:9.0f} Mpixel/s), ordered frames so far {ctx.ordered_frames()}")
