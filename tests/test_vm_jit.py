@@ -101,6 +101,9 @@ def test_nvrtc_compiles_the_generated_kernel(tmp_path, monkeypatch):
     assert lib.rxc_vm_jit_compile(arr, len(flat), -1, 0, log, len(log)) == n
     # an empty table has nothing to compile
     assert lib.rxc_vm_jit_compile(None, 0, -1, 0, log, len(log)) == 0
+    # the reference-order kernel with the programs compiled (carried globals / locals: vmj_pN_ps)
+    n2 = lib.rxc_vm_jit_compile(arr, len(flat), -2, 0, log, len(log))
+    assert n2 > 0, log.value.decode()
 
 
 # ---- which programs can observe the reference's per-tile Execution (rxc_vm_state_report) ----
