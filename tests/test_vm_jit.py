@@ -66,6 +66,16 @@ def test_programs_that_can_fault_stay_with_the_interpreter():
     assert "vmj_p0(" not in src and "vmj_p3(" in src
 
 
+def test_bare_return_is_only_translated_where_the_stack_below_is_empty():
+    """A callee's `Return` with none of its own values on the stack pops a value of its CALLER (the value stack is shared,
+    execution.rs:224-234): translated when every call site leaves nothing below it, left to the interpreter otherwise."""
+    bare = [("Return",)]
+    on_empty = rvm.Program([[("FunctionCall", 0, 0, 1), ("SetColor",)], bare], 0, 0, 0)
+    on_value = rvm.Program([[("UV",), ("FunctionCall", 0, 0, 1), ("Add",), ("SetColor",)], bare], 0, 0, 0)
+    _src, idx = _translate([on_empty, on_value])
+    assert idx == [0, NO_JIT]
+
+
 def test_palette_lookup_can_hand_over_to_the_interpreter():
     """PaletteIndex pushes nothing for a missing colour (execution.rs:735-742): the generated code returns 2 there."""
     progs = vm_programs.all_programs()
