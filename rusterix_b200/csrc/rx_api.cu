@@ -725,7 +725,7 @@ int32_t launch_group(rxc_ctx* ctx, const DFrame* h_frames, DCounters* h_counters
     bool ordered = false;
     if (ctx->vm_state_mode && S.general && S.vm.n_programs) {
         ordered = ctx->vm_state_mode == 1;
-        for (uint32_t r : ctx->vm_state_report) ordered = ordered || r == 1u;
+        for (uint32_t r : ctx->vm_state_report) ordered = ordered || r != 0u;   // can observe it, or could not be analysed
     }
     if (ordered) {
         // whole frames of one size, API tiles over at most 64 of the 32x32 device tiles whose lists the kernel merges; what it cannot
