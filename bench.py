@@ -312,7 +312,12 @@ def main():
         barrier()
         wall = time.perf_counter() - wall0
         ms = sum(a.elapsed_time(b) for a, b in zip(e0, e1))
+        timed.per_rank_ms = [ms / steps]
         if world > 1:
+            every = torch.zeros(world, dtype=torch.float64, device=dev)
+            every[rank] = ms / steps
+            dist.all_reduce(every, op=dist.ReduceOp.SUM)
+            timed.per_rank_ms = [round(float(x), 4) for x in every.tolist()]   # diagnostics: the value is computed from the slowest
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
@@ -327,6 +332,7 @@ def main():
         sampler.start()
     # warm-up is inside timed(); stats are reset after it by measuring launches per step separately
     ms_total, _ = timed(step_device, args.steps, args.warmup)
+    per_rank_ms = list(timed.per_rank_ms)
     clocks = sampler.stop() if rank == 0 else None
     st = ctx.stats()
     launches_per_step = st.kernel_launches // (args.steps + args.warmup)
@@ -436,7 +442,7 @@ def main():
                     "host_numa_binding": ("rank pinned to the %d cores next to its GPU" % len(numa_cpus)) if numa_cpus else "none"},
             "gpu_launches": int(gpu_launches), "launches_per_step": int(launches_per_step),
             "roofline": roofline, "clocks": clocks,
-            "kernels": kernels_note(ctx),
+            "kernels": kernels_note(ctx), "ms_per_step_per_rank": per_rank_ms,
         }
         if delivered:
             line["value_with_gather"] = delivered["value"]
