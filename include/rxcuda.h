@@ -513,7 +513,7 @@ int32_t rxc_set_vm_jit(rxc_ctx* ctx, int32_t mode);
  * scene with programs: forward shading in submission order, one GPU warp per tile (k_raster_ordered) -- the reference's frame for
  * state-dependent programs too, at a fraction of the speed; 2 (the default; environment RXC_VM_STATE_MODE) = that kernel only for
  * the scenes whose report (below) flags a program (1 or 2), the fast one otherwise: every frame equals the reference's and only the scenes
- * that need it pay for it.  The kernel renders whole frames (no band, no row pitch) with API tiles up to 224 x 224 pixels: what it
+ * that need it pay for it.  The kernel renders whole frames (no band) with API tiles up to 224 x 224 pixels: what it
  * cannot render is RXC_ERR_UNSUPPORTED in mode 1 and goes to the fast kernel in mode 2.
  * rxc_get_vm_state_mode: the mode and how many frames the reference-order kernel has rendered. */
 int32_t rxc_set_vm_state_mode(rxc_ctx* ctx, int32_t mode);

@@ -734,8 +734,8 @@ int32_t launch_group(rxc_ctx* ctx, const DFrame* h_frames, DCounters* h_counters
         const char* why = nullptr;
         for (uint32_t i = 0; i < n && !why; ++i) {
             const DFrame& F = h_frames[i];
-            if (F.band_x0 != 0 || F.band_y0 != 0 || F.band_x1 != F.width || F.band_y1 != F.height || pitch_px)
-                why = "reference-order mode (rxc_set_vm_state_mode) renders whole frames only (no band, no row pitch)";
+            if (F.band_x0 != 0 || F.band_y0 != 0 || F.band_x1 != F.width || F.band_y1 != F.height)
+                why = "reference-order mode (rxc_set_vm_state_mode) renders whole frames only (an API tile cut by a band would lose the state of its other part)";
             else if (F.tile_size != F0.tile_size || F.width != F0.width || F.height != F0.height)
                 why = "reference-order mode: the frames of a batch must share width, height and tile_size";
         }
