@@ -1,4 +1,5 @@
-// rx_jit.h -- interface of the batch-shader JIT (rx_jit.cu) towards rx_api.cu.  Not part of the C ABI.
+// rx_jit.h -- interface of the run-time kernel compilation (rx_jit.cu: batch shaders as straight-line code, raster kernels recompiled
+// with a scene's constants, the analysis of which programs can observe a carried Execution) towards rx_api.cu.  Not part of the C ABI.
 #pragma once
 #include <stdint.h>
 
