@@ -21,6 +21,10 @@
 //   k_vm_execute, k_selftest_div   diagnostics
 //
 // Reference cites are to /root/reference (markusmoenig/Rusterix).
+#ifndef __CUDACC_RTC__
+#include <set>
+#endif
+
 #include "rx_kernels.cuh"
 #include "rx_vm.cuh"
 
@@ -3279,6 +3283,13 @@ cudaError_t rxk_raster_ordered(const SceneDev& S, const Workspace& W, const Rast
     k_raster_ordered<<<grid, 128, 0, st>>>(S, W, out, n_frames, q);
     return cudaGetLastError();
 }
+// experiments: RXC_SMEM_CARVEOUT = preferred shared-memory carve-out of the raster kernels in percent (what is left is L1)
+static void raster_carveout(const void* kernel) {
+    static const int carve = getenv("RXC_SMEM_CARVEOUT") ? atoi(getenv("RXC_SMEM_CARVEOUT")) : -1;
+    if (carve < 0) return;
+    static std::set<const void*> done;
+    if (done.insert(kernel).second) { cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve); cudaGetLastError(); }
+}
 int rxk_raster_mode(const SceneDev& S, const Workspace& W) {
     return (S.general && S.vm.n_programs) ? 2 : S.general ? 1 : S.n_tris >= W.small_min_tris ? 3 : 0;
 }
@@ -3286,12 +3297,13 @@ cudaError_t rxk_raster(const SceneDev& S, const Workspace& W, const RasterOut& o
                        uint32_t counter, int sample_mode, int grid_x, cudaStream_t st, void* jit_kernel) {
     const bool planes = out.owner || out.depth;
     if (jit_kernel) {
+        raster_carveout(jit_kernel);
         // the same kernel recompiled for this scene (rx_jit.cu: its programs as straight-line code, its constants folded): same arguments
         SceneDev s = S; Workspace w = W; RasterOut o = out;
         void* args[] = {&s, &w, &o, &n_frames, &tile0, &n_tiles, &counter};
         return cudaLaunchKernel((const void*)jit_kernel, dim3(grid_x), dim3(RX_TILE_THREADS), args, 0, st);
     }
-#define RX_LAUNCH(SM, PL, MD) k_raster<SM, PL, MD><<<grid_x, RX_TILE_THREADS, 0, st>>>(S, W, out, n_frames, tile0, n_tiles, counter)
+#define RX_LAUNCH(SM, PL, MD) do { raster_carveout((const void*)k_raster<SM, PL, MD>); k_raster<SM, PL, MD><<<grid_x, RX_TILE_THREADS, 0, st>>>(S, W, out, n_frames, tile0, n_tiles, counter); } while (0)
 #define RX_LAUNCH2(SM, PL) do { if (S.general && S.vm.n_programs) RX_LAUNCH(SM, PL, 2); else if (S.general) RX_LAUNCH(SM, PL, 1); else if (S.n_tris >= W.small_min_tris) RX_LAUNCH(SM, PL, 3); else RX_LAUNCH(SM, PL, 0); } while (0)
     if (sample_mode == 0) { if (planes) RX_LAUNCH2(0, true); else RX_LAUNCH2(0, false); }
     else if (sample_mode == 1) { if (planes) RX_LAUNCH2(1, true); else RX_LAUNCH2(1, false); }
