@@ -1177,6 +1177,14 @@ __device__ __forceinline__ uint32_t fast_u8(float x) {
     asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(x * 255.0f));
     return r;
 }
+// linear_to_srgb_fast (rasterizer.rs:28-33: 1.055 s - 0.055 s^2 with s = sqrt(x)) and f32_to_u8_saturated in one: the 255 is folded into
+// the polynomial, s * (269.025 - 14.025 s), then the saturating round-to-nearest conversion -- sqrt, FMA, multiply, convert
+__device__ __forceinline__ uint32_t fast_srgb_u8(float x) {
+    const float s = fast_sqrt(x);
+    uint32_t r;
+    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(s * __fmaf_rn(-14.025f, s, 269.025f)));
+    return r;
+}
 // Texture::sample_nearest (texture.rs:307-323) for shading: floor(u*(W-1) + 0.5) instead of round() and
 // a saturating clamp; the exact version (rx_sample_tex) stays on the alpha-test path, which decides ownership.
 __device__ __forceinline__ float fast_wrap(float u, bool repeat) { return repeat ? (u - floorf(u)) : __saturatef(u); }
@@ -1478,9 +1486,8 @@ __device__ __forceinline__ uint32_t shade_owner(const SceneDev& S, const ShadeCo
         lit = {__fmaf_rn((kd.x + spec) * n_dot_l, radiance.x, lit.x), __fmaf_rn((kd.y + spec) * n_dot_l, radiance.y, lit.y),
                __fmaf_rn((kd.z + spec) * n_dot_l, radiance.z, lit.z)};
     }
-    auto l2s = [](float x) { const float s = fast_sqrt(x); return __fmaf_rn(-0.055f * s, s, 1.055f * s); };  // rasterizer.rs:28-33
     const uint32_t a8 = texel >> 24;  // f32_to_u8_saturated(a / 255) == a for every u8 a
-    return fast_u8(l2s(lit.x)) | (fast_u8(l2s(lit.y)) << 8) | (fast_u8(l2s(lit.z)) << 16) | (a8 << 24);
+    return fast_srgb_u8(lit.x) | (fast_srgb_u8(lit.y) << 8) | (fast_srgb_u8(lit.z) << 16) | (a8 << 24);
 }
 
 // shade_owner for TWO horizontally adjacent pixels (fpx, fpx + 1; same y) owned by the SAME triangle, in packed fp32
@@ -1740,8 +1747,7 @@ __device__ __forceinline__ uint32_t vm_light_3d(const SceneDev& S, const DFrame&
         brdf(ldir, n_dot_l, radiance, lit);
     }
     lit = rx_add3(lit, io.emissive);
-    auto l2s = [](float x) { const float s = fast_sqrt(x); return __fmaf_rn(-0.055f * s, s, 1.055f * s); };  // rasterizer.rs:28-33
-    return fast_u8(l2s(lit.x)) | (fast_u8(l2s(lit.y)) << 8) | (fast_u8(l2s(lit.z)) << 16) | (rx_f32_to_u8_saturated(io.opacity.x) << 24);
+    return fast_srgb_u8(lit.x) | (fast_srgb_u8(lit.y) << 8) | (fast_srgb_u8(lit.z) << 16) | (rx_f32_to_u8_saturated(io.opacity.x) << 24);
 }
 __device__ __noinline__ uint32_t shade_owner_vm(const SceneDev& S, const DFrame& F, const DLight* lights, const DFrameBatch& FB, const TriShade& sh,
                                                 float alpha, float beta, float z, float fpx, float fpy, uint32_t sample_mode, uint32_t* fault) {
