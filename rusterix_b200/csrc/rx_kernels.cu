@@ -34,6 +34,16 @@ namespace cg = cooperative_groups;
 
 namespace {
 
+// Programmatic dependent launch (sm_90+): every kernel of the frame's chain lets its successor become resident at once
+// (`launch_dependents`: the next grid's CTAs are placed as soon as every CTA of this one has started) and touches global memory
+// only after `wait` (all prerequisite grids complete, their writes visible) -- the drain / launch / ramp between two dependent
+// short kernels shrinks to the release of CTAs that are already there.  Both are no-ops for a launch without the
+// programmatic-serialization attribute (rxk_* below set it unless RXC_PDL=0).
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
@@ -625,6 +635,7 @@ __device__ __forceinline__ void d_tri_setup(const SceneDev& S, const Workspace& 
 // visibility verbatim; one thread per batch turns bounding_box into the scissor of rasterizer.rs:978-983.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_tri_setup_projected(SceneDev S, Workspace Wk, ProjectedDev Pj) {
+    pdl_enter();
     const DFrame& F = Wk.frames[0];
     DCounters& C = Wk.counters[0];
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -989,20 +1000,21 @@ __device__ __forceinline__ void d_list_sort_warp(const Workspace& Wk, int which,
 // the front-end as kernels ...
 // ---------------------------------------------------------------------------------------------
 #ifndef __CUDACC_RTC__
-__global__ void __launch_bounds__(256) k_frame_setup(SceneDev S, Workspace Wk, uint32_t tiles_per_frame) { d_frame_setup(S, Wk, tiles_per_frame, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
-__global__ void __launch_bounds__(RX_CHUNK_TRIS) k_tri_setup(SceneDev S, Workspace Wk) { d_tri_setup(S, Wk, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
-__global__ void __launch_bounds__(256) k_batch_finalize(SceneDev S, Workspace Wk) { d_batch_finalize(S, Wk, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
-__global__ void __launch_bounds__(128) k_clip_emit(SceneDev S, Workspace Wk) { d_clip_emit(S, Wk, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
-__global__ void __launch_bounds__(256) k_bin_count(SceneDev S, Workspace Wk) { d_bin_count(S, Wk, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
-__global__ void __launch_bounds__(256) k_tile_alloc(Workspace Wk, uint32_t tiles_per_frame, int which, int pow2) { d_tile_alloc(Wk, tiles_per_frame, which, pow2, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
-__global__ void __launch_bounds__(256) k_bin_fill(SceneDev S, Workspace Wk) { d_bin_fill(S, Wk, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
-__global__ void __launch_bounds__(256) k_bin2d(SceneDev S, Workspace Wk, int fill) { d_bin2d(S, Wk, fill, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
-__global__ void __launch_bounds__(256) k_bin_large(SceneDev S, Workspace Wk, int fill) { d_bin_large(S, Wk, fill, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
+__global__ void __launch_bounds__(256) k_frame_setup(SceneDev S, Workspace Wk, uint32_t tiles_per_frame) { pdl_enter(); d_frame_setup(S, Wk, tiles_per_frame, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
+__global__ void __launch_bounds__(RX_CHUNK_TRIS) k_tri_setup(SceneDev S, Workspace Wk) { pdl_enter(); d_tri_setup(S, Wk, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
+__global__ void __launch_bounds__(256) k_batch_finalize(SceneDev S, Workspace Wk) { pdl_enter(); d_batch_finalize(S, Wk, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
+__global__ void __launch_bounds__(128) k_clip_emit(SceneDev S, Workspace Wk) { pdl_enter(); d_clip_emit(S, Wk, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
+__global__ void __launch_bounds__(256) k_bin_count(SceneDev S, Workspace Wk) { pdl_enter(); d_bin_count(S, Wk, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
+__global__ void __launch_bounds__(256) k_tile_alloc(Workspace Wk, uint32_t tiles_per_frame, int which, int pow2) { pdl_enter(); d_tile_alloc(Wk, tiles_per_frame, which, pow2, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
+__global__ void __launch_bounds__(256) k_bin_fill(SceneDev S, Workspace Wk) { pdl_enter(); d_bin_fill(S, Wk, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
+__global__ void __launch_bounds__(256) k_bin2d(SceneDev S, Workspace Wk, int fill) { pdl_enter(); d_bin2d(S, Wk, fill, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
+__global__ void __launch_bounds__(256) k_bin_large(SceneDev S, Workspace Wk, int fill) { pdl_enter(); d_bin_large(S, Wk, fill, Blk{blockIdx.x, blockIdx.y, gridDim.x}); }
 
 // ... and fused for small scenes: one CTA per frame runs every front-end phase back to back (7 launches and
 // their gaps cost ~70 us per call, more than rasterising a 1080p frame of such a scene).  Phases communicate
 // through global memory written and read by this CTA only; __syncthreads orders them.
 __global__ void __launch_bounds__(256) k_front_small(SceneDev S, Workspace Wk, uint32_t tiles_per_frame, uint32_t n_frame_blocks) {
+    pdl_enter();
     const uint32_t f = blockIdx.x;
     for (uint32_t v = 0; v < n_frame_blocks; ++v) { d_frame_setup(S, Wk, tiles_per_frame, Blk{v, f, n_frame_blocks}); __syncthreads(); }
     if (S.n_tris == 0u) return;
@@ -1030,6 +1042,7 @@ __global__ void __launch_bounds__(256) k_front_small(SceneDev S, Workspace Wk, u
 // wait.acquire, which also orders the global-memory hand-over between phases) instead of at a kernel boundary:
 // seven dependent launches (~10 us each of drain + launch + ramp) become six barriers of well under a microsecond.
 __global__ void __launch_bounds__(256) k_front_cluster(SceneDev S, Workspace Wk, uint32_t tiles_per_frame, uint32_t n_frame_blocks, uint32_t stop_phase) {
+    pdl_enter();
     cg::cluster_group cl = cg::this_cluster();
     const uint32_t r = cl.block_rank(), R = cl.num_blocks();   // the cluster spans grid.x; grid.y = frames
     const uint32_t f = blockIdx.y;
@@ -2393,6 +2406,7 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
         const float x = (float)tid * (1.0f / 255.0f);
         s_kd[tid] = (__fmaf_rn(0.6975f, x * x, 0.3025f) * x) * (1.0f - 0.04f);  // visible after the first tile's barrier
     }
+    pdl_enter();   // everything above is private to the CTA; the front end's results are read from here on
 
     for (;;) {
         if (tid == 0) {
@@ -2930,6 +2944,7 @@ __global__ void __launch_bounds__(128) k_raster_ordered(SceneDev S, Workspace Wk
     // tile with one working lane: 36 ms.)
     __shared__ VmIO s_io[4];
     __shared__ VmPersist s_ps[4];
+    pdl_enter();
     const uint32_t f = blockIdx.y;
     if (f >= n_frames) return;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -3115,6 +3130,7 @@ __global__ void __launch_bounds__(128) k_raster_ordered(SceneDev S, Workspace Wk
 #define RX_SORT_SMEM 4096
 __global__ void __launch_bounds__(256) k_list_sort(Workspace Wk, int which) {
     __shared__ uint32_t sm[RX_SORT_SMEM];
+    pdl_enter();
     const uint32_t f = blockIdx.y, t = blockIdx.x, tid = threadIdx.x;
     const uint32_t n = (which ? Wk.tile_count2 : Wk.tile_count)[(size_t)f * Wk.tile_stride + t];
     if (n < 2u) return;
@@ -3193,89 +3209,97 @@ __global__ void __launch_bounds__(256) k_selftest_div(uint64_t seed, uint32_t it
 // ---------------------------------------------------------------------------------------------
 // launch wrappers
 // ---------------------------------------------------------------------------------------------
+// Kernels of a frame's chain are launched with programmatic stream serialization (see pdl_enter): the launch may begin once
+// every CTA of the kernel before it in the stream has started; the kernel's own griddepcontrol.wait orders the data.
+// RXC_PDL=0 launches them the ordinary way (A/B measurements).
+static bool pdl_enabled() {
+    static const bool on = !(getenv("RXC_PDL") && atoi(getenv("RXC_PDL")) == 0);
+    return on;
+}
+static void pdl_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* at, dim3 grid, dim3 block, cudaStream_t st, unsigned cluster_x = 0) {
+    *cfg = cudaLaunchConfig_t{};
+    cfg->gridDim = grid; cfg->blockDim = block; cfg->stream = st;
+    unsigned n = 0;
+    if (cluster_x) { at[n].id = cudaLaunchAttributeClusterDimension; at[n].val.clusterDim.x = cluster_x; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1; ++n; }
+    if (pdl_enabled()) { at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[n].val.programmaticStreamSerializationAllowed = 1; ++n; }
+    cfg->attrs = at; cfg->numAttrs = n;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t pdl_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg; cudaLaunchAttribute at[2];
+    pdl_config(&cfg, at, grid, block, st);
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+static cudaError_t pdl_launch_ptr(const void* kernel, dim3 grid, dim3 block, cudaStream_t st, void** args) {
+    cudaLaunchConfig_t cfg; cudaLaunchAttribute at[2];
+    pdl_config(&cfg, at, grid, block, st);
+    return cudaLaunchKernelExC(&cfg, kernel, args);
+}
 cudaError_t rxk_frame_setup(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, cudaStream_t st) {
     const uint32_t zero_blocks = max(max(1u, min(64u, (tiles_per_frame + 255u) / 256u)), min(64u, (S.n_b3 + 63u) / 64u));
     dim3 grid(1 + S.n_b2 + zero_blocks, n_frames);
-    k_frame_setup<<<grid, 256, 0, st>>>(S, W, tiles_per_frame);
-    return cudaGetLastError();
+    return pdl_launch(k_frame_setup, dim3(grid), dim3(256), st, S, W, tiles_per_frame);
 }
 cudaError_t rxk_front_small(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, cudaStream_t st) {
-    k_front_small<<<n_frames, 256, 0, st>>>(S, W, tiles_per_frame, 2u + S.n_b2);   // block 0, the 2D batches, one state/zeroing block
-    return cudaGetLastError();
+    return pdl_launch(k_front_small, dim3(n_frames), dim3(256), st, S, W, tiles_per_frame, 2u + S.n_b2);   // block 0, the 2D batches, one state/zeroing block
 }
 cudaError_t rxk_front_cluster(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, uint32_t stop_phase, cudaStream_t st) {
     const uint32_t zero_blocks = max(1u, min(64u, (tiles_per_frame + 255u) / 256u));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(RX_FRONT_CLUSTER, n_frames);
-    cfg.blockDim = dim3(256);
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = RX_FRONT_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchConfig_t cfg; cudaLaunchAttribute at[2];
+    pdl_config(&cfg, at, dim3(RX_FRONT_CLUSTER, n_frames), dim3(256), st, RX_FRONT_CLUSTER);
     return cudaLaunchKernelEx(&cfg, k_front_cluster, S, W, tiles_per_frame, 1u + S.n_b2 + zero_blocks, stop_phase);
 }
 cudaError_t rxk_tri_setup(const SceneDev& S, const Workspace& W, uint32_t n_frames, cudaStream_t st) {
     if (S.n_chunks == 0) return cudaSuccess;
     dim3 grid(S.n_chunks, n_frames);
-    k_tri_setup<<<grid, RX_CHUNK_TRIS, 0, st>>>(S, W);
-    return cudaGetLastError();
+    return pdl_launch(k_tri_setup, dim3(grid), dim3(RX_CHUNK_TRIS), st, S, W);
 }
 cudaError_t rxk_tri_setup_projected(const SceneDev& S, const Workspace& W, const ProjectedDev& P, cudaStream_t st) {
     const uint32_t n = max(max(S.n_tris, P.n_clipped), S.n_b3);
     if (n == 0) return cudaSuccess;
-    k_tri_setup_projected<<<(n + 255) / 256, 256, 0, st>>>(S, W, P);
-    return cudaGetLastError();
+    return pdl_launch(k_tri_setup_projected, dim3((n + 255) / 256), dim3(256), st, S, W, P);
 }
 
 cudaError_t rxk_batch_finalize(const SceneDev& S, const Workspace& W, uint32_t n_frames, cudaStream_t st) {
     if (S.n_b3 == 0) return cudaSuccess;
     dim3 grid((S.n_b3 + 7) / 8, n_frames);
-    k_batch_finalize<<<grid, 256, 0, st>>>(S, W);
-    return cudaGetLastError();
+    return pdl_launch(k_batch_finalize, dim3(grid), dim3(256), st, S, W);
 }
 cudaError_t rxk_clip_emit(const SceneDev& S, const Workspace& W, uint32_t n_frames, int grid_x, cudaStream_t st) {
     if (S.n_tris == 0) return cudaSuccess;
     dim3 grid(grid_x, n_frames);
-    k_clip_emit<<<grid, 128, 0, st>>>(S, W);
-    return cudaGetLastError();
+    return pdl_launch(k_clip_emit, dim3(grid), dim3(128), st, S, W);
 }
 cudaError_t rxk_bin_count(const SceneDev& S, const Workspace& W, uint32_t n_frames, int grid_x, cudaStream_t st) {
     if (S.n_tris == 0) return cudaSuccess;
     dim3 grid(grid_x, n_frames);
-    k_bin_count<<<grid, 256, 0, st>>>(S, W);
-    return cudaGetLastError();
+    return pdl_launch(k_bin_count, dim3(grid), dim3(256), st, S, W);
 }
 cudaError_t rxk_tile_alloc(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, int which, int pow2,
                            cudaStream_t st) {
     (void)S;
     dim3 grid((tiles_per_frame + 255) / 256, n_frames);
-    k_tile_alloc<<<grid, 256, 0, st>>>(W, tiles_per_frame, which, pow2);
-    return cudaGetLastError();
+    return pdl_launch(k_tile_alloc, dim3(grid), dim3(256), st, W, tiles_per_frame, which, pow2);
 }
 cudaError_t rxk_bin2d(const SceneDev& S, const Workspace& W, uint32_t n_frames, int fill, cudaStream_t st) {
     if (S.n_rec2d == 0) return cudaSuccess;
     dim3 grid((S.n_rec2d + 7) / 8, n_frames);
-    k_bin2d<<<grid, 256, 0, st>>>(S, W, fill);
-    return cudaGetLastError();
+    return pdl_launch(k_bin2d, dim3(grid), dim3(256), st, S, W, fill);
 }
 cudaError_t rxk_bin_large(const SceneDev& S, const Workspace& W, uint32_t n_frames, int fill, int grid_x, cudaStream_t st) {
     if (S.n_tris == 0) return cudaSuccess;
     dim3 grid(grid_x, n_frames);
-    k_bin_large<<<grid, 256, 0, st>>>(S, W, fill);
-    return cudaGetLastError();
+    return pdl_launch(k_bin_large, dim3(grid), dim3(256), st, S, W, fill);
 }
 cudaError_t rxk_list_sort(const SceneDev& S, const Workspace& W, uint32_t n_frames, uint32_t tiles_per_frame, int which, cudaStream_t st) {
     (void)S;
     dim3 grid(tiles_per_frame, n_frames);
-    k_list_sort<<<grid, 256, 0, st>>>(W, which);
-    return cudaGetLastError();
+    return pdl_launch(k_list_sort, dim3(grid), dim3(256), st, W, which);
 }
 cudaError_t rxk_bin_fill(const SceneDev& S, const Workspace& W, uint32_t n_frames, int grid_x, cudaStream_t st) {
     if (S.n_tris == 0) return cudaSuccess;
     dim3 grid(grid_x, n_frames);
-    k_bin_fill<<<grid, 256, 0, st>>>(S, W);
-    return cudaGetLastError();
+    return pdl_launch(k_bin_fill, dim3(grid), dim3(256), st, S, W);
 }
 cudaError_t rxk_raster_ordered(const SceneDev& S, const Workspace& W, const RasterOut& out, uint32_t n_frames, uint32_t api_tiles, float* z, float* zop,
                                uint32_t* cop, uint32_t* sid, uint32_t* some, uint32_t* own, size_t stride, cudaStream_t st, void* jit_kernel) {
@@ -3284,10 +3308,9 @@ cudaError_t rxk_raster_ordered(const SceneDev& S, const Workspace& W, const Rast
     if (jit_kernel) {   // the same kernel with the scene's programs compiled (rx_jit.cu)
         SceneDev s = S; Workspace w = W; RasterOut o = out;
         void* args[] = {&s, &w, &o, &n_frames, &q};
-        return cudaLaunchKernel((const void*)jit_kernel, grid, dim3(128), args, 0, st);
+        return pdl_launch_ptr((const void*)jit_kernel, grid, dim3(128), st, args);
     }
-    k_raster_ordered<<<grid, 128, 0, st>>>(S, W, out, n_frames, q);
-    return cudaGetLastError();
+    return pdl_launch(k_raster_ordered, grid, dim3(128), st, S, W, out, n_frames, q);
 }
 // experiments: RXC_SMEM_CARVEOUT = preferred shared-memory carve-out of the raster kernels in percent (what is left is L1)
 static void raster_carveout(const void* kernel) {
@@ -3307,9 +3330,9 @@ cudaError_t rxk_raster(const SceneDev& S, const Workspace& W, const RasterOut& o
         // the same kernel recompiled for this scene (rx_jit.cu: its programs as straight-line code, its constants folded): same arguments
         SceneDev s = S; Workspace w = W; RasterOut o = out;
         void* args[] = {&s, &w, &o, &n_frames, &tile0, &n_tiles, &counter};
-        return cudaLaunchKernel((const void*)jit_kernel, dim3(grid_x), dim3(RX_TILE_THREADS), args, 0, st);
+        return pdl_launch_ptr((const void*)jit_kernel, dim3(grid_x), dim3(RX_TILE_THREADS), st, args);
     }
-#define RX_LAUNCH(SM, PL, MD) do { raster_carveout((const void*)k_raster<SM, PL, MD>); k_raster<SM, PL, MD><<<grid_x, RX_TILE_THREADS, 0, st>>>(S, W, out, n_frames, tile0, n_tiles, counter); } while (0)
+#define RX_LAUNCH(SM, PL, MD) do { raster_carveout((const void*)k_raster<SM, PL, MD>); return pdl_launch(k_raster<SM, PL, MD>, dim3(grid_x), dim3(RX_TILE_THREADS), st, S, W, out, n_frames, tile0, n_tiles, counter); } while (0)
 #define RX_LAUNCH2(SM, PL) do { if (S.general && S.vm.n_programs) RX_LAUNCH(SM, PL, 2); else if (S.general) RX_LAUNCH(SM, PL, 1); else if (S.n_tris >= W.small_min_tris) RX_LAUNCH(SM, PL, 3); else RX_LAUNCH(SM, PL, 0); } while (0)
     if (sample_mode == 0) { if (planes) RX_LAUNCH2(0, true); else RX_LAUNCH2(0, false); }
     else if (sample_mode == 1) { if (planes) RX_LAUNCH2(1, true); else RX_LAUNCH2(1, false); }
