@@ -20,7 +20,7 @@ stream = torch.cuda.Stream(device="cuda:0")               # kernels, L2 flush an
 torch.cuda.set_stream(stream)
 ctx.set_stream(stream.cuda_stream)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
-tag = "pdl=" + os.environ.get("RXC_PDL", "1")
+tag = "pdl=" + os.environ.get("RXC_PDL", "1") + " heavy=" + os.environ.get("RXC_HEAVY_MIN", "256")
 
 
 def timed(run, n=30):
@@ -58,3 +58,16 @@ if R:
         worst = max(worst, med)
         print(f"{tag} dense8k column band {r}/{R} [{x0},{x1}) step mean {mean:.4f} median {med:.4f} min {best:.4f} ms", flush=True)
     print(f"{tag} dense8k {R} column bands: slowest band median {worst:.4f} ms", flush=True)
+    # what cost-balanced column bands would give (mgpu.BandBalancer over the tile columns, one band after the other on this GPU)
+    bal = mgpu.BandBalancer(W, R, 32)
+    for it in range(int(os.environ.get("AB_BALANCE", "0"))):
+        times = []
+        for r in range(R):
+            x0, x1 = bal.band(r)
+            if x1 <= x0:
+                times.append(0.0); continue
+            out = torch.empty((1, H, x1 - x0, 4), dtype=torch.uint8, device="cuda:0")
+            batch = Rasterizer.prepare_batch([cfg.rasterizer(frame_ids[0])], cfg.scene, W, H, cfg.tile_size, cfg.assets, band=(0, H, x0, x1))
+            times.append(timed(lambda: batch.run(out, sync=False), n=10)[1])
+        print(f"{tag} balanced columns, iteration {it}: edges {bal.edges} slowest {max(times):.4f} ms  " + " ".join(f"{t:.3f}" for t in times), flush=True)
+        bal.update(times)
