@@ -566,9 +566,10 @@ def sweep4096(rank, world, local_rank, dev, barrier, dl, total_frames=4096, per_
 def band_split(rank, world, local_rank, dev, flush, barrier, dl, steps=5, warmup=3, balance_iters=12):
     """BASELINE.json config D: one 7680x4320 frame of the 1M-triangle scene split by screen band over the ranks
     (SURVEY 8e).  Strong scaling of a single frame, time = max over ranks.  Every rank drops the batches that cannot
-    touch its rectangle before it loads a vertex of them (k_frame_setup), so the front end is sharded too.  Three splits
+    touch its rectangle before it loads a vertex of them (k_frame_setup), so the front end is sharded too.  Four splits
     are timed render-only (the band stays in the rank's HBM): equal-height row bands, row bands whose boundaries
-    `mgpu.BandBalancer` moved from the ranks' measured times, and equal-width column bands.  The two best are then timed
+    `mgpu.BandBalancer` moved from the ranks' measured times, equal-width column bands and column bands balanced the same
+    way.  The balanced ones and the equal columns are then timed
     DELIVERED: every rank's raster kernel writes its band in place into the full frame in rank 0's memory
     (rxc_mgpu_rasterize with the frame's row pitch), until rank 0 has seen every rank's completion flag."""
     import torch
@@ -621,6 +622,15 @@ def band_split(rank, world, local_rank, dev, flush, barrier, dl, steps=5, warmup
     col_bands = [(0, H) + mgpu.column_band_for_rank(W, r, world) for r in range(world)]
     cbatch = prepare(col_bands[rank])
     cols_ms = measure(local_run(cbatch))
+    # ... up to the triangles a band holds: the same balancer over the tile columns evens that out
+    cbal = mgpu.BandBalancer(W, world, 32)
+    for _ in range(balance_iters):
+        run = local_run(prepare((0, H) + cbal.band(rank)))
+        timed_frame(run)
+        cbal.update(mgpu.all_gather_times(timed_frame(run), device=dev))
+    bcol_bands = [(0, H) + b for b in cbal.use_best()]
+    bcbatch = prepare(bcol_bands[rank])
+    bcols_ms = measure(local_run(bcbatch))
 
     # delivered: the band written in place into rank 0's full frame
     dl.target(W * H * 4)
@@ -638,21 +648,27 @@ def band_split(rank, world, local_rank, dev, flush, barrier, dl, steps=5, warmup
 
     row_regions = mgpu.band_regions([(y0, y1, 0, W) for y0, y1 in row_bands], W)
     col_regions = mgpu.band_regions(col_bands, W)
+    bcol_regions = mgpu.band_regions(bcol_bands, W)
     rows_del = measure(delivered_run(rbatch, row_bands[rank], row_regions))
     cols_del = measure(delivered_run(cbatch, col_bands[rank], col_regions))
+    bcols_del = measure(delivered_run(bcbatch, bcol_bands[rank], bcol_regions))
     st = dl.status()
-    ms = min(cols_ms, rows_ms)
-    ms_del = min(cols_del, rows_del)
-    nv_bytes = (W * H - (col_bands[0][3] - col_bands[0][2]) * H) * 4 if cols_del <= rows_del else (H - (row_bands[0][1] - row_bands[0][0])) * W * 4
+    names = ("column bands", "cost-balanced row bands", "cost-balanced column bands")
+    ms, split = min(zip((cols_ms, rows_ms, bcols_ms), names))
+    ms_del, split_del = min(zip((cols_del, rows_del, bcols_del), names))
+    own0 = {"column bands": (col_bands[0][3] - col_bands[0][2]) * H, "cost-balanced row bands": (row_bands[0][1] - row_bands[0][0]) * W,
+            "cost-balanced column bands": (bcol_bands[0][3] - bcol_bands[0][2]) * H}[split_del]   # rank 0's own pixels do not cross NVLink
+    nv_bytes = (W * H - own0) * 4
     return {"workload": desc + ", split into %d bands" % world, "scaling": "strong", "ms_per_frame": ms,
             "Mpixel_per_s": W * H / (ms * 1e-3) / 1e6, "frames_per_s": 1.0 / (ms * 1e-3),
-            "split": "column bands" if cols_ms <= rows_ms else "cost-balanced row bands",
-            "column_bands_ms_per_frame": cols_ms, "balanced_row_bands_ms_per_frame": rows_ms, "equal_row_bands_ms_per_frame": equal_ms,
-            "row_band_edges": [b[0] for b in row_bands] + [H],
+            "split": split,
+            "column_bands_ms_per_frame": cols_ms, "balanced_column_bands_ms_per_frame": bcols_ms, "balanced_row_bands_ms_per_frame": rows_ms,
+            "equal_row_bands_ms_per_frame": equal_ms,
+            "row_band_edges": [b[0] for b in row_bands] + [H], "column_band_edges": [b[2] for b in bcol_bands] + [W],
             "row_bands": "cost-balanced from the ranks' measured times (mgpu.BandBalancer, %d frames)" % balance_iters,
             "delivered": {"ms_per_frame": ms_del, "Mpixel_per_s": W * H / (ms_del * 1e-3) / 1e6, "frames_per_s": 1.0 / (ms_del * 1e-3),
-                          "split": "column bands" if cols_del <= rows_del else "cost-balanced row bands",
-                          "column_bands_ms_per_frame": cols_del, "balanced_row_bands_ms_per_frame": rows_del,
+                          "split": split_del,
+                          "column_bands_ms_per_frame": cols_del, "balanced_column_bands_ms_per_frame": bcols_del, "balanced_row_bands_ms_per_frame": rows_del,
                           "bytes_to_rank0": nv_bytes, "rank0_ingest_GBps": nv_bytes / (ms_del * 1e-3) / 1e9,
                           "mode": "peer writes over NVLink (ranks > 0), local stores (rank 0)" if st["mode"] != "nccl" else "nccl send/recv",
                           "timeouts": st["timeouts"] if rank == 0 else None,
