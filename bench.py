@@ -396,7 +396,7 @@ def main():
                              "warp_instructions_per_launch_ncu": ncu_row.get("warp_instructions"),
                              "live_warp_inst_per_clk_per_smsp": (ncu_row.get("warp_instructions") / (raster_ms * 1e-3 * (clocks or {}).get("sm_mhz", 1965.0) * 1e6 * 148 * 4)) if ncu_row.get("warp_instructions") and rank == 0 else None,
                              "profile_version": ncu_row.get("version")},
-                "note": "the kernel is SM-issue bound, not HBM bound: about 640 thread-instructions per pixel (exact divisions, no FMA contraction, per-light BRDF) keep the issue slots ~80 % busy; see DESIGN.md section 5"}
+                "note": "the kernel is SM-issue bound, not HBM bound: about %s thread-instructions per pixel (exact divisions, no FMA contraction, per-light BRDF) keep the issue slots ~80 %% busy; see DESIGN.md section 5" % (ncu_row.get("thread_instructions_per_pixel") or 500)}
 
     # ---- the same step with delivery to rank 0 fused into the raster kernel's write-back (rxc_mgpu_*)
     delivered = None
