@@ -233,7 +233,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="map4k", choices=list(WORKLOADS))
-    ap.add_argument("--frames", type=int, default=8, help="frames per step (camera batch)")
+    ap.add_argument("--frames", type=int, default=32, help="frames per step (camera batch); 32 views of the camera path = 1.06 GB of 4K frames per call: the per-call front end and the raster grid's ramp / tail are paid once per call (8 per call: 55.5 Gpixel/s device-resident / 13.5 end to end, 16: 58.2 / 13.8, 32: 58.5 / 14.0, 64: 58.9 / 14.0)")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads and the CPU baseline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
@@ -379,7 +379,12 @@ def main():
     ncu_json = os.path.join(ROOT, "profiles", "ncu_summary.json")
     if os.path.exists(ncu_json):
         try:
-            ncu_row = json.load(open(ncu_json)).get(args.workload, {})
+            ncu_row = dict(json.load(open(ncu_json)).get(args.workload, {}))
+            # the capture's per-launch counts, scaled to this run's frames per launch when they differ
+            k_f = F / float(ncu_row.get("frames_per_launch") or F)
+            for key in ("k_raster_dram_bytes_per_launch", "warp_instructions", "dram_read_bytes"):
+                if ncu_row.get(key) is not None and k_f != 1.0:
+                    ncu_row[key] = int(round(ncu_row[key] * k_f))
             traffic = ncu_row.get("k_raster_dram_bytes_per_launch")
         except Exception:
             ncu_row, traffic = {}, None
@@ -486,11 +491,12 @@ def main():
         dist.destroy_process_group()
 
 
-def sweep4096(rank, world, local_rank, dev, barrier, dl, total_frames=4096, per_launch=32):
+def sweep4096(rank, world, local_rank, dev, barrier, dl, total_frames=4096, per_launch=int(os.environ.get("RXB_SWEEP_PER_LAUNCH", "128"))):
     """BASELINE.json config E as specified: 4096 frames of the map scene at 1920x1080, sharded by frame across the
     ranks in contiguous blocks -- STRONG scaling (the job is the same 4096 frames at every N).  A rank renders its
-    block `per_launch` frames per launch sequence (265 MB of frames: more than the L2 holds, so no flush is needed
-    between launches).  Two totals: render-only (frames stay in the rank's HBM, a ring of one launch) and delivered
+    block `per_launch` frames per launch sequence (128 frames = 1.06 GB of frames: more than the L2 holds, so no flush
+    is needed between launches; one front-end pass per launch, so its ~60 us are paid 32 times per 4096 frames instead of
+    128 times with 32 frames per launch: 0.1698 -> 0.1640 s on one GPU, 0.1631 with 256, 0.1627 with 512).  Two totals: render-only (frames stay in the rank's HBM, a ring of one launch) and delivered
     (every launch written straight into a two-slot ring in rank 0's memory, rxc_mgpu_*, release hand-shake included)."""
     import torch
     import torch.distributed as dist
@@ -560,7 +566,7 @@ def sweep4096(rank, world, local_rank, dev, barrier, dl, total_frames=4096, per_
                                    "bytes_to_rank0": (world - 1) * per_rank * fb, "rank0_ingest_GBps": (world - 1) * per_rank * fb / (ms_d * 1e-3) / 1e9 if world > 1 else None,
                                    "mode": ("peer writes over NVLink (ranks > 0), local stores (rank 0)" if st["mode"] != "nccl" else "nccl send/recv") if world > 1 else "local", "timeouts": st["timeouts"] if rank == 0 else None},
             "host_prepare_s": t_prep,
-            "timing": "one pair of CUDA events around the whole job on every rank's stream (best of 2 jobs after a 3-launch warm-up), max over ranks; every launch writes 265 MB of frames (> L2)"}
+            "timing": "one pair of CUDA events around the whole job on every rank's stream (best of 2 jobs after a 3-launch warm-up), max over ranks; every launch writes %d MB of frames (> L2)" % (per_launch * fb // 1000000)}
 
 
 def band_split(rank, world, local_rank, dev, flush, barrier, dl, steps=5, warmup=3, balance_iters=12):
