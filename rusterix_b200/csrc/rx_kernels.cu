@@ -3221,7 +3221,8 @@ static void pdl_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* at, dim3 gr
     cfg->gridDim = grid; cfg->blockDim = block; cfg->stream = st;
     unsigned n = 0;
     if (cluster_x) { at[n].id = cudaLaunchAttributeClusterDimension; at[n].val.clusterDim.x = cluster_x; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1; ++n; }
-    if (pdl_enabled()) { at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[n].val.programmaticStreamSerializationAllowed = 1; ++n; }
+    // (not on the legacy default stream, whose implicit synchronisation with other streams is not what the attribute relaxes)
+    if (pdl_enabled() && st != nullptr && st != cudaStreamLegacy) { at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[n].val.programmaticStreamSerializationAllowed = 1; ++n; }
     cfg->attrs = at; cfg->numAttrs = n;
 }
 template <typename... KArgs, typename... Args>
