@@ -347,7 +347,10 @@ int32_t rxc_create(int32_t device, rxc_ctx** out);
 void rxc_destroy(rxc_ctx* ctx);
 const char* rxc_last_error(const rxc_ctx* ctx);
 
-/* Launch on `cuda_stream` (a cudaStream_t) instead of the context's own stream; NULL restores it. */
+/* Launch on `cuda_stream` (a cudaStream_t) instead of the context's own stream; NULL restores it.
+ * The kernels of a frame follow each other by programmatic dependent launch (the next kernel's blocks become resident early and
+ * wait for their predecessor's completion on the device); work the caller enqueues on the stream before or after a call is
+ * ordered as usual.  RXC_PDL=0 in the environment launches them the ordinary way. */
 int32_t rxc_set_stream(rxc_ctx* ctx, void* cuda_stream);
 
 /* assets.tile_list (reference src/server/assets.rs:19): uploaded once, kept on device. */
