@@ -194,6 +194,28 @@ def test_band_balancer_converges_on_a_skewed_cost_profile():
         mgpu.BandBalancer(H, 4).update([1.0, 2.0])
 
 
+def test_band_balancer_over_tile_columns():
+    """The same balancer over the tile COLUMNS of the 8K frame (bench.py band_split's fourth split): column bands cut every tile
+    row alike, what differs is the triangles a band holds -- a mild bulge in the middle of the frame."""
+    W, align = 7680, 32
+    x = np.arange(W)
+    cost = (0.08 + 0.07 * np.exp(-((x - 3600.0) / 1500.0) ** 2)) / 960.0   # ms per column: 0.08 ms per eighth at the rim, 0.15 in the middle
+    for world in (2, 4, 8):
+        bal = mgpu.BandBalancer(W, world, align)
+        first = None
+        for _ in range(12):
+            bands = bal.bands()
+            assert bands[0][0] == 0 and bands[-1][1] == W and all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
+            assert all(v % align == 0 for x0, x1 in bands[:-1] for v in (x0, x1))
+            times = [0.065 + float(cost[x0:x1].sum()) * 8.0 / world for x0, x1 in bands]
+            first = first if first is not None else max(times)
+            bal.update(times)
+        bands = bal.use_best()
+        worst = max(0.065 + float(cost[x0:x1].sum()) * 8.0 / world for x0, x1 in bands)
+        optimum = 0.065 + float(cost.sum()) * 8.0 / world / world
+        assert worst <= first + 1e-12 and worst <= 1.05 * optimum, (world, worst, optimum)
+
+
 def test_bresenham_membership_closed_form_matches_the_serial_walk():
     """The device decides per pixel whether rasterize_line_bresenham (rasterizer.rs:1777-1821) plots it
     (line_covers in rx_kernels.cu).  Same closed form, checked against the serial walk for every
