@@ -2347,6 +2347,7 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
     __shared__ uint16_t s_sel[GENERAL ? 1 : RX_LARGE_CACHE];
     __shared__ uint32_t s_nsel;
     __shared__ int32_t s_work[4];   // frame (-1 = done), tile x0, tile y0, tile index
+    __shared__ uint32_t s_grp[2];   // frame groups: the group this CTA takes tiles from, and how many groups it has seen run dry
 #if RX_TMA_STORE
     // two dense 32x32 tiles in the tensor map's 128 B swizzle (16 B chunk c of row r sits at chunk c ^ (r & 7)), one draining
     __shared__ __align__(1024) uint32_t s_color[2 * RX_TILE_H * RX_TILE_W];
@@ -2408,13 +2409,32 @@ __global__ void __launch_bounds__(RX_TILE_THREADS, RX_RASTER_MIN_BLOCKS) k_raste
     }
     pdl_enter();   // everything above is private to the CTA; the front end's results are read from here on
 
+    // Frame groups (launches of many frames): what a CTA stages per frame (pointer block, shade constants, lights, the large
+    // records, the union boxes: three barriers and a bulk-copy round trip) is paid per (CTA, frame) pair, and with ONE counter
+    // over all tiles every CTA walks through every frame.  With G counters over G runs of consecutive frames a CTA stays with
+    // the frames of its group (blockIdx % G) and only moves on, group by group, when they are done.
+    const uint32_t n_groups = Wk.raster_groups > 1u ? Wk.raster_groups : 1u;
+    if (tid == 0) { s_grp[0] = blockIdx.x % n_groups; s_grp[1] = 0u; }
     for (;;) {
         if (tid == 0) {
-            const uint32_t work = atomicAdd(Wk.raster_counter + counter, 1u);
-            if (work >= total) {
+            uint32_t work = 0xFFFFFFFFu, f_base = 0u;
+            if (n_groups == 1u) {
+                const uint32_t w = atomicAdd(Wk.raster_counter + counter, 1u);
+                if (w < total) work = w;
+            } else {
+                uint32_t g = s_grp[0], dry = s_grp[1];
+                while (dry < n_groups) {
+                    const uint32_t f0 = (uint32_t)(((unsigned long long)g * n_frames) / n_groups), f1 = (uint32_t)(((unsigned long long)(g + 1u) * n_frames) / n_groups);
+                    const uint32_t w = atomicAdd(Wk.raster_counter + g, 1u);
+                    if (w < (f1 - f0) * tiles_per_frame) { work = w; f_base = f0; break; }
+                    g = g + 1u == n_groups ? 0u : g + 1u; ++dry;   // that group is done: help the next one
+                }
+                s_grp[0] = g; s_grp[1] = dry;
+            }
+            if (work == 0xFFFFFFFFu) {
                 s_work[0] = -1;
             } else {
-                const uint32_t f = work / tiles_per_frame, tile = tile0 + (work - f * tiles_per_frame);
+                const uint32_t df = work / tiles_per_frame, f = f_base + df, tile = tile0 + (work - df * tiles_per_frame);
                 const uint32_t tiles_x = (uint32_t)Wk.frames[f].tiles_x;
                 const uint32_t ty = tile / tiles_x;
                 s_work[0] = (int32_t)f; s_work[1] = (int32_t)((tile - ty * tiles_x) * RX_TILE_W); s_work[2] = (int32_t)(ty * RX_TILE_H);

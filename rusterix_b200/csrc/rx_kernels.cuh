@@ -72,6 +72,7 @@ struct Workspace {
     uint32_t* lists2;       uint32_t list2_stride;
     Tri2D* tri2d;           uint32_t tri2d_stride;
     uint32_t* raster_counter;  // RX_RASTER_COUNTERS work counters, one per k_raster launch of a call (zeroed by the frame setup)
+    uint32_t raster_groups;    // > 1: the frames of a launch are dealt out in this many groups, counters [0, groups) (k_raster's work fetch)
     uint32_t small_min_list, small_max_pix;  // k_raster's thread-per-record pass of long tile lists
     uint32_t small_gshift;                   // log2 of the lanes that share one record in the pass
     uint32_t small_min_tris;                 // scenes with at least this many triangles run the k_raster variant that has the pass (0xFFFFFFFF = never)
