@@ -114,6 +114,9 @@ def test_nvrtc_compiles_the_generated_kernel(tmp_path, monkeypatch):
     # the reference-order kernel with the programs compiled (carried globals / locals: vmj_pN_ps)
     n2 = lib.rxc_vm_jit_compile(arr, len(flat), -2, 0, log, len(log))
     assert n2 > 0, log.value.decode()
+    # the raster kernel itself (Nearest, pixels only, batch-shader mode) from the embedded sources: what a GPU box compiles at its first frame
+    n3 = lib.rxc_vm_jit_compile(arr, len(flat), 0, 0, log, len(log))
+    assert n3 > 0, log.value.decode()
 
 
 # ---- which programs can observe the reference's per-tile Execution (rxc_vm_state_report) ----
