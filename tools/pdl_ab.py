@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Whole-step device time (CUDA events around the step, no per-kernel events in between, so programmatic dependent
 launch is not broken up) of the bench workloads and of the R column bands of the dense 8K frame.
-Run once with RXC_PDL=1 and once with RXC_PDL=0.  usage: pdl_ab.py [bands R] [workload ...]"""
+Run once with RXC_PDL=1 and once with RXC_PDL=0 (or with RXC_RASTER_GROUPS=1 against unset: the frame groups of k_raster).  usage: pdl_ab.py [bands R] [workload ...]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -20,7 +20,7 @@ stream = torch.cuda.Stream(device="cuda:0")               # kernels, L2 flush an
 torch.cuda.set_stream(stream)
 ctx.set_stream(stream.cuda_stream)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
-tag = "pdl=" + os.environ.get("RXC_PDL", "1") + " heavy=" + os.environ.get("RXC_HEAVY_MIN", "256")
+tag = "pdl=" + os.environ.get("RXC_PDL", "1") + " groups=" + os.environ.get("RXC_RASTER_GROUPS", "auto")
 
 
 def timed(run, n=30):
